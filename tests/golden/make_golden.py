@@ -1,0 +1,279 @@
+"""
+Generates tests/golden/*.npz by running the REAL reference (imported from /root/reference, which
+exists only in the build container) and checks, while doing so, that the CPU oracle
+(`oracle/structure.py`, `oracle/ransac.py`) reproduces it.  Run from the repo root:
+
+    NUMBA_ENABLE_CUDASIM=1 python tests/golden/make_golden.py
+
+Import shim (documented in SURVEY.md appendix B; no reference source is modified or copied):
+  * `np.float_` alias   (octreelib/internal/point.py:15-16 predates numpy 2)
+  * stub `k3d` module   (octreelib/grid/grid.py:5 imports it; only `visualize` uses it)
+  * NUMBA_ENABLE_CUDASIM=1 -- the reference's own CI setting (.github/workflows/test.yml:47-48)
+Canonical point order = reference + "stable argsort" runtime shim.
+"""
+import os
+import sys
+import types
+
+os.environ.setdefault("NUMBA_ENABLE_CUDASIM", "1")
+import numpy as np
+
+np.float_ = np.float64
+sys.modules.setdefault("k3d", types.ModuleType("k3d"))
+REF = os.environ.get("OCTREELIB_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from octreelib.grid import Grid, GridConfig  # noqa: E402  (the reference)
+from octreelib.ransac.cuda_ransac import CudaRansac  # noqa: E402
+
+from oracle.structure import OracleGrid, max_points_criterion  # noqa: E402
+from oracle import ransac as oransac  # noqa: E402
+from octreelib_b200.synthetic import lidar64_scan, indoor_scene  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+class _StableInv(np.ndarray):
+    def argsort(self, *a, **k):
+        k.setdefault("kind", "stable")
+        return np.asarray(self).argsort(*a, **k)
+
+
+class stable_order:
+    """Makes the reference's `inverse.argsort()` (grid.py:88, octree.py:87) stable, at run time."""
+
+    def __enter__(self):
+        self._orig = np.unique
+
+        def _unique(*a, **k):
+            r = self._orig(*a, **k)
+            return (r[0], r[1].view(_StableInv)) if k.get("return_inverse") else r
+
+        np.unique = _unique
+
+    def __exit__(self, *exc):
+        np.unique = self._orig
+
+
+def _index_of(cloud):
+    """Map exact point bytes -> input index (inputs are generated without duplicate points)."""
+    d = {}
+    for i, p in enumerate(cloud):
+        d[p.tobytes()] = i
+    assert len(d) == len(cloud), "duplicate points in a golden input"
+    return d
+
+
+def dump_reference(grid, clouds):
+    """Flatten the reference grid into arrays (per pose: leaf corners, edges, sizes, point indices)."""
+    out = {}
+    for pose, cloud in clouds.items():
+        lut = _index_of(cloud)
+        leaves = grid.get_leaf_points(pose)
+        out[f"p{pose}_corner"] = np.array([np.asarray(v.corner_min, dtype=np.float64) for v in leaves]).reshape(-1, 3)
+        out[f"p{pose}_edge"] = np.array([float(v.edge_length) for v in leaves])
+        out[f"p{pose}_size"] = np.array([v.n_points for v in leaves], dtype=np.int64)
+        idx = [np.array([lut[p.tobytes()] for p in v.get_points()], dtype=np.int64) for v in leaves]
+        out[f"p{pose}_idx"] = np.concatenate(idx) if idx else np.empty(0, dtype=np.int64)
+        out[f"p{pose}_counts"] = np.array([grid.n_leaves(pose), grid.n_points(pose), grid.n_nodes(pose)])
+        gp = grid.get_points(pose)
+        out[f"p{pose}_getpoints_idx"] = np.array([lut[p.tobytes()] for p in gp], dtype=np.int64)
+        cells = grid._Grid__pose_voxel_coordinates[pose]
+        out[f"p{pose}_cells"] = np.array([np.asarray(c.corner_min) for c in cells], dtype=np.int64).reshape(-1, 3)
+    return out
+
+
+def dump_oracle(og, clouds):
+    out = {}
+    for pose in clouds:
+        leaves = og.get_leaf_points(pose)
+        out[f"p{pose}_corner"] = np.array([np.asarray(l.corner, dtype=np.float64) for l in leaves]).reshape(-1, 3)
+        out[f"p{pose}_edge"] = np.array([float(l.edge) for l in leaves])
+        out[f"p{pose}_size"] = np.array([len(l.idx) for l in leaves], dtype=np.int64)
+        out[f"p{pose}_idx"] = np.concatenate([l.idx for l in leaves]) if leaves else np.empty(0, dtype=np.int64)
+        out[f"p{pose}_counts"] = np.array([og.n_leaves(pose), og.n_points(pose), og.n_nodes(pose)])
+        out[f"p{pose}_getpoints_idx"] = og.get_point_indices(pose)
+        out[f"p{pose}_cells"] = np.array(og.pose_cells[pose], dtype=np.int64).reshape(-1, 3)
+    return out
+
+
+def compare(ref, ora, ordered: bool, tag: str):
+    for k in ref:
+        a, b = ref[k], ora[k]
+        if k.endswith("_idx") and not ordered:
+            # as-is reference order is host dependent (unstable argsort): compare per-leaf SETS
+            sizes = ref[k.replace("_getpoints_idx", "_size").replace("_idx", "_size")]
+            if k.endswith("getpoints_idx"):
+                assert sorted(a.tolist()) == sorted(b.tolist()), (tag, k)
+                continue
+            pos = 0
+            for s in sizes:
+                assert sorted(a[pos:pos + s].tolist()) == sorted(b[pos:pos + s].tolist()), (tag, k)
+                pos += s
+            continue
+        assert a.shape == b.shape and (a == b).all(), (tag, k, a[:8], b[:8])
+
+
+def structure_case(name, clouds, edge, max_points, subdivide_poses=None, filter_min=None):
+    crit = [lambda pts: len(pts) > max_points]
+    # (1) reference as-is: structure + point sets
+    g = Grid(GridConfig(voxel_edge_length=edge))
+    for pose, c in clouds.items():
+        g.insert_points(pose, c)
+    pre = dump_reference(g, clouds)
+    g.subdivide(crit, subdivide_poses)
+    if filter_min is not None:
+        g.filter([lambda pts: len(pts) >= filter_min])
+    asis = dump_reference(g, clouds)
+    # (2) reference + stable shim: canonical order
+    with stable_order():
+        gs = Grid(GridConfig(voxel_edge_length=edge))
+        for pose, c in clouds.items():
+            gs.insert_points(pose, c)
+        pre_s = dump_reference(gs, clouds)
+        gs.subdivide(crit, subdivide_poses)
+        if filter_min is not None:
+            gs.filter([lambda pts: len(pts) >= filter_min])
+        canon = dump_reference(gs, clouds)
+    # (3) oracle
+    og = OracleGrid(edge)
+    for pose, c in clouds.items():
+        og.insert_points(pose, c)
+    pre_o = dump_oracle(og, clouds)
+    og.subdivide([max_points_criterion(max_points)], subdivide_poses)
+    if filter_min is not None:
+        og.filter([lambda pts: len(pts) >= filter_min])
+    ora = dump_oracle(og, clouds)
+    compare(pre, pre_o, ordered=False, tag=name + ":pre/as-is")
+    compare(pre_s, pre_o, ordered=True, tag=name + ":pre/stable")
+    compare(asis, ora, ordered=False, tag=name + ":as-is")
+    compare(canon, ora, ordered=True, tag=name + ":stable")
+    save = {f"cloud{p}": c for p, c in clouds.items()}
+    save.update({"pre_" + k: v for k, v in pre_s.items()})
+    save.update(canon)
+    save["edge"] = np.float64(edge)
+    save["max_points"] = np.int64(max_points)
+    save["poses"] = np.array(list(clouds.keys()), dtype=np.int64)
+    save["subdivide_poses"] = np.array([] if subdivide_poses is None else subdivide_poses, dtype=np.int64)
+    save["filter_min"] = np.int64(-1 if filter_min is None else filter_min)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
+    n = sum(len(c) for c in clouds.values())
+    print(f"[golden] {name}: {n} pts, {len(og.cells)} cells, "
+          f"leaves/pose {[int(canon[f'p{p}_counts'][0]) for p in clouds]}  -- oracle == reference OK")
+
+
+def ransac_case(name, clouds, edge, max_points, H, K, threshold, seed, poses_per_batch):
+    """Runs the reference's numba kernel under CUDASIM (slow: keep #blocks * H small)."""
+    crit = [lambda pts: len(pts) > max_points]
+    with stable_order():
+        g = Grid(GridConfig(voxel_edge_length=edge))
+        for pose, c in clouds.items():
+            g.insert_points(pose, c)
+        g.subdivide(crit)
+    # restate grid.py:149-197 far enough to capture evaluate()'s inputs and output per batch
+    np.random.seed(seed)
+    ransac = CudaRansac(threshold=threshold, hypotheses_number=H, initial_points_number=K)
+    table = ransac._CudaRansac__random_hypotheses_cuda.copy_to_host()
+    assert (table == oransac.make_table(H, K, seed=seed)).all()
+    nposes = len(clouds)
+    batches = [list(range(i, min(i + poses_per_batch, nposes))) for i in range(0, nposes, poses_per_batch)]
+    save = {f"cloud{p}": c for p, c in clouds.items()}
+    total_ties = 0
+    for bi, batch in enumerate(batches):
+        pcs, sizes = [], []
+        for pose in batch:
+            leaves = g.get_leaf_points(pose)
+            pcs.append(np.vstack([v.get_points() for v in leaves]))
+            sizes.append(np.array([len(v.get_points()) for v in leaves], dtype=np.int32))
+        cloud = np.vstack(pcs)
+        bs = np.concatenate(sizes)
+        ref_mask = ransac.evaluate(cloud, bs)
+        ora = oransac.ransac_evaluate(cloud, bs, table, threshold, full=True)
+        onp = oransac.ransac_numpy(cloud, bs, table, threshold)
+        assert (ora["counts"] == onp["counts"]).all() and (ora["mask"] == onp["mask"]).all()
+        # tie-aware pin: the reference's mask must be the mask of SOME member of the tied-max set
+        starts = ora["block_start"]
+        chosen = np.full(len(bs), -1, dtype=np.int32)
+        for b, (n, s) in enumerate(zip(bs, starts)):
+            rm = ref_mask[s:s + n]
+            if n < K:
+                assert not rm.any()
+                continue
+            cnt = ora["counts"][b]
+            tied = np.flatnonzero(cnt == cnt.max())
+            total_ties += len(tied) > 1
+            for t in tied:
+                m = oransac.mask_for_plane(cloud, s, n, ora["planes"][b, t], threshold)
+                if (m.astype(bool) == rm).all():
+                    chosen[b] = t
+                    break
+            assert chosen[b] >= 0, (name, "block", b, "reference mask matches no tied-best hypothesis")
+            assert rm.sum() == cnt.max()
+        save[f"b{bi}_points"] = cloud
+        save[f"b{bi}_block_sizes"] = bs
+        save[f"b{bi}_ref_mask"] = ref_mask
+        save[f"b{bi}_ref_choice"] = chosen
+        save[f"b{bi}_best"] = ora["best"]
+        save[f"b{bi}_best_count"] = ora["best_count"]
+        save[f"b{bi}_plane"] = ora["plane"]
+        save[f"b{bi}_mask"] = ora["mask"]
+        save[f"b{bi}_poses"] = np.array(batch, dtype=np.int64)
+        print(f"[golden] {name} batch {bi}: {len(bs)} blocks, {int((bs >= K).sum())} scored, "
+              f"ref picks lowest index in {int((chosen == ora['best']).sum())}/{len(bs)}")
+    save["table"] = table
+    save["edge"], save["max_points"] = np.float64(edge), np.int64(max_points)
+    save["H"], save["K"], save["threshold"], save["seed"] = np.int64(H), np.int64(K), np.float64(threshold), np.int64(seed)
+    save["poses_per_batch"] = np.int64(poses_per_batch)
+    save["n_batches"] = np.int64(len(batches))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
+    print(f"[golden] {name}: blocks with ties {total_ties}  -- oracle == reference (tie-aware) OK")
+
+
+def main():
+    rng = np.random.default_rng(2024)
+
+    def f32(a):
+        return a.astype(np.float32).astype(np.float64)
+
+    # S1: the reference's own tiny fixtures (test/grid/test_grid.py:14-40)
+    tg0 = np.array([[0, 0, 1], [0, 0, 2], [0, 0, 3], [9, 9, 8], [9, 9, 9]], dtype=float)
+    tg1 = np.array([[1, 0, 1], [4, 0, 2], [0, 2, 3], [5, 9, 9], [9, 3, 8]], dtype=float)
+    structure_case("ref_test_grid_gt2", {0: tg0, 1: tg1}, 5, 2)
+    structure_case("ref_test_grid_gt3", {0: tg0, 1: tg1}, 5, 3)
+    # S2: random multi-pose cloud, negative coordinates, integer edge 2
+    clouds = {p: f32(rng.random((1500, 3)) * np.array([9.0, 7.0, 3.0]) - np.array([4.0, 3.0, 1.0])) for p in range(3)}
+    structure_case("random_3pose_edge2", clouds, 2, 10)
+    structure_case("random_3pose_edge2_filter", clouds, 2, 25, filter_min=4)
+    # S3: clustered cloud -> deep trees (depth ~6) with empty children
+    cl = []
+    for p in range(2):
+        centers = rng.random((6, 3)) * 6 - 3
+        pts = centers[rng.integers(0, 6, 1200)] + rng.normal(0, 0.03, (1200, 3))
+        cl.append(f32(pts))
+    structure_case("clustered_2pose_edge4", {0: cl[0], 1: cl[1]}, 4, 12)
+    # S4: 64-beam lidar, 2 poses x 12k points (first rings = dense near field), edge 1, 100/leaf
+    structure_case("lidar_2pose_edge1", {p: lidar64_scan(p, seed=0)[::10] for p in range(2)}, 1.0, 100)
+    # S5: indoor planes, one pose, edge 1
+    structure_case("indoor_1pose_edge1", {0: indoor_scene(8000, seed=1)}, 1.0, 40)
+    # S6: sparse pose numbering is not needed for structure (poses are dict keys): poses 0 and 1,
+    #     second pose lives partly in cells the first never touches
+    a = f32(rng.random((600, 3)) * 4)
+    b = f32(rng.random((600, 3)) * 4 + np.array([2.0, 0, 0]))
+    structure_case("offset_poses_edge1", {0: a, 1: b}, 1, 8)
+
+    # R1..: RANSAC under CUDASIM (about 2 s per block at H=1024 -> small H / few blocks)
+    pl = indoor_scene(700, seed=3)
+    ransac_case("ransac_indoor_h128", {0: pl[:350], 1: pl[350:]}, 8.0, 60, H=128, K=6, threshold=0.02, seed=11,
+                poses_per_batch=10)
+    ransac_case("ransac_indoor_ppb1_h64", {0: pl[:350], 1: pl[350:]}, 8.0, 80, H=64, K=6, threshold=0.02, seed=12,
+                poses_per_batch=1)
+    li = lidar64_scan(0, seed=5)[::40]
+    ransac_case("ransac_lidar_h64_k3", {0: li}, 8.0, 150, H=64, K=3, threshold=0.05, seed=13, poses_per_batch=10)
+    ransac_case("ransac_lidar_h1024", {0: li[:400]}, 16.0, 200, H=1024, K=6, threshold=0.03, seed=14,
+                poses_per_batch=10)
+
+
+if __name__ == "__main__":
+    main()
