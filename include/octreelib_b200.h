@@ -1,0 +1,197 @@
+/*
+ * liboctreelib_b200 -- C ABI of the B200-native octreelib grid pipeline.
+ *
+ * The reference (prime-slam/octreelib) is pure Python and has no FFI of its own; its "operator
+ * interface" for this path is the Python class surface.  Every entry point below is what a
+ * binding of that surface needs, and names the reference code it replaces (paths relative to the
+ * reference repository root).  The Python host in `octreelib_b200/` binds these with ctypes; a
+ * reference maintainer would add the same stubs.
+ *
+ * Conventions
+ *   - plain C types only; every function returns an ol_status (0 = OK); ol_last_error() gives the
+ *     message of the last failure on the calling thread.
+ *   - one forest handle = one CUDA device + one stream + one caller thread.
+ *   - device memory comes from the caller's allocator callbacks (the Python binding passes
+ *     torch's caching allocator); with NULL callbacks the library uses cudaMallocAsync.
+ *   - `*_host` pointers are host memory, `*_dev` pointers are device memory on the forest's device.
+ *   - poses are identified by a dense "pose index" = order of insertion (0, 1, 2, ...); the host
+ *     keeps the user's pose-number <-> index map.
+ */
+#ifndef OCTREELIB_B200_H
+#define OCTREELIB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OL_ABI_VERSION 1
+#define OL_MAX_DEPTH 21 /* 3 * 21 = 63 Morton bits */
+
+typedef enum ol_status {
+    OL_OK = 0,
+    OL_ERR_INVALID = 1,     /* bad argument                         -> ValueError */
+    OL_ERR_CUDA = 2,        /* CUDA runtime failure                 -> RuntimeError */
+    OL_ERR_ALLOC = 3,       /* allocator callback failed            -> MemoryError */
+    OL_ERR_RANGE = 4,       /* cell coordinates do not fit the key  -> ValueError */
+    OL_ERR_OUT_OF_NODE = 5, /* octree/octree.py:98 IndexError       -> IndexError */
+    OL_ERR_DEPTH_CAP = 6,   /* reference would recurse deeper       -> RecursionError */
+    OL_ERR_NONFINITE = 7,   /* NaN / inf input                      -> ValueError */
+    OL_ERR_STATE = 8,       /* call not valid in the current state  -> RuntimeError */
+    OL_ERR_POSE = 9         /* unknown pose index                   -> KeyError */
+} ol_status;
+
+typedef void *(*ol_alloc_fn)(void *user, size_t bytes);
+typedef void (*ol_free_fn)(void *user, void *ptr);
+
+typedef struct ol_forest ol_forest; /* opaque: a Grid (many cells) or one OctreeManager cell */
+
+typedef struct ol_forest_config {
+    double voxel_edge_length; /* GridConfig.voxel_edge_length, grid/grid_base.py:70 */
+    double corner[3];         /* GridConfig.corner, grid/grid_base.py:71; single_cell: corner_min */
+    int32_t single_cell;      /* 1 = one fixed cell (OctreeManager / Octree used directly,
+                                 octree_manager/octree_manager.py:21-34): no cell hashing */
+    int32_t max_depth;        /* octree depth cap, 1..OL_MAX_DEPTH (reference: unbounded) */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t reserved;
+    void *stream;             /* cudaStream_t all work is enqueued on */
+    ol_alloc_fn alloc;        /* device allocator callbacks (may be NULL) */
+    ol_free_fn free;
+    void *alloc_user;
+} ol_forest_config;
+
+typedef struct ol_forest_stats {
+    int64_t n_points_inserted; /* all points ever inserted */
+    int64_t n_points_alive;    /* after filter / RANSAC masks */
+    int64_t n_poses;
+    int64_t n_cells;
+    int64_t n_cell_poses;  /* (cell, pose) pairs that own an octree */
+    int64_t n_leaves;      /* leaves of the shared per-cell tree shape, empty ones included */
+    int64_t n_internal;    /* internal (split) nodes */
+    int64_t n_blocks;      /* non-empty (pose, leaf) pairs = RANSAC blocks */
+    int64_t max_block_size;
+    int64_t max_depth_reached;
+    int64_t key_bits;      /* significant bits of the packed cell key */
+    int64_t device_bytes_peak;
+} ol_forest_stats;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int ol_abi_version(void);
+const char *ol_last_error(void);
+
+/* ---- forest lifetime ------------------------------------------------------------------------ */
+/* Grid.__init__ (grid/grid.py:49-56) / OctreeManager.__init__ (octree_manager.py:21-34) */
+int ol_forest_create(const ol_forest_config *config, ol_forest **out);
+int ol_forest_destroy(ol_forest *f);
+
+/* ---- Grid.insert_points, grid/grid.py:58-109 ------------------------------------------------
+ * Appends one pose's cloud ([n][3] float64, host or device memory).  Returns the new pose index.
+ * The re-insert ValueError (grid.py:65-66) is raised by the host, which owns pose numbers. */
+int ol_forest_insert(ol_forest *f, const double *xyz, int64_t n, int32_t src_on_device, int32_t *out_pose_index);
+
+/* Multi-GPU form: the cloud is a concatenation of `n_segments` runs, run s holding
+ * `seg_sizes[s]` points of pose index `seg_pose[s]` whose first point has index `seg_first[s]`
+ * inside that pose's original cloud (what an all-to-all delivers: one run per (source rank, pose)).
+ * Pose indices may repeat and need not be dense; `n_poses_total` fixes the pose count. */
+int ol_forest_insert_segments(ol_forest *f, const double *xyz, int64_t n, int32_t src_on_device,
+                              const int64_t *seg_sizes, const int32_t *seg_pose, const int64_t *seg_first,
+                              int32_t n_segments, int32_t n_poses_total);
+
+/* ---- Grid.subdivide, grid/grid.py:244-258 -> OctreeManager.subdivide, octree_manager.py:36-66 --
+ * Level-synchronous split of every cell: a node splits iff (#points of the listed poses inside it)
+ * > max_points (criterion `len(points) > max_points`, octree/octree.py:26).  n_poses == 0 means
+ * "all poses of the cell" (octree_manager.py:46-47).  The shape is imposed on every pose. */
+int ol_forest_subdivide(ol_forest *f, int64_t max_points, const int32_t *pose_indices, int32_t n_poses);
+
+/* Same, but the per-node decision comes from a count -> {0,1} table (an arbitrary count-only
+ * criterion list folded by the host); counts >= table_len use split_beyond. */
+int ol_forest_subdivide_table(ol_forest *f, const uint8_t *split_table_host, int64_t table_len, int32_t split_beyond,
+                              const int32_t *pose_indices, int32_t n_poses);
+
+/* ---- Grid.filter, grid/grid.py:260-267 -> octree/octree.py:102-112 --------------------------
+ * A (pose, leaf) block of n points survives iff keep_table[min(n, table_len-1)] != 0; the tree
+ * shape is unchanged.  n_poses == 0: all poses. */
+int ol_forest_filter(ol_forest *f, const uint8_t *keep_table_host, int64_t table_len, const int32_t *pose_indices,
+                     int32_t n_poses);
+
+/* ---- Grid.map_leaf_points_cuda_ransac, grid/grid.py:124-215 ---------------------------------
+ * table_host: [H][K] float64 uniform [0,1) hypothesis table (ransac/cuda_ransac.py:39-41).
+ * pose_rank[p]: position of pose index p in the reference's batch order (= its pose number when
+ * numbers are 0..P-1, grid.py:149-157).  With apply != 0 the inlier masks are applied
+ * (grid.py:203-215); otherwise they are only stored for export. */
+int ol_forest_ransac(ol_forest *f, const double *table_host, int32_t H, int32_t K, double threshold,
+                     const int32_t *pose_rank, int32_t poses_per_batch, int32_t apply, uint32_t flags);
+/* applies the mask of the last ol_forest_ransac(apply = 0) call (grid.py:203-215) */
+int ol_forest_apply_mask(ol_forest *f);
+
+/* OctreeManager.apply_mask / Octree.apply_mask (octree_manager.py:173-180, octree/octree.py:265-274):
+ * mask_host[n] covers the points of pose `pose_index` in the order of ol_forest_export_points(order 0);
+ * points with mask 0 are removed. */
+int ol_forest_apply_pose_mask(ol_forest *f, const int32_t *pose_rank, int32_t pose_index, const uint8_t *mask_host,
+                              int64_t n);
+
+/* ---- counters: Grid.n_leaves / n_points / n_nodes, grid/grid.py:343-362 ---------------------- */
+int ol_forest_stats_get(ol_forest *f, ol_forest_stats *out);
+/* out[p] = {n_leaves, n_points, n_nodes} for pose index p, [n_poses][3] int64 */
+int ol_forest_pose_counts(ol_forest *f, int64_t *out_host);
+
+/* ---- exports (host buffers sized from ol_forest_stats_get; any pointer may be NULL) ----------
+ * cells, lexicographic by signed (ix,iy,iz) (grid.py:79-81):
+ *   q[C][3] integer cell coordinates, corner[C][3] float64 cell corner, first_pose[C] pose index
+ *   that created the cell (dict order of grid.py:56), n_nodes[C] nodes of the cell's tree,
+ *   leaf_begin[C+1] range of the cell's leaves in the leaf table below. */
+int ol_forest_export_cells(ol_forest *f, int64_t *q, double *corner, int32_t *first_pose, int64_t *n_nodes,
+                           int64_t *leaf_begin);
+/* (cell, pose) pairs, sorted by (cell, pose index): which poses own an octree in which cell */
+int ol_forest_export_cell_poses(ol_forest *f, int32_t *cell, int32_t *pose);
+/* leaves in the reference's enumeration order (cells lexicographic, inside a cell the
+ * `_cached_leaves` order of octree/octree_base.py:48-49 + octree/octree.py:183-191):
+ *   corner[L][3], edge[L] (octree.py:181-187), cell[L], depth[L] */
+int ol_forest_export_leaves(ol_forest *f, double *corner, double *edge, int32_t *cell, int32_t *depth);
+/* non-empty (pose, leaf) blocks in the order Grid.get_leaf_points / the RANSAC batches use
+ * (pose rank, then leaf order above):  pose[B], leaf[B] (index into the leaf table), size[B]. */
+int ol_forest_export_blocks(ol_forest *f, const int32_t *pose_rank, int32_t *pose, int32_t *leaf, int32_t *size);
+/* the block table as it was when ol_forest_ransac last ran (before the masks were applied), same
+ * order, plus per block: plane[B][4] float32, best[B] (hypothesis index, -1 = skipped because the
+ * block has fewer than K points, ransac/cuda_ransac.py:96-97), best_count[B] (its inlier count).
+ * *out_n = number of rows (pass NULL arrays first to size the buffers). */
+int ol_forest_export_ransac(ol_forest *f, int32_t *pose, int32_t *leaf, int32_t *size, float *plane, int32_t *best,
+                            int32_t *best_count, int64_t *out_n);
+/* points of one pose (pose_index >= 0) or of all poses (-1, pose-rank-major):
+ *   order 0: block order of ol_forest_export_blocks, original input order inside a block
+ *   order 1: cells lexicographic, depth-first leaf order inside a cell (octree.py:55-65)
+ * xyz[n][3] float64, idx[n] index of the point in its pose's inserted cloud, cell[n] cell index,
+ * mask[n] last RANSAC inlier mask (order 0 only, before it was applied). */
+int ol_forest_export_points(ol_forest *f, const int32_t *pose_rank, int32_t pose_index, int32_t order, double *xyz,
+                            int64_t *idx, int32_t *cell, uint8_t *mask, int64_t *out_n);
+
+/* ---- CudaRansac.evaluate, ransac/cuda_ransac.py:43-81 (kernel-level boundary) ----------------
+ * points_dev [n][3] float64, block_sizes_dev [B] int32 back to back, table_dev [H][K] float64;
+ * outputs: mask_dev [n] uint8, plane_dev [B][4] float32, best_dev [B], best_count_dev [B]
+ * (the three per-block outputs may be NULL).  flags: bit0 = no TMA staging (plain loads). */
+int ol_ransac_evaluate(void *stream, const double *points_dev, int64_t n, const int32_t *block_sizes_dev, int64_t B,
+                       const double *table_dev, int32_t H, int32_t K, double threshold, uint8_t *mask_dev,
+                       float *plane_dev, int32_t *best_dev, int32_t *best_count_dev, uint32_t flags,
+                       ol_alloc_fn alloc, ol_free_fn free_fn, void *alloc_user);
+
+/* ---- primitives, exported so that tests can check them in isolation -------------------------- */
+/* stable LSD radix sort of (key, value) pairs on bits [begin_bit, end_bit); result in keys_dev/vals_dev */
+int ol_sort_pairs_u64(void *stream, uint64_t *keys_dev, uint32_t *vals_dev, int64_t n, int32_t begin_bit,
+                      int32_t end_bit, ol_alloc_fn alloc, ol_free_fn free_fn, void *alloc_user);
+int ol_sort_pairs_u32(void *stream, uint32_t *keys_dev, uint32_t *vals_dev, int64_t n, int32_t begin_bit,
+                      int32_t end_bit, ol_alloc_fn alloc, ol_free_fn free_fn, void *alloc_user);
+/* exclusive prefix sum, in place allowed; total written to *total_host if non-NULL (synchronises) */
+int ol_exclusive_scan_u32(void *stream, const uint32_t *in_dev, uint32_t *out_dev, int64_t n, uint64_t *total_host,
+                          ol_alloc_fn alloc, ol_free_fn free_fn, void *alloc_user);
+/* host restatement of numpy's float64 floor_divide (grid.py:72-76), for CPU-side tests */
+double ol_host_floor_divide(double a, double b);
+/* cell coordinate + Morton code of one point exactly as the device computes them (CPU-side tests) */
+int ol_host_point_key(double edge, const double corner[3], int32_t single_cell, int32_t depth, const double p[3],
+                      int64_t q[3], uint64_t *morton, int32_t *bad_level);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCTREELIB_B200_H */

@@ -1,0 +1,125 @@
+"""
+`ForestHost`: the host-side logic shared by `Grid`, `OctreeManager` and `Octree` -- pose-number
+bookkeeping, criteria folding, counters and object materialisation on top of one native forest.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _views
+from .criteria import as_threshold, fold_count_criteria
+from .forest import Forest
+
+__all__ = ["ForestHost"]
+
+_TABLE_CAP = 1 << 20
+
+
+class ForestHost:
+    def __init__(self, edge, corner, single_cell: bool, max_depth: int = 21):
+        self._edge = edge
+        self._corner = corner
+        self._single_cell = single_cell
+        self._max_depth = max_depth
+        self._forest: Optional[Forest] = None
+        self.pose_index: Dict[int, int] = {}   # pose number -> dense pose index (insertion order)
+        self.pose_numbers: List[int] = []      # pose index -> pose number
+        self.pose_inserted: List[int] = []     # points inserted so far per pose index
+        self._counts_cache = None
+
+    # ---- plumbing --------------------------------------------------------------------------------
+    @property
+    def forest(self) -> Forest:
+        if self._forest is None:
+            corner = np.asarray(self._corner, dtype=np.float64).reshape(3)
+            self._forest = Forest(float(self._edge), corner, single_cell=self._single_cell, max_depth=self._max_depth)
+        return self._forest
+
+    @property
+    def empty(self) -> bool:
+        return self._forest is None or not self.pose_numbers
+
+    def _indices(self, pose_numbers: Optional[Sequence[int]]) -> Optional[List[int]]:
+        if pose_numbers is None:
+            return None
+        return [self.pose_index[p] for p in pose_numbers]  # KeyError like the reference (octree_manager.py:56)
+
+    # ---- insertion ------------------------------------------------------------------------------
+    def insert(self, pose_number: int, points, allow_append: bool):
+        n = int(points.shape[0]) if hasattr(points, "shape") and len(points.shape) == 2 else len(points)
+        if pose_number in self.pose_index:
+            if not allow_append:
+                raise ValueError(f"Cannot insert points to existing pose {pose_number}")
+            idx = self.pose_index[pose_number]
+            self.forest.insert_segments(points, [n], [idx], [self.pose_inserted[idx]], len(self.pose_numbers))
+            self.pose_inserted[idx] += n
+        else:
+            idx = self.forest.insert(points)
+            assert idx == len(self.pose_numbers)
+            self.pose_index[pose_number] = idx
+            self.pose_numbers.append(pose_number)
+            self.pose_inserted.append(n)
+        self._counts_cache = None
+
+    # ---- subdivision / filtering ----------------------------------------------------------------
+    def subdivide(self, criteria: Sequence[Callable], pose_numbers: Optional[Sequence[int]] = None):
+        if self.empty:
+            return
+        idx = self._indices(pose_numbers)
+        table, beyond = fold_count_criteria(criteria, "any", 1024)
+        thr = as_threshold(table, beyond)
+        if thr is not None:
+            self.forest.subdivide(thr, idx)
+        else:
+            n_alive = self.forest.stats()["n_points_alive"]
+            upto = min(n_alive + 1, _TABLE_CAP)
+            table, beyond = fold_count_criteria(criteria, "any", upto)
+            if beyond is None:
+                if upto <= n_alive:
+                    raise NotImplementedError("count criterion without a settled answer for very large nodes")
+                beyond = False
+            self.forest.subdivide_table(table, beyond, idx)
+        self._counts_cache = None
+
+    def filter(self, criteria: Sequence[Callable], pose_numbers: Optional[Sequence[int]] = None):
+        if self.empty:
+            return
+        idx = self._indices(pose_numbers)
+        max_block = self.forest.stats()["max_block_size"]
+        upto = min(max_block + 1, _TABLE_CAP)
+        table, beyond = fold_count_criteria(criteria, "all", upto)
+        if upto <= max_block:  # blocks larger than the table share its last entry
+            if beyond is None:
+                raise NotImplementedError("count criterion without a settled answer for very large leaves")
+            table[-1] = 1 if beyond else 0
+        # an EMPTY leaf is also "filtered" by the reference, which changes nothing
+        self.forest.filter(table, idx)
+        self._counts_cache = None
+
+    # ---- counters (grid.py:343-362) --------------------------------------------------------------
+    def counts(self) -> np.ndarray:
+        if self._counts_cache is None or self._counts_cache[0] != self.forest.version:
+            self._counts_cache = (self.forest.version, self.forest.pose_counts(len(self.pose_numbers)))
+        return self._counts_cache[1]
+
+    def count(self, pose_number: int, which: int) -> int:
+        if self.empty or pose_number not in self.pose_index:
+            return 0
+        return int(self.counts()[self.pose_index[pose_number], which])
+
+    # ---- materialisation -------------------------------------------------------------------------
+    def leaf_voxels(self, pose_number: int, non_empty: bool, root_corner, root_edge):
+        idx = self.pose_index[pose_number]
+        return _views.leaf_voxels(self.forest, idx, non_empty, root_corner, root_edge)
+
+    def points_dfs(self, pose_number: int) -> np.ndarray:
+        if self.empty or pose_number not in self.pose_index:
+            return np.empty((0, 3), dtype=float)
+        return self.forest.export_points(self.pose_index[pose_number], order=1)["xyz"]
+
+    def points_dict_order(self, pose_number: int) -> np.ndarray:
+        if self.empty or pose_number not in self.pose_index:
+            return np.empty((0, 3), dtype=float)
+        return _views.points_dict_order(self.forest, self.pose_index[pose_number])

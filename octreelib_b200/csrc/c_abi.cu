@@ -1,0 +1,338 @@
+// extern "C" entry points of liboctreelib_b200 (declared in include/octreelib_b200.h).
+#include <new>
+
+#include "forest.cuh"
+#include "primitives.cuh"
+
+struct ol_forest {
+    ol::Forest impl;
+    explicit ol_forest(const ol_forest_config& c) : impl(c) {}
+};
+
+namespace ol {
+static thread_local std::string g_last_error;
+void set_last_error(int code, const std::string& msg) { g_last_error = "[ol_status " + std::to_string(code) + "] " + msg; }
+}  // namespace ol
+
+#define OL_API_BEGIN try {
+#define OL_API_END                                                     \
+    }                                                                  \
+    catch (const ol::Error& e) {                                       \
+        ol::set_last_error(e.code, e.msg);                             \
+        return e.code;                                                 \
+    }                                                                  \
+    catch (const std::bad_alloc&) {                                    \
+        ol::set_last_error(OL_ERR_ALLOC, "host out of memory");        \
+        return OL_ERR_ALLOC;                                           \
+    }                                                                  \
+    catch (const std::exception& e) {                                  \
+        ol::set_last_error(OL_ERR_INVALID, e.what());                  \
+        return OL_ERR_INVALID;                                         \
+    }                                                                  \
+    return OL_OK;
+
+#define OL_NEED(p)                                                                       \
+    if (!(p)) {                                                                          \
+        ol::set_last_error(OL_ERR_INVALID, "NULL argument: " #p);                        \
+        return OL_ERR_INVALID;                                                           \
+    }
+
+extern "C" {
+
+int ol_abi_version(void) { return OL_ABI_VERSION; }
+const char* ol_last_error(void) { return ol::g_last_error.c_str(); }
+
+int ol_forest_create(const ol_forest_config* config, ol_forest** out) {
+    OL_NEED(config);
+    OL_NEED(out);
+    OL_API_BEGIN
+    *out = new ol_forest(*config);
+    OL_API_END
+}
+
+int ol_forest_destroy(ol_forest* f) {
+    OL_API_BEGIN
+    delete f;
+    OL_API_END
+}
+
+int ol_forest_insert(ol_forest* f, const double* xyz, int64_t n, int32_t src_on_device, int32_t* out_pose_index) {
+    OL_NEED(f);
+    OL_API_BEGIN
+    int p = f->impl.insert(xyz, n, src_on_device != 0, nullptr, nullptr, nullptr, 0, 0);
+    if (out_pose_index) *out_pose_index = p;
+    OL_API_END
+}
+
+int ol_forest_insert_segments(ol_forest* f, const double* xyz, int64_t n, int32_t src_on_device, const int64_t* seg_sizes,
+                              const int32_t* seg_pose, const int64_t* seg_first, int32_t n_segments, int32_t n_poses_total) {
+    OL_NEED(f);
+    OL_NEED(seg_sizes);
+    OL_NEED(seg_pose);
+    OL_API_BEGIN
+    OL_REQUIRE(n_segments > 0, OL_ERR_INVALID, "n_segments must be positive");
+    f->impl.insert(xyz, n, src_on_device != 0, seg_sizes, seg_pose, seg_first, n_segments, n_poses_total);
+    OL_API_END
+}
+
+int ol_forest_subdivide(ol_forest* f, int64_t max_points, const int32_t* pose_indices, int32_t n_poses) {
+    OL_NEED(f);
+    OL_API_BEGIN
+    OL_REQUIRE(max_points >= 0, OL_ERR_INVALID, "max_points must be >= 0 (an empty node would split forever)");
+    f->impl.subdivide(max_points, nullptr, 0, 0, pose_indices, n_poses);
+    OL_API_END
+}
+
+int ol_forest_subdivide_table(ol_forest* f, const uint8_t* split_table_host, int64_t table_len, int32_t split_beyond,
+                              const int32_t* pose_indices, int32_t n_poses) {
+    OL_NEED(f);
+    OL_NEED(split_table_host);
+    OL_API_BEGIN
+    f->impl.subdivide(0, split_table_host, table_len, split_beyond, pose_indices, n_poses);
+    OL_API_END
+}
+
+int ol_forest_filter(ol_forest* f, const uint8_t* keep_table_host, int64_t table_len, const int32_t* pose_indices,
+                     int32_t n_poses) {
+    OL_NEED(f);
+    OL_NEED(keep_table_host);
+    OL_API_BEGIN
+    f->impl.filter(keep_table_host, table_len, pose_indices, n_poses);
+    OL_API_END
+}
+
+int ol_forest_ransac(ol_forest* f, const double* table_host, int32_t H, int32_t K, double threshold, const int32_t* pose_rank,
+                     int32_t poses_per_batch, int32_t apply, uint32_t flags) {
+    OL_NEED(f);
+    OL_NEED(table_host);
+    OL_API_BEGIN
+    f->impl.ransac(table_host, H, K, threshold, pose_rank, poses_per_batch, apply != 0, flags);
+    OL_API_END
+}
+
+int ol_forest_apply_mask(ol_forest* f) {
+    OL_NEED(f);
+    OL_API_BEGIN
+    f->impl.apply_mask();
+    OL_API_END
+}
+
+int ol_forest_apply_pose_mask(ol_forest* f, const int32_t* pose_rank, int32_t pose_index, const uint8_t* mask_host, int64_t n) {
+    OL_NEED(f);
+    OL_API_BEGIN
+    f->impl.apply_pose_mask(pose_rank, pose_index, mask_host, n);
+    OL_API_END
+}
+
+int ol_forest_stats_get(ol_forest* f, ol_forest_stats* out) {
+    OL_NEED(f);
+    OL_NEED(out);
+    OL_API_BEGIN
+    f->impl.stats(out);
+    OL_API_END
+}
+
+int ol_forest_pose_counts(ol_forest* f, int64_t* out_host) {
+    OL_NEED(f);
+    OL_NEED(out_host);
+    OL_API_BEGIN
+    f->impl.pose_counts(out_host);
+    OL_API_END
+}
+
+int ol_forest_export_cells(ol_forest* f, int64_t* q, double* corner, int32_t* first_pose, int64_t* n_nodes, int64_t* leaf_begin) {
+    OL_NEED(f);
+    OL_API_BEGIN
+    f->impl.export_cells(q, corner, first_pose, n_nodes, leaf_begin);
+    OL_API_END
+}
+
+int ol_forest_export_cell_poses(ol_forest* f, int32_t* cell, int32_t* pose) {
+    OL_NEED(f);
+    OL_API_BEGIN
+    f->impl.export_cell_poses(cell, pose);
+    OL_API_END
+}
+
+int ol_forest_export_leaves(ol_forest* f, double* corner, double* edge, int32_t* cell, int32_t* depth) {
+    OL_NEED(f);
+    OL_API_BEGIN
+    f->impl.export_leaves(corner, edge, cell, depth);
+    OL_API_END
+}
+
+int ol_forest_export_blocks(ol_forest* f, const int32_t* pose_rank, int32_t* pose, int32_t* leaf, int32_t* size) {
+    OL_NEED(f);
+    OL_API_BEGIN
+    f->impl.export_blocks(pose_rank, pose, leaf, size);
+    OL_API_END
+}
+
+int ol_forest_export_ransac(ol_forest* f, int32_t* pose, int32_t* leaf, int32_t* size, float* plane, int32_t* best,
+                            int32_t* best_count, int64_t* out_n) {
+    OL_NEED(f);
+    OL_API_BEGIN
+    if (out_n) *out_n = f->impl.res_n;
+    f->impl.export_ransac(pose, leaf, size, plane, best, best_count);
+    OL_API_END
+}
+
+int ol_forest_export_points(ol_forest* f, const int32_t* pose_rank, int32_t pose_index, int32_t order, double* xyz, int64_t* idx,
+                            int32_t* cell, uint8_t* mask, int64_t* out_n) {
+    OL_NEED(f);
+    OL_API_BEGIN
+    int64_t n = f->impl.export_points(pose_rank, pose_index, order, xyz, idx, cell, mask);
+    if (out_n) *out_n = n;
+    OL_API_END
+}
+
+// ---- kernel-level RANSAC boundary (CudaRansac.evaluate, ransac/cuda_ransac.py:43-81) -----------
+namespace {
+__global__ void sizes_to_u32_kernel(const int32_t* sizes, uint32_t n, int K, uint32_t* out, uint32_t* wflags, uint32_t* maxsz) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    int s = sizes[b];
+    out[b] = s > 0 ? (uint32_t)s : 0u;
+    wflags[b] = s >= K ? 1u : 0u;
+    if (s > 0) atomicMax(maxsz, (uint32_t)s);
+}
+__global__ void starts_to_i64_kernel(const uint32_t* starts, uint32_t n, long long* out) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n) out[b] = (long long)starts[b];
+}
+__global__ void work_emit2_kernel(uint32_t nb, const uint32_t* flags, const uint32_t* scan_ex, uint32_t* work) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb && flags[b]) work[scan_ex[b]] = b;
+}
+ol::Ctx make_ctx(void* stream, ol_alloc_fn alloc, ol_free_fn free_fn, void* user) {
+    ol::Ctx c;
+    c.stream = (cudaStream_t)stream;
+    c.alloc_fn = alloc;
+    c.free_fn = free_fn;
+    c.alloc_user = user;
+    return c;
+}
+}  // namespace
+
+int ol_ransac_evaluate(void* stream, const double* points_dev, int64_t n, const int32_t* block_sizes_dev, int64_t B,
+                       const double* table_dev, int32_t H, int32_t K, double threshold, uint8_t* mask_dev, float* plane_dev,
+                       int32_t* best_dev, int32_t* best_count_dev, uint32_t flags, ol_alloc_fn alloc, ol_free_fn free_fn,
+                       void* alloc_user) {
+    OL_API_BEGIN
+    using namespace ol;
+    OL_REQUIRE(threshold > 0, OL_ERR_INVALID, "Threshold must be positive");
+    OL_REQUIRE(H >= 1 && H <= 1024, OL_ERR_INVALID, "hypotheses_number must be in 1..1024");
+    OL_REQUIRE(K >= 1 && K <= 64, OL_ERR_INVALID, "initial_points_number must be in 1..64");
+    OL_REQUIRE(n >= 0 && n < (1ll << 31) && B >= 0 && B < (1ll << 31), OL_ERR_INVALID, "sizes out of range");
+    Ctx c = make_ctx(stream, alloc, free_fn, alloc_user);
+    if (n) OL_CUDA(cudaMemsetAsync(mask_dev, 0, (size_t)n, c.stream));
+    if (B == 0) return OL_OK;
+    const uint32_t nb = (uint32_t)B;
+    DevBuf<uint32_t> err(c, 1), sizes(c, nb), starts(c, nb), wflags(c, nb), wscan(c, nb), maxsz(c, 1);
+    DevBuf<long long> ref(c, nb);
+    DevBuf<unsigned long long> d_total(c, 2);
+    err.zero();
+    maxsz.zero();
+    c.d_err = err.get();
+    const unsigned g = (nb + 255) / 256;
+    sizes_to_u32_kernel<<<g, 256, 0, c.stream>>>(block_sizes_dev, nb, K, sizes.get(), wflags.get(), maxsz.get());
+    OL_CHECK_LAUNCH();
+    exclusive_scan_u32(c, sizes.get(), starts.get(), nb, d_total.get());  // cuda_ransac.py:65-67
+    exclusive_scan_u32(c, wflags.get(), wscan.get(), nb, d_total.get() + 1);
+    starts_to_i64_kernel<<<g, 256, 0, c.stream>>>(starts.get(), nb, ref.get());
+    OL_CHECK_LAUNCH();
+    unsigned long long tot[2];
+    uint32_t mx;
+    OL_CUDA(cudaMemcpyAsync(tot, d_total.get(), 16, cudaMemcpyDeviceToHost, c.stream));
+    OL_CUDA(cudaMemcpyAsync(&mx, maxsz.get(), 4, cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    OL_REQUIRE((int64_t)tot[0] == n, OL_ERR_INVALID, "block_sizes do not add up to the number of points");
+    if (plane_dev) OL_CUDA(cudaMemsetAsync(plane_dev, 0, (size_t)nb * 16, c.stream));
+    if (best_count_dev) OL_CUDA(cudaMemsetAsync(best_count_dev, 0, (size_t)nb * 4, c.stream));
+    if (best_dev) {
+        fill_kernel<int32_t><<<g, 256, 0, c.stream>>>(best_dev, nb, -1);
+        OL_CHECK_LAUNCH();
+    }
+    const uint32_t n_work = (uint32_t)tot[1];
+    DevBuf<uint32_t> work(c, n_work);
+    work_emit2_kernel<<<g, 256, 0, c.stream>>>(nb, wflags.get(), wscan.get(), work.get());
+    OL_CHECK_LAUNCH();
+    launch_ransac(c, points_dev, n, starts.get(), block_sizes_dev, ref.get(), work.get(), n_work, mx, table_dev, H, K, threshold,
+                  mask_dev, plane_dev, best_dev, best_count_dev, flags);
+    c.sync();
+    OL_API_END
+}
+
+// ---- primitives ---------------------------------------------------------------------------------
+int ol_sort_pairs_u64(void* stream, uint64_t* keys_dev, uint32_t* vals_dev, int64_t n, int32_t begin_bit, int32_t end_bit,
+                      ol_alloc_fn alloc, ol_free_fn free_fn, void* alloc_user) {
+    OL_API_BEGIN
+    using namespace ol;
+    OL_REQUIRE(n >= 0 && begin_bit >= 0 && end_bit <= 64 && begin_bit <= end_bit, OL_ERR_INVALID, "bad sort arguments");
+    Ctx c = make_ctx(stream, alloc, free_fn, alloc_user);
+    DevBuf<uint64_t> k1(c, (size_t)n);
+    DevBuf<uint32_t> v1(c, (size_t)n);
+    int w = radix_sort_pairs<uint64_t>(c, keys_dev, k1.get(), vals_dev, v1.get(), (size_t)n, begin_bit, end_bit);
+    if (w) {
+        d2d(c, keys_dev, k1.get(), (size_t)n);
+        d2d(c, vals_dev, v1.get(), (size_t)n);
+    }
+    c.sync();
+    OL_API_END
+}
+
+int ol_sort_pairs_u32(void* stream, uint32_t* keys_dev, uint32_t* vals_dev, int64_t n, int32_t begin_bit, int32_t end_bit,
+                      ol_alloc_fn alloc, ol_free_fn free_fn, void* alloc_user) {
+    OL_API_BEGIN
+    using namespace ol;
+    OL_REQUIRE(n >= 0 && begin_bit >= 0 && end_bit <= 32 && begin_bit <= end_bit, OL_ERR_INVALID, "bad sort arguments");
+    Ctx c = make_ctx(stream, alloc, free_fn, alloc_user);
+    DevBuf<uint32_t> k1(c, (size_t)n), v1(c, (size_t)n);
+    int w = radix_sort_pairs<uint32_t>(c, keys_dev, k1.get(), vals_dev, v1.get(), (size_t)n, begin_bit, end_bit);
+    if (w) {
+        d2d(c, keys_dev, k1.get(), (size_t)n);
+        d2d(c, vals_dev, v1.get(), (size_t)n);
+    }
+    c.sync();
+    OL_API_END
+}
+
+int ol_exclusive_scan_u32(void* stream, const uint32_t* in_dev, uint32_t* out_dev, int64_t n, uint64_t* total_host,
+                          ol_alloc_fn alloc, ol_free_fn free_fn, void* alloc_user) {
+    OL_API_BEGIN
+    using namespace ol;
+    OL_REQUIRE(n >= 0, OL_ERR_INVALID, "negative length");
+    Ctx c = make_ctx(stream, alloc, free_fn, alloc_user);
+    DevBuf<unsigned long long> d_total(c, 1);
+    exclusive_scan_u32(c, in_dev, out_dev, (size_t)n, d_total.get());
+    if (total_host) {
+        unsigned long long t;
+        OL_CUDA(cudaMemcpyAsync(&t, d_total.get(), 8, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+        *total_host = t;
+    } else {
+        c.sync();
+    }
+    OL_API_END
+}
+
+double ol_host_floor_divide(double a, double b) { return ol::npy_floor_divide(a, b); }
+
+int ol_host_point_key(double edge, const double corner[3], int32_t single_cell, int32_t depth, const double p[3], int64_t q[3],
+                      uint64_t* morton, int32_t* bad_level) {
+    OL_API_BEGIN
+    OL_REQUIRE(depth >= 0 && depth <= OL_MAX_DEPTH, OL_ERR_INVALID, "depth out of range");
+    double c0[3];
+    for (int a = 0; a < 3; ++a) {
+        long long qa = single_cell ? 0 : (long long)ol::cell_coord(p[a], corner[a], edge);
+        q[a] = qa;
+        c0[a] = ol::cell_corner_coord(qa, corner[a], edge, single_cell);
+    }
+    int bad;
+    unsigned long long m = ol::point_morton(p, c0, edge, depth, &bad);
+    if (morton) *morton = m;
+    if (bad_level) *bad_level = bad;
+    OL_API_END
+}
+
+}  // extern "C"

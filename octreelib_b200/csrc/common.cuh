@@ -1,0 +1,195 @@
+// Common host/device helpers for liboctreelib_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/octreelib_b200.h"
+
+namespace ol {
+
+// ---------------------------------------------------------------------------------------------
+// error handling: every C-ABI entry point returns an ol_status; details via ol_last_error().
+// ---------------------------------------------------------------------------------------------
+struct Error {
+    int code;
+    std::string msg;
+};
+
+void set_last_error(int code, const std::string& msg);
+
+#define OL_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            throw ::ol::Error{OL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)};    \
+        }                                                                                          \
+    } while (0)
+
+#define OL_CHECK_LAUNCH() OL_CUDA(cudaGetLastError())
+
+#define OL_REQUIRE(cond, code, text)                 \
+    do {                                             \
+        if (!(cond)) throw ::ol::Error{(code), (text)}; \
+    } while (0)
+
+// device-side error bits (accumulated with atomicOr into Ctx::d_err, read at sync points)
+enum DevErr : uint32_t {
+    DEVERR_NONFINITE = 1u,      // NaN / inf coordinate
+    DEVERR_CELL_RANGE = 2u,     // cell coordinate outside the packed key range
+    DEVERR_OUT_OF_NODE = 4u,    // point outside its node at a level that is being split (octree.py:98)
+    DEVERR_DEPTH_CAP = 8u,      // a node still exceeds the criterion at the maximum depth
+    DEVERR_SAMPLE_OOB = 16u,    // RANSAC sample index fell outside its block (clamped)
+};
+
+// ---------------------------------------------------------------------------------------------
+// execution context: stream + allocator callbacks (the host binding passes torch's caching
+// allocator; NULL callbacks fall back to cudaMallocAsync / cudaFreeAsync on the stream).
+// ---------------------------------------------------------------------------------------------
+struct Ctx {
+    cudaStream_t stream = nullptr;
+    ol_alloc_fn alloc_fn = nullptr;
+    ol_free_fn free_fn = nullptr;
+    void* alloc_user = nullptr;
+    uint32_t* d_err = nullptr;  // device error word
+    int num_sms = 148;
+    size_t bytes_live = 0, bytes_peak = 0;
+
+    void* alloc(size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        void* p = nullptr;
+        if (alloc_fn) {
+            p = alloc_fn(alloc_user, bytes);
+            if (!p) throw Error{OL_ERR_ALLOC, "host allocator callback returned NULL for " + std::to_string(bytes) + " bytes"};
+        } else {
+            OL_CUDA(cudaMallocAsync(&p, bytes, stream));
+        }
+        bytes_live += bytes;
+        if (bytes_live > bytes_peak) bytes_peak = bytes_live;
+        return p;
+    }
+    void free(void* p, size_t bytes) {
+        if (!p) return;
+        if (bytes == 0) bytes = 16;
+        bytes_live -= bytes;
+        if (free_fn)
+            free_fn(alloc_user, p);
+        else
+            cudaFreeAsync(p, stream);
+    }
+    void sync() { OL_CUDA(cudaStreamSynchronize(stream)); }
+};
+
+// RAII device buffer of T, bound to a Ctx.
+template <typename T>
+struct DevBuf {
+    Ctx* ctx = nullptr;
+    T* ptr = nullptr;
+    size_t count = 0;
+
+    DevBuf() = default;
+    DevBuf(Ctx& c, size_t n) { reset(c, n); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept { *this = std::move(o); }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            ctx = o.ctx;
+            ptr = o.ptr;
+            count = o.count;
+            o.ptr = nullptr;
+            o.count = 0;
+        }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void reset(Ctx& c, size_t n) {
+        release();
+        ctx = &c;
+        count = n;
+        ptr = static_cast<T*>(c.alloc(n * sizeof(T)));
+    }
+    void release() {
+        if (ptr && ctx) ctx->free(ptr, count * sizeof(T));
+        ptr = nullptr;
+        count = 0;
+    }
+    void swap(DevBuf& o) {
+        std::swap(ctx, o.ctx);
+        std::swap(ptr, o.ptr);
+        std::swap(count, o.count);
+    }
+    void zero() {
+        if (count) OL_CUDA(cudaMemsetAsync(ptr, 0, count * sizeof(T), ctx->stream));
+    }
+    T* get() const { return ptr; }
+    size_t size() const { return count; }
+};
+
+template <typename T>
+inline void d2h(Ctx& c, T* host, const T* dev, size_t n) {
+    if (n) OL_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost, c.stream));
+}
+template <typename T>
+inline void h2d(Ctx& c, T* dev, const T* host, size_t n) {
+    if (n) OL_CUDA(cudaMemcpyAsync(dev, host, n * sizeof(T), cudaMemcpyHostToDevice, c.stream));
+}
+template <typename T>
+inline void d2d(Ctx& c, T* dst, const T* src, size_t n) {
+    if (n) OL_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToDevice, c.stream));
+}
+
+inline unsigned grid_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// ---------------------------------------------------------------------------------------------
+// numpy float64 floor_divide, restated (numpy/core/src/npymath/npy_math_internal.h.src,
+// npy_divmod): the arithmetic behind `(points - corner) // edge` in
+// /root/reference/octreelib/grid/grid.py:72-76.  fmod is exact on host and device, the rest is
+// plain IEEE add/sub/div (the library is compiled with -fmad=false), so host and device agree.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline double npy_floor_divide(double a, double b) {
+    if (b == 0.0) return a / b;
+    double mod = fmod(a, b);
+    double div = (a - mod) / b;
+    if (mod != 0.0) {
+        if ((b < 0) != (mod < 0)) {
+            div -= 1.0;
+        }
+    }
+    double floordiv;
+    if (div != 0.0) {
+        floordiv = floor(div);
+        if (div - floordiv > 0.5) floordiv += 1.0;
+    } else {
+        floordiv = copysign(0.0, a / b);
+    }
+    return floordiv;
+}
+
+// order-preserving map double -> int64 (for atomicMin/atomicMax on coordinates)
+__host__ __device__ inline long long double_to_ordered(double v) {
+    long long b;
+#ifdef __CUDA_ARCH__
+    b = __double_as_longlong(v);
+#else
+    memcpy(&b, &v, 8);
+#endif
+    return b < 0 ? (b ^ 0x7fffffffffffffffLL) : b;
+}
+__host__ __device__ inline double ordered_to_double(long long k) {
+    long long b = k < 0 ? (k ^ 0x7fffffffffffffffLL) : k;
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double(b);
+#else
+    double v;
+    memcpy(&v, &b, 8);
+    return v;
+#endif
+}
+
+}  // namespace ol

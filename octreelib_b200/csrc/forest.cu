@@ -1,0 +1,592 @@
+// Forest pipeline: K1 keygen, K2 sort (primitives.cuh), K3 cell segmentation, K4 level-synchronous
+// subdivision, K5 leaf enumeration order + geometry, (pose, leaf) block table, K7 filter / mask
+// compaction.  K6 (RANSAC) lives in ransac.cu.
+#include <algorithm>
+#include <climits>
+
+#include "forest.cuh"
+#include "primitives.cuh"
+
+namespace ol {
+
+// =============================================================================================
+// small device helpers
+// =============================================================================================
+// segment of global rank r: last s with seg_start[s] <= r   (seg_start has n_seg + 1 entries)
+__device__ __forceinline__ int seg_of_rank(const uint32_t* __restrict__ seg_start, int n_seg, uint32_t r) {
+    int lo = 0, hi = n_seg;  // invariant: seg_start[lo] <= r < seg_start[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (seg_start[mid] <= r)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// bits [lo, hi) of x (hi <= 64), safe for empty fields and lo >= 64
+__device__ __forceinline__ uint64_t key_field(uint64_t x, int lo, int hi) {
+    const int width = hi - lo;
+    if (width <= 0 || lo >= 64) return 0ull;
+    uint64_t v = x >> lo;
+    if (width < 64) v &= (1ull << width) - 1ull;
+    return v;
+}
+
+__device__ __forceinline__ void unpack_cell(const KeyParams& kp, uint64_t ckey, long long q[3]) {
+    // ckey = packed key without the pose bits: [ x field | y field | z field ]
+    const int s0 = kp.shift[0] - kp.pose_bits, s1 = kp.shift[1] - kp.pose_bits, s2 = kp.shift[2] - kp.pose_bits;
+    q[0] = kp.qmin[0] + (long long)key_field(ckey, s0, 64);
+    q[1] = kp.qmin[1] + (long long)key_field(ckey, s1, s0);
+    q[2] = kp.qmin[2] + (long long)key_field(ckey, s2, s1);
+}
+
+// =============================================================================================
+// K0: bounding box of a newly inserted cloud (ordered-int atomics), non-finite check
+// =============================================================================================
+__global__ void __launch_bounds__(256) bbox_kernel(const double* __restrict__ xyz, size_t n, long long* __restrict__ bbox,
+                                                   uint32_t* __restrict__ err) {
+    long long mn[3] = {LLONG_MAX, LLONG_MAX, LLONG_MAX}, mx[3] = {LLONG_MIN, LLONG_MIN, LLONG_MIN};
+    bool bad = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            double v = xyz[i * 3 + a];
+            if (!isfinite(v)) bad = true;
+            long long k = double_to_ordered(v);
+            mn[a] = k < mn[a] ? k : mn[a];
+            mx[a] = k > mx[a] ? k : mx[a];
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            long long t = __shfl_xor_sync(0xffffffffu, mn[a], o);
+            mn[a] = t < mn[a] ? t : mn[a];
+            t = __shfl_xor_sync(0xffffffffu, mx[a], o);
+            mx[a] = t > mx[a] ? t : mx[a];
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (mn[a] != LLONG_MAX) atomicMin(&bbox[a], mn[a]);
+            if (mx[a] != LLONG_MIN) atomicMax(&bbox[3 + a], mx[a]);
+        }
+    }
+    if (bad) atomicOr(err, (uint32_t)DEVERR_NONFINITE);
+}
+
+// =============================================================================================
+// K1: packed cell key + in-cell Morton code per point (one pass over the raw cloud)
+// =============================================================================================
+__global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ xyz, uint32_t n, KeyParams kp,
+                                                     const uint32_t* __restrict__ seg_start,
+                                                     const int32_t* __restrict__ seg_pose, int n_seg,
+                                                     uint64_t* __restrict__ keys, uint64_t* __restrict__ mort,
+                                                     uint32_t* __restrict__ err) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double p[3] = {xyz[(size_t)r * 3 + 0], xyz[(size_t)r * 3 + 1], xyz[(size_t)r * 3 + 2]};
+    long long q[3] = {0, 0, 0};
+    uint64_t key = 0;
+    uint32_t e = 0;
+    if (!kp.single_cell) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            double qa = cell_coord(p[a], kp.corner[a], kp.edge);
+            if (!(fabs(qa) < 4503599627370496.0)) {  // 2^52
+                e |= DEVERR_CELL_RANGE;
+                qa = 0.0;
+            }
+            q[a] = (long long)qa;
+            long long rel = q[a] - kp.qmin[a];
+            if (rel < 0) {
+                e |= DEVERR_CELL_RANGE;
+                rel = 0;
+            }
+            if (kp.shift[a] < 64) key |= ((uint64_t)rel) << kp.shift[a];
+        }
+    }
+    if (kp.pose_bits) key |= (uint64_t)seg_pose[seg_of_rank(seg_start, n_seg, r)];
+    double c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) c[a] = cell_corner_coord(q[a], kp.corner[a], kp.edge, kp.single_cell);
+    int bad;
+    uint64_t m = point_morton(p, c, kp.edge, kp.depth, &bad);
+    if (bad < kp.depth) m |= MORTON_BAD_BIT;
+    keys[r] = key;
+    mort[r] = m;
+    if (e) atomicOr(err, e);
+}
+
+// =============================================================================================
+// K3: run-length segmentation of the sorted keys
+// =============================================================================================
+__global__ void cell_heads_kernel(const uint64_t* __restrict__ keys, uint32_t n, int pose_bits, uint32_t* __restrict__ flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flags[i] = (i == 0) || ((keys[i] >> pose_bits) != (keys[i - 1] >> pose_bits));
+}
+
+// scan_ex[i] = exclusive scan of flags; the index of position i's run is scan_ex[i] + flags[i] - 1
+__global__ void cell_emit_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ flags,
+                                 const uint32_t* __restrict__ scan_ex, uint32_t n, int pose_bits,
+                                 uint32_t* __restrict__ cellidx, uint64_t* __restrict__ cell_key,
+                                 uint32_t* __restrict__ cell_start) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c = scan_ex[i] + flags[i] - 1u;
+    cellidx[i] = c;
+    if (flags[i]) {
+        cell_key[c] = keys[i] >> pose_bits;
+        cell_start[c] = i;
+    }
+}
+
+__global__ void cp_heads_kernel(const uint32_t* __restrict__ cellidx, const uint32_t* __restrict__ perm,
+                                const uint32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_pose, int n_seg,
+                                uint32_t n, uint32_t* __restrict__ flags, int32_t* __restrict__ pose_of_pos) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t p = seg_pose[seg_of_rank(seg_start, n_seg, perm[i])];
+    pose_of_pos[i] = p;
+    bool head = (i == 0);
+    if (!head) {
+        int32_t pp = seg_pose[seg_of_rank(seg_start, n_seg, perm[i - 1])];
+        head = (cellidx[i] != cellidx[i - 1]) || (pp != p);
+    }
+    flags[i] = head;
+}
+
+__global__ void cp_emit_kernel(const uint32_t* __restrict__ cellidx, const int32_t* __restrict__ pose_of_pos,
+                               const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan_ex, uint32_t n,
+                               uint32_t* __restrict__ cp_cell, int32_t* __restrict__ cp_pose,
+                               int32_t* __restrict__ cell_first_pose) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flags[i]) {
+        uint32_t j = scan_ex[i];
+        cp_cell[j] = cellidx[i];
+        cp_pose[j] = pose_of_pos[i];
+        if (i == 0 || cellidx[i] != cellidx[i - 1]) cell_first_pose[cellidx[i]] = pose_of_pos[i];
+    }
+}
+
+// =============================================================================================
+// generic keep-flag compaction of the per-position arrays
+// =============================================================================================
+__global__ void keep_to_u32_kernel(const uint8_t* __restrict__ keep, uint32_t n, uint32_t* __restrict__ flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = keep[i] ? 1u : 0u;
+}
+
+__global__ void alive_flags_kernel(const uint8_t* __restrict__ alive_r, const uint32_t* __restrict__ perm, uint32_t n,
+                                   uint32_t* __restrict__ flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = alive_r[perm[i]] ? 1u : 0u;
+}
+
+__global__ void compact_pos_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan_ex, uint32_t n,
+                                   const uint32_t* __restrict__ perm_in, const uint64_t* __restrict__ mort_in,
+                                   const uint32_t* __restrict__ aux_in, uint32_t* __restrict__ perm_out,
+                                   uint64_t* __restrict__ mort_out, uint32_t* __restrict__ aux_out,
+                                   uint8_t* __restrict__ alive_r) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flags[i]) {
+        uint32_t j = scan_ex[i];
+        perm_out[j] = perm_in[i];
+        mort_out[j] = mort_in[i];
+        aux_out[j] = aux_in[i];
+    } else if (alive_r) {
+        alive_r[perm_in[i]] = 0;
+    }
+}
+
+// new_start[k] = scan_ex[old_start[k]] (k < m), new_start[m] = total
+__global__ void remap_starts_kernel(const uint32_t* __restrict__ old_start, const uint32_t* __restrict__ scan_ex,
+                                    uint32_t m, uint32_t n_old, uint32_t total, uint32_t* __restrict__ new_start) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > m) return;
+    if (k == m) {
+        new_start[k] = total;
+        return;
+    }
+    uint32_t s = old_start[k];
+    new_start[k] = (s < n_old) ? scan_ex[s] : total;
+}
+
+// =============================================================================================
+// K4: level-synchronous subdivision
+// =============================================================================================
+__global__ void weighted_count_kernel(const uint32_t* __restrict__ leaf_of, const uint32_t* __restrict__ perm,
+                                      const uint8_t* __restrict__ ldepth, int level,
+                                      const uint32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_pose,
+                                      int n_seg, const uint8_t* __restrict__ listed, uint32_t n,
+                                      uint32_t* __restrict__ wcount) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool on = false;
+    uint32_t k = 0xffffffffu;
+    if (i < n) {
+        k = leaf_of[i];
+        if (ldepth[k] == level) on = listed[seg_pose[seg_of_rank(seg_start, n_seg, perm[i])]] != 0;
+    }
+    uint32_t key = on ? k : 0xffffffffu;
+    uint32_t peers = __match_any_sync(0xffffffffu, key);
+    if (on && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&wcount[k], __popc(peers));
+}
+
+__global__ void decide_kernel(uint32_t L, const uint32_t* __restrict__ lstart, const uint8_t* __restrict__ ldepth,
+                              int level, const uint32_t* __restrict__ wcount, long long max_points,
+                              const uint8_t* __restrict__ table, long long table_len, int beyond, int max_depth,
+                              uint32_t* __restrict__ splitf, uint32_t* __restrict__ expand, uint32_t* __restrict__ err) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= L) return;
+    bool want = false;
+    if (ldepth[k] == level) {
+        long long cnt = wcount ? (long long)wcount[k] : (long long)(lstart[k + 1] - lstart[k]);
+        if (table)
+            want = (cnt < table_len) ? (table[cnt] != 0) : (beyond != 0);
+        else
+            want = cnt > max_points;
+        if (want && level >= max_depth) {
+            atomicOr(err, (uint32_t)DEVERR_DEPTH_CAP);
+            want = false;
+        }
+    }
+    splitf[k] = want ? 1u : 0u;
+    expand[k] = want ? 8u : 1u;
+}
+
+constexpr int PART_THREADS = 256;
+constexpr int PART_ITEMS = 8;
+constexpr int PART_TILE = PART_THREADS * PART_ITEMS;
+
+__device__ __forceinline__ uint32_t level_digit(uint64_t m, int shift) { return (uint32_t)(m >> shift) & 7u; }
+
+// per-tile histogram of the level digit over positions that belong to splitting leaves
+__global__ void __launch_bounds__(PART_THREADS) part_hist_kernel(const uint32_t* __restrict__ leaf_of,
+                                                                  const uint64_t* __restrict__ mort,
+                                                                  const uint32_t* __restrict__ splitf, uint32_t n,
+                                                                  uint32_t num_tiles, int shift,
+                                                                  uint32_t* __restrict__ tile_hist) {
+    __shared__ uint32_t h[8];
+    if (threadIdx.x < 8) h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * PART_TILE;
+#pragma unroll
+    for (int j = 0; j < PART_ITEMS; ++j) {
+        uint32_t i = base + j * PART_THREADS + threadIdx.x;
+        uint32_t g = 0xffffffffu;
+        if (i < n && splitf[leaf_of[i]]) g = level_digit(mort[i], shift);
+        uint32_t peers = __match_any_sync(0xffffffffu, g);
+        if (g != 0xffffffffu && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&h[g], __popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) tile_hist[(size_t)threadIdx.x * num_tiles + blockIdx.x] = h[threadIdx.x];
+}
+
+struct Packed8 {
+    unsigned long long lo, hi;  // 8 x 16-bit counters (digits 0..3 in lo, 4..7 in hi)
+};
+__device__ __forceinline__ uint32_t packed_get(const Packed8& p, uint32_t g) {
+    return (uint32_t)(((g < 4 ? p.lo : p.hi) >> ((g & 3u) * 16)) & 0xffffull);
+}
+__device__ __forceinline__ void packed_inc(Packed8& p, uint32_t g) {
+    unsigned long long one = 1ull << ((g & 3u) * 16);
+    if (g < 4)
+        p.lo += one;
+    else
+        p.hi += one;
+}
+
+// stable rank of every position of a splitting leaf among the positions with the same digit
+// (global running count S_g), plus S at the first / one-past-last position of every splitting leaf
+__global__ void __launch_bounds__(PART_THREADS) part_rank_kernel(
+    const uint32_t* __restrict__ leaf_of, const uint64_t* __restrict__ mort, const uint32_t* __restrict__ splitf,
+    const uint32_t* __restrict__ iidx, const uint32_t* __restrict__ lstart, const uint32_t* __restrict__ tile_off,
+    uint32_t n, uint32_t num_tiles, int shift, uint32_t* __restrict__ rank, uint32_t* __restrict__ Sbeg,
+    uint32_t* __restrict__ Send) {
+    __shared__ unsigned long long wlo[8], whi[8];
+    __shared__ uint32_t G[8];
+    if (threadIdx.x < 8) G[threadIdx.x] = tile_off[(size_t)threadIdx.x * num_tiles + blockIdx.x];
+    const uint32_t first = blockIdx.x * PART_TILE + threadIdx.x * PART_ITEMS;
+    uint32_t leaf[PART_ITEMS];
+    uint32_t g[PART_ITEMS];
+    Packed8 cnt{0ull, 0ull};
+#pragma unroll
+    for (int j = 0; j < PART_ITEMS; ++j) {
+        uint32_t i = first + j;
+        g[j] = 8u;
+        leaf[j] = 0;
+        if (i < n) {
+            leaf[j] = leaf_of[i];
+            if (splitf[leaf[j]]) {
+                g[j] = level_digit(mort[i], shift);
+                packed_inc(cnt, g[j]);
+            }
+        }
+    }
+    // block exclusive scan of the packed counters
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long ilo = cnt.lo, ihi = cnt.hi;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long tl = __shfl_up_sync(0xffffffffu, ilo, o);
+        unsigned long long th = __shfl_up_sync(0xffffffffu, ihi, o);
+        if (lane >= o) {
+            ilo += tl;
+            ihi += th;
+        }
+    }
+    if (lane == 31) {
+        wlo[warp] = ilo;
+        whi[warp] = ihi;
+    }
+    __syncthreads();
+    unsigned long long blo = 0, bhi = 0;
+    for (int w = 0; w < warp; ++w) {
+        blo += wlo[w];
+        bhi += whi[w];
+    }
+    Packed8 run{blo + ilo - cnt.lo, bhi + ihi - cnt.hi};
+#pragma unroll
+    for (int j = 0; j < PART_ITEMS; ++j) {
+        uint32_t i = first + j;
+        if (g[j] < 8u) {
+            const uint32_t k = leaf[j];
+            if (i == lstart[k]) {
+                const uint32_t s = iidx[k];
+#pragma unroll
+                for (uint32_t c = 0; c < 8; ++c) Sbeg[(size_t)s * 8 + c] = G[c] + packed_get(run, c);
+            }
+            rank[i] = G[g[j]] + packed_get(run, g[j]);
+            packed_inc(run, g[j]);
+            if (i + 1 == lstart[k + 1]) {
+                const uint32_t s = iidx[k];
+#pragma unroll
+                for (uint32_t c = 0; c < 8; ++c) Send[(size_t)s * 8 + c] = G[c] + packed_get(run, c);
+            }
+        }
+    }
+}
+
+// stable 8-way partition of every splitting leaf's range; everything else is copied through
+__global__ void __launch_bounds__(256) part_scatter_kernel(
+    const uint32_t* __restrict__ leaf_of, const uint64_t* __restrict__ mort, const uint32_t* __restrict__ perm,
+    const uint32_t* __restrict__ splitf, const uint32_t* __restrict__ iidx, const uint32_t* __restrict__ newidx,
+    const uint32_t* __restrict__ lstart, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ Sbeg,
+    const uint32_t* __restrict__ Send, uint32_t n, int shift, int level, uint32_t* __restrict__ leaf_out,
+    uint64_t* __restrict__ mort_out, uint32_t* __restrict__ perm_out,
+    // for the out-of-node re-check
+    const double* __restrict__ xyz, const uint32_t* __restrict__ lcell, const uint64_t* __restrict__ cell_key,
+    KeyParams kp, uint32_t* __restrict__ err) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = leaf_of[i];
+    const uint64_t m = mort[i];
+    const uint32_t r = perm[i];
+    uint32_t dst = i, nl = newidx[k];
+    if (splitf[k]) {
+        const uint32_t g = level_digit(m, shift);
+        const uint32_t s = iidx[k];
+        uint32_t base = lstart[k];
+        for (uint32_t c = 0; c < g; ++c) base += Send[(size_t)s * 8 + c] - Sbeg[(size_t)s * 8 + c];
+        dst = base + (rank[i] - Sbeg[(size_t)s * 8 + g]);
+        nl += g;
+        if (m & MORTON_BAD_BIT) {
+            // the point left its node at some level: an error only if that level is being split
+            long long q[3] = {0, 0, 0};
+            if (!kp.single_cell) unpack_cell(kp, cell_key[lcell[k]], q);
+            double p[3] = {xyz[(size_t)r * 3], xyz[(size_t)r * 3 + 1], xyz[(size_t)r * 3 + 2]};
+            double c0[3];
+            for (int a = 0; a < 3; ++a) c0[a] = cell_corner_coord(q[a], kp.corner[a], kp.edge, kp.single_cell);
+            int bad;
+            point_morton(p, c0, kp.edge, kp.depth, &bad);
+            if (bad <= level) atomicOr(err, (uint32_t)DEVERR_OUT_OF_NODE);
+        }
+    }
+    leaf_out[dst] = nl;
+    mort_out[dst] = m;
+    perm_out[dst] = r;
+}
+
+__global__ void expand_leaves_kernel(uint32_t L, uint32_t A, uint32_t I_old, const uint32_t* __restrict__ splitf,
+                                     const uint32_t* __restrict__ iidx, const uint32_t* __restrict__ newidx,
+                                     const uint32_t* __restrict__ Sbeg, const uint32_t* __restrict__ Send,
+                                     const uint32_t* __restrict__ lstart, const uint32_t* __restrict__ lcell,
+                                     const int32_t* __restrict__ lparent, const uint64_t* __restrict__ lpath,
+                                     const uint8_t* __restrict__ ldepth, const uint8_t* __restrict__ lchild,
+                                     uint32_t L_new, uint32_t* __restrict__ lstart_n, uint32_t* __restrict__ lcell_n,
+                                     int32_t* __restrict__ lparent_n, uint64_t* __restrict__ lpath_n,
+                                     uint8_t* __restrict__ ldepth_n, uint8_t* __restrict__ lchild_n,
+                                     uint32_t* __restrict__ istart, uint32_t* __restrict__ icell,
+                                     uint8_t* __restrict__ idepth) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= L) return;
+    const uint32_t j0 = newidx[k];
+    if (!splitf[k]) {
+        lstart_n[j0] = lstart[k];
+        lcell_n[j0] = lcell[k];
+        lparent_n[j0] = lparent[k];
+        lpath_n[j0] = lpath[k];
+        ldepth_n[j0] = ldepth[k];
+        lchild_n[j0] = lchild[k];
+    } else {
+        const uint32_t s = iidx[k];
+        const uint32_t id = I_old + s;
+        istart[id] = lstart[k];
+        icell[id] = lcell[k];
+        idepth[id] = ldepth[k];
+        uint32_t run = lstart[k];
+        for (uint32_t c = 0; c < 8; ++c) {
+            const uint32_t j = j0 + c;
+            lstart_n[j] = run;
+            run += Send[(size_t)s * 8 + c] - Sbeg[(size_t)s * 8 + c];
+            lcell_n[j] = lcell[k];
+            lparent_n[j] = (int32_t)id;
+            lpath_n[j] = (lpath[k] << 3) | (uint64_t)c;
+            ldepth_n[j] = (uint8_t)(ldepth[k] + 1);
+            lchild_n[j] = (uint8_t)c;
+        }
+    }
+    if (k == L - 1) lstart_n[L_new] = A;
+}
+
+// =============================================================================================
+// K5: leaf enumeration order (reference `_cached_leaves` order) and leaf geometry
+// =============================================================================================
+__global__ void internal_keys_kernel(uint32_t I, const uint32_t* __restrict__ istart, const uint8_t* __restrict__ idepth,
+                                     uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= I) return;
+    keys[i] = ((uint64_t)istart[i] << 8) | (uint64_t)idepth[i];
+    vals[i] = i;
+}
+
+__global__ void internal_rank_kernel(uint32_t I, const uint32_t* __restrict__ sorted_ids, const uint8_t* __restrict__ idepth,
+                                     const uint32_t* __restrict__ icell, uint32_t* __restrict__ irank,
+                                     uint32_t* __restrict__ cell_ifirst) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= I) return;
+    uint32_t id = sorted_ids[j];
+    irank[id] = j;
+    if (idepth[id] == 0) cell_ifirst[icell[id]] = j;
+}
+
+__global__ void leaf_keys_kernel(uint32_t L, const uint32_t* __restrict__ lcell, const int32_t* __restrict__ lparent,
+                                 const uint8_t* __restrict__ lchild, const uint32_t* __restrict__ irank,
+                                 const uint32_t* __restrict__ cell_ifirst, uint64_t* __restrict__ keys,
+                                 uint32_t* __restrict__ vals) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= L) return;
+    uint32_t c = lcell[k];
+    uint64_t low = 0;
+    if (lparent[k] >= 0) low = ((uint64_t)(irank[lparent[k]] - cell_ifirst[c]) << 3) | (uint64_t)lchild[k];
+    keys[k] = ((uint64_t)c << 32) | low;
+    vals[k] = k;
+}
+
+__global__ void leaf_geometry_kernel(uint32_t L, const uint32_t* __restrict__ leaf_by_cache,
+                                     const uint32_t* __restrict__ lcell, const uint64_t* __restrict__ lpath,
+                                     const uint8_t* __restrict__ ldepth, const uint64_t* __restrict__ cell_key,
+                                     KeyParams kp, uint32_t* __restrict__ cache_rank, double* __restrict__ corner,
+                                     double* __restrict__ edge, uint32_t* __restrict__ cell_leaf_begin) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= L) return;
+    const uint32_t k = leaf_by_cache[j];
+    cache_rank[k] = j;
+    const uint32_t c = lcell[k];
+    if (j == 0 || lcell[leaf_by_cache[j - 1]] != c) cell_leaf_begin[c] = j;
+    long long q[3] = {0, 0, 0};
+    if (!kp.single_cell) unpack_cell(kp, cell_key[c], q);
+    double co[3];
+    for (int a = 0; a < 3; ++a) co[a] = cell_corner_coord(q[a], kp.corner[a], kp.edge, kp.single_cell);
+    double e = kp.edge;
+    const int depth = ldepth[k];
+    const uint64_t path = lpath[k];
+    for (int d = 0; d < depth; ++d) {
+        const double h = e * 0.5;  // octree.py:181
+        const uint32_t dig = (uint32_t)(path >> (3 * (depth - 1 - d))) & 7u;
+        if (dig & 4u) co[0] = co[0] + h;  // octree.py:186
+        if (dig & 2u) co[1] = co[1] + h;
+        if (dig & 1u) co[2] = co[2] + h;
+        e = h;
+    }
+    corner[(size_t)j * 3 + 0] = co[0];
+    corner[(size_t)j * 3 + 1] = co[1];
+    corner[(size_t)j * 3 + 2] = co[2];
+    edge[j] = e;
+}
+
+// =============================================================================================
+// (pose, leaf) blocks
+// =============================================================================================
+__global__ void block_heads_kernel(const uint32_t* __restrict__ leaf_of, const uint32_t* __restrict__ perm,
+                                   const uint32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_pose, int n_seg,
+                                   uint32_t n, uint32_t* __restrict__ flags, int32_t* __restrict__ pose_of_pos) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t p = seg_pose[seg_of_rank(seg_start, n_seg, perm[i])];
+    pose_of_pos[i] = p;
+    bool head = (i == 0);
+    if (!head) {
+        int32_t pp = seg_pose[seg_of_rank(seg_start, n_seg, perm[i - 1])];
+        head = (leaf_of[i] != leaf_of[i - 1]) || (pp != p);
+    }
+    flags[i] = head;
+}
+
+__global__ void block_emit_kernel(const uint32_t* __restrict__ leaf_of, const int32_t* __restrict__ pose_of_pos,
+                                  const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan_ex, uint32_t n,
+                                  uint32_t* __restrict__ blk_of_pos, uint32_t* __restrict__ blk_start,
+                                  uint32_t* __restrict__ blk_leaf, int32_t* __restrict__ blk_pose) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t b = scan_ex[i] + flags[i] - 1u;
+    blk_of_pos[i] = b;
+    if (flags[i]) {
+        blk_start[b] = i;
+        blk_leaf[b] = leaf_of[i];
+        blk_pose[b] = pose_of_pos[i];
+    }
+}
+
+__global__ void block_max_kernel(const uint32_t* __restrict__ blk_start, uint32_t nb, uint32_t* __restrict__ out_max) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t v = (b < nb) ? blk_start[b + 1] - blk_start[b] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        uint32_t t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    if ((threadIdx.x & 31) == 0 && v) atomicMax(out_max, v);
+}
+
+__global__ void block_keep_kernel(uint32_t nb, const uint32_t* __restrict__ blk_start, const int32_t* __restrict__ blk_pose,
+                                  const uint8_t* __restrict__ listed, const uint8_t* __restrict__ table,
+                                  long long table_len, uint8_t* __restrict__ keep_blk) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    uint8_t keep = 1;
+    if (!listed || listed[blk_pose[b]]) {
+        long long sz = (long long)(blk_start[b + 1] - blk_start[b]);
+        if (sz > table_len - 1) sz = table_len - 1;
+        keep = table[sz];
+    }
+    keep_blk[b] = keep;
+}
+
+__global__ void pos_keep_from_block_kernel(uint32_t n, const uint32_t* __restrict__ blk_of_pos,
+                                           const uint8_t* __restrict__ keep_blk, uint8_t* __restrict__ keep_pos) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keep_pos[i] = keep_blk[blk_of_pos[i]];
+}
+
+}  // namespace ol
+
+#include "forest_host.inl"
+#include "forest_host2.inl"

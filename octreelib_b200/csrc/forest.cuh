@@ -1,0 +1,136 @@
+// Forest: the device-resident state behind one Grid (many cells x many poses) or one
+// OctreeManager / Octree (a single cell).  See DESIGN.md for the data layout.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+#include "pointkey.cuh"
+
+namespace ol {
+
+struct Forest {
+    Ctx ctx;
+    ol_forest_config cfg{};
+    int max_depth = OL_MAX_DEPTH;
+
+    // ---- raw input, indexed by the global point rank r (insertion order) -----------------------
+    DevBuf<double> P64;          // [cap][3]
+    size_t cap = 0, N = 0;
+    DevBuf<uint8_t> alive_r;     // [cap] 1 = point still stored (filter / RANSAC masks clear it)
+    bool any_dead = false;
+    bool base_dirty = false;     // base order still contains dead points
+    std::vector<uint32_t> seg_start;  // host: first rank of every segment (+ sentinel N)
+    std::vector<int32_t> seg_pose;    // host: pose index of every segment
+    std::vector<int64_t> seg_first;   // host: index of the segment's first point inside its pose's cloud
+    bool segs_pose_monotone = true;
+    int n_poses = 0;
+    DevBuf<uint32_t> d_seg_start;
+    DevBuf<int32_t> d_seg_pose;
+    DevBuf<int64_t> d_seg_first;
+    DevBuf<long long> d_bbox;    // [6] ordered-int min xyz, max xyz
+    DevBuf<uint32_t> d_err;      // [1]
+    void* pinned = nullptr;      // small pinned scratch for read-backs (256 B)
+
+    // ---- base structure: points grouped by cell, (pose, input index) order inside a cell --------
+    bool built = false;
+    KeyParams kp{};
+    int key_bits = 0;
+    uint32_t A0 = 0;             // alive points in the base order
+    DevBuf<uint32_t> perm0;      // [A0] base position -> r
+    DevBuf<uint64_t> mort0;      // [A0] Morton code of the point (bit 63: out-of-node somewhere)
+    DevBuf<uint32_t> cellidx0;   // [A0] base position -> cell index
+    uint32_t C = 0;
+    DevBuf<uint64_t> cell_key;   // [C] packed cell key (without pose bits)
+    DevBuf<uint32_t> cell_start0;// [C+1]
+    uint32_t CP = 0;
+    DevBuf<uint32_t> cp_cell;    // [CP]
+    DevBuf<int32_t> cp_pose;     // [CP]
+    DevBuf<int32_t> cell_first_pose;  // [C]
+
+    // ---- current tree shape and point order -----------------------------------------------------
+    bool shaped = false;         // current arrays valid
+    uint32_t A = 0;
+    DevBuf<uint32_t> perm;       // [A] position -> r ; order = (cell, leaf DFS, pose, input index)
+    DevBuf<uint64_t> mort;       // [A]
+    DevBuf<uint32_t> leaf_of;    // [A] position -> leaf (DFS index)
+    uint32_t L = 0;
+    DevBuf<uint32_t> lstart;     // [L+1]
+    DevBuf<uint32_t> lcell;      // [L]
+    DevBuf<int32_t> lparent;     // [L] internal node id, -1 for an unsplit cell root
+    DevBuf<uint64_t> lpath;      // [L] Morton digits from the root (3 bits per level)
+    DevBuf<uint8_t> ldepth;      // [L]
+    DevBuf<uint8_t> lchild;      // [L]
+    uint32_t I = 0;
+    DevBuf<uint32_t> istart;     // [I] first position of the internal node's range
+    DevBuf<uint32_t> icell;      // [I]
+    DevBuf<uint8_t> idepth;      // [I]
+    int depth_reached = 0;
+
+    // ---- derived tables (rebuilt lazily after the shape or the point set changes) ---------------
+    bool order_valid = false;    // leaf enumeration order + geometry
+    DevBuf<uint32_t> cache_rank; // [L] DFS leaf -> position in the reference's leaf order
+    DevBuf<uint32_t> leaf_by_cache;  // [L] inverse
+    DevBuf<double> leaf_corner;  // [L][3] in cache order
+    DevBuf<double> leaf_edge;    // [L]   in cache order
+    DevBuf<uint32_t> cell_leaf_begin;  // [C+1] in cache order
+
+    bool blocks_valid = false;
+    uint32_t NB = 0;
+    DevBuf<uint32_t> blk_start;  // [NB+1] position of the block's first point
+    DevBuf<uint32_t> blk_leaf;   // [NB] DFS leaf index
+    DevBuf<int32_t> blk_pose;    // [NB]
+    DevBuf<uint32_t> blk_of_pos; // [A] position -> block
+    uint32_t max_block = 0;
+
+    // ---- RANSAC results of the last ol_forest_ransac call ----------------------------------------
+    bool ransac_valid = false;   // `mask` is aligned with the current point order (not applied yet)
+    DevBuf<uint8_t> mask;        // [A at the time of the call] inlier mask per position
+    uint32_t mask_n = 0;
+    uint32_t res_n = 0;          // snapshot of the block table in reference order, with the planes
+    DevBuf<int32_t> res_pose, res_leaf, res_size, res_best, res_count;  // [res_n]
+    DevBuf<float> res_plane;     // [res_n][4]
+    bool sample_oob_seen = false;
+
+    explicit Forest(const ol_forest_config& c);
+    ~Forest();
+
+    // pipeline stages
+    int insert(const double* xyz, int64_t n, bool on_device, const int64_t* seg_sizes, const int32_t* seg_pose_in,
+               const int64_t* seg_first_in, int n_segments, int n_poses_total);
+    void build();            // K1-K3: keygen, sort, cells
+    void compact_base();     // drop dead points from the base order
+    void reset_shape();      // current := base (every cell one leaf)
+    void subdivide(int64_t max_points, const uint8_t* table, int64_t table_len, int beyond, const int32_t* poses,
+                   int n_poses_listed);  // K4
+    void ensure_shape();
+    void ensure_order();     // K5: leaf enumeration order + geometry
+    void ensure_blocks();    // (pose, leaf) runs
+    void filter(const uint8_t* keep_table, int64_t table_len, const int32_t* poses, int n_poses_listed);
+    void apply_keep(const uint8_t* keep_pos);  // K7: drop positions with keep == 0
+    void compute_ref_order(const int32_t* pose_rank_host, DevBuf<uint32_t>& ref_order, DevBuf<int32_t>& d_pose_rank);
+    void ransac(const double* table_host, int H, int K, double threshold, const int32_t* pose_rank, int ppb, bool apply,
+                uint32_t flags);
+    void apply_mask();
+    void apply_pose_mask(const int32_t* pose_rank, int pose, const uint8_t* mask_host, int64_t n);
+    void pose_counts(int64_t* out_host);
+    void stats(ol_forest_stats* s);
+    void export_cells(int64_t* q, double* corner, int32_t* first_pose, int64_t* n_nodes, int64_t* leaf_begin);
+    void export_cell_poses(int32_t* cell, int32_t* pose);
+    void export_leaves(double* corner, double* edge, int32_t* cell, int32_t* depth);
+    void export_blocks(const int32_t* pose_rank, int32_t* pose, int32_t* leaf, int32_t* size);
+    void export_ransac(int32_t* pose, int32_t* leaf, int32_t* size, float* plane, int32_t* best, int32_t* count);
+    int64_t export_points(const int32_t* pose_rank, int pose, int order, double* xyz, int64_t* idx, int32_t* cell,
+                          uint8_t* mask_out);
+    void check_device_errors();
+    void upload_segments();
+    uint32_t read_u32(const uint32_t* dptr);
+    unsigned long long read_u64(const unsigned long long* dptr);
+};
+
+// ransac.cu
+void launch_ransac(Ctx& c, const double* points, int64_t n_points, const uint32_t* blk_phys_start,
+                   const int32_t* blk_size, const long long* blk_ref_start, const uint32_t* work_list, uint32_t n_work,
+                   uint32_t max_block, const double* table, int H, int K, double threshold, uint8_t* mask, float* plane,
+                   int32_t* best, int32_t* best_count, uint32_t flags);
+
+}  // namespace ol

@@ -1,0 +1,570 @@
+// Host-side orchestration of the Forest (included at the end of forest.cu).
+namespace ol {
+
+static inline unsigned nblk(size_t n, int t = 256) { return n ? (unsigned)((n + t - 1) / t) : 1u; }
+
+Forest::Forest(const ol_forest_config& c) : cfg(c) {
+    OL_REQUIRE(c.voxel_edge_length > 0 && std::isfinite(c.voxel_edge_length), OL_ERR_INVALID,
+               "voxel_edge_length must be a positive finite number");
+    max_depth = c.max_depth <= 0 ? OL_MAX_DEPTH : c.max_depth;
+    OL_REQUIRE(max_depth <= OL_MAX_DEPTH, OL_ERR_INVALID, "max_depth must be <= 21");
+    OL_CUDA(cudaSetDevice(c.device));
+    ctx.stream = (cudaStream_t)c.stream;
+    ctx.alloc_fn = c.alloc;
+    ctx.free_fn = c.free;
+    ctx.alloc_user = c.alloc_user;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
+    ctx.num_sms = sms;
+    d_bbox.reset(ctx, 6);
+    d_err.reset(ctx, 1);
+    d_err.zero();
+    ctx.d_err = d_err.get();
+    long long init[6] = {LLONG_MAX, LLONG_MAX, LLONG_MAX, LLONG_MIN, LLONG_MIN, LLONG_MIN};
+    OL_CUDA(cudaMemcpyAsync(d_bbox.get(), init, sizeof(init), cudaMemcpyHostToDevice, ctx.stream));
+    OL_CUDA(cudaMallocHost(&pinned, 256));
+    ctx.sync();
+    seg_start.push_back(0);
+}
+
+Forest::~Forest() {
+    cudaStreamSynchronize(ctx.stream);
+    if (pinned) cudaFreeHost(pinned);
+}
+
+uint32_t Forest::read_u32(const uint32_t* dptr) {
+    OL_CUDA(cudaMemcpyAsync(pinned, dptr, 4, cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+    return *(uint32_t*)pinned;
+}
+unsigned long long Forest::read_u64(const unsigned long long* dptr) {
+    OL_CUDA(cudaMemcpyAsync(pinned, dptr, 8, cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+    return *(unsigned long long*)pinned;
+}
+
+void Forest::check_device_errors() {
+    uint32_t e = read_u32(d_err.get());
+    if (!e) return;
+    d_err.zero();
+    if (e & DEVERR_NONFINITE) throw Error{OL_ERR_NONFINITE, "point cloud contains NaN or infinite coordinates"};
+    if (e & DEVERR_CELL_RANGE) throw Error{OL_ERR_RANGE, "cell coordinates out of the representable range"};
+    if (e & DEVERR_OUT_OF_NODE)
+        throw Error{OL_ERR_OUT_OF_NODE,
+                    "a point lies outside the octree node that is being subdivided (the reference raises IndexError "
+                    "or mis-routes it, octree/octree.py:94-98)"};
+    if (e & DEVERR_DEPTH_CAP)
+        throw Error{OL_ERR_DEPTH_CAP, "subdivision criterion still true at the maximum octree depth " +
+                                          std::to_string(max_depth) + " (the reference would keep recursing)"};
+}
+
+void Forest::upload_segments() {
+    size_t S = seg_pose.size();
+    d_seg_start.reset(ctx, S + 1);
+    d_seg_pose.reset(ctx, S ? S : 1);
+    d_seg_first.reset(ctx, S ? S : 1);
+    h2d(ctx, d_seg_start.get(), seg_start.data(), S + 1);
+    h2d(ctx, d_seg_pose.get(), seg_pose.data(), S);
+    h2d(ctx, d_seg_first.get(), seg_first.data(), S);
+    ctx.sync();  // host vectors may be modified afterwards
+}
+
+// ---------------------------------------------------------------------------------------------
+// Grid.insert_points (grid.py:58-109): upload + bounding box only; the grouping is deferred to
+// build() so that all poses are keyed and sorted in one pass.
+// ---------------------------------------------------------------------------------------------
+int Forest::insert(const double* xyz, int64_t n, bool on_device, const int64_t* seg_sizes, const int32_t* seg_pose_in,
+                   const int64_t* seg_first_in, int n_segments, int n_poses_total) {
+    OL_REQUIRE(n >= 0, OL_ERR_INVALID, "negative point count");
+    OL_REQUIRE(N + (size_t)n < (1ull << 31), OL_ERR_INVALID, "more than 2^31 - 1 points per forest are not supported");
+    OL_REQUIRE(!(shaped && I > 0), OL_ERR_STATE,
+               "inserting a pose after the grid was subdivided (scheme replay, octree_manager.py:171) is not "
+               "implemented yet");
+    if (N + (size_t)n > cap) {
+        size_t ncap = std::max<size_t>(N + (size_t)n, cap + cap / 2 + 1024);
+        DevBuf<double> np(ctx, ncap * 3);
+        DevBuf<uint8_t> na(ctx, ncap);
+        d2d(ctx, np.get(), P64.get(), N * 3);
+        d2d(ctx, na.get(), alive_r.get(), N);
+        P64.swap(np);
+        alive_r.swap(na);
+        cap = ncap;
+    }
+    if (n > 0) {
+        OL_CUDA(cudaMemcpyAsync(P64.get() + N * 3, xyz, (size_t)n * 24, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                ctx.stream));
+        OL_CUDA(cudaMemsetAsync(alive_r.get() + N, 1, (size_t)n, ctx.stream));
+        unsigned g = std::min<unsigned>(nblk((size_t)n), (unsigned)ctx.num_sms * 8);
+        bbox_kernel<<<g, 256, 0, ctx.stream>>>(P64.get() + N * 3, (size_t)n, d_bbox.get(), d_err.get());
+        OL_CHECK_LAUNCH();
+    }
+    int pose_index;
+    if (n_segments <= 0) {
+        pose_index = n_poses;
+        seg_pose.push_back(pose_index);
+        seg_first.push_back(0);
+        seg_start.back() = (uint32_t)N;
+        seg_start.push_back((uint32_t)(N + n));
+        n_poses += 1;
+    } else {
+        pose_index = -1;
+        size_t r = N;
+        int64_t tot = 0;
+        for (int s = 0; s < n_segments; ++s) {
+            OL_REQUIRE(seg_sizes[s] >= 0 && seg_pose_in[s] >= 0 && seg_pose_in[s] < n_poses_total, OL_ERR_INVALID,
+                       "bad segment description");
+            if (!seg_pose.empty() && seg_pose_in[s] < seg_pose.back()) segs_pose_monotone = false;
+            seg_pose.push_back(seg_pose_in[s]);
+            seg_first.push_back(seg_first_in ? seg_first_in[s] : 0);
+            seg_start.back() = (uint32_t)r;
+            r += (size_t)seg_sizes[s];
+            seg_start.push_back((uint32_t)r);
+            tot += seg_sizes[s];
+        }
+        OL_REQUIRE(tot == n, OL_ERR_INVALID, "segment sizes do not add up to n");
+        n_poses = std::max(n_poses, n_poses_total);
+    }
+    N += (size_t)n;
+    built = false;
+    shaped = false;
+    order_valid = blocks_valid = ransac_valid = false;
+    if (!on_device) ctx.sync();  // the caller may reuse / free the host buffer
+    return pose_index;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1-K3: keys, sort, cells, (cell, pose) table
+// ---------------------------------------------------------------------------------------------
+void Forest::build() {
+    if (built) return;
+    check_device_errors();
+    upload_segments();
+    const int S = (int)seg_pose.size();
+    kp = KeyParams{};
+    kp.edge = cfg.voxel_edge_length;
+    for (int a = 0; a < 3; ++a) kp.corner[a] = cfg.corner[a];
+    kp.single_cell = cfg.single_cell;
+    kp.depth = max_depth;
+    kp.pose_bits = segs_pose_monotone ? 0 : bit_length_u64((uint64_t)std::max(n_poses - 1, 0));
+    int bits[3] = {0, 0, 0};
+    if (!cfg.single_cell && N > 0) {
+        long long hb[6];
+        OL_CUDA(cudaMemcpyAsync(hb, d_bbox.get(), sizeof(hb), cudaMemcpyDeviceToHost, ctx.stream));
+        ctx.sync();
+        for (int a = 0; a < 3; ++a) {
+            double lo = cell_coord(ordered_to_double(hb[a]), kp.corner[a], kp.edge);
+            double hi = cell_coord(ordered_to_double(hb[3 + a]), kp.corner[a], kp.edge);
+            OL_REQUIRE(std::fabs(lo) < 4503599627370496.0 && std::fabs(hi) < 4503599627370496.0, OL_ERR_RANGE,
+                       "cell coordinates exceed 2^52");
+            kp.qmin[a] = (long long)lo;
+            bits[a] = bit_length_u64((uint64_t)((long long)hi - (long long)lo));
+        }
+    }
+    key_bits = bits[0] + bits[1] + bits[2] + kp.pose_bits;
+    OL_REQUIRE(key_bits <= 64, OL_ERR_RANGE,
+               "the grid spans too many cells: packed cell key needs " + std::to_string(key_bits) + " bits (max 64)");
+    kp.shift[2] = kp.pose_bits;
+    kp.shift[1] = kp.shift[2] + bits[2];
+    kp.shift[0] = kp.shift[1] + bits[1];
+
+    const uint32_t n = (uint32_t)N;
+    C = 0;
+    CP = 0;
+    A0 = n;
+    if (n == 0) {
+        perm0.reset(ctx, 0);
+        mort0.reset(ctx, 0);
+        cellidx0.reset(ctx, 0);
+        cell_key.reset(ctx, 0);
+        cell_start0.reset(ctx, 1);
+        cell_start0.zero();
+        cp_cell.reset(ctx, 0);
+        cp_pose.reset(ctx, 0);
+        cell_first_pose.reset(ctx, 0);
+        built = true;
+        base_dirty = false;
+        return;
+    }
+    DevBuf<uint64_t> keys0(ctx, n), keys1(ctx, n), mort_r(ctx, n);
+    DevBuf<uint32_t> vals0(ctx, n), vals1(ctx, n);
+    keygen_kernel<<<nblk(n), 256, 0, ctx.stream>>>(P64.get(), n, kp, d_seg_start.get(), d_seg_pose.get(), S, keys0.get(),
+                                                   mort_r.get(), d_err.get());
+    OL_CHECK_LAUNCH();
+    iota_kernel<<<nblk(n), 256, 0, ctx.stream>>>(vals0.get(), n, 0);
+    OL_CHECK_LAUNCH();
+    int which = radix_sort_pairs<uint64_t>(ctx, keys0.get(), keys1.get(), vals0.get(), vals1.get(), n, 0, key_bits);
+    if (which) {
+        keys0.swap(keys1);
+        vals0.swap(vals1);
+    }
+    keys1.release();
+    vals1.release();
+    perm0.swap(vals0);
+    mort0.reset(ctx, n);
+    gather_kernel<uint64_t><<<nblk(n), 256, 0, ctx.stream>>>(mort0.get(), mort_r.get(), perm0.get(), n);
+    OL_CHECK_LAUNCH();
+    mort_r.release();
+
+    // cells
+    DevBuf<uint32_t> flags(ctx, n), scan(ctx, n);
+    DevBuf<unsigned long long> d_total(ctx, 1);
+    cell_heads_kernel<<<nblk(n), 256, 0, ctx.stream>>>(keys0.get(), n, kp.pose_bits, flags.get());
+    OL_CHECK_LAUNCH();
+    exclusive_scan_u32(ctx, flags.get(), scan.get(), n, d_total.get());
+    C = (uint32_t)read_u64(d_total.get());
+    cellidx0.reset(ctx, n);
+    cell_key.reset(ctx, C);
+    cell_start0.reset(ctx, (size_t)C + 1);
+    cell_emit_kernel<<<nblk(n), 256, 0, ctx.stream>>>(keys0.get(), flags.get(), scan.get(), n, kp.pose_bits, cellidx0.get(),
+                                                      cell_key.get(), cell_start0.get());
+    OL_CHECK_LAUNCH();
+    OL_CUDA(cudaMemcpyAsync(cell_start0.get() + C, &n, 4, cudaMemcpyHostToDevice, ctx.stream));
+    keys0.release();
+
+    // (cell, pose) pairs that own an octree (octree_manager.py:166-169)
+    DevBuf<int32_t> pose_of_pos(ctx, n);
+    cp_heads_kernel<<<nblk(n), 256, 0, ctx.stream>>>(cellidx0.get(), perm0.get(), d_seg_start.get(), d_seg_pose.get(), S, n,
+                                                     flags.get(), pose_of_pos.get());
+    OL_CHECK_LAUNCH();
+    exclusive_scan_u32(ctx, flags.get(), scan.get(), n, d_total.get());
+    CP = (uint32_t)read_u64(d_total.get());
+    cp_cell.reset(ctx, CP);
+    cp_pose.reset(ctx, CP);
+    cell_first_pose.reset(ctx, C);
+    cp_emit_kernel<<<nblk(n), 256, 0, ctx.stream>>>(cellidx0.get(), pose_of_pos.get(), flags.get(), scan.get(), n,
+                                                    cp_cell.get(), cp_pose.get(), cell_first_pose.get());
+    OL_CHECK_LAUNCH();
+    check_device_errors();
+    built = true;
+    base_dirty = any_dead;  // points removed before a rebuild are dropped from the base order lazily
+}
+
+// drop dead points from the base order (cells keep their index even when they become empty)
+void Forest::compact_base() {
+    if (!base_dirty) return;
+    const uint32_t n = A0;
+    if (n) {
+        DevBuf<uint32_t> flags(ctx, n), scan(ctx, n);
+        DevBuf<unsigned long long> d_total(ctx, 1);
+        alive_flags_kernel<<<nblk(n), 256, 0, ctx.stream>>>(alive_r.get(), perm0.get(), n, flags.get());
+        OL_CHECK_LAUNCH();
+        exclusive_scan_u32(ctx, flags.get(), scan.get(), n, d_total.get());
+        uint32_t total = (uint32_t)read_u64(d_total.get());
+        DevBuf<uint32_t> p2(ctx, total), c2(ctx, total), s2(ctx, (size_t)C + 1);
+        DevBuf<uint64_t> m2(ctx, total);
+        compact_pos_kernel<<<nblk(n), 256, 0, ctx.stream>>>(flags.get(), scan.get(), n, perm0.get(), mort0.get(),
+                                                            cellidx0.get(), p2.get(), m2.get(), c2.get(), nullptr);
+        OL_CHECK_LAUNCH();
+        remap_starts_kernel<<<nblk((size_t)C + 1), 256, 0, ctx.stream>>>(cell_start0.get(), scan.get(), C, n, total, s2.get());
+        OL_CHECK_LAUNCH();
+        perm0.swap(p2);
+        mort0.swap(m2);
+        cellidx0.swap(c2);
+        cell_start0.swap(s2);
+        A0 = total;
+    }
+    base_dirty = false;
+}
+
+// current shape := one leaf per cell
+void Forest::reset_shape() {
+    build();
+    compact_base();
+    A = A0;
+    L = C;
+    I = 0;
+    depth_reached = 0;
+    perm.reset(ctx, A);
+    mort.reset(ctx, A);
+    leaf_of.reset(ctx, A);
+    d2d(ctx, perm.get(), perm0.get(), A);
+    d2d(ctx, mort.get(), mort0.get(), A);
+    d2d(ctx, leaf_of.get(), cellidx0.get(), A);
+    lstart.reset(ctx, (size_t)L + 1);
+    d2d(ctx, lstart.get(), cell_start0.get(), (size_t)L + 1);
+    lcell.reset(ctx, L);
+    lparent.reset(ctx, L);
+    lpath.reset(ctx, L);
+    ldepth.reset(ctx, L);
+    lchild.reset(ctx, L);
+    if (L) {
+        iota_kernel<<<nblk(L), 256, 0, ctx.stream>>>(lcell.get(), L, 0);
+        OL_CHECK_LAUNCH();
+        fill_kernel<int32_t><<<nblk(L), 256, 0, ctx.stream>>>(lparent.get(), L, -1);
+        OL_CHECK_LAUNCH();
+    }
+    lpath.zero();
+    ldepth.zero();
+    lchild.zero();
+    istart.reset(ctx, 0);
+    icell.reset(ctx, 0);
+    idepth.reset(ctx, 0);
+    shaped = true;
+    order_valid = blocks_valid = ransac_valid = false;
+}
+
+void Forest::ensure_shape() {
+    if (!shaped) reset_shape();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: Grid.subdivide (grid.py:244-258) -> OctreeManager.subdivide (octree_manager.py:36-66).
+// Every call rebuilds the shape from the cell roots, as the reference's fresh scheme octree does.
+// ---------------------------------------------------------------------------------------------
+void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t table_len, int beyond, const int32_t* poses,
+                       int n_listed) {
+    reset_shape();
+    if (L == 0 || A == 0) return;
+    const int S = (int)seg_pose.size();
+    DevBuf<uint8_t> listed, table;
+    if (n_listed > 0) {
+        std::vector<uint8_t> h(std::max(n_poses, 1), 0);
+        for (int i = 0; i < n_listed; ++i) {
+            OL_REQUIRE(poses[i] >= 0 && poses[i] < n_poses, OL_ERR_POSE, "unknown pose index " + std::to_string(poses[i]));
+            h[poses[i]] = 1;
+        }
+        listed.reset(ctx, h.size());
+        h2d(ctx, listed.get(), h.data(), h.size());
+        ctx.sync();
+    }
+    if (table_host) {
+        OL_REQUIRE(table_len > 0, OL_ERR_INVALID, "empty split table");
+        table.reset(ctx, (size_t)table_len);
+        h2d(ctx, table.get(), table_host, (size_t)table_len);
+        ctx.sync();
+    }
+    DevBuf<unsigned long long> d_tot(ctx, 2);
+    const uint32_t tiles = (A + PART_TILE - 1) / PART_TILE;
+    DevBuf<uint32_t> tile_hist(ctx, (size_t)8 * tiles), rank(ctx, A);
+    DevBuf<uint32_t> perm_b(ctx, A), leaf_b(ctx, A);
+    DevBuf<uint64_t> mort_b(ctx, A);
+    for (int level = 0;; ++level) {
+        DevBuf<uint32_t> splitf(ctx, L), expand(ctx, L), newidx(ctx, L), iidx(ctx, L), wcount;
+        if (n_listed > 0) {
+            wcount.reset(ctx, L);
+            wcount.zero();
+            weighted_count_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), perm.get(), ldepth.get(), level,
+                                                                   d_seg_start.get(), d_seg_pose.get(), S, listed.get(), A,
+                                                                   wcount.get());
+            OL_CHECK_LAUNCH();
+        }
+        decide_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, lstart.get(), ldepth.get(), level, wcount.get(), max_points,
+                                                       table.get(), table_len, beyond, max_depth, splitf.get(),
+                                                       expand.get(), d_err.get());
+        OL_CHECK_LAUNCH();
+        exclusive_scan_u32(ctx, expand.get(), newidx.get(), L, d_tot.get());
+        exclusive_scan_u32(ctx, splitf.get(), iidx.get(), L, d_tot.get() + 1);
+        unsigned long long tot[2];
+        OL_CUDA(cudaMemcpyAsync(pinned, d_tot.get(), 16, cudaMemcpyDeviceToHost, ctx.stream));
+        ctx.sync();
+        memcpy(tot, pinned, 16);
+        const uint32_t L_new = (uint32_t)tot[0], n_split = (uint32_t)tot[1];
+        if (n_split == 0) break;
+        OL_REQUIRE((unsigned long long)I + n_split < (1ull << 29), OL_ERR_RANGE, "too many internal nodes");
+        depth_reached = level + 1;
+        const int shift = 3 * (kp.depth - 1 - level);
+        DevBuf<uint32_t> Sbeg(ctx, (size_t)n_split * 8), Send(ctx, (size_t)n_split * 8);
+        Sbeg.zero();
+        Send.zero();
+        part_hist_kernel<<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), mort.get(), splitf.get(), A, tiles, shift,
+                                                                 tile_hist.get());
+        OL_CHECK_LAUNCH();
+        exclusive_scan_u32(ctx, tile_hist.get(), tile_hist.get(), (size_t)8 * tiles, nullptr);
+        part_rank_kernel<<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), mort.get(), splitf.get(), iidx.get(),
+                                                                 lstart.get(), tile_hist.get(), A, tiles, shift, rank.get(),
+                                                                 Sbeg.get(), Send.get());
+        OL_CHECK_LAUNCH();
+        part_scatter_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), mort.get(), perm.get(), splitf.get(), iidx.get(),
+                                                             newidx.get(), lstart.get(), rank.get(), Sbeg.get(), Send.get(), A,
+                                                             shift, level, leaf_b.get(), mort_b.get(), perm_b.get(), P64.get(),
+                                                             lcell.get(), cell_key.get(), kp, d_err.get());
+        OL_CHECK_LAUNCH();
+        // new leaf / internal tables
+        DevBuf<uint32_t> lstart_n(ctx, (size_t)L_new + 1), lcell_n(ctx, L_new), istart_n(ctx, (size_t)I + n_split),
+            icell_n(ctx, (size_t)I + n_split);
+        DevBuf<int32_t> lparent_n(ctx, L_new);
+        DevBuf<uint64_t> lpath_n(ctx, L_new);
+        DevBuf<uint8_t> ldepth_n(ctx, L_new), lchild_n(ctx, L_new), idepth_n(ctx, (size_t)I + n_split);
+        d2d(ctx, istart_n.get(), istart.get(), I);
+        d2d(ctx, icell_n.get(), icell.get(), I);
+        d2d(ctx, idepth_n.get(), idepth.get(), I);
+        expand_leaves_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, A, I, splitf.get(), iidx.get(), newidx.get(), Sbeg.get(),
+                                                              Send.get(), lstart.get(), lcell.get(), lparent.get(), lpath.get(),
+                                                              ldepth.get(), lchild.get(), L_new, lstart_n.get(), lcell_n.get(),
+                                                              lparent_n.get(), lpath_n.get(), ldepth_n.get(), lchild_n.get(),
+                                                              istart_n.get(), icell_n.get(), idepth_n.get());
+        OL_CHECK_LAUNCH();
+        lstart.swap(lstart_n);
+        lcell.swap(lcell_n);
+        lparent.swap(lparent_n);
+        lpath.swap(lpath_n);
+        ldepth.swap(ldepth_n);
+        lchild.swap(lchild_n);
+        istart.swap(istart_n);
+        icell.swap(icell_n);
+        idepth.swap(idepth_n);
+        perm.swap(perm_b);
+        mort.swap(mort_b);
+        leaf_of.swap(leaf_b);
+        L = L_new;
+        I += n_split;
+    }
+    check_device_errors();
+    order_valid = blocks_valid = ransac_valid = false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: leaf enumeration order of the reference + leaf geometry
+//   order inside a cell = for every internal node in DFS pre-order, its leaf children by child id
+//   (octree_base.py:48-49 appends, octree.py:183-191 removes the parent and appends 8 children);
+//   an unsplit root is the cell's only leaf.  DFS pre-order of the internal nodes = ascending
+//   (range start, depth).
+// ---------------------------------------------------------------------------------------------
+void Forest::ensure_order() {
+    ensure_shape();
+    if (order_valid) return;
+    cache_rank.reset(ctx, L);
+    leaf_by_cache.reset(ctx, L);
+    leaf_corner.reset(ctx, (size_t)L * 3);
+    leaf_edge.reset(ctx, L);
+    cell_leaf_begin.reset(ctx, (size_t)C + 1);
+    if (L == 0) {
+        cell_leaf_begin.zero();
+        order_valid = true;
+        return;
+    }
+    DevBuf<uint32_t> irank(ctx, I), cell_ifirst(ctx, C);
+    cell_ifirst.zero();
+    if (I) {
+        DevBuf<uint64_t> k0(ctx, I), k1(ctx, I);
+        DevBuf<uint32_t> v0(ctx, I), v1(ctx, I);
+        internal_keys_kernel<<<nblk(I), 256, 0, ctx.stream>>>(I, istart.get(), idepth.get(), k0.get(), v0.get());
+        OL_CHECK_LAUNCH();
+        int w = radix_sort_pairs<uint64_t>(ctx, k0.get(), k1.get(), v0.get(), v1.get(), I, 0, 8 + bit_length_u64(A));
+        internal_rank_kernel<<<nblk(I), 256, 0, ctx.stream>>>(I, w ? v1.get() : v0.get(), idepth.get(), icell.get(), irank.get(),
+                                                              cell_ifirst.get());
+        OL_CHECK_LAUNCH();
+    }
+    {
+        DevBuf<uint64_t> k0(ctx, L), k1(ctx, L);
+        DevBuf<uint32_t> v0(ctx, L), v1(ctx, L);
+        leaf_keys_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, lcell.get(), lparent.get(), lchild.get(), irank.get(),
+                                                          cell_ifirst.get(), k0.get(), v0.get());
+        OL_CHECK_LAUNCH();
+        // low field: (#internal nodes of a cell) * 8 fits in 3 + bit_length(I) bits; cell index above bit 32
+        int low_bits = 3 + bit_length_u64(I);
+        int w = radix_sort_pairs<uint64_t>(ctx, k0.get(), k1.get(), v0.get(), v1.get(), L, 0, low_bits);
+        uint64_t* ka = w ? k1.get() : k0.get();
+        uint64_t* kb = w ? k0.get() : k1.get();
+        uint32_t* va = w ? v1.get() : v0.get();
+        uint32_t* vb = w ? v0.get() : v1.get();
+        int w2 = radix_sort_pairs<uint64_t>(ctx, ka, kb, va, vb, L, 32, 32 + bit_length_u64(C ? C - 1 : 0));
+        d2d(ctx, leaf_by_cache.get(), w2 ? vb : va, L);
+    }
+    leaf_geometry_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, leaf_by_cache.get(), lcell.get(), lpath.get(), ldepth.get(),
+                                                          cell_key.get(), kp, cache_rank.get(), leaf_corner.get(),
+                                                          leaf_edge.get(), cell_leaf_begin.get());
+    OL_CHECK_LAUNCH();
+    OL_CUDA(cudaMemcpyAsync(cell_leaf_begin.get() + C, &L, 4, cudaMemcpyHostToDevice, ctx.stream));
+    ctx.sync();
+    order_valid = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// non-empty (pose, leaf) blocks = maximal runs of equal (leaf, pose) in the current point order
+// ---------------------------------------------------------------------------------------------
+void Forest::ensure_blocks() {
+    ensure_shape();
+    if (blocks_valid) return;
+    const int S = (int)seg_pose.size();
+    NB = 0;
+    max_block = 0;
+    blk_of_pos.reset(ctx, A);
+    if (A == 0) {
+        blk_start.reset(ctx, 1);
+        blk_start.zero();
+        blk_leaf.reset(ctx, 0);
+        blk_pose.reset(ctx, 0);
+        blocks_valid = true;
+        return;
+    }
+    DevBuf<uint32_t> flags(ctx, A), scan(ctx, A);
+    DevBuf<int32_t> pose_of_pos(ctx, A);
+    DevBuf<unsigned long long> d_total(ctx, 1);
+    block_heads_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), perm.get(), d_seg_start.get(), d_seg_pose.get(), S, A,
+                                                        flags.get(), pose_of_pos.get());
+    OL_CHECK_LAUNCH();
+    exclusive_scan_u32(ctx, flags.get(), scan.get(), A, d_total.get());
+    NB = (uint32_t)read_u64(d_total.get());
+    blk_start.reset(ctx, (size_t)NB + 1);
+    blk_leaf.reset(ctx, NB);
+    blk_pose.reset(ctx, NB);
+    block_emit_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), pose_of_pos.get(), flags.get(), scan.get(), A,
+                                                       blk_of_pos.get(), blk_start.get(), blk_leaf.get(), blk_pose.get());
+    OL_CHECK_LAUNCH();
+    OL_CUDA(cudaMemcpyAsync(blk_start.get() + NB, &A, 4, cudaMemcpyHostToDevice, ctx.stream));
+    DevBuf<uint32_t> d_max(ctx, 1);
+    d_max.zero();
+    block_max_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(blk_start.get(), NB, d_max.get());
+    OL_CHECK_LAUNCH();
+    max_block = read_u32(d_max.get());
+    blocks_valid = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7: drop the positions whose keep flag is 0 (filter, RANSAC mask).  Tree shape unchanged.
+// ---------------------------------------------------------------------------------------------
+void Forest::apply_keep(const uint8_t* keep_pos) {
+    const uint32_t n = A;
+    if (n == 0) return;
+    DevBuf<uint32_t> flags(ctx, n), scan(ctx, n);
+    DevBuf<unsigned long long> d_total(ctx, 1);
+    keep_to_u32_kernel<<<nblk(n), 256, 0, ctx.stream>>>(keep_pos, n, flags.get());
+    OL_CHECK_LAUNCH();
+    exclusive_scan_u32(ctx, flags.get(), scan.get(), n, d_total.get());
+    const uint32_t total = (uint32_t)read_u64(d_total.get());
+    if (total == n) return;
+    DevBuf<uint32_t> p2(ctx, total), l2(ctx, total), s2(ctx, (size_t)L + 1);
+    DevBuf<uint64_t> m2(ctx, total);
+    compact_pos_kernel<<<nblk(n), 256, 0, ctx.stream>>>(flags.get(), scan.get(), n, perm.get(), mort.get(), leaf_of.get(),
+                                                        p2.get(), m2.get(), l2.get(), alive_r.get());
+    OL_CHECK_LAUNCH();
+    remap_starts_kernel<<<nblk((size_t)L + 1), 256, 0, ctx.stream>>>(lstart.get(), scan.get(), L, n, total, s2.get());
+    OL_CHECK_LAUNCH();
+    perm.swap(p2);
+    mort.swap(m2);
+    leaf_of.swap(l2);
+    lstart.swap(s2);
+    A = total;
+    any_dead = true;
+    base_dirty = true;
+    blocks_valid = false;
+    ransac_valid = false;
+}
+
+// Grid.filter (grid.py:260-267): per (pose, leaf) block, keep iff the folded criteria say so
+void Forest::filter(const uint8_t* keep_table_host, int64_t table_len, const int32_t* poses, int n_listed) {
+    OL_REQUIRE(table_len > 0, OL_ERR_INVALID, "empty keep table");
+    ensure_blocks();
+    if (NB == 0) return;
+    DevBuf<uint8_t> listed, table(ctx, (size_t)table_len), keep_blk(ctx, NB), keep_pos(ctx, A);
+    if (n_listed > 0) {
+        std::vector<uint8_t> h(std::max(n_poses, 1), 0);
+        for (int i = 0; i < n_listed; ++i) {
+            OL_REQUIRE(poses[i] >= 0 && poses[i] < n_poses, OL_ERR_POSE, "unknown pose index " + std::to_string(poses[i]));
+            h[poses[i]] = 1;
+        }
+        listed.reset(ctx, h.size());
+        h2d(ctx, listed.get(), h.data(), h.size());
+    }
+    h2d(ctx, table.get(), keep_table_host, (size_t)table_len);
+    ctx.sync();
+    block_keep_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_start.get(), blk_pose.get(), listed.get(), table.get(),
+                                                        table_len, keep_blk.get());
+    OL_CHECK_LAUNCH();
+    pos_keep_from_block_kernel<<<nblk(A), 256, 0, ctx.stream>>>(A, blk_of_pos.get(), keep_blk.get(), keep_pos.get());
+    OL_CHECK_LAUNCH();
+    apply_keep(keep_pos.get());
+}
+
+}  // namespace ol

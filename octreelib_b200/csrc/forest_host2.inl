@@ -1,0 +1,532 @@
+// Forest: RANSAC orchestration, counters and host exports (included at the end of forest.cu).
+namespace ol {
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void block_refkey_kernel(uint32_t nb, const int32_t* __restrict__ blk_pose, const uint32_t* __restrict__ blk_leaf,
+                                    const int32_t* __restrict__ pose_rank, const uint32_t* __restrict__ cache_rank,
+                                    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    keys[b] = ((uint64_t)(uint32_t)pose_rank[blk_pose[b]] << 32) | (uint64_t)cache_rank[blk_leaf[b]];
+    vals[b] = b;
+}
+
+__global__ void block_sizes_ref_kernel(uint32_t nb, const uint32_t* __restrict__ ref_order, const uint32_t* __restrict__ blk_start,
+                                       uint32_t* __restrict__ sizes_ref, uint32_t* __restrict__ refpos,
+                                       int32_t* __restrict__ blk_size) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nb) return;
+    uint32_t b = ref_order[j];
+    uint32_t sz = blk_start[b + 1] - blk_start[b];
+    sizes_ref[j] = sz;
+    refpos[b] = j;
+    blk_size[b] = (int32_t)sz;
+}
+
+// first block of every batch of `ppb` consecutive pose ranks -> batch_base
+__global__ void batch_base_kernel(uint32_t nb, const uint32_t* __restrict__ ref_order, const int32_t* __restrict__ blk_pose,
+                                  const int32_t* __restrict__ pose_rank, int ppb, const uint32_t* __restrict__ refstart,
+                                  uint32_t* __restrict__ batch_base) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nb) return;
+    int batch = pose_rank[blk_pose[ref_order[j]]] / ppb;
+    if (j == 0 || pose_rank[blk_pose[ref_order[j - 1]]] / ppb != batch) batch_base[batch] = refstart[j];
+}
+
+__global__ void block_refstart_kernel(uint32_t nb, const uint32_t* __restrict__ ref_order, const int32_t* __restrict__ blk_pose,
+                                      const int32_t* __restrict__ pose_rank, int ppb, const uint32_t* __restrict__ refstart,
+                                      const uint32_t* __restrict__ batch_base, long long* __restrict__ blk_ref_start) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nb) return;
+    uint32_t b = ref_order[j];
+    int batch = pose_rank[blk_pose[b]] / ppb;
+    blk_ref_start[b] = (long long)refstart[j] - (long long)batch_base[batch];
+}
+
+__global__ void work_flags_kernel(uint32_t nb, const int32_t* __restrict__ blk_size, int K, uint32_t* __restrict__ flags) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb) flags[b] = blk_size[b] >= K ? 1u : 0u;
+}
+
+__global__ void work_emit_kernel(uint32_t nb, const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan_ex,
+                                 uint32_t* __restrict__ work) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb && flags[b]) work[scan_ex[b]] = b;
+}
+
+__global__ void gather_points_kernel(uint32_t n, const double* __restrict__ xyz, const uint32_t* __restrict__ perm,
+                                     double* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t r = perm[i];
+    out[(size_t)i * 3 + 0] = xyz[r * 3 + 0];
+    out[(size_t)i * 3 + 1] = xyz[r * 3 + 1];
+    out[(size_t)i * 3 + 2] = xyz[r * 3 + 2];
+}
+
+__global__ void ransac_snapshot_kernel(uint32_t nb, const uint32_t* __restrict__ ref_order, const int32_t* __restrict__ blk_pose,
+                                       const uint32_t* __restrict__ blk_leaf, const uint32_t* __restrict__ cache_rank,
+                                       const int32_t* __restrict__ blk_size, const float* __restrict__ plane,
+                                       const int32_t* __restrict__ best, const int32_t* __restrict__ best_count,
+                                       int32_t* __restrict__ o_pose, int32_t* __restrict__ o_leaf, int32_t* __restrict__ o_size,
+                                       float* __restrict__ o_plane, int32_t* __restrict__ o_best,
+                                       int32_t* __restrict__ o_count) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nb) return;
+    uint32_t b = ref_order[j];
+    o_pose[j] = blk_pose[b];
+    o_leaf[j] = (int32_t)cache_rank[blk_leaf[b]];
+    o_size[j] = blk_size[b];
+    if (plane) {
+        for (int c = 0; c < 4; ++c) o_plane[(size_t)j * 4 + c] = plane[(size_t)b * 4 + c];
+        o_best[j] = best[b];
+        o_count[j] = best_count[b];
+    }
+}
+
+__global__ void pose_block_counts_kernel(uint32_t nb, const uint32_t* __restrict__ blk_start, const int32_t* __restrict__ blk_pose,
+                                         unsigned long long* __restrict__ counts /*[P][3]*/) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const int p = blk_pose[b];
+    atomicAdd(&counts[(size_t)p * 3 + 0], 1ull);
+    atomicAdd(&counts[(size_t)p * 3 + 1], (unsigned long long)(blk_start[b + 1] - blk_start[b]));
+}
+
+__global__ void cell_leaf_count_kernel(uint32_t L, const uint32_t* __restrict__ lcell, uint32_t* __restrict__ cell_nl) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < L) atomicAdd(&cell_nl[lcell[k]], 1u);
+}
+
+__global__ void pose_node_counts_kernel(uint32_t ncp, const uint32_t* __restrict__ cp_cell, const int32_t* __restrict__ cp_pose,
+                                        const uint32_t* __restrict__ cell_nl, unsigned long long* __restrict__ counts) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncp) return;
+    const uint32_t nl = cell_nl[cp_cell[j]];  // leaves = 1 + 7 * internal  ->  nodes = leaves + (leaves - 1) / 7
+    atomicAdd(&counts[(size_t)cp_pose[j] * 3 + 2], (unsigned long long)(nl + (nl - 1) / 7));
+}
+
+__global__ void cell_export_kernel(uint32_t C, const uint64_t* __restrict__ cell_key, KeyParams kp,
+                                   const uint32_t* __restrict__ cell_leaf_begin, long long* __restrict__ q_out,
+                                   double* __restrict__ corner_out, long long* __restrict__ nodes_out,
+                                   long long* __restrict__ leaf_begin_out) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > C) return;
+    if (leaf_begin_out) leaf_begin_out[c] = cell_leaf_begin[c];
+    if (c == C) return;
+    long long q[3] = {0, 0, 0};
+    if (!kp.single_cell) unpack_cell(kp, cell_key[c], q);
+    for (int a = 0; a < 3; ++a) {
+        if (q_out) q_out[(size_t)c * 3 + a] = q[a];
+        if (corner_out) corner_out[(size_t)c * 3 + a] = cell_corner_coord(q[a], kp.corner[a], kp.edge, kp.single_cell);
+    }
+    if (nodes_out) {
+        const long long nl = (long long)cell_leaf_begin[c + 1] - (long long)cell_leaf_begin[c];
+        nodes_out[c] = nl + (nl - 1) / 7;
+    }
+}
+
+// selection flags over positions (export of one pose / all poses)
+__global__ void select_pose_kernel(uint32_t n, const uint32_t* __restrict__ blk_of_pos, const int32_t* __restrict__ blk_pose,
+                                   int pose, uint32_t* __restrict__ flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = (pose < 0 || blk_pose[blk_of_pos[i]] == pose) ? 1u : 0u;
+}
+
+__global__ void select_blocks_ref_kernel(uint32_t nb, const uint32_t* __restrict__ ref_order, const int32_t* __restrict__ blk_pose,
+                                         const uint32_t* __restrict__ blk_start, int pose, uint32_t* __restrict__ sel_sizes) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nb) return;
+    uint32_t b = ref_order[j];
+    sel_sizes[j] = (pose < 0 || blk_pose[b] == pose) ? blk_start[b + 1] - blk_start[b] : 0u;
+}
+
+// writes the selected points; dst = dfs ? scan over positions : block offset in reference order
+__global__ void export_points_kernel(uint32_t n, int pose, int dfs, const uint32_t* __restrict__ blk_of_pos,
+                                     const int32_t* __restrict__ blk_pose, const uint32_t* __restrict__ blk_start,
+                                     const uint32_t* __restrict__ refpos, const uint32_t* __restrict__ ref_off,
+                                     const uint32_t* __restrict__ pos_scan, const uint32_t* __restrict__ perm,
+                                     const double* __restrict__ xyz, const uint32_t* __restrict__ leaf_of,
+                                     const uint32_t* __restrict__ lcell, const uint32_t* __restrict__ seg_start,
+                                     const int64_t* __restrict__ seg_first, int n_seg, const uint8_t* __restrict__ mask,
+                                     double* __restrict__ o_xyz, long long* __restrict__ o_idx, int32_t* __restrict__ o_cell,
+                                     uint8_t* __restrict__ o_mask) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t b = blk_of_pos[i];
+    if (pose >= 0 && blk_pose[b] != pose) return;
+    const uint32_t dst = dfs ? pos_scan[i] : ref_off[refpos[b]] + (i - blk_start[b]);
+    const uint32_t r = perm[i];
+    if (o_xyz) {
+        o_xyz[(size_t)dst * 3 + 0] = xyz[(size_t)r * 3 + 0];
+        o_xyz[(size_t)dst * 3 + 1] = xyz[(size_t)r * 3 + 1];
+        o_xyz[(size_t)dst * 3 + 2] = xyz[(size_t)r * 3 + 2];
+    }
+    if (o_idx) {
+        const int s = seg_of_rank(seg_start, n_seg, r);
+        o_idx[dst] = (long long)(r - seg_start[s]) + seg_first[s];
+    }
+    if (o_cell) o_cell[dst] = (int32_t)lcell[leaf_of[i]];
+    if (o_mask) o_mask[dst] = mask ? mask[i] : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// block order of the reference: (pose rank, leaf enumeration order)   grid.py:173-191, 217-232
+// ---------------------------------------------------------------------------------------------
+void Forest::compute_ref_order(const int32_t* pose_rank_host, DevBuf<uint32_t>& ref_order, DevBuf<int32_t>& d_pose_rank) {
+    ensure_order();
+    ensure_blocks();
+    std::vector<int32_t> pr(std::max(n_poses, 1));
+    for (int p = 0; p < n_poses; ++p) pr[p] = pose_rank_host ? pose_rank_host[p] : p;
+    int max_rank = 0;
+    for (int p = 0; p < n_poses; ++p) {
+        OL_REQUIRE(pr[p] >= 0, OL_ERR_INVALID, "negative pose rank");
+        max_rank = std::max(max_rank, pr[p]);
+    }
+    d_pose_rank.reset(ctx, pr.size());
+    h2d(ctx, d_pose_rank.get(), pr.data(), pr.size());
+    ctx.sync();
+    ref_order.reset(ctx, NB);
+    if (NB == 0) return;
+    DevBuf<uint64_t> k0(ctx, NB), k1(ctx, NB);
+    DevBuf<uint32_t> v0(ctx, NB), v1(ctx, NB);
+    block_refkey_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_pose.get(), blk_leaf.get(), d_pose_rank.get(),
+                                                          cache_rank.get(), k0.get(), v0.get());
+    OL_CHECK_LAUNCH();
+    int w = radix_sort_pairs<uint64_t>(ctx, k0.get(), k1.get(), v0.get(), v1.get(), NB, 0, bit_length_u64(L));
+    uint64_t* ka = w ? k1.get() : k0.get();
+    uint64_t* kb = w ? k0.get() : k1.get();
+    uint32_t* va = w ? v1.get() : v0.get();
+    uint32_t* vb = w ? v0.get() : v1.get();
+    int w2 = radix_sort_pairs<uint64_t>(ctx, ka, kb, va, vb, NB, 32, 32 + bit_length_u64((uint64_t)max_rank));
+    d2d(ctx, ref_order.get(), w2 ? vb : va, NB);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Grid.map_leaf_points_cuda_ransac (grid.py:124-215)
+// ---------------------------------------------------------------------------------------------
+void Forest::ransac(const double* table_host, int H, int K, double threshold, const int32_t* pose_rank, int ppb, bool apply,
+                    uint32_t flags) {
+    OL_REQUIRE(threshold > 0, OL_ERR_INVALID, "Threshold must be positive");
+    OL_REQUIRE(H >= 1, OL_ERR_INVALID, "Number of RANSAC hypotheses must be positive");
+    OL_REQUIRE(H <= 1024, OL_ERR_INVALID, "Number of RANSAC hypotheses must be <= 1024 because of the CUDA thread limit.");
+    OL_REQUIRE(K >= 1 && K <= 64, OL_ERR_INVALID, "initial_points_number must be in 1..64");
+    OL_REQUIRE(ppb >= 1, OL_ERR_INVALID, "poses_per_batch must be positive");
+    DevBuf<uint32_t> ref_order;
+    DevBuf<int32_t> d_pose_rank;
+    compute_ref_order(pose_rank, ref_order, d_pose_rank);
+    res_n = NB;
+    res_pose.reset(ctx, NB);
+    res_leaf.reset(ctx, NB);
+    res_size.reset(ctx, NB);
+    res_plane.reset(ctx, (size_t)NB * 4);
+    res_best.reset(ctx, NB);
+    res_count.reset(ctx, NB);
+    mask.reset(ctx, A);
+    mask.zero();
+    mask_n = A;
+    if (NB == 0) {
+        ransac_valid = true;
+        return;
+    }
+    int max_rank = 0;
+    for (int p = 0; p < n_poses; ++p) max_rank = std::max(max_rank, pose_rank ? pose_rank[p] : p);
+    const int n_batches = max_rank / ppb + 1;
+    DevBuf<uint32_t> sizes_ref(ctx, NB), refstart(ctx, NB), refpos(ctx, NB), batch_base(ctx, n_batches), wflags(ctx, NB),
+        wscan(ctx, NB);
+    DevBuf<int32_t> blk_size(ctx, NB);
+    DevBuf<long long> blk_ref_start(ctx, NB);
+    DevBuf<unsigned long long> d_total(ctx, 1);
+    batch_base.zero();
+    block_sizes_ref_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_start.get(), sizes_ref.get(), refpos.get(),
+                                                             blk_size.get());
+    OL_CHECK_LAUNCH();
+    exclusive_scan_u32(ctx, sizes_ref.get(), refstart.get(), NB, nullptr);
+    batch_base_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), d_pose_rank.get(), ppb,
+                                                        refstart.get(), batch_base.get());
+    OL_CHECK_LAUNCH();
+    block_refstart_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), d_pose_rank.get(), ppb,
+                                                            refstart.get(), batch_base.get(), blk_ref_start.get());
+    OL_CHECK_LAUNCH();
+    work_flags_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_size.get(), K, wflags.get());
+    OL_CHECK_LAUNCH();
+    exclusive_scan_u32(ctx, wflags.get(), wscan.get(), NB, d_total.get());
+    const uint32_t n_work = (uint32_t)read_u64(d_total.get());
+    DevBuf<uint32_t> work(ctx, n_work);
+    work_emit_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, wflags.get(), wscan.get(), work.get());
+    OL_CHECK_LAUNCH();
+    // K5b: gather the points into leaf order so that every block is one contiguous float64 run
+    DevBuf<double> pleaf(ctx, (size_t)A * 3 + 2);
+    gather_points_kernel<<<nblk(A), 256, 0, ctx.stream>>>(A, P64.get(), perm.get(), pleaf.get());
+    OL_CHECK_LAUNCH();
+    DevBuf<double> table(ctx, (size_t)H * K);
+    h2d(ctx, table.get(), table_host, (size_t)H * K);
+    DevBuf<float> plane(ctx, (size_t)NB * 4);
+    DevBuf<int32_t> best(ctx, NB), best_count(ctx, NB);
+    plane.zero();
+    best_count.zero();
+    fill_kernel<int32_t><<<nblk(NB), 256, 0, ctx.stream>>>(best.get(), NB, -1);
+    OL_CHECK_LAUNCH();
+    launch_ransac(ctx, pleaf.get(), A, blk_start.get(), blk_size.get(), blk_ref_start.get(), work.get(), n_work, max_block,
+                  table.get(), H, K, threshold, mask.get(), plane.get(), best.get(), best_count.get(), flags);
+    ransac_snapshot_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), blk_leaf.get(), cache_rank.get(),
+                                                             blk_size.get(), plane.get(), best.get(), best_count.get(),
+                                                             res_pose.get(), res_leaf.get(), res_size.get(), res_plane.get(),
+                                                             res_best.get(), res_count.get());
+    OL_CHECK_LAUNCH();
+    // a sample index that left its block is clamped and only counted (see ransac.cu)
+    uint32_t e = read_u32(d_err.get());
+    if (e & DEVERR_SAMPLE_OOB) {
+        sample_oob_seen = true;
+        e &= ~(uint32_t)DEVERR_SAMPLE_OOB;
+        OL_CUDA(cudaMemcpyAsync(d_err.get(), &e, 4, cudaMemcpyHostToDevice, ctx.stream));
+        ctx.sync();
+    }
+    ransac_valid = true;
+    if (apply) apply_mask();
+}
+
+void Forest::apply_mask() {
+    OL_REQUIRE(ransac_valid && mask_n == A, OL_ERR_STATE, "no RANSAC mask to apply");
+    DevBuf<uint8_t> m;
+    m.swap(mask);
+    apply_keep(m.get());
+    ransac_valid = false;
+}
+
+__global__ void keep_from_pose_mask_kernel(uint32_t n, int pose, const uint32_t* __restrict__ blk_of_pos,
+                                          const int32_t* __restrict__ blk_pose, const uint32_t* __restrict__ blk_start,
+                                          const uint32_t* __restrict__ refpos, const uint32_t* __restrict__ ref_off,
+                                          const uint8_t* __restrict__ pose_mask, uint8_t* __restrict__ keep_pos) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t b = blk_of_pos[i];
+    uint8_t keep = 1;
+    if (blk_pose[b] == pose) keep = pose_mask[ref_off[refpos[b]] + (i - blk_start[b])];
+    keep_pos[i] = keep;
+}
+
+// OctreeManager.apply_mask (octree_manager.py:173-180): host mask in the pose's leaf order
+void Forest::apply_pose_mask(const int32_t* pose_rank, int pose, const uint8_t* mask_host, int64_t n) {
+    OL_REQUIRE(pose >= 0 && pose < n_poses, OL_ERR_POSE, "unknown pose index " + std::to_string(pose));
+    DevBuf<uint32_t> ref_order;
+    DevBuf<int32_t> d_pose_rank;
+    compute_ref_order(pose_rank, ref_order, d_pose_rank);
+    if (NB == 0) {
+        OL_REQUIRE(n == 0, OL_ERR_INVALID, "mask length does not match the pose's point count");
+        return;
+    }
+    DevBuf<uint32_t> sizes_ref(ctx, NB), sel(ctx, NB), refpos(ctx, NB), ref_off(ctx, NB);
+    DevBuf<int32_t> blk_size(ctx, NB);
+    DevBuf<unsigned long long> d_total(ctx, 1);
+    block_sizes_ref_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_start.get(), sizes_ref.get(), refpos.get(),
+                                                             blk_size.get());
+    OL_CHECK_LAUNCH();
+    select_blocks_ref_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), blk_start.get(), pose,
+                                                               sel.get());
+    OL_CHECK_LAUNCH();
+    exclusive_scan_u32(ctx, sel.get(), ref_off.get(), NB, d_total.get());
+    const uint64_t total = read_u64(d_total.get());
+    OL_REQUIRE((int64_t)total == n, OL_ERR_INVALID,
+               "mask length " + std::to_string(n) + " does not match the pose's point count " + std::to_string(total));
+    if (total == 0) return;
+    DevBuf<uint8_t> pm(ctx, total), keep_pos(ctx, A);
+    h2d(ctx, pm.get(), mask_host, total);
+    keep_from_pose_mask_kernel<<<nblk(A), 256, 0, ctx.stream>>>(A, pose, blk_of_pos.get(), blk_pose.get(), blk_start.get(),
+                                                                refpos.get(), ref_off.get(), pm.get(), keep_pos.get());
+    OL_CHECK_LAUNCH();
+    ctx.sync();
+    apply_keep(keep_pos.get());
+}
+
+// ---------------------------------------------------------------------------------------------
+// counters (grid.py:343-362)
+// ---------------------------------------------------------------------------------------------
+void Forest::pose_counts(int64_t* out_host) {
+    ensure_blocks();
+    const int P = std::max(n_poses, 1);
+    DevBuf<unsigned long long> counts(ctx, (size_t)P * 3);
+    counts.zero();
+    if (NB) {
+        pose_block_counts_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_start.get(), blk_pose.get(), counts.get());
+        OL_CHECK_LAUNCH();
+    }
+    if (CP) {
+        DevBuf<uint32_t> cell_nl(ctx, C);
+        cell_nl.zero();
+        cell_leaf_count_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, lcell.get(), cell_nl.get());
+        OL_CHECK_LAUNCH();
+        pose_node_counts_kernel<<<nblk(CP), 256, 0, ctx.stream>>>(CP, cp_cell.get(), cp_pose.get(), cell_nl.get(), counts.get());
+        OL_CHECK_LAUNCH();
+    }
+    std::vector<unsigned long long> h((size_t)P * 3);
+    d2h(ctx, h.data(), counts.get(), h.size());
+    ctx.sync();
+    for (int p = 0; p < n_poses; ++p)
+        for (int k = 0; k < 3; ++k) out_host[(size_t)p * 3 + k] = (int64_t)h[(size_t)p * 3 + k];
+}
+
+void Forest::stats(ol_forest_stats* s) {
+    ensure_blocks();
+    memset(s, 0, sizeof(*s));
+    s->n_points_inserted = (int64_t)N;
+    s->n_points_alive = A;
+    s->n_poses = n_poses;
+    s->n_cells = C;
+    s->n_cell_poses = CP;
+    s->n_leaves = L;
+    s->n_internal = I;
+    s->n_blocks = NB;
+    s->max_block_size = max_block;
+    s->max_depth_reached = depth_reached;
+    s->key_bits = key_bits;
+    s->device_bytes_peak = (int64_t)ctx.bytes_peak;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exports
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static void copy_out(Ctx& ctx, T* host, const T* dev, size_t n) {
+    if (host && n) d2h(ctx, host, dev, n);
+}
+
+void Forest::export_cells(int64_t* q, double* corner, int32_t* first_pose, int64_t* n_nodes, int64_t* leaf_begin) {
+    ensure_order();
+    DevBuf<long long> dq(ctx, (size_t)C * 3), dn(ctx, C), dl(ctx, (size_t)C + 1);
+    DevBuf<double> dc(ctx, (size_t)C * 3);
+    cell_export_kernel<<<nblk((size_t)C + 1), 256, 0, ctx.stream>>>(C, cell_key.get(), kp, cell_leaf_begin.get(), dq.get(),
+                                                                    dc.get(), dn.get(), dl.get());
+    OL_CHECK_LAUNCH();
+    copy_out(ctx, (long long*)q, dq.get(), (size_t)C * 3);
+    copy_out(ctx, corner, dc.get(), (size_t)C * 3);
+    copy_out(ctx, (long long*)n_nodes, dn.get(), C);
+    copy_out(ctx, (long long*)leaf_begin, dl.get(), (size_t)C + 1);
+    copy_out(ctx, first_pose, cell_first_pose.get(), C);
+    ctx.sync();
+}
+
+void Forest::export_cell_poses(int32_t* cell, int32_t* pose) {
+    build();
+    copy_out(ctx, (uint32_t*)cell, cp_cell.get(), CP);
+    copy_out(ctx, pose, cp_pose.get(), CP);
+    ctx.sync();
+}
+
+__global__ void leaf_meta_kernel(uint32_t L, const uint32_t* __restrict__ leaf_by_cache, const uint32_t* __restrict__ lcell,
+                                 const uint8_t* __restrict__ ldepth, int32_t* __restrict__ o_cell, int32_t* __restrict__ o_depth) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= L) return;
+    uint32_t k = leaf_by_cache[j];
+    o_cell[j] = (int32_t)lcell[k];
+    o_depth[j] = (int32_t)ldepth[k];
+}
+
+void Forest::export_leaves(double* corner, double* edge, int32_t* cell, int32_t* depth) {
+    ensure_order();
+    copy_out(ctx, corner, leaf_corner.get(), (size_t)L * 3);
+    copy_out(ctx, edge, leaf_edge.get(), L);
+    if ((cell || depth) && L) {
+        DevBuf<int32_t> dc(ctx, L), dd(ctx, L);
+        leaf_meta_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, leaf_by_cache.get(), lcell.get(), ldepth.get(), dc.get(), dd.get());
+        OL_CHECK_LAUNCH();
+        copy_out(ctx, cell, dc.get(), L);
+        copy_out(ctx, depth, dd.get(), L);
+        ctx.sync();
+    }
+    ctx.sync();
+}
+
+void Forest::export_blocks(const int32_t* pose_rank, int32_t* pose, int32_t* leaf, int32_t* size) {
+    DevBuf<uint32_t> ref_order;
+    DevBuf<int32_t> d_pose_rank;
+    compute_ref_order(pose_rank, ref_order, d_pose_rank);
+    if (NB == 0) return;
+    DevBuf<uint32_t> sizes_ref(ctx, NB), refpos(ctx, NB);
+    DevBuf<int32_t> blk_size(ctx, NB), o_pose(ctx, NB), o_leaf(ctx, NB), o_size(ctx, NB);
+    block_sizes_ref_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_start.get(), sizes_ref.get(), refpos.get(),
+                                                             blk_size.get());
+    OL_CHECK_LAUNCH();
+    ransac_snapshot_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), blk_leaf.get(), cache_rank.get(),
+                                                             blk_size.get(), nullptr, nullptr, nullptr, o_pose.get(), o_leaf.get(),
+                                                             o_size.get(), nullptr, nullptr, nullptr);
+    OL_CHECK_LAUNCH();
+    copy_out(ctx, pose, o_pose.get(), NB);
+    copy_out(ctx, leaf, o_leaf.get(), NB);
+    copy_out(ctx, size, o_size.get(), NB);
+    ctx.sync();
+}
+
+void Forest::export_ransac(int32_t* pose, int32_t* leaf, int32_t* size, float* plane, int32_t* best, int32_t* count) {
+    copy_out(ctx, pose, res_pose.get(), res_n);
+    copy_out(ctx, leaf, res_leaf.get(), res_n);
+    copy_out(ctx, size, res_size.get(), res_n);
+    copy_out(ctx, plane, res_plane.get(), (size_t)res_n * 4);
+    copy_out(ctx, best, res_best.get(), res_n);
+    copy_out(ctx, count, res_count.get(), res_n);
+    ctx.sync();
+}
+
+int64_t Forest::export_points(const int32_t* pose_rank, int pose, int order, double* xyz, int64_t* idx, int32_t* cell,
+                              uint8_t* mask_out) {
+    OL_REQUIRE(pose < n_poses, OL_ERR_POSE, "unknown pose index " + std::to_string(pose));
+    ensure_blocks();
+    if (A == 0) return 0;
+    const int S = (int)seg_pose.size();
+    const bool dfs = order == 1;
+    DevBuf<uint32_t> ref_order, refpos, ref_off, pos_scan;
+    DevBuf<int32_t> d_pose_rank;
+    DevBuf<unsigned long long> d_total(ctx, 1);
+    uint64_t total = 0;
+    if (dfs) {
+        DevBuf<uint32_t> flags(ctx, A);
+        pos_scan.reset(ctx, A);
+        select_pose_kernel<<<nblk(A), 256, 0, ctx.stream>>>(A, blk_of_pos.get(), blk_pose.get(), pose, flags.get());
+        OL_CHECK_LAUNCH();
+        exclusive_scan_u32(ctx, flags.get(), pos_scan.get(), A, d_total.get());
+        total = read_u64(d_total.get());
+    } else {
+        compute_ref_order(pose_rank, ref_order, d_pose_rank);
+        DevBuf<uint32_t> sizes_ref(ctx, NB), sel(ctx, NB);
+        DevBuf<int32_t> blk_size(ctx, NB);
+        refpos.reset(ctx, NB);
+        ref_off.reset(ctx, NB);
+        block_sizes_ref_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_start.get(), sizes_ref.get(),
+                                                                 refpos.get(), blk_size.get());
+        OL_CHECK_LAUNCH();
+        select_blocks_ref_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), blk_start.get(), pose,
+                                                                   sel.get());
+        OL_CHECK_LAUNCH();
+        exclusive_scan_u32(ctx, sel.get(), ref_off.get(), NB, d_total.get());
+        total = read_u64(d_total.get());
+    }
+    if (total == 0) return 0;
+    const bool want_mask = mask_out && ransac_valid && mask_n == A && !dfs;
+    DevBuf<double> o_xyz;
+    DevBuf<long long> o_idx;
+    DevBuf<int32_t> o_cell;
+    DevBuf<uint8_t> o_mask;
+    if (xyz) o_xyz.reset(ctx, total * 3);
+    if (idx) o_idx.reset(ctx, total);
+    if (cell) o_cell.reset(ctx, total);
+    if (mask_out) {
+        o_mask.reset(ctx, total);
+        o_mask.zero();
+    }
+    export_points_kernel<<<nblk(A), 256, 0, ctx.stream>>>(A, pose, dfs ? 1 : 0, blk_of_pos.get(), blk_pose.get(), blk_start.get(),
+                                                          refpos.get(), ref_off.get(), pos_scan.get(), perm.get(), P64.get(),
+                                                          leaf_of.get(), lcell.get(), d_seg_start.get(), d_seg_first.get(), S,
+                                                          want_mask ? mask.get() : nullptr, o_xyz.get(), o_idx.get(), o_cell.get(),
+                                                          o_mask.get());
+    OL_CHECK_LAUNCH();
+    copy_out(ctx, xyz, o_xyz.get(), total * 3);
+    copy_out(ctx, (long long*)idx, o_idx.get(), total);
+    copy_out(ctx, cell, o_cell.get(), total);
+    copy_out(ctx, mask_out, o_mask.get(), total);
+    ctx.sync();
+    return (int64_t)total;
+}
+
+}  // namespace ol

@@ -1,0 +1,273 @@
+"""
+`Forest`: thin Python owner of one native `ol_forest` handle.
+
+A forest is the device-resident state behind one `Grid` (many cells, many poses) or one
+`OctreeManager` / `Octree` (a single fixed cell).  This class only moves arguments across the C
+ABI, lends torch's caching allocator to the library (PyTorch tensors are used purely as device
+buffers) and turns status codes into the exceptions the reference raises.  All arithmetic happens
+in the CUDA library; nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+
+__all__ = ["Forest", "TorchAllocator", "require_cuda"]
+
+
+def require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "octreelib_b200 needs a CUDA device (B200, sm_100a): there is no CPU fallback for the grid pipeline")
+    return torch
+
+
+class TorchAllocator:
+    """Device allocator callbacks backed by torch's caching allocator."""
+
+    def __init__(self, device):
+        self.torch = require_cuda()
+        self.device = device
+        self.live = {}
+        self.alloc_cb = N.ALLOC_FN(self._alloc)
+        self.free_cb = N.FREE_FN(self._free)
+
+    def _alloc(self, _user, nbytes):
+        try:
+            t = self.torch.empty(int(nbytes), dtype=self.torch.uint8, device=self.device)
+            ptr = t.data_ptr()
+            self.live[ptr] = t
+            return ptr
+        except Exception:  # noqa: BLE001 - must not propagate through the C frame
+            return None
+
+    def _free(self, _user, ptr):
+        self.live.pop(ptr, None)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _i32_array(values: Optional[Sequence[int]]):
+    if values is None:
+        return None, 0
+    arr = np.ascontiguousarray(list(values), dtype=np.int32)
+    return arr, len(arr)
+
+
+class Forest:
+    def __init__(self, edge: float, corner=(0.0, 0.0, 0.0), single_cell: bool = False, max_depth: int = N.OL_MAX_DEPTH,
+                 device=None):
+        torch = require_cuda()
+        self._lib = N.lib()
+        self._torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._stream = torch.cuda.current_stream(self.device)
+        self._allocator = TorchAllocator(self.device)
+        cfg = N.ForestConfig()
+        cfg.voxel_edge_length = float(edge)
+        cfg.corner = (C.c_double * 3)(*[float(v) for v in corner])
+        cfg.single_cell = 1 if single_cell else 0
+        cfg.max_depth = int(max_depth)
+        cfg.device = self.device.index
+        cfg.stream = C.c_void_p(self._stream.cuda_stream)
+        cfg.alloc = self._allocator.alloc_cb
+        cfg.free = self._allocator.free_cb
+        cfg.alloc_user = None
+        self._h = C.c_void_p()
+        with self._scope():
+            N.check(self._lib.ol_forest_create(C.byref(cfg), C.byref(self._h)))
+        self.version = 0  # bumped by every mutating call; hosts cache exports per version
+
+    def _scope(self):
+        return self._torch.cuda.stream(self._stream)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            with self._scope():
+                self._lib.ol_forest_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ---- mutation ------------------------------------------------------------------------------
+    def insert(self, points) -> int:
+        """Append one pose's cloud: numpy (n,3) array or a CUDA float64 tensor.  Returns pose index."""
+        out = C.c_int32(-1)
+        src, n, on_dev, keep = self._as_source(points)
+        with self._scope():
+            N.check(self._lib.ol_forest_insert(self._h, src, n, on_dev, C.byref(out)))
+        del keep
+        self.version += 1
+        return out.value
+
+    def insert_segments(self, points, seg_sizes, seg_pose, seg_first, n_poses_total: int):
+        src, n, on_dev, keep = self._as_source(points)
+        ss = np.ascontiguousarray(seg_sizes, dtype=np.int64)
+        sp = np.ascontiguousarray(seg_pose, dtype=np.int32)
+        sf = np.ascontiguousarray(seg_first, dtype=np.int64)
+        with self._scope():
+            N.check(self._lib.ol_forest_insert_segments(self._h, src, n, on_dev, _ptr(ss), _ptr(sp), _ptr(sf), len(ss),
+                                                        int(n_poses_total)))
+        del keep
+        self.version += 1
+
+    def _as_source(self, points):
+        torch = self._torch
+        if isinstance(points, torch.Tensor):
+            t = points
+            if t.device.type != "cuda":
+                return self._as_source(t.numpy())
+            t = t.to(torch.float64).contiguous().reshape(-1, 3)
+            return C.c_void_p(t.data_ptr()), t.shape[0], 1, t
+        a = np.ascontiguousarray(np.asarray(points), dtype=np.float64)
+        if a.size == 0:
+            a = a.reshape(0, 3)
+        if a.ndim != 2 or a.shape[1] != 3:
+            raise ValueError(f"points must have shape (n, 3), got {a.shape}")
+        return _ptr(a), a.shape[0], 0, a
+
+    def subdivide(self, max_points: int, pose_indices: Optional[Sequence[int]] = None):
+        arr, n = _i32_array(pose_indices)
+        with self._scope():
+            N.check(self._lib.ol_forest_subdivide(self._h, int(max_points), _ptr(arr), n))
+        self.version += 1
+
+    def subdivide_table(self, table: np.ndarray, beyond: bool, pose_indices: Optional[Sequence[int]] = None):
+        arr, n = _i32_array(pose_indices)
+        tab = np.ascontiguousarray(table, dtype=np.uint8)
+        with self._scope():
+            N.check(self._lib.ol_forest_subdivide_table(self._h, _ptr(tab), len(tab), 1 if beyond else 0, _ptr(arr), n))
+        self.version += 1
+
+    def filter(self, keep_table: np.ndarray, pose_indices: Optional[Sequence[int]] = None):
+        arr, n = _i32_array(pose_indices)
+        tab = np.ascontiguousarray(keep_table, dtype=np.uint8)
+        with self._scope():
+            N.check(self._lib.ol_forest_filter(self._h, _ptr(tab), len(tab), _ptr(arr), n))
+        self.version += 1
+
+    def ransac(self, table: np.ndarray, threshold: float, pose_rank: Optional[Sequence[int]] = None,
+               poses_per_batch: int = 10, apply: bool = True, flags: int = 0):
+        tab = np.ascontiguousarray(table, dtype=np.float64)
+        H, K = tab.shape
+        pr, _ = _i32_array(pose_rank)
+        with self._scope():
+            N.check(self._lib.ol_forest_ransac(self._h, _ptr(tab), H, K, float(threshold), _ptr(pr), int(poses_per_batch),
+                                               1 if apply else 0, int(flags)))
+        self.version += 1
+
+    def apply_mask(self):
+        with self._scope():
+            N.check(self._lib.ol_forest_apply_mask(self._h))
+        self.version += 1
+
+    def apply_pose_mask(self, pose_index: int, mask):
+        m = np.ascontiguousarray(np.asarray(mask).astype(bool), dtype=np.uint8)
+        with self._scope():
+            N.check(self._lib.ol_forest_apply_pose_mask(self._h, None, int(pose_index), _ptr(m), len(m)))
+        self.version += 1
+
+    # ---- queries -------------------------------------------------------------------------------
+    def stats(self) -> dict:
+        s = N.ForestStats()
+        with self._scope():
+            N.check(self._lib.ol_forest_stats_get(self._h, C.byref(s)))
+        return {name: int(getattr(s, name)) for name, _ in s._fields_}
+
+    def pose_counts(self, n_poses: int) -> np.ndarray:
+        out = np.zeros((max(n_poses, 1), 3), dtype=np.int64)
+        with self._scope():
+            N.check(self._lib.ol_forest_pose_counts(self._h, _ptr(out)))
+        return out[:n_poses]
+
+    def export_cells(self) -> dict:
+        st = self.stats()
+        Cn = st["n_cells"]
+        q = np.zeros((Cn, 3), dtype=np.int64)
+        corner = np.zeros((Cn, 3), dtype=np.float64)
+        first_pose = np.zeros(Cn, dtype=np.int32)
+        n_nodes = np.zeros(Cn, dtype=np.int64)
+        leaf_begin = np.zeros(Cn + 1, dtype=np.int64)
+        with self._scope():
+            N.check(self._lib.ol_forest_export_cells(self._h, _ptr(q), _ptr(corner), _ptr(first_pose), _ptr(n_nodes),
+                                                     _ptr(leaf_begin)))
+        return dict(q=q, corner=corner, first_pose=first_pose, n_nodes=n_nodes, leaf_begin=leaf_begin)
+
+    def export_cell_poses(self) -> dict:
+        st = self.stats()
+        n = st["n_cell_poses"]
+        cell = np.zeros(n, dtype=np.int32)
+        pose = np.zeros(n, dtype=np.int32)
+        with self._scope():
+            N.check(self._lib.ol_forest_export_cell_poses(self._h, _ptr(cell), _ptr(pose)))
+        return dict(cell=cell, pose=pose)
+
+    def export_leaves(self) -> dict:
+        st = self.stats()
+        L = st["n_leaves"]
+        corner = np.zeros((L, 3), dtype=np.float64)
+        edge = np.zeros(L, dtype=np.float64)
+        cell = np.zeros(L, dtype=np.int32)
+        depth = np.zeros(L, dtype=np.int32)
+        with self._scope():
+            N.check(self._lib.ol_forest_export_leaves(self._h, _ptr(corner), _ptr(edge), _ptr(cell), _ptr(depth)))
+        return dict(corner=corner, edge=edge, cell=cell, depth=depth)
+
+    def export_blocks(self, pose_rank: Optional[Sequence[int]] = None) -> dict:
+        st = self.stats()
+        B = st["n_blocks"]
+        pose = np.zeros(B, dtype=np.int32)
+        leaf = np.zeros(B, dtype=np.int32)
+        size = np.zeros(B, dtype=np.int32)
+        pr, _ = _i32_array(pose_rank)
+        with self._scope():
+            N.check(self._lib.ol_forest_export_blocks(self._h, _ptr(pr), _ptr(pose), _ptr(leaf), _ptr(size)))
+        return dict(pose=pose, leaf=leaf, size=size)
+
+    def export_ransac(self) -> dict:
+        n = C.c_int64(0)
+        with self._scope():
+            N.check(self._lib.ol_forest_export_ransac(self._h, None, None, None, None, None, None, C.byref(n)))
+        B = n.value
+        pose = np.zeros(B, dtype=np.int32)
+        leaf = np.zeros(B, dtype=np.int32)
+        size = np.zeros(B, dtype=np.int32)
+        plane = np.zeros((B, 4), dtype=np.float32)
+        best = np.zeros(B, dtype=np.int32)
+        count = np.zeros(B, dtype=np.int32)
+        with self._scope():
+            N.check(self._lib.ol_forest_export_ransac(self._h, _ptr(pose), _ptr(leaf), _ptr(size), _ptr(plane), _ptr(best),
+                                                      _ptr(count), C.byref(n)))
+        return dict(pose=pose, leaf=leaf, size=size, plane=plane, best=best, best_count=count)
+
+    def export_points(self, pose_index: int = -1, order: int = 0, pose_rank: Optional[Sequence[int]] = None,
+                      n_hint: Optional[int] = None, want_mask: bool = False) -> dict:
+        """order 0: reference block order; order 1: cells lexicographic x depth-first leaves."""
+        if n_hint is None:
+            n_hint = self.stats()["n_points_alive"]
+        xyz = np.zeros((n_hint, 3), dtype=np.float64)
+        idx = np.zeros(n_hint, dtype=np.int64)
+        cell = np.zeros(n_hint, dtype=np.int32)
+        mask = np.zeros(n_hint, dtype=np.uint8) if want_mask else None
+        pr, _ = _i32_array(pose_rank)
+        n = C.c_int64(0)
+        with self._scope():
+            N.check(self._lib.ol_forest_export_points(self._h, _ptr(pr), int(pose_index), int(order), _ptr(xyz), _ptr(idx),
+                                                      _ptr(cell), _ptr(mask), C.byref(n)))
+        k = n.value
+        out = dict(xyz=xyz[:k], idx=idx[:k], cell=cell[:k])
+        if want_mask:
+            out["mask"] = mask[:k]
+        return out

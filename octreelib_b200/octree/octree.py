@@ -1,0 +1,111 @@
+"""
+`Octree`, `OctreeNode`, `OctreeConfig` with the reference's surface
+(octreelib/octree/octree.py:14-16, 19-200, 203-295), backed by a single-cell native forest.
+
+The reference keeps one Python `OctreeNode` object per node; here the tree lives on the GPU and
+these classes are handles: every method forwards to the forest and the returned leaves are host
+views (`LeafVoxel`).
+"""
+from dataclasses import dataclass
+from typing import Callable, Generic, List
+
+import numpy as np
+
+from .._host import ForestHost
+from ..internal import PointCloud, T, Voxel
+from .octree_base import OctreeBase, OctreeConfigBase, OctreeNodeBase
+
+__all__ = ["OctreeNode", "Octree", "OctreeConfig"]
+
+
+@dataclass
+class OctreeConfig(OctreeConfigBase):
+    pass
+
+
+class _SinglePose:
+    """One cell, one pose (pose number 0) on a native forest."""
+
+    def _init_native(self, corner_min, edge_length):
+        self._host = ForestHost(edge_length, corner_min, single_cell=True)
+
+    def _root_corner(self, _cell):
+        return self._corner_min
+
+    def subdivide(self, subdivision_criteria: List[Callable[[PointCloud], bool]]):
+        """Split while any criterion holds (octree.py:20-32, 214-220)."""
+        self._host.subdivide(subdivision_criteria)
+        self._sync_cache()
+
+    def subdivide_as(self, other):
+        raise NotImplementedError("copying another octree's shape is driven by OctreeManager in the native build")
+
+    def get_points(self) -> PointCloud:
+        """Stored points in depth-first leaf order (octree.py:55-65); input order while unsplit."""
+        return self._host.points_dfs(0)
+
+    def insert_points(self, points: PointCloud):
+        """Append points (octree.py:235-239)."""
+        self._host.insert(0, np.asarray(points), allow_append=True)
+        self._sync_cache()
+
+    def filter(self, filtering_criteria: List[Callable[[PointCloud], bool]]):
+        """Empty every leaf for which not all criteria hold (octree.py:102-112)."""
+        self._host.filter(filtering_criteria)
+
+    def map_leaf_points(self, function: Callable[[PointCloud], PointCloud]):
+        raise NotImplementedError("arbitrary per-leaf Python callbacks are not part of the GPU path")
+
+    def apply_mask(self, mask: np.ndarray):
+        """Keep the points whose mask entry is True; mask in leaf order (octree.py:265-274)."""
+        if not self._host.empty:
+            self._host.forest.apply_pose_mask(0, mask)
+
+    @property
+    def n_points(self):
+        return self._host.count(0, 1)
+
+    @property
+    def n_leaves(self):
+        return self._host.count(0, 0)
+
+    @property
+    def n_nodes(self):
+        return self._host.count(0, 2) if not self._host.empty else 1
+
+    def _leaves(self, non_empty: bool) -> List[Voxel]:
+        if self._host.empty:
+            return [] if non_empty else [self]
+        return self._host.leaf_voxels(0, non_empty, self._root_corner, self._edge_length)
+
+    def _sync_cache(self):
+        pass
+
+
+class OctreeNode(_SinglePose, OctreeNodeBase):
+    """A root node used directly (test/octree/test_octree.py:8-30).  `octree_cached_leaves` is kept in
+    sync with the native tree: after every structural change it lists all leaves, empty ones
+    included, in the reference's cache order."""
+
+    def __init__(self, corner_min, edge_length, octree_cached_leaves: List):
+        OctreeNodeBase.__init__(self, corner_min, edge_length, octree_cached_leaves)
+        self._init_native(corner_min, edge_length)
+
+    def _sync_cache(self):
+        self._cached_leaves[:] = self._leaves(non_empty=False)
+
+    def get_leaf_points(self) -> List[Voxel]:
+        return self._leaves(non_empty=True)
+
+
+class Octree(_SinglePose, OctreeBase, Generic[T]):
+    """One pose's points in one cell as an octree (octree.py:203-295)."""
+
+    _node_type = OctreeNode
+
+    def __init__(self, octree_config, corner_min, edge_length):
+        OctreeBase.__init__(self, octree_config, corner_min, edge_length)
+        self._init_native(corner_min, edge_length)
+
+    def get_leaf_points(self, non_empty: bool = True) -> List[Voxel]:
+        return self._leaves(non_empty)
