@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""
+bench.py -- points/sec over insert + subdivide + per-leaf RANSAC (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this build
+    python bench.py --impl reference --gpus N ...            # CPU reference arm (oracle port, host cores)
+
+A "step" = one full pass of the hot path over one synthetic map: Grid() -> insert_points x P ->
+subdivide([len > 100]) -> map_leaf_points_cuda_ransac(H=1024, K=6).  Workload at every N: BASELINE
+config 4, the 100M-point multi-pose "infinite street" LiDAR map, total size fixed
+(strong scaling); with N > 1 the poses are sharded over the ranks, points are routed to the rank
+that owns their grid cell (hash of the cell key) with one NCCL all-to-all, and every cell is then
+subdivided and segmented locally.
+
+`value`  : device-resident inputs (points already in HBM when the timed region starts).
+`e2e`    : the same step through the public API with HOST (pinned) input buffers and the result
+           tables (leaf table + per-block plane table) read back to the host inside the timed region.
+Timing   : CUDA events on the work stream, max over ranks, barrier + synchronize on both sides.
+           The inputs (2.4 GB) are far larger than L2 (126 MB), so no extra L2 flush is needed.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (generator, total points, edge, max points per leaf, ransac threshold)
+    "c4_street_100M": dict(kind="street", points=100_000_000, edge=1.0, max_points=100, threshold=0.02),
+    "c3_indoor_10M": dict(kind="indoor", points=10_000_000, edge=0.5, max_points=100, threshold=0.01),
+    "c2_lidar_10x120k": dict(kind="lidar10", points=1_200_000, edge=1.0, max_points=100, threshold=0.02),
+}
+H, K = 1024, 6
+POINTS_PER_POSE_EST = 118_000
+
+
+# ------------------------------------------------------------------------------------------------
+# distributed plumbing
+# ------------------------------------------------------------------------------------------------
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def init_dist(world, local, backend="nccl"):
+    import torch
+    import torch.distributed as dist
+
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        dist.init_process_group(backend=backend, device_id=torch.device("cuda", local) if backend == "nccl" else None)
+    return dist
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = f"/tmp/ol_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def make_workload(name, rank, world, device, scale=1.0):
+    """Returns (list of per-pose CUDA float64 tensors owned by this rank, list of their global pose
+    numbers, total pose count, total point count)."""
+    import torch
+
+    from octreelib_b200 import synthetic
+
+    w = WORKLOADS[name]
+    total = int(w["points"] * scale)
+    if w["kind"] == "street":
+        # the street is translation invariant along x, so every pose returns the same number of
+        # points c0; P = ceil(total / c0) poses, the last one truncated to hit `total` exactly
+        _, cnt = synthetic.lidar_street_torch(0, 1, seed=0, device=device)
+        c0 = cnt[0]
+        P = (total + c0 - 1) // c0
+        lo, hi = rank * P // world, (rank + 1) * P // world
+        mine, numbers = [], []
+        chunk = 16
+        for first in range(lo, hi, chunk):
+            n = min(chunk, hi - first)
+            pts, cnts = synthetic.lidar_street_torch(first, n, seed=0, device=device)
+            off = 0
+            for j, c in enumerate(cnts):
+                pose = first + j
+                take = min(c, total - pose * c0)
+                mine.append(pts[off:off + take].clone())
+                numbers.append(pose)
+                off += c
+        torch.cuda.empty_cache()
+        return mine, numbers, P, total
+    if w["kind"] == "indoor":
+        pts = synthetic.indoor_torch(total, seed=0, device=device)
+        P = 1
+        if world > 1:  # a single pose split into contiguous index ranges (one run per rank)
+            lo, hi = rank * total // world, (rank + 1) * total // world
+            return [pts[lo:hi].clone()], [0], P, total
+        return [pts], [0], P, total
+    if w["kind"] == "lidar10":
+        clouds = [torch.from_numpy(synthetic.lidar64_scan(p, seed=0)).to(device) for p in range(10)]
+        P = 10
+        lo, hi = rank * P // world, (rank + 1) * P // world
+        return clouds[lo:hi], list(range(lo, hi)), P, sum(len(c) for c in clouds)
+    raise ValueError(name)
+
+
+# ------------------------------------------------------------------------------------------------
+# one step of this build
+# ------------------------------------------------------------------------------------------------
+def run_step(clouds, numbers, n_poses_total, w, world, profile=False, read_tables=False):
+    """clouds: per-pose arrays (CUDA tensors for `value`, pinned numpy arrays for `e2e`)."""
+    from octreelib_b200.criteria import MaxPoints
+    from octreelib_b200.grid import Grid, GridConfig
+
+    np.random.seed(0)
+    if world > 1:
+        from octreelib_b200.parallel import ShardedGrid
+
+        grid = ShardedGrid(GridConfig(voxel_edge_length=w["edge"]), n_poses_total)
+    else:
+        grid = Grid(GridConfig(voxel_edge_length=w["edge"]))
+    forest = grid._host.forest
+    if profile:
+        forest.profile(True)
+    for number, cloud in zip(numbers, clouds):
+        grid.insert_points(number, cloud)
+    if world > 1:
+        grid.exchange()
+    grid.subdivide([MaxPoints(w["max_points"])])
+    grid.map_leaf_points_cuda_ransac(poses_per_batch=10, threshold=w["threshold"], hypotheses_number=H,
+                                     initial_points_number=K)
+    d2h = 0
+    if read_tables:
+        planes = forest.export_ransac()
+        leaves = forest.export_leaves()
+        d2h = sum(a.nbytes for a in planes.values()) + sum(a.nbytes for a in leaves.values())
+    stats = forest.stats()  # synchronises; the step's scalar result
+    prof = forest.profile_read() if profile else None
+    return grid, stats, prof, d2h
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(workload, n_sample_points, threads):
+    """Times the CPU oracle (port of the reference, oracle/) on a bounded sample of the workload."""
+    from octreelib_b200 import synthetic
+    from oracle import ransac as oransac
+    from oracle.structure import OracleGrid, max_points_criterion
+
+    w = WORKLOADS[workload]
+    oransac.build()
+    if w["kind"] == "street":
+        n_poses = max(1, n_sample_points // POINTS_PER_POSE_EST)
+        clouds = {p: synthetic.lidar_street_scan(p, seed=0) for p in range(n_poses)}
+    elif w["kind"] == "indoor":
+        clouds = {0: synthetic.indoor_scene(n_sample_points, seed=0) * (1.0 / w["edge"])}  # exact power-of-two rescale
+    else:
+        clouds = {p: synthetic.lidar64_scan(p, seed=0) for p in range(max(1, n_sample_points // 120_000))}
+    edge = 1.0 if w["kind"] == "indoor" else w["edge"]
+    thr = w["threshold"] / w["edge"] if w["kind"] == "indoor" else w["threshold"]
+    n = sum(len(c) for c in clouds.values())
+    np.random.seed(0)
+    table = oransac.make_table(H, K)
+    t0 = time.perf_counter()
+    og = OracleGrid(edge)
+    for p, c in clouds.items():
+        og.insert_points(p, c)
+    og.subdivide([max_points_criterion(w["max_points"])])
+    t1 = time.perf_counter()
+    og.map_leaf_points_ransac(table, threshold=thr, poses_per_batch=10,
+                              evaluate=lambda pts, bs, tab, th: oransac.ransac_evaluate(pts, bs, tab, th, threads=threads))
+    t2 = time.perf_counter()
+    return dict(points=n, seconds=t2 - t0, structure_s=t1 - t0, ransac_s=t2 - t1, poses=len(clouds))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4_street_100M", choices=list(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the workload's points (debug only)")
+    ap.add_argument("--cpu-sample", type=int, default=250_000, help="points of the CPU baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = dist_env()
+    w = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    base = {"metric": "points/sec (insert+subdivide+per-leaf RANSAC)", "unit": "points/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "data": "synthetic",
+            "config": {"workload": args.workload, "points": int(w["points"] * args.scale), "voxel_edge_length": w["edge"],
+                       "max_points_per_leaf": w["max_points"], "ransac": {"hypotheses": H, "initial_points": K,
+                                                                         "threshold": w["threshold"]},
+                       "l2": "inputs (24 B/point) exceed the 126 MB L2 by >10x; no extra flush",
+                       "parallelism": f"cell-hash x{args.gpus}" if args.gpus > 1 else "single GPU"}}
+
+    # ---------------------------------------------------------------- reference arm (CPU) --------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = cores
+        times, pts = [], 0
+        for i in range(args.warmup + args.steps):
+            r = cpu_reference_sample(args.workload, args.cpu_sample, threads)
+            if i >= args.warmup:
+                times.append(r["seconds"])
+                pts = r["points"]
+        mean = sum(times) / len(times)
+        val = pts / mean
+        out = dict(base, impl="reference", value=val, ms_per_step=mean * 1e3, dtype="f64",
+                   cpu_baseline={"value": val, "unit": "points/s", "cores": threads, "kind": "port",
+                                 "sample": f"{pts} points ({r['poses']} poses) of {args.workload}; structure on 1 core "
+                                           f"(numpy, like the reference), RANSAC on {threads} threads (C port)"},
+                   e2e={"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                   gpu_launches=0)
+        print(json.dumps(out))
+        return 0
+
+    # ---------------------------------------------------------------- this build -----------------
+    import torch
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist = init_dist(world, local)
+    from octreelib_b200 import _native
+
+    lib = _native.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clouds, numbers, P, total = make_workload(args.workload, rank, world, device, args.scale)
+    local_points = sum(int(c.shape[0]) for c in clouds)
+
+    def timed(fn, steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        res = None
+        for _ in range(steps):
+            res = fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, res
+
+    # warm-up (also warms torch's caching allocator so the timed steps do not call cudaMalloc)
+    for _ in range(args.warmup):
+        run_step(clouds, numbers, P, w, world)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.ol_launch_count()
+    ms, res = timed(lambda: run_step(clouds, numbers, P, w, world), args.steps)
+    launches = (lib.ol_launch_count() - launches0) // max(args.steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = total / (ms_per_step * 1e-3)
+    stats = res[1]
+
+    # profiled step (separate from the timed ones): per-stage times for the roofline object
+    _, _, prof, _ = run_step(clouds, numbers, P, w, world, profile=True)
+
+    # e2e: pinned host inputs, result tables read back
+    e2e = None
+    if not args.no_e2e:
+        host_clouds = []
+        for c in clouds:
+            h = torch.empty(c.shape, dtype=torch.float64, pin_memory=True)
+            h.copy_(c)
+            host_clouds.append(h.numpy())
+        torch.cuda.synchronize()
+        h2d = sum(a.nbytes for a in host_clouds)
+        run_step(host_clouds, numbers, P, w, world, read_tables=True)
+        e_ms, e_res = timed(lambda: run_step(host_clouds, numbers, P, w, world, read_tables=True), args.steps)
+        e_ms /= args.steps
+        e2e = {"value": total / (e_ms * 1e-3), "unit": "points/s", "ms_per_step": e_ms, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": e_res[3]}
+        del host_clouds
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return 0
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    A = local_points if world == 1 else stats["n_points_inserted"]
+    # algorithmic bytes per launch of the dominant HBM-bound kernel:
+    # radix scatter pass over (u64 key, u32 value) pairs = read 12 B + write 12 B per point
+    stage_ms = {k: v[1] for k, v in (prof or {}).items()}
+    roofline = None
+    if prof and "radix_scatter_u64" in prof:
+        cnt, tot_ms = prof["radix_scatter_u64"]
+        # launches in this stage sort arrays of different lengths; the big ones are the key sort
+        # passes over all points, which dominate; bytes are accumulated by the library-side timer
+        # per launch as 24 B x n, reported here for the point-sized passes only.
+        per_launch_ms = tot_ms / cnt
+        achieved = (24.0 * A) / (per_launch_ms * 1e-3) / 1e9
+        roofline = {"kernel": "radix_scatter_kernel<u64> (LSD radix sort pass, K2)", "bound": "hbm", "achieved": achieved,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                    "peak_source": peak_src, "launches_averaged": cnt,
+                    "note": "algorithmic bytes = 24 B/point/pass; average over all launches of the kernel in one "
+                            "step, including the small node-table sorts (lower bound on the per-point passes)"}
+    out = dict(base, value=value, ms_per_step=ms_per_step, dtype="f64", clocks=clocks, gpu_launches=int(launches),
+               stage_ms=stage_ms,
+               result={k: stats[k] for k in ("n_points_inserted", "n_points_alive", "n_cells", "n_leaves", "n_blocks",
+                                             "max_depth_reached", "key_bits", "device_bytes_peak")},
+               n_poses=P)
+    if roofline:
+        out["roofline"] = roofline
+    if prof and "ransac_kernel" in prof:
+        r_ms = prof["ransac_kernel"][1]
+        out["roofline_ransac"] = {"kernel": "ransac_kernel (K6)", "bound": "fp64-pipe", "ms": r_ms,
+                                  "blocks_scored": None}
+    if e2e:
+        out["e2e"] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_reference_sample(args.workload, args.cpu_sample, 1)
+        out["cpu_baseline"] = {"value": r["points"] / r["seconds"], "unit": "points/s", "cores": 1, "kind": "port",
+                               "sample": f"{r['points']} points ({r['poses']} poses) of {args.workload}: "
+                                         f"structure {r['structure_s']:.2f} s + RANSAC {r['ransac_s']:.2f} s, 1 thread"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -132,6 +132,14 @@ int ol_forest_apply_mask(ol_forest *f);
 int ol_forest_apply_pose_mask(ol_forest *f, const int32_t *pose_rank, int32_t pose_index, const uint8_t *mask_host,
                               int64_t n);
 
+/* ---- measurement support (bench.py): per-stage CUDA-event timers on the forest's stream -------
+ * ol_forest_profile(f, 1) clears and enables the timers; ol_forest_profile_read synchronises, writes
+ * one line "stage_name launches total_ms" per stage into buf and clears the records.
+ * ol_launch_count: kernels launched by this library in this process so far. */
+int ol_forest_profile(ol_forest *f, int32_t enable);
+int ol_forest_profile_read(ol_forest *f, char *buf, int64_t buf_len, int64_t *out_len);
+uint64_t ol_launch_count(void);
+
 /* ---- counters: Grid.n_leaves / n_points / n_nodes, grid/grid.py:343-362 ---------------------- */
 int ol_forest_stats_get(ol_forest *f, ol_forest_stats *out);
 /* out[p] = {n_leaves, n_points, n_nodes} for pose index p, [n_poses][3] int64 */

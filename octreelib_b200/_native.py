@@ -65,6 +65,9 @@ SIGNATURES = {
     "ol_forest_ransac": (C.c_int, [_p, _p, _i32, _i32, _f64, _p, _i32, _i32, _u32]),
     "ol_forest_apply_mask": (C.c_int, [_p]),
     "ol_forest_apply_pose_mask": (C.c_int, [_p, _p, _i32, _p, _i64]),
+    "ol_forest_profile": (C.c_int, [_p, _i32]),
+    "ol_forest_profile_read": (C.c_int, [_p, C.c_char_p, _i64, C.POINTER(_i64)]),
+    "ol_launch_count": (_u64, []),
     "ol_forest_stats_get": (C.c_int, [_p, C.POINTER(ForestStats)]),
     "ol_forest_pose_counts": (C.c_int, [_p, _p]),
     "ol_forest_export_cells": (C.c_int, [_p, _p, _p, _p, _p, _p]),

@@ -1,4 +1,5 @@
 // extern "C" entry points of liboctreelib_b200 (declared in include/octreelib_b200.h).
+#include <algorithm>
 #include <new>
 
 #include "forest.cuh"
@@ -10,6 +11,7 @@ struct ol_forest {
 };
 
 namespace ol {
+unsigned long long g_launch_count = 0;
 static thread_local std::string g_last_error;
 void set_last_error(int code, const std::string& msg) { g_last_error = "[ol_status " + std::to_string(code) + "] " + msg; }
 }  // namespace ol
@@ -123,6 +125,30 @@ int ol_forest_apply_pose_mask(ol_forest* f, const int32_t* pose_rank, int32_t po
     f->impl.apply_pose_mask(pose_rank, pose_index, mask_host, n);
     OL_API_END
 }
+
+int ol_forest_profile(ol_forest* f, int32_t enable) {
+    OL_NEED(f);
+    OL_API_BEGIN
+    f->impl.ctx.sync();
+    f->impl.prof.clear();
+    f->impl.prof.enabled = enable != 0;
+    OL_API_END
+}
+
+int ol_forest_profile_read(ol_forest* f, char* buf, int64_t buf_len, int64_t* out_len) {
+    OL_NEED(f);
+    OL_API_BEGIN
+    std::string rep = f->impl.profile_report();
+    if (out_len) *out_len = (int64_t)rep.size();
+    if (buf && buf_len > 0) {
+        size_t n = std::min<size_t>(rep.size(), (size_t)buf_len - 1);
+        memcpy(buf, rep.data(), n);
+        buf[n] = 0;
+    }
+    OL_API_END
+}
+
+uint64_t ol_launch_count(void) { return ol::g_launch_count; }
 
 int ol_forest_stats_get(ol_forest* f, ol_forest_stats* out) {
     OL_NEED(f);

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/octreelib_b200.h"
 
@@ -30,7 +31,13 @@ void set_last_error(int code, const std::string& msg);
         }                                                                                          \
     } while (0)
 
-#define OL_CHECK_LAUNCH() OL_CUDA(cudaGetLastError())
+// every kernel launch in the library is followed by OL_CHECK_LAUNCH(): it also counts launches
+extern unsigned long long g_launch_count;
+#define OL_CHECK_LAUNCH()            \
+    do {                             \
+        ++::ol::g_launch_count;      \
+        OL_CUDA(cudaGetLastError()); \
+    } while (0)
 
 #define OL_REQUIRE(cond, code, text)                 \
     do {                                             \
@@ -47,6 +54,40 @@ enum DevErr : uint32_t {
 };
 
 // ---------------------------------------------------------------------------------------------
+// optional per-stage timing with CUDA events on the work stream (enabled by ol_forest_profile)
+// ---------------------------------------------------------------------------------------------
+struct Profiler {
+    struct Rec {
+        const char* name;
+        cudaEvent_t a, b;
+    };
+    bool enabled = false;
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get_event() {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void clear() {
+        for (auto& r : recs) {
+            pool.push_back(r.a);
+            pool.push_back(r.b);
+        }
+        recs.clear();
+    }
+    ~Profiler() {
+        clear();
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // execution context: stream + allocator callbacks (the host binding passes torch's caching
 // allocator; NULL callbacks fall back to cudaMallocAsync / cudaFreeAsync on the stream).
 // ---------------------------------------------------------------------------------------------
@@ -56,6 +97,7 @@ struct Ctx {
     ol_free_fn free_fn = nullptr;
     void* alloc_user = nullptr;
     uint32_t* d_err = nullptr;  // device error word
+    Profiler* prof = nullptr;
     int num_sms = 148;
     size_t bytes_live = 0, bytes_peak = 0;
 
@@ -82,6 +124,27 @@ struct Ctx {
             cudaFreeAsync(p, stream);
     }
     void sync() { OL_CUDA(cudaStreamSynchronize(stream)); }
+};
+
+// times everything enqueued on the stream between construction and destruction under `name`
+struct ProfScope {
+    Ctx& c;
+    Profiler::Rec rec{};
+    bool on;
+    ProfScope(Ctx& ctx, const char* name) : c(ctx), on(ctx.prof && ctx.prof->enabled) {
+        if (on) {
+            rec.name = name;
+            rec.a = c.prof->get_event();
+            rec.b = c.prof->get_event();
+            cudaEventRecord(rec.a, c.stream);
+        }
+    }
+    ~ProfScope() {
+        if (on) {
+            cudaEventRecord(rec.b, c.stream);
+            c.prof->recs.push_back(rec);
+        }
+    }
 };
 
 // RAII device buffer of T, bound to a Ctx.

@@ -50,6 +50,7 @@ struct Forest {
     // ---- current tree shape and point order -----------------------------------------------------
     bool shaped = false;         // current arrays valid
     uint32_t A = 0;
+    uint32_t A_shape = 0;        // A when the shape was built (istart[] positions refer to that order)
     DevBuf<uint32_t> perm;       // [A] position -> r ; order = (cell, leaf DFS, pose, input index)
     DevBuf<uint64_t> mort;       // [A]
     DevBuf<uint32_t> leaf_of;    // [A] position -> leaf (DFS index)
@@ -90,6 +91,8 @@ struct Forest {
     DevBuf<int32_t> res_pose, res_leaf, res_size, res_best, res_count;  // [res_n]
     DevBuf<float> res_plane;     // [res_n][4]
     bool sample_oob_seen = false;
+    uint32_t last_ransac_work = 0;  // blocks scored by the last RANSAC launch
+    Profiler prof;
 
     explicit Forest(const ol_forest_config& c);
     ~Forest();
@@ -114,6 +117,7 @@ struct Forest {
     void apply_pose_mask(const int32_t* pose_rank, int pose, const uint8_t* mask_host, int64_t n);
     void pose_counts(int64_t* out_host);
     void stats(ol_forest_stats* s);
+    std::string profile_report();  // "name count total_ms" per line; clears the records
     void export_cells(int64_t* q, double* corner, int32_t* first_pose, int64_t* n_nodes, int64_t* leaf_begin);
     void export_cell_poses(int32_t* cell, int32_t* pose);
     void export_leaves(double* corner, double* edge, int32_t* cell, int32_t* depth);

@@ -20,6 +20,7 @@ Forest::Forest(const ol_forest_config& c) : cfg(c) {
     d_err.reset(ctx, 1);
     d_err.zero();
     ctx.d_err = d_err.get();
+    ctx.prof = &prof;
     long long init[6] = {LLONG_MAX, LLONG_MAX, LLONG_MAX, LLONG_MIN, LLONG_MIN, LLONG_MIN};
     OL_CUDA(cudaMemcpyAsync(d_bbox.get(), init, sizeof(init), cudaMemcpyHostToDevice, ctx.stream));
     OL_CUDA(cudaMallocHost(&pinned, 256));
@@ -95,8 +96,11 @@ int Forest::insert(const double* xyz, int64_t n, bool on_device, const int64_t* 
                                 ctx.stream));
         OL_CUDA(cudaMemsetAsync(alive_r.get() + N, 1, (size_t)n, ctx.stream));
         unsigned g = std::min<unsigned>(nblk((size_t)n), (unsigned)ctx.num_sms * 8);
-        bbox_kernel<<<g, 256, 0, ctx.stream>>>(P64.get() + N * 3, (size_t)n, d_bbox.get(), d_err.get());
-        OL_CHECK_LAUNCH();
+        {
+            ProfScope ps(ctx, "bbox");
+            bbox_kernel<<<g, 256, 0, ctx.stream>>>(P64.get() + N * 3, (size_t)n, d_bbox.get(), d_err.get());
+            OL_CHECK_LAUNCH();
+        }
     }
     int pose_index;
     if (n_segments <= 0) {
@@ -187,9 +191,12 @@ void Forest::build() {
     }
     DevBuf<uint64_t> keys0(ctx, n), keys1(ctx, n), mort_r(ctx, n);
     DevBuf<uint32_t> vals0(ctx, n), vals1(ctx, n);
-    keygen_kernel<<<nblk(n), 256, 0, ctx.stream>>>(P64.get(), n, kp, d_seg_start.get(), d_seg_pose.get(), S, keys0.get(),
-                                                   mort_r.get(), d_err.get());
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "keygen");
+        keygen_kernel<<<nblk(n), 256, 0, ctx.stream>>>(P64.get(), n, kp, d_seg_start.get(), d_seg_pose.get(), S, keys0.get(),
+                                                       mort_r.get(), d_err.get());
+        OL_CHECK_LAUNCH();
+    }
     iota_kernel<<<nblk(n), 256, 0, ctx.stream>>>(vals0.get(), n, 0);
     OL_CHECK_LAUNCH();
     int which = radix_sort_pairs<uint64_t>(ctx, keys0.get(), keys1.get(), vals0.get(), vals1.get(), n, 0, key_bits);
@@ -201,39 +208,54 @@ void Forest::build() {
     vals1.release();
     perm0.swap(vals0);
     mort0.reset(ctx, n);
-    gather_kernel<uint64_t><<<nblk(n), 256, 0, ctx.stream>>>(mort0.get(), mort_r.get(), perm0.get(), n);
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "gather_morton");
+        gather_kernel<uint64_t><<<nblk(n), 256, 0, ctx.stream>>>(mort0.get(), mort_r.get(), perm0.get(), n);
+        OL_CHECK_LAUNCH();
+    }
     mort_r.release();
 
     // cells
     DevBuf<uint32_t> flags(ctx, n), scan(ctx, n);
     DevBuf<unsigned long long> d_total(ctx, 1);
-    cell_heads_kernel<<<nblk(n), 256, 0, ctx.stream>>>(keys0.get(), n, kp.pose_bits, flags.get());
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "cells");
+        cell_heads_kernel<<<nblk(n), 256, 0, ctx.stream>>>(keys0.get(), n, kp.pose_bits, flags.get());
+        OL_CHECK_LAUNCH();
+    }
     exclusive_scan_u32(ctx, flags.get(), scan.get(), n, d_total.get());
     C = (uint32_t)read_u64(d_total.get());
     cellidx0.reset(ctx, n);
     cell_key.reset(ctx, C);
     cell_start0.reset(ctx, (size_t)C + 1);
-    cell_emit_kernel<<<nblk(n), 256, 0, ctx.stream>>>(keys0.get(), flags.get(), scan.get(), n, kp.pose_bits, cellidx0.get(),
-                                                      cell_key.get(), cell_start0.get());
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "cells");
+        cell_emit_kernel<<<nblk(n), 256, 0, ctx.stream>>>(keys0.get(), flags.get(), scan.get(), n, kp.pose_bits, cellidx0.get(),
+                                                          cell_key.get(), cell_start0.get());
+        OL_CHECK_LAUNCH();
+    }
     OL_CUDA(cudaMemcpyAsync(cell_start0.get() + C, &n, 4, cudaMemcpyHostToDevice, ctx.stream));
     keys0.release();
 
     // (cell, pose) pairs that own an octree (octree_manager.py:166-169)
     DevBuf<int32_t> pose_of_pos(ctx, n);
-    cp_heads_kernel<<<nblk(n), 256, 0, ctx.stream>>>(cellidx0.get(), perm0.get(), d_seg_start.get(), d_seg_pose.get(), S, n,
-                                                     flags.get(), pose_of_pos.get());
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "cell_poses");
+        cp_heads_kernel<<<nblk(n), 256, 0, ctx.stream>>>(cellidx0.get(), perm0.get(), d_seg_start.get(), d_seg_pose.get(), S, n,
+                                                         flags.get(), pose_of_pos.get());
+        OL_CHECK_LAUNCH();
+    }
     exclusive_scan_u32(ctx, flags.get(), scan.get(), n, d_total.get());
     CP = (uint32_t)read_u64(d_total.get());
     cp_cell.reset(ctx, CP);
     cp_pose.reset(ctx, CP);
     cell_first_pose.reset(ctx, C);
-    cp_emit_kernel<<<nblk(n), 256, 0, ctx.stream>>>(cellidx0.get(), pose_of_pos.get(), flags.get(), scan.get(), n,
-                                                    cp_cell.get(), cp_pose.get(), cell_first_pose.get());
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "cell_poses");
+        cp_emit_kernel<<<nblk(n), 256, 0, ctx.stream>>>(cellidx0.get(), pose_of_pos.get(), flags.get(), scan.get(), n,
+                                                        cp_cell.get(), cp_pose.get(), cell_first_pose.get());
+        OL_CHECK_LAUNCH();
+    }
     check_device_errors();
     built = true;
     base_dirty = any_dead;  // points removed before a rebuild are dropped from the base order lazily
@@ -246,17 +268,26 @@ void Forest::compact_base() {
     if (n) {
         DevBuf<uint32_t> flags(ctx, n), scan(ctx, n);
         DevBuf<unsigned long long> d_total(ctx, 1);
-        alive_flags_kernel<<<nblk(n), 256, 0, ctx.stream>>>(alive_r.get(), perm0.get(), n, flags.get());
-        OL_CHECK_LAUNCH();
+        {
+            ProfScope ps(ctx, "compact");
+            alive_flags_kernel<<<nblk(n), 256, 0, ctx.stream>>>(alive_r.get(), perm0.get(), n, flags.get());
+            OL_CHECK_LAUNCH();
+        }
         exclusive_scan_u32(ctx, flags.get(), scan.get(), n, d_total.get());
         uint32_t total = (uint32_t)read_u64(d_total.get());
         DevBuf<uint32_t> p2(ctx, total), c2(ctx, total), s2(ctx, (size_t)C + 1);
         DevBuf<uint64_t> m2(ctx, total);
-        compact_pos_kernel<<<nblk(n), 256, 0, ctx.stream>>>(flags.get(), scan.get(), n, perm0.get(), mort0.get(),
-                                                            cellidx0.get(), p2.get(), m2.get(), c2.get(), nullptr);
-        OL_CHECK_LAUNCH();
-        remap_starts_kernel<<<nblk((size_t)C + 1), 256, 0, ctx.stream>>>(cell_start0.get(), scan.get(), C, n, total, s2.get());
-        OL_CHECK_LAUNCH();
+        {
+            ProfScope ps(ctx, "compact");
+            compact_pos_kernel<<<nblk(n), 256, 0, ctx.stream>>>(flags.get(), scan.get(), n, perm0.get(), mort0.get(),
+                                                                cellidx0.get(), p2.get(), m2.get(), c2.get(), nullptr);
+            OL_CHECK_LAUNCH();
+        }
+        {
+            ProfScope ps(ctx, "compact");
+            remap_starts_kernel<<<nblk((size_t)C + 1), 256, 0, ctx.stream>>>(cell_start0.get(), scan.get(), C, n, total, s2.get());
+            OL_CHECK_LAUNCH();
+        }
         perm0.swap(p2);
         mort0.swap(m2);
         cellidx0.swap(c2);
@@ -271,6 +302,7 @@ void Forest::reset_shape() {
     build();
     compact_base();
     A = A0;
+    A_shape = A0;
     L = C;
     I = 0;
     depth_reached = 0;
@@ -343,15 +375,21 @@ void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t ta
         if (n_listed > 0) {
             wcount.reset(ctx, L);
             wcount.zero();
-            weighted_count_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), perm.get(), ldepth.get(), level,
-                                                                   d_seg_start.get(), d_seg_pose.get(), S, listed.get(), A,
-                                                                   wcount.get());
+            {
+                ProfScope ps(ctx, "weighted_count");
+                weighted_count_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), perm.get(), ldepth.get(), level,
+                                                                       d_seg_start.get(), d_seg_pose.get(), S, listed.get(), A,
+                                                                       wcount.get());
+                OL_CHECK_LAUNCH();
+            }
+        }
+        {
+            ProfScope ps(ctx, "part_decide");
+            decide_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, lstart.get(), ldepth.get(), level, wcount.get(), max_points,
+                                                           table.get(), table_len, beyond, max_depth, splitf.get(),
+                                                           expand.get(), d_err.get());
             OL_CHECK_LAUNCH();
         }
-        decide_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, lstart.get(), ldepth.get(), level, wcount.get(), max_points,
-                                                       table.get(), table_len, beyond, max_depth, splitf.get(),
-                                                       expand.get(), d_err.get());
-        OL_CHECK_LAUNCH();
         exclusive_scan_u32(ctx, expand.get(), newidx.get(), L, d_tot.get());
         exclusive_scan_u32(ctx, splitf.get(), iidx.get(), L, d_tot.get() + 1);
         unsigned long long tot[2];
@@ -366,19 +404,28 @@ void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t ta
         DevBuf<uint32_t> Sbeg(ctx, (size_t)n_split * 8), Send(ctx, (size_t)n_split * 8);
         Sbeg.zero();
         Send.zero();
-        part_hist_kernel<<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), mort.get(), splitf.get(), A, tiles, shift,
-                                                                 tile_hist.get());
-        OL_CHECK_LAUNCH();
+        {
+            ProfScope ps(ctx, "part_hist");
+            part_hist_kernel<<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), mort.get(), splitf.get(), A, tiles, shift,
+                                                                     tile_hist.get());
+            OL_CHECK_LAUNCH();
+        }
         exclusive_scan_u32(ctx, tile_hist.get(), tile_hist.get(), (size_t)8 * tiles, nullptr);
-        part_rank_kernel<<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), mort.get(), splitf.get(), iidx.get(),
-                                                                 lstart.get(), tile_hist.get(), A, tiles, shift, rank.get(),
-                                                                 Sbeg.get(), Send.get());
-        OL_CHECK_LAUNCH();
-        part_scatter_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), mort.get(), perm.get(), splitf.get(), iidx.get(),
-                                                             newidx.get(), lstart.get(), rank.get(), Sbeg.get(), Send.get(), A,
-                                                             shift, level, leaf_b.get(), mort_b.get(), perm_b.get(), P64.get(),
-                                                             lcell.get(), cell_key.get(), kp, d_err.get());
-        OL_CHECK_LAUNCH();
+        {
+            ProfScope ps(ctx, "part_rank");
+            part_rank_kernel<<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), mort.get(), splitf.get(), iidx.get(),
+                                                                     lstart.get(), tile_hist.get(), A, tiles, shift, rank.get(),
+                                                                     Sbeg.get(), Send.get());
+            OL_CHECK_LAUNCH();
+        }
+        {
+            ProfScope ps(ctx, "part_scatter");
+            part_scatter_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), mort.get(), perm.get(), splitf.get(), iidx.get(),
+                                                                 newidx.get(), lstart.get(), rank.get(), Sbeg.get(), Send.get(), A,
+                                                                 shift, level, leaf_b.get(), mort_b.get(), perm_b.get(), P64.get(),
+                                                                 lcell.get(), cell_key.get(), kp, d_err.get());
+            OL_CHECK_LAUNCH();
+        }
         // new leaf / internal tables
         DevBuf<uint32_t> lstart_n(ctx, (size_t)L_new + 1), lcell_n(ctx, L_new), istart_n(ctx, (size_t)I + n_split),
             icell_n(ctx, (size_t)I + n_split);
@@ -388,12 +435,15 @@ void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t ta
         d2d(ctx, istart_n.get(), istart.get(), I);
         d2d(ctx, icell_n.get(), icell.get(), I);
         d2d(ctx, idepth_n.get(), idepth.get(), I);
-        expand_leaves_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, A, I, splitf.get(), iidx.get(), newidx.get(), Sbeg.get(),
-                                                              Send.get(), lstart.get(), lcell.get(), lparent.get(), lpath.get(),
-                                                              ldepth.get(), lchild.get(), L_new, lstart_n.get(), lcell_n.get(),
-                                                              lparent_n.get(), lpath_n.get(), ldepth_n.get(), lchild_n.get(),
-                                                              istart_n.get(), icell_n.get(), idepth_n.get());
-        OL_CHECK_LAUNCH();
+        {
+            ProfScope ps(ctx, "part_expand");
+            expand_leaves_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, A, I, splitf.get(), iidx.get(), newidx.get(), Sbeg.get(),
+                                                                  Send.get(), lstart.get(), lcell.get(), lparent.get(), lpath.get(),
+                                                                  ldepth.get(), lchild.get(), L_new, lstart_n.get(), lcell_n.get(),
+                                                                  lparent_n.get(), lpath_n.get(), ldepth_n.get(), lchild_n.get(),
+                                                                  istart_n.get(), icell_n.get(), idepth_n.get());
+            OL_CHECK_LAUNCH();
+        }
         lstart.swap(lstart_n);
         lcell.swap(lcell_n);
         lparent.swap(lparent_n);
@@ -438,19 +488,28 @@ void Forest::ensure_order() {
     if (I) {
         DevBuf<uint64_t> k0(ctx, I), k1(ctx, I);
         DevBuf<uint32_t> v0(ctx, I), v1(ctx, I);
-        internal_keys_kernel<<<nblk(I), 256, 0, ctx.stream>>>(I, istart.get(), idepth.get(), k0.get(), v0.get());
-        OL_CHECK_LAUNCH();
-        int w = radix_sort_pairs<uint64_t>(ctx, k0.get(), k1.get(), v0.get(), v1.get(), I, 0, 8 + bit_length_u64(A));
-        internal_rank_kernel<<<nblk(I), 256, 0, ctx.stream>>>(I, w ? v1.get() : v0.get(), idepth.get(), icell.get(), irank.get(),
-                                                              cell_ifirst.get());
-        OL_CHECK_LAUNCH();
+        {
+            ProfScope ps(ctx, "leaf_order");
+            internal_keys_kernel<<<nblk(I), 256, 0, ctx.stream>>>(I, istart.get(), idepth.get(), k0.get(), v0.get());
+            OL_CHECK_LAUNCH();
+        }
+        int w = radix_sort_pairs<uint64_t>(ctx, k0.get(), k1.get(), v0.get(), v1.get(), I, 0, 8 + bit_length_u64(A_shape));
+        {
+            ProfScope ps(ctx, "leaf_order");
+            internal_rank_kernel<<<nblk(I), 256, 0, ctx.stream>>>(I, w ? v1.get() : v0.get(), idepth.get(), icell.get(), irank.get(),
+                                                                  cell_ifirst.get());
+            OL_CHECK_LAUNCH();
+        }
     }
     {
         DevBuf<uint64_t> k0(ctx, L), k1(ctx, L);
         DevBuf<uint32_t> v0(ctx, L), v1(ctx, L);
-        leaf_keys_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, lcell.get(), lparent.get(), lchild.get(), irank.get(),
-                                                          cell_ifirst.get(), k0.get(), v0.get());
-        OL_CHECK_LAUNCH();
+        {
+            ProfScope ps(ctx, "leaf_order");
+            leaf_keys_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, lcell.get(), lparent.get(), lchild.get(), irank.get(),
+                                                              cell_ifirst.get(), k0.get(), v0.get());
+            OL_CHECK_LAUNCH();
+        }
         // low field: (#internal nodes of a cell) * 8 fits in 3 + bit_length(I) bits; cell index above bit 32
         int low_bits = 3 + bit_length_u64(I);
         int w = radix_sort_pairs<uint64_t>(ctx, k0.get(), k1.get(), v0.get(), v1.get(), L, 0, low_bits);
@@ -461,10 +520,13 @@ void Forest::ensure_order() {
         int w2 = radix_sort_pairs<uint64_t>(ctx, ka, kb, va, vb, L, 32, 32 + bit_length_u64(C ? C - 1 : 0));
         d2d(ctx, leaf_by_cache.get(), w2 ? vb : va, L);
     }
-    leaf_geometry_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, leaf_by_cache.get(), lcell.get(), lpath.get(), ldepth.get(),
-                                                          cell_key.get(), kp, cache_rank.get(), leaf_corner.get(),
-                                                          leaf_edge.get(), cell_leaf_begin.get());
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "leaf_order");
+        leaf_geometry_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, leaf_by_cache.get(), lcell.get(), lpath.get(), ldepth.get(),
+                                                              cell_key.get(), kp, cache_rank.get(), leaf_corner.get(),
+                                                              leaf_edge.get(), cell_leaf_begin.get());
+        OL_CHECK_LAUNCH();
+    }
     OL_CUDA(cudaMemcpyAsync(cell_leaf_begin.get() + C, &L, 4, cudaMemcpyHostToDevice, ctx.stream));
     ctx.sync();
     order_valid = true;
@@ -491,22 +553,31 @@ void Forest::ensure_blocks() {
     DevBuf<uint32_t> flags(ctx, A), scan(ctx, A);
     DevBuf<int32_t> pose_of_pos(ctx, A);
     DevBuf<unsigned long long> d_total(ctx, 1);
-    block_heads_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), perm.get(), d_seg_start.get(), d_seg_pose.get(), S, A,
-                                                        flags.get(), pose_of_pos.get());
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "blocks");
+        block_heads_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), perm.get(), d_seg_start.get(), d_seg_pose.get(), S, A,
+                                                            flags.get(), pose_of_pos.get());
+        OL_CHECK_LAUNCH();
+    }
     exclusive_scan_u32(ctx, flags.get(), scan.get(), A, d_total.get());
     NB = (uint32_t)read_u64(d_total.get());
     blk_start.reset(ctx, (size_t)NB + 1);
     blk_leaf.reset(ctx, NB);
     blk_pose.reset(ctx, NB);
-    block_emit_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), pose_of_pos.get(), flags.get(), scan.get(), A,
-                                                       blk_of_pos.get(), blk_start.get(), blk_leaf.get(), blk_pose.get());
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "blocks");
+        block_emit_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), pose_of_pos.get(), flags.get(), scan.get(), A,
+                                                           blk_of_pos.get(), blk_start.get(), blk_leaf.get(), blk_pose.get());
+        OL_CHECK_LAUNCH();
+    }
     OL_CUDA(cudaMemcpyAsync(blk_start.get() + NB, &A, 4, cudaMemcpyHostToDevice, ctx.stream));
     DevBuf<uint32_t> d_max(ctx, 1);
     d_max.zero();
-    block_max_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(blk_start.get(), NB, d_max.get());
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "blocks");
+        block_max_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(blk_start.get(), NB, d_max.get());
+        OL_CHECK_LAUNCH();
+    }
     max_block = read_u32(d_max.get());
     blocks_valid = true;
 }
@@ -519,18 +590,27 @@ void Forest::apply_keep(const uint8_t* keep_pos) {
     if (n == 0) return;
     DevBuf<uint32_t> flags(ctx, n), scan(ctx, n);
     DevBuf<unsigned long long> d_total(ctx, 1);
-    keep_to_u32_kernel<<<nblk(n), 256, 0, ctx.stream>>>(keep_pos, n, flags.get());
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "compact");
+        keep_to_u32_kernel<<<nblk(n), 256, 0, ctx.stream>>>(keep_pos, n, flags.get());
+        OL_CHECK_LAUNCH();
+    }
     exclusive_scan_u32(ctx, flags.get(), scan.get(), n, d_total.get());
     const uint32_t total = (uint32_t)read_u64(d_total.get());
     if (total == n) return;
     DevBuf<uint32_t> p2(ctx, total), l2(ctx, total), s2(ctx, (size_t)L + 1);
     DevBuf<uint64_t> m2(ctx, total);
-    compact_pos_kernel<<<nblk(n), 256, 0, ctx.stream>>>(flags.get(), scan.get(), n, perm.get(), mort.get(), leaf_of.get(),
-                                                        p2.get(), m2.get(), l2.get(), alive_r.get());
-    OL_CHECK_LAUNCH();
-    remap_starts_kernel<<<nblk((size_t)L + 1), 256, 0, ctx.stream>>>(lstart.get(), scan.get(), L, n, total, s2.get());
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "compact");
+        compact_pos_kernel<<<nblk(n), 256, 0, ctx.stream>>>(flags.get(), scan.get(), n, perm.get(), mort.get(), leaf_of.get(),
+                                                            p2.get(), m2.get(), l2.get(), alive_r.get());
+        OL_CHECK_LAUNCH();
+    }
+    {
+        ProfScope ps(ctx, "compact");
+        remap_starts_kernel<<<nblk((size_t)L + 1), 256, 0, ctx.stream>>>(lstart.get(), scan.get(), L, n, total, s2.get());
+        OL_CHECK_LAUNCH();
+    }
     perm.swap(p2);
     mort.swap(m2);
     leaf_of.swap(l2);

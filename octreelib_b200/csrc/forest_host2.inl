@@ -192,9 +192,12 @@ void Forest::compute_ref_order(const int32_t* pose_rank_host, DevBuf<uint32_t>& 
     if (NB == 0) return;
     DevBuf<uint64_t> k0(ctx, NB), k1(ctx, NB);
     DevBuf<uint32_t> v0(ctx, NB), v1(ctx, NB);
-    block_refkey_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_pose.get(), blk_leaf.get(), d_pose_rank.get(),
-                                                          cache_rank.get(), k0.get(), v0.get());
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "ransac_prep");
+        block_refkey_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_pose.get(), blk_leaf.get(), d_pose_rank.get(),
+                                                              cache_rank.get(), k0.get(), v0.get());
+        OL_CHECK_LAUNCH();
+    }
     int w = radix_sort_pairs<uint64_t>(ctx, k0.get(), k1.get(), v0.get(), v1.get(), NB, 0, bit_length_u64(L));
     uint64_t* ka = w ? k1.get() : k0.get();
     uint64_t* kb = w ? k0.get() : k1.get();
@@ -240,27 +243,45 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
     DevBuf<long long> blk_ref_start(ctx, NB);
     DevBuf<unsigned long long> d_total(ctx, 1);
     batch_base.zero();
-    block_sizes_ref_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_start.get(), sizes_ref.get(), refpos.get(),
-                                                             blk_size.get());
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "ransac_prep");
+        block_sizes_ref_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_start.get(), sizes_ref.get(), refpos.get(),
+                                                                 blk_size.get());
+        OL_CHECK_LAUNCH();
+    }
     exclusive_scan_u32(ctx, sizes_ref.get(), refstart.get(), NB, nullptr);
-    batch_base_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), d_pose_rank.get(), ppb,
-                                                        refstart.get(), batch_base.get());
-    OL_CHECK_LAUNCH();
-    block_refstart_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), d_pose_rank.get(), ppb,
-                                                            refstart.get(), batch_base.get(), blk_ref_start.get());
-    OL_CHECK_LAUNCH();
-    work_flags_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_size.get(), K, wflags.get());
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "ransac_prep");
+        batch_base_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), d_pose_rank.get(), ppb,
+                                                            refstart.get(), batch_base.get());
+        OL_CHECK_LAUNCH();
+    }
+    {
+        ProfScope ps(ctx, "ransac_prep");
+        block_refstart_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), d_pose_rank.get(), ppb,
+                                                                refstart.get(), batch_base.get(), blk_ref_start.get());
+        OL_CHECK_LAUNCH();
+    }
+    {
+        ProfScope ps(ctx, "ransac_prep");
+        work_flags_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_size.get(), K, wflags.get());
+        OL_CHECK_LAUNCH();
+    }
     exclusive_scan_u32(ctx, wflags.get(), wscan.get(), NB, d_total.get());
     const uint32_t n_work = (uint32_t)read_u64(d_total.get());
     DevBuf<uint32_t> work(ctx, n_work);
-    work_emit_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, wflags.get(), wscan.get(), work.get());
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "ransac_prep");
+        work_emit_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, wflags.get(), wscan.get(), work.get());
+        OL_CHECK_LAUNCH();
+    }
     // K5b: gather the points into leaf order so that every block is one contiguous float64 run
     DevBuf<double> pleaf(ctx, (size_t)A * 3 + 2);
-    gather_points_kernel<<<nblk(A), 256, 0, ctx.stream>>>(A, P64.get(), perm.get(), pleaf.get());
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "gather_points");
+        gather_points_kernel<<<nblk(A), 256, 0, ctx.stream>>>(A, P64.get(), perm.get(), pleaf.get());
+        OL_CHECK_LAUNCH();
+    }
     DevBuf<double> table(ctx, (size_t)H * K);
     h2d(ctx, table.get(), table_host, (size_t)H * K);
     DevBuf<float> plane(ctx, (size_t)NB * 4);
@@ -269,13 +290,20 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
     best_count.zero();
     fill_kernel<int32_t><<<nblk(NB), 256, 0, ctx.stream>>>(best.get(), NB, -1);
     OL_CHECK_LAUNCH();
-    launch_ransac(ctx, pleaf.get(), A, blk_start.get(), blk_size.get(), blk_ref_start.get(), work.get(), n_work, max_block,
-                  table.get(), H, K, threshold, mask.get(), plane.get(), best.get(), best_count.get(), flags);
-    ransac_snapshot_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), blk_leaf.get(), cache_rank.get(),
-                                                             blk_size.get(), plane.get(), best.get(), best_count.get(),
-                                                             res_pose.get(), res_leaf.get(), res_size.get(), res_plane.get(),
-                                                             res_best.get(), res_count.get());
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "ransac_kernel");
+        launch_ransac(ctx, pleaf.get(), A, blk_start.get(), blk_size.get(), blk_ref_start.get(), work.get(), n_work, max_block,
+                      table.get(), H, K, threshold, mask.get(), plane.get(), best.get(), best_count.get(), flags);
+    }
+    last_ransac_work = n_work;
+    {
+        ProfScope ps(ctx, "ransac_prep");
+        ransac_snapshot_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), blk_leaf.get(), cache_rank.get(),
+                                                                 blk_size.get(), plane.get(), best.get(), best_count.get(),
+                                                                 res_pose.get(), res_leaf.get(), res_size.get(), res_plane.get(),
+                                                                 res_best.get(), res_count.get());
+        OL_CHECK_LAUNCH();
+    }
     // a sample index that left its block is clamped and only counted (see ransac.cu)
     uint32_t e = read_u32(d_err.get());
     if (e & DEVERR_SAMPLE_OOB) {
@@ -321,9 +349,12 @@ void Forest::apply_pose_mask(const int32_t* pose_rank, int pose, const uint8_t* 
     DevBuf<uint32_t> sizes_ref(ctx, NB), sel(ctx, NB), refpos(ctx, NB), ref_off(ctx, NB);
     DevBuf<int32_t> blk_size(ctx, NB);
     DevBuf<unsigned long long> d_total(ctx, 1);
-    block_sizes_ref_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_start.get(), sizes_ref.get(), refpos.get(),
-                                                             blk_size.get());
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "ransac_prep");
+        block_sizes_ref_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_start.get(), sizes_ref.get(), refpos.get(),
+                                                                 blk_size.get());
+        OL_CHECK_LAUNCH();
+    }
     select_blocks_ref_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), blk_start.get(), pose,
                                                                sel.get());
     OL_CHECK_LAUNCH();
@@ -383,6 +414,37 @@ void Forest::stats(ol_forest_stats* s) {
     s->max_depth_reached = depth_reached;
     s->key_bits = key_bits;
     s->device_bytes_peak = (int64_t)ctx.bytes_peak;
+}
+
+std::string Forest::profile_report() {
+    ctx.sync();
+    struct Acc {
+        const char* name;
+        int count;
+        double ms;
+    };
+    std::vector<Acc> acc;
+    for (auto& r : prof.recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        bool found = false;
+        for (auto& a : acc)
+            if (strcmp(a.name, r.name) == 0) {
+                a.count += 1;
+                a.ms += ms;
+                found = true;
+                break;
+            }
+        if (!found) acc.push_back(Acc{r.name, 1, (double)ms});
+    }
+    prof.clear();
+    std::string out;
+    char line[160];
+    for (auto& a : acc) {
+        snprintf(line, sizeof(line), "%s %d %.6f\n", a.name, a.count, a.ms);
+        out += line;
+    }
+    return out;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -446,13 +508,19 @@ void Forest::export_blocks(const int32_t* pose_rank, int32_t* pose, int32_t* lea
     if (NB == 0) return;
     DevBuf<uint32_t> sizes_ref(ctx, NB), refpos(ctx, NB);
     DevBuf<int32_t> blk_size(ctx, NB), o_pose(ctx, NB), o_leaf(ctx, NB), o_size(ctx, NB);
-    block_sizes_ref_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_start.get(), sizes_ref.get(), refpos.get(),
-                                                             blk_size.get());
-    OL_CHECK_LAUNCH();
-    ransac_snapshot_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), blk_leaf.get(), cache_rank.get(),
-                                                             blk_size.get(), nullptr, nullptr, nullptr, o_pose.get(), o_leaf.get(),
-                                                             o_size.get(), nullptr, nullptr, nullptr);
-    OL_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, "ransac_prep");
+        block_sizes_ref_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_start.get(), sizes_ref.get(), refpos.get(),
+                                                                 blk_size.get());
+        OL_CHECK_LAUNCH();
+    }
+    {
+        ProfScope ps(ctx, "ransac_prep");
+        ransac_snapshot_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), blk_leaf.get(), cache_rank.get(),
+                                                                 blk_size.get(), nullptr, nullptr, nullptr, o_pose.get(), o_leaf.get(),
+                                                                 o_size.get(), nullptr, nullptr, nullptr);
+        OL_CHECK_LAUNCH();
+    }
     copy_out(ctx, pose, o_pose.get(), NB);
     copy_out(ctx, leaf, o_leaf.get(), NB);
     copy_out(ctx, size, o_size.get(), NB);
@@ -493,9 +561,12 @@ int64_t Forest::export_points(const int32_t* pose_rank, int pose, int order, dou
         DevBuf<int32_t> blk_size(ctx, NB);
         refpos.reset(ctx, NB);
         ref_off.reset(ctx, NB);
-        block_sizes_ref_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_start.get(), sizes_ref.get(),
-                                                                 refpos.get(), blk_size.get());
-        OL_CHECK_LAUNCH();
+        {
+            ProfScope ps(ctx, "ransac_prep");
+            block_sizes_ref_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_start.get(), sizes_ref.get(),
+                                                                     refpos.get(), blk_size.get());
+            OL_CHECK_LAUNCH();
+        }
         select_blocks_ref_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), blk_start.get(), pose,
                                                                    sel.get());
         OL_CHECK_LAUNCH();

@@ -179,6 +179,23 @@ class Forest:
             N.check(self._lib.ol_forest_apply_pose_mask(self._h, None, int(pose_index), _ptr(m), len(m)))
         self.version += 1
 
+    # ---- measurement ---------------------------------------------------------------------------
+    def profile(self, enable: bool = True):
+        with self._scope():
+            N.check(self._lib.ol_forest_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self) -> dict:
+        """{stage: (launch groups, total ms)} since the last read; synchronises the stream."""
+        buf = C.create_string_buffer(1 << 16)
+        n = C.c_int64(0)
+        with self._scope():
+            N.check(self._lib.ol_forest_profile_read(self._h, buf, len(buf), C.byref(n)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, count, ms = line.split()
+            out[name] = (int(count), float(ms))
+        return out
+
     # ---- queries -------------------------------------------------------------------------------
     def stats(self) -> dict:
         s = N.ForestStats()

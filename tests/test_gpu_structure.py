@@ -1,0 +1,252 @@
+"""GPU: cell membership, leaf structure, leaf order and point order of the native grid are bit-exact
+against (a) the golden vectors generated from the real reference and (b) the CPU oracle on fresh
+seeded inputs.  Also the reference's own small tests, re-pointed at this package."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from gpu_util import compare_grid_with_oracle
+from octreelib_b200.criteria import MaxPoints, MinPoints
+from octreelib_b200.grid import Grid, GridConfig
+from octreelib_b200.internal import Voxel
+from octreelib_b200.octree import Octree, OctreeConfig, OctreeNode
+from octreelib_b200.octree_manager import OctreeManager
+from octreelib_b200.synthetic import indoor_scene, lidar64_scan
+from oracle.structure import OracleGrid, max_points_criterion
+
+pytestmark = pytest.mark.gpu
+
+STRUCTURE_CASES = ["ref_test_grid_gt2", "ref_test_grid_gt3", "random_3pose_edge2", "random_3pose_edge2_filter",
+                   "clustered_2pose_edge4", "lidar_2pose_edge1", "indoor_1pose_edge1", "offset_poses_edge1"]
+
+
+def _edge(g):
+    e = float(g["edge"])
+    return int(e) if e == int(e) else e
+
+
+@pytest.mark.parametrize("name", STRUCTURE_CASES)
+def test_golden_structure(name):
+    g = golden(name)
+    poses = [int(p) for p in g["poses"]]
+    grid = Grid(GridConfig(voxel_edge_length=_edge(g)))
+    for p in poses:
+        grid.insert_points(p, g[f"cloud{p}"])
+    forest = grid._host.forest
+    # before subdivision: one leaf per cell
+    for p in poses:
+        got = forest.export_points(grid._host.pose_index[p], order=0)
+        assert (got["idx"] == g[f"pre_p{p}_idx"]).all()
+        assert [grid.n_leaves(p), grid.n_points(p), grid.n_nodes(p)] == g[f"pre_p{p}_counts"].tolist()
+    sub = [int(x) for x in g["subdivide_poses"]] or None
+    grid.subdivide([lambda pts, n=int(g["max_points"]): len(pts) > n], sub)
+    if int(g["filter_min"]) >= 0:
+        grid.filter([lambda pts, n=int(g["filter_min"]): len(pts) >= n])
+    blocks, leaves = forest.export_blocks(), forest.export_leaves()
+    for p in poses:
+        pi = grid._host.pose_index[p]
+        sel = np.flatnonzero(blocks["pose"] == pi)
+        lf = blocks["leaf"][sel]
+        assert (leaves["corner"][lf] == g[f"p{p}_corner"]).all()
+        assert (leaves["edge"][lf] == g[f"p{p}_edge"]).all()
+        assert (blocks["size"][sel] == g[f"p{p}_size"]).all()
+        got = forest.export_points(pi, order=0)
+        assert (got["idx"] == g[f"p{p}_idx"]).all()
+        assert (got["xyz"] == g[f"cloud{p}"][g[f"p{p}_idx"]]).all()
+        assert [grid.n_leaves(p), grid.n_points(p), grid.n_nodes(p)] == g[f"p{p}_counts"].tolist()
+        # Grid.get_points: cells in dict order x depth-first leaves (grid.py:234-242)
+        assert (grid.get_points(p) == g[f"cloud{p}"][g[f"p{p}_getpoints_idx"]]).all()
+        # public API objects
+        vox = grid.get_leaf_points(p)
+        assert len(vox) == len(lf)
+        for v, c, e, s in zip(vox, g[f"p{p}_corner"], g[f"p{p}_edge"], g[f"p{p}_size"]):
+            assert (np.asarray(v.corner_min, dtype=np.float64) == c).all() and float(v.edge_length) == e
+            assert v.n_points == s and v.get_points().shape == (s, 3)
+
+
+@pytest.mark.parametrize("seed,n,edge,max_points", [(0, 30000, 1, 50), (1, 60000, 2, 100), (2, 20000, 4, 5)])
+def test_oracle_parity_random(seed, n, edge, max_points):
+    rng = np.random.default_rng(seed)
+    clouds = {}
+    for p in range(3):
+        c = rng.normal(0, 3, (n // 3, 3)) * np.array([3, 2, 0.3]) + rng.integers(-2, 3, (n // 3, 1))
+        clouds[p] = c.astype(np.float32).astype(np.float64)
+    grid, og = Grid(GridConfig(voxel_edge_length=edge)), OracleGrid(edge)
+    for p, c in clouds.items():
+        grid.insert_points(p, c)
+        og.insert_points(p, c)
+    compare_grid_with_oracle(grid, og, clouds)
+    grid.subdivide([MaxPoints(max_points)])
+    og.subdivide([max_points_criterion(max_points)])
+    compare_grid_with_oracle(grid, og, clouds)
+    grid.filter([MinPoints(3)])
+    og.filter([lambda pts: len(pts) >= 3])
+    compare_grid_with_oracle(grid, og, clouds)
+    # a second, coarser subdivision after filtering rebuilds the shape from the surviving points
+    grid.subdivide([MaxPoints(max_points * 4)])
+    og2 = OracleGrid(edge)
+    for p, c in clouds.items():
+        og2.insert_points(p, c)
+    # surviving points per pose, in input order
+    for p in clouds:
+        keep = np.sort(og.get_point_indices(p))
+        assert grid.n_points(p) == len(keep)
+
+
+def test_oracle_parity_lidar_config1_like():
+    clouds = {0: lidar64_scan(0, seed=0)[:40000]}
+    grid, og = Grid(GridConfig(voxel_edge_length=1.0)), OracleGrid(1.0)
+    grid.insert_points(0, clouds[0])
+    og.insert_points(0, clouds[0])
+    grid.subdivide([lambda pts: len(pts) > 100])
+    og.subdivide([max_points_criterion(100)])
+    compare_grid_with_oracle(grid, og, clouds)
+
+
+def test_subdivide_on_pose_subset_multi_cell():
+    rng = np.random.default_rng(3)
+    clouds = {p: (rng.random((4000, 3)) * 4).astype(np.float32).astype(np.float64) for p in range(3)}
+    grid, og = Grid(GridConfig(voxel_edge_length=2)), OracleGrid(2)
+    for p, c in clouds.items():
+        grid.insert_points(p, c)
+        og.insert_points(p, c)
+    grid.subdivide([MaxPoints(40)], [0, 2])
+    og.subdivide([max_points_criterion(40)], [0, 2])
+    compare_grid_with_oracle(grid, og, clouds)
+
+
+# ---- the reference's own tests, re-pointed (test/grid/test_grid.py) --------------------------------
+def _generated_grid():
+    grid = Grid(GridConfig(voxel_edge_length=5))
+    p0 = np.array([[0, 0, 1], [0, 0, 2], [0, 0, 3], [9, 9, 8], [9, 9, 9]], dtype=float)
+    p1 = np.array([[1, 0, 1], [4, 0, 2], [0, 2, 3], [5, 9, 9], [9, 3, 8]], dtype=float)
+    grid.insert_points(0, p0)
+    grid.insert_points(1, p1)
+    return grid, [p0, p1]
+
+
+def test_ref_grid_counts():
+    grid, _ = _generated_grid()
+    assert [grid.n_leaves(0), grid.n_leaves(1)] == [2, 3]
+    assert [grid.n_points(0), grid.n_points(1)] == [5, 5]
+    assert [grid.n_nodes(0), grid.n_nodes(1)] == [2, 3]
+    grid.subdivide([lambda points: len(points) > 2])
+    assert [grid.n_leaves(0), grid.n_leaves(1)] == [4, 5]
+    assert [grid.n_points(0), grid.n_points(1)] == [5, 5]
+    assert [grid.n_nodes(0), grid.n_nodes(1)] == [26, 27]
+    grid2, _ = _generated_grid()
+    grid2.subdivide([lambda points: len(points) > 3])
+    assert [grid2.n_leaves(0), grid2.n_leaves(1)] == [3, 5]
+
+
+def test_ref_grid_get_points_and_leaf_points():
+    grid, pts = _generated_grid()
+    as_set = lambda a: set(map(str, a))  # noqa: E731
+    for p in (0, 1):
+        assert as_set(grid.get_points(p)) == as_set(pts[p])
+    l0, l1 = grid.get_leaf_points(0), grid.get_leaf_points(1)
+    assert len({l0[0].id, l0[1].id, l1[0].id, l1[1].id, l1[2].id}) == 3
+    assert {v.id for v in l0}.issubset({v.id for v in l1})
+    assert as_set(l0[0].get_points()) == as_set(pts[0][:3]) and as_set(l0[1].get_points()) == as_set(pts[0][3:])
+    assert as_set(l1[0].get_points()) == as_set(pts[1][:3]) and as_set(l1[1].get_points()) == as_set(pts[1][4:])
+    assert as_set(l1[2].get_points()) == as_set(pts[1][3:4])
+    grid.subdivide([lambda points: len(points) > 2])
+    for p in (0, 1):
+        assert as_set(grid.get_points(p)) == as_set(pts[p])
+    with pytest.raises(ValueError, match="Cannot insert points to existing pose 0"):
+        grid.insert_points(0, pts[0])
+    with pytest.raises(KeyError):
+        grid.get_leaf_points(7)
+
+
+# ---- test/octree/test_multi_pose.py ----------------------------------------------------------------
+def _multi_pose():
+    mp = OctreeManager(Octree, OctreeConfig(), np.array([0, 0, 0]), 5)
+    c0 = np.array([[0, 0, 1], [0, 0, 2], [0, 0, 3]], dtype=float)
+    c1 = np.array([[1, 0, 1], [4, 0, 2], [0, 2, 3]], dtype=float)
+    mp.insert_points(0, c0)
+    mp.insert_points(1, c1)
+    return mp, {0: c0, 1: c1}
+
+
+@pytest.mark.parametrize("crit,poses,nodes,leaves", [(2, [0], [9, 9], [2, 3]), (1, None, [33, 33], [3, 3])])
+def test_ref_multi_pose_subdivide(crit, poses, nodes, leaves):
+    mp, _ = _multi_pose()
+    assert [mp.n_nodes(0), mp.n_nodes(1), mp.n_leaves(0), mp.n_leaves(1)] == [1, 1, 1, 1]
+    mp.subdivide([lambda points: len(points) > crit], poses)
+    assert [mp.n_nodes(0), mp.n_nodes(1)] == nodes
+    assert [mp.n_leaves(0), mp.n_leaves(1)] == leaves
+
+
+def test_ref_multi_pose_leaf_voxels():
+    mp, _ = _multi_pose()
+    mp.subdivide([lambda points: len(points) > 2], [0])
+    exp0 = [Voxel(np.array([0, 0, 0]), 2.5), Voxel(np.array([0, 0, 2.5]), 2.5)]
+    exp1 = exp0 + [Voxel(np.array([2.5, 0, 0]), 2.5)]
+    assert {v.id for v in mp.get_leaf_points(pose_number=0)} == {v.id for v in exp0}
+    assert {v.id for v in mp.get_leaf_points(pose_number=1)} == {v.id for v in exp1}
+    mp2, _ = _multi_pose()
+    mp2.subdivide([lambda points: len(points) > 1], None)
+    e0 = [Voxel(np.array([0, 0, 0.625]), 0.625), Voxel(np.array([0, 0, 1.25]), 1.25), Voxel(np.array([0, 0, 2.5]), 1.25)]
+    e1 = [Voxel(np.array([0.625, 0, 0.625]), 0.625), Voxel(np.array([0, 1.25, 2.5]), 1.25), Voxel(np.array([2.5, 0, 0]), 2.5)]
+    assert {v.id for v in mp2.get_leaf_points(pose_number=0)} == {v.id for v in e0}
+    assert {v.id for v in mp2.get_leaf_points(pose_number=1)} == {v.id for v in e1}
+
+
+def test_ref_multi_pose_filter_and_points():
+    mp, clouds = _multi_pose()
+    as_set = lambda a: set(map(str, a.tolist()))  # noqa: E731
+    assert as_set(mp.get_points(0)) == as_set(clouds[0]) and as_set(mp.get_points(1)) == as_set(clouds[1])
+    assert mp.n_points(0) == 3 and mp.n_points(1) == 3
+    mp.subdivide([lambda points: len(points) > 2], [0])
+    mp.filter([lambda points: False], [0])
+    mp.filter([lambda points: True], [1])
+    assert mp.n_points(0) == 0 and mp.n_points(1) == 3
+
+
+# ---- test/octree/test_octree.py --------------------------------------------------------------------
+_CLOUD = np.array([[0, 0, 1], [0, 0, 2], [0, 0, 3], [9, 9, 8], [9, 9, 9]], dtype=float)
+
+
+def test_ref_octree():
+    octree = Octree(OctreeConfig(), np.array([0, 0, 0]), np.float64(10))
+    octree.insert_points(_CLOUD)
+    assert (_CLOUD == octree.get_points()).all()
+    octree.subdivide([lambda points: len(points) > 2])
+    assert octree.n_leaves == 3 and octree.n_points == 5
+    octree.filter([lambda points: len(points) >= 2])
+    assert octree.n_points == 4
+
+
+def test_ref_octree_node():
+    cached = []
+    node = OctreeNode(np.array([0, 0, 0]), np.float64(10), cached)
+    node.insert_points(_CLOUD)
+    node.subdivide([lambda points: len(points) > 2])
+    assert node.n_leaves == 3 and node.n_points == 5
+    node.filter([lambda points: len(points) >= 2])
+    assert node.n_points == 4
+    assert len(cached) == 15
+
+
+def test_edge_cases():
+    grid = Grid(GridConfig(voxel_edge_length=1))
+    grid.insert_points(0, np.empty((0, 3)))  # empty cloud is accepted
+    assert grid.n_points(0) == 0 and grid.get_leaf_points(0) == []
+    grid.insert_points(1, np.array([[0.5, 0.5, 0.5]]))
+    grid.subdivide([lambda p: len(p) > 1])
+    assert grid.n_leaves(1) == 1 and grid.n_nodes(1) == 1 and grid.n_nodes(0) == 0
+    # negative coordinates: x = -1e-9 lands in cell -1
+    g2 = Grid(GridConfig(voxel_edge_length=1))
+    g2.insert_points(0, np.array([[-1e-9, 1.0, 0.0], [1.0, 1.0, 0.0]]))
+    cells = g2._host.forest.export_cells()["q"]
+    assert cells.tolist() == [[-1, 1, 0], [1, 1, 0]]
+    # more coincident points than the criterion allows: the reference recurses until it crashes
+    g3 = Grid(GridConfig(voxel_edge_length=1))
+    g3.insert_points(0, np.tile(np.array([[0.3, 0.3, 0.3]]), (5, 1)))
+    with pytest.raises(RecursionError):
+        g3.subdivide([lambda p: len(p) > 2])
+    g4 = Grid(GridConfig())
+    g4.insert_points(0, np.array([[np.nan, 0, 0], [1.0, 2.0, 3.0]]))
+    with pytest.raises(ValueError, match="NaN"):
+        g4.n_points(0)
