@@ -193,7 +193,7 @@ def run_step(clouds, numbers, n_poses_total, w, world, profile=False, read_table
                                      initial_points_number=K)
     d2h = 0
     if read_tables:
-        planes = forest.export_ransac()
+        planes = forest.export_ransac(scored_only=True)
         leaves = forest.export_leaves()
         d2h = sum(a.nbytes for a in planes.values()) + sum(a.nbytes for a in leaves.values())
     stats = forest.stats()  # synchronises; the step's scalar result
@@ -363,34 +363,35 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    A = local_points if world == 1 else stats["n_points_inserted"]
-    # algorithmic bytes per launch of the dominant HBM-bound kernel:
-    # radix scatter pass over (u64 key, u32 value) pairs = read 12 B + write 12 B per point
+    # algorithmic bytes per processed element of every HBM-bound stage
+    BYTES = {"keygen": 40, "radix_hist_u64": 8, "radix_scatter_u64": 24, "scan": 12, "gather_morton": 20, "part_hist": 12,
+             "part_rank": 16, "part_scatter": 36, "gather_points": 52}
     stage_ms = {k: v[1] for k, v in (prof or {}).items()}
+    stages = {}
+    for k, (cnt, tot_ms, units) in (prof or {}).items():
+        if k in BYTES and tot_ms > 0 and units > 0:
+            gbs = BYTES[k] * units / (tot_ms * 1e-3) / 1e9
+            stages[k] = {"launches": cnt, "ms": tot_ms, "elements": units, "bytes_per_element": BYTES[k], "GB/s": gbs,
+                         "frac_of_hbm_peak": gbs / hbm_peak}
     roofline = None
-    if prof and "radix_scatter_u64" in prof:
-        cnt, tot_ms = prof["radix_scatter_u64"]
-        # launches in this stage sort arrays of different lengths; the big ones are the key sort
-        # passes over all points, which dominate; bytes are accumulated by the library-side timer
-        # per launch as 24 B x n, reported here for the point-sized passes only.
-        per_launch_ms = tot_ms / cnt
-        achieved = (24.0 * A) / (per_launch_ms * 1e-3) / 1e9
-        roofline = {"kernel": "radix_scatter_kernel<u64> (LSD radix sort pass, K2)", "bound": "hbm", "achieved": achieved,
-                    "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                    "peak_source": peak_src, "launches_averaged": cnt,
-                    "note": "algorithmic bytes = 24 B/point/pass; average over all launches of the kernel in one "
-                            "step, including the small node-table sorts (lower bound on the per-point passes)"}
+    if "radix_scatter_u64" in stages:
+        st = stages["radix_scatter_u64"]
+        roofline = {"kernel": "radix_scatter_kernel<u64> (LSD radix sort scatter pass, K2)", "bound": "hbm",
+                    "achieved": st["GB/s"], "peak": hbm_peak, "unit": "GB/s", "frac": st["frac_of_hbm_peak"], "traffic": None,
+                    "peak_source": peak_src, "launches": st["launches"],
+                    "note": "achieved = 24 B x (sum of pairs over all launches of the kernel in one step) / (sum of their "
+                            "CUDA-event durations)"}
     out = dict(base, value=value, ms_per_step=ms_per_step, dtype="f64", clocks=clocks, gpu_launches=int(launches),
-               stage_ms=stage_ms,
+               stage_ms=stage_ms, stages=stages,
                result={k: stats[k] for k in ("n_points_inserted", "n_points_alive", "n_cells", "n_leaves", "n_blocks",
                                              "max_depth_reached", "key_bits", "device_bytes_peak")},
                n_poses=P)
     if roofline:
         out["roofline"] = roofline
     if prof and "ransac_kernel" in prof:
-        r_ms = prof["ransac_kernel"][1]
-        out["roofline_ransac"] = {"kernel": "ransac_kernel (K6)", "bound": "fp64-pipe", "ms": r_ms,
-                                  "blocks_scored": None}
+        r_ms, r_blocks = prof["ransac_kernel"][1], prof["ransac_kernel"][2]
+        out["roofline_ransac"] = {"kernel": "ransac_kernel (K6)", "bound": "fp64-pipe", "ms": r_ms, "blocks_scored": r_blocks,
+                                  "hypotheses_per_s": r_blocks * H / (r_ms * 1e-3) if r_ms else None}
     if e2e:
         out["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:

@@ -164,9 +164,10 @@ int ol_forest_export_blocks(ol_forest *f, const int32_t *pose_rank, int32_t *pos
 /* the block table as it was when ol_forest_ransac last ran (before the masks were applied), same
  * order, plus per block: plane[B][4] float32, best[B] (hypothesis index, -1 = skipped because the
  * block has fewer than K points, ransac/cuda_ransac.py:96-97), best_count[B] (its inlier count).
+ * scored_only != 0 keeps only the fitted blocks (best >= 0).
  * *out_n = number of rows (pass NULL arrays first to size the buffers). */
-int ol_forest_export_ransac(ol_forest *f, int32_t *pose, int32_t *leaf, int32_t *size, float *plane, int32_t *best,
-                            int32_t *best_count, int64_t *out_n);
+int ol_forest_export_ransac(ol_forest *f, int32_t scored_only, int32_t *pose, int32_t *leaf, int32_t *size, float *plane,
+                            int32_t *best, int32_t *best_count, int64_t *out_n);
 /* points of one pose (pose_index >= 0) or of all poses (-1, pose-rank-major):
  *   order 0: block order of ol_forest_export_blocks, original input order inside a block
  *   order 1: cells lexicographic, depth-first leaf order inside a cell (octree.py:55-65)
@@ -183,6 +184,16 @@ int ol_ransac_evaluate(void *stream, const double *points_dev, int64_t n, const 
                        const double *table_dev, int32_t H, int32_t K, double threshold, uint8_t *mask_dev,
                        float *plane_dev, int32_t *best_dev, int32_t *best_count_dev, uint32_t flags,
                        ol_alloc_fn alloc, ol_free_fn free_fn, void *alloc_user);
+
+/* ---- multi-GPU routing (no counterpart in the single-process reference) --------
+ * A cell (all poses of it) is owned by rank ol_host_cell_owner(cell coordinates, world).
+ * ol_partition_by_owner reorders a rank's local cloud xyz_dev ([n][3] float64, a concatenation of
+ * n_segments runs = poses) into out_xyz_dev grouped by owner rank, stable inside (owner, run), and
+ * returns counts[owner][run] (host, int64) - the send layout of one NCCL all-to-all. */
+uint32_t ol_host_cell_owner(int64_t qx, int64_t qy, int64_t qz, uint32_t world);
+int ol_partition_by_owner(void *stream, const double *xyz_dev, int64_t n, const int64_t *seg_sizes_host, int32_t n_segments,
+                          double edge, const double corner[3], int32_t world, double *out_xyz_dev, int64_t *out_counts_host,
+                          ol_alloc_fn alloc, ol_free_fn free_fn, void *alloc_user);
 
 /* ---- primitives, exported so that tests can check them in isolation -------------------------- */
 /* stable LSD radix sort of (key, value) pairs on bits [begin_bit, end_bit); result in keys_dev/vals_dev */

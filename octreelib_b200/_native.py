@@ -74,10 +74,13 @@ SIGNATURES = {
     "ol_forest_export_cell_poses": (C.c_int, [_p, _p, _p]),
     "ol_forest_export_leaves": (C.c_int, [_p, _p, _p, _p, _p]),
     "ol_forest_export_blocks": (C.c_int, [_p, _p, _p, _p, _p]),
-    "ol_forest_export_ransac": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, C.POINTER(_i64)]),
+    "ol_forest_export_ransac": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _p, C.POINTER(_i64)]),
     "ol_forest_export_points": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, C.POINTER(_i64)]),
     "ol_ransac_evaluate": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _i32, _i32, _f64, _p, _p, _p, _p, _u32, ALLOC_FN,
                                      FREE_FN, _p]),
+    "ol_host_cell_owner": (_u32, [_i64, _i64, _i64, _u32]),
+    "ol_partition_by_owner": (C.c_int, [_p, _p, _i64, _p, _i32, _f64, C.POINTER(_f64 * 3), _i32, _p, _p, ALLOC_FN, FREE_FN,
+                                        _p]),
     "ol_sort_pairs_u64": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, ALLOC_FN, FREE_FN, _p]),
     "ol_sort_pairs_u32": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, ALLOC_FN, FREE_FN, _p]),
     "ol_exclusive_scan_u32": (C.c_int, [_p, _p, _p, _i64, C.POINTER(_u64), ALLOC_FN, FREE_FN, _p]),

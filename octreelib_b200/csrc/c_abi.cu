@@ -194,12 +194,13 @@ int ol_forest_export_blocks(ol_forest* f, const int32_t* pose_rank, int32_t* pos
     OL_API_END
 }
 
-int ol_forest_export_ransac(ol_forest* f, int32_t* pose, int32_t* leaf, int32_t* size, float* plane, int32_t* best,
-                            int32_t* best_count, int64_t* out_n) {
+int ol_forest_export_ransac(ol_forest* f, int32_t scored_only, int32_t* pose, int32_t* leaf, int32_t* size, float* plane,
+                            int32_t* best, int32_t* best_count, int64_t* out_n) {
     OL_NEED(f);
     OL_API_BEGIN
-    if (out_n) *out_n = f->impl.res_n;
-    f->impl.export_ransac(pose, leaf, size, plane, best, best_count);
+    const bool count_only = !pose && !leaf && !size && !plane && !best && !best_count;
+    int64_t n = f->impl.export_ransac(scored_only != 0, count_only, pose, leaf, size, plane, best, best_count);
+    if (out_n) *out_n = n;
     OL_API_END
 }
 

@@ -60,6 +60,7 @@ struct Profiler {
     struct Rec {
         const char* name;
         cudaEvent_t a, b;
+        double units;  // elements processed (for bytes-per-launch accounting)
     };
     bool enabled = false;
     std::vector<Rec> recs;
@@ -131,9 +132,10 @@ struct ProfScope {
     Ctx& c;
     Profiler::Rec rec{};
     bool on;
-    ProfScope(Ctx& ctx, const char* name) : c(ctx), on(ctx.prof && ctx.prof->enabled) {
+    ProfScope(Ctx& ctx, const char* name, double units = 0.0) : c(ctx), on(ctx.prof && ctx.prof->enabled) {
         if (on) {
             rec.name = name;
+            rec.units = units;
             rec.a = c.prof->get_event();
             rec.b = c.prof->get_event();
             cudaEventRecord(rec.a, c.stream);

@@ -69,12 +69,26 @@ __global__ void __launch_bounds__(256) bbox_kernel(const double* __restrict__ xy
             mx[a] = t > mx[a] ? t : mx[a];
         }
     }
-    if ((threadIdx.x & 31) == 0) {
+    // block-level reduction first: one atomic per block and bound instead of one per warp
+    __shared__ long long s_mn[8][3], s_mx[8][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            if (mn[a] != LLONG_MAX) atomicMin(&bbox[a], mn[a]);
-            if (mx[a] != LLONG_MIN) atomicMax(&bbox[3 + a], mx[a]);
+            s_mn[warp][a] = mn[a];
+            s_mx[warp][a] = mx[a];
         }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int a = threadIdx.x;
+        long long lo = s_mn[0][a], hi = s_mx[0][a];
+        for (int w = 1; w < 8; ++w) {
+            lo = s_mn[w][a] < lo ? s_mn[w][a] : lo;
+            hi = s_mx[w][a] > hi ? s_mx[w][a] : hi;
+        }
+        if (lo != LLONG_MAX) atomicMin(&bbox[a], lo);
+        if (hi != LLONG_MIN) atomicMax(&bbox[3 + a], hi);
     }
     if (bad) atomicOr(err, (uint32_t)DEVERR_NONFINITE);
 }

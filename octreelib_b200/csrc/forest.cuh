@@ -122,7 +122,8 @@ struct Forest {
     void export_cell_poses(int32_t* cell, int32_t* pose);
     void export_leaves(double* corner, double* edge, int32_t* cell, int32_t* depth);
     void export_blocks(const int32_t* pose_rank, int32_t* pose, int32_t* leaf, int32_t* size);
-    void export_ransac(int32_t* pose, int32_t* leaf, int32_t* size, float* plane, int32_t* best, int32_t* count);
+    int64_t export_ransac(bool scored_only, bool count_only, int32_t* pose, int32_t* leaf, int32_t* size, float* plane,
+                          int32_t* best, int32_t* count);
     int64_t export_points(const int32_t* pose_rank, int pose, int order, double* xyz, int64_t* idx, int32_t* cell,
                           uint8_t* mask_out);
     void check_device_errors();

@@ -95,7 +95,7 @@ int Forest::insert(const double* xyz, int64_t n, bool on_device, const int64_t* 
         OL_CUDA(cudaMemcpyAsync(P64.get() + N * 3, xyz, (size_t)n * 24, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                 ctx.stream));
         OL_CUDA(cudaMemsetAsync(alive_r.get() + N, 1, (size_t)n, ctx.stream));
-        unsigned g = std::min<unsigned>(nblk((size_t)n), (unsigned)ctx.num_sms * 8);
+        unsigned g = std::min<unsigned>(nblk((size_t)n), (unsigned)ctx.num_sms * 2);
         {
             ProfScope ps(ctx, "bbox");
             bbox_kernel<<<g, 256, 0, ctx.stream>>>(P64.get() + N * 3, (size_t)n, d_bbox.get(), d_err.get());
@@ -192,7 +192,7 @@ void Forest::build() {
     DevBuf<uint64_t> keys0(ctx, n), keys1(ctx, n), mort_r(ctx, n);
     DevBuf<uint32_t> vals0(ctx, n), vals1(ctx, n);
     {
-        ProfScope ps(ctx, "keygen");
+        ProfScope ps(ctx, "keygen", (double)n);
         keygen_kernel<<<nblk(n), 256, 0, ctx.stream>>>(P64.get(), n, kp, d_seg_start.get(), d_seg_pose.get(), S, keys0.get(),
                                                        mort_r.get(), d_err.get());
         OL_CHECK_LAUNCH();
@@ -209,7 +209,7 @@ void Forest::build() {
     perm0.swap(vals0);
     mort0.reset(ctx, n);
     {
-        ProfScope ps(ctx, "gather_morton");
+        ProfScope ps(ctx, "gather_morton", (double)n);
         gather_kernel<uint64_t><<<nblk(n), 256, 0, ctx.stream>>>(mort0.get(), mort_r.get(), perm0.get(), n);
         OL_CHECK_LAUNCH();
     }
@@ -376,7 +376,7 @@ void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t ta
             wcount.reset(ctx, L);
             wcount.zero();
             {
-                ProfScope ps(ctx, "weighted_count");
+                ProfScope ps(ctx, "weighted_count", (double)A);
                 weighted_count_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), perm.get(), ldepth.get(), level,
                                                                        d_seg_start.get(), d_seg_pose.get(), S, listed.get(), A,
                                                                        wcount.get());
@@ -405,21 +405,21 @@ void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t ta
         Sbeg.zero();
         Send.zero();
         {
-            ProfScope ps(ctx, "part_hist");
+            ProfScope ps(ctx, "part_hist", (double)A);
             part_hist_kernel<<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), mort.get(), splitf.get(), A, tiles, shift,
                                                                      tile_hist.get());
             OL_CHECK_LAUNCH();
         }
         exclusive_scan_u32(ctx, tile_hist.get(), tile_hist.get(), (size_t)8 * tiles, nullptr);
         {
-            ProfScope ps(ctx, "part_rank");
+            ProfScope ps(ctx, "part_rank", (double)A);
             part_rank_kernel<<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), mort.get(), splitf.get(), iidx.get(),
                                                                      lstart.get(), tile_hist.get(), A, tiles, shift, rank.get(),
                                                                      Sbeg.get(), Send.get());
             OL_CHECK_LAUNCH();
         }
         {
-            ProfScope ps(ctx, "part_scatter");
+            ProfScope ps(ctx, "part_scatter", (double)A);
             part_scatter_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), mort.get(), perm.get(), splitf.get(), iidx.get(),
                                                                  newidx.get(), lstart.get(), rank.get(), Sbeg.get(), Send.get(), A,
                                                                  shift, level, leaf_b.get(), mort_b.get(), perm_b.get(), P64.get(),

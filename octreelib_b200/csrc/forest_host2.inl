@@ -278,7 +278,7 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
     // K5b: gather the points into leaf order so that every block is one contiguous float64 run
     DevBuf<double> pleaf(ctx, (size_t)A * 3 + 2);
     {
-        ProfScope ps(ctx, "gather_points");
+        ProfScope ps(ctx, "gather_points", (double)A);
         gather_points_kernel<<<nblk(A), 256, 0, ctx.stream>>>(A, P64.get(), perm.get(), pleaf.get());
         OL_CHECK_LAUNCH();
     }
@@ -291,7 +291,7 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
     fill_kernel<int32_t><<<nblk(NB), 256, 0, ctx.stream>>>(best.get(), NB, -1);
     OL_CHECK_LAUNCH();
     {
-        ProfScope ps(ctx, "ransac_kernel");
+        ProfScope ps(ctx, "ransac_kernel", (double)n_work);
         launch_ransac(ctx, pleaf.get(), A, blk_start.get(), blk_size.get(), blk_ref_start.get(), work.get(), n_work, max_block,
                       table.get(), H, K, threshold, mask.get(), plane.get(), best.get(), best_count.get(), flags);
     }
@@ -421,7 +421,7 @@ std::string Forest::profile_report() {
     struct Acc {
         const char* name;
         int count;
-        double ms;
+        double ms, units;
     };
     std::vector<Acc> acc;
     for (auto& r : prof.recs) {
@@ -432,16 +432,17 @@ std::string Forest::profile_report() {
             if (strcmp(a.name, r.name) == 0) {
                 a.count += 1;
                 a.ms += ms;
+                a.units += r.units;
                 found = true;
                 break;
             }
-        if (!found) acc.push_back(Acc{r.name, 1, (double)ms});
+        if (!found) acc.push_back(Acc{r.name, 1, (double)ms, r.units});
     }
     prof.clear();
     std::string out;
     char line[160];
     for (auto& a : acc) {
-        snprintf(line, sizeof(line), "%s %d %.6f\n", a.name, a.count, a.ms);
+        snprintf(line, sizeof(line), "%s %d %.6f %.0f\n", a.name, a.count, a.ms, a.units);
         out += line;
     }
     return out;
@@ -527,14 +528,65 @@ void Forest::export_blocks(const int32_t* pose_rank, int32_t* pose, int32_t* lea
     ctx.sync();
 }
 
-void Forest::export_ransac(int32_t* pose, int32_t* leaf, int32_t* size, float* plane, int32_t* best, int32_t* count) {
-    copy_out(ctx, pose, res_pose.get(), res_n);
-    copy_out(ctx, leaf, res_leaf.get(), res_n);
-    copy_out(ctx, size, res_size.get(), res_n);
-    copy_out(ctx, plane, res_plane.get(), (size_t)res_n * 4);
-    copy_out(ctx, best, res_best.get(), res_n);
-    copy_out(ctx, count, res_count.get(), res_n);
+__global__ void scored_flags_kernel(uint32_t n, const int32_t* __restrict__ best, uint32_t* __restrict__ flags) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) flags[j] = best[j] >= 0 ? 1u : 0u;
+}
+
+__global__ void scored_compact_kernel(uint32_t n, const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan_ex,
+                                      const int32_t* __restrict__ pose, const int32_t* __restrict__ leaf,
+                                      const int32_t* __restrict__ size, const float* __restrict__ plane,
+                                      const int32_t* __restrict__ best, const int32_t* __restrict__ count,
+                                      int32_t* __restrict__ o_pose, int32_t* __restrict__ o_leaf, int32_t* __restrict__ o_size,
+                                      float* __restrict__ o_plane, int32_t* __restrict__ o_best, int32_t* __restrict__ o_count) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n || !flags[j]) return;
+    const uint32_t d = scan_ex[j];
+    o_pose[d] = pose[j];
+    o_leaf[d] = leaf[j];
+    o_size[d] = size[j];
+    reinterpret_cast<float4*>(o_plane)[d] = reinterpret_cast<const float4*>(plane)[j];
+    o_best[d] = best[j];
+    o_count[d] = count[j];
+}
+
+// rows of the last RANSAC run in reference block order; scored_only keeps the blocks that were fitted
+int64_t Forest::export_ransac(bool scored_only, bool count_only, int32_t* pose, int32_t* leaf, int32_t* size, float* plane,
+                              int32_t* best, int32_t* count) {
+    if (!scored_only) {
+        if (!count_only) {
+            copy_out(ctx, pose, res_pose.get(), res_n);
+            copy_out(ctx, leaf, res_leaf.get(), res_n);
+            copy_out(ctx, size, res_size.get(), res_n);
+            copy_out(ctx, plane, res_plane.get(), (size_t)res_n * 4);
+            copy_out(ctx, best, res_best.get(), res_n);
+            copy_out(ctx, count, res_count.get(), res_n);
+            ctx.sync();
+        }
+        return res_n;
+    }
+    if (count_only) return last_ransac_work;
+    const uint32_t n = res_n, m = last_ransac_work;
+    if (n == 0 || m == 0) return 0;
+    DevBuf<uint32_t> flags(ctx, n), scan(ctx, n);
+    DevBuf<int32_t> o_pose(ctx, m), o_leaf(ctx, m), o_size(ctx, m), o_best(ctx, m), o_count(ctx, m);
+    DevBuf<float> o_plane(ctx, (size_t)m * 4);
+    scored_flags_kernel<<<nblk(n), 256, 0, ctx.stream>>>(n, res_best.get(), flags.get());
+    OL_CHECK_LAUNCH();
+    exclusive_scan_u32(ctx, flags.get(), scan.get(), n, nullptr);
+    scored_compact_kernel<<<nblk(n), 256, 0, ctx.stream>>>(n, flags.get(), scan.get(), res_pose.get(), res_leaf.get(),
+                                                           res_size.get(), res_plane.get(), res_best.get(), res_count.get(),
+                                                           o_pose.get(), o_leaf.get(), o_size.get(), o_plane.get(), o_best.get(),
+                                                           o_count.get());
+    OL_CHECK_LAUNCH();
+    copy_out(ctx, pose, o_pose.get(), m);
+    copy_out(ctx, leaf, o_leaf.get(), m);
+    copy_out(ctx, size, o_size.get(), m);
+    copy_out(ctx, plane, o_plane.get(), (size_t)m * 4);
+    copy_out(ctx, best, o_best.get(), m);
+    copy_out(ctx, count, o_count.get(), m);
     ctx.sync();
+    return m;
 }
 
 int64_t Forest::export_points(const int32_t* pose_rank, int pose, int order, double* xyz, int64_t* idx, int32_t* cell,

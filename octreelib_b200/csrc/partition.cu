@@ -1,0 +1,133 @@
+// Multi-GPU routing: owner rank = hash(grid-cell coordinates) mod world, stable
+// partition of a rank's local points by owner so that one NCCL all-to-all delivers every cell's
+// points - of all poses - to a single GPU.  The reference has no counterpart (single process);
+// the cell coordinates are the ones of /root/reference/octreelib/grid/grid.py:72-76.
+#include "common.cuh"
+#include "pointkey.cuh"
+#include "primitives.cuh"
+
+namespace ol {
+
+__host__ __device__ inline uint32_t cell_owner(long long qx, long long qy, long long qz, uint32_t world) {
+    unsigned long long h = (unsigned long long)qx * 0x9E3779B97F4A7C15ull;
+    h ^= (unsigned long long)qy * 0xC2B2AE3D27D4EB4Full;
+    h ^= (unsigned long long)qz * 0x165667B19E3779F9ull;
+    h ^= h >> 32;
+    h *= 0xD6E8FEB86659FD93ull;
+    h ^= h >> 32;
+    return (uint32_t)((h >> 16) % world);
+}
+
+namespace {
+
+__global__ void owner_kernel(const double* __restrict__ xyz, uint32_t n, double edge, double c0, double c1, double c2,
+                             uint32_t world, uint32_t* __restrict__ owner, uint32_t* __restrict__ iota, uint32_t* __restrict__ err) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double qx = cell_coord(xyz[(size_t)i * 3 + 0], c0, edge);
+    const double qy = cell_coord(xyz[(size_t)i * 3 + 1], c1, edge);
+    const double qz = cell_coord(xyz[(size_t)i * 3 + 2], c2, edge);
+    uint32_t o = 0;
+    if (fabs(qx) < 4503599627370496.0 && fabs(qy) < 4503599627370496.0 && fabs(qz) < 4503599627370496.0)
+        o = cell_owner((long long)qx, (long long)qy, (long long)qz, world);
+    else
+        atomicOr(err, (uint32_t)(isfinite(qx + qy + qz) ? DEVERR_CELL_RANGE : DEVERR_NONFINITE));
+    owner[i] = o;
+    iota[i] = i;
+}
+
+__global__ void route_gather_kernel(uint32_t n, const double* __restrict__ xyz, const uint32_t* __restrict__ perm,
+                                    double* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t r = perm[i];
+    out[(size_t)i * 3 + 0] = xyz[r * 3 + 0];
+    out[(size_t)i * 3 + 1] = xyz[r * 3 + 1];
+    out[(size_t)i * 3 + 2] = xyz[r * 3 + 2];
+}
+
+// (owner, segment) runs are contiguous after the stable sort: record where each run starts / ends
+__global__ void route_counts_kernel(uint32_t n, const uint32_t* __restrict__ owner_sorted, const uint32_t* __restrict__ perm,
+                                    const uint32_t* __restrict__ seg_start, int n_seg, unsigned long long* __restrict__ run_begin,
+                                    unsigned long long* __restrict__ run_end) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto seg_of = [&](uint32_t r) {
+        int lo = 0, hi = n_seg;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (seg_start[mid] <= r)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        return lo;
+    };
+    const uint32_t o = owner_sorted[i];
+    const int s = seg_of(perm[i]);
+    const size_t slot = (size_t)o * n_seg + s;
+    const bool head = (i == 0) || owner_sorted[i - 1] != o || seg_of(perm[i - 1]) != s;
+    const bool tail = (i == n - 1) || owner_sorted[i + 1] != o || seg_of(perm[i + 1]) != s;
+    if (head) run_begin[slot] = i;
+    if (tail) run_end[slot] = (unsigned long long)i + 1;
+}
+
+}  // namespace
+}  // namespace ol
+
+extern "C" {
+
+uint32_t ol_host_cell_owner(int64_t qx, int64_t qy, int64_t qz, uint32_t world) { return ol::cell_owner(qx, qy, qz, world); }
+
+int ol_partition_by_owner(void* stream, const double* xyz_dev, int64_t n, const int64_t* seg_sizes_host, int32_t n_segments,
+                          double edge, const double corner[3], int32_t world, double* out_xyz_dev, int64_t* out_counts_host,
+                          ol_alloc_fn alloc, ol_free_fn free_fn, void* alloc_user) {
+    using namespace ol;
+    try {
+        OL_REQUIRE(n >= 0 && n < (1ll << 31) && n_segments >= 1 && world >= 1 && edge > 0, OL_ERR_INVALID,
+                   "bad partition arguments");
+        Ctx c;
+        c.stream = (cudaStream_t)stream;
+        c.alloc_fn = alloc;
+        c.free_fn = free_fn;
+        c.alloc_user = alloc_user;
+        for (int64_t k = 0; k < (int64_t)world * n_segments; ++k) out_counts_host[k] = 0;
+        if (n == 0) return OL_OK;
+        const uint32_t m = (uint32_t)n;
+        std::vector<uint32_t> seg_start((size_t)n_segments + 1, 0);
+        for (int s = 0; s < n_segments; ++s) seg_start[s + 1] = seg_start[s] + (uint32_t)seg_sizes_host[s];
+        OL_REQUIRE(seg_start[n_segments] == m, OL_ERR_INVALID, "segment sizes do not add up to n");
+        DevBuf<uint32_t> err(c, 1), k0(c, m), k1(c, m), v0(c, m), v1(c, m), d_seg(c, seg_start.size());
+        DevBuf<unsigned long long> rb(c, (size_t)world * n_segments), re(c, (size_t)world * n_segments);
+        err.zero();
+        rb.zero();
+        re.zero();
+        h2d(c, d_seg.get(), seg_start.data(), seg_start.size());
+        const unsigned g = (m + 255) / 256;
+        owner_kernel<<<g, 256, 0, c.stream>>>(xyz_dev, m, edge, corner[0], corner[1], corner[2], (uint32_t)world, k0.get(), v0.get(),
+                                              err.get());
+        OL_CHECK_LAUNCH();
+        int w = radix_sort_pairs<uint32_t>(c, k0.get(), k1.get(), v0.get(), v1.get(), m, 0, bit_length_u64((uint64_t)world - 1));
+        const uint32_t* ks = w ? k1.get() : k0.get();
+        const uint32_t* vs = w ? v1.get() : v0.get();
+        route_gather_kernel<<<g, 256, 0, c.stream>>>(m, xyz_dev, vs, out_xyz_dev);
+        OL_CHECK_LAUNCH();
+        route_counts_kernel<<<g, 256, 0, c.stream>>>(m, ks, vs, d_seg.get(), n_segments, rb.get(), re.get());
+        OL_CHECK_LAUNCH();
+        std::vector<unsigned long long> hb((size_t)world * n_segments), he((size_t)world * n_segments);
+        uint32_t herr = 0;
+        d2h(c, hb.data(), rb.get(), hb.size());
+        d2h(c, he.data(), re.get(), he.size());
+        d2h(c, &herr, err.get(), 1);
+        c.sync();
+        OL_REQUIRE(!(herr & DEVERR_NONFINITE), OL_ERR_NONFINITE, "point cloud contains NaN or infinite coordinates");
+        OL_REQUIRE(!(herr & DEVERR_CELL_RANGE), OL_ERR_RANGE, "cell coordinates out of the representable range");
+        for (size_t k = 0; k < hb.size(); ++k) out_counts_host[k] = (int64_t)(he[k] - hb[k]);
+    } catch (const ol::Error& e) {
+        ol::set_last_error(e.code, e.msg);
+        return e.code;
+    }
+    return OL_OK;
+}
+
+}  // extern "C"

@@ -136,7 +136,7 @@ inline void exclusive_scan_u32(Ctx& c, const uint32_t* in, uint32_t* out, size_t
     }
     size_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     DevBuf<uint32_t> sums(c, tiles);
-    ProfScope ps(c, "scan");
+    ProfScope ps(c, "scan", (double)n);
     scan_reduce_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, c.stream>>>(in, sums.get(), n);
     OL_CHECK_LAUNCH();
     scan_tilesums_kernel<<<1, 1024, 0, c.stream>>>(sums.get(), tiles, d_total);
@@ -256,13 +256,13 @@ inline int radix_sort_pairs(Ctx& c, KeyT* keys0, KeyT* keys1, uint32_t* vals0, u
         uint32_t* vin = cur ? vals1 : vals0;
         uint32_t* vout = cur ? vals0 : vals1;
         {
-            ProfScope ps(c, sizeof(KeyT) == 8 ? "radix_hist_u64" : "radix_hist_u32");
+            ProfScope ps(c, sizeof(KeyT) == 8 ? "radix_hist_u64" : "radix_hist_u32", (double)n);
             radix_hist_kernel<KeyT><<<tiles, SORT_THREADS, 0, c.stream>>>(kin, counts.get(), (uint32_t)n, tiles, bit, nbins);
             OL_CHECK_LAUNCH();
         }
         exclusive_scan_u32(c, counts.get(), counts.get(), (size_t)nbins * tiles, nullptr);
         {
-            ProfScope ps(c, sizeof(KeyT) == 8 ? "radix_scatter_u64" : "radix_scatter_u32");
+            ProfScope ps(c, sizeof(KeyT) == 8 ? "radix_scatter_u64" : "radix_scatter_u32", (double)n);
             radix_scatter_kernel<KeyT><<<tiles, SORT_THREADS, 0, c.stream>>>(kin, vin, kout, vout, counts.get(), (uint32_t)n,
                                                                                tiles, bit, nbins);
             OL_CHECK_LAUNCH();

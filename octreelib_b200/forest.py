@@ -185,18 +185,27 @@ class Forest:
             N.check(self._lib.ol_forest_profile(self._h, 1 if enable else 0))
 
     def profile_read(self) -> dict:
-        """{stage: (launch groups, total ms)} since the last read; synchronises the stream."""
+        """{stage: (launch groups, total ms, elements processed)} since the last read; synchronises."""
         buf = C.create_string_buffer(1 << 16)
         n = C.c_int64(0)
         with self._scope():
             N.check(self._lib.ol_forest_profile_read(self._h, buf, len(buf), C.byref(n)))
         out = {}
         for line in buf.value.decode().splitlines():
-            name, count, ms = line.split()
-            out[name] = (int(count), float(ms))
+            name, count, ms, units = line.split()
+            out[name] = (int(count), float(ms), float(units))
         return out
 
     # ---- queries -------------------------------------------------------------------------------
+    def _host_array(self, shape, dtype) -> np.ndarray:
+        """Host destination of an export: page-locked (torch's caching host allocator) when large, so
+        that the device-to-host copy runs at full PCIe speed; small tables use plain numpy memory."""
+        n = int(np.prod(shape))
+        if n * np.dtype(dtype).itemsize < (1 << 20):
+            return np.zeros(shape, dtype=dtype)
+        t = self._torch.empty(n * np.dtype(dtype).itemsize, dtype=self._torch.uint8, pin_memory=True)
+        return t.numpy().view(dtype).reshape(shape)
+
     def stats(self) -> dict:
         s = N.ForestStats()
         with self._scope():
@@ -234,10 +243,10 @@ class Forest:
     def export_leaves(self) -> dict:
         st = self.stats()
         L = st["n_leaves"]
-        corner = np.zeros((L, 3), dtype=np.float64)
-        edge = np.zeros(L, dtype=np.float64)
-        cell = np.zeros(L, dtype=np.int32)
-        depth = np.zeros(L, dtype=np.int32)
+        corner = self._host_array((L, 3), np.float64)
+        edge = self._host_array(L, np.float64)
+        cell = self._host_array(L, np.int32)
+        depth = self._host_array(L, np.int32)
         with self._scope():
             N.check(self._lib.ol_forest_export_leaves(self._h, _ptr(corner), _ptr(edge), _ptr(cell), _ptr(depth)))
         return dict(corner=corner, edge=edge, cell=cell, depth=depth)
@@ -253,19 +262,21 @@ class Forest:
             N.check(self._lib.ol_forest_export_blocks(self._h, _ptr(pr), _ptr(pose), _ptr(leaf), _ptr(size)))
         return dict(pose=pose, leaf=leaf, size=size)
 
-    def export_ransac(self) -> dict:
+    def export_ransac(self, scored_only: bool = False) -> dict:
+        """Per-block result table of the last RANSAC run (reference block order)."""
         n = C.c_int64(0)
+        so = 1 if scored_only else 0
         with self._scope():
-            N.check(self._lib.ol_forest_export_ransac(self._h, None, None, None, None, None, None, C.byref(n)))
+            N.check(self._lib.ol_forest_export_ransac(self._h, so, None, None, None, None, None, None, C.byref(n)))
         B = n.value
-        pose = np.zeros(B, dtype=np.int32)
-        leaf = np.zeros(B, dtype=np.int32)
-        size = np.zeros(B, dtype=np.int32)
-        plane = np.zeros((B, 4), dtype=np.float32)
-        best = np.zeros(B, dtype=np.int32)
-        count = np.zeros(B, dtype=np.int32)
+        pose = self._host_array(B, np.int32)
+        leaf = self._host_array(B, np.int32)
+        size = self._host_array(B, np.int32)
+        plane = self._host_array((B, 4), np.float32)
+        best = self._host_array(B, np.int32)
+        count = self._host_array(B, np.int32)
         with self._scope():
-            N.check(self._lib.ol_forest_export_ransac(self._h, _ptr(pose), _ptr(leaf), _ptr(size), _ptr(plane), _ptr(best),
+            N.check(self._lib.ol_forest_export_ransac(self._h, so, _ptr(pose), _ptr(leaf), _ptr(size), _ptr(plane), _ptr(best),
                                                       _ptr(count), C.byref(n)))
         return dict(pose=pose, leaf=leaf, size=size, plane=plane, best=best, best_count=count)
 
@@ -274,10 +285,10 @@ class Forest:
         """order 0: reference block order; order 1: cells lexicographic x depth-first leaves."""
         if n_hint is None:
             n_hint = self.stats()["n_points_alive"]
-        xyz = np.zeros((n_hint, 3), dtype=np.float64)
-        idx = np.zeros(n_hint, dtype=np.int64)
-        cell = np.zeros(n_hint, dtype=np.int32)
-        mask = np.zeros(n_hint, dtype=np.uint8) if want_mask else None
+        xyz = self._host_array((n_hint, 3), np.float64)
+        idx = self._host_array(n_hint, np.int64)
+        cell = self._host_array(n_hint, np.int32)
+        mask = self._host_array(n_hint, np.uint8) if want_mask else None
         pr, _ = _i32_array(pose_rank)
         n = C.c_int64(0)
         with self._scope():

@@ -1,0 +1,209 @@
+"""
+Multi-GPU grid: one process per GPU, `torch.distributed` (NCCL over NVLink) as the
+plumbing.  Every grid cell is independent in the reference (`Grid.subdivide` / `filter` loop over
+cells, grid/grid.py:255-258, 266-267; the scheme octree is per cell, octree_manager.py:50-66; RANSAC
+is per (pose, leaf) block, cuda_ransac.py:94-97), so the grid shards by CELL:
+
+    owner(cell) = hash(ix, iy, iz) mod world            (csrc/partition.cu, `ol_host_cell_owner`)
+
+`ShardedGrid.insert_points` stages a rank's local clouds; `exchange()` partitions them by owner on the
+GPU (`ol_partition_by_owner`: owner kernel + stable radix sort + gather), moves them with ONE
+all-to-all (counts first) and inserts what arrived as (source rank, pose) runs.  After that every
+operation is local to the rank - there is no further data-path collective; only scalar counters and
+the final leaf / plane tables are reduced or gathered.
+
+The routing helpers (`routing_layout`, `exchange_points`) are device independent so that the host
+logic is covered by world_size-2 `gloo` tests on CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+from ._host import ForestHost
+from .forest import TorchAllocator, require_cuda
+
+__all__ = ["ShardedGrid", "routing_layout", "exchange_points", "segments_from_counts"]
+
+
+def routing_layout(counts_local: np.ndarray, pose_numbers: Sequence[int], n_poses_total: int) -> np.ndarray:
+    """counts_local[owner][local run] -> counts_global[owner][pose number] (runs of one pose add up)."""
+    world = counts_local.shape[0]
+    out = np.zeros((world, n_poses_total), dtype=np.int64)
+    for j, p in enumerate(pose_numbers):
+        out[:, p] += counts_local[:, j]
+    return out
+
+
+def exchange_points(send, send_counts: np.ndarray, group=None):
+    """One all-to-all of point records.
+
+    send: (n, 3) float64 tensor grouped by destination rank (then by pose); send_counts[dst][pose].
+    Returns (recv tensor, recv_counts[src][pose]).  Works with any torch.distributed backend.
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    dev = send.device
+    sc = torch.from_numpy(np.ascontiguousarray(send_counts, dtype=np.int64)).to(dev)
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc, group=group)  # row r of rc = what rank r sends to me, per pose
+    recv_counts = rc.cpu().numpy()
+    in_splits = [int(v) * 3 for v in recv_counts.sum(axis=1)]
+    out_splits = [int(v) * 3 for v in send_counts.sum(axis=1)]
+    recv = torch.empty((sum(in_splits) // 3, 3), dtype=send.dtype, device=dev)
+    dist.all_to_all_single(recv.view(-1), send.reshape(-1), output_split_sizes=in_splits, input_split_sizes=out_splits,
+                           group=group)
+    assert len(in_splits) == world
+    return recv, recv_counts
+
+
+def segments_from_counts(recv_counts: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(source rank, pose) runs of the received buffer: sizes, pose numbers, and the index of each
+    run's first point among the points of that pose received so far (keeps the original input order
+    of a pose when its source ranks hold increasing index ranges)."""
+    sizes, poses, first = [], [], []
+    seen = np.zeros(recv_counts.shape[1], dtype=np.int64)
+    for src in range(recv_counts.shape[0]):
+        for p in np.flatnonzero(recv_counts[src]):
+            sizes.append(int(recv_counts[src, p]))
+            poses.append(int(p))
+            first.append(int(seen[p]))
+            seen[p] += recv_counts[src, p]
+    return np.array(sizes, dtype=np.int64), np.array(poses, dtype=np.int32), np.array(first, dtype=np.int64)
+
+
+class ShardedGrid:
+    """The `Grid` operations of the hot path on a cell-sharded grid.  Pose numbers must be 0..P-1."""
+
+    def __init__(self, grid_config, n_poses_total: int, group=None):
+        import torch.distributed as dist
+
+        self._cfg = grid_config
+        self._group = group
+        self._dist = dist
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_poses_total = int(n_poses_total)
+        corner = np.asarray(grid_config.corner, dtype=np.float64).reshape(3)
+        self._corner = corner
+        self._host = ForestHost(grid_config.voxel_edge_length, corner, single_cell=False)
+        # the local forest knows every pose number (index == number)
+        self._host.pose_numbers = list(range(self.n_poses_total))
+        self._host.pose_index = {p: p for p in range(self.n_poses_total)}
+        self._host.pose_inserted = [0] * self.n_poses_total
+        self._staged: List[Tuple[int, object]] = []
+        self.exchanged = False
+        self.last_exchange = None
+
+    # ---- staging + routing ----------------------------------------------------------------------
+    def insert_points(self, pose_number: int, points):
+        if not 0 <= pose_number < self.n_poses_total:
+            raise KeyError(pose_number)
+        if self.exchanged:
+            raise RuntimeError("insert after exchange() is not supported")
+        self._staged.append((int(pose_number), points))
+
+    def exchange(self):
+        """Route every staged point to the rank that owns its cell (one NCCL all-to-all)."""
+        torch = require_cuda()
+        lib = N.lib()
+        dev = self._host.forest.device
+        stream = torch.cuda.current_stream(dev)
+        parts = []
+        for _, pts in self._staged:
+            t = pts if isinstance(pts, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pts, dtype=np.float64))
+            parts.append(t.to(dev, dtype=torch.float64, non_blocking=True).reshape(-1, 3))
+        numbers = [p for p, _ in self._staged]
+        sizes = np.array([int(t.shape[0]) for t in parts] or [0], dtype=np.int64)
+        local = torch.cat(parts) if parts else torch.empty((0, 3), dtype=torch.float64, device=dev)
+        n, n_seg = int(local.shape[0]), max(len(parts), 1)
+        send = torch.empty_like(local)
+        counts = np.zeros((self.world, n_seg), dtype=np.int64)
+        alloc = TorchAllocator(dev)
+        corner = (C.c_double * 3)(*self._corner)
+        N.check(lib.ol_partition_by_owner(C.c_void_p(stream.cuda_stream), C.c_void_p(local.data_ptr()), n,
+                                          sizes.ctypes.data_as(C.c_void_p), n_seg, float(self._cfg.voxel_edge_length),
+                                          C.byref(corner), self.world, C.c_void_p(send.data_ptr()),
+                                          counts.ctypes.data_as(C.c_void_p), alloc.alloc_cb, alloc.free_cb, None))
+        send_counts = routing_layout(counts[:, :len(parts)] if parts else counts[:, :0], numbers, self.n_poses_total)
+        if self.world > 1:
+            recv, recv_counts = exchange_points(send, send_counts, self._group)
+        else:
+            recv, recv_counts = send, send_counts
+        seg_sizes, seg_pose, seg_first = segments_from_counts(recv_counts)
+        if len(seg_sizes) == 0:
+            seg_sizes, seg_pose, seg_first = np.array([0], np.int64), np.array([0], np.int32), np.array([0], np.int64)
+        self._host.forest.insert_segments(recv, seg_sizes, seg_pose, seg_first, self.n_poses_total)
+        self.last_exchange = dict(sent=int(send_counts.sum() - send_counts[self.rank].sum()), received=int(recv.shape[0]),
+                                  kept=int(send_counts[self.rank].sum()))
+        self._staged = []
+        self.exchanged = True
+
+    # ---- local pipeline -------------------------------------------------------------------------
+    def subdivide(self, subdivision_criteria, pose_numbers: Optional[Sequence[int]] = None):
+        self._require_exchanged()
+        self._host.subdivide(subdivision_criteria, pose_numbers)
+
+    def filter(self, filtering_criteria):
+        self._require_exchanged()
+        self._host.filter(filtering_criteria)
+
+    def map_leaf_points_cuda_ransac(self, poses_per_batch: int = 10, threshold: float = 0.01, hypotheses_number: int = 1024,
+                                    initial_points_number: int = 6):
+        from .ransac.cuda_ransac import CudaRansac
+
+        self._require_exchanged()
+        if threshold <= 0:
+            raise ValueError("Threshold must be positive")
+        if hypotheses_number < 1:
+            raise ValueError("Number of RANSAC hypotheses must be positive")
+        if hypotheses_number > 1024:
+            raise ValueError("Number of RANSAC hypotheses must be <= 1024 because of the CUDA thread limit.")
+        # every rank draws the same table (same seed state is the caller's responsibility, as in the reference)
+        ransac = CudaRansac(threshold=threshold, hypotheses_number=hypotheses_number, initial_points_number=initial_points_number)
+        self._host.forest.ransac(ransac.random_hypotheses, threshold, list(range(self.n_poses_total)), poses_per_batch, apply=True)
+        self._host._counts_cache = None
+
+    def _require_exchanged(self):
+        if not self.exchanged:
+            self.exchange()
+
+    # ---- global counters: sums over the ranks (cells are disjoint) --------------------------------
+    def _global(self, which: int, pose_number: int) -> int:
+        import torch
+
+        local = self._host.count(pose_number, which)
+        if self.world == 1:
+            return local
+        t = torch.tensor([local], dtype=torch.int64, device=self._host.forest.device)
+        self._dist.all_reduce(t, group=self._group)
+        return int(t.item())
+
+    def n_leaves(self, pose_number: int) -> int:
+        return self._global(0, pose_number)
+
+    def n_points(self, pose_number: int) -> int:
+        return self._global(1, pose_number)
+
+    def n_nodes(self, pose_number: int) -> int:
+        return self._global(2, pose_number)
+
+    # ---- final gather of the leaf / plane tables ----------------------------------------------------
+    def gather_tables(self, dst: int = 0) -> Optional[Dict[str, np.ndarray]]:
+        """Leaf table (corner, edge) and fitted-plane table of every rank, concatenated on `dst`."""
+        forest = self._host.forest
+        mine = dict(leaves=forest.export_leaves(), planes=forest.export_ransac(scored_only=True))
+        if self.world == 1:
+            return mine
+        out = [None] * self.world if self.rank == dst else None
+        self._dist.gather_object(mine, out, dst=dst, group=self._group)
+        if self.rank != dst:
+            return None
+        return dict(leaves={k: np.concatenate([o["leaves"][k] for o in out]) for k in mine["leaves"]},
+                    planes={k: np.concatenate([o["planes"][k] for o in out]) for k in mine["planes"]},
+                    rank_of_leaf=np.concatenate([np.full(len(o["leaves"]["edge"]), r) for r, o in enumerate(out)]))

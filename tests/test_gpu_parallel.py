@@ -1,0 +1,129 @@
+"""GPU (single device): the device side of the multi-GPU path - owner partition kernel, run-based
+insertion - checked by emulating the ranks one after the other in one process, then comparing the
+union of the per-rank results with a plain single-GPU Grid and with the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from octreelib_b200 import _native as N
+from octreelib_b200.criteria import MaxPoints
+from octreelib_b200.forest import Forest, TorchAllocator
+from octreelib_b200.grid import Grid, GridConfig
+from octreelib_b200.parallel import routing_layout, segments_from_counts
+from octreelib_b200.synthetic import lidar64_scan
+
+pytestmark = pytest.mark.gpu
+
+
+def _partition(points_list, edge, world):
+    import torch
+
+    lib = N.lib()
+    dev = torch.device("cuda", 0)
+    local = torch.from_numpy(np.vstack(points_list)).to(dev)
+    sizes = np.array([len(p) for p in points_list], dtype=np.int64)
+    send = torch.empty_like(local)
+    counts = np.zeros((world, len(points_list)), dtype=np.int64)
+    alloc = TorchAllocator(dev)
+    corner = (C.c_double * 3)(0.0, 0.0, 0.0)
+    N.check(lib.ol_partition_by_owner(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), C.c_void_p(local.data_ptr()),
+                                      len(local), sizes.ctypes.data_as(C.c_void_p), len(sizes), float(edge), C.byref(corner),
+                                      world, C.c_void_p(send.data_ptr()), counts.ctypes.data_as(C.c_void_p), alloc.alloc_cb,
+                                      alloc.free_cb, None))
+    return send.cpu().numpy(), counts
+
+
+def test_partition_by_owner_matches_host_rule():
+    lib = N.lib()
+    rng = np.random.default_rng(0)
+    clouds = [(rng.random((3000 + 500 * k, 3)) * 20 - 10).astype(np.float32).astype(np.float64) for k in range(3)]
+    world = 4
+    send, counts = _partition(clouds, 1.0, world)
+    allpts = np.vstack(clouds)
+    q = np.floor_divide(allpts, 1.0).astype(np.int64)
+    owner = np.array([lib.ol_host_cell_owner(int(a), int(b), int(c), world) for a, b, c in q])
+    run = np.concatenate([np.full(len(c), j) for j, c in enumerate(clouds)])
+    order = np.lexsort((np.arange(len(allpts)), run, owner))
+    assert (send == allpts[order]).all()
+    exp = np.zeros_like(counts)
+    np.add.at(exp, (owner, run), 1)
+    assert (counts == exp).all()
+
+
+def test_emulated_two_rank_grid_equals_single_gpu_grid():
+    """Two 'ranks' (processed one after the other on one GPU) each hold half of the poses; after the
+    routing every cell lives on exactly one rank and the union of the per-rank leaf tables and leaf
+    point sets equals the single-GPU grid's."""
+    world, P = 2, 4
+    clouds = {p: lidar64_scan(p, seed=3)[::12] for p in range(P)}
+    held = {r: [p for p in range(P) if p % world == r] for r in range(world)}  # non-monotone arrival order
+    sends, counts = {}, {}
+    for r in range(world):
+        s, c = _partition([clouds[p] for p in held[r]], 1.0, world)
+        sends[r], counts[r] = s, routing_layout(c, held[r], P)
+    ref = Grid(GridConfig(voxel_edge_length=1.0))
+    for p in range(P):
+        ref.insert_points(p, clouds[p])
+    ref.subdivide([MaxPoints(50)])
+    ref_leaves = ref._host.forest.export_leaves()
+    ref_blocks = ref._host.forest.export_blocks()
+    ref_pts = ref._host.forest.export_points(-1, order=0)["xyz"]
+    ref_keys = set()
+    off = 0
+    for pose, leaf, size in zip(ref_blocks["pose"], ref_blocks["leaf"], ref_blocks["size"]):
+        key = (int(pose), tuple(ref_leaves["corner"][leaf]), float(ref_leaves["edge"][leaf]), ref_pts[off:off + size].tobytes())
+        ref_keys.add(key)
+        off += size
+    got_keys = set()
+    total_leaves = 0
+    for dst in range(world):
+        # what rank dst receives: from src 0 its slice, then from src 1 its slice
+        parts, rc = [], np.zeros((world, P), dtype=np.int64)
+        for src in range(world):
+            start = int(counts[src][:dst].sum())
+            n = int(counts[src][dst].sum())
+            parts.append(sends[src][start:start + n])
+            rc[src] = counts[src][dst]
+        recv = np.vstack(parts)
+        sizes, poses, first = segments_from_counts(rc)
+        f = Forest(1.0)
+        f.insert_segments(recv, sizes, poses, first, P)
+        f.subdivide(50)
+        lv, bl = f.export_leaves(), f.export_blocks()
+        pts = f.export_points(-1, order=0)["xyz"]
+        off = 0
+        for pose, leaf, size in zip(bl["pose"], bl["leaf"], bl["size"]):
+            got_keys.add((int(pose), tuple(lv["corner"][leaf]), float(lv["edge"][leaf]), pts[off:off + size].tobytes()))
+            off += size
+        total_leaves += f.stats()["n_leaves"]
+    assert got_keys == ref_keys
+    assert total_leaves == ref._host.forest.stats()["n_leaves"]
+
+
+def test_append_to_existing_pose_in_a_manager():
+    from octreelib_b200.octree import Octree, OctreeConfig
+    from octreelib_b200.octree_manager import OctreeManager
+    from oracle.structure import OracleGrid, max_points_criterion
+
+    rng = np.random.default_rng(1)
+    a = (rng.random((300, 3)) * 8).astype(np.float32).astype(np.float64)
+    b = (rng.random((200, 3)) * 8).astype(np.float32).astype(np.float64)
+    c = (rng.random((250, 3)) * 8).astype(np.float32).astype(np.float64)
+    mp = OctreeManager(Octree, OctreeConfig(), np.array([0, 0, 0]), 8)
+    mp.insert_points(0, a)
+    mp.insert_points(1, b)
+    mp.insert_points(0, c)  # appended to pose 0 (octree_manager.py:161-171)
+    mp.subdivide([lambda pts: len(pts) > 20])
+    og = OracleGrid(8)
+    og.insert_points(0, np.vstack([a, c]))
+    og.insert_points(1, b)
+    og.subdivide([max_points_criterion(20)])
+    for p in (0, 1):
+        want = og.get_leaf_points(p)
+        got = mp.get_leaf_points(pose_number=p)
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert (np.asarray(g.corner_min, dtype=float) == np.asarray(w.corner, dtype=float)).all()
+            assert (g.get_points() == w.points).all()
+        assert mp.n_nodes(p) == og.n_nodes(p) and mp.n_points(p) == og.n_points(p)
