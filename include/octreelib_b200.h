@@ -40,7 +40,8 @@ typedef enum ol_status {
     OL_ERR_DEPTH_CAP = 6,   /* reference would recurse deeper       -> RecursionError */
     OL_ERR_NONFINITE = 7,   /* NaN / inf input                      -> ValueError */
     OL_ERR_STATE = 8,       /* call not valid in the current state  -> RuntimeError */
-    OL_ERR_POSE = 9         /* unknown pose index                   -> KeyError */
+    OL_ERR_POSE = 9,        /* unknown pose index                   -> KeyError */
+    OL_ERR_INTERNAL = 10    /* self-check failed (RANSAC verify)    -> AssertionError */
 } ol_status;
 
 typedef void *(*ol_alloc_fn)(void *user, size_t bytes);
@@ -179,11 +180,26 @@ int ol_forest_export_points(ol_forest *f, const int32_t *pose_rank, int32_t pose
 /* ---- CudaRansac.evaluate, ransac/cuda_ransac.py:43-81 (kernel-level boundary) ----------------
  * points_dev [n][3] float64, block_sizes_dev [B] int32 back to back, table_dev [H][K] float64;
  * outputs: mask_dev [n] uint8, plane_dev [B][4] float32, best_dev [B], best_count_dev [B]
- * (the three per-block outputs may be NULL).  flags: bit0 = no TMA staging (plain loads). */
+ * (the three per-block outputs may be NULL).
+ * flags: OL_RANSAC_NO_TMA      plain loads instead of TMA bulk staging
+ *        OL_RANSAC_EXACT_ONLY  evaluate every hypothesis with the reference's float64 arithmetic (no FP32 pre-filter)
+ *        OL_RANSAC_VERIFY      exact evaluation of everything + check that every count lies inside its pre-filter
+ *                              interval (returns OL_ERR_INTERNAL if one does not)
+ *        OL_RANSAC_STATS       accumulate pre-filter statistics (ol_ransac_stats_read)
+ * All modes return identical results. */
+#define OL_RANSAC_NO_TMA 1u
+#define OL_RANSAC_EXACT_ONLY 2u
+#define OL_RANSAC_VERIFY 4u
+#define OL_RANSAC_STATS 8u
 int ol_ransac_evaluate(void *stream, const double *points_dev, int64_t n, const int32_t *block_sizes_dev, int64_t B,
                        const double *table_dev, int32_t H, int32_t K, double threshold, uint8_t *mask_dev,
                        float *plane_dev, int32_t *best_dev, int32_t *best_count_dev, uint32_t flags,
                        ol_alloc_fn alloc, ol_free_fn free_fn, void *alloc_user);
+
+/* pre-filter statistics since the last reset (device-wide synchronisation):
+ * out[0] blocks, [1] hypotheses filtered, [2] trivial intervals, [3] exact evaluations, [4] early exits,
+ * [5] interval violations (verify mode) */
+int ol_ransac_stats_read(uint64_t out[8], int32_t reset);
 
 /* ---- multi-GPU routing (no counterpart in the single-process reference) --------
  * A cell (all poses of it) is owned by rank ol_host_cell_owner(cell coordinates, world).

@@ -17,7 +17,8 @@ OL_OK = 0
 OL_ERR_INVALID, OL_ERR_CUDA, OL_ERR_ALLOC, OL_ERR_RANGE = 1, 2, 3, 4
 OL_ERR_OUT_OF_NODE, OL_ERR_DEPTH_CAP, OL_ERR_NONFINITE, OL_ERR_STATE, OL_ERR_POSE = 5, 6, 7, 8, 9
 OL_MAX_DEPTH = 21
-RANSAC_FLAG_NO_TMA = 1
+RANSAC_FLAG_NO_TMA, RANSAC_FLAG_EXACT_ONLY, RANSAC_FLAG_VERIFY, RANSAC_FLAG_STATS = 1, 2, 4, 8
+OL_ERR_INTERNAL = 10
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 FREE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
@@ -78,6 +79,7 @@ SIGNATURES = {
     "ol_forest_export_points": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, C.POINTER(_i64)]),
     "ol_ransac_evaluate": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _i32, _i32, _f64, _p, _p, _p, _p, _u32, ALLOC_FN,
                                      FREE_FN, _p]),
+    "ol_ransac_stats_read": (C.c_int, [C.POINTER(_u64 * 8), _i32]),
     "ol_host_cell_owner": (_u32, [_i64, _i64, _i64, _u32]),
     "ol_partition_by_owner": (C.c_int, [_p, _p, _i64, _p, _i32, _f64, C.POINTER(_f64 * 3), _i32, _p, _p, ALLOC_FN, FREE_FN,
                                         _p]),
@@ -121,6 +123,7 @@ _EXC = {
     OL_ERR_NONFINITE: ValueError,
     OL_ERR_STATE: RuntimeError,
     OL_ERR_POSE: KeyError,
+    OL_ERR_INTERNAL: AssertionError,
 }
 
 

@@ -286,7 +286,19 @@ int ol_ransac_evaluate(void* stream, const double* points_dev, int64_t n, const 
     OL_CHECK_LAUNCH();
     launch_ransac(c, points_dev, n, starts.get(), block_sizes_dev, ref.get(), work.get(), n_work, mx, table_dev, H, K, threshold,
                   mask_dev, plane_dev, best_dev, best_count_dev, flags);
+    uint32_t herr = 0;
+    OL_CUDA(cudaMemcpyAsync(&herr, err.get(), 4, cudaMemcpyDeviceToHost, c.stream));
     c.sync();
+    OL_REQUIRE(!(herr & DEVERR_FILTER_BOUND), OL_ERR_INTERNAL, "RANSAC verify: an exact inlier count left its pre-filter interval");
+    OL_API_END
+}
+
+int ol_ransac_stats_read(uint64_t out[8], int32_t reset) {
+    OL_NEED(out);
+    OL_API_BEGIN
+    unsigned long long tmp[8];
+    ol::ransac_stats_read(tmp, reset != 0);
+    for (int i = 0; i < 8; ++i) out[i] = tmp[i];
     OL_API_END
 }
 

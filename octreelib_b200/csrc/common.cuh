@@ -51,6 +51,7 @@ enum DevErr : uint32_t {
     DEVERR_OUT_OF_NODE = 4u,    // point outside its node at a level that is being split (octree.py:98)
     DEVERR_DEPTH_CAP = 8u,      // a node still exceeds the criterion at the maximum depth
     DEVERR_SAMPLE_OOB = 16u,    // RANSAC sample index fell outside its block (clamped)
+    DEVERR_FILTER_BOUND = 32u,  // RANSAC verify mode: an exact count left its pre-filter interval
 };
 
 // ---------------------------------------------------------------------------------------------

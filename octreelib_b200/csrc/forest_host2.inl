@@ -306,11 +306,13 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
     }
     // a sample index that left its block is clamped and only counted (see ransac.cu)
     uint32_t e = read_u32(d_err.get());
-    if (e & DEVERR_SAMPLE_OOB) {
-        sample_oob_seen = true;
-        e &= ~(uint32_t)DEVERR_SAMPLE_OOB;
+    if (e & (DEVERR_SAMPLE_OOB | DEVERR_FILTER_BOUND)) {
+        const bool bound = (e & DEVERR_FILTER_BOUND) != 0;
+        if (e & DEVERR_SAMPLE_OOB) sample_oob_seen = true;
+        e &= ~(uint32_t)(DEVERR_SAMPLE_OOB | DEVERR_FILTER_BOUND);
         OL_CUDA(cudaMemcpyAsync(d_err.get(), &e, 4, cudaMemcpyHostToDevice, ctx.stream));
         ctx.sync();
+        OL_REQUIRE(!bound, OL_ERR_INTERNAL, "RANSAC verify: an exact inlier count left its pre-filter interval");
     }
     ransac_valid = true;
     if (apply) apply_mask();

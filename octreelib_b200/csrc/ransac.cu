@@ -3,23 +3,51 @@
 // Replaces the reference's numba-CUDA kernel
 //   /root/reference/octreelib/ransac/cuda_ransac.py:85-155  (kernel body)
 //   /root/reference/octreelib/ransac/util.py:16-24, 28-84   (distance, plane fit)
-// with the same arithmetic (float64 plane fit without FMA contraction, plane rounded to float32,
-// float64 point-plane distance compared against a float64 threshold), so that every hypothesis'
-// inlier count - and therefore the arg-max and the mask - is identical to the reference's.
-// Differences by design:
-//   * the leaf's points are staged in shared memory once (TMA bulk copy + mbarrier) instead of
-//     being streamed from global memory by all 1024 threads;
+// and returns exactly what that arithmetic returns (float64 plane fit without FMA contraction,
+// plane rounded to float32, float64 point-plane distance compared against a float64 threshold):
+// every reported inlier count, the arg-max and the mask are identical to the reference's.
+//
+// How the work is organised:
+//   1. the block's float64 points are staged in shared memory once (TMA bulk copy + mbarrier)
+//      instead of being streamed from global memory by all 1024 threads;
+//   2. FP32 INTERVAL PRE-FILTER: every hypothesis is first fitted and scored in float32 on the
+//      block-local (origin-shifted) coordinates, together with a rigorous bound eps_t on
+//      |distance_reference - distance_fp32|.  That gives an interval lo_t <= count_t <= hi_t for the
+//      reference's exact inlier count.  Hypotheses whose fit is ill conditioned, whose adjugate-row
+//      selection is ambiguous, or whose sample index sits next to a rounding boundary get the
+//      trivial interval [0, n];
+//   3. only the hypotheses that can still be the winner (hi_t >= max lo, with the lowest-index
+//      tie-break taken into account) are evaluated with the reference's exact float64 arithmetic;
+//      typically 1-30 of 1024;
+//   4. hypotheses are processed in chunks of 256 in index order; as soon as one is certain to have
+//      ALL points as inliers, no later hypothesis can win (ties go to the lowest index) and the
+//      remaining chunks are skipped.
+// Flags select the plain exact evaluation of all hypotheses (RANSAC_FLAG_EXACT_ONLY) or a
+// verification mode (RANSAC_FLAG_VERIFY) that evaluates everything exactly AND checks
+// lo_t <= count_t <= hi_t for every hypothesis (tests run both and require identical output).
+// Differences to the reference by design:
 //   * ties between equally good hypotheses are broken deterministically (lowest index) where the
 //     reference has a CAS race (cuda_ransac.py:135-146);
 //   * the chosen plane, hypothesis index and inlier count are returned per block.
+#include <algorithm>
+
 #include "common.cuh"
 #include "forest.cuh"
 
 namespace ol {
 
 constexpr int RANSAC_THREADS = 256;
-constexpr uint32_t RANSAC_SMEM_POINTS_MAX = 8192;  // 192 KB of float64 xyz
+constexpr int RANSAC_MAX_H = 1024;
+constexpr int RANSAC_MAX_CHUNKS = RANSAC_MAX_H / RANSAC_THREADS;
+constexpr uint32_t RANSAC_SMEM_POINTS_MAX = 4096;  // 96 KB of float64 xyz + 64 KB of float4 local copies
 constexpr uint32_t RANSAC_FLAG_NO_TMA = 1u;
+constexpr uint32_t RANSAC_FLAG_EXACT_ONLY = 2u;
+constexpr uint32_t RANSAC_FLAG_VERIFY = 4u;
+constexpr uint32_t RANSAC_FLAG_STATS = 8u;
+constexpr int RANSAC_COOP_MIN_POINTS = 96;  // blocks at least this large score candidates warp-cooperatively
+
+// statistics of the pre-filter (only with RANSAC_FLAG_STATS / VERIFY): see ol_ransac_stats_read
+__device__ unsigned long long g_ransac_stats[8];
 
 struct RansacArgs {
     const double* points;
@@ -29,7 +57,9 @@ struct RansacArgs {
     const long long* blk_ref_start; // block_start_indices[b] of the reference's batch layout
     const uint32_t* work;           // blocks to score (size >= K)
     uint32_t n_work;
-    const double* table;            // [H][K]
+    const double* table;            // [H][K] float64 uniform [0,1)
+    const uint32_t* r32t;           // [K][H] floor(table * 2^32), transposed (pre-filter)
+    const uint32_t* table_ok;       // [1] 1 if every table entry is in [0, 1)
     int H, K;
     double thr;
     uint8_t* mask;
@@ -69,6 +99,9 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
                  : "memory");
 }
 
+// =============================================================================================
+// exact path: the reference's arithmetic, op for op
+// =============================================================================================
 // sample index of hypothesis t, draw i (cuda_ransac.py:103-107): float64 arithmetic on the
 // reference's batch-global start index, truncated to int32; returned relative to the block.
 __device__ __forceinline__ int sample_index(const double* __restrict__ table, int K, int t, int i, int n, long long ref_start,
@@ -83,8 +116,8 @@ __device__ __forceinline__ int sample_index(const double* __restrict__ table, in
 }
 
 // util.py:28-84, op for op (no contraction), result rounded to float32 (cuda_ransac.py:110-113)
-__device__ __forceinline__ float4 fit_plane(const double* __restrict__ pts, const double* __restrict__ table, int K, int t,
-                                            int n, long long ref_start, uint32_t* err) {
+__device__ __noinline__ float4 fit_plane(const double* __restrict__ pts, const double* __restrict__ table, int K, int t, int n,
+                                         long long ref_start, uint32_t* err) {
     double cx = 0.0, cy = 0.0, cz = 0.0;
     for (int i = 0; i < K; ++i) {
         const double* p = pts + 3 * sample_index(table, K, t, i, n, ref_start, err);
@@ -138,13 +171,173 @@ __device__ __forceinline__ double plane_distance(double a, double b, double c, d
     return fabs(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(a, p[0]), __dmul_rn(b, p[1])), __dmul_rn(c, p[2])), d));
 }
 
+__device__ __forceinline__ unsigned long long pack_key(int count, int t) {  // max count, ties -> lowest hypothesis index
+    return ((unsigned long long)(uint32_t)count << 32) | (unsigned long long)(0xffffffffu - (uint32_t)t);
+}
+
+// Exact evaluation of one hypothesis per lane (active lanes only); returns the lane's inlier count
+// (cuda_ransac.py:116-121).  Large blocks are scored warp-cooperatively: every active lane's plane
+// is broadcast in turn and all 32 lanes stride over the points.
+__device__ __forceinline__ int exact_count(const double* __restrict__ pts, int n, bool active, const float4 pl, double thr) {
+    int cnt = 0;
+    if (n < RANSAC_COOP_MIN_POINTS) {
+        if (active) {
+            const double a = (double)pl.x, b = (double)pl.y, c = (double)pl.z, d = (double)pl.w;
+            for (int i = 0; i < n; ++i) cnt += plane_distance(a, b, c, d, pts + 3 * i) < thr;
+        }
+        return cnt;
+    }
+    const int lane = threadIdx.x & 31;
+    uint32_t todo = __ballot_sync(0xffffffffu, active);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const double a = (double)__shfl_sync(0xffffffffu, pl.x, src), b = (double)__shfl_sync(0xffffffffu, pl.y, src);
+        const double c = (double)__shfl_sync(0xffffffffu, pl.z, src), d = (double)__shfl_sync(0xffffffffu, pl.w, src);
+        int part = 0;
+        for (int i = lane; i < n; i += 32) part += plane_distance(a, b, c, d, pts + 3 * i) < thr;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == src) cnt = part;
+    }
+    return cnt;
+}
+
+// =============================================================================================
+// FP32 interval pre-filter
+// =============================================================================================
+struct Interval {
+    int lo, hi;
+};
+
+// Bounds on the reference's exact inlier count of hypothesis t from a float32 fit on the block-local
+// coordinates q_j = fl32(p_j - p_0).  With u = 2^-24, Qm >= max_j |q_j|_2, Pm >= max_j |p_j|_1:
+//   reference side : the plane is rounded to float32 before scoring (cuda_ransac.py:110-113), which moves
+//                    a.x + b.y + c.z + d by at most 2^-25 |p|_1 + 2^-24 |d| <= 1.5 * 2^-24 Pm
+//   filter side    : covariance entries carry E_m (rounding of q, of the residuals and of the sums),
+//                    adjugate entries E_cof = 4 S E_m + 3 u S^2 (S = trace), so the unit normal is off
+//                    by <= ~2 eta with eta = sqrt(3) E_cof / |n|; a point is at most 2 Qm from the centroid.
+// Any hypothesis for which a bound cannot be given (eta too large, ambiguous adjugate row, sample index
+// next to a rounding boundary, non-finite intermediate) returns [0, n].
+__device__ __forceinline__ Interval filter_hypothesis(const float4* __restrict__ q, const uint32_t* __restrict__ r32t, int H,
+                                                      int K, int t, int n, float Pm, float Qm, float thr) {
+    const float u = 5.9604645e-8f;  // 2^-24
+    const uint32_t guard = 0u - ((uint32_t)n + 4096u);  // low word at / above this: floor(R n) may be off by one
+    bool ok = true;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    for (int i = 0; i < K; ++i) {
+        const uint32_t r = __ldg(&r32t[(size_t)i * H + t]);
+        ok = ok && (r * (uint32_t)n < guard);
+        const float4 p = q[__umulhi(r, (uint32_t)n)];
+        cx += p.x;
+        cy += p.y;
+        cz += p.z;
+    }
+    const float inv_k = 1.0f / (float)K;
+    cx *= inv_k;
+    cy *= inv_k;
+    cz *= inv_k;
+    float xx = 0.f, xy = 0.f, xz = 0.f, yy = 0.f, yz = 0.f, zz = 0.f;
+    for (int i = 0; i < K; ++i) {
+        const float4 p = q[__umulhi(__ldg(&r32t[(size_t)i * H + t]), (uint32_t)n)];
+        const float rx = p.x - cx, ry = p.y - cy, rz = p.z - cz;
+        xx = fmaf(rx, rx, xx);
+        xy = fmaf(rx, ry, xy);
+        xz = fmaf(rx, rz, xz);
+        yy = fmaf(ry, ry, yy);
+        yz = fmaf(ry, rz, yz);
+        zz = fmaf(rz, rz, zz);
+    }
+    const float kf = (float)K;
+    const float S = (xx + yy + zz) * 1.0001f;
+    const float g = (kf + 2.f) * u * Qm;            // centroid error (common to all residuals: second order)
+    const float gr = 1.8e-15f * (kf + 1.f) * Pm;    // the reference's own centroid error, 2^-53 (K+1) Pm (x2)
+    const float Em = (2.f * kf + 6.f) * u * S + 4.f * u * Qm * sqrtf(kf * S) + 2.f * kf * (g * g + gr * gr);
+    const float Ecof = 4.f * S * Em + 3.f * u * S * S;
+    const float det_x = fmaf(yy, zz, -(yz * yz));
+    const float det_y = fmaf(xx, zz, -(xz * xz));
+    const float det_z = fmaf(xx, yy, -(xy * xy));
+    // which adjugate row does the reference take (util.py:63-74)?  Only accept a certain answer.
+    const float e2 = 2.f * Ecof;
+    const bool b1 = (det_x - det_y > e2) && (det_x - det_z > e2);
+    const bool nb1 = (det_y - det_x >= e2) || (det_z - det_x >= e2);
+    const bool b2 = nb1 && (det_y - det_z > e2);
+    const bool b3 = nb1 && (det_z - det_y >= e2);
+    ok = ok && (b1 || b2 || b3);
+    const float c_xy = fmaf(xz, yz, -(xy * zz));  // shared off-diagonal cofactors
+    const float c_xz = fmaf(xy, yz, -(xz * yy));
+    const float c_yz = fmaf(xy, xz, -(yz * xx));
+    float ax, ay, az;
+    if (b1) {
+        ax = det_x;
+        ay = c_xy;
+        az = c_xz;
+    } else if (b2) {
+        ax = c_xy;
+        ay = det_y;
+        az = c_yz;
+    } else {
+        ax = c_xz;
+        ay = c_yz;
+        az = det_z;
+    }
+    const float nn = fmaf(ax, ax, fmaf(ay, ay, az * az));
+    const float inv = rsqrtf(nn);
+    const float eta = 1.7321f * Ecof * inv;
+    ok = ok && (eta <= 0.05f) && (S >= 1e-30f);
+    const float nx = ax * inv, ny = ay * inv, nz = az * inv;
+    const float dn = -fmaf(nx, cx, fmaf(ny, cy, nz * cz));
+    float eps = 1.1920929e-7f * Pm                       // 2^-23 Pm: float32 rounding of the reference plane
+                + 2.f * Qm * (3.2f * eta + 16.f * u)     // direction error x lever arm, normalisation, dot product
+                + 1.7321f * g + 4.f * u * thr;           // centroid error, threshold rounding
+    eps *= 1.01f;
+    ok = ok && (eps <= 0.25f * thr);
+    const float t_lo = thr - eps, t_hi = thr + eps;
+    int lo = 0, hi = 0;
+    for (int j = 0; j < n; ++j) {
+        const float4 p = q[j];
+        const float d = fabsf(fmaf(nx, p.x, fmaf(ny, p.y, fmaf(nz, p.z, dn))));
+        lo += d < t_lo;
+        hi += d < t_hi;
+    }
+    Interval out;
+    out.lo = ok ? lo : 0;
+    out.hi = ok ? hi : n;
+    return out;
+}
+
+// [K][H] transposed 32-bit fixed-point copy of the hypothesis table for the pre-filter
+__global__ void ransac_table_prep_kernel(const double* __restrict__ table, int H, int K, uint32_t* __restrict__ r32t,
+                                         uint32_t* __restrict__ table_ok) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= H * K) return;
+    const int t = e / K, i = e - t * K;
+    const double r = table[e];
+    uint32_t v = 0;
+    if (r >= 0.0 && r < 1.0)
+        v = (uint32_t)(unsigned long long)(r * 4294967296.0);  // exact: power-of-two scaling, then truncation
+    else
+        atomicAnd(table_ok, 0u);
+    r32t[(size_t)i * H + t] = v;
+}
+
+// shared-memory header (bytes): [0,8) mbarrier | [8,16) best exact key | [16,24) best lower-bound key |
+// [24,28) Pmax bits | [28,32) Qmax^2 bits | [32,36) candidate count | [36,48) statistics | [48,64) winning plane
+constexpr int RANSAC_SMEM_HEADER = 64;
+
 __global__ void __launch_bounds__(RANSAC_THREADS) ransac_kernel(RansacArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [0,8) mbarrier | [8,16) best key | [16, 16 + H*16) planes | staged points (16 B aligned)
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw);
     unsigned long long* s_best = reinterpret_cast<unsigned long long*>(smem_raw + 8);
-    float4* s_plane = reinterpret_cast<float4*>(smem_raw + 16);
-    double* s_pts_raw = reinterpret_cast<double*>(smem_raw + 16 + (size_t)A.H * 16);
+    unsigned long long* s_sel = reinterpret_cast<unsigned long long*>(smem_raw + 16);
+    uint32_t* s_pmax = reinterpret_cast<uint32_t*>(smem_raw + 24);
+    uint32_t* s_qmax2 = reinterpret_cast<uint32_t*>(smem_raw + 28);
+    uint32_t* s_nc = reinterpret_cast<uint32_t*>(smem_raw + 32);
+    uint32_t* s_stat = reinterpret_cast<uint32_t*>(smem_raw + 36);  // [0] uncertain [1] violations
+    float4* s_bp = reinterpret_cast<float4*>(smem_raw + 48);
+    uint16_t* s_cand = reinterpret_cast<uint16_t*>(smem_raw + RANSAC_SMEM_HEADER);  // [1024]
+    double* s_pts_raw = reinterpret_cast<double*>(smem_raw + RANSAC_SMEM_HEADER + 2 * RANSAC_MAX_H);
+    float4* s_q = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(s_pts_raw) + ((((size_t)A.cap * 3 + 2) * 8 + 15) & ~(size_t)15));
 
     const uint32_t b = A.work[blockIdx.x];
     const int n = A.blk_size[b];
@@ -153,9 +346,21 @@ __global__ void __launch_bounds__(RANSAC_THREADS) ransac_kernel(RansacArgs A) {
     const double* gsrc = A.points + (size_t)ps * 3;
     const double* pts = gsrc;
     const int tid = threadIdx.x;
+    const bool staged = (uint32_t)n <= A.cap;
+    const bool verify = (A.flags & RANSAC_FLAG_VERIFY) != 0;
+    const bool use_filter = staged && (verify || !(A.flags & RANSAC_FLAG_EXACT_ONLY)) && (__ldg(A.table_ok) != 0u);
+    const int nch = (A.H + RANSAC_THREADS - 1) / RANSAC_THREADS;
 
-    if (tid == 0) *s_best = 0ull;
-    if ((uint32_t)n <= A.cap) {
+    if (tid == 0) {
+        *s_best = 0ull;
+        *s_sel = 0ull;
+        *s_pmax = 0u;
+        *s_qmax2 = 0u;
+        *s_nc = 0u;
+        s_stat[0] = 0u;
+        s_stat[1] = 0u;
+    }
+    if (staged) {
         if (!(A.flags & RANSAC_FLAG_NO_TMA)) {
             // TMA bulk copy of the block's contiguous float64 xyz run.  Source must be 16-byte
             // aligned: start from the aligned-down address (the host guarantees the buffer base
@@ -192,37 +397,423 @@ __global__ void __launch_bounds__(RANSAC_THREADS) ransac_kernel(RansacArgs A) {
         __syncthreads();
     }
 
-    // ---- hypotheses: thread t handles t, t + 256, ... ----------------------------------------
-    unsigned long long my_best = 0ull;
-    for (int t = tid; t < A.H; t += RANSAC_THREADS) {
-        const float4 pl = fit_plane(pts, A.table, A.K, t, n, rs, A.err);
-        s_plane[t] = pl;
-        const double a = (double)pl.x, bb = (double)pl.y, c = (double)pl.z, d = (double)pl.w;
-        int cnt = 0;
-        for (int i = 0; i < n; ++i) cnt += plane_distance(a, bb, c, d, pts + 3 * i) < A.thr;  // cuda_ransac.py:116-121
-        // max count, ties -> lowest hypothesis index
-        const unsigned long long key = ((unsigned long long)(uint32_t)cnt << 32) | (unsigned long long)(0xffffffffu - (uint32_t)t);
-        my_best = key > my_best ? key : my_best;
-    }
+    // ---- block-local float32 copies + magnitude bounds for the pre-filter ----------------------
+    float Pm = 0.f, Qm = 0.f;
+    if (use_filter) {
+        const double ox = pts[0], oy = pts[1], oz = pts[2];
+        float pm = 0.f, q2 = 0.f;
+        for (int j = tid; j < n; j += RANSAC_THREADS) {
+            const double x = pts[3 * j], y = pts[3 * j + 1], z = pts[3 * j + 2];
+            const float qx = (float)(x - ox), qy = (float)(y - oy), qz = (float)(z - oz);
+            s_q[j] = make_float4(qx, qy, qz, 0.f);
+            pm = fmaxf(pm, (float)(fabs(x) + fabs(y) + fabs(z)));
+            q2 = fmaxf(q2, fmaf(qx, qx, fmaf(qy, qy, qz * qz)));
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long other = __shfl_xor_sync(0xffffffffu, my_best, o);
-        my_best = other > my_best ? other : my_best;
+        for (int o = 16; o > 0; o >>= 1) {
+            pm = fmaxf(pm, __shfl_xor_sync(0xffffffffu, pm, o));
+            q2 = fmaxf(q2, __shfl_xor_sync(0xffffffffu, q2, o));
+        }
+        if ((tid & 31) == 0) {  // non-negative floats order like their bit patterns; NaN patterns compare above +inf
+            atomicMax(s_pmax, __float_as_uint(pm));
+            atomicMax(s_qmax2, __float_as_uint(q2));
+        }
+        __syncthreads();
+        Pm = __uint_as_float(*s_pmax) * 1.0001f;
+        Qm = sqrtf(__uint_as_float(*s_qmax2)) * 1.0001f;
     }
-    if ((tid & 31) == 0) atomicMax(s_best, my_best);
+
+    // ---- hypotheses in chunks of RANSAC_THREADS, in index order ----------------------------------
+    const float thr_f = (float)A.thr;
+    Interval iv[RANSAC_MAX_CHUNKS];
+    unsigned long long my_key = 0ull;  // this thread's best exact (count, index) key and its plane
+    float4 my_pl = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (use_filter && !verify) {
+        unsigned long long my_sel = 0ull;
+        int processed = 0;
+        bool stop = false;
+#pragma unroll
+        for (int k = 0; k < RANSAC_MAX_CHUNKS; ++k) {
+            iv[k].lo = 0;
+            iv[k].hi = -1;
+            if (k < nch && !stop) {  // CTA-uniform
+                const int t = k * RANSAC_THREADS + tid;
+                bool full = false;
+                if (t < A.H) {
+                    iv[k] = filter_hypothesis(s_q, A.r32t, A.H, A.K, t, n, Pm, Qm, thr_f);
+                    const unsigned long long key = pack_key(iv[k].lo, t);
+                    my_sel = key > my_sel ? key : my_sel;
+                    full = iv[k].lo == n;
+                    if ((A.flags & RANSAC_FLAG_STATS) && iv[k].hi - iv[k].lo == n) atomicAdd(&s_stat[0], 1u);
+                }
+                processed = k + 1;
+                // a hypothesis that certainly keeps every point cannot be beaten by a later index
+                stop = __syncthreads_or(full) != 0;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, my_sel, o);
+            my_sel = other > my_sel ? other : my_sel;
+        }
+        if ((tid & 31) == 0) atomicMax(s_sel, my_sel);
+        __syncthreads();
+        const unsigned long long sel = *s_sel;
+        const int M = (int)(sel >> 32);
+        const int t0 = (int)(0xffffffffu - (uint32_t)(sel & 0xffffffffull));
+        // candidates: everything that can still be the (count desc, index asc) maximum
+#pragma unroll
+        for (int k = 0; k < RANSAC_MAX_CHUNKS; ++k) {
+            const int t = k * RANSAC_THREADS + tid;
+            if (k < processed && t < A.H) {
+                const bool cand = (t < t0) ? (iv[k].hi >= M) : (t == t0 || iv[k].hi > M);
+                if (cand) s_cand[atomicAdd(s_nc, 1u)] = (uint16_t)t;
+            }
+        }
+        __syncthreads();
+        const int nc = (int)*s_nc;
+        for (int c0 = 0; c0 < nc; c0 += RANSAC_THREADS) {  // CTA-uniform trip count
+            const int c = c0 + tid;
+            const bool active = c < nc;
+            float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
+            int t = 0;
+            if (active) {
+                t = s_cand[c];
+                pl = fit_plane(pts, A.table, A.K, t, n, rs, A.err);
+            }
+            const int cnt = exact_count(pts, n, active, pl, A.thr);
+            if (active) {
+                const unsigned long long key = pack_key(cnt, t);
+                if (key > my_key) {
+                    my_key = key;
+                    my_pl = pl;
+                }
+            }
+        }
+        if (A.flags & RANSAC_FLAG_STATS) {
+            if (tid == 0) {
+                atomicAdd(&g_ransac_stats[0], 1ull);                                       // blocks
+                atomicAdd(&g_ransac_stats[1], (unsigned long long)min(processed * RANSAC_THREADS, A.H));  // filtered
+                atomicAdd(&g_ransac_stats[2], (unsigned long long)s_stat[0]);              // trivial intervals
+                atomicAdd(&g_ransac_stats[3], (unsigned long long)nc);                     // exact evaluations
+                atomicAdd(&g_ransac_stats[4], processed < nch ? 1ull : 0ull);              // early exits
+            }
+        }
+    } else {
+        // exact evaluation of every hypothesis (plus interval verification)
+        for (int k = 0; k < nch; ++k) {
+            const int t = k * RANSAC_THREADS + tid;
+            const bool active = t < A.H;
+            float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (active) pl = fit_plane(pts, A.table, A.K, t, n, rs, A.err);
+            const int cnt = exact_count(pts, n, active, pl, A.thr);
+            bool full = false;
+            if (active) {
+                const unsigned long long key = pack_key(cnt, t);
+                if (key > my_key) {
+                    my_key = key;
+                    my_pl = pl;
+                }
+                full = cnt == n;
+                if (use_filter) {  // verify mode
+                    const Interval v = filter_hypothesis(s_q, A.r32t, A.H, A.K, t, n, Pm, Qm, thr_f);
+                    if (cnt < v.lo || cnt > v.hi) {
+                        atomicOr(A.err, (uint32_t)DEVERR_FILTER_BOUND);
+                        atomicAdd(&s_stat[1], 1u);
+                    }
+                    if (v.hi - v.lo == n) atomicAdd(&s_stat[0], 1u);
+                }
+            }
+            // same early exit as the filtered path (not in verify mode: check every hypothesis)
+            if (!verify && __syncthreads_or(full)) break;
+        }
+        if (verify && tid == 0) {
+            atomicAdd(&g_ransac_stats[0], 1ull);
+            atomicAdd(&g_ransac_stats[1], (unsigned long long)A.H);
+            atomicAdd(&g_ransac_stats[2], (unsigned long long)s_stat[0]);
+            atomicAdd(&g_ransac_stats[5], (unsigned long long)s_stat[1]);  // interval violations
+        }
+    }
+
+    // ---- block-wide maximum of the exact keys; its owner publishes the plane -------------------------
+    {
+        unsigned long long wb = my_key;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, wb, o);
+            wb = other > wb ? other : wb;
+        }
+        if ((tid & 31) == 0) atomicMax(s_best, wb);
+    }
     __syncthreads();
     const unsigned long long bk = *s_best;
-    const int best_t = (int)(0xffffffffu - (uint32_t)(bk & 0xffffffffull));
-    const int best_cnt = (int)(bk >> 32);
-    const float4 bp = s_plane[best_t];
-    if (tid == 0) {
-        if (A.plane) reinterpret_cast<float4*>(A.plane)[b] = bp;
-        if (A.best) A.best[b] = best_t;
-        if (A.best_count) A.best_count[b] = best_cnt;
+    if (my_key == bk) {  // keys are unique per hypothesis: exactly one thread
+        *s_bp = my_pl;
+        if (A.plane) reinterpret_cast<float4*>(A.plane)[b] = my_pl;
+        if (A.best) A.best[b] = (int)(0xffffffffu - (uint32_t)(bk & 0xffffffffull));
+        if (A.best_count) A.best_count[b] = (int)(bk >> 32);
     }
+    __syncthreads();
+    const float4 bp = *s_bp;
     // ---- final mask (cuda_ransac.py:149-155) ---------------------------------------------------
     const double a = (double)bp.x, bb = (double)bp.y, c = (double)bp.z, d = (double)bp.w;
     for (int i = tid; i < n; i += RANSAC_THREADS) A.mask[(size_t)ps + i] = plane_distance(a, bb, c, d, pts + 3 * i) < A.thr ? 1 : 0;
+}
+
+
+// =============================================================================================
+// small blocks (n <= RS_MAX_POINTS): one WARP per block, persistent warps pulling work items.
+// Step 0 evaluates hypotheses 0..31 exactly.  If one of them keeps every point it is the winner (ties
+// go to the lowest index) - on LiDAR leaves that ends > 99 % of the blocks after 32 of 1024 hypotheses.
+// Otherwise hypotheses 32.. go through the FP32 interval pre-filter, 32 per step, and the surviving
+// candidates are evaluated exactly in index order.
+// =============================================================================================
+constexpr int RS_WARPS = 8;
+constexpr int RS_MAX_POINTS = 128;
+
+struct __align__(16) RansacWarpSmem {
+    double pts[RS_MAX_POINTS * 3 + 2];  // TMA destination (16-byte aligned run + optional 8-byte lead)
+    float4 q[RS_MAX_POINTS];            // block-local float32 copies; reused as the uint16 candidate list
+    uint8_t hi[RANSAC_MAX_H];           // upper bound of every filtered hypothesis
+    unsigned long long bar;
+    unsigned long long pad;
+};
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = other > v ? other : v;
+    }
+    return v;
+}
+
+__device__ __forceinline__ int exact_count_serial(const double* __restrict__ pts, int n, const float4 pl, double thr) {
+    const double a = (double)pl.x, b = (double)pl.y, c = (double)pl.z, d = (double)pl.w;
+    int cnt = 0;
+    for (int i = 0; i < n; ++i) cnt += plane_distance(a, b, c, d, pts + 3 * i) < thr;
+    return cnt;
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32, 3) ransac_small_kernel(RansacArgs A, uint32_t* __restrict__ counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RansacWarpSmem* sm = reinterpret_cast<RansacWarpSmem*>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    RansacWarpSmem& W = sm[threadIdx.x >> 5];
+    const uint32_t bar = smem_addr(&W.bar);
+    const bool verify = (A.flags & RANSAC_FLAG_VERIFY) != 0;
+    const bool filter_on = (verify || !(A.flags & RANSAC_FLAG_EXACT_ONLY)) && (__ldg(A.table_ok) != 0u);
+    const bool tma = !(A.flags & RANSAC_FLAG_NO_TMA);
+    const int nsteps = (A.H + 31) >> 5;
+    const float thr_f = (float)A.thr;
+    if (tma) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    uint32_t parity = 0;
+    uint32_t st_blocks = 0, st_filtered = 0, st_trivial = 0, st_exact = 0, st_early = 0, st_viol = 0;  // per-lane / per-warp tallies
+    for (;;) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(counter, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= A.n_work) break;
+        const uint32_t b = A.work[w];
+        const int n = A.blk_size[b];
+        if (n > RS_MAX_POINTS) continue;  // handled by the CTA-per-block kernel
+        const uint32_t ps = A.blk_start[b];
+        const long long rs = A.blk_ref_start[b];
+        const double* gsrc = A.points + (size_t)ps * 3;
+        const double* pts;
+        // ---- stage the block's float64 points (TMA bulk copy, completion on the warp's mbarrier) --
+        if (tma) {
+            const uintptr_t src_addr = reinterpret_cast<uintptr_t>(gsrc);
+            const uint32_t lead = (uint32_t)(src_addr & 15u);  // 0 or 8
+            const unsigned char* asrc = reinterpret_cast<const unsigned char*>(src_addr - lead);
+            const uint32_t total = lead + (uint32_t)n * 24u;
+            const uint32_t bulk = total & ~15u;
+            if (lane == 0) {
+                // order the previous item's generic-proxy reads before the async-proxy overwrite
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(bar, bulk);
+                tma_bulk_g2s(smem_addr(W.pts), asrc, bulk, bar);
+                if (total != bulk) W.pts[bulk / 8] = reinterpret_cast<const double*>(asrc)[bulk / 8];
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            __syncwarp();
+            pts = W.pts + lead / 8;
+        } else {
+            for (int i = lane; i < n * 3; i += 32) W.pts[i] = gsrc[i];
+            __syncwarp();
+            pts = W.pts;
+        }
+
+        unsigned long long my_key = 0ull;
+        float4 my_pl = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool done = false;
+        int k = 0;
+        // ---- exact steps: step 0 always; every step in EXACT_ONLY / VERIFY mode ---------------------
+        float Pm = 0.f, Qm = 0.f;
+        bool have_q = false;
+        auto prepare_filter = [&]() {
+            const double ox = pts[0], oy = pts[1], oz = pts[2];
+            float pm = 0.f, q2 = 0.f;
+            for (int j = lane; j < n; j += 32) {
+                const double x = pts[3 * j], y = pts[3 * j + 1], z = pts[3 * j + 2];
+                const float qx = (float)(x - ox), qy = (float)(y - oy), qz = (float)(z - oz);
+                W.q[j] = make_float4(qx, qy, qz, 0.f);
+                pm = fmaxf(pm, (float)(fabs(x) + fabs(y) + fabs(z)));
+                q2 = fmaxf(q2, fmaf(qx, qx, fmaf(qy, qy, qz * qz)));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                // bit-pattern max: NaN patterns order above +inf, so a NaN coordinate poisons the bound (=> trivial intervals)
+                pm = __uint_as_float(max(__float_as_uint(pm), __shfl_xor_sync(0xffffffffu, __float_as_uint(pm), o)));
+                q2 = __uint_as_float(max(__float_as_uint(q2), __shfl_xor_sync(0xffffffffu, __float_as_uint(q2), o)));
+            }
+            Pm = pm * 1.0001f;
+            Qm = sqrtf(q2) * 1.0001f;
+            have_q = true;
+            __syncwarp();
+        };
+        if (verify && filter_on) prepare_filter();
+        const int exact_steps = (filter_on && !verify) ? 1 : nsteps;
+        for (; k < exact_steps && !done; ++k) {
+            const int t = (k << 5) + lane;
+            if (t < A.H) {
+                const float4 pl = fit_plane(pts, A.table, A.K, t, n, rs, A.err);
+                const int cnt = exact_count_serial(pts, n, pl, A.thr);
+                const unsigned long long key = pack_key(cnt, t);
+                if (key > my_key) {
+                    my_key = key;
+                    my_pl = pl;
+                }
+                if (verify && filter_on) {
+                    const Interval v = filter_hypothesis(W.q, A.r32t, A.H, A.K, t, n, Pm, Qm, thr_f);
+                    if (cnt < v.lo || cnt > v.hi) {
+                        atomicOr(A.err, (uint32_t)DEVERR_FILTER_BOUND);
+                        ++st_viol;
+                    }
+                    if (v.hi - v.lo == n) ++st_trivial;
+                    ++st_filtered;
+                }
+            }
+            // a hypothesis that keeps every point cannot be beaten by a later index
+            if (!verify && __any_sync(0xffffffffu, (int)(my_key >> 32) == n)) done = true;
+        }
+        // ---- FP32 interval pre-filter for the remaining hypotheses ---------------------------------------
+        if (!done && k < nsteps) {
+            if (!have_q) prepare_filter();
+            const int cnt0 = (int)(warp_max_u64(my_key) >> 32);  // best exact count so far (lower indices)
+            unsigned long long my_sel = 0ull;                     // best (lower bound, index) among the filtered ones
+            int k_end = nsteps;
+            for (int kk = k; kk < nsteps; ++kk) {
+                const int t = (kk << 5) + lane;
+                bool full = false;
+                if (t < A.H) {
+                    const Interval v = filter_hypothesis(W.q, A.r32t, A.H, A.K, t, n, Pm, Qm, thr_f);
+                    W.hi[t] = (uint8_t)v.hi;
+                    const unsigned long long key = pack_key(v.lo, t);
+                    my_sel = key > my_sel ? key : my_sel;
+                    full = v.lo == n;
+                    if (v.hi - v.lo == n) ++st_trivial;
+                    ++st_filtered;
+                }
+                if (__any_sync(0xffffffffu, full)) {
+                    k_end = kk + 1;
+                    ++st_early;
+                    break;
+                }
+            }
+            const unsigned long long sel = warp_max_u64(my_sel);
+            const int M = (int)(sel >> 32);
+            const int t0 = (int)(0xffffffffu - (uint32_t)(sel & 0xffffffffull));
+            __syncwarp();
+            // candidates, in index order, into the (now dead) q area
+            uint16_t* list = reinterpret_cast<uint16_t*>(W.q);
+            int nc = 0;
+            for (int kk = k; kk < k_end; ++kk) {
+                const int t = (kk << 5) + lane;
+                bool cand = false;
+                if (t < A.H) {
+                    const int hi = W.hi[t];
+                    cand = hi > cnt0 && ((t < t0) ? (hi >= M) : (t == t0 || hi > M));
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, cand);
+                if (cand) list[nc + __popc(m & ((1u << lane) - 1u))] = (uint16_t)t;
+                nc += __popc(m);
+            }
+            __syncwarp();
+            for (int c0 = 0; c0 < nc; c0 += 32) {
+                const int c = c0 + lane;
+                if (c < nc) {
+                    const int t = list[c];
+                    const float4 pl = fit_plane(pts, A.table, A.K, t, n, rs, A.err);
+                    const int cnt = exact_count_serial(pts, n, pl, A.thr);
+                    const unsigned long long key = pack_key(cnt, t);
+                    if (key > my_key) {
+                        my_key = key;
+                        my_pl = pl;
+                    }
+                    ++st_exact;
+                }
+                if (__any_sync(0xffffffffu, (int)(my_key >> 32) == n)) break;  // later indices cannot win
+            }
+        } else if (done) {
+            ++st_early;
+        }
+        // ---- winner, outputs, mask (cuda_ransac.py:149-155) -----------------------------------------------
+        const unsigned long long bk = warp_max_u64(my_key);
+        const int src = __ffs(__ballot_sync(0xffffffffu, my_key == bk)) - 1;
+        float4 bp;
+        bp.x = __shfl_sync(0xffffffffu, my_pl.x, src);
+        bp.y = __shfl_sync(0xffffffffu, my_pl.y, src);
+        bp.z = __shfl_sync(0xffffffffu, my_pl.z, src);
+        bp.w = __shfl_sync(0xffffffffu, my_pl.w, src);
+        if (lane == 0) {
+            if (A.plane) reinterpret_cast<float4*>(A.plane)[b] = bp;
+            if (A.best) A.best[b] = (int)(0xffffffffu - (uint32_t)(bk & 0xffffffffull));
+            if (A.best_count) A.best_count[b] = (int)(bk >> 32);
+        }
+        const double a = (double)bp.x, bb = (double)bp.y, c = (double)bp.z, d = (double)bp.w;
+        for (int i = lane; i < n; i += 32) A.mask[(size_t)ps + i] = plane_distance(a, bb, c, d, pts + 3 * i) < A.thr ? 1 : 0;
+        ++st_blocks;
+        __syncwarp();
+    }
+    if (A.flags & (RANSAC_FLAG_STATS | RANSAC_FLAG_VERIFY)) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            st_filtered += __shfl_xor_sync(0xffffffffu, st_filtered, o);
+            st_trivial += __shfl_xor_sync(0xffffffffu, st_trivial, o);
+            st_exact += __shfl_xor_sync(0xffffffffu, st_exact, o);
+            st_viol += __shfl_xor_sync(0xffffffffu, st_viol, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&g_ransac_stats[0], (unsigned long long)st_blocks);
+            atomicAdd(&g_ransac_stats[1], (unsigned long long)st_filtered);
+            atomicAdd(&g_ransac_stats[2], (unsigned long long)st_trivial);
+            atomicAdd(&g_ransac_stats[3], (unsigned long long)st_exact);
+            atomicAdd(&g_ransac_stats[4], (unsigned long long)st_early);
+            atomicAdd(&g_ransac_stats[5], (unsigned long long)st_viol);
+        }
+    }
+}
+
+// work items whose block is too large for the warp kernel -> compact list for the CTA kernel
+__global__ void ransac_split_kernel(const uint32_t* __restrict__ work, uint32_t n_work, const int32_t* __restrict__ blk_size,
+                                    uint32_t* __restrict__ large, uint32_t* __restrict__ n_large) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool big = i < n_work && blk_size[work[i]] > RS_MAX_POINTS;
+    const uint32_t m = __ballot_sync(0xffffffffu, big);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(n_large, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (big) large[base + __popc(m & ((1u << lane) - 1u))] = work[i];
 }
 
 void launch_ransac(Ctx& c, const double* points, int64_t n_points, const uint32_t* blk_phys_start, const int32_t* blk_size,
@@ -230,6 +821,14 @@ void launch_ransac(Ctx& c, const double* points, int64_t n_points, const uint32_
                    const double* table, int H, int K, double threshold, uint8_t* mask, float* plane, int32_t* best,
                    int32_t* best_count, uint32_t flags) {
     if (n_work == 0) return;
+    OL_REQUIRE(H >= 1 && H <= RANSAC_MAX_H, OL_ERR_INVALID, "hypotheses_number must be in 1..1024");
+    DevBuf<uint32_t> r32t(c, (size_t)H * K), table_ok(c, 1);
+    {
+        const uint32_t one = 1u;
+        OL_CUDA(cudaMemcpyAsync(table_ok.get(), &one, 4, cudaMemcpyHostToDevice, c.stream));
+        ransac_table_prep_kernel<<<(H * K + 255) / 256, 256, 0, c.stream>>>(table, H, K, r32t.get(), table_ok.get());
+        OL_CHECK_LAUNCH();
+    }
     RansacArgs a{};
     a.points = points;
     a.n_points = n_points;
@@ -239,6 +838,8 @@ void launch_ransac(Ctx& c, const double* points, int64_t n_points, const uint32_
     a.work = work_list;
     a.n_work = n_work;
     a.table = table;
+    a.r32t = r32t.get();
+    a.table_ok = table_ok.get();
     a.H = H;
     a.K = K;
     a.thr = threshold;
@@ -250,11 +851,48 @@ void launch_ransac(Ctx& c, const double* points, int64_t n_points, const uint32_
     a.flags = flags;
     a.err = c.d_err;
     if (reinterpret_cast<uintptr_t>(points) & 15u) a.flags |= RANSAC_FLAG_NO_TMA;
-    size_t smem = 16 + (size_t)H * 16 + ((size_t)a.cap * 3 + 2) * 8;
-    smem = (smem + 15) & ~(size_t)15;
-    OL_CUDA(cudaFuncSetAttribute(ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ransac_kernel<<<n_work, RANSAC_THREADS, smem, c.stream>>>(a);
-    OL_CHECK_LAUNCH();
+    // ---- warp-per-block kernel: persistent warps over every work item (skips the large blocks) ------------
+    DevBuf<uint32_t> counters(c, 2);
+    counters.zero();
+    {
+        const size_t smem_small = sizeof(RansacWarpSmem) * RS_WARPS;
+        OL_CUDA(cudaFuncSetAttribute(ransac_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
+        int per_sm = 4;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ransac_small_kernel, RS_WARPS * 32, smem_small);
+        if (per_sm < 1) per_sm = 1;
+        const unsigned long long want = ((unsigned long long)n_work + RS_WARPS - 1) / RS_WARPS;
+        const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)c.num_sms * per_sm);
+        ransac_small_kernel<<<grid, RS_WARPS * 32, smem_small, c.stream>>>(a, counters.get());
+        OL_CHECK_LAUNCH();
+    }
+    // ---- CTA-per-block kernel for blocks above RS_MAX_POINTS points -------------------------------------------
+    if (max_block > (uint32_t)RS_MAX_POINTS) {
+        DevBuf<uint32_t> large(c, n_work);
+        ransac_split_kernel<<<(n_work + 255) / 256, 256, 0, c.stream>>>(work_list, n_work, blk_size, large.get(), counters.get() + 1);
+        OL_CHECK_LAUNCH();
+        uint32_t n_large = 0;
+        OL_CUDA(cudaMemcpyAsync(&n_large, counters.get() + 1, 4, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+        if (n_large) {
+            a.work = large.get();
+            a.n_work = n_large;
+            size_t smem = RANSAC_SMEM_HEADER + 2 * RANSAC_MAX_H + ((((size_t)a.cap * 3 + 2) * 8 + 15) & ~(size_t)15) + (size_t)a.cap * 16;
+            smem = (smem + 15) & ~(size_t)15;
+            OL_CUDA(cudaFuncSetAttribute(ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ransac_kernel<<<n_large, RANSAC_THREADS, smem, c.stream>>>(a);
+            OL_CHECK_LAUNCH();
+            c.sync();  // `large` is released on return
+        }
+    }
+}
+
+void ransac_stats_read(unsigned long long out[8], bool reset) {
+    OL_CUDA(cudaDeviceSynchronize());
+    OL_CUDA(cudaMemcpyFromSymbol(out, g_ransac_stats, sizeof(unsigned long long) * 8));
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        OL_CUDA(cudaMemcpyToSymbol(g_ransac_stats, z, sizeof(z)));
+    }
 }
 
 }  // namespace ol

@@ -28,7 +28,10 @@ def _check_against_oracle(pts, bs, table, thr, r: CudaRansac, mask):
     assert (mask == ora["mask"].astype(bool)).all(), "masks differ"
 
 
-@pytest.mark.parametrize("flags", [0, N.RANSAC_FLAG_NO_TMA])
+ALL_MODES = [0, N.RANSAC_FLAG_NO_TMA, N.RANSAC_FLAG_EXACT_ONLY, N.RANSAC_FLAG_VERIFY]
+
+
+@pytest.mark.parametrize("flags", ALL_MODES)
 @pytest.mark.parametrize("name", RANSAC_CASES)
 def test_evaluate_golden(name, flags):
     g = golden(name)
@@ -57,7 +60,8 @@ def test_evaluate_golden(name, flags):
 
 @pytest.mark.parametrize("seed,nblocks,maxn,H,K,thr", [(0, 400, 120, 1024, 6, 0.02), (1, 1500, 40, 256, 6, 0.01),
                                                         (2, 50, 3000, 512, 4, 0.015), (3, 300, 12, 100, 9, 0.03)])
-def test_evaluate_random_blocks(seed, nblocks, maxn, H, K, thr):
+@pytest.mark.parametrize("flags", [0, N.RANSAC_FLAG_VERIFY])
+def test_evaluate_random_blocks(seed, nblocks, maxn, H, K, thr, flags):
     rng = np.random.default_rng(seed)
     bs = rng.integers(0, maxn + 1, size=nblocks).astype(np.int32)
     n = int(bs.sum())
@@ -67,8 +71,90 @@ def test_evaluate_random_blocks(seed, nblocks, maxn, H, K, thr):
     pts = pts.astype(np.float32).astype(np.float64)
     np.random.seed(seed + 100)
     r = CudaRansac(threshold=thr, hypotheses_number=H, initial_points_number=K)
+    r.flags = flags
     mask = r.evaluate(pts, bs)
     _check_against_oracle(pts, bs, r.random_hypotheses, thr, r, mask)
+
+
+def _adversarial_blocks(rng):
+    """Blocks built to stress the FP32 pre-filter's error bounds: collinear and duplicated samples,
+    exactly planar data, tiny and huge extents, coordinates far from the origin, points sitting on the
+    threshold, scan-ring like lines."""
+    blocks = []
+
+    def add(p):
+        blocks.append(np.asarray(p, dtype=np.float64).reshape(-1, 3))
+
+    for n in (6, 7, 8, 12, 40):
+        t = rng.random(n)
+        add(np.c_[t, 2 * t, -t] + [5.0, -3.0, 1.0])                                   # exactly collinear
+        add(np.c_[t, 2 * t, -t] + rng.normal(0, 1e-7, (n, 3)) + [5.0, -3.0, 1.0])     # almost collinear
+        add(np.repeat(rng.random((2, 3)), (n + 1) // 2, axis=0)[:n])                  # two distinct points
+        add(np.repeat(rng.random((3, 3)), (n + 2) // 3, axis=0)[:n] * 3)              # three distinct points
+        xy = rng.random((n, 2))
+        add(np.c_[xy, np.zeros(n)])                                                   # exactly planar, axis aligned
+        add(np.c_[xy, 0.3 * xy[:, 0] - 0.7 * xy[:, 1]] + [1000.0, -2000.0, 50.0])     # planar, far from the origin
+        add(np.c_[xy, rng.normal(0, 0.01, n)] * 1e-4 + [812.0, 9.5, 0.1])             # tiny extent, far away
+        add(np.c_[xy, rng.normal(0, 0.01, n)] * 1e3)                                  # huge extent
+        add(np.c_[xy, rng.choice([0.0, 0.01, -0.01, 0.02], n)] + [100.0, 0.0, 0.0])   # distances exactly on thresholds
+        rings = np.repeat(np.arange(3), (n + 2) // 3)[:n] * 0.07                       # LiDAR-ring like rows
+        add(np.c_[np.arange(n) * 0.033, rings, rng.normal(0, 0.02, n)] + [30.0, 4.0, 0.0])
+        add(np.c_[xy * 0.1, rng.normal(0, 0.02, n)] + [1e5, 1e5, 10.0])               # float32 ulp ~ 8 mm of the coordinates
+        add(rng.normal(0, 1.0, (n, 3)) * [1.0, 1.0, 1e-3])                            # generic noisy plane
+        add(np.zeros((n, 3)))                                                         # all points at the origin
+    return blocks
+
+
+@pytest.mark.parametrize("thr", [0.01, 0.02, 1e-4])
+@pytest.mark.parametrize("H,K", [(1024, 6), (300, 3), (64, 9)])
+def test_prefilter_bounds_adversarial(H, K, thr):
+    """Filtered, exact-only and verify modes give the oracle's answer on inputs that stress the bounds;
+    verify mode additionally proves lo <= exact count <= hi for EVERY hypothesis (it raises otherwise)."""
+    rng = np.random.default_rng(1234)
+    blocks = _adversarial_blocks(rng)
+    pts = np.vstack(blocks)
+    pts32 = pts.astype(np.float32).astype(np.float64)
+    bs = np.array([len(b) for b in blocks], dtype=np.int32)
+    for cloud in (pts, pts32):
+        ora = None
+        for flags in (0, N.RANSAC_FLAG_VERIFY, N.RANSAC_FLAG_EXACT_ONLY):
+            np.random.seed(77)
+            r = CudaRansac(threshold=thr, hypotheses_number=H, initial_points_number=K)
+            r.flags = flags
+            mask = r.evaluate(cloud, bs)
+            if ora is None:
+                ora = oransac.ransac_evaluate(cloud, bs, r.random_hypotheses, thr, threads=8)
+            assert (r.last_best == ora["best"]).all(), f"flags {flags}: chosen hypothesis differs"
+            assert (r.last_best_count == ora["best_count"]).all()
+            assert (r.last_planes.view(np.uint32) == ora["plane"].view(np.uint32)).all()
+            assert (mask == ora["mask"].astype(bool)).all()
+
+
+def test_prefilter_statistics():
+    """The pre-filter must actually prune: on a LiDAR-like leaf set only a small share of the hypotheses
+    needs the exact float64 evaluation."""
+    import ctypes as C
+    lib = N.lib()
+    out = (C.c_uint64 * 8)()
+    N.check(lib.ol_ransac_stats_read(C.byref(out), 1))
+    clouds = lidar64_scan(0, seed=0)[::3]
+    grid = Grid(GridConfig(voxel_edge_length=1.0))
+    grid.insert_points(0, clouds)
+    grid.subdivide([MaxPoints(100)])
+    np.random.seed(3)
+    table = oransac.make_table(1024, 6)
+    host = grid._host
+    host.forest.ransac(table, 0.02, [0], 10, apply=False, flags=N.RANSAC_FLAG_STATS)
+    N.check(lib.ol_ransac_stats_read(C.byref(out), 1))
+    blocks, filtered, trivial, exact = out[0], out[1], out[2], out[3]
+    assert blocks > 0 and filtered > 0
+    assert exact < 0.25 * filtered, (blocks, filtered, trivial, exact)
+    res_a = host.forest.export_ransac()
+    host.forest.ransac(table, 0.02, [0], 10, apply=False, flags=N.RANSAC_FLAG_VERIFY)
+    res_b = host.forest.export_ransac()
+    for k in ("best", "best_count", "size"):
+        assert (res_a[k] == res_b[k]).all()
+    assert (res_a["plane"].view(np.uint32) == res_b["plane"].view(np.uint32)).all()
 
 
 def test_evaluate_edge_cases():
