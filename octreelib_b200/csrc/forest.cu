@@ -49,14 +49,22 @@ __global__ void __launch_bounds__(256) bbox_kernel(const double* __restrict__ xy
                                                    uint32_t* __restrict__ err) {
     long long mn[3] = {LLONG_MAX, LLONG_MAX, LLONG_MAX}, mx[3] = {LLONG_MIN, LLONG_MIN, LLONG_MIN};
     bool bad = false;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            double v = xyz[i * 3 + a];
-            if (!isfinite(v)) bad = true;
-            long long k = double_to_ordered(v);
-            mn[a] = k < mn[a] ? k : mn[a];
-            mx[a] = k > mx[a] ? k : mx[a];
+    // flat, fully coalesced walk over the 3n doubles; the axis of element e is e mod 3
+    const size_t total = n * 3, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const double v = xyz[e];
+        const int a = (int)(e % 3);
+        if (!isfinite(v)) bad = true;
+        const long long k = double_to_ordered(v);
+        if (a == 0) {
+            mn[0] = k < mn[0] ? k : mn[0];
+            mx[0] = k > mx[0] ? k : mx[0];
+        } else if (a == 1) {
+            mn[1] = k < mn[1] ? k : mn[1];
+            mx[1] = k > mx[1] ? k : mx[1];
+        } else {
+            mn[2] = k < mn[2] ? k : mn[2];
+            mx[2] = k > mx[2] ? k : mx[2];
         }
     }
 #pragma unroll

@@ -16,7 +16,8 @@ struct Forest {
     // ---- raw input, indexed by the global point rank r (insertion order) -----------------------
     DevBuf<double> P64;          // [cap][3]
     size_t cap = 0, N = 0;
-    DevBuf<uint8_t> alive_r;     // [cap] 1 = point still stored (filter / RANSAC masks clear it)
+    size_t bbox_done = 0;        // points already folded into d_bbox / checked for NaN
+    DevBuf<uint8_t> alive_r;     // [cap] 1 = point still stored; allocated by the first removal (filter / RANSAC mask)
     bool any_dead = false;
     bool base_dirty = false;     // base order still contains dead points
     std::vector<uint32_t> seg_start;  // host: first rank of every segment (+ sentinel N)

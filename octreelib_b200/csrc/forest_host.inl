@@ -84,24 +84,20 @@ int Forest::insert(const double* xyz, int64_t n, bool on_device, const int64_t* 
     if (N + (size_t)n > cap) {
         size_t ncap = std::max<size_t>(N + (size_t)n, cap + cap / 2 + 1024);
         DevBuf<double> np(ctx, ncap * 3);
-        DevBuf<uint8_t> na(ctx, ncap);
         d2d(ctx, np.get(), P64.get(), N * 3);
-        d2d(ctx, na.get(), alive_r.get(), N);
         P64.swap(np);
-        alive_r.swap(na);
+        if (alive_r.get()) {  // only exists once something was removed (apply_keep)
+            DevBuf<uint8_t> na(ctx, ncap);
+            d2d(ctx, na.get(), alive_r.get(), N);
+            OL_CUDA(cudaMemsetAsync(na.get() + N, 1, ncap - N, ctx.stream));
+            alive_r.swap(na);
+        }
         cap = ncap;
     }
-    if (n > 0) {
+    // one copy per insert; the bounding box / non-finite check of the new points runs once, in build()
+    if (n > 0)
         OL_CUDA(cudaMemcpyAsync(P64.get() + N * 3, xyz, (size_t)n * 24, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                 ctx.stream));
-        OL_CUDA(cudaMemsetAsync(alive_r.get() + N, 1, (size_t)n, ctx.stream));
-        unsigned g = std::min<unsigned>(nblk((size_t)n), (unsigned)ctx.num_sms * 2);
-        {
-            ProfScope ps(ctx, "bbox");
-            bbox_kernel<<<g, 256, 0, ctx.stream>>>(P64.get() + N * 3, (size_t)n, d_bbox.get(), d_err.get());
-            OL_CHECK_LAUNCH();
-        }
-    }
     int pose_index;
     if (n_segments <= 0) {
         pose_index = n_poses;
@@ -141,6 +137,14 @@ int Forest::insert(const double* xyz, int64_t n, bool on_device, const int64_t* 
 // ---------------------------------------------------------------------------------------------
 void Forest::build() {
     if (built) return;
+    if (bbox_done < N) {  // K0 over everything inserted since the last build
+        const size_t m = N - bbox_done;
+        unsigned g = std::min<unsigned>(nblk(m), (unsigned)ctx.num_sms * 8);
+        ProfScope ps(ctx, "bbox", (double)m);
+        bbox_kernel<<<g, 256, 0, ctx.stream>>>(P64.get() + bbox_done * 3, m, d_bbox.get(), d_err.get());
+        OL_CHECK_LAUNCH();
+        bbox_done = N;
+    }
     check_device_errors();
     upload_segments();
     const int S = (int)seg_pose.size();
@@ -600,6 +604,10 @@ void Forest::apply_keep(const uint8_t* keep_pos) {
     if (total == n) return;
     DevBuf<uint32_t> p2(ctx, total), l2(ctx, total), s2(ctx, (size_t)L + 1);
     DevBuf<uint64_t> m2(ctx, total);
+    if (!alive_r.get()) {  // first removal: every inserted point was alive so far
+        alive_r.reset(ctx, cap);
+        OL_CUDA(cudaMemsetAsync(alive_r.get(), 1, cap, ctx.stream));
+    }
     {
         ProfScope ps(ctx, "compact");
         compact_pos_kernel<<<nblk(n), 256, 0, ctx.stream>>>(flags.get(), scan.get(), n, perm.get(), mort.get(), leaf_of.get(),

@@ -9,6 +9,7 @@ in the CUDA library; nothing here falls back to the CPU.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import Optional, Sequence
 
@@ -17,6 +18,9 @@ import numpy as np
 from . import _native as N
 
 __all__ = ["Forest", "TorchAllocator", "require_cuda"]
+
+
+_NULL_SCOPE = contextlib.nullcontext()
 
 
 def require_cuda():
@@ -70,6 +74,7 @@ class Forest:
         self._torch = torch
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._stream = torch.cuda.current_stream(self.device)
+        self._raw_stream = self._stream.cuda_stream
         self._allocator = TorchAllocator(self.device)
         cfg = N.ForestConfig()
         cfg.voxel_edge_length = float(edge)
@@ -87,6 +92,14 @@ class Forest:
         self.version = 0  # bumped by every mutating call; hosts cache exports per version
 
     def _scope(self):
+        """Context in which torch's current stream is the forest's stream (the allocator callbacks allocate
+        on the current stream).  Entering torch.cuda.stream() costs ~12 us, so it is skipped when the
+        caller already is on that stream - the common case."""
+        try:
+            if self._torch._C._cuda_getCurrentRawStream(self.device.index) == self._raw_stream:
+                return _NULL_SCOPE
+        except AttributeError:  # private torch API moved: fall back to the public, slower path
+            pass
         return self._torch.cuda.stream(self._stream)
 
     def close(self):
@@ -129,7 +142,10 @@ class Forest:
             t = points
             if t.device.type != "cuda":
                 return self._as_source(t.numpy())
-            t = t.to(torch.float64).contiguous().reshape(-1, 3)
+            if t.dtype != torch.float64 or not t.is_contiguous():
+                t = t.to(torch.float64).contiguous()
+            if t.dim() != 2 or t.shape[1] != 3:
+                t = t.reshape(-1, 3)
             return C.c_void_p(t.data_ptr()), t.shape[0], 1, t
         a = np.ascontiguousarray(np.asarray(points), dtype=np.float64)
         if a.size == 0:
