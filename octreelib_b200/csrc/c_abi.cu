@@ -12,6 +12,7 @@ struct ol_forest {
 
 namespace ol {
 unsigned long long g_launch_count = 0;
+bool g_force_legacy_sort = false;
 static thread_local std::string g_last_error;
 void set_last_error(int code, const std::string& msg) { g_last_error = "[ol_status " + std::to_string(code) + "] " + msg; }
 }  // namespace ol
@@ -303,6 +304,11 @@ int ol_ransac_stats_read(uint64_t out[8], int32_t reset) {
 }
 
 // ---- primitives ---------------------------------------------------------------------------------
+int ol_debug_force_legacy_sort(int32_t on) {
+    ol::g_force_legacy_sort = on != 0;
+    return OL_OK;
+}
+
 int ol_sort_pairs_u64(void* stream, uint64_t* keys_dev, uint32_t* vals_dev, int64_t n, int32_t begin_bit, int32_t end_bit,
                       ol_alloc_fn alloc, ol_free_fn free_fn, void* alloc_user) {
     OL_API_BEGIN

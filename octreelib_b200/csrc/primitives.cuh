@@ -3,6 +3,7 @@
 // temporaries come from Ctx::alloc.
 #pragma once
 #include "common.cuh"
+#include "onesweep.cuh"
 
 namespace ol {
 
@@ -235,13 +236,16 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(const KeyT*
 }
 
 // Sorts (keys0, vals0) by bits [begin_bit, end_bit) using (keys1, vals1) as the alternate buffer.
-// Returns 0 if the result is in buffer 0, 1 if it is in buffer 1.
+// Returns 0 if the result is in buffer 0, 1 if it is in buffer 1.  Onesweep (onesweep.cuh) below 2^30
+// pairs; the three-kernel LSD sort in this file above that (and when g_force_legacy_sort is set: tests).
+extern bool g_force_legacy_sort;
 template <typename KeyT>
 inline int radix_sort_pairs(Ctx& c, KeyT* keys0, KeyT* keys1, uint32_t* vals0, uint32_t* vals1, size_t n, int begin_bit,
                             int end_bit) {
     OL_REQUIRE(n < (1ull << 31), OL_ERR_INVALID, "radix_sort_pairs: n must be < 2^31");
     int bits = end_bit - begin_bit;
     if (n <= 1 || bits <= 0) return 0;
+    if (n < (1ull << 30) && !g_force_legacy_sort) return onesweep_sort_pairs<KeyT>(c, keys0, keys1, vals0, vals1, n, begin_bit, end_bit);
     int passes = (bits + 7) / 8;
     int per = (bits + passes - 1) / passes;
     uint32_t tiles = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);

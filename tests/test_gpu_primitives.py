@@ -52,3 +52,23 @@ def test_sort_all_equal_and_presorted():
     keys = np.arange(n, dtype=np.uint64)
     gk, gv = sort_pairs(keys, vals[::-1].copy(), 0, 17)
     assert (gk == keys).all() and (gv == vals[::-1]).all()
+
+
+@pytest.mark.parametrize("n", [4097, 250_000])
+def test_legacy_sort_path_agrees_with_onesweep(n):
+    """radix_sort_pairs uses onesweep below 2^30 pairs and the three-kernel LSD sort above it; the
+    legacy path is kept honest by forcing it here."""
+    from octreelib_b200 import _native as N
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << 40, size=n, dtype=np.uint64)
+    keys[::5] = keys[1]
+    vals = np.arange(n, dtype=np.uint32)
+    a = sort_pairs(keys, vals, 0, 40)
+    N.lib().ol_debug_force_legacy_sort(1)
+    try:
+        b = sort_pairs(keys, vals, 0, 40)
+    finally:
+        N.lib().ol_debug_force_legacy_sort(0)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+    order = np.argsort(keys, kind="stable")
+    assert (a[1] == vals[order]).all()
