@@ -196,7 +196,7 @@ def run_step(clouds, numbers, n_poses_total, w, world, profile=False, read_table
         planes = forest.export_ransac(scored_only=True)
         leaves = forest.export_leaves()
         d2h = sum(a.nbytes for a in planes.values()) + sum(a.nbytes for a in leaves.values())
-    stats = forest.stats()  # synchronises; the step's scalar result
+    stats = forest.stats(light=True)  # waits for the step; the step's scalar results (alive points, leaves, ...)
     prof = forest.profile_read() if profile else None
     return grid, stats, prof, d2h
 
@@ -383,7 +383,7 @@ def main():
                             "CUDA-event durations)"}
     out = dict(base, value=value, ms_per_step=ms_per_step, dtype="f64", clocks=clocks, gpu_launches=int(launches),
                stage_ms=stage_ms, stages=stages,
-               result={k: stats[k] for k in ("n_points_inserted", "n_points_alive", "n_cells", "n_leaves", "n_blocks",
+               result={k: stats[k] for k in ("n_points_inserted", "n_points_alive", "n_cells", "n_leaves",
                                              "max_depth_reached", "key_bits", "device_bytes_peak")},
                n_poses=P)
     if roofline:

@@ -143,6 +143,9 @@ uint64_t ol_launch_count(void);
 
 /* ---- counters: Grid.n_leaves / n_points / n_nodes, grid/grid.py:343-362 ---------------------- */
 int ol_forest_stats_get(ol_forest *f, ol_forest_stats *out);
+/* same, but builds no derived table: n_blocks / max_block_size are -1 when the (pose, leaf) block table is stale
+ * (after a filter / RANSAC mask); synchronises the stream, so it doubles as the step's completion point */
+int ol_forest_stats_light(ol_forest *f, ol_forest_stats *out);
 /* out[p] = {n_leaves, n_points, n_nodes} for pose index p, [n_poses][3] int64 */
 int ol_forest_pose_counts(ol_forest *f, int64_t *out_host);
 

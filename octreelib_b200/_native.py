@@ -70,6 +70,7 @@ SIGNATURES = {
     "ol_forest_profile_read": (C.c_int, [_p, C.c_char_p, _i64, C.POINTER(_i64)]),
     "ol_launch_count": (_u64, []),
     "ol_forest_stats_get": (C.c_int, [_p, C.POINTER(ForestStats)]),
+    "ol_forest_stats_light": (C.c_int, [_p, C.POINTER(ForestStats)]),
     "ol_forest_pose_counts": (C.c_int, [_p, _p]),
     "ol_forest_export_cells": (C.c_int, [_p, _p, _p, _p, _p, _p]),
     "ol_forest_export_cell_poses": (C.c_int, [_p, _p, _p]),

@@ -151,6 +151,14 @@ int ol_forest_profile_read(ol_forest* f, char* buf, int64_t buf_len, int64_t* ou
 
 uint64_t ol_launch_count(void) { return ol::g_launch_count; }
 
+int ol_forest_stats_light(ol_forest* f, ol_forest_stats* out) {
+    OL_NEED(f);
+    OL_NEED(out);
+    OL_API_BEGIN
+    f->impl.stats(out, true);
+    OL_API_END
+}
+
 int ol_forest_stats_get(ol_forest* f, ol_forest_stats* out) {
     OL_NEED(f);
     OL_NEED(out);

@@ -218,7 +218,7 @@ inline unsigned grid_for(size_t n, int threads) { return (unsigned)((n + threads
 // /root/reference/octreelib/grid/grid.py:72-76.  fmod is exact on host and device, the rest is
 // plain IEEE add/sub/div (the library is compiled with -fmad=false), so host and device agree.
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ inline double npy_floor_divide(double a, double b) {
+__host__ __device__ inline double npy_floor_divide_ref(double a, double b) {
     if (b == 0.0) return a / b;
     double mod = fmod(a, b);
     double div = (a - mod) / b;
@@ -235,6 +235,20 @@ __host__ __device__ inline double npy_floor_divide(double a, double b) {
         floordiv = copysign(0.0, a / b);
     }
     return floordiv;
+}
+
+// Fast path used by the kernels.  For finite a and finite b > 0 with |a / b| < 2^51 numpy's result above IS the
+// exact mathematical floor(a / b) (fmod is exact, the rest only snaps (a - mod) / b back to the integer it
+// approximates).  The same integer is obtained without the iterative fmod: q0 = floor(fl(a / b)) is either the
+// exact floor k or k + 1 (rounding to nearest is monotone and k, k + 1 are representable, so k <= fl(a / b) <= k + 1),
+// and it is k + 1 exactly when the residual a - q0 b is negative; the single-rounded fma keeps that sign.
+// tests/test_cpu_native_host.py checks this against numpy on random and adversarial operands.
+__host__ __device__ inline double npy_floor_divide(double a, double b) {
+    if (!(b > 0.0) || !(fabs(a) < 1.7e308) || !(b < 1.7e308)) return npy_floor_divide_ref(a, b);
+    double q = floor(a / b);
+    if (!(fabs(q) < 2251799813685248.0)) return npy_floor_divide_ref(a, b);  // 2^51
+    if (fma(-q, b, a) < 0.0) q -= 1.0;
+    return q;
 }
 
 // order-preserving map double -> int64 (for atomicMin/atomicMax on coordinates)

@@ -144,6 +144,29 @@ __global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ 
     if (e) atomicOr(err, e);
 }
 
+// Morton codes of already ordered points at a (deeper) depth: position i holds point perm[i] of cell
+// cell_of[i] (or lcell[cell_of[i]] when lcell != nullptr, i.e. cell_of is the leaf index).
+__global__ void __launch_bounds__(256) remorton_kernel(const double* __restrict__ xyz, const uint32_t* __restrict__ perm,
+                                                       const uint32_t* __restrict__ cell_of, const uint32_t* __restrict__ lcell,
+                                                       const uint64_t* __restrict__ cell_key, KeyParams kp, uint32_t n,
+                                                       uint64_t* __restrict__ mort) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t r = perm[i];
+    uint32_t c = cell_of[i];
+    if (lcell) c = lcell[c];
+    long long q[3] = {0, 0, 0};
+    if (!kp.single_cell) unpack_cell(kp, cell_key[c], q);
+    const double p[3] = {xyz[r * 3], xyz[r * 3 + 1], xyz[r * 3 + 2]};
+    double c0[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) c0[a] = cell_corner_coord(q[a], kp.corner[a], kp.edge, kp.single_cell);
+    int bad;
+    uint64_t m = point_morton(p, c0, kp.edge, kp.depth, &bad);
+    if (bad < kp.depth) m |= MORTON_BAD_BIT;
+    mort[i] = m;
+}
+
 // =============================================================================================
 // K3: run-length segmentation of the sorted keys
 // =============================================================================================

@@ -8,6 +8,8 @@
 
 namespace ol {
 
+constexpr int MORTON_INITIAL_DEPTH = 8;
+
 struct Forest {
     Ctx ctx;
     ol_forest_config cfg{};
@@ -103,6 +105,7 @@ struct Forest {
                const int64_t* seg_first_in, int n_segments, int n_poses_total);
     void build();            // K1-K3: keygen, sort, cells
     void compact_base();     // drop dead points from the base order
+    void extend_morton();    // Morton codes at the full depth (lazy: MORTON_INITIAL_DEPTH levels first)
     void reset_shape();      // current := base (every cell one leaf)
     void subdivide(int64_t max_points, const uint8_t* table, int64_t table_len, int beyond, const int32_t* poses,
                    int n_poses_listed);  // K4
@@ -117,7 +120,7 @@ struct Forest {
     void apply_mask();
     void apply_pose_mask(const int32_t* pose_rank, int pose, const uint8_t* mask_host, int64_t n);
     void pose_counts(int64_t* out_host);
-    void stats(ol_forest_stats* s);
+    void stats(ol_forest_stats* s, bool light = false);
     std::string profile_report();  // "name count total_ms" per line; clears the records
     void export_cells(int64_t* q, double* corner, int32_t* first_pose, int64_t* n_nodes, int64_t* leaf_begin);
     void export_cell_poses(int32_t* cell, int32_t* pose);

@@ -152,7 +152,7 @@ void Forest::build() {
     kp.edge = cfg.voxel_edge_length;
     for (int a = 0; a < 3; ++a) kp.corner[a] = cfg.corner[a];
     kp.single_cell = cfg.single_cell;
-    kp.depth = max_depth;
+    kp.depth = std::min(max_depth, MORTON_INITIAL_DEPTH);  // deeper levels are computed on demand (extend_morton)
     kp.pose_bits = segs_pose_monotone ? 0 : bit_length_u64((uint64_t)std::max(n_poses - 1, 0));
     int bits[3] = {0, 0, 0};
     if (!cfg.single_cell && N > 0) {
@@ -301,6 +301,24 @@ void Forest::compact_base() {
     base_dirty = false;
 }
 
+// The Morton codes carry MORTON_INITIAL_DEPTH levels at first (3 bits each); a subdivision that goes deeper
+// recomputes them at the full depth for the base order and for the current order.
+void Forest::extend_morton() {
+    if (kp.depth >= max_depth) return;
+    kp.depth = max_depth;
+    ProfScope ps(ctx, "keygen", (double)(A0 + (shaped ? A : 0)));
+    if (A0) {
+        remorton_kernel<<<nblk(A0), 256, 0, ctx.stream>>>(P64.get(), perm0.get(), cellidx0.get(), nullptr, cell_key.get(), kp, A0,
+                                                          mort0.get());
+        OL_CHECK_LAUNCH();
+    }
+    if (shaped && A) {
+        remorton_kernel<<<nblk(A), 256, 0, ctx.stream>>>(P64.get(), perm.get(), leaf_of.get(), lcell.get(), cell_key.get(), kp, A,
+                                                         mort.get());
+        OL_CHECK_LAUNCH();
+    }
+}
+
 // current shape := one leaf per cell
 void Forest::reset_shape() {
     build();
@@ -404,6 +422,7 @@ void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t ta
         if (n_split == 0) break;
         OL_REQUIRE((unsigned long long)I + n_split < (1ull << 29), OL_ERR_RANGE, "too many internal nodes");
         depth_reached = level + 1;
+        if (level >= kp.depth) extend_morton();
         const int shift = 3 * (kp.depth - 1 - level);
         DevBuf<uint32_t> Sbeg(ctx, (size_t)n_split * 8), Send(ctx, (size_t)n_split * 8);
         Sbeg.zero();

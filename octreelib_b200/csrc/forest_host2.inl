@@ -401,8 +401,13 @@ void Forest::pose_counts(int64_t* out_host) {
         for (int k = 0; k < 3; ++k) out_host[(size_t)p * 3 + k] = (int64_t)h[(size_t)p * 3 + k];
 }
 
-void Forest::stats(ol_forest_stats* s) {
-    ensure_blocks();
+void Forest::stats(ol_forest_stats* s, bool light) {
+    if (light) {  // no derived table is (re)built: block fields are -1 when the block table is stale
+        ensure_shape();
+        ctx.sync();
+    } else {
+        ensure_blocks();
+    }
     memset(s, 0, sizeof(*s));
     s->n_points_inserted = (int64_t)N;
     s->n_points_alive = A;
@@ -411,8 +416,8 @@ void Forest::stats(ol_forest_stats* s) {
     s->n_cell_poses = CP;
     s->n_leaves = L;
     s->n_internal = I;
-    s->n_blocks = NB;
-    s->max_block_size = max_block;
+    s->n_blocks = blocks_valid ? (int64_t)NB : -1;
+    s->max_block_size = blocks_valid ? (int64_t)max_block : -1;
     s->max_depth_reached = depth_reached;
     s->key_bits = key_bits;
     s->device_bytes_peak = (int64_t)ctx.bytes_peak;

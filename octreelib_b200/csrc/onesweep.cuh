@@ -18,8 +18,8 @@
 
 namespace ol {
 
-constexpr int OS_THREADS = 512;
-constexpr int OS_ITEMS = 8;
+constexpr int OS_THREADS = 256;
+constexpr int OS_ITEMS = 16;
 constexpr int OS_TILE = OS_THREADS * OS_ITEMS;
 constexpr int OS_WARPS = OS_THREADS / 32;
 constexpr int OS_MAX_PASSES = 8;
@@ -130,7 +130,7 @@ __device__ __forceinline__ void os_st_status(uint32_t* p, uint32_t v) {
 }
 
 template <typename KeyT>
-__global__ void __launch_bounds__(OS_THREADS, (sizeof(KeyT) == 8 ? 2 : 3)) os_pass_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+__global__ void __launch_bounds__(OS_THREADS, (sizeof(KeyT) == 8 ? 3 : 4)) os_pass_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                              KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                              const uint32_t* __restrict__ gbase /*[256] exclusive digit offsets*/,
                                                              uint32_t* __restrict__ status /*[tiles][256]*/,

@@ -222,10 +222,13 @@ class Forest:
         t = self._torch.empty(n * np.dtype(dtype).itemsize, dtype=self._torch.uint8, pin_memory=True)
         return t.numpy().view(dtype).reshape(shape)
 
-    def stats(self) -> dict:
+    def stats(self, light: bool = False) -> dict:
+        """Counters of the forest.  light=True builds no derived table (n_blocks / max_block_size are -1 when
+        the block table is stale) and only waits for the enqueued work."""
         s = N.ForestStats()
+        fn = self._lib.ol_forest_stats_light if light else self._lib.ol_forest_stats_get
         with self._scope():
-            N.check(self._lib.ol_forest_stats_get(self._h, C.byref(s)))
+            N.check(fn(self._h, C.byref(s)))
         return {name: int(getattr(s, name)) for name, _ in s._fields_}
 
     def pose_counts(self, n_poses: int) -> np.ndarray:

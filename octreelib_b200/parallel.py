@@ -110,7 +110,18 @@ class ShardedGrid:
 
     def exchange(self):
         """Route every staged point to the rank that owns its cell (one NCCL all-to-all)."""
+        import os
+        import time
         torch = require_cuda()
+        timing = os.environ.get("OL_TIMING") == "1"
+        marks = []
+
+        def mark(name):
+            if timing:
+                torch.cuda.synchronize()
+                marks.append((name, time.perf_counter()))
+
+        mark("start")
         lib = N.lib()
         dev = self._host.forest.device
         stream = torch.cuda.current_stream(dev)
@@ -121,6 +132,7 @@ class ShardedGrid:
         numbers = [p for p, _ in self._staged]
         sizes = np.array([int(t.shape[0]) for t in parts] or [0], dtype=np.int64)
         local = torch.cat(parts) if parts else torch.empty((0, 3), dtype=torch.float64, device=dev)
+        mark("stage")
         n, n_seg = int(local.shape[0]), max(len(parts), 1)
         send = torch.empty_like(local)
         counts = np.zeros((self.world, n_seg), dtype=np.int64)
@@ -130,12 +142,15 @@ class ShardedGrid:
                                           sizes.ctypes.data_as(C.c_void_p), n_seg, float(self._cfg.voxel_edge_length),
                                           C.byref(corner), self.world, C.c_void_p(send.data_ptr()),
                                           counts.ctypes.data_as(C.c_void_p), alloc.alloc_cb, alloc.free_cb, None))
+        mark("partition")
         send_counts = routing_layout(counts[:, :len(parts)] if parts else counts[:, :0], numbers, self.n_poses_total)
         if self.world > 1:
             recv, recv_counts = exchange_points(send, send_counts, self._group)
         else:
             recv, recv_counts = send, send_counts
+        mark("all_to_all")
         seg_sizes, seg_pose, seg_first = segments_from_counts(recv_counts)
+        mark("segments")
         if len(seg_sizes) == 0:
             seg_sizes, seg_pose, seg_first = np.array([0], np.int64), np.array([0], np.int32), np.array([0], np.int64)
         self._host.forest.insert_segments(recv, seg_sizes, seg_pose, seg_first, self.n_poses_total)
@@ -143,6 +158,9 @@ class ShardedGrid:
                                   kept=int(send_counts[self.rank].sum()))
         self._staged = []
         self.exchanged = True
+        mark("insert")
+        if timing and self.rank == 0:
+            print("[exchange] " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f} ms" for a, b in zip(marks, marks[1:])), flush=True)
 
     # ---- local pipeline -------------------------------------------------------------------------
     def subdivide(self, subdivision_criteria, pose_numbers: Optional[Sequence[int]] = None):

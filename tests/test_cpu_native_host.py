@@ -35,6 +35,25 @@ def test_floor_divide_matches_numpy():
         assert (want == got).all(), b
 
 
+def test_floor_divide_fast_path_adversarial():
+    """The kernels use q = floor(a / b) corrected by the sign of fma(-q, b, a) instead of numpy's fmod-based
+    formula (csrc/common.cuh); both must give the same integer, also next to multiples of b, for quotients up
+    to 2^50 and for edges that are not exactly representable."""
+    lib = _native.lib()
+    rng = np.random.default_rng(1)
+    for b in [1.0, 0.1, 0.3, 1.0 / 3.0, 0.7, 2.5, 1e-3, 1e-6, 123.456, 2.0 ** -20, 3e7]:
+        k = np.concatenate([rng.integers(-10 ** 6, 10 ** 6, 3000), rng.integers(-2 ** 50, 2 ** 50, 1000), [0, 1, -1, 2, -2]])
+        base = k.astype(np.float64) * b  # (rounded) multiples of b
+        cand = [base, np.nextafter(base, np.inf), np.nextafter(base, -np.inf), base + b * 0.5, base * (1 + 2.0 ** -52),
+                base * (1 - 2.0 ** -52), np.nextafter(np.nextafter(base, np.inf), np.inf)]
+        a = np.concatenate(cand)
+        a = a[np.isfinite(a)]
+        want = np.floor_divide(a, b)
+        got = np.array([lib.ol_host_floor_divide(float(x), float(b)) for x in a])
+        bad = np.flatnonzero(want != got)
+        assert len(bad) == 0, (b, a[bad[:5]], want[bad[:5]], got[bad[:5]])
+
+
 def _host_key(lib, edge, corner, single, depth, p):
     q = (C.c_int64 * 3)()
     m = C.c_uint64()
