@@ -13,6 +13,7 @@ struct ol_forest {
 namespace ol {
 unsigned long long g_launch_count = 0;
 bool g_force_legacy_sort = false;
+int g_os_variant = 0;
 static thread_local std::string g_last_error;
 void set_last_error(int code, const std::string& msg) { g_last_error = "[ol_status " + std::to_string(code) + "] " + msg; }
 }  // namespace ol
@@ -312,6 +313,11 @@ int ol_ransac_stats_read(uint64_t out[8], int32_t reset) {
 }
 
 // ---- primitives ---------------------------------------------------------------------------------
+int ol_debug_sort_variant(int32_t variant) {
+    ol::g_os_variant = variant;
+    return OL_OK;
+}
+
 int ol_debug_force_legacy_sort(int32_t on) {
     ol::g_force_legacy_sort = on != 0;
     return OL_OK;

@@ -93,6 +93,10 @@ struct Forest {
     uint32_t res_n = 0;          // snapshot of the block table in reference order, with the planes
     DevBuf<int32_t> res_pose, res_leaf, res_size, res_best, res_count;  // [res_n]
     DevBuf<float> res_plane;     // [res_n][4]
+    bool snap_pending = false;   // res_* not gathered yet: raw per-block arrays of the last run (block-table order)
+    DevBuf<uint32_t> sn_ref_order, sn_leaf;
+    DevBuf<int32_t> sn_pose, sn_size, sn_best, sn_count;
+    DevBuf<float> sn_plane;
     bool sample_oob_seen = false;
     uint32_t last_ransac_work = 0;  // blocks scored by the last RANSAC launch
     Profiler prof;
@@ -118,6 +122,8 @@ struct Forest {
     void ransac(const double* table_host, int H, int K, double threshold, const int32_t* pose_rank, int ppb, bool apply,
                 uint32_t flags);
     void apply_mask();
+    void materialize_snapshot();
+    void drop_snapshot();
     void apply_pose_mask(const int32_t* pose_rank, int pose, const uint8_t* mask_host, int64_t n);
     void pose_counts(int64_t* out_host);
     void stats(ol_forest_stats* s, bool light = false);

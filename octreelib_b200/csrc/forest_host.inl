@@ -78,6 +78,7 @@ int Forest::insert(const double* xyz, int64_t n, bool on_device, const int64_t* 
                    const int64_t* seg_first_in, int n_segments, int n_poses_total) {
     OL_REQUIRE(n >= 0, OL_ERR_INVALID, "negative point count");
     OL_REQUIRE(N + (size_t)n < (1ull << 31), OL_ERR_INVALID, "more than 2^31 - 1 points per forest are not supported");
+    materialize_snapshot();
     OL_REQUIRE(!(shaped && I > 0), OL_ERR_STATE,
                "inserting a pose after the grid was subdivided (scheme replay, octree_manager.py:171) is not "
                "implemented yet");
@@ -321,6 +322,7 @@ void Forest::extend_morton() {
 
 // current shape := one leaf per cell
 void Forest::reset_shape() {
+    materialize_snapshot();
     build();
     compact_base();
     A = A0;

@@ -220,18 +220,14 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
     DevBuf<uint32_t> ref_order;
     DevBuf<int32_t> d_pose_rank;
     compute_ref_order(pose_rank, ref_order, d_pose_rank);
+    drop_snapshot();
     res_n = NB;
-    res_pose.reset(ctx, NB);
-    res_leaf.reset(ctx, NB);
-    res_size.reset(ctx, NB);
-    res_plane.reset(ctx, (size_t)NB * 4);
-    res_best.reset(ctx, NB);
-    res_count.reset(ctx, NB);
     mask.reset(ctx, A);
     mask.zero();
     mask_n = A;
     if (NB == 0) {
         ransac_valid = true;
+        last_ransac_work = 0;
         return;
     }
     int max_rank = 0;
@@ -296,14 +292,25 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
                       table.get(), H, K, threshold, mask.get(), plane.get(), best.get(), best_count.get(), flags);
     }
     last_ransac_work = n_work;
-    {
-        ProfScope ps(ctx, "ransac_prep");
-        ransac_snapshot_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), blk_leaf.get(), cache_rank.get(),
-                                                                 blk_size.get(), plane.get(), best.get(), best_count.get(),
-                                                                 res_pose.get(), res_leaf.get(), res_size.get(), res_plane.get(),
-                                                                 res_best.get(), res_count.get());
-        OL_CHECK_LAUNCH();
+    // The per-block result table in reference order (res_*) is only gathered when somebody asks for it
+    // (materialize_snapshot): keep the raw inputs of that gather.  The block table itself is consumed by the
+    // mask application, so it is moved, not copied, when the mask is applied right away.
+    sn_ref_order.swap(ref_order);
+    sn_size.swap(blk_size);
+    sn_plane.swap(plane);
+    sn_best.swap(best);
+    sn_count.swap(best_count);
+    if (apply) {
+        sn_pose.swap(blk_pose);
+        sn_leaf.swap(blk_leaf);
+        blocks_valid = false;
+    } else {
+        sn_pose.reset(ctx, NB);
+        sn_leaf.reset(ctx, NB);
+        d2d(ctx, sn_pose.get(), blk_pose.get(), NB);
+        d2d(ctx, sn_leaf.get(), blk_leaf.get(), NB);
     }
+    snap_pending = true;
     // a sample index that left its block is clamped and only counted (see ransac.cu)
     uint32_t e = read_u32(d_err.get());
     if (e & (DEVERR_SAMPLE_OOB | DEVERR_FILTER_BOUND)) {
@@ -557,9 +564,43 @@ __global__ void scored_compact_kernel(uint32_t n, const uint32_t* __restrict__ f
     o_count[d] = count[j];
 }
 
+void Forest::drop_snapshot() {
+    snap_pending = false;
+    sn_ref_order.release();
+    sn_pose.release();
+    sn_leaf.release();
+    sn_size.release();
+    sn_plane.release();
+    sn_best.release();
+    sn_count.release();
+}
+
+// gathers the result table of the last RANSAC run into reference block order (res_*); must run before the
+// leaf enumeration order it refers to (cache_rank) is rebuilt
+void Forest::materialize_snapshot() {
+    if (!snap_pending) return;
+    const uint32_t nb = res_n;
+    res_pose.reset(ctx, nb);
+    res_leaf.reset(ctx, nb);
+    res_size.reset(ctx, nb);
+    res_plane.reset(ctx, (size_t)nb * 4);
+    res_best.reset(ctx, nb);
+    res_count.reset(ctx, nb);
+    if (nb) {
+        ProfScope ps(ctx, "ransac_prep");
+        ransac_snapshot_kernel<<<nblk(nb), 256, 0, ctx.stream>>>(nb, sn_ref_order.get(), sn_pose.get(), sn_leaf.get(), cache_rank.get(),
+                                                                 sn_size.get(), sn_plane.get(), sn_best.get(), sn_count.get(),
+                                                                 res_pose.get(), res_leaf.get(), res_size.get(), res_plane.get(),
+                                                                 res_best.get(), res_count.get());
+        OL_CHECK_LAUNCH();
+    }
+    drop_snapshot();
+}
+
 // rows of the last RANSAC run in reference block order; scored_only keeps the blocks that were fitted
 int64_t Forest::export_ransac(bool scored_only, bool count_only, int32_t* pose, int32_t* leaf, int32_t* size, float* plane,
                               int32_t* best, int32_t* count) {
+    if (!count_only) materialize_snapshot();
     if (!scored_only) {
         if (!count_only) {
             copy_out(ctx, pose, res_pose.get(), res_n);

@@ -129,12 +129,14 @@ __device__ __forceinline__ void os_st_status(uint32_t* p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <typename KeyT>
-__global__ void __launch_bounds__(OS_THREADS, (sizeof(KeyT) == 8 ? 3 : 4)) os_pass_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+template <typename KeyT, int OS_THREADS, int OS_ITEMS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(OS_THREADS, MIN_BLOCKS) os_pass_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                              KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                              const uint32_t* __restrict__ gbase /*[256] exclusive digit offsets*/,
                                                              uint32_t* __restrict__ status /*[tiles][256]*/,
                                                              uint32_t* __restrict__ tile_counter, uint32_t n, int shift, int nbits) {
+    constexpr int OS_TILE = OS_THREADS * OS_ITEMS;
+    constexpr int OS_WARPS = OS_THREADS / 32;
     extern __shared__ __align__(16) unsigned char os_smem[];
     KeyT* s_keys = reinterpret_cast<KeyT*>(os_smem);                                // [OS_TILE]
     uint32_t* s_vals = reinterpret_cast<uint32_t*>(os_smem + sizeof(KeyT) * OS_TILE);  // [OS_TILE]
@@ -203,12 +205,30 @@ __global__ void __launch_bounds__(OS_THREADS, (sizeof(KeyT) == 8 ? 3 : 4)) os_pa
     }
     if (digit_thread && lane == 31) s_warp_scan[warp] = inc;
     __syncthreads();
+    uint32_t local_first = 0;
     if (digit_thread) {
         uint32_t wb = 0;
         for (int w = 0; w < warp; ++w) wb += s_warp_scan[w];
-        const uint32_t local_first = wb + inc - count;
+        local_first = wb + inc - count;
         s_excl[d] = local_first;
-        // decoupled look-back: sum the aggregates of the preceding tiles until an inclusive prefix is found
+    }
+    __syncthreads();
+
+    // ---- reorder inside the tile (shared memory): keys and values to their local sorted position.  This runs
+    // BETWEEN publishing the tile's aggregate and the look-back, so the value loads and the shared-memory
+    // scatter overlap with the predecessors finishing their own prefixes (shorter look-back walks).
+#pragma unroll
+    for (int j = 0; j < OS_ITEMS; ++j) {
+        const uint32_t i = wbase + j * 32 + lane;
+        if (i < n) {
+            const uint32_t dg = (uint32_t)(k[j] >> shift) & mask;
+            const uint32_t p = s_excl[dg] + wh[dg] + rnk[j];
+            s_keys[p] = k[j];
+            s_vals[p] = vals_in[i];
+        }
+    }
+    // ---- decoupled look-back: sum the aggregates of the preceding tiles until an inclusive prefix is found ----
+    if (digit_thread) {
         uint32_t excl = 0;
         if (tile > 0) {
             const uint32_t* st = status + d;
@@ -225,19 +245,6 @@ __global__ void __launch_bounds__(OS_THREADS, (sizeof(KeyT) == 8 ? 3 : 4)) os_pa
         s_delta[d] = gbase[d] + excl - local_first;
     }
     __syncthreads();
-
-    // ---- reorder inside the tile (shared memory), then digit-run coalesced stores --------------------------------
-#pragma unroll
-    for (int j = 0; j < OS_ITEMS; ++j) {
-        const uint32_t i = wbase + j * 32 + lane;
-        if (i < n) {
-            const uint32_t dg = (uint32_t)(k[j] >> shift) & mask;
-            const uint32_t p = s_excl[dg] + wh[dg] + rnk[j];
-            s_keys[p] = k[j];
-            s_vals[p] = vals_in[i];
-        }
-    }
-    __syncthreads();
     const uint32_t tile_n = min((uint32_t)OS_TILE, n - tile * OS_TILE);
 #pragma unroll
     for (int j = 0; j < OS_ITEMS; ++j) {
@@ -251,9 +258,28 @@ __global__ void __launch_bounds__(OS_THREADS, (sizeof(KeyT) == 8 ? 3 : 4)) os_pa
     }
 }
 
-template <typename KeyT>
+template <typename KeyT, int THREADS, int ITEMS>
 inline size_t os_pass_smem() {
-    return sizeof(KeyT) * OS_TILE + 4 * OS_TILE + 4 * (OS_WARPS * 256 + 256 + 256);
+    return sizeof(KeyT) * THREADS * ITEMS + 4 * THREADS * ITEMS + 4 * ((THREADS / 32) * 256 + 256 + 256);
+}
+
+// tile shapes selectable at run time (ol_debug_sort_variant): A/B measurements inside one process
+extern int g_os_variant;
+
+template <typename KeyT, int THREADS, int ITEMS, int MIN_BLOCKS>
+inline void os_launch_pass(Ctx& c, const KeyT* kin, const uint32_t* vin, KeyT* kout, uint32_t* vout, const uint32_t* gbase,
+                           uint32_t* status, uint32_t* counter, uint32_t n, int shift, int nbits) {
+    static bool attr_set = false;
+    const size_t smem = os_pass_smem<KeyT, THREADS, ITEMS>();
+    if (!attr_set) {
+        OL_CUDA(cudaFuncSetAttribute(os_pass_kernel<KeyT, THREADS, ITEMS, MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+        attr_set = true;
+    }
+    const uint32_t tiles = (n + THREADS * ITEMS - 1) / (THREADS * ITEMS);
+    os_pass_kernel<KeyT, THREADS, ITEMS, MIN_BLOCKS><<<tiles, THREADS, smem, c.stream>>>(kin, vin, kout, vout, gbase, status, counter, n,
+                                                                                        shift, nbits);
+    OL_CHECK_LAUNCH();
 }
 
 // Sorts (keys0, vals0) by bits [begin_bit, end_bit) using (keys1, vals1) as the alternate buffer.
@@ -264,8 +290,9 @@ inline int onesweep_sort_pairs(Ctx& c, KeyT* keys0, KeyT* keys1, uint32_t* vals0
     const OsPlan plan = os_make_plan(begin_bit, end_bit);
     OL_REQUIRE(plan.passes <= OS_MAX_PASSES, OL_ERR_INVALID, "onesweep: too many digit passes");
     const uint32_t tiles = (uint32_t)((n + OS_TILE - 1) / OS_TILE);
+    const uint32_t max_tiles = tiles;  // both tile shapes hold 4096 pairs
     // [passes][256] histograms | [passes] tile counters | [tiles][256] status words (re-zeroed per pass)
-    DevBuf<uint32_t> ghist(c, (size_t)plan.passes * 256 + OS_MAX_PASSES), status(c, (size_t)tiles * 256);
+    DevBuf<uint32_t> ghist(c, (size_t)plan.passes * 256 + OS_MAX_PASSES), status(c, (size_t)max_tiles * 256);
     ghist.zero();
     const char* hname = sizeof(KeyT) == 8 ? "radix_hist_u64" : "radix_hist_u32";
     const char* sname = sizeof(KeyT) == 8 ? "radix_scatter_u64" : "radix_scatter_u32";
@@ -277,12 +304,6 @@ inline int onesweep_sort_pairs(Ctx& c, KeyT* keys0, KeyT* keys1, uint32_t* vals0
         os_scan_kernel<<<plan.passes, 256, 0, c.stream>>>(ghist.get());
         OL_CHECK_LAUNCH();
     }
-    static bool attr_set[2] = {false, false};
-    const size_t smem = os_pass_smem<KeyT>();
-    if (!attr_set[sizeof(KeyT) == 8]) {
-        OL_CUDA(cudaFuncSetAttribute(os_pass_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[sizeof(KeyT) == 8] = true;
-    }
     int cur = 0;
     for (int p = 0; p < plan.passes; ++p) {
         KeyT* kin = cur ? keys1 : keys0;
@@ -291,10 +312,12 @@ inline int onesweep_sort_pairs(Ctx& c, KeyT* keys0, KeyT* keys1, uint32_t* vals0
         uint32_t* vout = cur ? vals0 : vals1;
         status.zero();
         ProfScope ps(c, sname, (double)n);
-        os_pass_kernel<KeyT><<<tiles, OS_THREADS, smem, c.stream>>>(kin, vin, kout, vout, ghist.get() + (size_t)p * 256, status.get(),
-                                                                    ghist.get() + (size_t)plan.passes * 256 + p, (uint32_t)n,
-                                                                    plan.bit[p], plan.nbits[p]);
-        OL_CHECK_LAUNCH();
+        const uint32_t* gb = ghist.get() + (size_t)p * 256;
+        uint32_t* ctr = ghist.get() + (size_t)plan.passes * 256 + p;
+        switch (g_os_variant) {
+            case 1: os_launch_pass<KeyT, 512, 8, 2>(c, kin, vin, kout, vout, gb, status.get(), ctr, (uint32_t)n, plan.bit[p], plan.nbits[p]); break;
+            default: os_launch_pass<KeyT, 256, 16, 3>(c, kin, vin, kout, vout, gb, status.get(), ctr, (uint32_t)n, plan.bit[p], plan.nbits[p]); break;
+        }
         cur ^= 1;
     }
     return cur;
