@@ -363,9 +363,9 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    # algorithmic bytes per processed element of every HBM-bound stage (DESIGN.md section 5)
-    BYTES = {"keygen": 40, "radix_hist_u64": 8, "radix_scatter_u64": 24, "scan": 12, "gather_morton": 20, "part_hist": 12,
-             "part_rank": 16, "part_scatter": 36, "gather_points": 52}
+    # algorithmic bytes per processed element of every HBM-bound stage (DESIGN.md section 4)
+    BYTES = {"bbox": 24, "keygen": 40, "sort_main_hist": 8, "sort_main_pass": 24, "radix_hist_u64": 8, "radix_scatter_u64": 24,
+             "scan": 12, "gather_morton": 20, "part_hist": 12, "part_rank": 16, "part_scatter": 36, "gather_points": 52}
     stage_ms = {k: v[1] for k, v in (prof or {}).items()}
     stages = {}
     for k, (cnt, tot_ms, units) in (prof or {}).items():
@@ -374,13 +374,19 @@ def main():
             stages[k] = {"launches": cnt, "ms": tot_ms, "elements": units, "bytes_per_element": BYTES[k], "GB/s": gbs,
                          "frac_of_hbm_peak": gbs / hbm_peak}
     roofline = None
-    if "radix_scatter_u64" in stages:
-        st = stages["radix_scatter_u64"]
-        roofline = {"kernel": "radix_scatter_kernel<u64> (LSD radix sort scatter pass, K2)", "bound": "hbm",
-                    "achieved": st["GB/s"], "peak": hbm_peak, "unit": "GB/s", "frac": st["frac_of_hbm_peak"], "traffic": None,
-                    "peak_source": peak_src, "launches": st["launches"],
-                    "note": "achieved = 24 B x (sum of pairs over all launches of the kernel in one step) / (sum of their "
-                            "CUDA-event durations)"}
+    if "sort_main_pass" in stages:
+        # the dominant HBM-bound kernel: one onesweep digit pass over all points (K2).  Per launch: 12 B read +
+        # 12 B written per (u64 key, u32 index) pair.  `traffic` is the ncu figure of the same kernel on a 1e8-pair
+        # launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_summary_v1.md) scaled to this launch.
+        st = stages["sort_main_pass"]
+        per_launch_units = st["elements"] / st["launches"]
+        roofline = {"kernel": "os_pass_kernel<u64> (onesweep radix digit pass over all points, K2)", "bound": "hbm",
+                    "achieved": st["GB/s"], "peak": hbm_peak, "unit": "GB/s", "frac": st["frac_of_hbm_peak"],
+                    "traffic": 2.382e9 * per_launch_units / 1e8, "algorithmic_bytes_per_launch": 24 * per_launch_units,
+                    "avg_launch_ms": st["ms"] / st["launches"], "peak_source": peak_src, "launches": st["launches"],
+                    "note": "achieved = 24 B x pairs per launch / average CUDA-event duration of the launches of one step; "
+                            "the step's other kernels are listed under `stages`, the FP64-bound RANSAC kernel under "
+                            "`roofline_ransac`"}
     out = dict(base, value=value, ms_per_step=ms_per_step, dtype="f64", clocks=clocks, gpu_launches=int(launches),
                stage_ms=stage_ms, stages=stages,
                result={k: stats[k] for k in ("n_points_inserted", "n_points_alive", "n_cells", "n_leaves",
@@ -390,8 +396,11 @@ def main():
         out["roofline"] = roofline
     if prof and "ransac_kernel" in prof:
         r_ms, r_blocks = prof["ransac_kernel"][1], prof["ransac_kernel"][2]
-        out["roofline_ransac"] = {"kernel": "ransac_kernel (K6)", "bound": "fp64-pipe", "ms": r_ms, "blocks_scored": r_blocks,
-                                  "hypotheses_per_s": r_blocks * H / (r_ms * 1e-3) if r_ms else None}
+        out["roofline_ransac"] = {"kernel": "ransac_small_kernel / ransac_kernel (K6)", "bound": "fp64-pipe (issue)", "ms": r_ms,
+                                  "blocks_fitted": r_blocks,
+                                  "reference_equivalent_hypotheses_per_s": r_blocks * H / (r_ms * 1e-3) if r_ms else None,
+                                  "note": "exact-arithmetic early exit + FP32 interval pre-filter: most blocks evaluate 32 of "
+                                          "the 1024 hypotheses (DESIGN.md 4.6); v1 evaluated all of them in 81 ms"}
     if e2e:
         out["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:

@@ -98,6 +98,45 @@ class ForestHost:
         self.forest.filter(table, idx)
         self._counts_cache = None
 
+    # ---- generic per-leaf callback (grid.py:111-122 -> octree_manager.py:68-83 -> octree.py:114-123) -----
+    def map_leaf_points(self, function: Callable, pose_numbers: Optional[Sequence[int]] = None):
+        """Host-callback compatibility path: every non-empty (pose, leaf) block is copied to the
+        host, handed to the opaque Python `function`, and the result is written back.  The forest stores points
+        by reference into the inserted clouds, so the result must be a selection of the leaf's own rows (the
+        reference's tests use `lambda cloud: [cloud[0]]`); a function that invents new coordinates raises
+        NotImplementedError.  Like the reference, empty leaves are skipped and unknown poses are ignored."""
+        if self.empty:
+            return
+        numbers = list(self.pose_numbers) if pose_numbers is None else [p for p in pose_numbers if p in self.pose_index]
+        blocks = _views.tables(self.forest)["blocks"]
+        plan = []
+        for number in numbers:
+            idx = self.pose_index[number]
+            sizes = blocks["size"][blocks["pose"] == idx].astype(np.int64)
+            if sizes.sum() == 0:
+                continue
+            xyz = self.forest.export_points(idx, order=0, n_hint=int(sizes.sum()))["xyz"]
+            mask = np.zeros(len(xyz), dtype=bool)
+            start = 0
+            for n in sizes:
+                block = xyz[start:start + n]
+                res = np.asarray(function(block.copy()), dtype=np.float64).reshape(-1, 3)
+                j = 0
+                for row in res:  # the result must be a subsequence of the leaf's rows
+                    while j < n and not (block[j] == row).all():
+                        j += 1
+                    if j == n:
+                        raise NotImplementedError(
+                            "map_leaf_points: the function returned points that are not a selection of the leaf's own "
+                            "points; coordinate-changing maps are outside the GPU path (DESIGN.md section 8)")
+                    mask[start + j] = True
+                    j += 1
+                start += n
+            plan.append((idx, mask))
+        for idx, mask in plan:
+            self.forest.apply_pose_mask(idx, mask)
+        self._counts_cache = None
+
     # ---- counters (grid.py:343-362) --------------------------------------------------------------
     def counts(self) -> np.ndarray:
         if self._counts_cache is None or self._counts_cache[0] != self.forest.version:

@@ -204,7 +204,7 @@ void Forest::build() {
     }
     iota_kernel<<<nblk(n), 256, 0, ctx.stream>>>(vals0.get(), n, 0);
     OL_CHECK_LAUNCH();
-    int which = radix_sort_pairs<uint64_t>(ctx, keys0.get(), keys1.get(), vals0.get(), vals1.get(), n, 0, key_bits);
+    int which = radix_sort_pairs<uint64_t>(ctx, keys0.get(), keys1.get(), vals0.get(), vals1.get(), n, 0, key_bits, true);
     if (which) {
         keys0.swap(keys1);
         vals0.swap(vals1);

@@ -241,11 +241,11 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(const KeyT*
 extern bool g_force_legacy_sort;
 template <typename KeyT>
 inline int radix_sort_pairs(Ctx& c, KeyT* keys0, KeyT* keys1, uint32_t* vals0, uint32_t* vals1, size_t n, int begin_bit,
-                            int end_bit) {
+                            int end_bit, bool main_sort = false) {
     OL_REQUIRE(n < (1ull << 31), OL_ERR_INVALID, "radix_sort_pairs: n must be < 2^31");
     int bits = end_bit - begin_bit;
     if (n <= 1 || bits <= 0) return 0;
-    if (n < (1ull << 30) && !g_force_legacy_sort) return onesweep_sort_pairs<KeyT>(c, keys0, keys1, vals0, vals1, n, begin_bit, end_bit);
+    if (n < (1ull << 30) && !g_force_legacy_sort) return onesweep_sort_pairs<KeyT>(c, keys0, keys1, vals0, vals1, n, begin_bit, end_bit, main_sort);
     int passes = (bits + 7) / 8;
     int per = (bits + passes - 1) / passes;
     uint32_t tiles = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);

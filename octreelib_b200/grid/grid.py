@@ -48,9 +48,9 @@ class Grid(GridBase):
 
     # ---- grid.py:111-122 ------------------------------------------------------------------------
     def map_leaf_points(self, function: Callable[[PointCloud], PointCloud], pose_numbers: Optional[List[int]] = None):
-        raise NotImplementedError(
-            "Grid.map_leaf_points applies an opaque Python function per leaf; it is outside the GPU hot path "
-            "(SURVEY.md 8(f)). Use map_leaf_points_cuda_ransac / filter, or export leaves with get_leaf_points.")
+        """Host-callback compatibility path: see ForestHost.map_leaf_points (the function must return a selection of
+        the leaf's own points).  The data-parallel equivalents are `filter` and `map_leaf_points_cuda_ransac`."""
+        self._host.map_leaf_points(function, pose_numbers)
 
     # ---- grid.py:124-215 ------------------------------------------------------------------------
     def map_leaf_points_cuda_ransac(self, poses_per_batch: int = 10, threshold: float = 0.01,

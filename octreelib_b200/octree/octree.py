@@ -54,7 +54,8 @@ class _SinglePose:
         self._host.filter(filtering_criteria)
 
     def map_leaf_points(self, function: Callable[[PointCloud], PointCloud]):
-        raise NotImplementedError("arbitrary per-leaf Python callbacks are not part of the GPU path")
+        """octree.py:249-254 (host-callback compatibility path, see ForestHost.map_leaf_points)."""
+        self._host.map_leaf_points(function)
 
     def apply_mask(self, mask: np.ndarray):
         """Keep the points whose mask entry is True; mask in leaf order (octree.py:265-274)."""

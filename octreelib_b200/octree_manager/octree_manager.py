@@ -36,7 +36,8 @@ class OctreeManager(VoxelBase):
         self._host.subdivide(subdivision_criteria, pose_numbers)
 
     def map_leaf_points(self, function, pose_numbers: Optional[List[int]] = None):
-        raise NotImplementedError("arbitrary per-leaf Python callbacks are not part of the GPU path")
+        """octree_manager.py:68-83 (host-callback compatibility path, see ForestHost.map_leaf_points)."""
+        self._host.map_leaf_points(function, pose_numbers)
 
     def filter(self, filtering_criteria: List[Callable[[PointCloud], bool]], pose_numbers: Optional[List[int]] = None):
         """octree_manager.py:85-99"""

@@ -33,8 +33,8 @@ def routing_layout(counts_local: np.ndarray, pose_numbers: Sequence[int], n_pose
     """counts_local[owner][local run] -> counts_global[owner][pose number] (runs of one pose add up)."""
     world = counts_local.shape[0]
     out = np.zeros((world, n_poses_total), dtype=np.int64)
-    for j, p in enumerate(pose_numbers):
-        out[:, p] += counts_local[:, j]
+    if len(pose_numbers):
+        np.add.at(out, (slice(None), np.asarray(pose_numbers, dtype=np.int64)), counts_local[:, :len(pose_numbers)])
     return out
 
 
@@ -66,15 +66,11 @@ def segments_from_counts(recv_counts: np.ndarray) -> Tuple[np.ndarray, np.ndarra
     """(source rank, pose) runs of the received buffer: sizes, pose numbers, and the index of each
     run's first point among the points of that pose received so far (keeps the original input order
     of a pose when its source ranks hold increasing index ranges)."""
-    sizes, poses, first = [], [], []
-    seen = np.zeros(recv_counts.shape[1], dtype=np.int64)
-    for src in range(recv_counts.shape[0]):
-        for p in np.flatnonzero(recv_counts[src]):
-            sizes.append(int(recv_counts[src, p]))
-            poses.append(int(p))
-            first.append(int(seen[p]))
-            seen[p] += recv_counts[src, p]
-    return np.array(sizes, dtype=np.int64), np.array(poses, dtype=np.int32), np.array(first, dtype=np.int64)
+    rc = np.asarray(recv_counts, dtype=np.int64)
+    # index of a run's first point inside its pose = points of that pose received from lower source ranks
+    before = np.cumsum(rc, axis=0) - rc
+    src, pose = np.nonzero(rc)  # row-major: source rank, then pose -> the order of the received buffer
+    return rc[src, pose].astype(np.int64), pose.astype(np.int32), before[src, pose].astype(np.int64)
 
 
 class ShardedGrid:

@@ -159,6 +159,32 @@ def test_ref_grid_get_points_and_leaf_points():
         grid.get_leaf_points(7)
 
 
+def test_ref_grid_map_leaf_points():
+    """test/grid/test_grid.py:96-103: the callback returns a LIST holding the leaf's first point."""
+    grid, _ = _generated_grid()
+    grid.subdivide([lambda points: len(points) > 2])
+    grid.map_leaf_points(lambda cloud: [cloud[0]])
+    for p in (0, 1):
+        assert grid.n_points(p) == grid.n_leaves(p)
+    with pytest.raises(NotImplementedError):  # coordinate-changing maps are outside the GPU path
+        grid.map_leaf_points(lambda cloud: cloud + 1.0)
+
+
+def test_map_leaf_points_selection_matches_oracle_filtering():
+    rng = np.random.default_rng(8)
+    cloud = (rng.random((5000, 3)) * 6).astype(np.float32).astype(np.float64)
+    grid = Grid(GridConfig(voxel_edge_length=2))
+    grid.insert_points(0, cloud)
+    grid.subdivide([MaxPoints(40)])
+    before = grid._host.forest.export_points(0, order=0)
+    sizes = grid._host.forest.export_blocks()["size"]
+    grid.map_leaf_points(lambda pts: pts[::2])  # keep every second point of every leaf
+    after = grid._host.forest.export_points(0, order=0)
+    starts = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    want = np.concatenate([before["idx"][s:s + n:2] for s, n in zip(starts, sizes)])
+    assert (after["idx"] == want).all()
+
+
 # ---- test/octree/test_multi_pose.py ----------------------------------------------------------------
 def _multi_pose():
     mp = OctreeManager(Octree, OctreeConfig(), np.array([0, 0, 0]), 5)
@@ -176,6 +202,13 @@ def test_ref_multi_pose_subdivide(crit, poses, nodes, leaves):
     mp.subdivide([lambda points: len(points) > crit], poses)
     assert [mp.n_nodes(0), mp.n_nodes(1)] == nodes
     assert [mp.n_leaves(0), mp.n_leaves(1)] == leaves
+
+
+def test_ref_multi_pose_map_leaf_points():
+    """test/octree/test_multi_pose.py:71-75"""
+    mp, _ = _multi_pose()
+    mp.map_leaf_points(lambda points: points[0].reshape((1, 3)), [0])
+    assert mp.n_points(0) == 1 and mp.n_points(1) == 3
 
 
 def test_ref_multi_pose_leaf_voxels():
