@@ -63,6 +63,7 @@ int ol_forest_destroy(ol_forest* f) {
 int ol_forest_insert(ol_forest* f, const double* xyz, int64_t n, int32_t src_on_device, int32_t* out_pose_index) {
     OL_NEED(f);
     OL_API_BEGIN
+    ol::PoolScope pool_scope(f->impl.ctx);
     int p = f->impl.insert(xyz, n, src_on_device != 0, nullptr, nullptr, nullptr, 0, 0);
     if (out_pose_index) *out_pose_index = p;
     OL_API_END
@@ -75,6 +76,7 @@ int ol_forest_insert_segments(ol_forest* f, const double* xyz, int64_t n, int32_
     OL_NEED(seg_pose);
     OL_API_BEGIN
     OL_REQUIRE(n_segments > 0, OL_ERR_INVALID, "n_segments must be positive");
+    ol::PoolScope pool_scope(f->impl.ctx);
     f->impl.insert(xyz, n, src_on_device != 0, seg_sizes, seg_pose, seg_first, n_segments, n_poses_total);
     OL_API_END
 }
@@ -83,6 +85,7 @@ int ol_forest_subdivide(ol_forest* f, int64_t max_points, const int32_t* pose_in
     OL_NEED(f);
     OL_API_BEGIN
     OL_REQUIRE(max_points >= 0, OL_ERR_INVALID, "max_points must be >= 0 (an empty node would split forever)");
+    ol::PoolScope pool_scope(f->impl.ctx);
     f->impl.subdivide(max_points, nullptr, 0, 0, pose_indices, n_poses);
     OL_API_END
 }
@@ -92,6 +95,7 @@ int ol_forest_subdivide_table(ol_forest* f, const uint8_t* split_table_host, int
     OL_NEED(f);
     OL_NEED(split_table_host);
     OL_API_BEGIN
+    ol::PoolScope pool_scope(f->impl.ctx);
     f->impl.subdivide(0, split_table_host, table_len, split_beyond, pose_indices, n_poses);
     OL_API_END
 }
@@ -101,6 +105,7 @@ int ol_forest_filter(ol_forest* f, const uint8_t* keep_table_host, int64_t table
     OL_NEED(f);
     OL_NEED(keep_table_host);
     OL_API_BEGIN
+    ol::PoolScope pool_scope(f->impl.ctx);
     f->impl.filter(keep_table_host, table_len, pose_indices, n_poses);
     OL_API_END
 }
@@ -110,6 +115,7 @@ int ol_forest_ransac(ol_forest* f, const double* table_host, int32_t H, int32_t 
     OL_NEED(f);
     OL_NEED(table_host);
     OL_API_BEGIN
+    ol::PoolScope pool_scope(f->impl.ctx);
     f->impl.ransac(table_host, H, K, threshold, pose_rank, poses_per_batch, apply != 0, flags);
     OL_API_END
 }
@@ -117,6 +123,7 @@ int ol_forest_ransac(ol_forest* f, const double* table_host, int32_t H, int32_t 
 int ol_forest_apply_mask(ol_forest* f) {
     OL_NEED(f);
     OL_API_BEGIN
+    ol::PoolScope pool_scope(f->impl.ctx);
     f->impl.apply_mask();
     OL_API_END
 }
@@ -124,6 +131,7 @@ int ol_forest_apply_mask(ol_forest* f) {
 int ol_forest_apply_pose_mask(ol_forest* f, const int32_t* pose_rank, int32_t pose_index, const uint8_t* mask_host, int64_t n) {
     OL_NEED(f);
     OL_API_BEGIN
+    ol::PoolScope pool_scope(f->impl.ctx);
     f->impl.apply_pose_mask(pose_rank, pose_index, mask_host, n);
     OL_API_END
 }
@@ -156,6 +164,7 @@ int ol_forest_stats_light(ol_forest* f, ol_forest_stats* out) {
     OL_NEED(f);
     OL_NEED(out);
     OL_API_BEGIN
+    ol::PoolScope pool_scope(f->impl.ctx);
     f->impl.stats(out, true);
     OL_API_END
 }
@@ -164,6 +173,7 @@ int ol_forest_stats_get(ol_forest* f, ol_forest_stats* out) {
     OL_NEED(f);
     OL_NEED(out);
     OL_API_BEGIN
+    ol::PoolScope pool_scope(f->impl.ctx);
     f->impl.stats(out);
     OL_API_END
 }
@@ -172,6 +182,7 @@ int ol_forest_pose_counts(ol_forest* f, int64_t* out_host) {
     OL_NEED(f);
     OL_NEED(out_host);
     OL_API_BEGIN
+    ol::PoolScope pool_scope(f->impl.ctx);
     f->impl.pose_counts(out_host);
     OL_API_END
 }
@@ -179,6 +190,7 @@ int ol_forest_pose_counts(ol_forest* f, int64_t* out_host) {
 int ol_forest_export_cells(ol_forest* f, int64_t* q, double* corner, int32_t* first_pose, int64_t* n_nodes, int64_t* leaf_begin) {
     OL_NEED(f);
     OL_API_BEGIN
+    ol::PoolScope pool_scope(f->impl.ctx);
     f->impl.export_cells(q, corner, first_pose, n_nodes, leaf_begin);
     OL_API_END
 }
@@ -186,6 +198,7 @@ int ol_forest_export_cells(ol_forest* f, int64_t* q, double* corner, int32_t* fi
 int ol_forest_export_cell_poses(ol_forest* f, int32_t* cell, int32_t* pose) {
     OL_NEED(f);
     OL_API_BEGIN
+    ol::PoolScope pool_scope(f->impl.ctx);
     f->impl.export_cell_poses(cell, pose);
     OL_API_END
 }
@@ -193,6 +206,7 @@ int ol_forest_export_cell_poses(ol_forest* f, int32_t* cell, int32_t* pose) {
 int ol_forest_export_leaves(ol_forest* f, double* corner, double* edge, int32_t* cell, int32_t* depth) {
     OL_NEED(f);
     OL_API_BEGIN
+    ol::PoolScope pool_scope(f->impl.ctx);
     f->impl.export_leaves(corner, edge, cell, depth);
     OL_API_END
 }
@@ -200,6 +214,7 @@ int ol_forest_export_leaves(ol_forest* f, double* corner, double* edge, int32_t*
 int ol_forest_export_blocks(ol_forest* f, const int32_t* pose_rank, int32_t* pose, int32_t* leaf, int32_t* size) {
     OL_NEED(f);
     OL_API_BEGIN
+    ol::PoolScope pool_scope(f->impl.ctx);
     f->impl.export_blocks(pose_rank, pose, leaf, size);
     OL_API_END
 }
@@ -209,6 +224,7 @@ int ol_forest_export_ransac(ol_forest* f, int32_t scored_only, int32_t* pose, in
     OL_NEED(f);
     OL_API_BEGIN
     const bool count_only = !pose && !leaf && !size && !plane && !best && !best_count;
+    ol::PoolScope pool_scope(f->impl.ctx);
     int64_t n = f->impl.export_ransac(scored_only != 0, count_only, pose, leaf, size, plane, best, best_count);
     if (out_n) *out_n = n;
     OL_API_END
@@ -218,6 +234,7 @@ int ol_forest_export_points(ol_forest* f, const int32_t* pose_rank, int32_t pose
                             int32_t* cell, uint8_t* mask, int64_t* out_n) {
     OL_NEED(f);
     OL_API_BEGIN
+    ol::PoolScope pool_scope(f->impl.ctx);
     int64_t n = f->impl.export_points(pose_rank, pose_index, order, xyz, idx, cell, mask);
     if (out_n) *out_n = n;
     OL_API_END
@@ -247,6 +264,7 @@ ol::Ctx make_ctx(void* stream, ol_alloc_fn alloc, ol_free_fn free_fn, void* user
     c.alloc_fn = alloc;
     c.free_fn = free_fn;
     c.alloc_user = user;
+    c.pool_enabled = true;  // trimmed by ~Ctx when the entry point returns
     return c;
 }
 }  // namespace

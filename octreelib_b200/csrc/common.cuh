@@ -103,15 +103,31 @@ struct Ctx {
     int num_sms = 148;
     size_t bytes_live = 0, bytes_peak = 0;
 
+    // Freed temporaries are parked in a small exact-size pool and handed out again inside the same public call
+    // (the level loops allocate the same sizes over and over; every allocator callback is a trip into Python).
+    // trim_pool() returns everything at the end of each C-ABI entry point, so nothing is held between calls.
+    struct Parked {
+        void* ptr;
+        size_t bytes;
+    };
+    std::vector<Parked> pool;
+    size_t pool_bytes = 0;
+    static constexpr size_t POOL_MAX_ENTRIES = 64;
+
     void* alloc(size_t bytes) {
         if (bytes == 0) bytes = 16;
-        void* p = nullptr;
-        if (alloc_fn) {
-            p = alloc_fn(alloc_user, bytes);
-            if (!p) throw Error{OL_ERR_ALLOC, "host allocator callback returned NULL for " + std::to_string(bytes) + " bytes"};
-        } else {
-            OL_CUDA(cudaMallocAsync(&p, bytes, stream));
+        for (size_t i = pool.size(); i-- > 0;) {
+            if (pool[i].bytes == bytes) {
+                void* p = pool[i].ptr;
+                pool[i] = pool.back();
+                pool.pop_back();
+                pool_bytes -= bytes;
+                bytes_live += bytes;
+                if (bytes_live > bytes_peak) bytes_peak = bytes_live;
+                return p;
+            }
         }
+        void* p = raw_alloc(bytes);
         bytes_live += bytes;
         if (bytes_live > bytes_peak) bytes_peak = bytes_live;
         return p;
@@ -120,12 +136,51 @@ struct Ctx {
         if (!p) return;
         if (bytes == 0) bytes = 16;
         bytes_live -= bytes;
+        if (pool_enabled && pool.size() < POOL_MAX_ENTRIES) {
+            pool.push_back(Parked{p, bytes});
+            pool_bytes += bytes;
+            return;
+        }
+        raw_free(p);
+    }
+    void trim_pool() {
+        for (auto& e : pool) raw_free(e.ptr);
+        pool.clear();
+        pool_bytes = 0;
+    }
+    bool pool_enabled = false;
+    void* raw_alloc(size_t bytes) {
+        void* p = nullptr;
+        if (alloc_fn) {
+            p = alloc_fn(alloc_user, bytes);
+            if (!p) {
+                trim_pool();  // give the parked buffers back and retry once
+                p = alloc_fn(alloc_user, bytes);
+            }
+            if (!p) throw Error{OL_ERR_ALLOC, "host allocator callback returned NULL for " + std::to_string(bytes) + " bytes"};
+        } else {
+            OL_CUDA(cudaMallocAsync(&p, bytes, stream));
+        }
+        return p;
+    }
+    void raw_free(void* p) {
         if (free_fn)
             free_fn(alloc_user, p);
         else
             cudaFreeAsync(p, stream);
     }
     void sync() { OL_CUDA(cudaStreamSynchronize(stream)); }
+    ~Ctx() { trim_pool(); }
+};
+
+// enables the temporary pool for the duration of one public call
+struct PoolScope {
+    Ctx& c;
+    explicit PoolScope(Ctx& ctx) : c(ctx) { c.pool_enabled = true; }
+    ~PoolScope() {
+        c.pool_enabled = false;
+        c.trim_pool();
+    }
 };
 
 // times everything enqueued on the stream between construction and destruction under `name`
