@@ -214,6 +214,20 @@ int ol_partition_by_owner(void *stream, const double *xyz_dev, int64_t n, const 
                           double edge, const double corner[3], int32_t world, double *out_xyz_dev, int64_t *out_counts_host,
                           ol_alloc_fn alloc, ol_free_fn free_fn, void *alloc_user);
 
+/* Fused form used when the ranks of one node can map each other's memory (NVLink peer access):
+ * ol_route_plan        = the same owner computation and stable sort, but only the permutation
+ *                        (out_perm_dev[i] = source row of the i-th row in (owner, run) order) and the counts are
+ *                        produced - no local staging copy;
+ * ol_route_to_peers    = one kernel that reads the rows in that order and stores each one directly into the receive
+ *                        buffer of its owner rank (peer_base_host[o], device pointers valid in THIS process) starting
+ *                        at row recv_row_base_host[o]; owner_first_host[o] = first sorted position owned by rank o
+ *                        (world + 1 entries).  The caller orders it against the peers with its own barriers. */
+int ol_route_plan(void *stream, const double *xyz_dev, int64_t n, const int64_t *seg_sizes_host, int32_t n_segments, double edge,
+                  const double corner[3], int32_t world, uint32_t *out_perm_dev, int64_t *out_counts_host, ol_alloc_fn alloc,
+                  ol_free_fn free_fn, void *alloc_user);
+int ol_route_to_peers(void *stream, const double *xyz_dev, const uint32_t *perm_dev, int64_t n, int32_t world,
+                      const int64_t *owner_first_host, void *const *peer_base_host, const int64_t *recv_row_base_host);
+
 /* ---- primitives, exported so that tests can check them in isolation -------------------------- */
 /* stable LSD radix sort of (key, value) pairs on bits [begin_bit, end_bit); result in keys_dev/vals_dev */
 int ol_sort_pairs_u64(void *stream, uint64_t *keys_dev, uint32_t *vals_dev, int64_t n, int32_t begin_bit,

@@ -84,6 +84,8 @@ SIGNATURES = {
     "ol_host_cell_owner": (_u32, [_i64, _i64, _i64, _u32]),
     "ol_partition_by_owner": (C.c_int, [_p, _p, _i64, _p, _i32, _f64, C.POINTER(_f64 * 3), _i32, _p, _p, ALLOC_FN, FREE_FN,
                                         _p]),
+    "ol_route_plan": (C.c_int, [_p, _p, _i64, _p, _i32, _f64, C.POINTER(_f64 * 3), _i32, _p, _p, ALLOC_FN, FREE_FN, _p]),
+    "ol_route_to_peers": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p]),
     "ol_sort_pairs_u64": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, ALLOC_FN, FREE_FN, _p]),
     "ol_sort_pairs_u32": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, ALLOC_FN, FREE_FN, _p]),
     "ol_debug_force_legacy_sort": (C.c_int, [_i32]),

@@ -72,6 +72,29 @@ __global__ void route_counts_kernel(uint32_t n, const uint32_t* __restrict__ own
     if (tail) run_end[slot] = (unsigned long long)i + 1;
 }
 
+constexpr int ROUTE_MAX_WORLD = 64;
+struct RouteArgs {
+    double* peer[ROUTE_MAX_WORLD];        // receive buffer of every rank, mapped into this process (NVLink peer memory)
+    long long base[ROUTE_MAX_WORLD];      // first row this rank may write in that buffer
+    uint32_t first[ROUTE_MAX_WORLD + 1];  // first sorted position owned by every rank
+    int world;
+};
+
+// Fused gather + all-to-all: row i of the owner-sorted order is read from the local cloud and stored straight
+// into the owning rank's receive buffer over NVLink (P2P stores; consecutive threads write consecutive rows).
+__global__ void __launch_bounds__(256) route_to_peers_kernel(const double* __restrict__ xyz, const uint32_t* __restrict__ perm,
+                                                             uint32_t n, RouteArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int o = 0;
+    while (o + 1 < a.world && a.first[o + 1] <= i) ++o;
+    const size_t r = perm[i];
+    double* dst = a.peer[o] + (size_t)(a.base[o] + (long long)(i - a.first[o])) * 3;
+    dst[0] = xyz[r * 3 + 0];
+    dst[1] = xyz[r * 3 + 1];
+    dst[2] = xyz[r * 3 + 2];
+}
+
 }  // namespace
 }  // namespace ol
 
@@ -79,50 +102,102 @@ extern "C" {
 
 uint32_t ol_host_cell_owner(int64_t qx, int64_t qy, int64_t qz, uint32_t world) { return ol::cell_owner(qx, qy, qz, world); }
 
+// shared by ol_partition_by_owner / ol_route_plan: owner per point, stable sort by owner, (owner, run) counts
+static void route_plan(ol::Ctx& c, const double* xyz_dev, int64_t n, const int64_t* seg_sizes_host, int32_t n_segments, double edge,
+                       const double corner[3], int32_t world, uint32_t* out_perm_dev, double* out_xyz_dev,
+                       int64_t* out_counts_host) {
+    using namespace ol;
+    OL_REQUIRE(n >= 0 && n < (1ll << 31) && n_segments >= 1 && world >= 1 && edge > 0, OL_ERR_INVALID, "bad partition arguments");
+    for (int64_t k = 0; k < (int64_t)world * n_segments; ++k) out_counts_host[k] = 0;
+    if (n == 0) return;
+    const uint32_t m = (uint32_t)n;
+    std::vector<uint32_t> seg_start((size_t)n_segments + 1, 0);
+    for (int s = 0; s < n_segments; ++s) seg_start[s + 1] = seg_start[s] + (uint32_t)seg_sizes_host[s];
+    OL_REQUIRE(seg_start[n_segments] == m, OL_ERR_INVALID, "segment sizes do not add up to n");
+    DevBuf<uint32_t> err(c, 1), k0(c, m), k1(c, m), v0(c, m), v1(c, m), d_seg(c, seg_start.size());
+    DevBuf<unsigned long long> rb(c, (size_t)world * n_segments), re(c, (size_t)world * n_segments);
+    err.zero();
+    rb.zero();
+    re.zero();
+    h2d(c, d_seg.get(), seg_start.data(), seg_start.size());
+    const unsigned g = (m + 255) / 256;
+    owner_kernel<<<g, 256, 0, c.stream>>>(xyz_dev, m, edge, corner[0], corner[1], corner[2], (uint32_t)world, k0.get(), v0.get(),
+                                          err.get());
+    OL_CHECK_LAUNCH();
+    int w = radix_sort_pairs<uint32_t>(c, k0.get(), k1.get(), v0.get(), v1.get(), m, 0, bit_length_u64((uint64_t)world - 1));
+    const uint32_t* ks = w ? k1.get() : k0.get();
+    const uint32_t* vs = w ? v1.get() : v0.get();
+    if (out_xyz_dev) {
+        route_gather_kernel<<<g, 256, 0, c.stream>>>(m, xyz_dev, vs, out_xyz_dev);
+        OL_CHECK_LAUNCH();
+    }
+    if (out_perm_dev) d2d(c, out_perm_dev, vs, m);
+    route_counts_kernel<<<g, 256, 0, c.stream>>>(m, ks, vs, d_seg.get(), n_segments, rb.get(), re.get());
+    OL_CHECK_LAUNCH();
+    std::vector<unsigned long long> hb((size_t)world * n_segments), he((size_t)world * n_segments);
+    uint32_t herr = 0;
+    d2h(c, hb.data(), rb.get(), hb.size());
+    d2h(c, he.data(), re.get(), he.size());
+    d2h(c, &herr, err.get(), 1);
+    c.sync();
+    OL_REQUIRE(!(herr & DEVERR_NONFINITE), OL_ERR_NONFINITE, "point cloud contains NaN or infinite coordinates");
+    OL_REQUIRE(!(herr & DEVERR_CELL_RANGE), OL_ERR_RANGE, "cell coordinates out of the representable range");
+    for (size_t k = 0; k < hb.size(); ++k) out_counts_host[k] = (int64_t)(he[k] - hb[k]);
+}
+
+static ol::Ctx route_ctx(void* stream, ol_alloc_fn alloc, ol_free_fn free_fn, void* alloc_user) {
+    ol::Ctx c;
+    c.stream = (cudaStream_t)stream;
+    c.alloc_fn = alloc;
+    c.free_fn = free_fn;
+    c.alloc_user = alloc_user;
+    c.pool_enabled = true;
+    return c;
+}
+
 int ol_partition_by_owner(void* stream, const double* xyz_dev, int64_t n, const int64_t* seg_sizes_host, int32_t n_segments,
                           double edge, const double corner[3], int32_t world, double* out_xyz_dev, int64_t* out_counts_host,
                           ol_alloc_fn alloc, ol_free_fn free_fn, void* alloc_user) {
+    try {
+        ol::Ctx c = route_ctx(stream, alloc, free_fn, alloc_user);
+        route_plan(c, xyz_dev, n, seg_sizes_host, n_segments, edge, corner, world, nullptr, out_xyz_dev, out_counts_host);
+    } catch (const ol::Error& e) {
+        ol::set_last_error(e.code, e.msg);
+        return e.code;
+    }
+    return OL_OK;
+}
+
+int ol_route_plan(void* stream, const double* xyz_dev, int64_t n, const int64_t* seg_sizes_host, int32_t n_segments, double edge,
+                  const double corner[3], int32_t world, uint32_t* out_perm_dev, int64_t* out_counts_host, ol_alloc_fn alloc,
+                  ol_free_fn free_fn, void* alloc_user) {
+    try {
+        ol::Ctx c = route_ctx(stream, alloc, free_fn, alloc_user);
+        route_plan(c, xyz_dev, n, seg_sizes_host, n_segments, edge, corner, world, out_perm_dev, nullptr, out_counts_host);
+    } catch (const ol::Error& e) {
+        ol::set_last_error(e.code, e.msg);
+        return e.code;
+    }
+    return OL_OK;
+}
+
+int ol_route_to_peers(void* stream, const double* xyz_dev, const uint32_t* perm_dev, int64_t n, int32_t world,
+                      const int64_t* owner_first_host, void* const* peer_base_host, const int64_t* recv_row_base_host) {
     using namespace ol;
     try {
-        OL_REQUIRE(n >= 0 && n < (1ll << 31) && n_segments >= 1 && world >= 1 && edge > 0, OL_ERR_INVALID,
-                   "bad partition arguments");
-        Ctx c;
-        c.stream = (cudaStream_t)stream;
-        c.alloc_fn = alloc;
-        c.free_fn = free_fn;
-        c.alloc_user = alloc_user;
-        for (int64_t k = 0; k < (int64_t)world * n_segments; ++k) out_counts_host[k] = 0;
+        OL_REQUIRE(world >= 1 && world <= ROUTE_MAX_WORLD && n >= 0 && n < (1ll << 31), OL_ERR_INVALID, "bad routing arguments");
         if (n == 0) return OL_OK;
-        const uint32_t m = (uint32_t)n;
-        std::vector<uint32_t> seg_start((size_t)n_segments + 1, 0);
-        for (int s = 0; s < n_segments; ++s) seg_start[s + 1] = seg_start[s] + (uint32_t)seg_sizes_host[s];
-        OL_REQUIRE(seg_start[n_segments] == m, OL_ERR_INVALID, "segment sizes do not add up to n");
-        DevBuf<uint32_t> err(c, 1), k0(c, m), k1(c, m), v0(c, m), v1(c, m), d_seg(c, seg_start.size());
-        DevBuf<unsigned long long> rb(c, (size_t)world * n_segments), re(c, (size_t)world * n_segments);
-        err.zero();
-        rb.zero();
-        re.zero();
-        h2d(c, d_seg.get(), seg_start.data(), seg_start.size());
-        const unsigned g = (m + 255) / 256;
-        owner_kernel<<<g, 256, 0, c.stream>>>(xyz_dev, m, edge, corner[0], corner[1], corner[2], (uint32_t)world, k0.get(), v0.get(),
-                                              err.get());
+        RouteArgs a{};
+        a.world = world;
+        for (int o = 0; o < world; ++o) {
+            a.peer[o] = static_cast<double*>(peer_base_host[o]);
+            a.base[o] = recv_row_base_host[o];
+            a.first[o] = (uint32_t)owner_first_host[o];
+        }
+        a.first[world] = (uint32_t)owner_first_host[world];
+        OL_REQUIRE(owner_first_host[world] == n, OL_ERR_INVALID, "owner offsets do not cover the cloud");
+        route_to_peers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(xyz_dev, perm_dev, (uint32_t)n, a);
         OL_CHECK_LAUNCH();
-        int w = radix_sort_pairs<uint32_t>(c, k0.get(), k1.get(), v0.get(), v1.get(), m, 0, bit_length_u64((uint64_t)world - 1));
-        const uint32_t* ks = w ? k1.get() : k0.get();
-        const uint32_t* vs = w ? v1.get() : v0.get();
-        route_gather_kernel<<<g, 256, 0, c.stream>>>(m, xyz_dev, vs, out_xyz_dev);
-        OL_CHECK_LAUNCH();
-        route_counts_kernel<<<g, 256, 0, c.stream>>>(m, ks, vs, d_seg.get(), n_segments, rb.get(), re.get());
-        OL_CHECK_LAUNCH();
-        std::vector<unsigned long long> hb((size_t)world * n_segments), he((size_t)world * n_segments);
-        uint32_t herr = 0;
-        d2h(c, hb.data(), rb.get(), hb.size());
-        d2h(c, he.data(), re.get(), he.size());
-        d2h(c, &herr, err.get(), 1);
-        c.sync();
-        OL_REQUIRE(!(herr & DEVERR_NONFINITE), OL_ERR_NONFINITE, "point cloud contains NaN or infinite coordinates");
-        OL_REQUIRE(!(herr & DEVERR_CELL_RANGE), OL_ERR_RANGE, "cell coordinates out of the representable range");
-        for (size_t k = 0; k < hb.size(); ++k) out_counts_host[k] = (int64_t)(he[k] - hb[k]);
     } catch (const ol::Error& e) {
         ol::set_last_error(e.code, e.msg);
         return e.code;

@@ -73,6 +73,45 @@ def segments_from_counts(recv_counts: np.ndarray) -> Tuple[np.ndarray, np.ndarra
     return rc[src, pose].astype(np.int64), pose.astype(np.int32), before[src, pose].astype(np.int64)
 
 
+class _PeerBuffers:
+    """Symmetric receive buffers (torch.distributed._symmetric_memory: every rank's buffer is mapped into every
+    process of the node, so a kernel can store into a peer over NVLink).  One set per (group, capacity), reused
+    by every ShardedGrid of the process."""
+
+    _cache: Dict[Tuple[int, int], "_PeerBuffers"] = {}
+    disabled_reason: Optional[str] = None
+
+    def __init__(self, rows: int, device, group):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.rows = rows
+        self.buf = symm.empty(rows * 3, dtype=torch.float64, device=device)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+
+    @classmethod
+    def get(cls, rows_needed: int, device, group, world: int) -> Optional["_PeerBuffers"]:
+        """Collective: every rank calls it with the same rows_needed."""
+        if cls.disabled_reason is not None:
+            return None
+        best = None
+        for (w, rows), pb in cls._cache.items():
+            if w == world and rows >= rows_needed and (best is None or rows < best.rows):
+                best = pb
+        if best is not None:
+            return best
+        try:
+            rows = int(rows_needed * 1.25) + 4096
+            pb = cls(rows, device, group)
+        except Exception as exc:  # noqa: BLE001 - symmetric memory unavailable: stay on the NCCL all-to-all
+            cls.disabled_reason = f"{type(exc).__name__}: {exc}"
+            return None
+        cls._cache[(world, rows)] = pb
+        return pb
+
+
 class ShardedGrid:
     """The `Grid` operations of the hot path on a cell-sharded grid.  Pose numbers must be 0..P-1."""
 
@@ -130,20 +169,57 @@ class ShardedGrid:
         local = torch.cat(parts) if parts else torch.empty((0, 3), dtype=torch.float64, device=dev)
         mark("stage")
         n, n_seg = int(local.shape[0]), max(len(parts), 1)
-        send = torch.empty_like(local)
         counts = np.zeros((self.world, n_seg), dtype=np.int64)
         alloc = TorchAllocator(dev)
         corner = (C.c_double * 3)(*self._corner)
-        N.check(lib.ol_partition_by_owner(C.c_void_p(stream.cuda_stream), C.c_void_p(local.data_ptr()), n,
-                                          sizes.ctypes.data_as(C.c_void_p), n_seg, float(self._cfg.voxel_edge_length),
-                                          C.byref(corner), self.world, C.c_void_p(send.data_ptr()),
-                                          counts.ctypes.data_as(C.c_void_p), alloc.alloc_cb, alloc.free_cb, None))
+        use_p2p = self.world > 1 and os.environ.get("OL_EXCHANGE", "p2p") == "p2p" and self._dist.get_backend(self._group) == "nccl"
+        perm = send = None
+        if use_p2p:
+            perm = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+            N.check(lib.ol_route_plan(C.c_void_p(stream.cuda_stream), C.c_void_p(local.data_ptr()), n,
+                                      sizes.ctypes.data_as(C.c_void_p), n_seg, float(self._cfg.voxel_edge_length), C.byref(corner),
+                                      self.world, C.c_void_p(perm.data_ptr()), counts.ctypes.data_as(C.c_void_p), alloc.alloc_cb,
+                                      alloc.free_cb, None))
+        else:
+            send = torch.empty_like(local)
+            N.check(lib.ol_partition_by_owner(C.c_void_p(stream.cuda_stream), C.c_void_p(local.data_ptr()), n,
+                                              sizes.ctypes.data_as(C.c_void_p), n_seg, float(self._cfg.voxel_edge_length),
+                                              C.byref(corner), self.world, C.c_void_p(send.data_ptr()),
+                                              counts.ctypes.data_as(C.c_void_p), alloc.alloc_cb, alloc.free_cb, None))
         mark("partition")
         send_counts = routing_layout(counts[:, :len(parts)] if parts else counts[:, :0], numbers, self.n_poses_total)
-        if self.world > 1:
-            recv, recv_counts = exchange_points(send, send_counts, self._group)
-        else:
-            recv, recv_counts = send, send_counts
+        recv = None
+        if use_p2p:
+            # every rank learns the whole (source, destination, pose) count cube: 8 x 8 x P integers
+            mine = torch.from_numpy(send_counts).to(dev)
+            cube_t = torch.empty((self.world,) + tuple(mine.shape), dtype=torch.int64, device=dev)
+            self._dist.all_gather_into_tensor(cube_t, mine, group=self._group)
+            cube = cube_t.cpu().numpy()                      # [src][dst][pose]
+            tot = cube.sum(axis=2)                           # [src][dst]
+            pb = _PeerBuffers.get(int(tot.sum(axis=0).max()), dev, self._group, self.world)
+            if pb is None:
+                use_p2p = False
+                send = torch.empty_like(local)
+                N.check(lib.ol_partition_by_owner(C.c_void_p(stream.cuda_stream), C.c_void_p(local.data_ptr()), n,
+                                                  sizes.ctypes.data_as(C.c_void_p), n_seg, float(self._cfg.voxel_edge_length),
+                                                  C.byref(corner), self.world, C.c_void_p(send.data_ptr()),
+                                                  counts.ctypes.data_as(C.c_void_p), alloc.alloc_cb, alloc.free_cb, None))
+            else:
+                owner_first = np.concatenate([[0], np.cumsum(send_counts.sum(axis=1))]).astype(np.int64)
+                base = (np.cumsum(tot, axis=0) - tot)[self.rank].astype(np.int64)   # rows of lower source ranks, per destination
+                ptrs = (C.c_void_p * self.world)(*pb.ptrs)
+                pb.hdl.barrier()                             # the peers have consumed what the previous exchange delivered
+                N.check(lib.ol_route_to_peers(C.c_void_p(stream.cuda_stream), C.c_void_p(local.data_ptr()),
+                                              C.c_void_p(perm.data_ptr()), n, self.world, owner_first.ctypes.data_as(C.c_void_p),
+                                              ptrs, base.ctypes.data_as(C.c_void_p)))
+                pb.hdl.barrier()                             # every rank's rows have landed
+                recv_counts = cube[:, self.rank, :]
+                recv = pb.buf[: int(recv_counts.sum()) * 3].view(-1, 3)
+        if not use_p2p:
+            if self.world > 1:
+                recv, recv_counts = exchange_points(send, send_counts, self._group)
+            else:
+                recv, recv_counts = send, send_counts
         mark("all_to_all")
         seg_sizes, seg_pose, seg_first = segments_from_counts(recv_counts)
         mark("segments")
