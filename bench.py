@@ -38,6 +38,7 @@ WORKLOADS = {
     "c2_lidar_10x120k": dict(kind="lidar10", points=1_200_000, edge=1.0, max_points=100, threshold=0.02),
 }
 H, K = 1024, 6
+_LAST_STEP_END = 0.0
 POINTS_PER_POSE_EST = 118_000
 
 
@@ -66,7 +67,14 @@ def init_dist(world, local, backend="nccl"):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """SM clock / throttle-reason samples taken DURING the warm-up and the timed steps.
+
+    Source: NVML queried from the benchmark's own thread twice per step while the step's kernels are in flight
+    (`sample()`; 3-10 us per query, measured with tools/nvml_cost.py) - the same counters that
+    `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints (B200_PROFILING.md).  A polling side process
+    (`nvidia-smi -lms 200`) or a polling thread was measured to stall the GPU for 10-300 ms per sample once
+    peer-mapped memory exists (24 ms steps became 50-60 ms at N = 2), which would put the measurement tool inside
+    the measurement; the subprocess is therefore only the fallback when NVML cannot be loaded."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -75,18 +83,69 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu_index = gpu_index
         self.proc = None
+        self.nvml = None
+        self.handle = None
+        self.max_mhz = None
+        self.samples = []  # (sm_mhz, reasons bitmask)
         self.path = f"/tmp/ol_clocks_{os.getpid()}.csv"
+        self.source = None
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")  # NVML enumerates physical devices
+            idx = self.gpu_index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu_index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))  # 1.5 ms: once
+            self.nvml = pynvml
+            self.source = "nvml, benchmark thread, two samples per step while its kernels are in flight"
+            return
+        except Exception:  # noqa: BLE001
+            self.nvml = None
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                                           "-i", str(self.gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            self.source = "nvidia-smi -lms 200"
         except Exception:  # noqa: BLE001
             self.proc = None
 
+    def sample(self):
+        if self.nvml is None:
+            return
+        p = self.nvml
+        t0 = time.perf_counter()
+        try:
+            sm = p.nvmlDeviceGetClockInfo(self.handle, p.NVML_CLOCK_SM)
+            try:
+                reasons = p.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            except Exception:  # noqa: BLE001 - older bindings
+                reasons = p.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            self.samples.append((float(sm), int(reasons)))
+        except Exception:  # noqa: BLE001
+            pass
+        self.max_sample_ms = max(getattr(self, "max_sample_ms", 0.0), 1e3 * (time.perf_counter() - t0))
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        if self.nvml is not None:
+            p = self.nvml
+            bits = {"hw_slowdown": getattr(p, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(p, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(p, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(p, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            if self.samples:
+                seen = 0
+                for _, r in self.samples:
+                    seen |= r
+                out.update(sm_mhz=statistics.median(s[0] for s in self.samples), sm_max_mhz=self.max_mhz,
+                           reasons=sorted(n for n, b in bits.items() if seen & b), samples=len(self.samples),
+                           slowest_query_ms=round(getattr(self, "max_sample_ms", 0.0), 3))
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -169,12 +228,14 @@ def make_workload(name, rank, world, device, scale=1.0):
 # ------------------------------------------------------------------------------------------------
 # one step of this build
 # ------------------------------------------------------------------------------------------------
-def run_step(clouds, numbers, n_poses_total, w, world, profile=False, read_tables=False):
+def run_step(clouds, numbers, n_poses_total, w, world, profile=False, read_tables=False, sampler=None):
     """clouds: per-pose arrays (CUDA tensors for `value`, pinned numpy arrays for `e2e`)."""
     from octreelib_b200.criteria import MaxPoints
     from octreelib_b200.grid import Grid, GridConfig
 
     np.random.seed(0)
+    dbg = os.environ.get("OL_TIMING") == "host"
+    t_dbg = [time.perf_counter()]
     if world > 1:
         from octreelib_b200.parallel import ShardedGrid
 
@@ -186,11 +247,19 @@ def run_step(clouds, numbers, n_poses_total, w, world, profile=False, read_table
         forest.profile(True)
     for number, cloud in zip(numbers, clouds):
         grid.insert_points(number, cloud)
+    t_dbg.append(time.perf_counter())
     if world > 1:
         grid.exchange()
+    t_dbg.append(time.perf_counter())
     grid.subdivide([MaxPoints(w["max_points"])])
+    if sampler is not None:
+        sampler.sample()
+    t_dbg.append(time.perf_counter())
     grid.map_leaf_points_cuda_ransac(poses_per_batch=10, threshold=w["threshold"], hypotheses_number=H,
                                      initial_points_number=K)
+    t_dbg.append(time.perf_counter())
+    if sampler is not None:
+        sampler.sample()  # the mask compaction kernels of this step are still in flight
     d2h = 0
     if read_tables:
         planes = forest.export_ransac(scored_only=True)
@@ -198,6 +267,13 @@ def run_step(clouds, numbers, n_poses_total, w, world, profile=False, read_table
         d2h = sum(a.nbytes for a in planes.values()) + sum(a.nbytes for a in leaves.values())
     stats = forest.stats(light=True)  # waits for the step; the step's scalar results (alive points, leaves, ...)
     prof = forest.profile_read() if profile else None
+    if dbg and int(os.environ.get("RANK", "0")) == 0:
+        t_dbg.append(time.perf_counter())
+        names = ["insert", "exchange", "subdivide", "ransac", "stats"]
+        global _LAST_STEP_END
+        gap = 1e3 * (t_dbg[0] - _LAST_STEP_END) if _LAST_STEP_END else 0.0
+        _LAST_STEP_END = time.perf_counter()
+        print(f"[step host ms] gap-before {gap:.2f}, " + ", ".join(f"{n} {1e3 * (b - a):.2f}" for n, a, b in zip(names, t_dbg, t_dbg[1:])), flush=True)
     return grid, stats, prof, d2h
 
 
@@ -307,6 +383,10 @@ def main():
         ev0.record()
         res = None
         for _ in range(steps):
+            # drop the previous step's grid BEFORE building the next one, exactly like the warm-up loop does: with two
+            # grids alive the caching allocator needs a second set of multi-GB blocks that the warm-up never created,
+            # and the cudaMalloc calls for it (100-300 ms) would land inside the timed region
+            res = None
             res = fn()
         ev1.record()
         barrier()
@@ -317,14 +397,16 @@ def main():
             ms = float(t.item())
         return ms, res
 
+    # clock samples are taken inside the warm-up and the timed steps (same load); see ClockSampler
+    sampler = ClockSampler(local)
+    if rank == 0 and os.environ.get("OL_NO_SAMPLER") != "1":  # diagnostic switch; the default run always samples
+        sampler.start()
+    smp = sampler if rank == 0 else None
     # warm-up (also warms torch's caching allocator so the timed steps do not call cudaMalloc)
     for _ in range(args.warmup):
-        run_step(clouds, numbers, P, w, world)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+        run_step(clouds, numbers, P, w, world, sampler=smp)
     launches0 = lib.ol_launch_count()
-    ms, res = timed(lambda: run_step(clouds, numbers, P, w, world), args.steps)
+    ms, res = timed(lambda: run_step(clouds, numbers, P, w, world, sampler=smp), args.steps)
     launches = (lib.ol_launch_count() - launches0) // max(args.steps, 1)
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps

@@ -284,14 +284,36 @@ __global__ void weighted_count_kernel(const uint32_t* __restrict__ leaf_of, cons
     if (on && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&wcount[k], __popc(peers));
 }
 
+// key of a tree node for the scheme replay: (cell index, depth <= REPLAY_MAX_DEPTH, Morton path)
+constexpr int REPLAY_MAX_DEPTH = 9;
+__host__ __device__ inline uint64_t replay_key(uint32_t cell, uint32_t depth, uint64_t path) {
+    return ((uint64_t)cell << 32) | ((uint64_t)depth << 27) | (path & 0x7ffffffull);
+}
+
 __global__ void decide_kernel(uint32_t L, const uint32_t* __restrict__ lstart, const uint8_t* __restrict__ ldepth,
                               int level, const uint32_t* __restrict__ wcount, long long max_points,
                               const uint8_t* __restrict__ table, long long table_len, int beyond, int max_depth,
-                              uint32_t* __restrict__ splitf, uint32_t* __restrict__ expand, uint32_t* __restrict__ err) {
+                              const uint64_t* __restrict__ replay_keys, uint32_t n_replay, const uint32_t* __restrict__ lcell,
+                              const uint64_t* __restrict__ lpath, uint32_t* __restrict__ splitf, uint32_t* __restrict__ expand,
+                              uint32_t* __restrict__ err) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= L) return;
     bool want = false;
-    if (ldepth[k] == level) {
+    if (replay_keys) {
+        // scheme replay (octree_manager.py:171 -> octree.py:222-227): split exactly the nodes of the recorded shape
+        if (ldepth[k] == level && level < REPLAY_MAX_DEPTH) {
+            const uint64_t key = replay_key(lcell[k], (uint32_t)level, lpath[k]);
+            uint32_t lo = 0, hi = n_replay;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (replay_keys[mid] < key)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            want = lo < n_replay && replay_keys[lo] == key;
+        }
+    } else if (ldepth[k] == level) {
         long long cnt = wcount ? (long long)wcount[k] : (long long)(lstart[k + 1] - lstart[k]);
         if (table)
             want = (cnt < table_len) ? (table[cnt] != 0) : (beyond != 0);
@@ -469,7 +491,7 @@ __global__ void expand_leaves_kernel(uint32_t L, uint32_t A, uint32_t I_old, con
                                      int32_t* __restrict__ lparent_n, uint64_t* __restrict__ lpath_n,
                                      uint8_t* __restrict__ ldepth_n, uint8_t* __restrict__ lchild_n,
                                      uint32_t* __restrict__ istart, uint32_t* __restrict__ icell,
-                                     uint8_t* __restrict__ idepth) {
+                                     uint8_t* __restrict__ idepth, uint64_t* __restrict__ ipath) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= L) return;
     const uint32_t j0 = newidx[k];
@@ -486,6 +508,7 @@ __global__ void expand_leaves_kernel(uint32_t L, uint32_t A, uint32_t I_old, con
         istart[id] = lstart[k];
         icell[id] = lcell[k];
         idepth[id] = ldepth[k];
+        ipath[id] = lpath[k];
         uint32_t run = lstart[k];
         for (uint32_t c = 0; c < 8; ++c) {
             const uint32_t j = j0 + c;
@@ -499,6 +522,55 @@ __global__ void expand_leaves_kernel(uint32_t L, uint32_t A, uint32_t I_old, con
         }
     }
     if (k == L - 1) lstart_n[L_new] = A;
+}
+
+// ---- scheme replay: record the split nodes by cell COORDINATES (the packed key changes when the grid is rebuilt) ----
+__global__ void save_shape_kernel(uint32_t I, const uint32_t* __restrict__ icell, const uint8_t* __restrict__ idepth,
+                                  const uint64_t* __restrict__ ipath, const uint64_t* __restrict__ cell_key, KeyParams kp,
+                                  long long* __restrict__ q_out /*[I][3]*/, uint32_t* __restrict__ depth_out,
+                                  uint64_t* __restrict__ path_out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= I) return;
+    long long q[3] = {0, 0, 0};
+    if (!kp.single_cell) unpack_cell(kp, cell_key[icell[i]], q);
+    q_out[(size_t)i * 3 + 0] = q[0];
+    q_out[(size_t)i * 3 + 1] = q[1];
+    q_out[(size_t)i * 3 + 2] = q[2];
+    depth_out[i] = idepth[i];
+    path_out[i] = ipath[i];
+}
+
+// recorded split node -> key under the NEW cell table (binary search of the packed cell key); ~0 if the cell is gone
+__global__ void replay_keys_kernel(uint32_t n, const long long* __restrict__ q_in, const uint32_t* __restrict__ depth_in,
+                                   const uint64_t* __restrict__ path_in, const uint64_t* __restrict__ cell_key, uint32_t C,
+                                   KeyParams kp, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t out = ~0ull;
+    uint64_t packed = 0;
+    bool ok = true;
+    if (!kp.single_cell) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const long long rel = q_in[(size_t)i * 3 + a] - kp.qmin[a];
+            if (rel < 0) ok = false;
+            const int s = kp.shift[a] - kp.pose_bits;
+            if (ok && s < 64) packed |= ((uint64_t)rel) << s;
+        }
+    }
+    if (ok) {
+        uint32_t lo = 0, hi = C;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (cell_key[mid] < packed)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        if (lo < C && cell_key[lo] == packed) out = replay_key(lo, depth_in[i], path_in[i]);
+    }
+    keys[i] = out;
+    vals[i] = i;
 }
 
 // =============================================================================================

@@ -68,6 +68,7 @@ struct Forest {
     DevBuf<uint32_t> istart;     // [I] first position of the internal node's range
     DevBuf<uint32_t> icell;      // [I]
     DevBuf<uint8_t> idepth;      // [I]
+    DevBuf<uint64_t> ipath;      // [I] Morton digits from the cell root
     int depth_reached = 0;
 
     // ---- derived tables (rebuilt lazily after the shape or the point set changes) ---------------
@@ -77,6 +78,14 @@ struct Forest {
     DevBuf<double> leaf_corner;  // [L][3] in cache order
     DevBuf<double> leaf_edge;    // [L]   in cache order
     DevBuf<uint32_t> cell_leaf_begin;  // [C+1] in cache order
+
+    // scheme replay (insert after a subdivision, octree_manager.py:161-171): the split nodes of the last shape,
+    // by cell coordinates, imposed again on the rebuilt grid the next time the shape is needed
+    bool replay_pending = false;
+    uint32_t sp_n = 0;
+    DevBuf<long long> sp_q;      // [sp_n][3]
+    DevBuf<uint32_t> sp_depth;   // [sp_n]
+    DevBuf<uint64_t> sp_path;    // [sp_n]
 
     bool blocks_valid = false;
     uint32_t NB = 0;
@@ -113,6 +122,10 @@ struct Forest {
     void reset_shape();      // current := base (every cell one leaf)
     void subdivide(int64_t max_points, const uint8_t* table, int64_t table_len, int beyond, const int32_t* poses,
                    int n_poses_listed);  // K4
+    void split_levels(int64_t max_points, const uint8_t* d_table, int64_t table_len, int beyond, const uint8_t* d_listed,
+                      int n_listed, const uint64_t* replay_keys, uint32_t n_replay);  // the level loop of K4
+    void save_shape();       // record the split nodes before a rebuild
+    void replay_shape();     // impose the recorded shape on the rebuilt grid
     void ensure_shape();
     void ensure_order();     // K5: leaf enumeration order + geometry
     void ensure_blocks();    // (pose, leaf) runs

@@ -79,9 +79,7 @@ int Forest::insert(const double* xyz, int64_t n, bool on_device, const int64_t* 
     OL_REQUIRE(n >= 0, OL_ERR_INVALID, "negative point count");
     OL_REQUIRE(N + (size_t)n < (1ull << 31), OL_ERR_INVALID, "more than 2^31 - 1 points per forest are not supported");
     materialize_snapshot();
-    OL_REQUIRE(!(shaped && I > 0), OL_ERR_STATE,
-               "inserting a pose after the grid was subdivided (scheme replay, octree_manager.py:171) is not "
-               "implemented yet");
+    if (shaped && I > 0) save_shape();  // a later pose follows the existing subdivision (octree_manager.py:171)
     if (N + (size_t)n > cap) {
         size_t ncap = std::max<size_t>(N + (size_t)n, cap + cap / 2 + 1024);
         DevBuf<double> np(ctx, ncap * 3);
@@ -355,12 +353,46 @@ void Forest::reset_shape() {
     istart.reset(ctx, 0);
     icell.reset(ctx, 0);
     idepth.reset(ctx, 0);
+    ipath.reset(ctx, 0);
     shaped = true;
     order_valid = blocks_valid = ransac_valid = false;
 }
 
 void Forest::ensure_shape() {
-    if (!shaped) reset_shape();
+    if (shaped) return;
+    reset_shape();
+    if (replay_pending) replay_shape();
+}
+
+void Forest::save_shape() {
+    if (replay_pending) return;  // still waiting for a rebuild: the recorded shape is the current one
+    OL_REQUIRE(depth_reached <= REPLAY_MAX_DEPTH, OL_ERR_STATE,
+               "inserting a pose into a grid subdivided deeper than " + std::to_string(REPLAY_MAX_DEPTH) + " levels is not supported");
+    sp_n = I;
+    sp_q.reset(ctx, (size_t)I * 3);
+    sp_depth.reset(ctx, I);
+    sp_path.reset(ctx, I);
+    save_shape_kernel<<<nblk(I), 256, 0, ctx.stream>>>(I, icell.get(), idepth.get(), ipath.get(), cell_key.get(), kp, sp_q.get(),
+                                                       sp_depth.get(), sp_path.get());
+    OL_CHECK_LAUNCH();
+    replay_pending = true;
+}
+
+void Forest::replay_shape() {
+    replay_pending = false;
+    const uint32_t n = sp_n;
+    if (n == 0 || L == 0 || A == 0) return;
+    DevBuf<uint64_t> k0(ctx, n), k1(ctx, n);
+    DevBuf<uint32_t> v0(ctx, n), v1(ctx, n);
+    replay_keys_kernel<<<nblk(n), 256, 0, ctx.stream>>>(n, sp_q.get(), sp_depth.get(), sp_path.get(), cell_key.get(), C, kp, k0.get(),
+                                                        v0.get());
+    OL_CHECK_LAUNCH();
+    const int w = radix_sort_pairs<uint64_t>(ctx, k0.get(), k1.get(), v0.get(), v1.get(), n, 0, 64);
+    split_levels(0, nullptr, 0, 0, nullptr, 0, w ? k1.get() : k0.get(), n);
+    sp_q.release();
+    sp_depth.release();
+    sp_path.release();
+    sp_n = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -369,9 +401,9 @@ void Forest::ensure_shape() {
 // ---------------------------------------------------------------------------------------------
 void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t table_len, int beyond, const int32_t* poses,
                        int n_listed) {
+    replay_pending = false;  // a fresh scheme replaces whatever shape was recorded
     reset_shape();
     if (L == 0 || A == 0) return;
-    const int S = (int)seg_pose.size();
     DevBuf<uint8_t> listed, table;
     if (n_listed > 0) {
         std::vector<uint8_t> h(std::max(n_poses, 1), 0);
@@ -389,6 +421,14 @@ void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t ta
         h2d(ctx, table.get(), table_host, (size_t)table_len);
         ctx.sync();
     }
+    split_levels(max_points, table.get(), table_len, beyond, listed.get(), n_listed, nullptr, 0);
+}
+
+// The level loop of K4.  Decision per leaf of the current level: count criterion (all points, or the points of
+// the listed poses), count table, or - replay_keys != nullptr - membership in a recorded shape.
+void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t table_len, int beyond, const uint8_t* d_listed,
+                          int n_listed, const uint64_t* replay_keys, uint32_t n_replay) {
+    const int S = (int)seg_pose.size();
     DevBuf<unsigned long long> d_tot(ctx, 2);
     const uint32_t tiles = (A + PART_TILE - 1) / PART_TILE;
     DevBuf<uint32_t> tile_hist(ctx, (size_t)8 * tiles), rank(ctx, A);
@@ -402,16 +442,16 @@ void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t ta
             {
                 ProfScope ps(ctx, "weighted_count", (double)A);
                 weighted_count_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), perm.get(), ldepth.get(), level,
-                                                                       d_seg_start.get(), d_seg_pose.get(), S, listed.get(), A,
+                                                                       d_seg_start.get(), d_seg_pose.get(), S, d_listed, A,
                                                                        wcount.get());
                 OL_CHECK_LAUNCH();
             }
         }
         {
             ProfScope ps(ctx, "part_decide");
-            decide_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, lstart.get(), ldepth.get(), level, wcount.get(), max_points,
-                                                           table.get(), table_len, beyond, max_depth, splitf.get(),
-                                                           expand.get(), d_err.get());
+            decide_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, lstart.get(), ldepth.get(), level, wcount.get(), max_points, d_table,
+                                                           table_len, beyond, max_depth, replay_keys, n_replay, lcell.get(),
+                                                           lpath.get(), splitf.get(), expand.get(), d_err.get());
             OL_CHECK_LAUNCH();
         }
         exclusive_scan_u32(ctx, expand.get(), newidx.get(), L, d_tot.get());
@@ -457,6 +497,8 @@ void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t ta
         DevBuf<int32_t> lparent_n(ctx, L_new);
         DevBuf<uint64_t> lpath_n(ctx, L_new);
         DevBuf<uint8_t> ldepth_n(ctx, L_new), lchild_n(ctx, L_new), idepth_n(ctx, (size_t)I + n_split);
+        DevBuf<uint64_t> ipath_n(ctx, (size_t)I + n_split);
+        d2d(ctx, ipath_n.get(), ipath.get(), I);
         d2d(ctx, istart_n.get(), istart.get(), I);
         d2d(ctx, icell_n.get(), icell.get(), I);
         d2d(ctx, idepth_n.get(), idepth.get(), I);
@@ -466,7 +508,7 @@ void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t ta
                                                                   Send.get(), lstart.get(), lcell.get(), lparent.get(), lpath.get(),
                                                                   ldepth.get(), lchild.get(), L_new, lstart_n.get(), lcell_n.get(),
                                                                   lparent_n.get(), lpath_n.get(), ldepth_n.get(), lchild_n.get(),
-                                                                  istart_n.get(), icell_n.get(), idepth_n.get());
+                                                                  istart_n.get(), icell_n.get(), idepth_n.get(), ipath_n.get());
             OL_CHECK_LAUNCH();
         }
         lstart.swap(lstart_n);
@@ -478,6 +520,7 @@ void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t ta
         istart.swap(istart_n);
         icell.swap(icell_n);
         idepth.swap(idepth_n);
+        ipath.swap(ipath_n);
         perm.swap(perm_b);
         mort.swap(mort_b);
         leaf_of.swap(leaf_b);

@@ -151,9 +151,13 @@ class ShardedGrid:
         timing = os.environ.get("OL_TIMING") == "1"
         marks = []
 
+        host_only = os.environ.get("OL_TIMING") == "host"  # host wall time per phase, no device synchronisation
+        timing = timing or host_only
+
         def mark(name):
             if timing:
-                torch.cuda.synchronize()
+                if not host_only:
+                    torch.cuda.synchronize()
                 marks.append((name, time.perf_counter()))
 
         mark("start")
@@ -208,11 +212,28 @@ class ShardedGrid:
                 owner_first = np.concatenate([[0], np.cumsum(send_counts.sum(axis=1))]).astype(np.int64)
                 base = (np.cumsum(tot, axis=0) - tot)[self.rank].astype(np.int64)   # rows of lower source ranks, per destination
                 ptrs = (C.c_void_p * self.world)(*pb.ptrs)
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if (timing and not host_only) else None
+                mark("allgather")
+                if ev:
+                    ev[0].record()
                 pb.hdl.barrier()                             # the peers have consumed what the previous exchange delivered
+                if ev:
+                    ev[1].record()
+                mark("barrier0")
                 N.check(lib.ol_route_to_peers(C.c_void_p(stream.cuda_stream), C.c_void_p(local.data_ptr()),
                                               C.c_void_p(perm.data_ptr()), n, self.world, owner_first.ctypes.data_as(C.c_void_p),
                                               ptrs, base.ctypes.data_as(C.c_void_p)))
+                if ev:
+                    ev[2].record()
+                mark("route")
                 pb.hdl.barrier()                             # every rank's rows have landed
+                mark("barrier1")
+                if ev:
+                    ev[3].record()
+                    torch.cuda.synchronize()
+                    if self.rank == 0:
+                        print(f"[p2p] barrier0 {ev[0].elapsed_time(ev[1]):.3f} ms, route kernel {ev[1].elapsed_time(ev[2]):.3f} ms, "
+                              f"barrier1 {ev[2].elapsed_time(ev[3]):.3f} ms", flush=True)
                 recv_counts = cube[:, self.rank, :]
                 recv = pb.buf[: int(recv_counts.sum()) * 3].view(-1, 3)
         if not use_p2p:

@@ -164,6 +164,41 @@ def structure_case(name, clouds, edge, max_points, subdivide_poses=None, filter_
           f"leaves/pose {[int(canon[f'p{p}_counts'][0]) for p in clouds]}  -- oracle == reference OK")
 
 
+def late_pose_case(name, clouds, late, edge, max_points):
+    """Poses inserted AFTER a subdivision follow the existing scheme (octree_manager.py:161-171); new cells stay
+    unsplit.  `late` = the pose numbers inserted after the subdivide call."""
+    crit = [lambda pts: len(pts) > max_points]
+    early = [p for p in clouds if p not in late]
+
+    def run(make_grid, insert, subdivide):
+        g = make_grid()
+        for p in early:
+            insert(g, p, clouds[p])
+        subdivide(g)
+        for p in late:
+            insert(g, p, clouds[p])
+        return g
+
+    ref_asis = dump_reference(run(lambda: Grid(GridConfig(voxel_edge_length=edge)), lambda g, p, c: g.insert_points(p, c),
+                                  lambda g: g.subdivide(crit)), clouds)
+    with stable_order():
+        canon = dump_reference(run(lambda: Grid(GridConfig(voxel_edge_length=edge)), lambda g, p, c: g.insert_points(p, c),
+                                   lambda g: g.subdivide(crit)), clouds)
+    og = run(lambda: OracleGrid(edge), lambda g, p, c: g.insert_points(p, c),
+             lambda g: g.subdivide([max_points_criterion(max_points)]))
+    ora = dump_oracle(og, clouds)
+    compare(ref_asis, ora, ordered=False, tag=name + ":as-is")
+    compare(canon, ora, ordered=True, tag=name + ":stable")
+    save = {f"cloud{p}": c for p, c in clouds.items()}
+    save.update(canon)
+    save["edge"], save["max_points"] = np.float64(edge), np.int64(max_points)
+    save["poses"] = np.array(list(clouds.keys()), dtype=np.int64)
+    save["late"] = np.array(list(late), dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
+    print(f"[golden] {name}: late poses {list(late)}, leaves/pose {[int(canon[f'p{p}_counts'][0]) for p in clouds]}"
+          "  -- oracle == reference OK")
+
+
 def ransac_case(name, clouds, edge, max_points, H, K, threshold, seed, poses_per_batch):
     """Runs the reference's numba kernel under CUDASIM (slow: keep #blocks * H small)."""
     crit = [lambda pts: len(pts) > max_points]
@@ -233,6 +268,15 @@ def ransac_case(name, clouds, edge, max_points, H, K, threshold, seed, poses_per
 
 def main():
     rng = np.random.default_rng(2024)
+    only = os.environ.get("GOLDEN_ONLY")  # GOLDEN_ONLY=late regenerates only the late-pose fixture (own RNG stream)
+    if only == "late":
+        def f32(a):
+            return a.astype(np.float32).astype(np.float64)
+        rng7 = np.random.default_rng(777)
+        c3 = {p: f32(rng7.random((900, 3)) * np.array([5.0, 4.0, 2.0]) + np.array([0.3 * p, 0, 0])) for p in range(3)}
+        c3[3] = f32(rng7.random((700, 3)) * np.array([5.0, 4.0, 2.0]) + np.array([3.0, 2.0, 0.0]))
+        late_pose_case("late_poses_edge2", c3, late=[2, 3], edge=2, max_points=12)
+        return
 
     def f32(a):
         return a.astype(np.float32).astype(np.float64)
@@ -262,6 +306,12 @@ def main():
     a = f32(rng.random((600, 3)) * 4)
     b = f32(rng.random((600, 3)) * 4 + np.array([2.0, 0, 0]))
     structure_case("offset_poses_edge1", {0: a, 1: b}, 1, 8)
+
+    # S7: two poses inserted after the subdivision; the last one also opens cells the scheme never saw
+    rng7 = np.random.default_rng(777)
+    c3 = {p: f32(rng7.random((900, 3)) * np.array([5.0, 4.0, 2.0]) + np.array([0.3 * p, 0, 0])) for p in range(3)}
+    c3[3] = f32(rng7.random((700, 3)) * np.array([5.0, 4.0, 2.0]) + np.array([3.0, 2.0, 0.0]))
+    late_pose_case("late_poses_edge2", c3, late=[2, 3], edge=2, max_points=12)
 
     # R1..: RANSAC under CUDASIM (about 2 s per block at H=1024 -> small H / few blocks)
     pl = indoor_scene(700, seed=3)
