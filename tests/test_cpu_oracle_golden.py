@@ -47,6 +47,27 @@ def test_structure_oracle_matches_reference_golden(name):
         assert (np.array(og.pose_cells[p], dtype=np.int64).reshape(-1, 3) == g[f"p{p}_cells"]).all()
 
 
+def test_late_pose_oracle_matches_reference_golden():
+    """Poses inserted after the subdivision follow the existing scheme (octree_manager.py:161-171)."""
+    g = golden("late_poses_edge2")
+    late = [int(p) for p in g["late"]]
+    poses = [int(p) for p in g["poses"]]
+    og = OracleGrid(int(g["edge"]))
+    for p in poses:
+        if p not in late:
+            og.insert_points(p, g[f"cloud{p}"])
+    og.subdivide([max_points_criterion(int(g["max_points"]))])
+    for p in late:
+        og.insert_points(p, g[f"cloud{p}"])
+    for p in poses:
+        leaves = og.get_leaf_points(p)
+        corner = np.array([np.asarray(l.corner, dtype=np.float64) for l in leaves]).reshape(-1, 3)
+        assert (corner == g[f"p{p}_corner"]).all() and (np.array([float(l.edge) for l in leaves]) == g[f"p{p}_edge"]).all()
+        assert (np.concatenate([l.idx for l in leaves]) == g[f"p{p}_idx"]).all()
+        assert [og.n_leaves(p), og.n_points(p), og.n_nodes(p)] == g[f"p{p}_counts"].tolist()
+        assert (og.get_point_indices(p) == g[f"p{p}_getpoints_idx"]).all()
+
+
 @pytest.mark.parametrize("name", RANSAC_CASES)
 def test_ransac_oracle_matches_reference_golden(name):
     g = golden(name)

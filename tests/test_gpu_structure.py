@@ -64,6 +64,51 @@ def test_golden_structure(name):
             assert v.n_points == s and v.get_points().shape == (s, 3)
 
 
+def test_golden_late_poses_follow_the_scheme():
+    """Insert after subdivide (octree_manager.py:161-171): golden vectors recorded from the real reference."""
+    g = golden("late_poses_edge2")
+    late = [int(p) for p in g["late"]]
+    poses = [int(p) for p in g["poses"]]
+    grid = Grid(GridConfig(voxel_edge_length=int(g["edge"])))
+    for p in poses:
+        if p not in late:
+            grid.insert_points(p, g[f"cloud{p}"])
+    grid.subdivide([lambda pts, n=int(g["max_points"]): len(pts) > n])
+    for k, p in enumerate(late):
+        grid.insert_points(p, g[f"cloud{p}"])
+        if k == 0:
+            assert grid.n_points(p) == len(g[f"cloud{p}"])  # a query between two late inserts replays the scheme
+    forest = grid._host.forest
+    blocks, leaves = forest.export_blocks(), forest.export_leaves()
+    for p in poses:
+        pi = grid._host.pose_index[p]
+        sel = np.flatnonzero(blocks["pose"] == pi)
+        lf = blocks["leaf"][sel]
+        assert (leaves["corner"][lf] == g[f"p{p}_corner"]).all() and (leaves["edge"][lf] == g[f"p{p}_edge"]).all()
+        assert (blocks["size"][sel] == g[f"p{p}_size"]).all()
+        assert (forest.export_points(pi, order=0)["idx"] == g[f"p{p}_idx"]).all()
+        assert [grid.n_leaves(p), grid.n_points(p), grid.n_nodes(p)] == g[f"p{p}_counts"].tolist()
+        assert (grid.get_points(p) == g[f"cloud{p}"][g[f"p{p}_getpoints_idx"]]).all()
+
+
+def test_late_pose_matches_oracle_lidar():
+    clouds = {p: lidar64_scan(p, seed=4)[::6] for p in range(4)}
+    grid, og = Grid(GridConfig(voxel_edge_length=1.0)), OracleGrid(1.0)
+    for p in (0, 1):
+        grid.insert_points(p, clouds[p])
+        og.insert_points(p, clouds[p])
+    grid.subdivide([MaxPoints(40)])
+    og.subdivide([max_points_criterion(40)])
+    for p in (2, 3):
+        grid.insert_points(p, clouds[p])
+        og.insert_points(p, clouds[p])
+    compare_grid_with_oracle(grid, og, clouds)
+    # a new subdivide over all four poses starts from a fresh scheme again
+    grid.subdivide([MaxPoints(40)])
+    og.subdivide([max_points_criterion(40)])
+    compare_grid_with_oracle(grid, og, clouds)
+
+
 @pytest.mark.parametrize("seed,n,edge,max_points", [(0, 30000, 1, 50), (1, 60000, 2, 100), (2, 20000, 4, 5)])
 def test_oracle_parity_random(seed, n, edge, max_points):
     rng = np.random.default_rng(seed)
