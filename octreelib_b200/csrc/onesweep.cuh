@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(OS_THREADS, MIN_BLOCKS) os_pass_kernel(const K
     uint32_t* s_whist = s_vals + OS_TILE;                                           // [OS_WARPS][256]
     uint32_t* s_delta = s_whist + OS_WARPS * 256;                                   // [256] global position - local position
     uint32_t* s_excl = s_delta + 256;                                               // [256] first local position of the digit
+    uint32_t* s_vraw = s_excl + 256;                                                // [OS_TILE] values in input order (cp.async)
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp_scan[8];
 
@@ -151,6 +152,24 @@ __global__ void __launch_bounds__(OS_THREADS, MIN_BLOCKS) os_pass_kernel(const K
     for (int i = threadIdx.x; i < OS_WARPS * 256; i += OS_THREADS) s_whist[i] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
+    // The values are only needed for the tile reorder: start an asynchronous global -> shared copy of the tile's
+    // values now (LDGSTS, no registers held) so that their latency hides behind ranking and the chained scan.
+    {
+        const uint32_t tbase = tile * OS_TILE;
+        const uint32_t tcount = min((uint32_t)OS_TILE, n - tbase);
+        if (tcount == (uint32_t)OS_TILE) {
+            for (uint32_t e = threadIdx.x * 4; e < (uint32_t)OS_TILE; e += OS_THREADS * 4) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_vraw + e);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(vals_in + tbase + e) : "memory");
+            }
+        } else {
+            for (uint32_t e = threadIdx.x; e < tcount; e += OS_THREADS) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_vraw + e);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(vals_in + tbase + e) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     const uint32_t mask = (1u << nbits) - 1u;
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t wbase = tile * OS_TILE + warp * (32 * OS_ITEMS);
@@ -212,7 +231,8 @@ __global__ void __launch_bounds__(OS_THREADS, MIN_BLOCKS) os_pass_kernel(const K
         local_first = wb + inc - count;
         s_excl[d] = local_first;
     }
-    __syncthreads();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's share of the value copy has landed ...
+    __syncthreads();                                      // ... and after the barrier everybody's has
 
     // ---- reorder inside the tile (shared memory): keys and values to their local sorted position.  This runs
     // BETWEEN publishing the tile's aggregate and the look-back, so the value loads and the shared-memory
@@ -224,7 +244,7 @@ __global__ void __launch_bounds__(OS_THREADS, MIN_BLOCKS) os_pass_kernel(const K
             const uint32_t dg = (uint32_t)(k[j] >> shift) & mask;
             const uint32_t p = s_excl[dg] + wh[dg] + rnk[j];
             s_keys[p] = k[j];
-            s_vals[p] = vals_in[i];
+            s_vals[p] = s_vraw[i - tile * OS_TILE];
         }
     }
     // ---- decoupled look-back: sum the aggregates of the preceding tiles until an inclusive prefix is found ----
@@ -260,7 +280,7 @@ __global__ void __launch_bounds__(OS_THREADS, MIN_BLOCKS) os_pass_kernel(const K
 
 template <typename KeyT, int THREADS, int ITEMS>
 inline size_t os_pass_smem() {
-    return sizeof(KeyT) * THREADS * ITEMS + 4 * THREADS * ITEMS + 4 * ((THREADS / 32) * 256 + 256 + 256);
+    return sizeof(KeyT) * THREADS * ITEMS + 4 * THREADS * ITEMS + 4 * ((THREADS / 32) * 256 + 256 + 256) + 4 * THREADS * ITEMS;
 }
 
 // tile shapes selectable at run time (ol_debug_sort_variant): A/B measurements inside one process
