@@ -14,7 +14,25 @@ namespace ol {
 // =============================================================================================
 // segment of global rank r: last s with seg_start[s] <= r   (seg_start has n_seg + 1 entries)
 __device__ __forceinline__ int seg_of_rank(const uint32_t* __restrict__ seg_start, int n_seg, uint32_t r) {
+    // poses have similar sizes, so an interpolated first guess is usually right or off by one; a few linear
+    // probes, then plain bisection of whatever interval is left
+    const uint32_t total = seg_start[n_seg];
+    int s = (int)((float)r * __fdividef((float)n_seg, (float)(total ? total : 1u)));  // a guess: any value is corrected below
+    s = s < 0 ? 0 : (s >= n_seg ? n_seg - 1 : s);
     int lo = 0, hi = n_seg;  // invariant: seg_start[lo] <= r < seg_start[hi]
+#pragma unroll 1
+    for (int probe = 0; probe < 3; ++probe) {
+        if (seg_start[s] > r) {
+            hi = s;
+            s = s - 1;
+        } else if (seg_start[s + 1] <= r) {
+            lo = s + 1;
+            s = s + 1;
+        } else {
+            return s;
+        }
+        if (s < lo || s >= hi) break;
+    }
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
         if (seg_start[mid] <= r)
@@ -170,55 +188,52 @@ __global__ void __launch_bounds__(256) remorton_kernel(const double* __restrict_
 // =============================================================================================
 // K3: run-length segmentation of the sorted keys
 // =============================================================================================
-__global__ void cell_heads_kernel(const uint64_t* __restrict__ keys, uint32_t n, int pose_bits, uint32_t* __restrict__ flags) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    flags[i] = (i == 0) || ((keys[i] >> pose_bits) != (keys[i - 1] >> pose_bits));
-}
-
-// scan_ex[i] = exclusive scan of flags; the index of position i's run is scan_ex[i] + flags[i] - 1
-__global__ void cell_emit_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ flags,
-                                 const uint32_t* __restrict__ scan_ex, uint32_t n, int pose_bits,
-                                 uint32_t* __restrict__ cellidx, uint64_t* __restrict__ cell_key,
-                                 uint32_t* __restrict__ cell_start) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t c = scan_ex[i] + flags[i] - 1u;
-    cellidx[i] = c;
-    if (flags[i]) {
-        cell_key[c] = keys[i] >> pose_bits;
-        cell_start[c] = i;
+// key / emit functors for segment_runs (primitives.cuh)
+struct CellKeyFn {  // grid cell of a sorted position: the packed key without its pose bits
+    const uint64_t* keys;
+    int pose_bits;
+    __device__ uint64_t operator()(uint32_t i) const { return keys[i] >> pose_bits; }
+};
+struct CellEmitFn {
+    uint64_t* cell_key;
+    uint32_t* cell_start;
+    __device__ void operator()(uint32_t run, uint32_t i, uint64_t key) const {
+        cell_key[run] = key;
+        cell_start[run] = i;
     }
-}
-
-__global__ void cp_heads_kernel(const uint32_t* __restrict__ cellidx, const uint32_t* __restrict__ perm,
-                                const uint32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_pose, int n_seg,
-                                uint32_t n, uint32_t* __restrict__ flags, int32_t* __restrict__ pose_of_pos) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int32_t p = seg_pose[seg_of_rank(seg_start, n_seg, perm[i])];
-    pose_of_pos[i] = p;
-    bool head = (i == 0);
-    if (!head) {
-        int32_t pp = seg_pose[seg_of_rank(seg_start, n_seg, perm[i - 1])];
-        head = (cellidx[i] != cellidx[i - 1]) || (pp != p);
+};
+struct GroupPoseKeyFn {  // (group of the position, pose of its point): group = cell index or leaf index
+    const uint32_t* group;
+    const uint32_t* perm;
+    const uint32_t* seg_start;
+    const int32_t* seg_pose;
+    int n_seg;
+    __device__ uint64_t operator()(uint32_t i) const {
+        return ((uint64_t)group[i] << 32) | (uint64_t)(uint32_t)seg_pose[seg_of_rank(seg_start, n_seg, perm[i])];
     }
-    flags[i] = head;
-}
-
-__global__ void cp_emit_kernel(const uint32_t* __restrict__ cellidx, const int32_t* __restrict__ pose_of_pos,
-                               const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan_ex, uint32_t n,
-                               uint32_t* __restrict__ cp_cell, int32_t* __restrict__ cp_pose,
-                               int32_t* __restrict__ cell_first_pose) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (flags[i]) {
-        uint32_t j = scan_ex[i];
-        cp_cell[j] = cellidx[i];
-        cp_pose[j] = pose_of_pos[i];
-        if (i == 0 || cellidx[i] != cellidx[i - 1]) cell_first_pose[cellidx[i]] = pose_of_pos[i];
+};
+struct CellPoseEmitFn {  // (cell, pose) pairs that own an octree; the first pose of a cell created it (dict order, grid.py:56)
+    uint32_t* cp_cell;
+    int32_t* cp_pose;
+    int32_t* cell_first_pose;
+    const uint32_t* cellidx;
+    __device__ void operator()(uint32_t run, uint32_t i, uint64_t key) const {
+        const uint32_t cell = (uint32_t)(key >> 32);
+        cp_cell[run] = cell;
+        cp_pose[run] = (int32_t)(uint32_t)key;
+        if (i == 0 || cellidx[i - 1] != cell) cell_first_pose[cell] = (int32_t)(uint32_t)key;
     }
-}
+};
+struct BlockEmitFn {  // non-empty (pose, leaf) blocks
+    uint32_t* blk_start;
+    uint32_t* blk_leaf;
+    int32_t* blk_pose;
+    __device__ void operator()(uint32_t run, uint32_t i, uint64_t key) const {
+        blk_start[run] = i;
+        blk_leaf[run] = (uint32_t)(key >> 32);
+        blk_pose[run] = (int32_t)(uint32_t)key;
+    }
+};
 
 // =============================================================================================
 // generic keep-flag compaction of the per-position arrays
@@ -642,36 +657,6 @@ __global__ void leaf_geometry_kernel(uint32_t L, const uint32_t* __restrict__ le
 // =============================================================================================
 // (pose, leaf) blocks
 // =============================================================================================
-__global__ void block_heads_kernel(const uint32_t* __restrict__ leaf_of, const uint32_t* __restrict__ perm,
-                                   const uint32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_pose, int n_seg,
-                                   uint32_t n, uint32_t* __restrict__ flags, int32_t* __restrict__ pose_of_pos) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int32_t p = seg_pose[seg_of_rank(seg_start, n_seg, perm[i])];
-    pose_of_pos[i] = p;
-    bool head = (i == 0);
-    if (!head) {
-        int32_t pp = seg_pose[seg_of_rank(seg_start, n_seg, perm[i - 1])];
-        head = (leaf_of[i] != leaf_of[i - 1]) || (pp != p);
-    }
-    flags[i] = head;
-}
-
-__global__ void block_emit_kernel(const uint32_t* __restrict__ leaf_of, const int32_t* __restrict__ pose_of_pos,
-                                  const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan_ex, uint32_t n,
-                                  uint32_t* __restrict__ blk_of_pos, uint32_t* __restrict__ blk_start,
-                                  uint32_t* __restrict__ blk_leaf, int32_t* __restrict__ blk_pose) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t b = scan_ex[i] + flags[i] - 1u;
-    blk_of_pos[i] = b;
-    if (flags[i]) {
-        blk_start[b] = i;
-        blk_leaf[b] = leaf_of[i];
-        blk_pose[b] = pose_of_pos[i];
-    }
-}
-
 __global__ void block_max_kernel(const uint32_t* __restrict__ blk_start, uint32_t nb, uint32_t* __restrict__ out_max) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t v = (b < nb) ? blk_start[b + 1] - blk_start[b] : 0;

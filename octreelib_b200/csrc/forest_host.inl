@@ -218,46 +218,37 @@ void Forest::build() {
     }
     mort_r.release();
 
-    // cells
-    DevBuf<uint32_t> flags(ctx, n), scan(ctx, n);
+    // K3: cells = runs of equal cell key; (cell, pose) pairs = runs of equal (cell, pose) (octree_manager.py:166-169)
     DevBuf<unsigned long long> d_total(ctx, 1);
+    DevBuf<uint32_t> tile_off;
     {
-        ProfScope ps(ctx, "cells");
-        cell_heads_kernel<<<nblk(n), 256, 0, ctx.stream>>>(keys0.get(), n, kp.pose_bits, flags.get());
-        OL_CHECK_LAUNCH();
-    }
-    exclusive_scan_u32(ctx, flags.get(), scan.get(), n, d_total.get());
-    C = (uint32_t)read_u64(d_total.get());
-    cellidx0.reset(ctx, n);
-    cell_key.reset(ctx, C);
-    cell_start0.reset(ctx, (size_t)C + 1);
-    {
-        ProfScope ps(ctx, "cells");
-        cell_emit_kernel<<<nblk(n), 256, 0, ctx.stream>>>(keys0.get(), flags.get(), scan.get(), n, kp.pose_bits, cellidx0.get(),
-                                                          cell_key.get(), cell_start0.get());
-        OL_CHECK_LAUNCH();
+        const CellKeyFn key{keys0.get(), kp.pose_bits};
+        {
+            ProfScope ps(ctx, "cells", (double)n);
+            segment_runs_count(ctx, key, n, tile_off, d_total.get());
+        }
+        C = (uint32_t)read_u64(d_total.get());
+        cellidx0.reset(ctx, n);
+        cell_key.reset(ctx, C);
+        cell_start0.reset(ctx, (size_t)C + 1);
+        ProfScope ps(ctx, "cells", (double)n);
+        segment_runs_emit(ctx, key, CellEmitFn{cell_key.get(), cell_start0.get()}, n, tile_off, cellidx0.get());
     }
     OL_CUDA(cudaMemcpyAsync(cell_start0.get() + C, &n, 4, cudaMemcpyHostToDevice, ctx.stream));
     keys0.release();
-
-    // (cell, pose) pairs that own an octree (octree_manager.py:166-169)
-    DevBuf<int32_t> pose_of_pos(ctx, n);
     {
-        ProfScope ps(ctx, "cell_poses");
-        cp_heads_kernel<<<nblk(n), 256, 0, ctx.stream>>>(cellidx0.get(), perm0.get(), d_seg_start.get(), d_seg_pose.get(), S, n,
-                                                         flags.get(), pose_of_pos.get());
-        OL_CHECK_LAUNCH();
-    }
-    exclusive_scan_u32(ctx, flags.get(), scan.get(), n, d_total.get());
-    CP = (uint32_t)read_u64(d_total.get());
-    cp_cell.reset(ctx, CP);
-    cp_pose.reset(ctx, CP);
-    cell_first_pose.reset(ctx, C);
-    {
-        ProfScope ps(ctx, "cell_poses");
-        cp_emit_kernel<<<nblk(n), 256, 0, ctx.stream>>>(cellidx0.get(), pose_of_pos.get(), flags.get(), scan.get(), n,
-                                                        cp_cell.get(), cp_pose.get(), cell_first_pose.get());
-        OL_CHECK_LAUNCH();
+        const GroupPoseKeyFn key{cellidx0.get(), perm0.get(), d_seg_start.get(), d_seg_pose.get(), S};
+        {
+            ProfScope ps(ctx, "cell_poses", (double)n);
+            segment_runs_count(ctx, key, n, tile_off, d_total.get());
+        }
+        CP = (uint32_t)read_u64(d_total.get());
+        cp_cell.reset(ctx, CP);
+        cp_pose.reset(ctx, CP);
+        cell_first_pose.reset(ctx, C);
+        ProfScope ps(ctx, "cell_poses", (double)n);
+        segment_runs_emit(ctx, key, CellPoseEmitFn{cp_cell.get(), cp_pose.get(), cell_first_pose.get(), cellidx0.get()}, n, tile_off,
+                          nullptr);
     }
     check_device_errors();
     built = true;
@@ -618,25 +609,20 @@ void Forest::ensure_blocks() {
         blocks_valid = true;
         return;
     }
-    DevBuf<uint32_t> flags(ctx, A), scan(ctx, A);
-    DevBuf<int32_t> pose_of_pos(ctx, A);
     DevBuf<unsigned long long> d_total(ctx, 1);
+    DevBuf<uint32_t> tile_off;
+    const GroupPoseKeyFn key{leaf_of.get(), perm.get(), d_seg_start.get(), d_seg_pose.get(), S};
     {
-        ProfScope ps(ctx, "blocks");
-        block_heads_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), perm.get(), d_seg_start.get(), d_seg_pose.get(), S, A,
-                                                            flags.get(), pose_of_pos.get());
-        OL_CHECK_LAUNCH();
+        ProfScope ps(ctx, "blocks", (double)A);
+        segment_runs_count(ctx, key, A, tile_off, d_total.get());
     }
-    exclusive_scan_u32(ctx, flags.get(), scan.get(), A, d_total.get());
     NB = (uint32_t)read_u64(d_total.get());
     blk_start.reset(ctx, (size_t)NB + 1);
     blk_leaf.reset(ctx, NB);
     blk_pose.reset(ctx, NB);
     {
-        ProfScope ps(ctx, "blocks");
-        block_emit_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), pose_of_pos.get(), flags.get(), scan.get(), A,
-                                                           blk_of_pos.get(), blk_start.get(), blk_leaf.get(), blk_pose.get());
-        OL_CHECK_LAUNCH();
+        ProfScope ps(ctx, "blocks", (double)A);
+        segment_runs_emit(ctx, key, BlockEmitFn{blk_start.get(), blk_leaf.get(), blk_pose.get()}, A, tile_off, blk_of_pos.get());
     }
     OL_CUDA(cudaMemcpyAsync(blk_start.get() + NB, &A, 4, cudaMemcpyHostToDevice, ctx.stream));
     DevBuf<uint32_t> d_max(ctx, 1);

@@ -278,6 +278,122 @@ inline int radix_sort_pairs(Ctx& c, KeyT* keys0, KeyT* keys1, uint32_t* vals0, u
 }
 
 // =============================================================================================
+// run segmentation: maximal runs of equal key(i) over i in [0, n)  (K3 cells, (cell, pose) pairs, (pose, leaf) blocks)
+//   runs_count_kernel  heads per 2048-element tile
+//   (exclusive scan of the tile counts, total = number of runs)
+//   runs_emit_kernel   recomputes the head flags, ranks them with ballots, writes run_of_pos[i] and calls emit(run, i, key)
+//                      for every head
+// Traffic: the key inputs are read twice and run_of_pos is written once; no flag / scan arrays of length n.
+// KeyFn:  __device__ uint64_t operator()(uint32_t i) const;      EmitFn: __device__ void operator()(uint32_t run, uint32_t i, uint64_t key) const
+// =============================================================================================
+constexpr int RUNS_THREADS = 256;
+constexpr int RUNS_ITEMS = 8;
+constexpr int RUNS_TILE = RUNS_THREADS * RUNS_ITEMS;
+
+template <typename KeyFn>
+__device__ __forceinline__ void runs_warp_flags(const KeyFn& key, uint32_t wbase, uint32_t n, int lane, uint32_t masks[RUNS_ITEMS],
+                                                uint64_t keys[RUNS_ITEMS]) {
+    // the warp walks RUNS_ITEMS x 32 consecutive elements; element (j, lane) = wbase + 32 j + lane
+    uint64_t carry = 0;  // key of the element just before the current group of 32 (valid in every lane)
+    bool have_carry = false;
+    if (wbase > 0 && wbase < n) {
+        carry = key(wbase - 1);
+        have_carry = true;
+    }
+#pragma unroll
+    for (int j = 0; j < RUNS_ITEMS; ++j) {
+        const uint32_t i = wbase + 32 * j + lane;
+        const bool valid = i < n;
+        const uint64_t k = valid ? key(i) : 0ull;
+        uint64_t prev = __shfl_up_sync(0xffffffffu, k, 1);
+        bool has_prev = true;
+        if (lane == 0) {
+            prev = carry;
+            has_prev = have_carry;
+        }
+        const bool head = valid && (!has_prev || prev != k);
+        masks[j] = __ballot_sync(0xffffffffu, head);
+        keys[j] = k;
+        carry = __shfl_sync(0xffffffffu, k, 31);
+        have_carry = true;
+    }
+}
+
+template <typename KeyFn>
+__global__ void __launch_bounds__(RUNS_THREADS) runs_count_kernel(KeyFn key, uint32_t n, uint32_t* __restrict__ tile_counts) {
+    __shared__ uint32_t s_w[RUNS_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t wbase = blockIdx.x * RUNS_TILE + warp * (32 * RUNS_ITEMS);
+    uint32_t masks[RUNS_ITEMS];
+    uint64_t keys[RUNS_ITEMS];
+    runs_warp_flags(key, wbase, n, lane, masks, keys);
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int j = 0; j < RUNS_ITEMS; ++j) cnt += __popc(masks[j]);
+    if (lane == 0) s_w[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < RUNS_THREADS / 32; ++w) t += s_w[w];
+        tile_counts[blockIdx.x] = t;
+    }
+}
+
+template <typename KeyFn, typename EmitFn>
+__global__ void __launch_bounds__(RUNS_THREADS) runs_emit_kernel(KeyFn key, EmitFn emit, uint32_t n,
+                                                                 const uint32_t* __restrict__ tile_offsets,
+                                                                 uint32_t* __restrict__ run_of_pos) {
+    __shared__ uint32_t s_w[RUNS_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t wbase = blockIdx.x * RUNS_TILE + warp * (32 * RUNS_ITEMS);
+    uint32_t masks[RUNS_ITEMS];
+    uint64_t keys[RUNS_ITEMS];
+    runs_warp_flags(key, wbase, n, lane, masks, keys);
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int j = 0; j < RUNS_ITEMS; ++j) cnt += __popc(masks[j]);
+    if (lane == 0) s_w[warp] = cnt;
+    __syncthreads();
+    uint32_t run = tile_offsets[blockIdx.x];  // heads before this warp's first element
+    for (int w = 0; w < warp; ++w) run += s_w[w];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < RUNS_ITEMS; ++j) {
+        const uint32_t i = wbase + 32 * j + lane;
+        const bool head = (masks[j] >> lane) & 1u;
+        const uint32_t mine = run + __popc(masks[j] & lt) + (head ? 1u : 0u) - 1u;  // index of the run element i belongs to
+        if (i < n) {
+            if (run_of_pos) run_of_pos[i] = mine;
+            if (head) emit(mine, i, keys[j]);
+        }
+        run += __popc(masks[j]);
+    }
+}
+
+// number of runs is written to d_total (device, 64-bit); run tables must be sized by the caller after reading it, so
+// the emit pass is a separate call
+template <typename KeyFn>
+inline void segment_runs_count(Ctx& c, KeyFn key, size_t n, DevBuf<uint32_t>& tile_offsets, unsigned long long* d_total) {
+    const size_t tiles = (n + RUNS_TILE - 1) / RUNS_TILE;
+    tile_offsets.reset(c, tiles ? tiles : 1);
+    if (n == 0) {
+        OL_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), c.stream));
+        return;
+    }
+    runs_count_kernel<KeyFn><<<(unsigned)tiles, RUNS_THREADS, 0, c.stream>>>(key, (uint32_t)n, tile_offsets.get());
+    OL_CHECK_LAUNCH();
+    exclusive_scan_u32(c, tile_offsets.get(), tile_offsets.get(), tiles, d_total);
+}
+
+template <typename KeyFn, typename EmitFn>
+inline void segment_runs_emit(Ctx& c, KeyFn key, EmitFn emit, size_t n, const DevBuf<uint32_t>& tile_offsets, uint32_t* run_of_pos) {
+    if (n == 0) return;
+    const size_t tiles = (n + RUNS_TILE - 1) / RUNS_TILE;
+    runs_emit_kernel<KeyFn, EmitFn><<<(unsigned)tiles, RUNS_THREADS, 0, c.stream>>>(key, emit, (uint32_t)n, tile_offsets.get(), run_of_pos);
+    OL_CHECK_LAUNCH();
+}
+
+// =============================================================================================
 // small elementwise helpers
 // =============================================================================================
 static __global__ void iota_kernel(uint32_t* out, uint32_t n, uint32_t first) {
