@@ -352,20 +352,31 @@ __device__ __forceinline__ uint32_t level_digit(uint64_t m, int shift) { return 
 // per-tile histogram of the level digit over positions that belong to splitting leaves
 __global__ void __launch_bounds__(PART_THREADS) part_hist_kernel(const uint32_t* __restrict__ leaf_of,
                                                                   const uint64_t* __restrict__ mort,
-                                                                  const uint32_t* __restrict__ splitf, uint32_t n,
-                                                                  uint32_t num_tiles, int shift,
-                                                                  uint32_t* __restrict__ tile_hist) {
+                                                                  const uint32_t* __restrict__ splitf,
+                                                                  const uint32_t* __restrict__ iidx, uint32_t n,
+                                                                  uint32_t num_tiles, uint32_t n_split, int shift,
+                                                                  uint32_t* __restrict__ tile_hist,
+                                                                  uint32_t* __restrict__ leaf_cnt /*[8][n_split]*/) {
     __shared__ uint32_t h[8];
     if (threadIdx.x < 8) h[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t base = blockIdx.x * PART_TILE;
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int j = 0; j < PART_ITEMS; ++j) {
         uint32_t i = base + j * PART_THREADS + threadIdx.x;
-        uint32_t g = 0xffffffffu;
-        if (i < n && splitf[leaf_of[i]]) g = level_digit(mort[i], shift);
-        uint32_t peers = __match_any_sync(0xffffffffu, g);
-        if (g != 0xffffffffu && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&h[g], __popc(peers));
+        uint32_t key = 0xffffffffu;  // (split-leaf index << 3) | digit
+        if (i < n) {
+            const uint32_t k = leaf_of[i];
+            if (splitf[k]) key = (iidx[k] << 3) | level_digit(mort[i], shift);
+        }
+        // positions are leaf-ordered, so a warp holds few distinct (leaf, digit) pairs: one atomic per pair
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        if (key != 0xffffffffu && lane == (__ffs(peers) - 1)) {
+            const uint32_t c = (uint32_t)__popc(peers);
+            atomicAdd(&h[key & 7u], c);
+            atomicAdd(&leaf_cnt[(size_t)(key & 7u) * n_split + (key >> 3)], c);
+        }
     }
     __syncthreads();
     if (threadIdx.x < 8) tile_hist[(size_t)threadIdx.x * num_tiles + blockIdx.x] = h[threadIdx.x];
@@ -385,29 +396,42 @@ __device__ __forceinline__ void packed_inc(Packed8& p, uint32_t g) {
         p.hi += one;
 }
 
-// stable rank of every position of a splitting leaf among the positions with the same digit
-// (global running count S_g), plus S at the first / one-past-last position of every splitting leaf
-__global__ void __launch_bounds__(PART_THREADS) part_rank_kernel(
-    const uint32_t* __restrict__ leaf_of, const uint64_t* __restrict__ mort, const uint32_t* __restrict__ splitf,
-    const uint32_t* __restrict__ iidx, const uint32_t* __restrict__ lstart, const uint32_t* __restrict__ tile_off,
-    uint32_t n, uint32_t num_tiles, int shift, uint32_t* __restrict__ rank, uint32_t* __restrict__ Sbeg,
-    uint32_t* __restrict__ Send) {
+// Stable 8-way partition of every splitting leaf's range in ONE pass (everything else is copied through).
+// With S_g(i) = number of active positions before i whose digit is g (a global running count: the tile's offset from
+// the scanned tile histograms plus a running count inside the tile), the destination of an active position i of leaf k
+// (split index s) with digit g is
+//     lstart[k] + sum_{c<g} leaf_cnt[c][s] + (S_g(i) - S_g(first position of k)),
+// and S_g(first position of k) is the exclusive scan over the split leaves of leaf_cnt[g][.] (leaf_beg) because split
+// leaves appear in position order.  Blocked arrangement (8 consecutive positions per thread): measured 4.2 ms for the
+// three levels of the 100 M workload against 7.3 ms for a warp-striped variant with match-based ranking.
+__global__ void __launch_bounds__(PART_THREADS) part_move_kernel(
+    const uint32_t* __restrict__ leaf_of, const uint64_t* __restrict__ mort, const uint32_t* __restrict__ perm,
+    const uint32_t* __restrict__ splitf, const uint32_t* __restrict__ iidx, const uint32_t* __restrict__ newidx,
+    const uint32_t* __restrict__ lstart, const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ leaf_cnt,
+    const uint32_t* __restrict__ leaf_beg, uint32_t n, uint32_t num_tiles, uint32_t n_split, int shift, int level,
+    uint32_t* __restrict__ leaf_out, uint64_t* __restrict__ mort_out, uint32_t* __restrict__ perm_out,
+    // for the out-of-node re-check
+    const double* __restrict__ xyz, const uint32_t* __restrict__ lcell, const uint64_t* __restrict__ cell_key, KeyParams kp,
+    uint32_t* __restrict__ err) {
     __shared__ unsigned long long wlo[8], whi[8];
     __shared__ uint32_t G[8];
     if (threadIdx.x < 8) G[threadIdx.x] = tile_off[(size_t)threadIdx.x * num_tiles + blockIdx.x];
     const uint32_t first = blockIdx.x * PART_TILE + threadIdx.x * PART_ITEMS;
     uint32_t leaf[PART_ITEMS];
     uint32_t g[PART_ITEMS];
+    uint64_t m[PART_ITEMS];
     Packed8 cnt{0ull, 0ull};
 #pragma unroll
     for (int j = 0; j < PART_ITEMS; ++j) {
         uint32_t i = first + j;
         g[j] = 8u;
         leaf[j] = 0;
+        m[j] = 0;
         if (i < n) {
             leaf[j] = leaf_of[i];
+            m[j] = mort[i];
             if (splitf[leaf[j]]) {
-                g[j] = level_digit(mort[i], shift);
+                g[j] = level_digit(m[j], shift);
                 packed_inc(cnt, g[j]);
             }
         }
@@ -437,68 +461,40 @@ __global__ void __launch_bounds__(PART_THREADS) part_rank_kernel(
     Packed8 run{blo + ilo - cnt.lo, bhi + ihi - cnt.hi};
 #pragma unroll
     for (int j = 0; j < PART_ITEMS; ++j) {
-        uint32_t i = first + j;
+        const uint32_t i = first + j;
+        if (i >= n) break;
+        const uint32_t k = leaf[j];
+        uint32_t dst = i, nl = newidx[k];
         if (g[j] < 8u) {
-            const uint32_t k = leaf[j];
-            if (i == lstart[k]) {
-                const uint32_t s = iidx[k];
-#pragma unroll
-                for (uint32_t c = 0; c < 8; ++c) Sbeg[(size_t)s * 8 + c] = G[c] + packed_get(run, c);
-            }
-            rank[i] = G[g[j]] + packed_get(run, g[j]);
+            const uint32_t s = iidx[k];
+            const uint32_t S = G[g[j]] + packed_get(run, g[j]);
             packed_inc(run, g[j]);
-            if (i + 1 == lstart[k + 1]) {
-                const uint32_t s = iidx[k];
-#pragma unroll
-                for (uint32_t c = 0; c < 8; ++c) Send[(size_t)s * 8 + c] = G[c] + packed_get(run, c);
+            uint32_t base = lstart[k];
+            for (uint32_t c = 0; c < g[j]; ++c) base += leaf_cnt[(size_t)c * n_split + s];
+            dst = base + (S - leaf_beg[(size_t)g[j] * n_split + s]);
+            nl += g[j];
+            if (m[j] & MORTON_BAD_BIT) {
+                // the point left its node at some level: an error only if that level is being split
+                const uint32_t r = perm[i];
+                long long q[3] = {0, 0, 0};
+                if (!kp.single_cell) unpack_cell(kp, cell_key[lcell[k]], q);
+                double p[3] = {xyz[(size_t)r * 3], xyz[(size_t)r * 3 + 1], xyz[(size_t)r * 3 + 2]};
+                double c0[3];
+                for (int a = 0; a < 3; ++a) c0[a] = cell_corner_coord(q[a], kp.corner[a], kp.edge, kp.single_cell);
+                int bad;
+                point_morton(p, c0, kp.edge, kp.depth, &bad);
+                if (bad <= level) atomicOr(err, (uint32_t)DEVERR_OUT_OF_NODE);
             }
         }
+        leaf_out[dst] = nl;
+        mort_out[dst] = m[j];
+        perm_out[dst] = perm[i];
     }
-}
-
-// stable 8-way partition of every splitting leaf's range; everything else is copied through
-__global__ void __launch_bounds__(256) part_scatter_kernel(
-    const uint32_t* __restrict__ leaf_of, const uint64_t* __restrict__ mort, const uint32_t* __restrict__ perm,
-    const uint32_t* __restrict__ splitf, const uint32_t* __restrict__ iidx, const uint32_t* __restrict__ newidx,
-    const uint32_t* __restrict__ lstart, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ Sbeg,
-    const uint32_t* __restrict__ Send, uint32_t n, int shift, int level, uint32_t* __restrict__ leaf_out,
-    uint64_t* __restrict__ mort_out, uint32_t* __restrict__ perm_out,
-    // for the out-of-node re-check
-    const double* __restrict__ xyz, const uint32_t* __restrict__ lcell, const uint64_t* __restrict__ cell_key,
-    KeyParams kp, uint32_t* __restrict__ err) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t k = leaf_of[i];
-    const uint64_t m = mort[i];
-    const uint32_t r = perm[i];
-    uint32_t dst = i, nl = newidx[k];
-    if (splitf[k]) {
-        const uint32_t g = level_digit(m, shift);
-        const uint32_t s = iidx[k];
-        uint32_t base = lstart[k];
-        for (uint32_t c = 0; c < g; ++c) base += Send[(size_t)s * 8 + c] - Sbeg[(size_t)s * 8 + c];
-        dst = base + (rank[i] - Sbeg[(size_t)s * 8 + g]);
-        nl += g;
-        if (m & MORTON_BAD_BIT) {
-            // the point left its node at some level: an error only if that level is being split
-            long long q[3] = {0, 0, 0};
-            if (!kp.single_cell) unpack_cell(kp, cell_key[lcell[k]], q);
-            double p[3] = {xyz[(size_t)r * 3], xyz[(size_t)r * 3 + 1], xyz[(size_t)r * 3 + 2]};
-            double c0[3];
-            for (int a = 0; a < 3; ++a) c0[a] = cell_corner_coord(q[a], kp.corner[a], kp.edge, kp.single_cell);
-            int bad;
-            point_morton(p, c0, kp.edge, kp.depth, &bad);
-            if (bad <= level) atomicOr(err, (uint32_t)DEVERR_OUT_OF_NODE);
-        }
-    }
-    leaf_out[dst] = nl;
-    mort_out[dst] = m;
-    perm_out[dst] = r;
 }
 
 __global__ void expand_leaves_kernel(uint32_t L, uint32_t A, uint32_t I_old, const uint32_t* __restrict__ splitf,
                                      const uint32_t* __restrict__ iidx, const uint32_t* __restrict__ newidx,
-                                     const uint32_t* __restrict__ Sbeg, const uint32_t* __restrict__ Send,
+                                     const uint32_t* __restrict__ leaf_cnt, uint32_t n_split,
                                      const uint32_t* __restrict__ lstart, const uint32_t* __restrict__ lcell,
                                      const int32_t* __restrict__ lparent, const uint64_t* __restrict__ lpath,
                                      const uint8_t* __restrict__ ldepth, const uint8_t* __restrict__ lchild,
@@ -528,7 +524,7 @@ __global__ void expand_leaves_kernel(uint32_t L, uint32_t A, uint32_t I_old, con
         for (uint32_t c = 0; c < 8; ++c) {
             const uint32_t j = j0 + c;
             lstart_n[j] = run;
-            run += Send[(size_t)s * 8 + c] - Sbeg[(size_t)s * 8 + c];
+            run += leaf_cnt[(size_t)c * n_split + s];
             lcell_n[j] = lcell[k];
             lparent_n[j] = (int32_t)id;
             lpath_n[j] = (lpath[k] << 3) | (uint64_t)c;

@@ -422,7 +422,7 @@ void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t ta
     const int S = (int)seg_pose.size();
     DevBuf<unsigned long long> d_tot(ctx, 2);
     const uint32_t tiles = (A + PART_TILE - 1) / PART_TILE;
-    DevBuf<uint32_t> tile_hist(ctx, (size_t)8 * tiles), rank(ctx, A);
+    DevBuf<uint32_t> tile_hist(ctx, (size_t)8 * tiles);
     DevBuf<uint32_t> perm_b(ctx, A), leaf_b(ctx, A);
     DevBuf<uint64_t> mort_b(ctx, A);
     for (int level = 0;; ++level) {
@@ -457,29 +457,23 @@ void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t ta
         depth_reached = level + 1;
         if (level >= kp.depth) extend_morton();
         const int shift = 3 * (kp.depth - 1 - level);
-        DevBuf<uint32_t> Sbeg(ctx, (size_t)n_split * 8), Send(ctx, (size_t)n_split * 8);
-        Sbeg.zero();
-        Send.zero();
+        DevBuf<uint32_t> leaf_cnt(ctx, (size_t)n_split * 8), leaf_beg(ctx, (size_t)n_split * 8);
+        leaf_cnt.zero();
         {
             ProfScope ps(ctx, "part_hist", (double)A);
-            part_hist_kernel<<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), mort.get(), splitf.get(), A, tiles, shift,
-                                                                     tile_hist.get());
+            part_hist_kernel<<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), mort.get(), splitf.get(), iidx.get(), A, tiles,
+                                                                     n_split, shift, tile_hist.get(), leaf_cnt.get());
             OL_CHECK_LAUNCH();
         }
         exclusive_scan_u32(ctx, tile_hist.get(), tile_hist.get(), (size_t)8 * tiles, nullptr);
+        exclusive_scan_u32(ctx, leaf_cnt.get(), leaf_beg.get(), (size_t)8 * n_split, nullptr);
         {
-            ProfScope ps(ctx, "part_rank", (double)A);
-            part_rank_kernel<<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), mort.get(), splitf.get(), iidx.get(),
-                                                                     lstart.get(), tile_hist.get(), A, tiles, shift, rank.get(),
-                                                                     Sbeg.get(), Send.get());
-            OL_CHECK_LAUNCH();
-        }
-        {
-            ProfScope ps(ctx, "part_scatter", (double)A);
-            part_scatter_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), mort.get(), perm.get(), splitf.get(), iidx.get(),
-                                                                 newidx.get(), lstart.get(), rank.get(), Sbeg.get(), Send.get(), A,
-                                                                 shift, level, leaf_b.get(), mort_b.get(), perm_b.get(), P64.get(),
-                                                                 lcell.get(), cell_key.get(), kp, d_err.get());
+            ProfScope ps(ctx, "part_move", (double)A);
+            part_move_kernel<<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), mort.get(), perm.get(), splitf.get(), iidx.get(),
+                                                                     newidx.get(), lstart.get(), tile_hist.get(), leaf_cnt.get(),
+                                                                     leaf_beg.get(), A, tiles, n_split, shift, level, leaf_b.get(),
+                                                                     mort_b.get(), perm_b.get(), P64.get(), lcell.get(), cell_key.get(),
+                                                                     kp, d_err.get());
             OL_CHECK_LAUNCH();
         }
         // new leaf / internal tables
@@ -495,8 +489,8 @@ void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t ta
         d2d(ctx, idepth_n.get(), idepth.get(), I);
         {
             ProfScope ps(ctx, "part_expand");
-            expand_leaves_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, A, I, splitf.get(), iidx.get(), newidx.get(), Sbeg.get(),
-                                                                  Send.get(), lstart.get(), lcell.get(), lparent.get(), lpath.get(),
+            expand_leaves_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, A, I, splitf.get(), iidx.get(), newidx.get(), leaf_cnt.get(),
+                                                                  n_split, lstart.get(), lcell.get(), lparent.get(), lpath.get(),
                                                                   ldepth.get(), lchild.get(), L_new, lstart_n.get(), lcell_n.get(),
                                                                   lparent_n.get(), lpath_n.get(), ldepth_n.get(), lchild_n.get(),
                                                                   istart_n.get(), icell_n.get(), idepth_n.get(), ipath_n.get());
