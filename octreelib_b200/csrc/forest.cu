@@ -63,58 +63,33 @@ __device__ __forceinline__ void unpack_cell(const KeyParams& kp, uint64_t ckey, 
 // =============================================================================================
 // K0: bounding box of a newly inserted cloud (ordered-int atomics), non-finite check
 // =============================================================================================
-__global__ void __launch_bounds__(256) bbox_kernel(const double* __restrict__ xyz, size_t n, long long* __restrict__ bbox,
-                                                   uint32_t* __restrict__ err) {
-    long long mn[3] = {LLONG_MAX, LLONG_MAX, LLONG_MAX}, mx[3] = {LLONG_MIN, LLONG_MIN, LLONG_MIN};
+// Flat, fully coalesced walk over the 3n doubles.  192 threads per block (a multiple of 3) make the grid stride a
+// multiple of 3 as well, so every thread only ever sees ONE axis (tid % 3) and keeps a single min / max pair.
+constexpr int BBOX_THREADS = 192;
+__global__ void __launch_bounds__(BBOX_THREADS) bbox_kernel(const double* __restrict__ xyz, size_t n, long long* __restrict__ bbox,
+                                                            uint32_t* __restrict__ err) {
+    long long mn = LLONG_MAX, mx = LLONG_MIN;
     bool bad = false;
-    // flat, fully coalesced walk over the 3n doubles; the axis of element e is e mod 3
-    const size_t total = n * 3, stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const size_t total = n * 3, stride = (size_t)gridDim.x * BBOX_THREADS;
+    for (size_t e = (size_t)blockIdx.x * BBOX_THREADS + threadIdx.x; e < total; e += stride) {
         const double v = xyz[e];
-        const int a = (int)(e % 3);
         if (!isfinite(v)) bad = true;
         const long long k = double_to_ordered(v);
-        if (a == 0) {
-            mn[0] = k < mn[0] ? k : mn[0];
-            mx[0] = k > mx[0] ? k : mx[0];
-        } else if (a == 1) {
-            mn[1] = k < mn[1] ? k : mn[1];
-            mx[1] = k > mx[1] ? k : mx[1];
-        } else {
-            mn[2] = k < mn[2] ? k : mn[2];
-            mx[2] = k > mx[2] ? k : mx[2];
-        }
+        mn = k < mn ? k : mn;
+        mx = k > mx ? k : mx;
     }
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            long long t = __shfl_xor_sync(0xffffffffu, mn[a], o);
-            mn[a] = t < mn[a] ? t : mn[a];
-            t = __shfl_xor_sync(0xffffffffu, mx[a], o);
-            mx[a] = t > mx[a] ? t : mx[a];
-        }
-    }
-    // block-level reduction first: one atomic per block and bound instead of one per warp
-    __shared__ long long s_mn[8][3], s_mx[8][3];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            s_mn[warp][a] = mn[a];
-            s_mx[warp][a] = mx[a];
-        }
-    }
+    __shared__ long long s_mn[BBOX_THREADS], s_mx[BBOX_THREADS];
+    s_mn[threadIdx.x] = mn;
+    s_mx[threadIdx.x] = mx;
     __syncthreads();
-    if (threadIdx.x < 3) {
-        const int a = threadIdx.x;
-        long long lo = s_mn[0][a], hi = s_mx[0][a];
-        for (int w = 1; w < 8; ++w) {
-            lo = s_mn[w][a] < lo ? s_mn[w][a] : lo;
-            hi = s_mx[w][a] > hi ? s_mx[w][a] : hi;
+    if (threadIdx.x < 3) {  // axis a = threadIdx.x: combine the threads a, a + 3, a + 6, ...
+        long long lo = LLONG_MAX, hi = LLONG_MIN;
+        for (int t = threadIdx.x; t < BBOX_THREADS; t += 3) {
+            lo = s_mn[t] < lo ? s_mn[t] : lo;
+            hi = s_mx[t] > hi ? s_mx[t] : hi;
         }
-        if (lo != LLONG_MAX) atomicMin(&bbox[a], lo);
-        if (hi != LLONG_MIN) atomicMax(&bbox[3 + a], hi);
+        if (lo != LLONG_MAX) atomicMin(&bbox[threadIdx.x], lo);
+        if (hi != LLONG_MIN) atomicMax(&bbox[3 + threadIdx.x], hi);
     }
     if (bad) atomicOr(err, (uint32_t)DEVERR_NONFINITE);
 }

@@ -138,9 +138,9 @@ void Forest::build() {
     if (built) return;
     if (bbox_done < N) {  // K0 over everything inserted since the last build
         const size_t m = N - bbox_done;
-        unsigned g = std::min<unsigned>(nblk(m), (unsigned)ctx.num_sms * 8);
+        unsigned g = std::min<unsigned>(nblk(m * 3, BBOX_THREADS), (unsigned)ctx.num_sms * 10);
         ProfScope ps(ctx, "bbox", (double)m);
-        bbox_kernel<<<g, 256, 0, ctx.stream>>>(P64.get() + bbox_done * 3, m, d_bbox.get(), d_err.get());
+        bbox_kernel<<<g, BBOX_THREADS, 0, ctx.stream>>>(P64.get() + bbox_done * 3, m, d_bbox.get(), d_err.get());
         OL_CHECK_LAUNCH();
         bbox_done = N;
     }
