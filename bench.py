@@ -15,8 +15,13 @@ subdivided and segmented locally.
 `value`  : device-resident inputs (points already in HBM when the timed region starts).
 `e2e`    : the same step through the public API with HOST (pinned) input buffers and the result
            tables (leaf table + per-block plane table) read back to the host inside the timed region.
-Timing   : CUDA events on the work stream, max over ranks, barrier + synchronize on both sides.
-           The inputs (2.4 GB) are far larger than L2 (126 MB), so no extra L2 flush is needed.
+Timing   : CUDA events on the work stream, max over ranks, barrier + synchronize on both sides, W >= 3 warm-up
+           steps.  The inputs (2.4 GB) are far larger than L2 (126 MB), so no extra L2 flush is needed.
+`roofline`: the dominant HBM-bound kernel (one onesweep radix digit pass over all points), timed live by the
+           library's CUDA-event stage profiler in a separate profiled step; `stages` lists every stage the same way,
+           `roofline_ransac` the FP64-bound RANSAC kernel.  Peak = MEASURED_PEAKS.json (HBM copy GB/s).
+`clocks` : NVML samples taken by the benchmark thread inside every warm-up and timed step (see ClockSampler).
+`cpu_baseline` / `--impl reference`: the CPU oracle port (oracle/) on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -38,7 +43,6 @@ WORKLOADS = {
     "c2_lidar_10x120k": dict(kind="lidar10", points=1_200_000, edge=1.0, max_points=100, threshold=0.02),
 }
 H, K = 1024, 6
-_LAST_STEP_END = 0.0
 POINTS_PER_POSE_EST = 118_000
 
 
@@ -234,8 +238,6 @@ def run_step(clouds, numbers, n_poses_total, w, world, profile=False, read_table
     from octreelib_b200.grid import Grid, GridConfig
 
     np.random.seed(0)
-    dbg = os.environ.get("OL_TIMING") == "host"
-    t_dbg = [time.perf_counter()]
     if world > 1:
         from octreelib_b200.parallel import ShardedGrid
 
@@ -247,17 +249,13 @@ def run_step(clouds, numbers, n_poses_total, w, world, profile=False, read_table
         forest.profile(True)
     for number, cloud in zip(numbers, clouds):
         grid.insert_points(number, cloud)
-    t_dbg.append(time.perf_counter())
     if world > 1:
         grid.exchange()
-    t_dbg.append(time.perf_counter())
     grid.subdivide([MaxPoints(w["max_points"])])
     if sampler is not None:
         sampler.sample()
-    t_dbg.append(time.perf_counter())
     grid.map_leaf_points_cuda_ransac(poses_per_batch=10, threshold=w["threshold"], hypotheses_number=H,
                                      initial_points_number=K)
-    t_dbg.append(time.perf_counter())
     if sampler is not None:
         sampler.sample()  # the mask compaction kernels of this step are still in flight
     d2h = 0
@@ -267,13 +265,6 @@ def run_step(clouds, numbers, n_poses_total, w, world, profile=False, read_table
         d2h = sum(a.nbytes for a in planes.values()) + sum(a.nbytes for a in leaves.values())
     stats = forest.stats(light=True)  # waits for the step; the step's scalar results (alive points, leaves, ...)
     prof = forest.profile_read() if profile else None
-    if dbg and int(os.environ.get("RANK", "0")) == 0:
-        t_dbg.append(time.perf_counter())
-        names = ["insert", "exchange", "subdivide", "ransac", "stats"]
-        global _LAST_STEP_END
-        gap = 1e3 * (t_dbg[0] - _LAST_STEP_END) if _LAST_STEP_END else 0.0
-        _LAST_STEP_END = time.perf_counter()
-        print(f"[step host ms] gap-before {gap:.2f}, " + ", ".join(f"{n} {1e3 * (b - a):.2f}" for n, a, b in zip(names, t_dbg, t_dbg[1:])), flush=True)
     return grid, stats, prof, d2h
 
 
@@ -399,7 +390,7 @@ def main():
 
     # clock samples are taken inside the warm-up and the timed steps (same load); see ClockSampler
     sampler = ClockSampler(local)
-    if rank == 0 and os.environ.get("OL_NO_SAMPLER") != "1":  # diagnostic switch; the default run always samples
+    if rank == 0:
         sampler.start()
     smp = sampler if rank == 0 else None
     # warm-up (also warms torch's caching allocator so the timed steps do not call cudaMalloc)

@@ -623,7 +623,7 @@ void Forest::ensure_blocks() {
     d_max.zero();
     {
         ProfScope ps(ctx, "blocks");
-        block_max_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(blk_start.get(), NB, d_max.get());
+        block_max_kernel<<<std::min<unsigned>(nblk(NB), (unsigned)ctx.num_sms * 8), 256, 0, ctx.stream>>>(blk_start.get(), NB, d_max.get());
         OL_CHECK_LAUNCH();
     }
     max_block = read_u32(d_max.get());

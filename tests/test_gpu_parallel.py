@@ -127,3 +127,42 @@ def test_append_to_existing_pose_in_a_manager():
             assert (np.asarray(g.corner_min, dtype=float) == np.asarray(w.corner, dtype=float)).all()
             assert (g.get_points() == w.points).all()
         assert mp.n_nodes(p) == og.n_nodes(p) and mp.n_points(p) == og.n_points(p)
+
+
+def test_fused_route_to_peers_matches_partition():
+    """ol_route_plan + ol_route_to_peers (the fused gather + all-to-all kernel): with the 'peer' receive buffers
+    emulated by separate buffers on one device, what lands in them equals the owner-grouped staging copy of
+    ol_partition_by_owner, at the row offsets the count cube prescribes."""
+    import torch
+
+    lib = N.lib()
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(5)
+    clouds = [(rng.random((2500 + 300 * k, 3)) * 30 - 15).astype(np.float32).astype(np.float64) for k in range(4)]
+    world = 4
+    want_send, counts = _partition(clouds, 1.0, world)
+    local = torch.from_numpy(np.vstack(clouds)).to(dev)
+    n = len(local)
+    sizes = np.array([len(c) for c in clouds], dtype=np.int64)
+    perm = torch.empty(n, dtype=torch.int32, device=dev)
+    counts2 = np.zeros_like(counts)
+    alloc = TorchAllocator(dev)
+    corner = (C.c_double * 3)(0.0, 0.0, 0.0)
+    stream = torch.cuda.current_stream(dev)
+    N.check(lib.ol_route_plan(C.c_void_p(stream.cuda_stream), C.c_void_p(local.data_ptr()), n, sizes.ctypes.data_as(C.c_void_p),
+                              len(sizes), 1.0, C.byref(corner), world, C.c_void_p(perm.data_ptr()),
+                              counts2.ctypes.data_as(C.c_void_p), alloc.alloc_cb, alloc.free_cb, None))
+    assert (counts2 == counts).all()
+    per_owner = counts.sum(axis=1)
+    owner_first = np.concatenate([[0], np.cumsum(per_owner)]).astype(np.int64)
+    base = np.array([7, 0, 3, 11], dtype=np.int64)  # as if lower source ranks had already claimed these rows
+    bufs = [torch.full((int(per_owner[o] + base[o]) * 3 + 3,), -1.0, dtype=torch.float64, device=dev) for o in range(world)]
+    ptrs = (C.c_void_p * world)(*[b.data_ptr() for b in bufs])
+    N.check(lib.ol_route_to_peers(C.c_void_p(stream.cuda_stream), C.c_void_p(local.data_ptr()), C.c_void_p(perm.data_ptr()), n, world,
+                                  owner_first.ctypes.data_as(C.c_void_p), ptrs, base.ctypes.data_as(C.c_void_p)))
+    torch.cuda.synchronize()
+    for o in range(world):
+        got = bufs[o].cpu().numpy()
+        lo, hi = int(base[o]) * 3, int(base[o] + per_owner[o]) * 3
+        assert (got[:lo] == -1.0).all() and (got[hi:] == -1.0).all(), "wrote outside the assigned rows"
+        assert (got[lo:hi].reshape(-1, 3) == want_send[owner_first[o]:owner_first[o + 1]]).all()
