@@ -312,7 +312,7 @@ int ol_ransac_evaluate(void* stream, const double* points_dev, int64_t n, const 
     DevBuf<uint32_t> work(c, n_work);
     work_emit2_kernel<<<g, 256, 0, c.stream>>>(nb, wflags.get(), wscan.get(), work.get());
     OL_CHECK_LAUNCH();
-    launch_ransac(c, points_dev, n, starts.get(), block_sizes_dev, ref.get(), work.get(), n_work, mx, table_dev, H, K, threshold,
+    launch_ransac(c, points_dev, n, starts.get(), block_sizes_dev, ref.get(), work.get(), nullptr, n_work, mx, table_dev, H, K, threshold,
                   mask_dev, plane_dev, best_dev, best_count_dev, flags);
     uint32_t herr = 0;
     OL_CUDA(cudaMemcpyAsync(&herr, err.get(), 4, cudaMemcpyDeviceToHost, c.stream));

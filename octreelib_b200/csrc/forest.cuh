@@ -157,8 +157,8 @@ struct Forest {
 
 // ransac.cu
 void launch_ransac(Ctx& c, const double* points, int64_t n_points, const uint32_t* blk_phys_start,
-                   const int32_t* blk_size, const long long* blk_ref_start, const uint32_t* work_list, uint32_t n_work,
-                   uint32_t max_block, const double* table, int H, int K, double threshold, uint8_t* mask, float* plane,
+                   const int32_t* blk_size, const long long* blk_ref_start, const uint32_t* work_list, const uint32_t* pk_start,
+                   uint32_t n_work, uint32_t max_block, const double* table, int H, int K, double threshold, uint8_t* mask, float* plane,
                    int32_t* best, int32_t* best_count, uint32_t flags);
 
 void ransac_stats_read(unsigned long long out[8], bool reset);

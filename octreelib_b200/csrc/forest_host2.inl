@@ -56,14 +56,30 @@ __global__ void work_emit_kernel(uint32_t nb, const uint32_t* __restrict__ flags
     if (b < nb && flags[b]) work[scan_ex[b]] = b;
 }
 
-__global__ void gather_points_kernel(uint32_t n, const double* __restrict__ xyz, const uint32_t* __restrict__ perm,
-                                     double* __restrict__ out) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const size_t r = perm[i];
-    out[(size_t)i * 3 + 0] = xyz[r * 3 + 0];
-    out[(size_t)i * 3 + 1] = xyz[r * 3 + 1];
-    out[(size_t)i * 3 + 2] = xyz[r * 3 + 2];
+// sizes of the fitted blocks (work items), for the packed layout of their points
+__global__ void work_sizes_kernel(uint32_t n_work, const uint32_t* __restrict__ work, const int32_t* __restrict__ blk_size,
+                                  uint32_t* __restrict__ sizes) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < n_work) sizes[w] = (uint32_t)blk_size[work[w]];
+}
+
+// K5b: gather ONLY the points of the fitted blocks, block after block, so that every block is one contiguous float64
+// run for the TMA staging (most (pose, leaf) blocks of a LiDAR map are smaller than K and never reach the kernel).
+// One warp per work item; a flat thread-per-double copy inside it.
+__global__ void __launch_bounds__(256) gather_blocks_kernel(uint32_t n_work, const uint32_t* __restrict__ work,
+                                                            const uint32_t* __restrict__ blk_start, const int32_t* __restrict__ blk_size,
+                                                            const uint32_t* __restrict__ pk_start, const double* __restrict__ xyz,
+                                                            const uint32_t* __restrict__ perm, double* __restrict__ out) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_work) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t b = work[w];
+    const uint32_t src0 = blk_start[b], dst0 = pk_start[w];
+    const uint32_t n3 = (uint32_t)blk_size[b] * 3u;
+    for (uint32_t e = lane; e < n3; e += 32) {
+        const uint32_t j = e / 3u, c = e - j * 3u;
+        out[(size_t)dst0 * 3 + e] = xyz[(size_t)perm[src0 + j] * 3 + c];
+    }
 }
 
 __global__ void ransac_snapshot_kernel(uint32_t nb, const uint32_t* __restrict__ ref_order, const int32_t* __restrict__ blk_pose,
@@ -271,11 +287,20 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
         work_emit_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, wflags.get(), wscan.get(), work.get());
         OL_CHECK_LAUNCH();
     }
-    // K5b: gather the points into leaf order so that every block is one contiguous float64 run
-    DevBuf<double> pleaf(ctx, (size_t)A * 3 + 2);
+    // K5b: packed copy of the fitted blocks' points
+    DevBuf<uint32_t> wsizes(ctx, n_work), pk_start(ctx, n_work);
     {
-        ProfScope ps(ctx, "gather_points", (double)A);
-        gather_points_kernel<<<nblk(A), 256, 0, ctx.stream>>>(A, P64.get(), perm.get(), pleaf.get());
+        ProfScope ps(ctx, "ransac_prep");
+        work_sizes_kernel<<<nblk(n_work), 256, 0, ctx.stream>>>(n_work, work.get(), blk_size.get(), wsizes.get());
+        OL_CHECK_LAUNCH();
+    }
+    exclusive_scan_u32(ctx, wsizes.get(), pk_start.get(), n_work, d_total.get());
+    const uint64_t n_packed = read_u64(d_total.get());
+    DevBuf<double> pleaf(ctx, (size_t)n_packed * 3 + 2);
+    if (n_work) {
+        ProfScope ps(ctx, "gather_points", (double)n_packed);
+        gather_blocks_kernel<<<nblk((size_t)n_work * 32), 256, 0, ctx.stream>>>(n_work, work.get(), blk_start.get(), blk_size.get(),
+                                                                                pk_start.get(), P64.get(), perm.get(), pleaf.get());
         OL_CHECK_LAUNCH();
     }
     DevBuf<double> table(ctx, (size_t)H * K);
@@ -288,7 +313,8 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
     OL_CHECK_LAUNCH();
     {
         ProfScope ps(ctx, "ransac_kernel", (double)n_work);
-        launch_ransac(ctx, pleaf.get(), A, blk_start.get(), blk_size.get(), blk_ref_start.get(), work.get(), n_work, max_block,
+        launch_ransac(ctx, pleaf.get(), (int64_t)n_packed, blk_start.get(), blk_size.get(), blk_ref_start.get(), work.get(), pk_start.get(),
+                      n_work, max_block,
                       table.get(), H, K, threshold, mask.get(), plane.get(), best.get(), best_count.get(), flags);
     }
     last_ransac_work = n_work;

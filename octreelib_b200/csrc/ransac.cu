@@ -55,8 +55,12 @@ struct RansacArgs {
     const uint32_t* blk_start;      // physical first point of block b
     const int32_t* blk_size;        // points in block b
     const long long* blk_ref_start; // block_start_indices[b] of the reference's batch layout
-    const uint32_t* work;           // blocks to score (size >= K)
+    const uint32_t* work;           // blocks to score (size >= K), indexed by work item w
     uint32_t n_work;
+    const uint32_t* sub;            // optional: the work items this launch handles (CTA kernel); NULL = all of them
+    uint32_t n_sub;
+    const uint32_t* pk_start;       // optional [n_work]: first point of work item w inside `points` when `points` only
+                                    // holds the fitted blocks back to back; NULL = `points` is indexed by blk_start
     const double* table;            // [H][K] float64 uniform [0,1)
     const uint32_t* r32t;           // [K][H] floor(table * 2^32), transposed (pre-filter)
     const uint32_t* table_ok;       // [1] 1 if every table entry is in [0, 1)
@@ -339,11 +343,12 @@ __global__ void __launch_bounds__(RANSAC_THREADS) ransac_kernel(RansacArgs A) {
     double* s_pts_raw = reinterpret_cast<double*>(smem_raw + RANSAC_SMEM_HEADER + 2 * RANSAC_MAX_H);
     float4* s_q = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(s_pts_raw) + ((((size_t)A.cap * 3 + 2) * 8 + 15) & ~(size_t)15));
 
-    const uint32_t b = A.work[blockIdx.x];
+    const uint32_t w = A.sub ? A.sub[blockIdx.x] : blockIdx.x;
+    const uint32_t b = A.work[w];
     const int n = A.blk_size[b];
     const uint32_t ps = A.blk_start[b];
     const long long rs = A.blk_ref_start[b];
-    const double* gsrc = A.points + (size_t)ps * 3;
+    const double* gsrc = A.points + (size_t)(A.pk_start ? A.pk_start[w] : ps) * 3;
     const double* pts = gsrc;
     const int tid = threadIdx.x;
     const bool staged = (uint32_t)n <= A.cap;
@@ -625,7 +630,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) ransac_small_kernel(RansacAr
         if (n > RS_MAX_POINTS) continue;  // handled by the CTA-per-block kernel
         const uint32_t ps = A.blk_start[b];
         const long long rs = A.blk_ref_start[b];
-        const double* gsrc = A.points + (size_t)ps * 3;
+        const double* gsrc = A.points + (size_t)(A.pk_start ? A.pk_start[w] : ps) * 3;
         const double* pts;
         // ---- stage the block's float64 points (TMA bulk copy, completion on the warp's mbarrier) --
         if (tma) {
@@ -813,11 +818,12 @@ __global__ void ransac_split_kernel(const uint32_t* __restrict__ work, uint32_t 
     uint32_t base = 0;
     if (lane == __ffs(m) - 1) base = atomicAdd(n_large, (uint32_t)__popc(m));
     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (big) large[base + __popc(m & ((1u << lane) - 1u))] = work[i];
+    if (big) large[base + __popc(m & ((1u << lane) - 1u))] = i;  // the work item, not the block id
 }
 
 void launch_ransac(Ctx& c, const double* points, int64_t n_points, const uint32_t* blk_phys_start, const int32_t* blk_size,
-                   const long long* blk_ref_start, const uint32_t* work_list, uint32_t n_work, uint32_t max_block,
+                   const long long* blk_ref_start, const uint32_t* work_list, const uint32_t* pk_start, uint32_t n_work,
+                   uint32_t max_block,
                    const double* table, int H, int K, double threshold, uint8_t* mask, float* plane, int32_t* best,
                    int32_t* best_count, uint32_t flags) {
     if (n_work == 0) return;
@@ -837,6 +843,7 @@ void launch_ransac(Ctx& c, const double* points, int64_t n_points, const uint32_
     a.blk_ref_start = blk_ref_start;
     a.work = work_list;
     a.n_work = n_work;
+    a.pk_start = pk_start;
     a.table = table;
     a.r32t = r32t.get();
     a.table_ok = table_ok.get();
@@ -874,8 +881,8 @@ void launch_ransac(Ctx& c, const double* points, int64_t n_points, const uint32_
         OL_CUDA(cudaMemcpyAsync(&n_large, counters.get() + 1, 4, cudaMemcpyDeviceToHost, c.stream));
         c.sync();
         if (n_large) {
-            a.work = large.get();
-            a.n_work = n_large;
+            a.sub = large.get();
+            a.n_sub = n_large;
             size_t smem = RANSAC_SMEM_HEADER + 2 * RANSAC_MAX_H + ((((size_t)a.cap * 3 + 2) * 8 + 15) & ~(size_t)15) + (size_t)a.cap * 16;
             smem = (smem + 15) & ~(size_t)15;
             OL_CUDA(cudaFuncSetAttribute(ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
