@@ -127,7 +127,18 @@ int Forest::insert(const double* xyz, int64_t n, bool on_device, const int64_t* 
     built = false;
     shaped = false;
     order_valid = blocks_valid = ransac_valid = false;
-    if (!on_device) ctx.sync();  // the caller may reuse / free the host buffer
+    if (!on_device && n > 0) {
+        // Pageable host memory: cudaMemcpyAsync returns once the source has been staged, so the caller may reuse it.
+        // Page-locked (pinned) host memory is read by DMA later: the caller deliberately handed over an asynchronous
+        // buffer and must leave it unchanged until the next call that returns results (documented in Grid.insert_points);
+        // waiting here would serialise 839 copies of a 100 M-point map with ~25 us bubbles each.
+        cudaPointerAttributes attr{};
+        const bool pinned = cudaPointerGetAttributes(&attr, xyz) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        if (!pinned) {
+            cudaGetLastError();  // an unregistered pointer may leave a sticky-free error code behind on old drivers
+            ctx.sync();
+        }
+    }
     return pose_index;
 }
 

@@ -97,6 +97,7 @@ class Forest:
         with self._scope():
             N.check(self._lib.ol_forest_create(C.byref(cfg), C.byref(self._h)))
         self.version = 0  # bumped by every mutating call; hosts cache exports per version
+        self._pending_sources = []  # sources of inserts that may still be in flight
 
     def _scope(self):
         """Context in which torch's current stream is the forest's stream (the allocator callbacks allocate
@@ -128,7 +129,8 @@ class Forest:
         src, n, on_dev, keep = self._as_source(points)
         with self._scope():
             N.check(self._lib.ol_forest_insert(self._h, src, n, on_dev, C.byref(out)))
-        del keep
+        # a pinned host source is read asynchronously (csrc/forest_host.inl): keep it alive until the next synchronising call
+        self._pending_sources.append(keep)
         self.version += 1
         return out.value
 
@@ -140,7 +142,7 @@ class Forest:
         with self._scope():
             N.check(self._lib.ol_forest_insert_segments(self._h, src, n, on_dev, _ptr(ss), _ptr(sp), _ptr(sf), len(ss),
                                                         int(n_poses_total)))
-        del keep
+        self._pending_sources.append(keep)
         self.version += 1
 
     def _as_source(self, points):
@@ -165,6 +167,7 @@ class Forest:
         arr, n = _i32_array(pose_indices)
         with self._scope():
             N.check(self._lib.ol_forest_subdivide(self._h, int(max_points), _ptr(arr), n))
+        self._pending_sources.clear()  # the build read every inserted cloud and synchronised
         self.version += 1
 
     def subdivide_table(self, table: np.ndarray, beyond: bool, pose_indices: Optional[Sequence[int]] = None):
@@ -236,6 +239,7 @@ class Forest:
         fn = self._lib.ol_forest_stats_light if light else self._lib.ol_forest_stats_get
         with self._scope():
             N.check(fn(self._h, C.byref(s)))
+        self._pending_sources.clear()  # both variants synchronise the stream
         return {name: int(getattr(s, name)) for name, _ in s._fields_}
 
     def pose_counts(self, n_poses: int) -> np.ndarray:

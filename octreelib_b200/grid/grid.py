@@ -41,7 +41,11 @@ class Grid(GridBase):
 
     # ---- grid.py:58-109 -------------------------------------------------------------------------
     def insert_points(self, pose_number: int, points: PointCloud):
-        """Insert a pose's cloud: (n, 3) array-like (numpy, or a CUDA torch tensor to skip the upload)."""
+        """Insert a pose's cloud: (n, 3) array-like (numpy, or a CUDA torch tensor to skip the upload).
+
+        Ordinary (pageable) host arrays are consumed before the call returns, like in the reference.  A PAGE-LOCKED
+        (pinned) host array is uploaded asynchronously: leave it unchanged until the next call that returns results
+        (`subdivide`, `n_points`, `get_leaf_points`, ...)."""
         if pose_number in self._host.pose_index:
             raise ValueError(f"Cannot insert points to existing pose {pose_number}")
         self._host.insert(pose_number, points if hasattr(points, "device") else np.asarray(points), allow_append=False)
