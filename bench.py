@@ -403,6 +403,7 @@ def main():
     ms_per_step = ms / args.steps
     value = total / (ms_per_step * 1e-3)
     stats = res[1]
+    del res  # the last timed grid must not stay alive next to the profiled / e2e grids (memory at the 1e9-point scale)
 
     # profiled step (separate from the timed ones): per-stage times for the roofline object
     _, _, prof, _ = run_step(clouds, numbers, P, w, world, profile=True)
@@ -422,7 +423,7 @@ def main():
         e_ms /= args.steps
         e2e = {"value": total / (e_ms * 1e-3), "unit": "points/s", "ms_per_step": e_ms, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": e_res[3]}
-        del host_clouds
+        del host_clouds, e_res
 
     if rank != 0:
         if world > 1:
