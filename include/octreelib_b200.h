@@ -89,7 +89,9 @@ int ol_forest_destroy(ol_forest *f);
 
 /* ---- Grid.insert_points, grid/grid.py:58-109 ------------------------------------------------
  * Appends one pose's cloud ([n][3] float64, host or device memory).  Returns the new pose index.
- * The re-insert ValueError (grid.py:65-66) is raised by the host, which owns pose numbers. */
+ * The re-insert ValueError (grid.py:65-66) is raised by the host, which owns pose numbers.
+ * Device and pageable host sources are consumed before the call returns; a PAGE-LOCKED host source is uploaded
+ * asynchronously and must stay unchanged until the next call that returns results. */
 int ol_forest_insert(ol_forest *f, const double *xyz, int64_t n, int32_t src_on_device, int32_t *out_pose_index);
 
 /* Multi-GPU form: the cloud is a concatenation of `n_segments` runs, run s holding
