@@ -4,13 +4,36 @@ namespace ol {
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-__global__ void block_refkey_kernel(uint32_t nb, const int32_t* __restrict__ blk_pose, const uint32_t* __restrict__ blk_leaf,
-                                    const int32_t* __restrict__ pose_rank, const uint32_t* __restrict__ cache_rank,
-                                    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+// Reference block order = (pose rank, leaf enumeration order).  The block table is ordered (leaf DFS index, pose), and
+// the blocks of one leaf are consecutive, so the leaf part of the order is a permutation of whole leaf segments:
+//   A: per leaf (in enumeration order) the number of its blocks, and the first block of every leaf;
+//   (exclusive scan over the leaves)
+//   B: block b goes to slot off[cache_rank[leaf]] + (b - first block of the leaf); its sort key is only the pose rank.
+// A stable radix sort on the pose-rank bits alone then yields the reference order (2 passes of 32-bit keys for 839
+// poses instead of 5 passes of 64-bit (pose rank, leaf) keys).
+__global__ void leaf_block_count_kernel(uint32_t nb, const uint32_t* __restrict__ blk_leaf, const uint32_t* __restrict__ cache_rank,
+                                        uint32_t* __restrict__ cnt_c, uint32_t* __restrict__ first_b) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
-    keys[b] = ((uint64_t)(uint32_t)pose_rank[blk_pose[b]] << 32) | (uint64_t)cache_rank[blk_leaf[b]];
-    vals[b] = b;
+    const uint32_t leaf = blk_leaf[b];
+    if (b == 0 || blk_leaf[b - 1] != leaf) {
+        first_b[leaf] = b;
+        uint32_t e = b + 1;  // blocks of one leaf = its poses: a short run
+        while (e < nb && blk_leaf[e] == leaf) ++e;
+        cnt_c[cache_rank[leaf]] = e - b;
+    }
+}
+
+__global__ void block_arrange_kernel(uint32_t nb, const uint32_t* __restrict__ blk_leaf, const int32_t* __restrict__ blk_pose,
+                                     const int32_t* __restrict__ pose_rank, const uint32_t* __restrict__ cache_rank,
+                                     const uint32_t* __restrict__ off_c, const uint32_t* __restrict__ first_b,
+                                     uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const uint32_t leaf = blk_leaf[b];
+    const uint32_t dst = off_c[cache_rank[leaf]] + (b - first_b[leaf]);
+    keys[dst] = (uint32_t)pose_rank[blk_pose[b]];
+    vals[dst] = b;
 }
 
 __global__ void block_sizes_ref_kernel(uint32_t nb, const uint32_t* __restrict__ ref_order, const uint32_t* __restrict__ blk_start,
@@ -206,21 +229,22 @@ void Forest::compute_ref_order(const int32_t* pose_rank_host, DevBuf<uint32_t>& 
     ctx.sync();
     ref_order.reset(ctx, NB);
     if (NB == 0) return;
-    DevBuf<uint64_t> k0(ctx, NB), k1(ctx, NB);
-    DevBuf<uint32_t> v0(ctx, NB), v1(ctx, NB);
+    DevBuf<uint32_t> k0(ctx, NB), k1(ctx, NB), v0(ctx, NB), v1(ctx, NB), cnt_c(ctx, L), off_c(ctx, L), first_b(ctx, L);
+    cnt_c.zero();
     {
         ProfScope ps(ctx, "ransac_prep");
-        block_refkey_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_pose.get(), blk_leaf.get(), d_pose_rank.get(),
-                                                              cache_rank.get(), k0.get(), v0.get());
+        leaf_block_count_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_leaf.get(), cache_rank.get(), cnt_c.get(), first_b.get());
         OL_CHECK_LAUNCH();
     }
-    int w = radix_sort_pairs<uint64_t>(ctx, k0.get(), k1.get(), v0.get(), v1.get(), NB, 0, bit_length_u64(L));
-    uint64_t* ka = w ? k1.get() : k0.get();
-    uint64_t* kb = w ? k0.get() : k1.get();
-    uint32_t* va = w ? v1.get() : v0.get();
-    uint32_t* vb = w ? v0.get() : v1.get();
-    int w2 = radix_sort_pairs<uint64_t>(ctx, ka, kb, va, vb, NB, 32, 32 + bit_length_u64((uint64_t)max_rank));
-    d2d(ctx, ref_order.get(), w2 ? vb : va, NB);
+    exclusive_scan_u32(ctx, cnt_c.get(), off_c.get(), L, nullptr);
+    {
+        ProfScope ps(ctx, "ransac_prep");
+        block_arrange_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_leaf.get(), blk_pose.get(), d_pose_rank.get(), cache_rank.get(),
+                                                               off_c.get(), first_b.get(), k0.get(), v0.get());
+        OL_CHECK_LAUNCH();
+    }
+    const int w = radix_sort_pairs<uint32_t>(ctx, k0.get(), k1.get(), v0.get(), v1.get(), NB, 0, bit_length_u64((uint64_t)max_rank));
+    d2d(ctx, ref_order.get(), w ? v1.get() : v0.get(), NB);
 }
 
 // ---------------------------------------------------------------------------------------------
