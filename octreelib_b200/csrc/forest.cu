@@ -3,6 +3,7 @@
 // compaction.  K6 (RANSAC) lives in ransac.cu.
 #include <algorithm>
 #include <climits>
+#include <mutex>
 
 #include "forest.cuh"
 #include "primitives.cuh"

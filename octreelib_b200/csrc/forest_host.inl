@@ -3,6 +3,30 @@ namespace ol {
 
 static inline unsigned nblk(size_t n, int t = 256) { return n ? (unsigned)((n + t - 1) / t) : 1u; }
 
+// Page-locked scratch blocks (256 B) for scalar read-backs.  cudaMallocHost / cudaFreeHost cost 10-200 ms each once
+// gigabytes of device memory are mapped (measured: 24 ms of a 31 ms step went into creating the forest), so the blocks
+// are recycled process-wide instead of being allocated per forest; they are never returned to the driver.
+static std::mutex g_pinned_mutex;
+static std::vector<void*> g_pinned_free;
+static void* pinned_scratch_get() {
+    {
+        std::lock_guard<std::mutex> lock(g_pinned_mutex);
+        if (!g_pinned_free.empty()) {
+            void* p = g_pinned_free.back();
+            g_pinned_free.pop_back();
+            return p;
+        }
+    }
+    void* p = nullptr;
+    OL_CUDA(cudaMallocHost(&p, 256));
+    return p;
+}
+static void pinned_scratch_put(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_pinned_mutex);
+    g_pinned_free.push_back(p);
+}
+
 Forest::Forest(const ol_forest_config& c) : cfg(c) {
     OL_REQUIRE(c.voxel_edge_length > 0 && std::isfinite(c.voxel_edge_length), OL_ERR_INVALID,
                "voxel_edge_length must be a positive finite number");
@@ -23,14 +47,14 @@ Forest::Forest(const ol_forest_config& c) : cfg(c) {
     ctx.prof = &prof;
     long long init[6] = {LLONG_MAX, LLONG_MAX, LLONG_MAX, LLONG_MIN, LLONG_MIN, LLONG_MIN};
     OL_CUDA(cudaMemcpyAsync(d_bbox.get(), init, sizeof(init), cudaMemcpyHostToDevice, ctx.stream));
-    OL_CUDA(cudaMallocHost(&pinned, 256));
+    pinned = pinned_scratch_get();
     ctx.sync();
     seg_start.push_back(0);
 }
 
 Forest::~Forest() {
     cudaStreamSynchronize(ctx.stream);
-    if (pinned) cudaFreeHost(pinned);
+    pinned_scratch_put(pinned);
 }
 
 uint32_t Forest::read_u32(const uint32_t* dptr) {
