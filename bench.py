@@ -398,7 +398,8 @@ def main():
         run_step(clouds, numbers, P, w, world, sampler=smp)
     launches0 = lib.ol_launch_count()
     ms, res = timed(lambda: run_step(clouds, numbers, P, w, world, sampler=smp), args.steps)
-    launches = (lib.ol_launch_count() - launches0) // max(args.steps, 1)
+    launches_total = lib.ol_launch_count() - launches0  # this rank's kernels inside the timed region
+    launches = launches_total // max(args.steps, 1)
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = total / (ms_per_step * 1e-3)
@@ -461,7 +462,7 @@ def main():
                     "note": "achieved = 24 B x pairs per launch / average CUDA-event duration of the launches of one step; "
                             "the step's other kernels are listed under `stages`, the FP64-bound RANSAC kernel under "
                             "`roofline_ransac`"}
-    out = dict(base, value=value, ms_per_step=ms_per_step, dtype="f64", clocks=clocks, gpu_launches=int(launches),
+    out = dict(base, value=value, ms_per_step=ms_per_step, dtype="f64", clocks=clocks, gpu_launches=int(launches_total), gpu_launches_per_step=int(launches),
                stage_ms=stage_ms, stages=stages,
                result={k: stats[k] for k in ("n_points_inserted", "n_points_alive", "n_cells", "n_leaves",
                                              "max_depth_reached", "key_bits", "device_bytes_peak")},
