@@ -61,6 +61,14 @@ __device__ __forceinline__ void unpack_cell(const KeyParams& kp, uint64_t ckey, 
     q[2] = kp.qmin[2] + (long long)key_field(ckey, s2, s1);
 }
 
+// Morton codes are stored as 32-bit words while at most MORTON32_MAX_DEPTH levels are encoded (3 bits per level + the
+// out-of-node flag in the top bit) and as 64-bit words after extend_morton(): the partition kernels move them, so the
+// narrow form saves a quarter of their traffic.
+template <typename MortT>
+struct MortBits {
+    static constexpr MortT bad = (MortT)1 << (sizeof(MortT) * 8 - 1);
+};
+
 // =============================================================================================
 // K0: bounding box of a newly inserted cloud (ordered-int atomics), non-finite check
 // =============================================================================================
@@ -98,10 +106,11 @@ __global__ void __launch_bounds__(BBOX_THREADS) bbox_kernel(const double* __rest
 // =============================================================================================
 // K1: packed cell key + in-cell Morton code per point (one pass over the raw cloud)
 // =============================================================================================
+template <typename MortT>
 __global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ xyz, uint32_t n, KeyParams kp,
                                                      const uint32_t* __restrict__ seg_start,
                                                      const int32_t* __restrict__ seg_pose, int n_seg,
-                                                     uint64_t* __restrict__ keys, uint64_t* __restrict__ mort,
+                                                     uint64_t* __restrict__ keys, MortT* __restrict__ mort,
                                                      uint32_t* __restrict__ err) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
@@ -131,8 +140,8 @@ __global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ 
 #pragma unroll
     for (int a = 0; a < 3; ++a) c[a] = cell_corner_coord(q[a], kp.corner[a], kp.edge, kp.single_cell);
     int bad;
-    uint64_t m = point_morton(p, c, kp.edge, kp.depth, &bad);
-    if (bad < kp.depth) m |= MORTON_BAD_BIT;
+    MortT m = (MortT)point_morton(p, c, kp.edge, kp.depth, &bad);
+    if (bad < kp.depth) m |= MortBits<MortT>::bad;
     keys[r] = key;
     mort[r] = m;
     if (e) atomicOr(err, e);
@@ -140,10 +149,11 @@ __global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ 
 
 // Morton codes of already ordered points at a (deeper) depth: position i holds point perm[i] of cell
 // cell_of[i] (or lcell[cell_of[i]] when lcell != nullptr, i.e. cell_of is the leaf index).
+template <typename MortT>
 __global__ void __launch_bounds__(256) remorton_kernel(const double* __restrict__ xyz, const uint32_t* __restrict__ perm,
                                                        const uint32_t* __restrict__ cell_of, const uint32_t* __restrict__ lcell,
                                                        const uint64_t* __restrict__ cell_key, KeyParams kp, uint32_t n,
-                                                       uint64_t* __restrict__ mort) {
+                                                       MortT* __restrict__ mort) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const size_t r = perm[i];
@@ -156,8 +166,8 @@ __global__ void __launch_bounds__(256) remorton_kernel(const double* __restrict_
 #pragma unroll
     for (int a = 0; a < 3; ++a) c0[a] = cell_corner_coord(q[a], kp.corner[a], kp.edge, kp.single_cell);
     int bad;
-    uint64_t m = point_morton(p, c0, kp.edge, kp.depth, &bad);
-    if (bad < kp.depth) m |= MORTON_BAD_BIT;
+    MortT m = (MortT)point_morton(p, c0, kp.edge, kp.depth, &bad);
+    if (bad < kp.depth) m |= MortBits<MortT>::bad;
     mort[i] = m;
 }
 
@@ -225,10 +235,11 @@ __global__ void alive_flags_kernel(const uint8_t* __restrict__ alive_r, const ui
     if (i < n) flags[i] = alive_r[perm[i]] ? 1u : 0u;
 }
 
+template <typename MortT>
 __global__ void compact_pos_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan_ex, uint32_t n,
-                                   const uint32_t* __restrict__ perm_in, const uint64_t* __restrict__ mort_in,
+                                   const uint32_t* __restrict__ perm_in, const MortT* __restrict__ mort_in,
                                    const uint32_t* __restrict__ aux_in, uint32_t* __restrict__ perm_out,
-                                   uint64_t* __restrict__ mort_out, uint32_t* __restrict__ aux_out,
+                                   MortT* __restrict__ mort_out, uint32_t* __restrict__ aux_out,
                                    uint8_t* __restrict__ alive_r) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -323,11 +334,15 @@ constexpr int PART_THREADS = 256;
 constexpr int PART_ITEMS = 8;
 constexpr int PART_TILE = PART_THREADS * PART_ITEMS;
 
-__device__ __forceinline__ uint32_t level_digit(uint64_t m, int shift) { return (uint32_t)(m >> shift) & 7u; }
+template <typename MortT>
+__device__ __forceinline__ uint32_t level_digit(MortT m, int shift) {
+    return (uint32_t)(m >> shift) & 7u;
+}
 
 // per-tile histogram of the level digit over positions that belong to splitting leaves
+template <typename MortT>
 __global__ void __launch_bounds__(PART_THREADS) part_hist_kernel(const uint32_t* __restrict__ leaf_of,
-                                                                  const uint64_t* __restrict__ mort,
+                                                                  const MortT* __restrict__ mort,
                                                                   const uint32_t* __restrict__ splitf,
                                                                   const uint32_t* __restrict__ iidx, uint32_t n,
                                                                   uint32_t num_tiles, uint32_t n_split, int shift,
@@ -380,12 +395,13 @@ __device__ __forceinline__ void packed_inc(Packed8& p, uint32_t g) {
 // and S_g(first position of k) is the exclusive scan over the split leaves of leaf_cnt[g][.] (leaf_beg) because split
 // leaves appear in position order.  Blocked arrangement (8 consecutive positions per thread): measured 4.2 ms for the
 // three levels of the 100 M workload against 7.3 ms for a warp-striped variant with match-based ranking.
+template <typename MortT>
 __global__ void __launch_bounds__(PART_THREADS) part_move_kernel(
-    const uint32_t* __restrict__ leaf_of, const uint64_t* __restrict__ mort, const uint32_t* __restrict__ perm,
+    const uint32_t* __restrict__ leaf_of, const MortT* __restrict__ mort, const uint32_t* __restrict__ perm,
     const uint32_t* __restrict__ splitf, const uint32_t* __restrict__ iidx, const uint32_t* __restrict__ newidx,
     const uint32_t* __restrict__ lstart, const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ leaf_cnt,
     const uint32_t* __restrict__ leaf_beg, uint32_t n, uint32_t num_tiles, uint32_t n_split, int shift, int level,
-    uint32_t* __restrict__ leaf_out, uint64_t* __restrict__ mort_out, uint32_t* __restrict__ perm_out,
+    uint32_t* __restrict__ leaf_out, MortT* __restrict__ mort_out, uint32_t* __restrict__ perm_out,
     // for the out-of-node re-check
     const double* __restrict__ xyz, const uint32_t* __restrict__ lcell, const uint64_t* __restrict__ cell_key, KeyParams kp,
     uint32_t* __restrict__ err) {
@@ -395,7 +411,7 @@ __global__ void __launch_bounds__(PART_THREADS) part_move_kernel(
     const uint32_t first = blockIdx.x * PART_TILE + threadIdx.x * PART_ITEMS;
     uint32_t leaf[PART_ITEMS];
     uint32_t g[PART_ITEMS];
-    uint64_t m[PART_ITEMS];
+    MortT m[PART_ITEMS];
     Packed8 cnt{0ull, 0ull};
 #pragma unroll
     for (int j = 0; j < PART_ITEMS; ++j) {
@@ -449,7 +465,7 @@ __global__ void __launch_bounds__(PART_THREADS) part_move_kernel(
             for (uint32_t c = 0; c < g[j]; ++c) base += leaf_cnt[(size_t)c * n_split + s];
             dst = base + (S - leaf_beg[(size_t)g[j] * n_split + s]);
             nl += g[j];
-            if (m[j] & MORTON_BAD_BIT) {
+            if (m[j] & MortBits<MortT>::bad) {
                 // the point left its node at some level: an error only if that level is being split
                 const uint32_t r = perm[i];
                 long long q[3] = {0, 0, 0};

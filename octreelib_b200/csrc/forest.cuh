@@ -9,6 +9,7 @@
 namespace ol {
 
 constexpr int MORTON_INITIAL_DEPTH = 8;
+constexpr int MORTON32_MAX_DEPTH = 10;  // 30 digit bits + the out-of-node flag fit a 32-bit word
 
 struct Forest {
     Ctx ctx;
@@ -40,7 +41,10 @@ struct Forest {
     int key_bits = 0;
     uint32_t A0 = 0;             // alive points in the base order
     DevBuf<uint32_t> perm0;      // [A0] base position -> r
-    DevBuf<uint64_t> mort0;      // [A0] Morton code of the point (bit 63: out-of-node somewhere)
+    DevBuf<uint64_t> mort0;      // [A0] Morton code of the point (top bit: out-of-node somewhere); 32-bit words packed two
+                                 // per element while mort32 is set (kp.depth <= MORTON32_MAX_DEPTH), 64-bit words after
+    bool mort32 = true;
+    size_t mort_len(size_t n) const { return mort32 ? (n + 1) / 2 : n; }  // DevBuf<uint64_t> elements for n codes
     DevBuf<uint32_t> cellidx0;   // [A0] base position -> cell index
     uint32_t C = 0;
     DevBuf<uint64_t> cell_key;   // [C] packed cell key (without pose bits)

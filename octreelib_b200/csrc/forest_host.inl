@@ -187,6 +187,7 @@ void Forest::build() {
     for (int a = 0; a < 3; ++a) kp.corner[a] = cfg.corner[a];
     kp.single_cell = cfg.single_cell;
     kp.depth = std::min(max_depth, MORTON_INITIAL_DEPTH);  // deeper levels are computed on demand (extend_morton)
+    mort32 = kp.depth <= MORTON32_MAX_DEPTH;
     kp.pose_bits = segs_pose_monotone ? 0 : bit_length_u64((uint64_t)std::max(n_poses - 1, 0));
     int bits[3] = {0, 0, 0};
     if (!cfg.single_cell && N > 0) {
@@ -227,12 +228,16 @@ void Forest::build() {
         base_dirty = false;
         return;
     }
-    DevBuf<uint64_t> keys0(ctx, n), keys1(ctx, n), mort_r(ctx, n);
+    DevBuf<uint64_t> keys0(ctx, n), keys1(ctx, n), mort_r(ctx, mort_len(n));
     DevBuf<uint32_t> vals0(ctx, n), vals1(ctx, n);
     {
         ProfScope ps(ctx, "keygen", (double)n);
-        keygen_kernel<<<nblk(n), 256, 0, ctx.stream>>>(P64.get(), n, kp, d_seg_start.get(), d_seg_pose.get(), S, keys0.get(),
-                                                       mort_r.get(), d_err.get());
+        if (mort32)
+            keygen_kernel<uint32_t><<<nblk(n), 256, 0, ctx.stream>>>(P64.get(), n, kp, d_seg_start.get(), d_seg_pose.get(), S, keys0.get(),
+                                                                     reinterpret_cast<uint32_t*>(mort_r.get()), d_err.get());
+        else
+            keygen_kernel<uint64_t><<<nblk(n), 256, 0, ctx.stream>>>(P64.get(), n, kp, d_seg_start.get(), d_seg_pose.get(), S, keys0.get(),
+                                                                     mort_r.get(), d_err.get());
         OL_CHECK_LAUNCH();
     }
     iota_kernel<<<nblk(n), 256, 0, ctx.stream>>>(vals0.get(), n, 0);
@@ -245,10 +250,14 @@ void Forest::build() {
     keys1.release();
     vals1.release();
     perm0.swap(vals0);
-    mort0.reset(ctx, n);
+    mort0.reset(ctx, mort_len(n));
     {
         ProfScope ps(ctx, "gather_morton", (double)n);
-        gather_kernel<uint64_t><<<nblk(n), 256, 0, ctx.stream>>>(mort0.get(), mort_r.get(), perm0.get(), n);
+        if (mort32)
+            gather_kernel<uint32_t><<<nblk(n), 256, 0, ctx.stream>>>(reinterpret_cast<uint32_t*>(mort0.get()),
+                                                                     reinterpret_cast<const uint32_t*>(mort_r.get()), perm0.get(), n);
+        else
+            gather_kernel<uint64_t><<<nblk(n), 256, 0, ctx.stream>>>(mort0.get(), mort_r.get(), perm0.get(), n);
         OL_CHECK_LAUNCH();
     }
     mort_r.release();
@@ -305,11 +314,16 @@ void Forest::compact_base() {
         exclusive_scan_u32(ctx, flags.get(), scan.get(), n, d_total.get());
         uint32_t total = (uint32_t)read_u64(d_total.get());
         DevBuf<uint32_t> p2(ctx, total), c2(ctx, total), s2(ctx, (size_t)C + 1);
-        DevBuf<uint64_t> m2(ctx, total);
+        DevBuf<uint64_t> m2(ctx, mort_len(total));
         {
             ProfScope ps(ctx, "compact");
-            compact_pos_kernel<<<nblk(n), 256, 0, ctx.stream>>>(flags.get(), scan.get(), n, perm0.get(), mort0.get(),
-                                                                cellidx0.get(), p2.get(), m2.get(), c2.get(), nullptr);
+            if (mort32)
+                compact_pos_kernel<uint32_t><<<nblk(n), 256, 0, ctx.stream>>>(flags.get(), scan.get(), n, perm0.get(),
+                                                                              reinterpret_cast<const uint32_t*>(mort0.get()), cellidx0.get(),
+                                                                              p2.get(), reinterpret_cast<uint32_t*>(m2.get()), c2.get(), nullptr);
+            else
+                compact_pos_kernel<uint64_t><<<nblk(n), 256, 0, ctx.stream>>>(flags.get(), scan.get(), n, perm0.get(), mort0.get(),
+                                                                              cellidx0.get(), p2.get(), m2.get(), c2.get(), nullptr);
             OL_CHECK_LAUNCH();
         }
         {
@@ -331,17 +345,21 @@ void Forest::compact_base() {
 void Forest::extend_morton() {
     if (kp.depth >= max_depth) return;
     kp.depth = max_depth;
+    const bool was32 = mort32;
+    mort32 = kp.depth <= MORTON32_MAX_DEPTH;
     ProfScope ps(ctx, "keygen", (double)(A0 + (shaped ? A : 0)));
-    if (A0) {
-        remorton_kernel<<<nblk(A0), 256, 0, ctx.stream>>>(P64.get(), perm0.get(), cellidx0.get(), nullptr, cell_key.get(), kp, A0,
-                                                          mort0.get());
+    auto recompute = [&](DevBuf<uint64_t>& buf, const uint32_t* perm_p, const uint32_t* cell_of, const uint32_t* lcell_p, uint32_t n) {
+        if (was32 != mort32) buf.reset(ctx, mort_len(n));
+        if (n == 0) return;
+        if (mort32)
+            remorton_kernel<uint32_t><<<nblk(n), 256, 0, ctx.stream>>>(P64.get(), perm_p, cell_of, lcell_p, cell_key.get(), kp, n,
+                                                                       reinterpret_cast<uint32_t*>(buf.get()));
+        else
+            remorton_kernel<uint64_t><<<nblk(n), 256, 0, ctx.stream>>>(P64.get(), perm_p, cell_of, lcell_p, cell_key.get(), kp, n, buf.get());
         OL_CHECK_LAUNCH();
-    }
-    if (shaped && A) {
-        remorton_kernel<<<nblk(A), 256, 0, ctx.stream>>>(P64.get(), perm.get(), leaf_of.get(), lcell.get(), cell_key.get(), kp, A,
-                                                         mort.get());
-        OL_CHECK_LAUNCH();
-    }
+    };
+    recompute(mort0, perm0.get(), cellidx0.get(), nullptr, A0);
+    if (shaped) recompute(mort, perm.get(), leaf_of.get(), lcell.get(), A);
 }
 
 // current shape := one leaf per cell
@@ -355,10 +373,10 @@ void Forest::reset_shape() {
     I = 0;
     depth_reached = 0;
     perm.reset(ctx, A);
-    mort.reset(ctx, A);
+    mort.reset(ctx, mort_len(A));
     leaf_of.reset(ctx, A);
     d2d(ctx, perm.get(), perm0.get(), A);
-    d2d(ctx, mort.get(), mort0.get(), A);
+    d2d(ctx, mort.get(), mort0.get(), mort_len(A));
     d2d(ctx, leaf_of.get(), cellidx0.get(), A);
     lstart.reset(ctx, (size_t)L + 1);
     d2d(ctx, lstart.get(), cell_start0.get(), (size_t)L + 1);
@@ -459,7 +477,7 @@ void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t ta
     const uint32_t tiles = (A + PART_TILE - 1) / PART_TILE;
     DevBuf<uint32_t> tile_hist(ctx, (size_t)8 * tiles);
     DevBuf<uint32_t> perm_b(ctx, A), leaf_b(ctx, A);
-    DevBuf<uint64_t> mort_b(ctx, A);
+    DevBuf<uint64_t> mort_b(ctx, mort_len(A));
     for (int level = 0;; ++level) {
         DevBuf<uint32_t> splitf(ctx, L), expand(ctx, L), newidx(ctx, L), iidx(ctx, L), wcount;
         if (n_listed > 0) {
@@ -490,25 +508,38 @@ void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t ta
         if (n_split == 0) break;
         OL_REQUIRE((unsigned long long)I + n_split < (1ull << 29), OL_ERR_RANGE, "too many internal nodes");
         depth_reached = level + 1;
-        if (level >= kp.depth) extend_morton();
+        if (level >= kp.depth) {
+            extend_morton();
+            mort_b.reset(ctx, mort_len(A));  // the word size may have changed
+        }
         const int shift = 3 * (kp.depth - 1 - level);
         DevBuf<uint32_t> leaf_cnt(ctx, (size_t)n_split * 8), leaf_beg(ctx, (size_t)n_split * 8);
         leaf_cnt.zero();
         {
             ProfScope ps(ctx, "part_hist", (double)A);
-            part_hist_kernel<<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), mort.get(), splitf.get(), iidx.get(), A, tiles,
-                                                                     n_split, shift, tile_hist.get(), leaf_cnt.get());
+            if (mort32)
+                part_hist_kernel<uint32_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), reinterpret_cast<const uint32_t*>(mort.get()),
+                                                                                   splitf.get(), iidx.get(), A, tiles, n_split, shift,
+                                                                                   tile_hist.get(), leaf_cnt.get());
+            else
+                part_hist_kernel<uint64_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), mort.get(), splitf.get(), iidx.get(), A, tiles,
+                                                                                   n_split, shift, tile_hist.get(), leaf_cnt.get());
             OL_CHECK_LAUNCH();
         }
         exclusive_scan_u32(ctx, tile_hist.get(), tile_hist.get(), (size_t)8 * tiles, nullptr);
         exclusive_scan_u32(ctx, leaf_cnt.get(), leaf_beg.get(), (size_t)8 * n_split, nullptr);
         {
             ProfScope ps(ctx, "part_move", (double)A);
-            part_move_kernel<<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), mort.get(), perm.get(), splitf.get(), iidx.get(),
-                                                                     newidx.get(), lstart.get(), tile_hist.get(), leaf_cnt.get(),
-                                                                     leaf_beg.get(), A, tiles, n_split, shift, level, leaf_b.get(),
-                                                                     mort_b.get(), perm_b.get(), P64.get(), lcell.get(), cell_key.get(),
-                                                                     kp, d_err.get());
+            if (mort32)
+                part_move_kernel<uint32_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(
+                    leaf_of.get(), reinterpret_cast<const uint32_t*>(mort.get()), perm.get(), splitf.get(), iidx.get(), newidx.get(),
+                    lstart.get(), tile_hist.get(), leaf_cnt.get(), leaf_beg.get(), A, tiles, n_split, shift, level, leaf_b.get(),
+                    reinterpret_cast<uint32_t*>(mort_b.get()), perm_b.get(), P64.get(), lcell.get(), cell_key.get(), kp, d_err.get());
+            else
+                part_move_kernel<uint64_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(
+                    leaf_of.get(), mort.get(), perm.get(), splitf.get(), iidx.get(), newidx.get(), lstart.get(), tile_hist.get(),
+                    leaf_cnt.get(), leaf_beg.get(), A, tiles, n_split, shift, level, leaf_b.get(), mort_b.get(), perm_b.get(), P64.get(),
+                    lcell.get(), cell_key.get(), kp, d_err.get());
             OL_CHECK_LAUNCH();
         }
         // new leaf / internal tables
@@ -682,15 +713,20 @@ void Forest::apply_keep(const uint8_t* keep_pos) {
     const uint32_t total = (uint32_t)read_u64(d_total.get());
     if (total == n) return;
     DevBuf<uint32_t> p2(ctx, total), l2(ctx, total), s2(ctx, (size_t)L + 1);
-    DevBuf<uint64_t> m2(ctx, total);
+    DevBuf<uint64_t> m2(ctx, mort_len(total));
     if (!alive_r.get()) {  // first removal: every inserted point was alive so far
         alive_r.reset(ctx, cap);
         OL_CUDA(cudaMemsetAsync(alive_r.get(), 1, cap, ctx.stream));
     }
     {
         ProfScope ps(ctx, "compact");
-        compact_pos_kernel<<<nblk(n), 256, 0, ctx.stream>>>(flags.get(), scan.get(), n, perm.get(), mort.get(), leaf_of.get(),
-                                                            p2.get(), m2.get(), l2.get(), alive_r.get());
+        if (mort32)
+            compact_pos_kernel<uint32_t><<<nblk(n), 256, 0, ctx.stream>>>(flags.get(), scan.get(), n, perm.get(),
+                                                                          reinterpret_cast<const uint32_t*>(mort.get()), leaf_of.get(), p2.get(),
+                                                                          reinterpret_cast<uint32_t*>(m2.get()), l2.get(), alive_r.get());
+        else
+            compact_pos_kernel<uint64_t><<<nblk(n), 256, 0, ctx.stream>>>(flags.get(), scan.get(), n, perm.get(), mort.get(), leaf_of.get(),
+                                                                          p2.get(), m2.get(), l2.get(), alive_r.get());
         OL_CHECK_LAUNCH();
     }
     {
