@@ -1,6 +1,7 @@
-// Forest pipeline: K1 keygen, K2 sort (primitives.cuh), K3 cell segmentation, K4 level-synchronous
-// subdivision, K5 leaf enumeration order + geometry, (pose, leaf) block table, K7 filter / mask
-// compaction.  K6 (RANSAC) lives in ransac.cu.
+// Forest pipeline: K0 bounding box, K1 keygen, K2 sort (onesweep.cuh / primitives.cuh), K3 run segmentation into cells
+// and (cell, pose) pairs, K4 level-synchronous subdivision (per-leaf digit histogram + fused stable partition),
+// scheme replay for late poses, K5 leaf enumeration order + geometry, (pose, leaf) block table, K7 filter / mask
+// compaction.  K6 (RANSAC) lives in ransac.cu, the multi-GPU routing in partition.cu.
 #include <algorithm>
 #include <climits>
 #include <mutex>

@@ -1,6 +1,8 @@
 // Multi-GPU routing: owner rank = hash(grid-cell coordinates) mod world, stable
-// partition of a rank's local points by owner so that one NCCL all-to-all delivers every cell's
-// points - of all poses - to a single GPU.  The reference has no counterpart (single process);
+// partition of a rank's local points by owner so that one exchange delivers every cell's points - of
+// all poses - to a single GPU: either a staging copy for an NCCL all-to-all (ol_partition_by_owner) or
+// the fused route kernel that stores every row straight into its owner's peer-mapped receive buffer
+// over NVLink (ol_route_plan + ol_route_to_peers).  The reference has no counterpart (single process);
 // the cell coordinates are the ones of /root/reference/octreelib/grid/grid.py:72-76.
 #include "common.cuh"
 #include "pointkey.cuh"

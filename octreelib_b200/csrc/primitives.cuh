@@ -1,6 +1,6 @@
-// Device-wide primitives used by the forest pipeline: exclusive scan (u32), stable LSD radix
-// sort of (key, u32 value) pairs, head-flag compaction.  All work is enqueued on Ctx::stream;
-// temporaries come from Ctx::alloc.
+// Device-wide primitives used by the forest pipeline: exclusive scan (u32), stable LSD radix sort of (key, u32 value)
+// pairs (onesweep.cuh below 2^30 pairs, the three-kernel sort in this file above), run segmentation (count + emit).
+// All work is enqueued on Ctx::stream; temporaries come from Ctx::alloc.
 #pragma once
 #include "common.cuh"
 #include "onesweep.cuh"
