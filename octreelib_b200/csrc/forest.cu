@@ -412,21 +412,43 @@ __global__ void __launch_bounds__(PART_THREADS) part_move_kernel(
     const uint32_t first = blockIdx.x * PART_TILE + threadIdx.x * PART_ITEMS;
     uint32_t leaf[PART_ITEMS];
     uint32_t g[PART_ITEMS];
+    uint32_t pr[PART_ITEMS];
     MortT m[PART_ITEMS];
     Packed8 cnt{0ull, 0ull};
+    static_assert(PART_ITEMS == 8, "vector loads below assume 8 items per thread");
+    if (first + PART_ITEMS <= n) {
+        // the thread's 8 consecutive elements are one or two aligned 32-byte segments: 16-byte vector loads
+        const uint4 l0 = reinterpret_cast<const uint4*>(leaf_of + first)[0], l1 = reinterpret_cast<const uint4*>(leaf_of + first)[1];
+        const uint4 p0 = reinterpret_cast<const uint4*>(perm + first)[0], p1 = reinterpret_cast<const uint4*>(perm + first)[1];
+        leaf[0] = l0.x, leaf[1] = l0.y, leaf[2] = l0.z, leaf[3] = l0.w, leaf[4] = l1.x, leaf[5] = l1.y, leaf[6] = l1.z, leaf[7] = l1.w;
+        pr[0] = p0.x, pr[1] = p0.y, pr[2] = p0.z, pr[3] = p0.w, pr[4] = p1.x, pr[5] = p1.y, pr[6] = p1.z, pr[7] = p1.w;
+        if (sizeof(MortT) == 4) {
+            const uint4 m0 = reinterpret_cast<const uint4*>(mort + first)[0], m1 = reinterpret_cast<const uint4*>(mort + first)[1];
+            m[0] = (MortT)m0.x, m[1] = (MortT)m0.y, m[2] = (MortT)m0.z, m[3] = (MortT)m0.w;
+            m[4] = (MortT)m1.x, m[5] = (MortT)m1.y, m[6] = (MortT)m1.z, m[7] = (MortT)m1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < PART_ITEMS; j += 2) {
+                const ulonglong2 v = reinterpret_cast<const ulonglong2*>(mort + first)[j / 2];
+                m[j] = (MortT)v.x;
+                m[j + 1] = (MortT)v.y;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < PART_ITEMS; ++j) {
+            const uint32_t i = first + j;
+            leaf[j] = i < n ? leaf_of[i] : 0u;
+            pr[j] = i < n ? perm[i] : 0u;
+            m[j] = i < n ? mort[i] : (MortT)0;
+        }
+    }
 #pragma unroll
     for (int j = 0; j < PART_ITEMS; ++j) {
-        uint32_t i = first + j;
         g[j] = 8u;
-        leaf[j] = 0;
-        m[j] = 0;
-        if (i < n) {
-            leaf[j] = leaf_of[i];
-            m[j] = mort[i];
-            if (splitf[leaf[j]]) {
-                g[j] = level_digit(m[j], shift);
-                packed_inc(cnt, g[j]);
-            }
+        if (first + j < n && splitf[leaf[j]]) {
+            g[j] = level_digit(m[j], shift);
+            packed_inc(cnt, g[j]);
         }
     }
     // block exclusive scan of the packed counters
@@ -468,7 +490,7 @@ __global__ void __launch_bounds__(PART_THREADS) part_move_kernel(
             nl += g[j];
             if (m[j] & MortBits<MortT>::bad) {
                 // the point left its node at some level: an error only if that level is being split
-                const uint32_t r = perm[i];
+                const uint32_t r = pr[j];
                 long long q[3] = {0, 0, 0};
                 if (!kp.single_cell) unpack_cell(kp, cell_key[lcell[k]], q);
                 double p[3] = {xyz[(size_t)r * 3], xyz[(size_t)r * 3 + 1], xyz[(size_t)r * 3 + 2]};
@@ -481,7 +503,7 @@ __global__ void __launch_bounds__(PART_THREADS) part_move_kernel(
         }
         leaf_out[dst] = nl;
         mort_out[dst] = m[j];
-        perm_out[dst] = perm[i];
+        perm_out[dst] = pr[j];
     }
 }
 
