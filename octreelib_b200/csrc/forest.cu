@@ -388,6 +388,28 @@ __device__ __forceinline__ void packed_inc(Packed8& p, uint32_t g) {
         p.hi += one;
 }
 
+// per split leaf s and digit g: (first destination of the leaf's digit-g child) - S_g(first position of the leaf), so that
+// the move kernel needs ONE 4-byte gather per point instead of walking leaf_cnt / leaf_beg (up to 9 dependent gathers)
+__global__ void part_delta_kernel(uint32_t L, const uint32_t* __restrict__ splitf, const uint32_t* __restrict__ iidx,
+                                  const uint32_t* __restrict__ lstart, const uint32_t* __restrict__ leaf_cnt,
+                                  const uint32_t* __restrict__ leaf_beg, uint32_t n_split, uint32_t* __restrict__ delta /*[n_split][8]*/,
+                                  uint32_t* __restrict__ sidx /*[L] split index or ~0*/) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= L) return;
+    if (!splitf[k]) {
+        sidx[k] = 0xffffffffu;
+        return;
+    }
+    const uint32_t s = iidx[k];
+    sidx[k] = s;
+    uint32_t run = lstart[k];
+#pragma unroll
+    for (uint32_t g = 0; g < 8; ++g) {
+        delta[(size_t)s * 8 + g] = run - leaf_beg[(size_t)g * n_split + s];
+        run += leaf_cnt[(size_t)g * n_split + s];
+    }
+}
+
 // Stable 8-way partition of every splitting leaf's range in ONE pass (everything else is copied through).
 // With S_g(i) = number of active positions before i whose digit is g (a global running count: the tile's offset from
 // the scanned tile histograms plus a running count inside the tile), the destination of an active position i of leaf k
@@ -399,9 +421,8 @@ __device__ __forceinline__ void packed_inc(Packed8& p, uint32_t g) {
 template <typename MortT>
 __global__ void __launch_bounds__(PART_THREADS) part_move_kernel(
     const uint32_t* __restrict__ leaf_of, const MortT* __restrict__ mort, const uint32_t* __restrict__ perm,
-    const uint32_t* __restrict__ splitf, const uint32_t* __restrict__ iidx, const uint32_t* __restrict__ newidx,
-    const uint32_t* __restrict__ lstart, const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ leaf_cnt,
-    const uint32_t* __restrict__ leaf_beg, uint32_t n, uint32_t num_tiles, uint32_t n_split, int shift, int level,
+    const uint32_t* __restrict__ sidx, const uint32_t* __restrict__ newidx, const uint32_t* __restrict__ tile_off,
+    const uint32_t* __restrict__ delta, uint32_t n, uint32_t num_tiles, int shift, int level,
     uint32_t* __restrict__ leaf_out, MortT* __restrict__ mort_out, uint32_t* __restrict__ perm_out,
     // for the out-of-node re-check
     const double* __restrict__ xyz, const uint32_t* __restrict__ lcell, const uint64_t* __restrict__ cell_key, KeyParams kp,
@@ -444,9 +465,12 @@ __global__ void __launch_bounds__(PART_THREADS) part_move_kernel(
         }
     }
 #pragma unroll
+    uint32_t sp[PART_ITEMS];  // split index of the item's leaf (~0: the leaf does not split)
+#pragma unroll
     for (int j = 0; j < PART_ITEMS; ++j) {
         g[j] = 8u;
-        if (first + j < n && splitf[leaf[j]]) {
+        sp[j] = first + j < n ? sidx[leaf[j]] : 0xffffffffu;
+        if (sp[j] != 0xffffffffu) {
             g[j] = level_digit(m[j], shift);
             packed_inc(cnt, g[j]);
         }
@@ -481,12 +505,9 @@ __global__ void __launch_bounds__(PART_THREADS) part_move_kernel(
         const uint32_t k = leaf[j];
         uint32_t dst = i, nl = newidx[k];
         if (g[j] < 8u) {
-            const uint32_t s = iidx[k];
             const uint32_t S = G[g[j]] + packed_get(run, g[j]);
             packed_inc(run, g[j]);
-            uint32_t base = lstart[k];
-            for (uint32_t c = 0; c < g[j]; ++c) base += leaf_cnt[(size_t)c * n_split + s];
-            dst = base + (S - leaf_beg[(size_t)g[j] * n_split + s]);
+            dst = S + delta[(size_t)sp[j] * 8 + g[j]];
             nl += g[j];
             if (m[j] & MortBits<MortT>::bad) {
                 // the point left its node at some level: an error only if that level is being split

@@ -528,18 +528,24 @@ void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t ta
         }
         exclusive_scan_u32(ctx, tile_hist.get(), tile_hist.get(), (size_t)8 * tiles, nullptr);
         exclusive_scan_u32(ctx, leaf_cnt.get(), leaf_beg.get(), (size_t)8 * n_split, nullptr);
+        DevBuf<uint32_t> delta(ctx, (size_t)n_split * 8), sidx(ctx, L);
+        {
+            ProfScope ps(ctx, "part_decide");
+            part_delta_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, splitf.get(), iidx.get(), lstart.get(), leaf_cnt.get(), leaf_beg.get(),
+                                                               n_split, delta.get(), sidx.get());
+            OL_CHECK_LAUNCH();
+        }
         {
             ProfScope ps(ctx, "part_move", (double)A);
             if (mort32)
                 part_move_kernel<uint32_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(
-                    leaf_of.get(), reinterpret_cast<const uint32_t*>(mort.get()), perm.get(), splitf.get(), iidx.get(), newidx.get(),
-                    lstart.get(), tile_hist.get(), leaf_cnt.get(), leaf_beg.get(), A, tiles, n_split, shift, level, leaf_b.get(),
-                    reinterpret_cast<uint32_t*>(mort_b.get()), perm_b.get(), P64.get(), lcell.get(), cell_key.get(), kp, d_err.get());
+                    leaf_of.get(), reinterpret_cast<const uint32_t*>(mort.get()), perm.get(), sidx.get(), newidx.get(), tile_hist.get(),
+                    delta.get(), A, tiles, shift, level, leaf_b.get(), reinterpret_cast<uint32_t*>(mort_b.get()), perm_b.get(), P64.get(),
+                    lcell.get(), cell_key.get(), kp, d_err.get());
             else
                 part_move_kernel<uint64_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(
-                    leaf_of.get(), mort.get(), perm.get(), splitf.get(), iidx.get(), newidx.get(), lstart.get(), tile_hist.get(),
-                    leaf_cnt.get(), leaf_beg.get(), A, tiles, n_split, shift, level, leaf_b.get(), mort_b.get(), perm_b.get(), P64.get(),
-                    lcell.get(), cell_key.get(), kp, d_err.get());
+                    leaf_of.get(), mort.get(), perm.get(), sidx.get(), newidx.get(), tile_hist.get(), delta.get(), A, tiles, shift, level,
+                    leaf_b.get(), mort_b.get(), perm_b.get(), P64.get(), lcell.get(), cell_key.get(), kp, d_err.get());
             OL_CHECK_LAUNCH();
         }
         // new leaf / internal tables
