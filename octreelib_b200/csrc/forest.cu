@@ -344,8 +344,7 @@ __device__ __forceinline__ uint32_t level_digit(MortT m, int shift) {
 template <typename MortT>
 __global__ void __launch_bounds__(PART_THREADS) part_hist_kernel(const uint32_t* __restrict__ leaf_of,
                                                                   const MortT* __restrict__ mort,
-                                                                  const uint32_t* __restrict__ splitf,
-                                                                  const uint32_t* __restrict__ iidx, uint32_t n,
+                                                                  const uint32_t* __restrict__ sidx, uint32_t n,
                                                                   uint32_t num_tiles, uint32_t n_split, int shift,
                                                                   uint32_t* __restrict__ tile_hist,
                                                                   uint32_t* __restrict__ leaf_cnt /*[8][n_split]*/) {
@@ -359,8 +358,8 @@ __global__ void __launch_bounds__(PART_THREADS) part_hist_kernel(const uint32_t*
         uint32_t i = base + j * PART_THREADS + threadIdx.x;
         uint32_t key = 0xffffffffu;  // (split-leaf index << 3) | digit
         if (i < n) {
-            const uint32_t k = leaf_of[i];
-            if (splitf[k]) key = (iidx[k] << 3) | level_digit(mort[i], shift);
+            const uint32_t sp = sidx[leaf_of[i]];
+            if (sp != 0xffffffffu) key = (sp << 3) | level_digit(mort[i], shift);
         }
         // positions are leaf-ordered, so a warp holds few distinct (leaf, digit) pairs: one atomic per pair
         const uint32_t peers = __match_any_sync(0xffffffffu, key);
@@ -388,20 +387,21 @@ __device__ __forceinline__ void packed_inc(Packed8& p, uint32_t g) {
         p.hi += one;
 }
 
+// split index of every leaf (~0 = does not split): one gather per point in the partition kernels instead of two
+__global__ void split_index_kernel(uint32_t L, const uint32_t* __restrict__ splitf, const uint32_t* __restrict__ iidx,
+                                   uint32_t* __restrict__ sidx) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < L) sidx[k] = splitf[k] ? iidx[k] : 0xffffffffu;
+}
+
 // per split leaf s and digit g: (first destination of the leaf's digit-g child) - S_g(first position of the leaf), so that
 // the move kernel needs ONE 4-byte gather per point instead of walking leaf_cnt / leaf_beg (up to 9 dependent gathers)
 __global__ void part_delta_kernel(uint32_t L, const uint32_t* __restrict__ splitf, const uint32_t* __restrict__ iidx,
                                   const uint32_t* __restrict__ lstart, const uint32_t* __restrict__ leaf_cnt,
-                                  const uint32_t* __restrict__ leaf_beg, uint32_t n_split, uint32_t* __restrict__ delta /*[n_split][8]*/,
-                                  uint32_t* __restrict__ sidx /*[L] split index or ~0*/) {
+                                  const uint32_t* __restrict__ leaf_beg, uint32_t n_split, uint32_t* __restrict__ delta /*[n_split][8]*/) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= L) return;
-    if (!splitf[k]) {
-        sidx[k] = 0xffffffffu;
-        return;
-    }
+    if (k >= L || !splitf[k]) return;
     const uint32_t s = iidx[k];
-    sidx[k] = s;
     uint32_t run = lstart[k];
 #pragma unroll
     for (uint32_t g = 0; g < 8; ++g) {

@@ -513,26 +513,31 @@ void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t ta
             mort_b.reset(ctx, mort_len(A));  // the word size may have changed
         }
         const int shift = 3 * (kp.depth - 1 - level);
-        DevBuf<uint32_t> leaf_cnt(ctx, (size_t)n_split * 8), leaf_beg(ctx, (size_t)n_split * 8);
+        DevBuf<uint32_t> leaf_cnt(ctx, (size_t)n_split * 8), leaf_beg(ctx, (size_t)n_split * 8), sidx(ctx, L);
         leaf_cnt.zero();
+        {
+            ProfScope ps(ctx, "part_decide");
+            split_index_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, splitf.get(), iidx.get(), sidx.get());
+            OL_CHECK_LAUNCH();
+        }
         {
             ProfScope ps(ctx, "part_hist", (double)A);
             if (mort32)
                 part_hist_kernel<uint32_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), reinterpret_cast<const uint32_t*>(mort.get()),
-                                                                                   splitf.get(), iidx.get(), A, tiles, n_split, shift,
-                                                                                   tile_hist.get(), leaf_cnt.get());
+                                                                                   sidx.get(), A, tiles, n_split, shift, tile_hist.get(),
+                                                                                   leaf_cnt.get());
             else
-                part_hist_kernel<uint64_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), mort.get(), splitf.get(), iidx.get(), A, tiles,
-                                                                                   n_split, shift, tile_hist.get(), leaf_cnt.get());
+                part_hist_kernel<uint64_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), mort.get(), sidx.get(), A, tiles, n_split,
+                                                                                   shift, tile_hist.get(), leaf_cnt.get());
             OL_CHECK_LAUNCH();
         }
         exclusive_scan_u32(ctx, tile_hist.get(), tile_hist.get(), (size_t)8 * tiles, nullptr);
         exclusive_scan_u32(ctx, leaf_cnt.get(), leaf_beg.get(), (size_t)8 * n_split, nullptr);
-        DevBuf<uint32_t> delta(ctx, (size_t)n_split * 8), sidx(ctx, L);
+        DevBuf<uint32_t> delta(ctx, (size_t)n_split * 8);
         {
             ProfScope ps(ctx, "part_decide");
             part_delta_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, splitf.get(), iidx.get(), lstart.get(), leaf_cnt.get(), leaf_beg.get(),
-                                                               n_split, delta.get(), sidx.get());
+                                                               n_split, delta.get());
             OL_CHECK_LAUNCH();
         }
         {
