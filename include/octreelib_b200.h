@@ -94,6 +94,13 @@ int ol_forest_destroy(ol_forest *f);
  * asynchronously and must stay unchanged until the next call that returns results. */
 int ol_forest_insert(ol_forest *f, const double *xyz, int64_t n, int32_t src_on_device, int32_t *out_pose_index);
 
+/* The same for `count` DEVICE-resident clouds at once (a host array of device pointers and their point counts): every
+ * cloud becomes one new pose, in order; *out_first_pose_index = index of the first.  One exact growth of the point
+ * array and one copy kernel instead of a driver call per pose - the Python host defers `insert_points` of CUDA tensors
+ * into such a batch and flushes it before the next grid operation. */
+int ol_forest_insert_batch(ol_forest *f, const double *const *xyz_dev_ptrs_host, const int64_t *sizes_host, int32_t count,
+                           int32_t *out_first_pose_index);
+
 /* Multi-GPU form: the cloud is a concatenation of `n_segments` runs, run s holding
  * `seg_sizes[s]` points of pose index `seg_pose[s]` whose first point has index `seg_first[s]`
  * inside that pose's original cloud (what an all-to-all delivers: one run per (source rank, pose)).

@@ -59,6 +59,7 @@ SIGNATURES = {
     "ol_forest_create": (C.c_int, [C.POINTER(ForestConfig), C.POINTER(_p)]),
     "ol_forest_destroy": (C.c_int, [_p]),
     "ol_forest_insert": (C.c_int, [_p, _p, _i64, _i32, C.POINTER(_i32)]),
+    "ol_forest_insert_batch": (C.c_int, [_p, _p, _p, _i32, C.POINTER(_i32)]),
     "ol_forest_insert_segments": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _i32, _i32]),
     "ol_forest_subdivide": (C.c_int, [_p, _i64, _p, _i32]),
     "ol_forest_subdivide_table": (C.c_int, [_p, _p, _i64, _i32, _p, _i32]),

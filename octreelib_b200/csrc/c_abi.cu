@@ -69,6 +69,17 @@ int ol_forest_insert(ol_forest* f, const double* xyz, int64_t n, int32_t src_on_
     OL_API_END
 }
 
+int ol_forest_insert_batch(ol_forest* f, const double* const* xyz_dev_ptrs_host, const int64_t* sizes_host, int32_t count,
+                           int32_t* out_first_pose_index) {
+    OL_NEED(f);
+    OL_API_BEGIN
+    OL_REQUIRE(count == 0 || (xyz_dev_ptrs_host && sizes_host), OL_ERR_INVALID, "NULL batch tables");
+    ol::PoolScope pool_scope(f->impl.ctx);
+    int p = f->impl.insert_batch(xyz_dev_ptrs_host, sizes_host, count);
+    if (out_first_pose_index) *out_first_pose_index = p;
+    OL_API_END
+}
+
 int ol_forest_insert_segments(ol_forest* f, const double* xyz, int64_t n, int32_t src_on_device, const int64_t* seg_sizes,
                               const int32_t* seg_pose, const int64_t* seg_first, int32_t n_segments, int32_t n_poses_total) {
     OL_NEED(f);

@@ -120,6 +120,7 @@ struct Forest {
     // pipeline stages
     int insert(const double* xyz, int64_t n, bool on_device, const int64_t* seg_sizes, const int32_t* seg_pose_in,
                const int64_t* seg_first_in, int n_segments, int n_poses_total);
+    int insert_batch(const double* const* xyz_dev, const int64_t* sizes, int count);  // many device clouds, one copy kernel
     void build();            // K1-K3: keygen, sort, cells
     void compact_base();     // drop dead points from the base order
     void extend_morton();    // Morton codes at the full depth (lazy: MORTON_INITIAL_DEPTH levels first)

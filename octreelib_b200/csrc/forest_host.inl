@@ -166,6 +166,63 @@ int Forest::insert(const double* xyz, int64_t n, bool on_device, const int64_t* 
     return pose_index;
 }
 
+// Many device-resident poses at once (the Python host defers `insert_points` of CUDA tensors and flushes them here):
+// one exact-size growth of the point array, one pointer-table upload, one copy kernel - instead of a driver call and a
+// possible re-allocation per pose.  Every cloud becomes one new pose; returns the index of the first one.
+int Forest::insert_batch(const double* const* xyz_dev, const int64_t* sizes, int count) {
+    OL_REQUIRE(count >= 0, OL_ERR_INVALID, "negative batch size");
+    const int first_pose = n_poses;
+    if (count == 0) return first_pose;
+    size_t total = 0;
+    for (int c = 0; c < count; ++c) {
+        OL_REQUIRE(sizes[c] >= 0, OL_ERR_INVALID, "negative point count");
+        total += (size_t)sizes[c];
+    }
+    OL_REQUIRE(N + total < (1ull << 31), OL_ERR_INVALID, "more than 2^31 - 1 points per forest are not supported");
+    materialize_snapshot();
+    if (shaped && I > 0) save_shape();
+    if (N + total > cap) {
+        const size_t ncap = N + total;  // the batch is usually the whole map: grow exactly once
+        DevBuf<double> np(ctx, ncap * 3);
+        d2d(ctx, np.get(), P64.get(), N * 3);
+        P64.swap(np);
+        if (alive_r.get()) {
+            DevBuf<uint8_t> na(ctx, ncap);
+            d2d(ctx, na.get(), alive_r.get(), N);
+            OL_CUDA(cudaMemsetAsync(na.get() + N, 1, ncap - N, ctx.stream));
+            alive_r.swap(na);
+        }
+        cap = ncap;
+    }
+    std::vector<unsigned long long> dst_start((size_t)count + 1, 0);
+    size_t r = N;
+    for (int c = 0; c < count; ++c) {
+        dst_start[c + 1] = dst_start[c] + (unsigned long long)sizes[c] * 3ull;
+        seg_pose.push_back(n_poses);
+        seg_first.push_back(0);
+        seg_start.back() = (uint32_t)r;
+        r += (size_t)sizes[c];
+        seg_start.push_back((uint32_t)r);
+        n_poses += 1;
+    }
+    if (total) {
+        DevBuf<const double*> d_src(ctx, (size_t)count);
+        DevBuf<unsigned long long> d_start(ctx, (size_t)count + 1);
+        h2d(ctx, d_src.get(), xyz_dev, (size_t)count);
+        h2d(ctx, d_start.get(), dst_start.data(), (size_t)count + 1);
+        const unsigned g = std::min<unsigned>(nblk(total * 3), (unsigned)ctx.num_sms * 16);
+        ProfScope ps(ctx, "insert_batch", (double)total);
+        insert_batch_kernel<<<g, 256, 0, ctx.stream>>>(d_src.get(), d_start.get(), count, P64.get() + N * 3);
+        OL_CHECK_LAUNCH();
+        ctx.sync();  // the pageable host tables above and the caller's tensors may be released after return
+    }
+    N += total;
+    built = false;
+    shaped = false;
+    order_valid = blocks_valid = ransac_valid = false;
+    return first_pose;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1-K3: keys, sort, cells, (cell, pose) table
 // ---------------------------------------------------------------------------------------------

@@ -93,16 +93,21 @@ class Forest:
         cfg.alloc = self._allocator.alloc_cb
         cfg.free = self._allocator.free_cb
         cfg.alloc_user = None
+        self._pending_sources = []  # sources of inserts that may still be in flight
+        self._batch = []            # CUDA tensors whose insert is deferred (one native call for all of them)
+        self._n_poses_native = 0    # poses the native forest knows about
         self._h = C.c_void_p()
         with self._scope():
             N.check(self._lib.ol_forest_create(C.byref(cfg), C.byref(self._h)))
         self.version = 0  # bumped by every mutating call; hosts cache exports per version
-        self._pending_sources = []  # sources of inserts that may still be in flight
 
-    def _scope(self):
+    def _scope(self, flush: bool = True):
         """Context in which torch's current stream is the forest's stream (the allocator callbacks allocate
         on the current stream).  Entering torch.cuda.stream() costs ~12 us, so it is skipped when the
-        caller already is on that stream - the common case."""
+        caller already is on that stream - the common case.  Every native call except the batched insert itself
+        first flushes the deferred CUDA-tensor inserts, so the native side always sees the poses in insertion order."""
+        if flush and self._batch:
+            self._flush()
         try:
             if self._torch._C._cuda_getCurrentRawStream(self.device.index) == self._raw_stream:
                 return _NULL_SCOPE
@@ -111,6 +116,7 @@ class Forest:
         return self._torch.cuda.stream(self._stream)
 
     def close(self):
+        self._batch = []
         if getattr(self, "_h", None) is not None and self._h:
             with self._scope():
                 self._lib.ol_forest_destroy(self._h)
@@ -124,15 +130,45 @@ class Forest:
 
     # ---- mutation ------------------------------------------------------------------------------
     def insert(self, points) -> int:
-        """Append one pose's cloud: numpy (n,3) array or a CUDA float64 tensor.  Returns pose index."""
+        """Append one pose's cloud: numpy (n,3) array or a CUDA float64 tensor.  Returns pose index.
+
+        CUDA tensors are not copied right away: they are collected (by reference) and handed to the native side in ONE
+        call before the next grid operation (`ol_forest_insert_batch`: one growth of the point array, one copy kernel
+        instead of a driver call per pose).  Do not modify such a tensor in place between `insert_points` and the next
+        operation on the grid."""
+        torch = self._torch
+        if isinstance(points, torch.Tensor) and points.device.type == "cuda":
+            t = points
+            if t.dtype != torch.float64 or not t.is_contiguous():
+                t = t.to(torch.float64).contiguous()
+            if t.dim() != 2 or t.shape[1] != 3:
+                t = t.reshape(-1, 3)
+            self._batch.append(t)
+            self.version += 1
+            return self._n_poses_native + len(self._batch) - 1
         out = C.c_int32(-1)
         src, n, on_dev, keep = self._as_source(points)
         with self._scope():
             N.check(self._lib.ol_forest_insert(self._h, src, n, on_dev, C.byref(out)))
         # a pinned host source is read asynchronously (csrc/forest_host.inl): keep it alive until the next synchronising call
         self._pending_sources.append(keep)
+        self._n_poses_native += 1
         self.version += 1
         return out.value
+
+    def _flush(self):
+        """Hand the deferred CUDA-tensor inserts to the native forest (one call)."""
+        batch, self._batch = self._batch, []
+        if not batch:
+            return
+        count = len(batch)
+        ptrs = (C.c_void_p * count)(*[t.data_ptr() for t in batch])
+        sizes = (C.c_int64 * count)(*[t.shape[0] for t in batch])
+        first = C.c_int32(-1)
+        with self._scope(flush=False):
+            N.check(self._lib.ol_forest_insert_batch(self._h, ptrs, sizes, count, C.byref(first)))
+        assert first.value == self._n_poses_native, (first.value, self._n_poses_native)
+        self._n_poses_native += count
 
     def insert_segments(self, points, seg_sizes, seg_pose, seg_first, n_poses_total: int):
         src, n, on_dev, keep = self._as_source(points)
@@ -143,6 +179,7 @@ class Forest:
             N.check(self._lib.ol_forest_insert_segments(self._h, src, n, on_dev, _ptr(ss), _ptr(sp), _ptr(sf), len(ss),
                                                         int(n_poses_total)))
         self._pending_sources.append(keep)
+        self._n_poses_native = max(self._n_poses_native, int(n_poses_total))
         self.version += 1
 
     def _as_source(self, points):

@@ -328,3 +328,33 @@ def test_edge_cases():
     g4.insert_points(0, np.array([[np.nan, 0, 0], [1.0, 2.0, 3.0]]))
     with pytest.raises(ValueError, match="NaN"):
         g4.n_points(0)
+
+
+def test_deferred_cuda_tensor_inserts_match_host_inserts():
+    """CUDA tensors are inserted by reference and flushed in one native call (ol_forest_insert_batch); mixing them with
+    host arrays, appending to a pose and querying in between must give exactly the grid built from host arrays."""
+    import torch
+
+    dev = torch.device("cuda", 0)
+    clouds = {p: lidar64_scan(p, seed=9)[::9] for p in range(5)}
+    a, b = Grid(GridConfig(voxel_edge_length=1.0)), Grid(GridConfig(voxel_edge_length=1.0))
+    for p, c in clouds.items():
+        a.insert_points(p, c)
+    b.insert_points(0, torch.from_numpy(clouds[0]).to(dev))
+    b.insert_points(1, torch.from_numpy(clouds[1]).to(dev))
+    b.insert_points(2, clouds[2])                                   # host array in the middle: flushes the batch first
+    b.insert_points(3, torch.from_numpy(clouds[3]).to(dev).to(torch.float32).to(torch.float64))  # values are float32-exact
+    assert b.n_points(3) == len(clouds[3])                          # a query flushes too
+    b.insert_points(4, torch.from_numpy(clouds[4]).to(dev))
+    with pytest.raises(ValueError, match="Cannot insert points to existing pose 4"):
+        b.insert_points(4, clouds[4])
+    for g in (a, b):
+        g.subdivide([MaxPoints(30)])
+    fa, fb = a._host.forest, b._host.forest
+    la, lb = fa.export_leaves(), fb.export_leaves()
+    assert (la["corner"] == lb["corner"]).all() and (la["edge"] == lb["edge"]).all()
+    ba, bb = fa.export_blocks(), fb.export_blocks()
+    for k in ("pose", "leaf", "size"):
+        assert (ba[k] == bb[k]).all()
+    pa, pb = fa.export_points(-1, order=0), fb.export_points(-1, order=0)
+    assert (pa["idx"] == pb["idx"]).all() and (pa["xyz"] == pb["xyz"]).all()
