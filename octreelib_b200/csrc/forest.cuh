@@ -136,7 +136,8 @@ struct Forest {
     void ensure_blocks();    // (pose, leaf) runs
     void filter(const uint8_t* keep_table, int64_t table_len, const int32_t* poses, int n_poses_listed);
     void apply_keep(const uint8_t* keep_pos);  // K7: drop positions with keep == 0
-    void compute_ref_order(const int32_t* pose_rank_host, DevBuf<uint32_t>& ref_order, DevBuf<int32_t>& d_pose_rank);
+    void compute_ref_order(const int32_t* pose_rank_host, DevBuf<uint32_t>& ref_order, DevBuf<int32_t>& d_pose_rank,
+                           DevBuf<uint32_t>* sorted_rank = nullptr);
     void ransac(const double* table_host, int H, int K, double threshold, const int32_t* pose_rank, int ppb, bool apply,
                 uint32_t flags);
     void apply_mask();

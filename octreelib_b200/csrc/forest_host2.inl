@@ -48,29 +48,48 @@ __global__ void block_sizes_ref_kernel(uint32_t nb, const uint32_t* __restrict__
     blk_size[b] = (int32_t)sz;
 }
 
-// first block of every batch of `ppb` consecutive pose ranks -> batch_base
-__global__ void batch_base_kernel(uint32_t nb, const uint32_t* __restrict__ ref_order, const int32_t* __restrict__ blk_pose,
-                                  const int32_t* __restrict__ pose_rank, int ppb, const uint32_t* __restrict__ refstart,
-                                  uint32_t* __restrict__ batch_base) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nb) return;
-    int batch = pose_rank[blk_pose[ref_order[j]]] / ppb;
-    if (j == 0 || pose_rank[blk_pose[ref_order[j - 1]]] / ppb != batch) batch_base[batch] = refstart[j];
-}
-
-__global__ void block_refstart_kernel(uint32_t nb, const uint32_t* __restrict__ ref_order, const int32_t* __restrict__ blk_pose,
-                                      const int32_t* __restrict__ pose_rank, int ppb, const uint32_t* __restrict__ refstart,
-                                      const uint32_t* __restrict__ batch_base, long long* __restrict__ blk_ref_start) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nb) return;
-    uint32_t b = ref_order[j];
-    int batch = pose_rank[blk_pose[b]] / ppb;
-    blk_ref_start[b] = (long long)refstart[j] - (long long)batch_base[batch];
-}
-
-__global__ void work_flags_kernel(uint32_t nb, const int32_t* __restrict__ blk_size, int K, uint32_t* __restrict__ flags) {
+// block sizes and "has at least K points" flags, in block-table order (coalesced)
+__global__ void block_size_flag_kernel(uint32_t nb, const uint32_t* __restrict__ blk_start, int K, int32_t* __restrict__ blk_size,
+                                       uint32_t* __restrict__ flags) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < nb) flags[b] = blk_size[b] >= K ? 1u : 0u;
+    if (b >= nb) return;
+    const uint32_t sz = blk_start[b + 1] - blk_start[b];
+    blk_size[b] = (int32_t)sz;
+    flags[b] = sz >= (uint32_t)K ? 1u : 0u;
+}
+
+__global__ void gather_sizes_kernel(uint32_t nb, const uint32_t* __restrict__ ref_order, const int32_t* __restrict__ blk_size,
+                                    uint32_t* __restrict__ sizes_ref) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nb) sizes_ref[j] = (uint32_t)blk_size[ref_order[j]];
+}
+
+// first point of every batch of `ppb` consecutive pose ranks: the reference positions are sorted by pose rank, so the
+// first block of batch t is found by bisection
+__global__ void batch_base_search_kernel(int n_batches, int ppb, uint32_t nb, const uint32_t* __restrict__ sorted_rank,
+                                         const uint32_t* __restrict__ refstart, uint32_t* __restrict__ batch_base) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_batches) return;
+    const uint32_t want = (uint32_t)t * (uint32_t)ppb;
+    uint32_t lo = 0, hi = nb;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (sorted_rank[mid] < want)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    batch_base[t] = lo < nb ? refstart[lo] : 0u;
+}
+
+// reference start index (cuda_ransac.py:65-67, per batch) of the blocks that will be fitted; the others never use it
+__global__ void work_refstart_kernel(uint32_t nb, int K, int ppb, const uint32_t* __restrict__ ref_order,
+                                     const uint32_t* __restrict__ sorted_rank, const uint32_t* __restrict__ sizes_ref,
+                                     const uint32_t* __restrict__ refstart, const uint32_t* __restrict__ batch_base,
+                                     long long* __restrict__ blk_ref_start) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nb || sizes_ref[j] < (uint32_t)K) return;
+    blk_ref_start[ref_order[j]] = (long long)refstart[j] - (long long)batch_base[sorted_rank[j] / (uint32_t)ppb];
 }
 
 __global__ void work_emit_kernel(uint32_t nb, const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan_ex,
@@ -214,7 +233,8 @@ __global__ void export_points_kernel(uint32_t n, int pose, int dfs, const uint32
 // ---------------------------------------------------------------------------------------------
 // block order of the reference: (pose rank, leaf enumeration order)   grid.py:173-191, 217-232
 // ---------------------------------------------------------------------------------------------
-void Forest::compute_ref_order(const int32_t* pose_rank_host, DevBuf<uint32_t>& ref_order, DevBuf<int32_t>& d_pose_rank) {
+void Forest::compute_ref_order(const int32_t* pose_rank_host, DevBuf<uint32_t>& ref_order, DevBuf<int32_t>& d_pose_rank,
+                               DevBuf<uint32_t>* sorted_rank) {
     ensure_order();
     ensure_blocks();
     std::vector<int32_t> pr(std::max(n_poses, 1));
@@ -227,8 +247,10 @@ void Forest::compute_ref_order(const int32_t* pose_rank_host, DevBuf<uint32_t>& 
     d_pose_rank.reset(ctx, pr.size());
     h2d(ctx, d_pose_rank.get(), pr.data(), pr.size());
     ctx.sync();
-    ref_order.reset(ctx, NB);
-    if (NB == 0) return;
+    if (NB == 0) {
+        ref_order.reset(ctx, 0);
+        return;
+    }
     DevBuf<uint32_t> k0(ctx, NB), k1(ctx, NB), v0(ctx, NB), v1(ctx, NB), cnt_c(ctx, L), off_c(ctx, L), first_b(ctx, L);
     cnt_c.zero();
     {
@@ -244,7 +266,8 @@ void Forest::compute_ref_order(const int32_t* pose_rank_host, DevBuf<uint32_t>& 
         OL_CHECK_LAUNCH();
     }
     const int w = radix_sort_pairs<uint32_t>(ctx, k0.get(), k1.get(), v0.get(), v1.get(), NB, 0, bit_length_u64((uint64_t)max_rank));
-    d2d(ctx, ref_order.get(), w ? v1.get() : v0.get(), NB);
+    ref_order.swap(w ? v1 : v0);
+    if (sorted_rank) sorted_rank->swap(w ? k1 : k0);  // pose rank of the block at every reference position
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -257,9 +280,9 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
     OL_REQUIRE(H <= 1024, OL_ERR_INVALID, "Number of RANSAC hypotheses must be <= 1024 because of the CUDA thread limit.");
     OL_REQUIRE(K >= 1 && K <= 64, OL_ERR_INVALID, "initial_points_number must be in 1..64");
     OL_REQUIRE(ppb >= 1, OL_ERR_INVALID, "poses_per_batch must be positive");
-    DevBuf<uint32_t> ref_order;
+    DevBuf<uint32_t> ref_order, sorted_rank;
     DevBuf<int32_t> d_pose_rank;
-    compute_ref_order(pose_rank, ref_order, d_pose_rank);
+    compute_ref_order(pose_rank, ref_order, d_pose_rank, &sorted_rank);
     drop_snapshot();
     res_n = NB;
     mask.reset(ctx, A);
@@ -273,34 +296,25 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
     int max_rank = 0;
     for (int p = 0; p < n_poses; ++p) max_rank = std::max(max_rank, pose_rank ? pose_rank[p] : p);
     const int n_batches = max_rank / ppb + 1;
-    DevBuf<uint32_t> sizes_ref(ctx, NB), refstart(ctx, NB), refpos(ctx, NB), batch_base(ctx, n_batches), wflags(ctx, NB),
-        wscan(ctx, NB);
+    DevBuf<uint32_t> sizes_ref(ctx, NB), refstart(ctx, NB), batch_base(ctx, n_batches), wflags(ctx, NB), wscan(ctx, NB);
     DevBuf<int32_t> blk_size(ctx, NB);
     DevBuf<long long> blk_ref_start(ctx, NB);
     DevBuf<unsigned long long> d_total(ctx, 1);
-    batch_base.zero();
     {
         ProfScope ps(ctx, "ransac_prep");
-        block_sizes_ref_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_start.get(), sizes_ref.get(), refpos.get(),
-                                                                 blk_size.get());
+        block_size_flag_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_start.get(), K, blk_size.get(), wflags.get());
+        OL_CHECK_LAUNCH();
+        gather_sizes_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_size.get(), sizes_ref.get());
         OL_CHECK_LAUNCH();
     }
     exclusive_scan_u32(ctx, sizes_ref.get(), refstart.get(), NB, nullptr);
     {
         ProfScope ps(ctx, "ransac_prep");
-        batch_base_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), d_pose_rank.get(), ppb,
-                                                            refstart.get(), batch_base.get());
+        batch_base_search_kernel<<<nblk((size_t)n_batches), 256, 0, ctx.stream>>>(n_batches, ppb, NB, sorted_rank.get(), refstart.get(),
+                                                                                  batch_base.get());
         OL_CHECK_LAUNCH();
-    }
-    {
-        ProfScope ps(ctx, "ransac_prep");
-        block_refstart_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), d_pose_rank.get(), ppb,
-                                                                refstart.get(), batch_base.get(), blk_ref_start.get());
-        OL_CHECK_LAUNCH();
-    }
-    {
-        ProfScope ps(ctx, "ransac_prep");
-        work_flags_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_size.get(), K, wflags.get());
+        work_refstart_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, K, ppb, ref_order.get(), sorted_rank.get(), sizes_ref.get(),
+                                                               refstart.get(), batch_base.get(), blk_ref_start.get());
         OL_CHECK_LAUNCH();
     }
     exclusive_scan_u32(ctx, wflags.get(), wscan.get(), NB, d_total.get());
