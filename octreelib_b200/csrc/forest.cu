@@ -62,34 +62,20 @@ __device__ __forceinline__ void unpack_cell(const KeyParams& kp, uint64_t ckey, 
     q[2] = kp.qmin[2] + (long long)key_field(ckey, s2, s1);
 }
 
-// Batched insert: copies `count` device clouds (pointer table) into the raw point array in one launch, one thread per
-// double; dst_start[c] = first destination double of cloud c (count + 1 entries).
-__global__ void __launch_bounds__(256) insert_batch_kernel(const double* const* __restrict__ src, const unsigned long long* __restrict__ dst_start,
-                                                           int count, double* __restrict__ dst) {
-    const unsigned long long total = dst_start[count];
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        // clouds have similar sizes: interpolated guess, then bisection of what is left
-        int lo = 0, hi = count;  // dst_start[lo] <= e < dst_start[hi]
-        int c = (int)((double)e * (double)count / (double)total);
-        c = c < 0 ? 0 : (c >= count ? count - 1 : c);
-        if (dst_start[c] <= e && e < dst_start[c + 1]) {
-            lo = c;
-        } else {
-            if (dst_start[c] > e)
-                hi = c;
-            else
-                lo = c + 1;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (dst_start[mid] <= e)
-                    lo = mid;
-                else
-                    hi = mid;
-            }
-        }
-        dst[e] = src[lo][e - dst_start[lo]];
-    }
+// Batched insert: copies many device clouds into the raw point array in one launch.  The host cuts the clouds into
+// chunks of at most INSERT_CHUNK doubles; CTA c copies chunk c (plain coalesced loop, no per-element search).
+constexpr unsigned INSERT_CHUNK = 1u << 15;
+struct InsertChunk {
+    const double* src;
+    unsigned long long dst;  // first destination double
+    unsigned len;
+    unsigned pad;
+};
+__global__ void __launch_bounds__(256) insert_batch_kernel(const InsertChunk* __restrict__ chunks, double* __restrict__ dst) {
+    const InsertChunk c = chunks[blockIdx.x];
+    const double* __restrict__ s = c.src;
+    double* __restrict__ d = dst + c.dst;
+    for (unsigned e = threadIdx.x; e < c.len; e += 256) d[e] = s[e];
 }
 
 // Morton codes are stored as 32-bit words while at most MORTON32_MAX_DEPTH levels are encoded (3 bits per level + the

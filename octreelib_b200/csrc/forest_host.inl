@@ -194,10 +194,15 @@ int Forest::insert_batch(const double* const* xyz_dev, const int64_t* sizes, int
         }
         cap = ncap;
     }
-    std::vector<unsigned long long> dst_start((size_t)count + 1, 0);
+    std::vector<InsertChunk> chunks;
+    chunks.reserve(total * 3 / INSERT_CHUNK + (size_t)count + 1);
     size_t r = N;
+    unsigned long long dst = 0;
     for (int c = 0; c < count; ++c) {
-        dst_start[c + 1] = dst_start[c] + (unsigned long long)sizes[c] * 3ull;
+        const unsigned long long len = (unsigned long long)sizes[c] * 3ull;
+        for (unsigned long long off = 0; off < len; off += INSERT_CHUNK)
+            chunks.push_back(InsertChunk{xyz_dev[c] + off, dst + off, (unsigned)std::min<unsigned long long>(INSERT_CHUNK, len - off), 0u});
+        dst += len;
         seg_pose.push_back(n_poses);
         seg_first.push_back(0);
         seg_start.back() = (uint32_t)r;
@@ -205,16 +210,13 @@ int Forest::insert_batch(const double* const* xyz_dev, const int64_t* sizes, int
         seg_start.push_back((uint32_t)r);
         n_poses += 1;
     }
-    if (total) {
-        DevBuf<const double*> d_src(ctx, (size_t)count);
-        DevBuf<unsigned long long> d_start(ctx, (size_t)count + 1);
-        h2d(ctx, d_src.get(), xyz_dev, (size_t)count);
-        h2d(ctx, d_start.get(), dst_start.data(), (size_t)count + 1);
-        const unsigned g = std::min<unsigned>(nblk(total * 3), (unsigned)ctx.num_sms * 16);
+    if (!chunks.empty()) {
+        DevBuf<InsertChunk> d_chunks(ctx, chunks.size());
+        h2d(ctx, d_chunks.get(), chunks.data(), chunks.size());
         ProfScope ps(ctx, "insert_batch", (double)total);
-        insert_batch_kernel<<<g, 256, 0, ctx.stream>>>(d_src.get(), d_start.get(), count, P64.get() + N * 3);
+        insert_batch_kernel<<<(unsigned)chunks.size(), 256, 0, ctx.stream>>>(d_chunks.get(), P64.get() + N * 3);
         OL_CHECK_LAUNCH();
-        ctx.sync();  // the pageable host tables above and the caller's tensors may be released after return
+        ctx.sync();  // the pageable chunk table above and the caller's tensors may be released after return
     }
     N += total;
     built = false;

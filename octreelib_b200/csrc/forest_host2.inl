@@ -107,18 +107,19 @@ __global__ void work_sizes_kernel(uint32_t n_work, const uint32_t* __restrict__ 
 
 // K5b: gather ONLY the points of the fitted blocks, block after block, so that every block is one contiguous float64
 // run for the TMA staging (most (pose, leaf) blocks of a LiDAR map are smaller than K and never reach the kernel).
-// One warp per work item; a flat thread-per-double copy inside it.
+// Eight lanes per work item; a flat thread-per-double copy inside it.
 __global__ void __launch_bounds__(256) gather_blocks_kernel(uint32_t n_work, const uint32_t* __restrict__ work,
                                                             const uint32_t* __restrict__ blk_start, const int32_t* __restrict__ blk_size,
                                                             const uint32_t* __restrict__ pk_start, const double* __restrict__ xyz,
                                                             const uint32_t* __restrict__ perm, double* __restrict__ out) {
-    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // 8 lanes per work item (fitted blocks of a LiDAR map hold ~7 points = 21 doubles)
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     if (w >= n_work) return;
-    const int lane = threadIdx.x & 31;
+    const uint32_t sub = threadIdx.x & 7u;
     const uint32_t b = work[w];
     const uint32_t src0 = blk_start[b], dst0 = pk_start[w];
     const uint32_t n3 = (uint32_t)blk_size[b] * 3u;
-    for (uint32_t e = lane; e < n3; e += 32) {
+    for (uint32_t e = sub; e < n3; e += 8) {
         const uint32_t j = e / 3u, c = e - j * 3u;
         out[(size_t)dst0 * 3 + e] = xyz[(size_t)perm[src0 + j] * 3 + c];
     }
@@ -337,7 +338,7 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
     DevBuf<double> pleaf(ctx, (size_t)n_packed * 3 + 2);
     if (n_work) {
         ProfScope ps(ctx, "gather_points", (double)n_packed);
-        gather_blocks_kernel<<<nblk((size_t)n_work * 32), 256, 0, ctx.stream>>>(n_work, work.get(), blk_start.get(), blk_size.get(),
+        gather_blocks_kernel<<<nblk((size_t)n_work * 8), 256, 0, ctx.stream>>>(n_work, work.get(), blk_start.get(), blk_size.get(),
                                                                                 pk_start.get(), P64.get(), perm.get(), pleaf.get());
         OL_CHECK_LAUNCH();
     }
