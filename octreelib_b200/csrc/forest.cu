@@ -62,20 +62,47 @@ __device__ __forceinline__ void unpack_cell(const KeyParams& kp, uint64_t ckey, 
     q[2] = kp.qmin[2] + (long long)key_field(ckey, s2, s1);
 }
 
-// Batched insert: copies many device clouds into the raw point array in one launch.  The host cuts the clouds into
-// chunks of at most INSERT_CHUNK doubles; CTA c copies chunk c (plain coalesced loop, no per-element search).
-constexpr unsigned INSERT_CHUNK = 1u << 15;
+// Batched insert: copies many device clouds into the raw point array in one launch AND folds them into the bounding
+// box / non-finite check (K0) on the way, so the separate pass over the new points is not needed.  The host cuts the
+// clouds into chunks of at most INSERT_CHUNK doubles (a multiple of 3, like every cloud and the thread count), so each
+// thread of CTA c - which copies chunk c with a plain coalesced loop - only ever sees one axis.
+constexpr unsigned INSERT_CHUNK = 3u * 10920u;
+constexpr int INSERT_THREADS = 192;
 struct InsertChunk {
     const double* src;
     unsigned long long dst;  // first destination double
     unsigned len;
     unsigned pad;
 };
-__global__ void __launch_bounds__(256) insert_batch_kernel(const InsertChunk* __restrict__ chunks, double* __restrict__ dst) {
+__global__ void __launch_bounds__(INSERT_THREADS) insert_batch_kernel(const InsertChunk* __restrict__ chunks, double* __restrict__ dst,
+                                                                      long long* __restrict__ bbox, uint32_t* __restrict__ err) {
     const InsertChunk c = chunks[blockIdx.x];
     const double* __restrict__ s = c.src;
     double* __restrict__ d = dst + c.dst;
-    for (unsigned e = threadIdx.x; e < c.len; e += 256) d[e] = s[e];
+    long long mn = LLONG_MAX, mx = LLONG_MIN;
+    bool bad = false;
+    for (unsigned e = threadIdx.x; e < c.len; e += INSERT_THREADS) {
+        const double v = s[e];
+        d[e] = v;
+        if (!isfinite(v)) bad = true;
+        const long long k = double_to_ordered(v);
+        mn = k < mn ? k : mn;
+        mx = k > mx ? k : mx;
+    }
+    __shared__ long long s_mn[INSERT_THREADS], s_mx[INSERT_THREADS];
+    s_mn[threadIdx.x] = mn;
+    s_mx[threadIdx.x] = mx;
+    __syncthreads();
+    if (threadIdx.x < 3) {  // axis a = threadIdx.x (chunk starts are multiples of 3)
+        long long lo = LLONG_MAX, hi = LLONG_MIN;
+        for (int t = threadIdx.x; t < INSERT_THREADS; t += 3) {
+            lo = s_mn[t] < lo ? s_mn[t] : lo;
+            hi = s_mx[t] > hi ? s_mx[t] : hi;
+        }
+        if (lo != LLONG_MAX) atomicMin(&bbox[threadIdx.x], lo);
+        if (hi != LLONG_MIN) atomicMax(&bbox[3 + threadIdx.x], hi);
+    }
+    if (bad) atomicOr(err, (uint32_t)DEVERR_NONFINITE);
 }
 
 // Morton codes are stored as 32-bit words while at most MORTON32_MAX_DEPTH levels are encoded (3 bits per level + the

@@ -214,10 +214,12 @@ int Forest::insert_batch(const double* const* xyz_dev, const int64_t* sizes, int
         DevBuf<InsertChunk> d_chunks(ctx, chunks.size());
         h2d(ctx, d_chunks.get(), chunks.data(), chunks.size());
         ProfScope ps(ctx, "insert_batch", (double)total);
-        insert_batch_kernel<<<(unsigned)chunks.size(), 256, 0, ctx.stream>>>(d_chunks.get(), P64.get() + N * 3);
+        insert_batch_kernel<<<(unsigned)chunks.size(), INSERT_THREADS, 0, ctx.stream>>>(d_chunks.get(), P64.get() + N * 3, d_bbox.get(),
+                                                                                        d_err.get());
         OL_CHECK_LAUNCH();
         ctx.sync();  // the pageable chunk table above and the caller's tensors may be released after return
     }
+    if (bbox_done == N) bbox_done = N + total;  // the copy kernel already folded the batch into the bounding box
     N += total;
     built = false;
     shaped = false;
