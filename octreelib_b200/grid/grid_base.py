@@ -54,17 +54,14 @@ class GridConfigBase(ABC):
     corner: Point = field(default_factory=lambda: np.array(([0.0, 0.0, 0.0])))
 
     def __post_init__(self):
-        # messages pinned by test/grid/test_grid.py:148-182
-        if not issubclass(self.octree_manager_type, OctreeManager):
-            raise TypeError(
-                f"Cannot use the provided octree manager type {self.octree_manager_type.__name__}. "
-                "It has to be a subclass of octree_manager.OctreeManager."
-            )
-        if not issubclass(self.octree_type, OctreeBase):
-            raise TypeError(
-                f"Cannot use the provided octree type {self.octree_type.__name__}. "
-                "It has to be a subclass of octree.OctreeBase."
-            )
+        # same checks and messages as grid_base.py:73-87 (the messages are pinned by test/grid/test_grid.py:148-182)
+        plug_points = (
+            (self.octree_manager_type, OctreeManager, "octree manager type", "octree_manager.OctreeManager"),
+            (self.octree_type, OctreeBase, "octree type", "octree.OctreeBase"),
+        )
+        for given, required, what, where in plug_points:
+            if not issubclass(given, required):
+                raise TypeError(f"Cannot use the provided {what} {given.__name__}. It has to be a subclass of {where}.")
 
 
 class GridBase(ABC, Generic[T]):

@@ -6,15 +6,19 @@ __all__ = ["WithID"]
 
 
 class WithID(ABC):
-    """`.id` is either the id handed to the constructor or the next value of a process-wide counter."""
+    """`.id` is either the id handed to the constructor or the next value of a process-wide counter
+    (`WithID._id_static_counter`, shared by every subclass exactly like in the reference)."""
 
     _id_static_counter = 0
 
+    @staticmethod
+    def _draw_id() -> int:
+        drawn = WithID._id_static_counter
+        WithID._id_static_counter = drawn + 1
+        return drawn
+
     def __init__(self, _id: Optional[int] = None):
-        if _id is None:
-            _id = WithID._id_static_counter
-            WithID._id_static_counter += 1
-        self._id = _id
+        self._id = WithID._draw_id() if _id is None else _id
 
     @property
     def id(self):
