@@ -303,7 +303,18 @@ def cpu_reference_sample(workload, n_sample_points, threads):
     return dict(points=n, seconds=t2 - t0, structure_s=t1 - t0, ransac_s=t2 - t1, poses=len(clouds))
 
 
+def _claim_stdout():
+    """The driver reads ONE JSON line from stdout, but libraries write there too (NCCL prints its version banner to
+    stdout during communicator creation).  Point file descriptor 1 at stderr for the whole run and keep a private
+    duplicate of the real stdout for the result line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    result_out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -346,7 +357,7 @@ def main():
                                            f"(numpy, like the reference), RANSAC on {threads} threads (C port)"},
                    e2e={"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                    gpu_launches=0)
-        print(json.dumps(out))
+        print(json.dumps(out), file=result_out, flush=True)
         return 0
 
     # ---------------------------------------------------------------- this build -----------------
@@ -485,7 +496,7 @@ def main():
         out["cpu_baseline"] = {"value": r["points"] / r["seconds"], "unit": "points/s", "cores": 1, "kind": "port",
                                "sample": f"{r['points']} points ({r['poses']} poses) of {args.workload}: "
                                          f"structure {r['structure_s']:.2f} s + RANSAC {r['ransac_s']:.2f} s, 1 thread"}
-    print(json.dumps(out))
+    print(json.dumps(out), file=result_out, flush=True)
     if world > 1:
         dist.barrier()
     return 0
