@@ -68,7 +68,7 @@ typedef struct ol_forest_stats {
     int64_t n_points_alive;    /* after filter / RANSAC masks */
     int64_t n_poses;
     int64_t n_cells;
-    int64_t n_cell_poses;  /* (cell, pose) pairs that own an octree */
+    int64_t n_cell_poses;  /* (cell, pose) pairs that own an octree (-1 from ol_forest_stats_light while not built) */
     int64_t n_leaves;      /* leaves of the shared per-cell tree shape, empty ones included */
     int64_t n_internal;    /* internal (split) nodes */
     int64_t n_blocks;      /* non-empty (pose, leaf) pairs = RANSAC blocks */

@@ -154,8 +154,8 @@ template <typename MortT>
 __global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ xyz, uint32_t n, KeyParams kp,
                                                      const uint32_t* __restrict__ seg_start,
                                                      const int32_t* __restrict__ seg_pose, int n_seg,
-                                                     uint64_t* __restrict__ keys, MortT* __restrict__ mort,
-                                                     uint32_t* __restrict__ err) {
+                                                     uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                     MortT* __restrict__ mort, uint32_t* __restrict__ err) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     double p[3] = {xyz[(size_t)r * 3 + 0], xyz[(size_t)r * 3 + 1], xyz[(size_t)r * 3 + 2]};
@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ 
     MortT m = (MortT)point_morton(p, c, kp.edge, kp.depth, &bad);
     if (bad < kp.depth) m |= MortBits<MortT>::bad;
     keys[r] = key;
+    vals[r] = r;  // the sort's payload: the point's rank
     mort[r] = m;
     if (e) atomicOr(err, e);
 }

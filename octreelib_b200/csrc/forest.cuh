@@ -50,6 +50,7 @@ struct Forest {
     DevBuf<uint64_t> cell_key;   // [C] packed cell key (without pose bits)
     DevBuf<uint32_t> cell_start0;// [C+1]
     uint32_t CP = 0;
+    bool cp_valid = false;       // cp_* / cell_first_pose built (lazily: ensure_cell_poses)
     DevBuf<uint32_t> cp_cell;    // [CP]
     DevBuf<int32_t> cp_pose;     // [CP]
     DevBuf<int32_t> cell_first_pose;  // [C]
@@ -122,6 +123,7 @@ struct Forest {
                const int64_t* seg_first_in, int n_segments, int n_poses_total);
     int insert_batch(const double* const* xyz_dev, const int64_t* sizes, int count);  // many device clouds, one copy kernel
     void build();            // K1-K3: keygen, sort, cells
+    void ensure_cell_poses();  // (cell, pose) pairs of the base order
     void compact_base();     // drop dead points from the base order
     void extend_morton();    // Morton codes at the full depth (lazy: MORTON_INITIAL_DEPTH levels first)
     void reset_shape();      // current := base (every cell one leaf)

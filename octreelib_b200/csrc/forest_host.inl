@@ -285,6 +285,7 @@ void Forest::build() {
         cp_cell.reset(ctx, 0);
         cp_pose.reset(ctx, 0);
         cell_first_pose.reset(ctx, 0);
+        cp_valid = true;
         built = true;
         base_dirty = false;
         return;
@@ -295,14 +296,12 @@ void Forest::build() {
         ProfScope ps(ctx, "keygen", (double)n);
         if (mort32)
             keygen_kernel<uint32_t><<<nblk(n), 256, 0, ctx.stream>>>(P64.get(), n, kp, d_seg_start.get(), d_seg_pose.get(), S, keys0.get(),
-                                                                     reinterpret_cast<uint32_t*>(mort_r.get()), d_err.get());
+                                                                     vals0.get(), reinterpret_cast<uint32_t*>(mort_r.get()), d_err.get());
         else
             keygen_kernel<uint64_t><<<nblk(n), 256, 0, ctx.stream>>>(P64.get(), n, kp, d_seg_start.get(), d_seg_pose.get(), S, keys0.get(),
-                                                                     mort_r.get(), d_err.get());
+                                                                     vals0.get(), mort_r.get(), d_err.get());
         OL_CHECK_LAUNCH();
     }
-    iota_kernel<<<nblk(n), 256, 0, ctx.stream>>>(vals0.get(), n, 0);
-    OL_CHECK_LAUNCH();
     int which = radix_sort_pairs<uint64_t>(ctx, keys0.get(), keys1.get(), vals0.get(), vals1.get(), n, 0, key_bits, true);
     if (which) {
         keys0.swap(keys1);
@@ -326,6 +325,7 @@ void Forest::build() {
     // K3: cells = runs of equal cell key; (cell, pose) pairs = runs of equal (cell, pose) (octree_manager.py:166-169)
     DevBuf<unsigned long long> d_total(ctx, 1);
     DevBuf<uint32_t> tile_off;
+    CP = 0;
     {
         const CellKeyFn key{keys0.get(), kp.pose_bits};
         {
@@ -341,28 +341,41 @@ void Forest::build() {
     }
     OL_CUDA(cudaMemcpyAsync(cell_start0.get() + C, &n, 4, cudaMemcpyHostToDevice, ctx.stream));
     keys0.release();
-    {
-        const GroupPoseKeyFn key{cellidx0.get(), perm0.get(), d_seg_start.get(), d_seg_pose.get(), S};
-        {
-            ProfScope ps(ctx, "cell_poses", (double)n);
-            segment_runs_count(ctx, key, n, tile_off, d_total.get());
-        }
-        CP = (uint32_t)read_u64(d_total.get());
-        cp_cell.reset(ctx, CP);
-        cp_pose.reset(ctx, CP);
-        cell_first_pose.reset(ctx, C);
-        ProfScope ps(ctx, "cell_poses", (double)n);
-        segment_runs_emit(ctx, key, CellPoseEmitFn{cp_cell.get(), cp_pose.get(), cell_first_pose.get(), cellidx0.get()}, n, tile_off,
-                          nullptr);
-    }
+    cp_valid = false;  // the (cell, pose) table is built on first use (ensure_cell_poses)
     check_device_errors();
     built = true;
     base_dirty = any_dead;  // points removed before a rebuild are dropped from the base order lazily
 }
 
+// (cell, pose) pairs = runs of equal (cell, pose) in the base order (octree_manager.py:166-169).  Only the node counters
+// and the cell exports read the table, so it is built on first use - but always before the base order loses points, because
+// a pose keeps its octree in a cell after its points are filtered away.
+void Forest::ensure_cell_poses() {
+    if (cp_valid) return;
+    const uint32_t n = A0;
+    DevBuf<unsigned long long> d_total(ctx, 1);
+    DevBuf<uint32_t> tile_off;
+    const GroupPoseKeyFn key{cellidx0.get(), perm0.get(), d_seg_start.get(), d_seg_pose.get(), (int)seg_pose.size()};
+    {
+        ProfScope ps(ctx, "cell_poses", (double)n);
+        segment_runs_count(ctx, key, n, tile_off, d_total.get());
+    }
+    CP = (uint32_t)read_u64(d_total.get());
+    cp_cell.reset(ctx, CP);
+    cp_pose.reset(ctx, CP);
+    cell_first_pose.reset(ctx, C);
+    {
+        ProfScope ps(ctx, "cell_poses", (double)n);
+        segment_runs_emit(ctx, key, CellPoseEmitFn{cp_cell.get(), cp_pose.get(), cell_first_pose.get(), cellidx0.get()}, n, tile_off,
+                          nullptr);
+    }
+    cp_valid = true;
+}
+
 // drop dead points from the base order (cells keep their index even when they become empty)
 void Forest::compact_base() {
     if (!base_dirty) return;
+    ensure_cell_poses();
     const uint32_t n = A0;
     if (n) {
         DevBuf<uint32_t> flags(ctx, n), scan(ctx, n);

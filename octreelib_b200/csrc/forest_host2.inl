@@ -451,6 +451,7 @@ void Forest::apply_pose_mask(const int32_t* pose_rank, int pose, const uint8_t* 
 // ---------------------------------------------------------------------------------------------
 void Forest::pose_counts(int64_t* out_host) {
     ensure_blocks();
+    ensure_cell_poses();
     const int P = std::max(n_poses, 1);
     DevBuf<unsigned long long> counts(ctx, (size_t)P * 3);
     counts.zero();
@@ -479,13 +480,14 @@ void Forest::stats(ol_forest_stats* s, bool light) {
         ctx.sync();
     } else {
         ensure_blocks();
+        ensure_cell_poses();
     }
     memset(s, 0, sizeof(*s));
     s->n_points_inserted = (int64_t)N;
     s->n_points_alive = A;
     s->n_poses = n_poses;
     s->n_cells = C;
-    s->n_cell_poses = CP;
+    s->n_cell_poses = cp_valid ? (int64_t)CP : -1;
     s->n_leaves = L;
     s->n_internal = I;
     s->n_blocks = blocks_valid ? (int64_t)NB : -1;
@@ -537,6 +539,7 @@ static void copy_out(Ctx& ctx, T* host, const T* dev, size_t n) {
 
 void Forest::export_cells(int64_t* q, double* corner, int32_t* first_pose, int64_t* n_nodes, int64_t* leaf_begin) {
     ensure_order();
+    ensure_cell_poses();
     DevBuf<long long> dq(ctx, (size_t)C * 3), dn(ctx, C), dl(ctx, (size_t)C + 1);
     DevBuf<double> dc(ctx, (size_t)C * 3);
     cell_export_kernel<<<nblk((size_t)C + 1), 256, 0, ctx.stream>>>(C, cell_key.get(), kp, cell_leaf_begin.get(), dq.get(),
@@ -552,6 +555,7 @@ void Forest::export_cells(int64_t* q, double* corner, int32_t* first_pose, int64
 
 void Forest::export_cell_poses(int32_t* cell, int32_t* pose) {
     build();
+    ensure_cell_poses();
     copy_out(ctx, (uint32_t*)cell, cp_cell.get(), CP);
     copy_out(ctx, pose, cp_pose.get(), CP);
     ctx.sync();
