@@ -267,48 +267,108 @@ struct BlockEmitFn {  // non-empty (pose, leaf) blocks
 };
 
 // =============================================================================================
-// generic keep-flag compaction of the per-position arrays
+// keep-flag compaction of the per-position arrays (K7: apply_keep, compact_base)
+//   keep_bits_kernel     keep bytes -> one bit word per 32 positions + the kept count of every 2048-position tile
+//   (exclusive scan of the tile counts; total = kept positions)
+//   compact_move_kernel  ranks inside the tile from the bit words (64 words per tile), moves perm / mort / aux and
+//                        leaves word_off[] = new position of every word's first kept element
+//   remap_starts_kernel  new_start[k] = word_off[s >> 5] + popc(bits[s >> 5] below bit s & 31),  s = old_start[k]
+// Traffic: 1 B + 12 B read per position, 12 B written per kept position, 8 B of tables per 32 positions.
 // =============================================================================================
-__global__ void keep_to_u32_kernel(const uint8_t* __restrict__ keep, uint32_t n, uint32_t* __restrict__ flags) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flags[i] = keep[i] ? 1u : 0u;
-}
+constexpr int CMP_THREADS = 256;
+constexpr int CMP_TILE = 2048;
+constexpr int CMP_WORDS = CMP_TILE / 32;
 
-__global__ void alive_flags_kernel(const uint8_t* __restrict__ alive_r, const uint32_t* __restrict__ perm, uint32_t n,
-                                   uint32_t* __restrict__ flags) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flags[i] = alive_r[perm[i]] ? 1u : 0u;
+// keep bit of position i = keep[via ? via[i] : i]
+__global__ void __launch_bounds__(CMP_THREADS) keep_bits_kernel(const uint8_t* __restrict__ keep, const uint32_t* __restrict__ via,
+                                                                uint32_t n, uint32_t* __restrict__ bits,
+                                                                uint32_t* __restrict__ tile_cnt) {
+    __shared__ uint32_t s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * CMP_TILE;
+    const int lane = threadIdx.x & 31;
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < CMP_TILE / CMP_THREADS; ++j) {
+        const uint32_t i = base + j * CMP_THREADS + threadIdx.x;
+        bool k = false;
+        if (i < n) k = keep[via ? via[i] : i] != 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, k);
+        if (lane == 0 && i < n) {
+            bits[i >> 5] = m;
+            c += __popc(m);
+        }
+    }
+    if (lane == 0 && c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = s_cnt;
 }
 
 template <typename MortT>
-__global__ void compact_pos_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan_ex, uint32_t n,
-                                   const uint32_t* __restrict__ perm_in, const MortT* __restrict__ mort_in,
-                                   const uint32_t* __restrict__ aux_in, uint32_t* __restrict__ perm_out,
-                                   MortT* __restrict__ mort_out, uint32_t* __restrict__ aux_out,
-                                   uint8_t* __restrict__ alive_r) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (flags[i]) {
-        uint32_t j = scan_ex[i];
-        perm_out[j] = perm_in[i];
-        mort_out[j] = mort_in[i];
-        aux_out[j] = aux_in[i];
-    } else if (alive_r) {
-        alive_r[perm_in[i]] = 0;
+__global__ void __launch_bounds__(CMP_THREADS) compact_move_kernel(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ tile_off,
+                                                                   uint32_t n, const uint32_t* __restrict__ perm_in,
+                                                                   const MortT* __restrict__ mort_in, const uint32_t* __restrict__ aux_in,
+                                                                   uint32_t* __restrict__ perm_out, MortT* __restrict__ mort_out,
+                                                                   uint32_t* __restrict__ aux_out, uint32_t* __restrict__ word_off) {
+    __shared__ uint32_t s_mask[CMP_WORDS], s_off[CMP_WORDS], s_half;
+    const uint32_t base = blockIdx.x * CMP_TILE;
+    const uint32_t n_words = (n + 31) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < CMP_WORDS) {  // warps 0 and 1: exclusive scan of the 64 word counts
+        const uint32_t w = (base >> 5) + threadIdx.x;
+        const uint32_t m = w < n_words ? bits[w] : 0u;
+        const uint32_t c = __popc(m);
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += v;
+        }
+        if (threadIdx.x == 31) s_half = inc;
+        s_mask[threadIdx.x] = m;
+        s_off[threadIdx.x] = inc - c;
+    }
+    __syncthreads();
+    if (threadIdx.x < CMP_WORDS) {
+        const uint32_t off = tile_off[blockIdx.x] + s_off[threadIdx.x] + (warp ? s_half : 0u);
+        s_off[threadIdx.x] = off;
+        const uint32_t w = (base >> 5) + threadIdx.x;
+        if (w < n_words) word_off[w] = off;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < CMP_TILE / CMP_THREADS; ++j) {
+        const uint32_t i = base + j * CMP_THREADS + threadIdx.x;
+        const int w = j * (CMP_THREADS / 32) + warp;
+        const uint32_t m = s_mask[w];
+        if (i < n && ((m >> lane) & 1u)) {
+            const uint32_t dst = s_off[w] + __popc(m & ((1u << lane) - 1u));
+            perm_out[dst] = perm_in[i];
+            mort_out[dst] = mort_in[i];
+            aux_out[dst] = aux_in[i];
+        }
     }
 }
 
-// new_start[k] = scan_ex[old_start[k]] (k < m), new_start[m] = total
-__global__ void remap_starts_kernel(const uint32_t* __restrict__ old_start, const uint32_t* __restrict__ scan_ex,
-                                    uint32_t m, uint32_t n_old, uint32_t total, uint32_t* __restrict__ new_start) {
+// new_start[k] = kept positions before old_start[k] (k < m), new_start[m] = total
+__global__ void remap_starts_kernel(const uint32_t* __restrict__ old_start, const uint32_t* __restrict__ bits,
+                                    const uint32_t* __restrict__ word_off, uint32_t m, uint32_t n_old, uint32_t total,
+                                    uint32_t* __restrict__ new_start) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > m) return;
     if (k == m) {
         new_start[k] = total;
         return;
     }
-    uint32_t s = old_start[k];
-    new_start[k] = (s < n_old) ? scan_ex[s] : total;
+    const uint32_t s = old_start[k];
+    new_start[k] = (s < n_old) ? word_off[s >> 5] + __popc(bits[s >> 5] & ((1u << (s & 31u)) - 1u)) : total;
+}
+
+// alive_r[perm[i]] = 1 for the positions of the current order (ensure_alive)
+__global__ void mark_alive_kernel(const uint32_t* __restrict__ perm, uint32_t n, uint8_t* __restrict__ alive_r) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) alive_r[perm[i]] = 1;
 }
 
 // =============================================================================================

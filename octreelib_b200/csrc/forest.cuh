@@ -22,6 +22,7 @@ struct Forest {
     size_t bbox_done = 0;        // points already folded into d_bbox / checked for NaN
     DevBuf<uint8_t> alive_r;     // [cap] 1 = point still stored; allocated by the first removal (filter / RANSAC mask)
     bool any_dead = false;
+    bool alive_stale = false;    // alive_r lags behind the current order (apply_keep); see ensure_alive
     bool base_dirty = false;     // base order still contains dead points
     std::vector<uint32_t> seg_start;  // host: first rank of every segment (+ sentinel N)
     std::vector<int32_t> seg_pose;    // host: pose index of every segment
@@ -57,6 +58,7 @@ struct Forest {
 
     // ---- current tree shape and point order -----------------------------------------------------
     bool shaped = false;         // current arrays valid
+    bool order_virgin = false;   // perm / mort / leaf_of not copied from the base order yet (see reset_shape)
     uint32_t A = 0;
     uint32_t A_shape = 0;        // A when the shape was built (istart[] positions refer to that order)
     DevBuf<uint32_t> perm;       // [A] position -> r ; order = (cell, leaf DFS, pose, input index)
@@ -125,6 +127,13 @@ struct Forest {
     void build();            // K1-K3: keygen, sort, cells
     void ensure_cell_poses();  // (cell, pose) pairs of the base order
     void compact_base();     // drop dead points from the base order
+    struct CompactTables {
+        DevBuf<uint32_t> bits, word_off, tile_off;
+    };
+    uint32_t compact_tables(const uint8_t* keep, const uint32_t* via, uint32_t n, CompactTables& t);
+    void compact_move(CompactTables& t, uint32_t n, const uint32_t* perm_in, const uint64_t* mort_in, const uint32_t* aux_in,
+                      uint32_t* perm_out, uint64_t* mort_out, uint32_t* aux_out);
+    void ensure_alive();     // alive_r := membership in the current order, if apply_keep left it stale
     void extend_morton();    // Morton codes at the full depth (lazy: MORTON_INITIAL_DEPTH levels first)
     void reset_shape();      // current := base (every cell one leaf)
     void subdivide(int64_t max_points, const uint8_t* table, int64_t table_len, int beyond, const int32_t* poses,
@@ -134,6 +143,7 @@ struct Forest {
     void save_shape();       // record the split nodes before a rebuild
     void replay_shape();     // impose the recorded shape on the rebuilt grid
     void ensure_shape();
+    void materialize_order();  // perm / mort / leaf_of := base order, if reset_shape deferred the copy
     void ensure_order();     // K5: leaf enumeration order + geometry
     void ensure_blocks();    // (pose, leaf) runs
     void filter(const uint8_t* keep_table, int64_t table_len, const int32_t* poses, int n_poses_listed);

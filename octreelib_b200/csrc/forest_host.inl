@@ -103,6 +103,7 @@ int Forest::insert(const double* xyz, int64_t n, bool on_device, const int64_t* 
     OL_REQUIRE(n >= 0, OL_ERR_INVALID, "negative point count");
     OL_REQUIRE(N + (size_t)n < (1ull << 31), OL_ERR_INVALID, "more than 2^31 - 1 points per forest are not supported");
     materialize_snapshot();
+    ensure_alive();
     if (shaped && I > 0) save_shape();  // a later pose follows the existing subdivision (octree_manager.py:171)
     if (N + (size_t)n > cap) {
         size_t ncap = std::max<size_t>(N + (size_t)n, cap + cap / 2 + 1024);
@@ -180,6 +181,7 @@ int Forest::insert_batch(const double* const* xyz_dev, const int64_t* sizes, int
     }
     OL_REQUIRE(N + total < (1ull << 31), OL_ERR_INVALID, "more than 2^31 - 1 points per forest are not supported");
     materialize_snapshot();
+    ensure_alive();
     if (shaped && I > 0) save_shape();
     if (N + total > cap) {
         const size_t ncap = N + total;  // the batch is usually the whole map: grow exactly once
@@ -376,33 +378,18 @@ void Forest::ensure_cell_poses() {
 void Forest::compact_base() {
     if (!base_dirty) return;
     ensure_cell_poses();
+    ensure_alive();
     const uint32_t n = A0;
     if (n) {
-        DevBuf<uint32_t> flags(ctx, n), scan(ctx, n);
-        DevBuf<unsigned long long> d_total(ctx, 1);
-        {
-            ProfScope ps(ctx, "compact");
-            alive_flags_kernel<<<nblk(n), 256, 0, ctx.stream>>>(alive_r.get(), perm0.get(), n, flags.get());
-            OL_CHECK_LAUNCH();
-        }
-        exclusive_scan_u32(ctx, flags.get(), scan.get(), n, d_total.get());
-        uint32_t total = (uint32_t)read_u64(d_total.get());
+        CompactTables t;
+        const uint32_t total = compact_tables(alive_r.get(), perm0.get(), n, t);
         DevBuf<uint32_t> p2(ctx, total), c2(ctx, total), s2(ctx, (size_t)C + 1);
         DevBuf<uint64_t> m2(ctx, mort_len(total));
+        compact_move(t, n, perm0.get(), mort0.get(), cellidx0.get(), p2.get(), m2.get(), c2.get());
         {
             ProfScope ps(ctx, "compact");
-            if (mort32)
-                compact_pos_kernel<uint32_t><<<nblk(n), 256, 0, ctx.stream>>>(flags.get(), scan.get(), n, perm0.get(),
-                                                                              reinterpret_cast<const uint32_t*>(mort0.get()), cellidx0.get(),
-                                                                              p2.get(), reinterpret_cast<uint32_t*>(m2.get()), c2.get(), nullptr);
-            else
-                compact_pos_kernel<uint64_t><<<nblk(n), 256, 0, ctx.stream>>>(flags.get(), scan.get(), n, perm0.get(), mort0.get(),
-                                                                              cellidx0.get(), p2.get(), m2.get(), c2.get(), nullptr);
-            OL_CHECK_LAUNCH();
-        }
-        {
-            ProfScope ps(ctx, "compact");
-            remap_starts_kernel<<<nblk((size_t)C + 1), 256, 0, ctx.stream>>>(cell_start0.get(), scan.get(), C, n, total, s2.get());
+            remap_starts_kernel<<<nblk((size_t)C + 1), 256, 0, ctx.stream>>>(cell_start0.get(), t.bits.get(), t.word_off.get(), C, n, total,
+                                                                              s2.get());
             OL_CHECK_LAUNCH();
         }
         perm0.swap(p2);
@@ -412,6 +399,52 @@ void Forest::compact_base() {
         A0 = total;
     }
     base_dirty = false;
+}
+
+// keep flags (keep[via ? via[i] : i]) -> bit words, tile offsets; returns the number of kept positions
+uint32_t Forest::compact_tables(const uint8_t* keep, const uint32_t* via, uint32_t n, CompactTables& t) {
+    const uint32_t tiles = (n + CMP_TILE - 1) / CMP_TILE;
+    t.bits.reset(ctx, (n + 31) / 32);
+    t.word_off.reset(ctx, (n + 31) / 32);
+    t.tile_off.reset(ctx, tiles);
+    DevBuf<unsigned long long> d_total(ctx, 1);
+    {
+        ProfScope ps(ctx, "compact", (double)n);
+        keep_bits_kernel<<<tiles, CMP_THREADS, 0, ctx.stream>>>(keep, via, n, t.bits.get(), t.tile_off.get());
+        OL_CHECK_LAUNCH();
+    }
+    exclusive_scan_u32(ctx, t.tile_off.get(), t.tile_off.get(), tiles, d_total.get());
+    return (uint32_t)read_u64(d_total.get());
+}
+
+void Forest::compact_move(CompactTables& t, uint32_t n, const uint32_t* perm_in, const uint64_t* mort_in, const uint32_t* aux_in,
+                          uint32_t* perm_out, uint64_t* mort_out, uint32_t* aux_out) {
+    const uint32_t tiles = (n + CMP_TILE - 1) / CMP_TILE;
+    ProfScope ps(ctx, "compact", (double)n);
+    if (mort32)
+        compact_move_kernel<uint32_t><<<tiles, CMP_THREADS, 0, ctx.stream>>>(t.bits.get(), t.tile_off.get(), n, perm_in,
+                                                                             reinterpret_cast<const uint32_t*>(mort_in), aux_in, perm_out,
+                                                                             reinterpret_cast<uint32_t*>(mort_out), aux_out, t.word_off.get());
+    else
+        compact_move_kernel<uint64_t><<<tiles, CMP_THREADS, 0, ctx.stream>>>(t.bits.get(), t.tile_off.get(), n, perm_in, mort_in, aux_in,
+                                                                             perm_out, mort_out, aux_out, t.word_off.get());
+    OL_CHECK_LAUNCH();
+}
+
+// The byte map of stored points is only read when the base order is rebuilt or compacted (insert after a removal,
+// a second subdivide): apply_keep leaves it stale and it is re-derived here from the current order, whose positions
+// are exactly the stored points - |kept| scattered byte stores instead of |removed| ones inside every apply_keep.
+void Forest::ensure_alive() {
+    if (!alive_stale) return;
+    alive_stale = false;
+    if (!alive_r.get()) alive_r.reset(ctx, cap);
+    OL_CUDA(cudaMemsetAsync(alive_r.get(), 0, N, ctx.stream));
+    if (cap > N) OL_CUDA(cudaMemsetAsync(alive_r.get() + N, 1, cap - N, ctx.stream));
+    if (A) {
+        ProfScope ps(ctx, "compact", (double)A);
+        mark_alive_kernel<<<nblk(A), 256, 0, ctx.stream>>>(perm.get(), A, alive_r.get());
+        OL_CHECK_LAUNCH();
+    }
 }
 
 // The Morton codes carry MORTON_INITIAL_DEPTH levels at first (3 bits each); a subdivision that goes deeper
@@ -446,12 +479,12 @@ void Forest::reset_shape() {
     L = C;
     I = 0;
     depth_reached = 0;
-    perm.reset(ctx, A);
-    mort.reset(ctx, mort_len(A));
-    leaf_of.reset(ctx, A);
-    d2d(ctx, perm.get(), perm0.get(), A);
-    d2d(ctx, mort.get(), mort0.get(), mort_len(A));
-    d2d(ctx, leaf_of.get(), cellidx0.get(), A);
+    // the current point order starts as the base order: not copied until somebody needs it as such - the first
+    // partition level reads the base arrays directly (split_levels), everything else calls materialize_order()
+    perm.reset(ctx, 0);
+    mort.reset(ctx, 0);
+    leaf_of.reset(ctx, 0);
+    order_virgin = true;
     lstart.reset(ctx, (size_t)L + 1);
     d2d(ctx, lstart.get(), cell_start0.get(), (size_t)L + 1);
     lcell.reset(ctx, L);
@@ -476,10 +509,22 @@ void Forest::reset_shape() {
     order_valid = blocks_valid = ransac_valid = false;
 }
 
+void Forest::materialize_order() {
+    if (!order_virgin) return;
+    order_virgin = false;
+    perm.reset(ctx, A);
+    mort.reset(ctx, mort_len(A));
+    leaf_of.reset(ctx, A);
+    d2d(ctx, perm.get(), perm0.get(), A);
+    d2d(ctx, mort.get(), mort0.get(), mort_len(A));
+    d2d(ctx, leaf_of.get(), cellidx0.get(), A);
+}
+
 void Forest::ensure_shape() {
     if (shaped) return;
     reset_shape();
     if (replay_pending) replay_shape();
+    materialize_order();
 }
 
 void Forest::save_shape() {
@@ -521,7 +566,10 @@ void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t ta
                        int n_listed) {
     replay_pending = false;  // a fresh scheme replaces whatever shape was recorded
     reset_shape();
-    if (L == 0 || A == 0) return;
+    if (L == 0 || A == 0) {
+        materialize_order();
+        return;
+    }
     DevBuf<uint8_t> listed, table;
     if (n_listed > 0) {
         std::vector<uint8_t> h(std::max(n_poses, 1), 0);
@@ -553,13 +601,16 @@ void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t ta
     DevBuf<uint32_t> perm_b(ctx, A), leaf_b(ctx, A);
     DevBuf<uint64_t> mort_b(ctx, mort_len(A));
     for (int level = 0;; ++level) {
+        // level 0 of a fresh shape partitions straight out of the base order (reset_shape made no copy)
+        const uint32_t* src_leaf = order_virgin ? cellidx0.get() : leaf_of.get();
+        const uint32_t* src_perm = order_virgin ? perm0.get() : perm.get();
         DevBuf<uint32_t> splitf(ctx, L), expand(ctx, L), newidx(ctx, L), iidx(ctx, L), wcount;
         if (n_listed > 0) {
             wcount.reset(ctx, L);
             wcount.zero();
             {
                 ProfScope ps(ctx, "weighted_count", (double)A);
-                weighted_count_kernel<<<nblk(A), 256, 0, ctx.stream>>>(leaf_of.get(), perm.get(), ldepth.get(), level,
+                weighted_count_kernel<<<nblk(A), 256, 0, ctx.stream>>>(src_leaf, src_perm, ldepth.get(), level,
                                                                        d_seg_start.get(), d_seg_pose.get(), S, d_listed, A,
                                                                        wcount.get());
                 OL_CHECK_LAUNCH();
@@ -583,9 +634,13 @@ void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t ta
         OL_REQUIRE((unsigned long long)I + n_split < (1ull << 29), OL_ERR_RANGE, "too many internal nodes");
         depth_reached = level + 1;
         if (level >= kp.depth) {
+            materialize_order();
+            src_leaf = leaf_of.get();
+            src_perm = perm.get();
             extend_morton();
             mort_b.reset(ctx, mort_len(A));  // the word size may have changed
         }
+        const uint64_t* src_mort = order_virgin ? mort0.get() : mort.get();
         const int shift = 3 * (kp.depth - 1 - level);
         DevBuf<uint32_t> leaf_cnt(ctx, (size_t)n_split * 8), leaf_beg(ctx, (size_t)n_split * 8), sidx(ctx, L);
         leaf_cnt.zero();
@@ -597,11 +652,11 @@ void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t ta
         {
             ProfScope ps(ctx, "part_hist", (double)A);
             if (mort32)
-                part_hist_kernel<uint32_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), reinterpret_cast<const uint32_t*>(mort.get()),
+                part_hist_kernel<uint32_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(src_leaf, reinterpret_cast<const uint32_t*>(src_mort),
                                                                                    sidx.get(), A, tiles, n_split, shift, tile_hist.get(),
                                                                                    leaf_cnt.get());
             else
-                part_hist_kernel<uint64_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(leaf_of.get(), mort.get(), sidx.get(), A, tiles, n_split,
+                part_hist_kernel<uint64_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(src_leaf, src_mort, sidx.get(), A, tiles, n_split,
                                                                                    shift, tile_hist.get(), leaf_cnt.get());
             OL_CHECK_LAUNCH();
         }
@@ -618,12 +673,12 @@ void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t ta
             ProfScope ps(ctx, "part_move", (double)A);
             if (mort32)
                 part_move_kernel<uint32_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(
-                    leaf_of.get(), reinterpret_cast<const uint32_t*>(mort.get()), perm.get(), sidx.get(), newidx.get(), tile_hist.get(),
+                    src_leaf, reinterpret_cast<const uint32_t*>(src_mort), src_perm, sidx.get(), newidx.get(), tile_hist.get(),
                     delta.get(), A, tiles, shift, level, leaf_b.get(), reinterpret_cast<uint32_t*>(mort_b.get()), perm_b.get(), P64.get(),
                     lcell.get(), cell_key.get(), kp, d_err.get());
             else
                 part_move_kernel<uint64_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(
-                    leaf_of.get(), mort.get(), perm.get(), sidx.get(), newidx.get(), tile_hist.get(), delta.get(), A, tiles, shift, level,
+                    src_leaf, src_mort, src_perm, sidx.get(), newidx.get(), tile_hist.get(), delta.get(), A, tiles, shift, level,
                     leaf_b.get(), mort_b.get(), perm_b.get(), P64.get(), lcell.get(), cell_key.get(), kp, d_err.get());
             OL_CHECK_LAUNCH();
         }
@@ -660,9 +715,16 @@ void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t ta
         perm.swap(perm_b);
         mort.swap(mort_b);
         leaf_of.swap(leaf_b);
+        if (order_virgin) {  // the swapped-out buffers were the empty placeholders
+            order_virgin = false;
+            perm_b.reset(ctx, A);
+            leaf_b.reset(ctx, A);
+            mort_b.reset(ctx, mort_len(A));
+        }
         L = L_new;
         I += n_split;
     }
+    materialize_order();  // no level split anything: the current order is the base order
     check_device_errors();
     order_valid = blocks_valid = ransac_valid = false;
 }
@@ -787,36 +849,15 @@ void Forest::ensure_blocks() {
 void Forest::apply_keep(const uint8_t* keep_pos) {
     const uint32_t n = A;
     if (n == 0) return;
-    DevBuf<uint32_t> flags(ctx, n), scan(ctx, n);
-    DevBuf<unsigned long long> d_total(ctx, 1);
-    {
-        ProfScope ps(ctx, "compact");
-        keep_to_u32_kernel<<<nblk(n), 256, 0, ctx.stream>>>(keep_pos, n, flags.get());
-        OL_CHECK_LAUNCH();
-    }
-    exclusive_scan_u32(ctx, flags.get(), scan.get(), n, d_total.get());
-    const uint32_t total = (uint32_t)read_u64(d_total.get());
+    CompactTables t;
+    const uint32_t total = compact_tables(keep_pos, nullptr, n, t);
     if (total == n) return;
     DevBuf<uint32_t> p2(ctx, total), l2(ctx, total), s2(ctx, (size_t)L + 1);
     DevBuf<uint64_t> m2(ctx, mort_len(total));
-    if (!alive_r.get()) {  // first removal: every inserted point was alive so far
-        alive_r.reset(ctx, cap);
-        OL_CUDA(cudaMemsetAsync(alive_r.get(), 1, cap, ctx.stream));
-    }
+    compact_move(t, n, perm.get(), mort.get(), leaf_of.get(), p2.get(), m2.get(), l2.get());
     {
         ProfScope ps(ctx, "compact");
-        if (mort32)
-            compact_pos_kernel<uint32_t><<<nblk(n), 256, 0, ctx.stream>>>(flags.get(), scan.get(), n, perm.get(),
-                                                                          reinterpret_cast<const uint32_t*>(mort.get()), leaf_of.get(), p2.get(),
-                                                                          reinterpret_cast<uint32_t*>(m2.get()), l2.get(), alive_r.get());
-        else
-            compact_pos_kernel<uint64_t><<<nblk(n), 256, 0, ctx.stream>>>(flags.get(), scan.get(), n, perm.get(), mort.get(), leaf_of.get(),
-                                                                          p2.get(), m2.get(), l2.get(), alive_r.get());
-        OL_CHECK_LAUNCH();
-    }
-    {
-        ProfScope ps(ctx, "compact");
-        remap_starts_kernel<<<nblk((size_t)L + 1), 256, 0, ctx.stream>>>(lstart.get(), scan.get(), L, n, total, s2.get());
+        remap_starts_kernel<<<nblk((size_t)L + 1), 256, 0, ctx.stream>>>(lstart.get(), t.bits.get(), t.word_off.get(), L, n, total, s2.get());
         OL_CHECK_LAUNCH();
     }
     perm.swap(p2);
@@ -825,6 +866,7 @@ void Forest::apply_keep(const uint8_t* keep_pos) {
     lstart.swap(s2);
     A = total;
     any_dead = true;
+    alive_stale = true;  // the byte map of stored points is re-derived on demand (ensure_alive)
     base_dirty = true;
     blocks_valid = false;
     ransac_valid = false;

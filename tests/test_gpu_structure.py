@@ -109,6 +109,34 @@ def test_late_pose_matches_oracle_lidar():
     compare_grid_with_oracle(grid, og, clouds)
 
 
+@pytest.mark.parametrize("seed", [11, 12])
+def test_late_pose_after_removal_matches_oracle(seed):
+    """filter removes points, then a pose arrives: the stored-point map is re-derived from the current order, the
+    rebuilt base order drops the removed points and the recorded scheme is replayed (checked against the real
+    reference for seed 11 while writing the test)."""
+    rng = np.random.default_rng(seed)
+    clouds = {}
+    for p in range(3):
+        c = rng.normal(0, 3, (4000, 3)) * np.array([3, 2, 0.3]) + rng.integers(-2, 3, (4000, 1))
+        clouds[p] = c.astype(np.float32).astype(np.float64)
+    grid, og = Grid(GridConfig(voxel_edge_length=2)), OracleGrid(2)
+    for p in (0, 1):
+        grid.insert_points(p, clouds[p])
+        og.insert_points(p, clouds[p])
+    grid.subdivide([MaxPoints(30)])
+    og.subdivide([max_points_criterion(30)])
+    grid.filter([MinPoints(6)])
+    og.filter([lambda pts: len(pts) >= 6])
+    compare_grid_with_oracle(grid, og, {0: clouds[0], 1: clouds[1]})
+    grid.insert_points(2, clouds[2])
+    og.insert_points(2, clouds[2])
+    compare_grid_with_oracle(grid, og, clouds)
+    # a second removal on top of the rebuilt grid
+    grid.filter([MinPoints(9)])
+    og.filter([lambda pts: len(pts) >= 9])
+    compare_grid_with_oracle(grid, og, clouds)
+
+
 @pytest.mark.parametrize("seed,n,edge,max_points", [(0, 30000, 1, 50), (1, 60000, 2, 100), (2, 20000, 4, 5)])
 def test_oracle_parity_random(seed, n, edge, max_points):
     rng = np.random.default_rng(seed)
