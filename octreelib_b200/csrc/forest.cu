@@ -523,7 +523,7 @@ __global__ void part_delta_kernel(uint32_t L, const uint32_t* __restrict__ split
 // leaves appear in position order.  Blocked arrangement (8 consecutive positions per thread): measured 4.2 ms for the
 // three levels of the 100 M workload against 7.3 ms for a warp-striped variant with match-based ranking.
 template <typename MortT>
-__global__ void __launch_bounds__(PART_THREADS) part_move_kernel(
+__global__ void __launch_bounds__(PART_THREADS, 3) part_move_kernel(
     const uint32_t* __restrict__ leaf_of, const MortT* __restrict__ mort, const uint32_t* __restrict__ perm,
     const uint32_t* __restrict__ sidx, const uint32_t* __restrict__ newidx, const uint32_t* __restrict__ tile_off,
     const uint32_t* __restrict__ delta, uint32_t n, uint32_t num_tiles, int shift, int level,
@@ -533,8 +533,16 @@ __global__ void __launch_bounds__(PART_THREADS) part_move_kernel(
     uint32_t* __restrict__ err) {
     __shared__ unsigned long long wlo[8], whi[8];
     __shared__ uint32_t G[8];
+    // Output staging: a leaf is partitioned inside its own range, so nearly every destination lies in the tile's own
+    // range of positions.  Those go through shared memory and leave as 16-byte coalesced stores; only the pieces of a
+    // splitting leaf that straddles a tile boundary are stored directly.  s_mask marks the staged positions.
+    __shared__ __align__(16) uint32_t s_leaf[PART_TILE], s_perm[PART_TILE];
+    __shared__ __align__(16) MortT s_mort[PART_TILE];
+    __shared__ uint32_t s_mask[PART_TILE / 32];
     if (threadIdx.x < 8) G[threadIdx.x] = tile_off[(size_t)threadIdx.x * num_tiles + blockIdx.x];
-    const uint32_t first = blockIdx.x * PART_TILE + threadIdx.x * PART_ITEMS;
+    if (threadIdx.x < PART_TILE / 32) s_mask[threadIdx.x] = 0u;
+    const uint32_t tile_base = blockIdx.x * PART_TILE;
+    const uint32_t first = tile_base + threadIdx.x * PART_ITEMS;
     uint32_t leaf[PART_ITEMS];
     uint32_t g[PART_ITEMS];
     uint32_t pr[PART_ITEMS];
@@ -626,9 +634,43 @@ __global__ void __launch_bounds__(PART_THREADS) part_move_kernel(
                 if (bad <= level) atomicOr(err, (uint32_t)DEVERR_OUT_OF_NODE);
             }
         }
-        leaf_out[dst] = nl;
-        mort_out[dst] = m[j];
-        perm_out[dst] = pr[j];
+        const uint32_t rel = dst - tile_base;  // wraps to a huge value below the tile
+        if (rel < (uint32_t)PART_TILE) {
+            s_leaf[rel] = nl;
+            s_mort[rel] = m[j];
+            s_perm[rel] = pr[j];
+            atomicOr(&s_mask[rel >> 5], 1u << (rel & 31u));
+        } else {
+            leaf_out[dst] = nl;
+            mort_out[dst] = m[j];
+            perm_out[dst] = pr[j];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < PART_TILE / (PART_THREADS * 4); ++h) {
+        const uint32_t o = (uint32_t)h * PART_THREADS * 4 + threadIdx.x * 4;  // 4 consecutive positions, lane-consecutive
+        const uint32_t nib = (s_mask[o >> 5] >> (o & 31u)) & 0xfu;
+        const uint32_t gpos = tile_base + o;
+        if (nib == 0xfu) {
+            *reinterpret_cast<uint4*>(leaf_out + gpos) = *reinterpret_cast<const uint4*>(&s_leaf[o]);
+            *reinterpret_cast<uint4*>(perm_out + gpos) = *reinterpret_cast<const uint4*>(&s_perm[o]);
+            if (sizeof(MortT) == 4) {
+                *reinterpret_cast<uint4*>(mort_out + gpos) = *reinterpret_cast<const uint4*>(&s_mort[o]);
+            } else {
+                reinterpret_cast<ulonglong2*>(mort_out + gpos)[0] = reinterpret_cast<const ulonglong2*>(&s_mort[o])[0];
+                reinterpret_cast<ulonglong2*>(mort_out + gpos)[1] = reinterpret_cast<const ulonglong2*>(&s_mort[o])[1];
+            }
+        } else if (nib) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if ((nib >> b) & 1u) {
+                    leaf_out[gpos + b] = s_leaf[o + b];
+                    mort_out[gpos + b] = s_mort[o + b];
+                    perm_out[gpos + b] = s_perm[o + b];
+                }
+            }
+        }
     }
 }
 
