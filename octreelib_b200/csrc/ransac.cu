@@ -120,22 +120,33 @@ __device__ __forceinline__ int sample_index(const double* __restrict__ table, in
 }
 
 // util.py:28-84, op for op (no contraction), result rounded to float32 (cuda_ransac.py:110-113)
-__device__ __noinline__ float4 fit_plane(const double* __restrict__ pts, const double* __restrict__ table, int K, int t, int n,
-                                         long long ref_start, uint32_t* err) {
+// KC > 0: the number of draws is known at compile time (the loops unroll and the K sample indices stay in registers
+// instead of being recomputed for the second pass); KC = 0: any K.  SMEM: `pts` points into shared memory (LDS instead
+// of generic loads).  The arithmetic and its order are the same in every instantiation.
+template <int KC, bool SMEM>
+__device__ __forceinline__ float4 fit_plane_impl(const double* __restrict__ pts, const double* __restrict__ table, int K, int t, int n,
+                                                 long long ref_start, uint32_t* err) {
+    if (SMEM) __builtin_assume(__isShared(pts));
+    const int kk = KC ? KC : K;
+    int idx[KC ? KC : 1];
     double cx = 0.0, cy = 0.0, cz = 0.0;
-    for (int i = 0; i < K; ++i) {
-        const double* p = pts + 3 * sample_index(table, K, t, i, n, ref_start, err);
+#pragma unroll
+    for (int i = 0; i < kk; ++i) {
+        const int s = sample_index(table, kk, t, i, n, ref_start, err);
+        if (KC) idx[i] = s;
+        const double* p = pts + 3 * s;
         cx = __dadd_rn(cx, p[0]);
         cy = __dadd_rn(cy, p[1]);
         cz = __dadd_rn(cz, p[2]);
     }
-    const double kd = (double)K;
+    const double kd = (double)kk;
     cx = __ddiv_rn(cx, kd);
     cy = __ddiv_rn(cy, kd);
     cz = __ddiv_rn(cz, kd);
     double xx = 0.0, xy = 0.0, xz = 0.0, yy = 0.0, yz = 0.0, zz = 0.0;
-    for (int i = 0; i < K; ++i) {
-        const double* p = pts + 3 * sample_index(table, K, t, i, n, ref_start, err);
+#pragma unroll
+    for (int i = 0; i < kk; ++i) {
+        const double* p = pts + 3 * (KC ? idx[i] : sample_index(table, kk, t, i, n, ref_start, err));
         const double rx = __dsub_rn(p[0], cx), ry = __dsub_rn(p[1], cy), rz = __dsub_rn(p[2], cz);
         xx = __dadd_rn(xx, __dmul_rn(rx, rx));
         xy = __dadd_rn(xy, __dmul_rn(rx, ry));
@@ -168,6 +179,19 @@ __device__ __noinline__ float4 fit_plane(const double* __restrict__ pts, const d
     az = __ddiv_rn(az, norm);
     const double d = -__dadd_rn(__dadd_rn(__dmul_rn(ax, cx), __dmul_rn(ay, cy)), __dmul_rn(az, cz));
     return make_float4((float)ax, (float)ay, (float)az, (float)d);
+}
+
+// generic address space (the CTA kernel streams blocks > cap points from global memory)
+__device__ __noinline__ float4 fit_plane(const double* __restrict__ pts, const double* __restrict__ table, int K, int t, int n,
+                                         long long ref_start, uint32_t* err) {
+    if (K == 6) return fit_plane_impl<6, false>(pts, table, K, t, n, ref_start, err);
+    return fit_plane_impl<0, false>(pts, table, K, t, n, ref_start, err);
+}
+// points staged in shared memory (warp-per-block kernel)
+__device__ __noinline__ float4 fit_plane_smem(const double* __restrict__ pts, const double* __restrict__ table, int K, int t, int n,
+                                              long long ref_start, uint32_t* err) {
+    if (K == 6) return fit_plane_impl<6, true>(pts, table, K, t, n, ref_start, err);
+    return fit_plane_impl<0, true>(pts, table, K, t, n, ref_start, err);
 }
 
 // util.py:16-24: float32 plane promoted to float64, left-to-right sum, no contraction
@@ -689,7 +713,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) ransac_small_kernel(RansacAr
         for (; k < exact_steps && !done; ++k) {
             const int t = (k << 5) + lane;
             if (t < A.H) {
-                const float4 pl = fit_plane(pts, A.table, A.K, t, n, rs, A.err);
+                const float4 pl = fit_plane_smem(pts, A.table, A.K, t, n, rs, A.err);
                 const int cnt = exact_count_serial(pts, n, pl, A.thr);
                 const unsigned long long key = pack_key(cnt, t);
                 if (key > my_key) {
@@ -756,7 +780,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) ransac_small_kernel(RansacAr
                 const int c = c0 + lane;
                 if (c < nc) {
                     const int t = list[c];
-                    const float4 pl = fit_plane(pts, A.table, A.K, t, n, rs, A.err);
+                    const float4 pl = fit_plane_smem(pts, A.table, A.K, t, n, rs, A.err);
                     const int cnt = exact_count_serial(pts, n, pl, A.thr);
                     const unsigned long long key = pack_key(cnt, t);
                     if (key > my_key) {
