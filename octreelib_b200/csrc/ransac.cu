@@ -599,6 +599,7 @@ __global__ void __launch_bounds__(RANSAC_THREADS) ransac_kernel(RansacArgs A) {
 // =============================================================================================
 constexpr int RS_WARPS = 8;
 constexpr int RS_MAX_POINTS = 128;
+constexpr int RS_GRAB = 8;  // work items a warp takes per atomic (size of the d_* arrays below)
 
 struct __align__(16) RansacWarpSmem {
     double pts[RS_MAX_POINTS * 3 + 2];  // TMA destination (16-byte aligned run + optional 8-byte lead)
@@ -606,6 +607,9 @@ struct __align__(16) RansacWarpSmem {
     uint8_t hi[RANSAC_MAX_H];           // upper bound of every filtered hypothesis
     unsigned long long bar;
     unsigned long long pad;
+    long long d_rs[RS_GRAB];                 // descriptors of the RS_GRAB work items the warp took with one atomic
+    uint32_t d_b[RS_GRAB], d_ps[RS_GRAB], d_pk[RS_GRAB];
+    int d_n[RS_GRAB];
 };
 
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
@@ -645,16 +649,32 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) ransac_small_kernel(RansacAr
     uint32_t parity = 0;
     uint32_t st_blocks = 0, st_filtered = 0, st_trivial = 0, st_exact = 0, st_early = 0, st_viol = 0;  // per-lane / per-warp tallies
     for (;;) {
-        uint32_t w = 0;
-        if (lane == 0) w = atomicAdd(counter, 1u);
-        w = __shfl_sync(0xffffffffu, w, 0);
-        if (w >= A.n_work) break;
-        const uint32_t b = A.work[w];
-        const int n = A.blk_size[b];
+        // RS_GRAB work items per atomic; their descriptors are fetched by RS_GRAB lanes at once, so the dependent
+        // counter -> work[] -> block table round trips are paid once per grab instead of once per block
+        uint32_t w0 = 0;
+        if (lane == 0) w0 = atomicAdd(counter, (uint32_t)RS_GRAB);
+        w0 = __shfl_sync(0xffffffffu, w0, 0);
+        if (w0 >= A.n_work) break;
+        __syncwarp();
+        if (lane < RS_GRAB && w0 + lane < A.n_work) {
+            const uint32_t db = A.work[w0 + lane];
+            const uint32_t dps = A.blk_start[db];
+            W.d_b[lane] = db;
+            W.d_n[lane] = A.blk_size[db];
+            W.d_ps[lane] = dps;
+            W.d_rs[lane] = A.blk_ref_start[db];
+            W.d_pk[lane] = A.pk_start ? A.pk_start[w0 + lane] : dps;
+        }
+        __syncwarp();
+        const int items = (int)min((uint32_t)RS_GRAB, A.n_work - w0);
+      for (int it = 0; it < items; ++it) {
+        const int n = W.d_n[it];
         if (n > RS_MAX_POINTS) continue;  // handled by the CTA-per-block kernel
-        const uint32_t ps = A.blk_start[b];
-        const long long rs = A.blk_ref_start[b];
-        const double* gsrc = A.points + (size_t)(A.pk_start ? A.pk_start[w] : ps) * 3;
+        const uint32_t b = W.d_b[it];
+        const uint32_t ps = W.d_ps[it];
+        const long long rs = W.d_rs[it];
+        const uint32_t pk = W.d_pk[it];
+        const double* gsrc = A.points + (size_t)pk * 3;
         const double* pts;
         // ---- stage the block's float64 points (TMA bulk copy, completion on the warp's mbarrier) --
         if (tma) {
@@ -811,6 +831,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) ransac_small_kernel(RansacAr
         for (int i = lane; i < n; i += 32) A.mask[(size_t)ps + i] = plane_distance(a, bb, c, d, pts + 3 * i) < A.thr ? 1 : 0;
         ++st_blocks;
         __syncwarp();
+      }
     }
     if (A.flags & (RANSAC_FLAG_STATS | RANSAC_FLAG_VERIFY)) {
 #pragma unroll
