@@ -4,6 +4,7 @@
 // compaction.  K6 (RANSAC) lives in ransac.cu, the multi-GPU routing in partition.cu.
 #include <algorithm>
 #include <climits>
+#include <exception>
 #include <mutex>
 
 #include "forest.cuh"

@@ -565,11 +565,6 @@ void Forest::replay_shape() {
 void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t table_len, int beyond, const int32_t* poses,
                        int n_listed) {
     replay_pending = false;  // a fresh scheme replaces whatever shape was recorded
-    reset_shape();
-    if (L == 0 || A == 0) {
-        materialize_order();
-        return;
-    }
     DevBuf<uint8_t> listed, table;
     if (n_listed > 0) {
         std::vector<uint8_t> h(std::max(n_poses, 1), 0);
@@ -587,6 +582,11 @@ void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t ta
         h2d(ctx, table.get(), table_host, (size_t)table_len);
         ctx.sync();
     }
+    reset_shape();  // after the argument checks: the deferred copy of the base order must not outlive an early error
+    if (L == 0 || A == 0) {
+        materialize_order();
+        return;
+    }
     split_levels(max_points, table.get(), table_len, beyond, listed.get(), n_listed, nullptr, 0);
 }
 
@@ -595,6 +595,17 @@ void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t ta
 void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t table_len, int beyond, const uint8_t* d_listed,
                           int n_listed, const uint64_t* replay_keys, uint32_t n_replay) {
     const int S = (int)seg_pose.size();
+    // an error thrown while the current order is still the un-copied base order: drop the shape, the next call rebuilds it
+    struct VirginGuard {
+        Forest* f;
+        int live = std::uncaught_exceptions();
+        ~VirginGuard() {
+            if (f->order_virgin && std::uncaught_exceptions() > live) {
+                f->order_virgin = false;
+                f->shaped = false;
+            }
+        }
+    } virgin_guard{this};
     DevBuf<unsigned long long> d_tot(ctx, 2);
     const uint32_t tiles = (A + PART_TILE - 1) / PART_TILE;
     DevBuf<uint32_t> tile_hist(ctx, (size_t)8 * tiles);

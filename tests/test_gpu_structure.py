@@ -109,6 +109,21 @@ def test_late_pose_matches_oracle_lidar():
     compare_grid_with_oracle(grid, og, clouds)
 
 
+def test_error_in_subdivide_leaves_the_grid_usable():
+    """A rejected call (unknown pose index at the C ABI) must not leave a half-built shape behind."""
+    rng = np.random.default_rng(3)
+    clouds = {p: (rng.random((3000, 3)) * 5).astype(np.float32).astype(np.float64) for p in range(2)}
+    grid, og = Grid(GridConfig(voxel_edge_length=1)), OracleGrid(1)
+    for p, c in clouds.items():
+        grid.insert_points(p, c)
+        og.insert_points(p, c)
+    grid.subdivide([MaxPoints(20)])
+    og.subdivide([max_points_criterion(20)])
+    with pytest.raises(KeyError):
+        grid._host.forest.subdivide(20, [7])
+    compare_grid_with_oracle(grid, og, clouds)
+
+
 @pytest.mark.parametrize("seed", [11, 12])
 def test_late_pose_after_removal_matches_oracle(seed):
     """filter removes points, then a pose arrives: the stored-point map is re-derived from the current order, the
