@@ -199,6 +199,61 @@ def late_pose_case(name, clouds, late, edge, max_points):
           "  -- oracle == reference OK")
 
 
+def resubdivide_case(name, clouds, late, edge, first_max, second_max):
+    """A second, finer subdivide ("deepening re-subdivides" are inside the reference's domain).  Every pose
+    octree keeps its `_cached_leaves` list across calls (octree_base.py:48-49, octree.py:183-191), so the leaf order
+    after the second call depends on WHEN a node was split: leaves created by the first call stay in front of the
+    children appended by the second one, and a pose inserted between the calls (`late`) sees one single pass instead.
+    The fixture stores the state after each stage and asserts that it really differs from a one-shot subdivision."""
+    early = [p for p in clouds if p not in late]
+
+    def run(make_grid, crit):
+        stages = []
+        g = make_grid()
+        for p in early:
+            g.insert_points(p, clouds[p])
+        g.subdivide(crit(first_max))
+        stages.append((g, {p: clouds[p] for p in early}))
+        snap1 = (dump_reference if isinstance(g, Grid) else dump_oracle)(g, {p: clouds[p] for p in early})
+        for p in late:
+            g.insert_points(p, clouds[p])
+        snap2 = (dump_reference if isinstance(g, Grid) else dump_oracle)(g, clouds)
+        g.subdivide(crit(second_max))
+        snap3 = (dump_reference if isinstance(g, Grid) else dump_oracle)(g, clouds)
+        return snap1, snap2, snap3
+
+    ref_crit = lambda m: [lambda pts: len(pts) > m]  # noqa: E731
+    ora_crit = lambda m: [max_points_criterion(m)]  # noqa: E731
+    asis = run(lambda: Grid(GridConfig(voxel_edge_length=edge)), ref_crit)
+    with stable_order():
+        canon = run(lambda: Grid(GridConfig(voxel_edge_length=edge)), ref_crit)
+        fresh = Grid(GridConfig(voxel_edge_length=edge))
+        for p in clouds:
+            fresh.insert_points(p, clouds[p])
+        fresh.subdivide(ref_crit(second_max))
+        oneshot = dump_reference(fresh, clouds)
+    ora = run(lambda: OracleGrid(edge), ora_crit)
+    for i, tag in enumerate(("first", "late", "second")):
+        compare(asis[i], ora[i], ordered=False, tag=f"{name}:{tag}/as-is")
+        compare(canon[i], ora[i], ordered=True, tag=f"{name}:{tag}/stable")
+    differs = [p for p in clouds if canon[2][f"p{p}_corner"].shape != oneshot[f"p{p}_corner"].shape
+               or (canon[2][f"p{p}_corner"] != oneshot[f"p{p}_corner"]).any()]
+    same_set = all(sorted(map(tuple, canon[2][f"p{p}_corner"])) == sorted(map(tuple, oneshot[f"p{p}_corner"])) for p in clouds)
+    assert differs and same_set, "the fixture must exercise the history-dependent leaf order (same leaves, other order)"
+    save = {f"cloud{p}": c for p, c in clouds.items()}
+    save.update({"s1_" + k: v for k, v in canon[0].items()})
+    save.update({"s2_" + k: v for k, v in canon[1].items()})
+    save.update(canon[2])
+    save["edge"], save["first_max"], save["second_max"] = np.float64(edge), np.int64(first_max), np.int64(second_max)
+    save["poses"] = np.array(list(clouds.keys()), dtype=np.int64)
+    save["late"] = np.array(list(late), dtype=np.int64)
+    save["order_differs_from_one_shot"] = np.array(differs, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
+    print(f"[golden] {name}: subdivide(>{first_max}), late poses {list(late)}, subdivide(>{second_max}); leaves/pose "
+          f"{[int(canon[2][f'p{p}_counts'][0]) for p in clouds]}, history order != one-shot order for poses {differs}"
+          "  -- oracle == reference OK")
+
+
 def ransac_case(name, clouds, edge, max_points, H, K, threshold, seed, poses_per_batch):
     """Runs the reference's numba kernel under CUDASIM (slow: keep #blocks * H small)."""
     crit = [lambda pts: len(pts) > max_points]
@@ -266,9 +321,27 @@ def ransac_case(name, clouds, edge, max_points, H, K, threshold, seed, poses_per
     print(f"[golden] {name}: blocks with ties {total_ties}  -- oracle == reference (tie-aware) OK")
 
 
+def resubdivide_fixture():
+    """S8: clustered clouds (deep trees) subdivided twice, one pose arriving between the two calls (own RNG stream)."""
+    r8 = np.random.default_rng(888)
+
+    def f32(a):
+        return a.astype(np.float32).astype(np.float64)
+
+    cl = {}
+    centers = r8.random((10, 3)) * 8
+    for p in range(3):
+        pts = centers[r8.integers(0, 10, 900)] + r8.normal(0, 0.25, (900, 3))
+        cl[p] = f32(np.clip(pts, 0.01, 7.99))
+    resubdivide_case("resubdivide_deepen_edge4", cl, late=[2], edge=4, first_max=60, second_max=12)
+
+
 def main():
     rng = np.random.default_rng(2024)
     only = os.environ.get("GOLDEN_ONLY")  # GOLDEN_ONLY=late regenerates only the late-pose fixture (own RNG stream)
+    if only == "resub":
+        resubdivide_fixture()
+        return
     if only == "late":
         def f32(a):
             return a.astype(np.float32).astype(np.float64)
@@ -312,6 +385,8 @@ def main():
     c3 = {p: f32(rng7.random((900, 3)) * np.array([5.0, 4.0, 2.0]) + np.array([0.3 * p, 0, 0])) for p in range(3)}
     c3[3] = f32(rng7.random((700, 3)) * np.array([5.0, 4.0, 2.0]) + np.array([3.0, 2.0, 0.0]))
     late_pose_case("late_poses_edge2", c3, late=[2, 3], edge=2, max_points=12)
+    # S8: deepening re-subdivide with a pose inserted between the two calls
+    resubdivide_fixture()
 
     # R1..: RANSAC under CUDASIM (about 2 s per block at H=1024 -> small H / few blocks)
     pl = indoor_scene(700, seed=3)

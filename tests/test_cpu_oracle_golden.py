@@ -68,6 +68,38 @@ def test_late_pose_oracle_matches_reference_golden():
         assert (og.get_point_indices(p) == g[f"p{p}_getpoints_idx"]).all()
 
 
+def _assert_oracle_stage(og, g, poses, prefix):
+    for p in poses:
+        leaves = og.get_leaf_points(p)
+        corner = np.array([np.asarray(l.corner, dtype=np.float64) for l in leaves]).reshape(-1, 3)
+        assert (corner == g[f"{prefix}p{p}_corner"]).all(), (prefix, p)
+        assert (np.array([float(l.edge) for l in leaves]) == g[f"{prefix}p{p}_edge"]).all()
+        assert (np.concatenate([l.idx for l in leaves]) == g[f"{prefix}p{p}_idx"]).all()
+        assert [og.n_leaves(p), og.n_points(p), og.n_nodes(p)] == g[f"{prefix}p{p}_counts"].tolist()
+        assert (og.get_point_indices(p) == g[f"{prefix}p{p}_getpoints_idx"]).all()
+
+
+def test_resubdivide_oracle_matches_reference_golden():
+    """A second, finer subdivide: every pose octree keeps its leaf list across calls (octree_base.py:48-49,
+    octree.py:183-191), so the leaf order is history dependent; a pose inserted between the calls sees the first
+    scheme as one pass.  The fixture (real reference) records all three stages."""
+    g = golden("resubdivide_deepen_edge4")
+    late = [int(p) for p in g["late"]]
+    poses = [int(p) for p in g["poses"]]
+    early = [p for p in poses if p not in late]
+    og = OracleGrid(int(g["edge"]))
+    for p in early:
+        og.insert_points(p, g[f"cloud{p}"])
+    og.subdivide([max_points_criterion(int(g["first_max"]))])
+    _assert_oracle_stage(og, g, early, "s1_")
+    for p in late:
+        og.insert_points(p, g[f"cloud{p}"])
+    _assert_oracle_stage(og, g, poses, "s2_")
+    og.subdivide([max_points_criterion(int(g["second_max"]))])
+    _assert_oracle_stage(og, g, poses, "")
+    assert len(g["order_differs_from_one_shot"]) > 0  # the fixture discriminates history order from a fresh build
+
+
 @pytest.mark.parametrize("name", RANSAC_CASES)
 def test_ransac_oracle_matches_reference_golden(name):
     g = golden(name)

@@ -64,6 +64,76 @@ def test_golden_structure(name):
             assert v.n_points == s and v.get_points().shape == (s, 3)
 
 
+def _golden_stage(grid, g, poses, prefix, ordered=True):
+    forest = grid._host.forest
+    blocks, leaves = forest.export_blocks(), forest.export_leaves()
+    for p in poses:
+        pi = grid._host.pose_index[p]
+        sel = np.flatnonzero(blocks["pose"] == pi)
+        lf = blocks["leaf"][sel]
+        got = forest.export_points(pi, order=0)
+        assert [grid.n_leaves(p), grid.n_points(p), grid.n_nodes(p)] == g[f"{prefix}p{p}_counts"].tolist()
+        assert (grid.get_points(p) == g[f"cloud{p}"][g[f"{prefix}p{p}_getpoints_idx"]]).all()
+        if ordered:
+            assert (leaves["corner"][lf] == g[f"{prefix}p{p}_corner"]).all()
+            assert (leaves["edge"][lf] == g[f"{prefix}p{p}_edge"]).all()
+            assert (got["idx"] == g[f"{prefix}p{p}_idx"]).all()
+            continue
+        # same leaves with the same points in the same order inside each leaf, whatever the order of the leaves
+        def table(corner, edge, size, idx):
+            out, off = {}, 0
+            for c, e, n in zip(corner, edge, size):
+                out[(tuple(c), float(e))] = idx[off:off + n].tolist()
+                off += n
+            return out
+        want = table(g[f"{prefix}p{p}_corner"], g[f"{prefix}p{p}_edge"], g[f"{prefix}p{p}_size"], g[f"{prefix}p{p}_idx"])
+        have = table(leaves["corner"][lf], leaves["edge"][lf], blocks["size"][sel], got["idx"])
+        assert have == want
+
+
+def _resubdivide_grid(g, upto):
+    late = [int(p) for p in g["late"]]
+    poses = [int(p) for p in g["poses"]]
+    early = [p for p in poses if p not in late]
+    grid = Grid(GridConfig(voxel_edge_length=_edge(g)))
+    for p in early:
+        grid.insert_points(p, g[f"cloud{p}"])
+    grid.subdivide([MaxPoints(int(g["first_max"]))])
+    if upto == 1:
+        return grid, early
+    for p in late:
+        grid.insert_points(p, g[f"cloud{p}"])
+    if upto == 2:
+        return grid, poses
+    grid.subdivide([MaxPoints(int(g["second_max"]))])
+    return grid, poses
+
+
+def test_golden_resubdivide_first_call_and_late_pose():
+    """Stages 1 and 2 of the re-subdivide fixture (real reference): one subdivide, then a pose that follows the scheme."""
+    g = golden("resubdivide_deepen_edge4")
+    grid, poses = _resubdivide_grid(g, 1)
+    _golden_stage(grid, g, poses, "s1_")
+    grid, poses = _resubdivide_grid(g, 2)
+    _golden_stage(grid, g, poses, "s2_")
+
+
+def test_golden_resubdivide_same_leaves_and_points():
+    """After a second, finer subdivide the leaves, their points, the counters and get_points equal the reference's."""
+    g = golden("resubdivide_deepen_edge4")
+    grid, poses = _resubdivide_grid(g, 3)
+    _golden_stage(grid, g, poses, "", ordered=False)
+
+
+@pytest.mark.xfail(reason="known gap (DESIGN.md section 8): after a SECOND subdivide the reference enumerates leaves in the "
+                          "order its per-pose leaf lists grew over both calls; the forest rebuilds the order from scratch",
+                   strict=False)
+def test_golden_resubdivide_leaf_order():
+    g = golden("resubdivide_deepen_edge4")
+    grid, poses = _resubdivide_grid(g, 3)
+    _golden_stage(grid, g, poses, "")
+
+
 def test_golden_late_poses_follow_the_scheme():
     """Insert after subdivide (octree_manager.py:161-171): golden vectors recorded from the real reference."""
     g = golden("late_poses_edge2")
