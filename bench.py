@@ -451,7 +451,7 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     # algorithmic bytes per processed element of every HBM-bound stage
     # (Morton codes are 32-bit words for trees of at most 10 levels, which covers every bench workload)
-    BYTES = {"bbox": 24, "keygen": 36, "sort_main_hist": 8, "sort_main_pass": 24, "radix_hist_u64": 8, "radix_scatter_u64": 24,
+    BYTES = {"bbox": 24, "keygen": 40, "sort_main_hist": 8, "sort_main_pass": 24, "radix_hist_u64": 8, "radix_scatter_u64": 24,
              "radix_hist_u32": 4, "radix_scatter_u32": 16, "scan": 12, "gather_morton": 12, "part_hist": 8, "part_move": 24,
              "gather_points": 52}
     stage_ms = {k: v[1] for k, v in (prof or {}).items()}
