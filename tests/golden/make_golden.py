@@ -336,11 +336,23 @@ def resubdivide_fixture():
     resubdivide_case("resubdivide_deepen_edge4", cl, late=[2], edge=4, first_max=60, second_max=12)
 
 
+def subset_fixture():
+    """S9: subdivide(criteria, pose_numbers=[0, 2]) - the scheme is built from the listed poses only and imposed on
+    every pose of the cell (octree_manager.py:36-66).  Every pose lives in every cell (the reference raises KeyError
+    for a listed pose that is absent from a cell)."""
+    r9 = np.random.default_rng(999)
+    clouds = {p: (r9.random((1400, 3)) * 4).astype(np.float32).astype(np.float64) for p in range(3)}
+    structure_case("subset_subdivide_edge2", clouds, 2, 30, subdivide_poses=[0, 2])
+
+
 def main():
     rng = np.random.default_rng(2024)
     only = os.environ.get("GOLDEN_ONLY")  # GOLDEN_ONLY=late regenerates only the late-pose fixture (own RNG stream)
     if only == "resub":
         resubdivide_fixture()
+        return
+    if only == "subset":
+        subset_fixture()
         return
     if only == "late":
         def f32(a):
@@ -387,6 +399,8 @@ def main():
     late_pose_case("late_poses_edge2", c3, late=[2, 3], edge=2, max_points=12)
     # S8: deepening re-subdivide with a pose inserted between the two calls
     resubdivide_fixture()
+    # S9: subdivision driven by a subset of the poses
+    subset_fixture()
 
     # R1..: RANSAC under CUDASIM (about 2 s per block at H=1024 -> small H / few blocks)
     pl = indoor_scene(700, seed=3)
