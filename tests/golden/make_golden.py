@@ -345,6 +345,14 @@ def subset_fixture():
     structure_case("subset_subdivide_edge2", clouds, 2, 30, subdivide_poses=[0, 2])
 
 
+def far_fixture():
+    """S10: UTM-like coordinates with full float64 mantissas: `p - corner` and `corner + edge / 2` round at every level."""
+    r10 = np.random.default_rng(1010)
+    base = np.array([451234.0, 5412345.0, 120.0])
+    clouds = {p: base + r10.random((1500, 3)) * np.array([6.0, 5.0, 2.0]) + np.array([0.7 * p, 0, 0]) for p in range(2)}
+    structure_case("far_offset_edge1", clouds, 1, 6)
+
+
 def main():
     rng = np.random.default_rng(2024)
     only = os.environ.get("GOLDEN_ONLY")  # GOLDEN_ONLY=late regenerates only the late-pose fixture (own RNG stream)
@@ -353,6 +361,9 @@ def main():
         return
     if only == "subset":
         subset_fixture()
+        return
+    if only == "far":
+        far_fixture()
         return
     if only == "late":
         def f32(a):
@@ -401,6 +412,8 @@ def main():
     resubdivide_fixture()
     # S9: subdivision driven by a subset of the poses
     subset_fixture()
+    # S10: far from the origin
+    far_fixture()
 
     # R1..: RANSAC under CUDASIM (about 2 s per block at H=1024 -> small H / few blocks)
     pl = indoor_scene(700, seed=3)

@@ -5,6 +5,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 from conftest import ROOT
 from octreelib_b200 import _native
@@ -65,13 +66,22 @@ def _host_key(lib, edge, corner, single, depth, p):
     return [q[0], q[1], q[2]], m.value, bad.value
 
 
-def test_point_key_matches_reference_cell_and_child_routing():
+@pytest.mark.parametrize("edge,offset,f32", [
+    (2, (0.0, 0.0, 0.0), True),
+    (1, (451234.0, 5412345.0, 120.0), False),      # UTM-like coordinates, full float64 mantissas
+    (3, (-98765.0, 12345.0, -4321.0), False),      # negative cells, edge that is not a power of two
+    (4, (1.0e7, -1.0e7, 0.0), False),
+])
+def test_point_key_matches_reference_cell_and_child_routing(edge, offset, f32):
     """cell = ((p - corner) // edge * edge).astype(int) (grid.py:72-76); Morton digits = the child ids the
-    oracle's level-by-level routing produces (octree.py:73-75, 94-97)."""
+    oracle's level-by-level routing produces (octree.py:73-75, 94-97).  Far from the origin `p - corner` and
+    `corner + edge / 2` round, and the key code (the same source the device kernels are compiled from) has to round
+    the same way."""
     lib = _native.lib()
     rng = np.random.default_rng(1)
-    edge = 2
-    pts = (rng.random((300, 3)) * 12 - 6).astype(np.float32).astype(np.float64)
+    pts = rng.random((300, 3)) * 12 - 6 + np.asarray(offset)
+    if f32:
+        pts = pts.astype(np.float32).astype(np.float64)
     og = OracleGrid(edge)
     og.insert_points(0, pts)
     og.subdivide([max_points_criterion(1)])  # split until every point is alone -> deep paths
