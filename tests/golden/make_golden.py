@@ -353,6 +353,13 @@ def far_fixture():
     structure_case("far_offset_edge1", clouds, 1, 6)
 
 
+def ransac_far_fixture():
+    """R5: the RANSAC kernel on planes 450 km / 5400 km from the origin (float32 plane offsets lose the threshold's
+    precision there, exactly like in the reference: cuda_ransac.py:110-113), two poses, two batches."""
+    pl = indoor_scene(500, seed=6) + np.array([451234.0, 5412345.0, 120.0])
+    ransac_case("ransac_far_h64", {0: pl[:250], 1: pl[250:]}, 8.0, 70, H=64, K=6, threshold=0.05, seed=15, poses_per_batch=1)
+
+
 def main():
     rng = np.random.default_rng(2024)
     only = os.environ.get("GOLDEN_ONLY")  # GOLDEN_ONLY=late regenerates only the late-pose fixture (own RNG stream)
@@ -364,6 +371,9 @@ def main():
         return
     if only == "far":
         far_fixture()
+        return
+    if only == "ransac_far":
+        ransac_far_fixture()
         return
     if only == "late":
         def f32(a):
@@ -425,6 +435,7 @@ def main():
     ransac_case("ransac_lidar_h64_k3", {0: li}, 8.0, 150, H=64, K=3, threshold=0.05, seed=13, poses_per_batch=10)
     ransac_case("ransac_lidar_h1024", {0: li[:400]}, 16.0, 200, H=1024, K=6, threshold=0.03, seed=14,
                 poses_per_batch=10)
+    ransac_far_fixture()
 
 
 if __name__ == "__main__":
