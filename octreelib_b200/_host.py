@@ -9,6 +9,7 @@ from typing import Callable, Dict, List, Optional, Sequence
 import numpy as np
 
 from . import _views
+from ._history import LeafHistory
 from .criteria import as_threshold, fold_count_criteria
 from .forest import Forest
 
@@ -28,6 +29,10 @@ class ForestHost:
         self.pose_numbers: List[int] = []      # pose index -> pose number
         self.pose_inserted: List[int] = []     # points inserted so far per pose index
         self._counts_cache = None
+        # leaf order across several subdivide calls (_history.py): nothing is recorded before a SECOND call
+        self._n_subdivides = 0
+        self._pose_epoch: Dict[int, int] = {}  # pose index -> subdivide calls made before the pose was created
+        self._history: Optional[LeafHistory] = None
 
     # ---- plumbing --------------------------------------------------------------------------------
     @property
@@ -61,6 +66,7 @@ class ForestHost:
             self.pose_index[pose_number] = idx
             self.pose_numbers.append(pose_number)
             self.pose_inserted.append(n)
+            self._pose_epoch[idx] = self._n_subdivides
         self._counts_cache = None
 
     # ---- subdivision / filtering ----------------------------------------------------------------
@@ -70,6 +76,12 @@ class ForestHost:
         idx = self._indices(pose_numbers)
         table, beyond = fold_count_criteria(criteria, "any", 1024)
         thr = as_threshold(table, beyond)
+        if self._n_subdivides >= 1 and self._history is None:
+            # a second call: from here on the reference's leaf order depends on when a node was split (_history.py);
+            # every node that exists now dates from the first call
+            t = _views.tables(self.forest)
+            self._history = LeafHistory()
+            self._history.record(t["leaves"], t["cells"], self._n_subdivides)
         if thr is not None:
             self.forest.subdivide(thr, idx)
         else:
@@ -81,6 +93,10 @@ class ForestHost:
                     raise NotImplementedError("count criterion without a settled answer for very large nodes")
                 beyond = False
             self.forest.subdivide_table(table, beyond, idx)
+        self._n_subdivides += 1
+        if self._history is not None:
+            t = _views.tables(self.forest)
+            self._history.record(t["leaves"], t["cells"], self._n_subdivides)
         self._counts_cache = None
 
     def filter(self, criteria: Sequence[Callable], pose_numbers: Optional[Sequence[int]] = None):
@@ -151,7 +167,8 @@ class ForestHost:
     # ---- materialisation -------------------------------------------------------------------------
     def leaf_voxels(self, pose_number: int, non_empty: bool, root_corner, root_edge):
         idx = self.pose_index[pose_number]
-        return _views.leaf_voxels(self.forest, idx, non_empty, root_corner, root_edge)
+        history = self._history if self._history is not None and not self._history.trivial else None
+        return _views.leaf_voxels(self.forest, idx, non_empty, root_corner, root_edge, history, self._pose_epoch.get(idx, 0))
 
     def points_dfs(self, pose_number: int) -> np.ndarray:
         if self.empty or pose_number not in self.pose_index:

@@ -22,8 +22,12 @@ def tables(forest) -> dict:
     return cache
 
 
-def leaf_voxels(forest, pose_index: int, non_empty: bool, root_corner, root_edge):
+def leaf_voxels(forest, pose_index: int, non_empty: bool, root_corner, root_edge, history=None, pose_epoch: int = 0):
     """`get_leaf_points` of one pose (grid/grid.py:217-232 -> octree/octree.py:256-263).
+
+    history: a `_history.LeafHistory` once the grid has been subdivided more than once (the reference's leaf lists
+    grow across calls, so the enumeration order then depends on when a node was split); None = the one-call order
+    the forest exports.
 
     root_corner(cell_index) -> corner object of an unsplit cell root (an int64 array for grid cells,
     grid.py:96-105; the user's array for a stand-alone OctreeManager); root_edge: its edge object.
@@ -43,7 +47,8 @@ def leaf_voxels(forest, pose_index: int, non_empty: bool, root_corner, root_edge
         return LeafVoxel(leaves["corner"][leaf].copy(), np.float64(leaves["edge"][leaf]), pts)
 
     if non_empty:
-        return [make(int(l), xyz[offs[j]:offs[j + 1]]) for j, l in enumerate(blk_leaf)]
+        order = range(len(blk_leaf)) if history is None else history.order(blk_leaf, leaves, t["cells"], t["version"], pose_epoch)
+        return [make(int(blk_leaf[j]), xyz[offs[j]:offs[j + 1]]) for j in order]
     # every leaf (empty ones included) of the cells in which this pose owns an octree
     cp = t["cell_poses"]
     cells_of_pose = cp["cell"][cp["pose"] == pose_index]
@@ -52,7 +57,10 @@ def leaf_voxels(forest, pose_index: int, non_empty: bool, root_corner, root_edge
     out = []
     empty = np.empty((0, 3), dtype=float)
     for c in cells_of_pose:
-        for leaf in range(int(begin[c]), int(begin[c + 1])):
+        ids = np.arange(int(begin[c]), int(begin[c + 1]))
+        if history is not None:
+            ids = ids[history.order(ids, leaves, t["cells"], t["version"], pose_epoch)]
+        for leaf in ids.tolist():
             j = slot.get(leaf)
             out.append(make(leaf, empty if j is None else xyz[offs[j]:offs[j + 1]]))
     return out

@@ -1,0 +1,158 @@
+"""CPU stand-in for `octreelib_b200.forest.Forest`, backed by the oracle (test infrastructure only).
+
+It answers the calls `ForestHost` / `_views` make with tables in the NATIVE forest's format and order: cells
+lexicographic, leaves of a cell in the one-call order (depth-first rank of the parent, child id) whatever the call
+history was - the native forest rebuilds its shape from scratch on every subdivide.  That lets the host-side logic
+(`_host.py`, `_views.py`, `_history.py`, `grid/grid.py`) run in the `-m "not gpu"` suite.
+"""
+import numpy as np
+
+from oracle.structure import OracleGrid, max_points_criterion
+
+
+def _shape_leaves(node, path=()):
+    """(parent path or None, child id, path) of the leaves below `node`, depth-first"""
+    if node.children is None:
+        return [(None, 0, path)] if path == () else []
+    out = []
+    for cid, ch in enumerate(node.children):
+        if ch.children is None:
+            out.append((path, cid, path + (cid,)))
+        else:
+            out += _shape_leaves(ch, path + (cid,))
+    return out
+
+
+def _internal_paths(node, path=()):
+    if node.children is None:
+        return []
+    out = [path]
+    for cid, ch in enumerate(node.children):
+        out += _internal_paths(ch, path + (cid,))
+    return out
+
+
+def _node_at(root, path):
+    node = root
+    for cid in path:
+        if node.children is None:
+            return None
+        node = node.children[cid]
+    return node
+
+
+class FakeForest:
+    def __init__(self, edge):
+        self.og = OracleGrid(edge)
+        self.edge = edge
+        self.version = 0
+        self.clouds = []
+
+    # ---- mutations -------------------------------------------------------------------------------
+    def insert(self, points):
+        idx = len(self.clouds)
+        pts = np.asarray(points, dtype=np.float64)
+        self.clouds.append(pts)
+        self.og.insert_points(idx, pts)
+        self.version += 1
+        return idx
+
+    def subdivide(self, max_points, pose_indices=None):
+        self.og.subdivide([max_points_criterion(int(max_points))], pose_indices)
+        self.version += 1
+
+    def subdivide_table(self, table, beyond, pose_indices=None):
+        table = np.asarray(table)
+        self.og.subdivide([lambda pts: bool(table[len(pts)]) if len(pts) < len(table) else bool(beyond)], pose_indices)
+        self.version += 1
+
+    def filter(self, keep_table, pose_indices=None):
+        table = np.asarray(keep_table)
+        self.og.filter([lambda pts: bool(table[min(len(pts), len(table) - 1)])], pose_indices)
+        self.version += 1
+
+    # ---- tables in the native order --------------------------------------------------------------------
+    def _cell_keys(self):
+        return sorted(self.og.cells.keys())
+
+    def _shape(self, key):
+        """leaf paths of a cell in the forest's one-call order; the shape is the one every pose tree of the cell has"""
+        cell = self.og.cells[key]
+        root = next(iter(cell.trees.values())).root if cell.trees else cell.scheme.root
+        rank = {p: r for r, p in enumerate(_internal_paths(root))}
+        leaves = _shape_leaves(root)
+        leaves.sort(key=lambda t: (0, 0) if t[0] is None else (rank[t[0]], t[1]))
+        return root, [t[2] for t in leaves]
+
+    def _tables(self):
+        keys = self._cell_keys()
+        cells_q, cells_corner, first_pose, n_nodes, leaf_begin = [], [], [], [], [0]
+        leaf_corner, leaf_edge, leaf_cell, leaf_depth, leaf_path = [], [], [], [], []
+        for ci, key in enumerate(keys):
+            cell = self.og.cells[key]
+            root, paths = self._shape(key)
+            cells_q.append([int(round(k / self.edge)) for k in key])
+            cells_corner.append([float(k) for k in key])
+            first_pose.append(min(cell.trees.keys()))
+            n_nodes.append(len(paths) + (len(paths) - 1) // 7)
+            for path in paths:
+                node = _node_at(root, path)
+                leaf_corner.append(np.asarray(node.corner, dtype=np.float64))
+                leaf_edge.append(float(node.edge))
+                leaf_cell.append(ci)
+                leaf_depth.append(len(path))
+                leaf_path.append((key, path))
+            leaf_begin.append(len(leaf_cell))
+        cells = dict(q=np.array(cells_q, dtype=np.int64).reshape(-1, 3), corner=np.array(cells_corner, dtype=np.float64).reshape(-1, 3),
+                     first_pose=np.array(first_pose, dtype=np.int32), n_nodes=np.array(n_nodes, dtype=np.int64),
+                     leaf_begin=np.array(leaf_begin, dtype=np.int64))
+        leaves = dict(corner=np.array(leaf_corner, dtype=np.float64).reshape(-1, 3), edge=np.array(leaf_edge, dtype=np.float64),
+                      cell=np.array(leaf_cell, dtype=np.int32), depth=np.array(leaf_depth, dtype=np.int32))
+        return keys, cells, leaves, leaf_path
+
+    def export_cells(self):
+        return self._tables()[1]
+
+    def export_leaves(self):
+        return self._tables()[2]
+
+    def export_cell_poses(self):
+        keys = self._cell_keys()
+        pairs = [(ci, p) for ci, key in enumerate(keys) for p in sorted(self.og.cells[key].trees.keys())]
+        return dict(cell=np.array([c for c, _ in pairs], dtype=np.int32), pose=np.array([p for _, p in pairs], dtype=np.int32))
+
+    def _blocks(self):
+        _, _, _, leaf_path = self._tables()
+        out = []  # (pose, leaf id, idx array)
+        for pose in range(len(self.clouds)):
+            for lid, (key, path) in enumerate(leaf_path):
+                tree = self.og.cells[key].trees.get(pose)
+                if tree is None:
+                    continue
+                node = _node_at(tree.root, path)
+                if node is not None and len(node.idx):
+                    out.append((pose, lid, node.idx))
+        return out
+
+    def export_blocks(self, pose_rank=None):
+        blocks = self._blocks()
+        return dict(pose=np.array([b[0] for b in blocks], dtype=np.int32), leaf=np.array([b[1] for b in blocks], dtype=np.int32),
+                    size=np.array([len(b[2]) for b in blocks], dtype=np.int32))
+
+    def export_points(self, pose_index=-1, order=0, pose_rank=None, n_hint=None, want_mask=False):
+        assert order == 0 and pose_index >= 0, "the fake only serves the per-pose block order"
+        _, _, leaves, _ = self._tables()
+        idx = [b[2] for b in self._blocks() if b[0] == pose_index]
+        cell = [np.full(len(b[2]), leaves["cell"][b[1]], dtype=np.int32) for b in self._blocks() if b[0] == pose_index]
+        idx = np.concatenate(idx) if idx else np.empty(0, dtype=np.int64)
+        return dict(xyz=self.clouds[pose_index][idx], idx=idx, cell=np.concatenate(cell) if cell else np.empty(0, dtype=np.int32))
+
+    def stats(self, light=False):
+        _, cells, leaves, _ = self._tables()
+        blocks = self._blocks()
+        return dict(n_points_inserted=sum(len(c) for c in self.clouds), n_points_alive=sum(len(b[2]) for b in blocks),
+                    n_poses=len(self.clouds), n_cells=len(cells["q"]), n_leaves=len(leaves["edge"]), n_blocks=len(blocks),
+                    max_block_size=max([len(b[2]) for b in blocks], default=0))
+
+    def pose_counts(self, n_poses):
+        return np.array([[self.og.n_leaves(p), self.og.n_points(p), self.og.n_nodes(p)] for p in range(n_poses)], dtype=np.int64)
