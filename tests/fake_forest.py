@@ -71,6 +71,22 @@ class FakeForest:
         self.og.filter([lambda pts: bool(table[min(len(pts), len(table) - 1)])], pose_indices)
         self.version += 1
 
+    def apply_pose_mask(self, pose_index, mask):
+        """mask over the pose's points in block order (reference order of its non-empty leaves)"""
+        mask = np.asarray(mask, dtype=bool)
+        _, _, _, leaf_path = self._tables()
+        start = 0
+        for pose, lid, idx in self._blocks():
+            if pose != pose_index:
+                continue
+            key, path = leaf_path[lid]
+            node = _node_at(self.og.cells[key].trees[pose].root, path)
+            keep = mask[start:start + len(idx)]
+            node.idx, node.pts = node.idx[keep], node.pts[keep]
+            start += len(idx)
+        assert start == len(mask)
+        self.version += 1
+
     # ---- tables in the native order --------------------------------------------------------------------
     def _cell_keys(self):
         return sorted(self.og.cells.keys())
@@ -140,7 +156,18 @@ class FakeForest:
                     size=np.array([len(b[2]) for b in blocks], dtype=np.int32))
 
     def export_points(self, pose_index=-1, order=0, pose_rank=None, n_hint=None, want_mask=False):
-        assert order == 0 and pose_index >= 0, "the fake only serves the per-pose block order"
+        assert pose_index >= 0, "the fake only serves per-pose exports"
+        if order == 1:  # cells lexicographic x depth-first leaves
+            idx, cell = [], []
+            for ci, key in enumerate(self._cell_keys()):
+                tree = self.og.cells[key].trees.get(pose_index)
+                if tree is None:
+                    continue
+                for leaf in tree.leaves_dfs():
+                    idx.append(leaf.idx)
+                    cell.append(np.full(len(leaf.idx), ci, dtype=np.int32))
+            idx = np.concatenate(idx) if idx else np.empty(0, dtype=np.int64)
+            return dict(xyz=self.clouds[pose_index][idx], idx=idx, cell=np.concatenate(cell) if cell else np.empty(0, dtype=np.int32))
         _, _, leaves, _ = self._tables()
         idx = [b[2] for b in self._blocks() if b[0] == pose_index]
         cell = [np.full(len(b[2]), leaves["cell"][b[1]], dtype=np.int32) for b in self._blocks() if b[0] == pose_index]
