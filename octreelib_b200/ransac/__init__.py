@@ -1,5 +1,5 @@
-"""Per-leaf RANSAC (reference: octreelib/ransac/)."""
-from . import cuda_ransac as _cuda_ransac
-from .cuda_ransac import *  # noqa: F401,F403
+"""Per-leaf plane fitting on the GPU; `CudaRansac` keeps the name and call signature of the reference's class
+(octreelib/ransac/cuda_ransac.py:18-81) and binds `ol_ransac_evaluate` of the native library."""
+from .cuda_ransac import CudaRansac
 
-__all__ = _cuda_ransac.__all__
+__all__ = ["CudaRansac"]
