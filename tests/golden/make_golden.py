@@ -360,6 +360,22 @@ def ransac_far_fixture():
     ransac_case("ransac_far_h64", {0: pl[:250], 1: pl[250:]}, 8.0, 70, H=64, K=6, threshold=0.05, seed=15, poses_per_batch=1)
 
 
+def ransac_degenerate_fixture():
+    """R6: leaves whose samples are collinear, coincident or exactly coplanar: a zero normal makes the reference return
+    the plane (0, 0, 0, 0) (util.py:76-78), for which every point is an inlier; exact planes give many tied hypotheses."""
+    r = np.random.default_rng(66)
+    cells = []
+    t = r.random(40)
+    cells.append(np.c_[t * 7.0, t * 3.0 + 1.0, t * 2.0 + 0.5])                           # a line through cell (0,0,0)
+    cells.append(np.tile(np.array([[9.5, 1.5, 2.5]]), (12, 1)) + np.r_[np.zeros((11, 3)), [[0.25, 0.5, 0.125]]])  # 11 copies + 1
+    xy = r.integers(0, 32, (60, 2)) / 4.0
+    cells.append(np.c_[16.0 + xy[:, 0] * 0.9, xy[:, 1] * 0.9, np.full(60, 3.0)])            # an exact plane z = 3
+    cells.append(np.c_[r.random((50, 2)) * 7.5, 8.0 + r.random(50) * 7.5])                   # a generic cloud (cell (0,0,8))
+    cloud = np.vstack(cells).astype(np.float32).astype(np.float64)
+    # duplicates are part of the case, so the index map of dump_reference is not used here (ransac_case does not need it)
+    ransac_case("ransac_degenerate_h64", {0: cloud}, 8.0, 1000, H=64, K=6, threshold=0.02, seed=16, poses_per_batch=10)
+
+
 def main():
     rng = np.random.default_rng(2024)
     only = os.environ.get("GOLDEN_ONLY")  # GOLDEN_ONLY=late regenerates only the late-pose fixture (own RNG stream)
@@ -374,6 +390,9 @@ def main():
         return
     if only == "ransac_far":
         ransac_far_fixture()
+        return
+    if only == "ransac_degenerate":
+        ransac_degenerate_fixture()
         return
     if only == "late":
         def f32(a):
@@ -436,6 +455,7 @@ def main():
     ransac_case("ransac_lidar_h1024", {0: li[:400]}, 16.0, 200, H=1024, K=6, threshold=0.03, seed=14,
                 poses_per_batch=10)
     ransac_far_fixture()
+    ransac_degenerate_fixture()
 
 
 if __name__ == "__main__":

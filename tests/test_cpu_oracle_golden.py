@@ -10,7 +10,7 @@ from oracle.structure import OracleGrid, max_points_criterion
 STRUCTURE_CASES = ["ref_test_grid_gt2", "ref_test_grid_gt3", "random_3pose_edge2", "random_3pose_edge2_filter",
                    "clustered_2pose_edge4", "lidar_2pose_edge1", "indoor_1pose_edge1", "offset_poses_edge1",
                    "subset_subdivide_edge2", "far_offset_edge1"]
-RANSAC_CASES = ["ransac_indoor_h128", "ransac_indoor_ppb1_h64", "ransac_lidar_h64_k3", "ransac_lidar_h1024", "ransac_far_h64"]
+RANSAC_CASES = ["ransac_indoor_h128", "ransac_indoor_ppb1_h64", "ransac_lidar_h64_k3", "ransac_lidar_h1024", "ransac_far_h64", "ransac_degenerate_h64"]
 
 
 def build_oracle(g):

@@ -15,7 +15,7 @@ from oracle.structure import OracleGrid, max_points_criterion
 
 pytestmark = pytest.mark.gpu
 
-RANSAC_CASES = ["ransac_indoor_h128", "ransac_indoor_ppb1_h64", "ransac_lidar_h64_k3", "ransac_lidar_h1024", "ransac_far_h64"]
+RANSAC_CASES = ["ransac_indoor_h128", "ransac_indoor_ppb1_h64", "ransac_lidar_h64_k3", "ransac_lidar_h1024", "ransac_far_h64", "ransac_degenerate_h64"]
 
 
 def _check_against_oracle(pts, bs, table, thr, r: CudaRansac, mask):
