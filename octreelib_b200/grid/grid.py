@@ -133,15 +133,19 @@ class Grid(GridBase):
         black = 0x000000
         colors = {}
         boxes = []
+        by_pose = config.type is GridVisualizationType.POSE
         for pose_number in self._host.pose_numbers:
-            pose_color = random.randrange(0, 0xFFFFFF)
+            # one colour per pose, or one per voxel id on its first appearance; the draws from `random` follow the
+            # reference's sequence (grid.py:278-311: a voxel colour is drawn even when the voxel is then painted black)
+            pose_color = random.randrange(0, 0xFFFFFF) if by_pose else None
             for leaf in self.get_leaf_points(pose_number):
                 boxes.append(leaf.all_corners)
-                if config.type is GridVisualizationType.POSE:
+                if by_pose:
                     color = black if leaf.id in config.unused_voxels else pose_color
                 else:
                     if leaf.id not in colors:
-                        colors[leaf.id] = black if leaf.id in config.unused_voxels else random.randrange(0, 0xFFFFFF)
+                        drawn = random.randrange(0, 0xFFFFFF)
+                        colors[leaf.id] = black if leaf.id in config.unused_voxels else drawn
                     color = colors[leaf.id]
                 plot += k3d.points(positions=leaf.get_points(), point_size=config.point_size, color=color)
         faces = [[0, 2, 2, 6, 6, 4, 4, 0], [0, 1, 1, 5, 5, 4, 4, 0], [0, 1, 1, 3, 3, 2, 2, 0],

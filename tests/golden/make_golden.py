@@ -376,6 +376,83 @@ def ransac_degenerate_fixture():
     ransac_case("ransac_degenerate_h64", {0: cloud}, 8.0, 1000, H=64, K=6, threshold=0.02, seed=16, poses_per_batch=10)
 
 
+class RecordingK3d:
+    """Stand-in for the k3d module that records what `Grid.visualize` (grid.py:269-341) draws."""
+
+    class Plot(list):
+        def __iadd__(self, item):
+            self.append(item)
+            return self
+
+        def get_snapshot(self):
+            return f"<recorded {len(self)} objects>"
+
+    def __init__(self):
+        self.plots = []
+
+    def install(self, module):
+        rec = self
+
+        def make_plot():
+            plot = RecordingK3d.Plot()
+            rec.plots.append(plot)
+            return plot
+
+        module.Plot = make_plot
+        module.points = lambda positions, point_size, color: ("points", np.array(positions, dtype=np.float64).reshape(-1, 3),
+                                                              float(point_size), int(color))
+        module.lines = lambda vertices, indices, width, color, indices_type: (
+            "lines", np.array(vertices, dtype=np.float64).reshape(-1, 3), float(width), int(color), np.array(indices), indices_type)
+
+    @staticmethod
+    def flatten(plot):
+        kinds = np.array([0 if o[0] == "points" else 1 for o in plot], dtype=np.int64)
+        sizes = np.array([len(o[1]) for o in plot], dtype=np.int64)
+        data = np.vstack([np.empty((0, 3))] + [o[1] for o in plot])
+        scalar = np.array([o[2] for o in plot], dtype=np.float64)
+        color = np.array([o[3] for o in plot], dtype=np.int64)
+        return dict(kinds=kinds, sizes=sizes, data=data, scalar=scalar, color=color)
+
+
+def visualize_fixture():
+    """V1: what the reference's `Grid.visualize` hands to k3d (object order, colours drawn from `random.seed(seed)`,
+    voxel wire frames), for both visualisation types and with unused voxels; recorded through a stub k3d module."""
+    import tempfile
+
+    import octreelib.grid.grid as ref_grid_module
+    from octreelib.grid import GridVisualizationType, VisualizationConfig
+
+    rec = RecordingK3d()
+    rec.install(ref_grid_module.k3d)
+    r = np.random.default_rng(4242)
+    clouds = {p: (r.random((160, 3)) * np.array([7.0, 3.5, 3.5]) + np.array([0.4 * p, 0, 0])).astype(np.float32).astype(np.float64)
+              for p in range(3)}
+    with stable_order():
+        g = Grid(GridConfig(voxel_edge_length=4))
+        for p, c in clouds.items():
+            g.insert_points(p, c)
+        g.subdivide([lambda pts: len(pts) > 25])
+        # "unused" voxels named the way a user would: ids read off the leaves of pose 1
+        picked = [1, 4]
+        unused = [g.get_leaf_points(1)[i].id for i in picked]
+        save = {f"cloud{p}": c for p, c in clouds.items()}
+        save["edge"], save["max_points"] = np.float64(4), np.int64(25)
+        save["unused_from_pose"], save["unused_leaf_positions"] = np.int64(1), np.array(picked, dtype=np.int64)
+        cases = [("pose", GridVisualizationType.POSE, 3, []), ("voxel", GridVisualizationType.VOXEL, 5, []),
+                 ("pose_unused", GridVisualizationType.POSE, 7, unused), ("voxel_unused", GridVisualizationType.VOXEL, 9, unused)]
+        with tempfile.TemporaryDirectory() as tmp:
+            for tag, vtype, seed, unused_ids in cases:
+                cfg = VisualizationConfig(type=vtype, point_size=0.05, line_width_size=0.02, line_color=0x00FF00,
+                                          filepath=os.path.join(tmp, tag + ".html"), seed=seed, unused_voxels=list(unused_ids))
+                g.visualize(cfg)
+                flat = RecordingK3d.flatten(rec.plots[-1])
+                save.update({f"{tag}_{k}": v for k, v in flat.items()})
+                save[f"{tag}_seed"] = np.int64(seed)
+                assert open(cfg.filepath).read().startswith("<recorded")
+    np.savez_compressed(os.path.join(OUT, "visualize_edge4.npz"), **save)
+    print(f"[golden] visualize_edge4: {[len(p) for p in rec.plots]} k3d objects per call recorded from the reference")
+
+
 def main():
     rng = np.random.default_rng(2024)
     only = os.environ.get("GOLDEN_ONLY")  # GOLDEN_ONLY=late regenerates only the late-pose fixture (own RNG stream)
@@ -393,6 +470,9 @@ def main():
         return
     if only == "ransac_degenerate":
         ransac_degenerate_fixture()
+        return
+    if only == "visualize":
+        visualize_fixture()
         return
     if only == "late":
         def f32(a):
@@ -456,6 +536,7 @@ def main():
                 poses_per_batch=10)
     ransac_far_fixture()
     ransac_degenerate_fixture()
+    visualize_fixture()
 
 
 if __name__ == "__main__":
