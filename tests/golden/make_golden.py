@@ -453,6 +453,48 @@ def visualize_fixture():
     print(f"[golden] visualize_edge4: {[len(p) for p in rec.plots]} k3d objects per call recorded from the reference")
 
 
+def all_leaves_fixture():
+    """S11: `get_leaf_points(pose, non_empty=False)` (grid.py:217-232): every leaf - empty ones included - of the cells in
+    which the pose owns an octree, before and after a filter that empties leaves."""
+    r = np.random.default_rng(1111)
+    clouds = {0: (r.random((500, 3)) * np.array([6.0, 4.0, 2.0])).astype(np.float32).astype(np.float64),
+              1: (r.random((300, 3)) * np.array([3.0, 4.0, 2.0]) + np.array([3.5, 0.0, 0.0])).astype(np.float32).astype(np.float64)}
+    crit = [lambda pts: len(pts) > 12]
+
+    def table(leaves, corner, edge, npts):
+        return dict(corner=np.array([np.asarray(corner(v), dtype=np.float64) for v in leaves]).reshape(-1, 3),
+                    edge=np.array([float(edge(v)) for v in leaves]), size=np.array([npts(v) for v in leaves], dtype=np.int64))
+
+    with stable_order():
+        g = Grid(GridConfig(voxel_edge_length=2))
+        for p, c in clouds.items():
+            g.insert_points(p, c)
+        g.subdivide(crit)
+        ref1 = {p: table(g.get_leaf_points(p, non_empty=False), lambda v: v.corner_min, lambda v: v.edge_length, lambda v: v.n_points)
+                for p in clouds}
+        g.filter([lambda pts: len(pts) >= 5])
+        ref2 = {p: table(g.get_leaf_points(p, non_empty=False), lambda v: v.corner_min, lambda v: v.edge_length, lambda v: v.n_points)
+                for p in clouds}
+    og = OracleGrid(2)
+    for p, c in clouds.items():
+        og.insert_points(p, c)
+    og.subdivide([max_points_criterion(12)])
+    ora1 = {p: table(og.get_leaf_points(p, non_empty=False), lambda l: l.corner, lambda l: l.edge, lambda l: len(l.idx)) for p in clouds}
+    og.filter([lambda pts: len(pts) >= 5])
+    ora2 = {p: table(og.get_leaf_points(p, non_empty=False), lambda l: l.corner, lambda l: l.edge, lambda l: len(l.idx)) for p in clouds}
+    save = {f"cloud{p}": c for p, c in clouds.items()}
+    for p in clouds:
+        for stage, ref, ora in (("a", ref1, ora1), ("b", ref2, ora2)):
+            for k in ("corner", "edge", "size"):
+                assert ref[p][k].shape == ora[p][k].shape and (ref[p][k] == ora[p][k]).all(), (p, stage, k)
+                save[f"{stage}_p{p}_{k}"] = ref[p][k]
+        assert (ref2[p]["size"] == 0).any(), "the fixture must contain empty leaves"
+    save["edge"], save["max_points"], save["filter_min"] = np.float64(2), np.int64(12), np.int64(5)
+    np.savez_compressed(os.path.join(OUT, "all_leaves_edge2.npz"), **save)
+    print(f"[golden] all_leaves_edge2: leaves/pose incl. empty {[len(ref2[p]['size']) for p in clouds]}, empty "
+          f"{[int((ref2[p]['size'] == 0).sum()) for p in clouds]}  -- oracle == reference OK")
+
+
 def main():
     rng = np.random.default_rng(2024)
     only = os.environ.get("GOLDEN_ONLY")  # GOLDEN_ONLY=late regenerates only the late-pose fixture (own RNG stream)
@@ -473,6 +515,9 @@ def main():
         return
     if only == "visualize":
         visualize_fixture()
+        return
+    if only == "all_leaves":
+        all_leaves_fixture()
         return
     if only == "late":
         def f32(a):
@@ -537,6 +582,7 @@ def main():
     ransac_far_fixture()
     ransac_degenerate_fixture()
     visualize_fixture()
+    all_leaves_fixture()
 
 
 if __name__ == "__main__":

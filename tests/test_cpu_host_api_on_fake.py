@@ -83,3 +83,20 @@ def test_map_leaf_points_with_a_selection_callback():
         assert grid.n_points(p) == len(before[p])
     with pytest.raises(NotImplementedError):
         grid.map_leaf_points(lambda cloud: cloud + 1.0)
+
+
+def test_all_leaves_including_empty_ones():
+    """`get_leaf_points(pose, non_empty=False)` (grid.py:217-232) before and after a filter that empties leaves."""
+    g = golden("all_leaves_edge2")
+    grid = _grid(float(g["edge"]))
+    for p in (0, 1):
+        grid.insert_points(p, g[f"cloud{p}"])
+    grid.subdivide([lambda pts, n=int(g["max_points"]): len(pts) > n])
+    for stage in ("a", "b"):
+        if stage == "b":
+            grid.filter([lambda pts, n=int(g["filter_min"]): len(pts) >= n])
+        for p in (0, 1):
+            vox = grid.get_leaf_points(p, non_empty=False)
+            assert (np.array([np.asarray(v.corner_min, dtype=np.float64) for v in vox]).reshape(-1, 3) == g[f"{stage}_p{p}_corner"]).all()
+            assert (np.array([float(v.edge_length) for v in vox]) == g[f"{stage}_p{p}_edge"]).all()
+            assert (np.array([v.n_points for v in vox], dtype=np.int64) == g[f"{stage}_p{p}_size"]).all()

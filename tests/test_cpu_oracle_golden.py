@@ -101,6 +101,23 @@ def test_resubdivide_oracle_matches_reference_golden():
     assert len(g["order_differs_from_one_shot"]) > 0  # the fixture discriminates history order from a fresh build
 
 
+def test_all_leaves_oracle_matches_reference_golden():
+    """get_leaf_points(non_empty=False): empty leaves included (grid.py:217-232 -> octree.py:256-263)."""
+    g = golden("all_leaves_edge2")
+    og = OracleGrid(int(g["edge"]))
+    for p in (0, 1):
+        og.insert_points(p, g[f"cloud{p}"])
+    og.subdivide([max_points_criterion(int(g["max_points"]))])
+    for stage in ("a", "b"):
+        if stage == "b":
+            og.filter([lambda pts, n=int(g["filter_min"]): len(pts) >= n])
+        for p in (0, 1):
+            leaves = og.get_leaf_points(p, non_empty=False)
+            assert (np.array([np.asarray(l.corner, dtype=np.float64) for l in leaves]).reshape(-1, 3) == g[f"{stage}_p{p}_corner"]).all()
+            assert (np.array([float(l.edge) for l in leaves]) == g[f"{stage}_p{p}_edge"]).all()
+            assert (np.array([len(l.idx) for l in leaves]) == g[f"{stage}_p{p}_size"]).all()
+
+
 @pytest.mark.parametrize("name", RANSAC_CASES)
 def test_ransac_oracle_matches_reference_golden(name):
     g = golden(name)

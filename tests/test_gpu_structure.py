@@ -148,6 +148,23 @@ def test_golden_resubdivide_device_table_order():
     _golden_stage(grid, g, poses, "")
 
 
+def test_golden_all_leaves_including_empty_ones():
+    """`get_leaf_points(pose, non_empty=False)` against the real reference, before and after a filter that empties leaves."""
+    g = golden("all_leaves_edge2")
+    grid = Grid(GridConfig(voxel_edge_length=_edge(g)))
+    for p in (0, 1):
+        grid.insert_points(p, g[f"cloud{p}"])
+    grid.subdivide([MaxPoints(int(g["max_points"]))])
+    for stage in ("a", "b"):
+        if stage == "b":
+            grid.filter([MinPoints(int(g["filter_min"]))])
+        for p in (0, 1):
+            vox = grid.get_leaf_points(p, non_empty=False)
+            assert (np.array([np.asarray(v.corner_min, dtype=np.float64) for v in vox]).reshape(-1, 3) == g[f"{stage}_p{p}_corner"]).all()
+            assert (np.array([float(v.edge_length) for v in vox]) == g[f"{stage}_p{p}_edge"]).all()
+            assert (np.array([v.n_points for v in vox], dtype=np.int64) == g[f"{stage}_p{p}_size"]).all()
+
+
 def test_golden_late_poses_follow_the_scheme():
     """Insert after subdivide (octree_manager.py:161-171): golden vectors recorded from the real reference."""
     g = golden("late_poses_edge2")
