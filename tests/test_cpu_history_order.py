@@ -127,3 +127,29 @@ def test_same_criterion_twice_keeps_the_one_call_order():
     assert grid._host._history is not None and grid._host._history.trivial
     after = _leaf_table(grid, 0)
     assert all((a == b).all() for a, b in zip(before, after))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_call_sequences_match_the_oracle(seed):
+    """poses arriving at random times between subdivide calls of decreasing capacity, several cells"""
+    rng = np.random.default_rng(100 + seed)
+    edge = int(rng.choice([2, 4]))
+    grid = _grid(edge)
+    og = grid._host._forest.og
+    centers = rng.random((6, 3)) * 8
+    n_poses, capacity = 0, int(rng.integers(40, 120))
+    for _ in range(int(rng.integers(4, 8))):
+        if n_poses == 0 or rng.random() < 0.5:
+            n = int(rng.integers(100, 500))
+            pts = centers[rng.integers(0, 6, n)] + rng.normal(0, 0.4, (n, 3)) + (rng.random(3) * 6 if rng.random() < 0.3 else 0)
+            grid.insert_points(n_poses, pts.astype(np.float32).astype(np.float64))
+            n_poses += 1
+        else:
+            grid.subdivide([MaxPoints(capacity)])
+            capacity = max(3, int(capacity * rng.uniform(0.3, 0.9)))
+    for p in range(n_poses):
+        for non_empty in (True, False):
+            corner, edge_l, sizes, _ = _leaf_table(grid, p, non_empty)
+            w_corner, w_edge, w_sizes = _oracle_leaf_table(og, p, non_empty)
+            assert corner.shape == w_corner.shape and (corner == w_corner).all(), (p, non_empty)
+            assert (edge_l == w_edge).all() and (sizes == w_sizes).all()
