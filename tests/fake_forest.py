@@ -183,3 +183,46 @@ class FakeForest:
 
     def pose_counts(self, n_poses):
         return np.array([[self.og.n_leaves(p), self.og.n_points(p), self.og.n_nodes(p)] for p in range(n_poses)], dtype=np.int64)
+
+
+class FakeSingleCellForest(FakeForest):
+    """The forest behind a stand-alone `OctreeManager` / `Octree` / `OctreeNode`: one fixed cell, poses may be appended to."""
+
+    def __init__(self, edge, corner):
+        from oracle.structure import _Cell
+
+        super().__init__(edge)
+        self.key = tuple(float(c) for c in np.asarray(corner).reshape(3))
+        self.og.cells[self.key] = _Cell(np.asarray(corner), edge)
+
+    def _insert_into(self, pose, idx, pts):
+        from oracle.structure import _Tree
+
+        cell = self.og.cells[self.key]
+        self.og.pose_cells.setdefault(pose, [self.key])
+        tree = cell.trees.get(pose)
+        if tree is None:
+            tree = cell.trees[pose] = _Tree(cell.key, cell.edge)
+        tree.insert(tree.root, idx.astype(np.int64), pts)
+        tree.subdivide_as(tree.root, cell.scheme.root)
+        self.version += 1
+
+    def insert(self, points):
+        pose = len(self.clouds)
+        pts = np.asarray(points, dtype=np.float64).reshape(-1, 3)
+        self.clouds.append(pts)
+        self._insert_into(pose, np.arange(len(pts)), pts)
+        return pose
+
+    def insert_segments(self, points, seg_sizes, seg_pose, seg_first, n_poses_total):
+        pts = np.asarray(points, dtype=np.float64).reshape(-1, 3)
+        assert len(seg_sizes) == 1 and seg_sizes[0] == len(pts)
+        pose, first = int(seg_pose[0]), int(seg_first[0])
+        assert first == len(self.clouds[pose])
+        self.clouds[pose] = np.vstack([self.clouds[pose], pts])
+        self._insert_into(pose, first + np.arange(len(pts)), pts)
+
+    def _tables(self):
+        keys, cells, leaves, leaf_path = super()._tables()
+        cells["q"][:] = 0  # a single-cell forest has no cell coordinates
+        return keys, cells, leaves, leaf_path
