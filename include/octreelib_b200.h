@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OL_ABI_VERSION 1
+#define OL_ABI_VERSION 2
 #define OL_MAX_DEPTH 21 /* 3 * 21 = 63 Morton bits */
 
 typedef enum ol_status {
@@ -76,6 +76,9 @@ typedef struct ol_forest_stats {
     int64_t max_depth_reached;
     int64_t key_bits;      /* significant bits of the packed cell key */
     int64_t device_bytes_peak;
+    int64_t sample_oob_seen; /* 1 if a RANSAC sample index int32(R*n + start) ever fell outside its block (it is clamped
+                                into the block; the reference, ransac/cuda_ransac.py:104-107, would read a neighbouring
+                                block's point there).  bench.py asserts 0. */
 } ol_forest_stats;
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -90,8 +93,9 @@ int ol_forest_destroy(ol_forest *f);
 /* ---- Grid.insert_points, grid/grid.py:58-109 ------------------------------------------------
  * Appends one pose's cloud ([n][3] float64, host or device memory).  Returns the new pose index.
  * The re-insert ValueError (grid.py:65-66) is raised by the host, which owns pose numbers.
- * Device and pageable host sources are consumed before the call returns; a PAGE-LOCKED host source is uploaded
- * asynchronously and must stay unchanged until the next call that returns results. */
+ * Pageable host sources are consumed before the call returns; a PAGE-LOCKED host source and a DEVICE source are read
+ * asynchronously on the forest's stream and must stay unchanged until that work has run (any call that returns results
+ * has waited for it; memory recycled in stream order on the same stream - torch's caching allocator - is safe). */
 int ol_forest_insert(ol_forest *f, const double *xyz, int64_t n, int32_t src_on_device, int32_t *out_pose_index);
 
 /* The same for `count` DEVICE-resident clouds at once (a host array of device pointers and their point counts): every
@@ -119,6 +123,17 @@ int ol_forest_subdivide(ol_forest *f, int64_t max_points, const int32_t *pose_in
  * criterion list folded by the host); counts >= table_len use split_beyond. */
 int ol_forest_subdivide_table(ol_forest *f, const uint8_t *split_table_host, int64_t table_len, int32_t split_beyond,
                               const int32_t *pose_indices, int32_t n_poses);
+
+/* Size thresholds (BASELINE north_star: "splitting by point-count and size thresholds").  The reference's criteria see
+ * only the points (octree/octree.py:26), so a node-size limit is a property of the criterion OBJECT
+ * (octreelib_b200/criteria.py: MaxPoints(n, max_depth=, min_edge=), MaxDepth, MinEdge); the host folds a criterion list
+ * into a rule that is piecewise constant in the octree level: entry e applies to the levels
+ * [first_level[e], first_level[e + 1]) (first_level[0] == 0, ascending; the last entry applies to every deeper level).
+ * Threshold form: level_max_points[e] (a node splits iff count > it; 1 << 62 = never); table form (split_tables_host !=
+ * NULL): split_tables_host[e][count] with split_beyond[e] for counts >= table_len. */
+int ol_forest_subdivide_levels(ol_forest *f, const int32_t *first_level, int32_t n_entries, const int64_t *level_max_points,
+                               const uint8_t *split_tables_host, int64_t table_len, const int32_t *split_beyond,
+                               const int32_t *pose_indices, int32_t n_poses);
 
 /* ---- Grid.filter, grid/grid.py:260-267 -> octree/octree.py:102-112 --------------------------
  * A (pose, leaf) block of n points survives iff keep_table[min(n, table_len-1)] != 0; the tree

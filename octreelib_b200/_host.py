@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _views
 from ._history import LeafHistory
-from .criteria import as_threshold, fold_count_criteria
+from .criteria import CountCriterion, as_threshold, fold_count_criteria, fold_levels
 from .forest import Forest
 
 __all__ = ["ForestHost"]
@@ -74,25 +74,45 @@ class ForestHost:
         if self.empty:
             return
         idx = self._indices(pose_numbers)
-        table, beyond = fold_count_criteria(criteria, "any", 1024)
-        thr = as_threshold(table, beyond)
+        criteria = list(criteria)
+        guarded = any(isinstance(c, CountCriterion) and c.size_guarded for c in criteria)
+        # [(first level, table, beyond, criteria active from that level on)]; one entry unless node-size guards are used
+        levels = fold_levels(criteria, float(self._edge), 1024) if guarded else None
+        if levels is None:
+            table, beyond = fold_count_criteria(criteria, "any", 1024)
+            levels = [(0, table, beyond, criteria)]
+        thresholds = [as_threshold(t, b, active) if active else (1 << 62) for _, t, b, active in levels]
         if self._n_subdivides >= 1 and self._history is None:
             # a second call: from here on the reference's leaf order depends on when a node was split (_history.py);
             # every node that exists now dates from the first call
             t = _views.tables(self.forest)
             self._history = LeafHistory()
             self._history.record(t["leaves"], t["cells"], self._n_subdivides)
-        if thr is not None:
-            self.forest.subdivide(thr, idx)
+        firsts = [lv[0] for lv in levels]
+        if all(t is not None for t in thresholds):
+            if len(levels) == 1:
+                self.forest.subdivide(thresholds[0], idx)
+            else:
+                self.forest.subdivide_levels(firsts, thresholds=thresholds, pose_indices=idx)
         else:
             n_alive = self.forest.stats()["n_points_alive"]
             upto = min(n_alive + 1, _TABLE_CAP)
-            table, beyond = fold_count_criteria(criteria, "any", upto)
-            if beyond is None:
-                if upto <= n_alive:
-                    raise NotImplementedError("count criterion without a settled answer for very large nodes")
-                beyond = False
-            self.forest.subdivide_table(table, beyond, idx)
+            tables, beyonds = [], []
+            for _, _, _, active in levels:
+                if active:
+                    table, beyond = fold_count_criteria(active, "any", upto)
+                else:
+                    table, beyond = np.zeros(upto + 1, dtype=np.uint8), False
+                if beyond is None:
+                    if upto <= n_alive:
+                        raise NotImplementedError("count criterion without a settled answer for very large nodes")
+                    beyond = False
+                tables.append(table)
+                beyonds.append(beyond)
+            if len(levels) == 1:
+                self.forest.subdivide_table(tables[0], beyonds[0], idx)
+            else:
+                self.forest.subdivide_levels(firsts, tables=tables, beyonds=beyonds, pose_indices=idx)
         self._n_subdivides += 1
         if self._history is not None:
             t = _views.tables(self.forest)
@@ -103,6 +123,8 @@ class ForestHost:
         if self.empty:
             return
         idx = self._indices(pose_numbers)
+        if any(isinstance(c, CountCriterion) and c.size_guarded for c in criteria):
+            raise NotImplementedError("node-size guards (max_depth / min_edge) apply to subdivision criteria, not to filters")
         max_block = self.forest.stats()["max_block_size"]
         upto = min(max_block + 1, _TABLE_CAP)
         table, beyond = fold_count_criteria(criteria, "all", upto)

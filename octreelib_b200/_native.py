@@ -42,7 +42,7 @@ class ForestConfig(C.Structure):
 class ForestStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "n_points_inserted", "n_points_alive", "n_poses", "n_cells", "n_cell_poses", "n_leaves", "n_internal",
-        "n_blocks", "max_block_size", "max_depth_reached", "key_bits", "device_bytes_peak")]
+        "n_blocks", "max_block_size", "max_depth_reached", "key_bits", "device_bytes_peak", "sample_oob_seen")]
 
 
 class NativeLibraryMissing(ImportError):
@@ -63,6 +63,7 @@ SIGNATURES = {
     "ol_forest_insert_segments": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _i32, _i32]),
     "ol_forest_subdivide": (C.c_int, [_p, _i64, _p, _i32]),
     "ol_forest_subdivide_table": (C.c_int, [_p, _p, _i64, _i32, _p, _i32]),
+    "ol_forest_subdivide_levels": (C.c_int, [_p, _p, _i32, _p, _p, _i64, _p, _p, _i32]),
     "ol_forest_filter": (C.c_int, [_p, _p, _i64, _p, _i32]),
     "ol_forest_ransac": (C.c_int, [_p, _p, _i32, _i32, _f64, _p, _i32, _i32, _u32]),
     "ol_forest_apply_mask": (C.c_int, [_p]),
@@ -113,7 +114,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.ol_abi_version() != 1:
+        if handle.ol_abi_version() != 2:
             raise ImportError("liboctreelib_b200.so ABI version mismatch; rebuild it")
         _lib = handle
     return _lib

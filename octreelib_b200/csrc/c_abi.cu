@@ -97,7 +97,10 @@ int ol_forest_subdivide(ol_forest* f, int64_t max_points, const int32_t* pose_in
     OL_API_BEGIN
     OL_REQUIRE(max_points >= 0, OL_ERR_INVALID, "max_points must be >= 0 (an empty node would split forever)");
     ol::PoolScope pool_scope(f->impl.ctx);
-    f->impl.subdivide(max_points, nullptr, 0, 0, pose_indices, n_poses);
+    ol::Forest::SplitRule rule;
+    rule.first_level = {0};
+    rule.max_points = {max_points};
+    f->impl.subdivide(rule, pose_indices, n_poses);
     OL_API_END
 }
 
@@ -107,7 +110,38 @@ int ol_forest_subdivide_table(ol_forest* f, const uint8_t* split_table_host, int
     OL_NEED(split_table_host);
     OL_API_BEGIN
     ol::PoolScope pool_scope(f->impl.ctx);
-    f->impl.subdivide(0, split_table_host, table_len, split_beyond, pose_indices, n_poses);
+    ol::Forest::SplitRule rule;
+    rule.first_level = {0};
+    rule.tables_host = split_table_host;
+    rule.table_len = table_len;
+    rule.beyond = {split_beyond};
+    f->impl.subdivide(rule, pose_indices, n_poses);
+    OL_API_END
+}
+
+int ol_forest_subdivide_levels(ol_forest* f, const int32_t* first_level, int32_t n_entries, const int64_t* level_max_points,
+                               const uint8_t* split_tables_host, int64_t table_len, const int32_t* split_beyond,
+                               const int32_t* pose_indices, int32_t n_poses) {
+    OL_NEED(f);
+    OL_NEED(first_level);
+    OL_API_BEGIN
+    OL_REQUIRE(n_entries >= 1 && n_entries <= 64, OL_ERR_INVALID, "split rule needs 1..64 level entries");
+    OL_REQUIRE(split_tables_host ? split_beyond != nullptr : level_max_points != nullptr, OL_ERR_INVALID,
+               "split rule needs thresholds or tables");
+    ol::PoolScope pool_scope(f->impl.ctx);
+    ol::Forest::SplitRule rule;
+    for (int e = 0; e < n_entries; ++e) {
+        rule.first_level.push_back(first_level[e]);
+        if (split_tables_host) {
+            rule.beyond.push_back(split_beyond[e]);
+        } else {
+            OL_REQUIRE(level_max_points[e] >= 0, OL_ERR_INVALID, "max_points must be >= 0 (an empty node would split forever)");
+            rule.max_points.push_back(level_max_points[e]);
+        }
+    }
+    rule.tables_host = split_tables_host;
+    rule.table_len = split_tables_host ? table_len : 0;
+    f->impl.subdivide(rule, pose_indices, n_poses);
     OL_API_END
 }
 

@@ -6,6 +6,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
+#include <iterator>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -103,9 +106,17 @@ struct Ctx {
     int num_sms = 148;
     size_t bytes_live = 0, bytes_peak = 0;
 
-    // Freed temporaries are parked in a small exact-size pool and handed out again inside the same public call
-    // (the level loops allocate the same sizes over and over; every allocator callback is a trip into Python).
-    // trim_pool() returns everything at the end of each C-ABI entry point, so nothing is held between calls.
+    // ---- device memory ---------------------------------------------------------------------------------------------
+    // Every allocator callback is a trip into the host language (Python: ~5-10 us per torch.empty), and one pipeline step
+    // makes several hundred short-lived allocations - measured as the largest part of the time the GPU spent waiting for
+    // the host.  So:
+    //   * requests up to ARENA_MAX_REQUEST bytes are served by a native best-fit ARENA that sub-allocates chunks obtained
+    //     from the callback (4 MB doubling to 128 MB).  Everything runs on ONE stream, so a block may be reused the moment
+    //     it is freed (stream order), exactly like torch's caching allocator on a single stream.  Chunks stay with the Ctx
+    //     until it is destroyed (release_arena()).
+    //   * larger requests go to the callback directly; inside one public call freed ones are parked in a small
+    //     exact-size pool and handed out again (the level loops allocate the same sizes over and over).  trim_pool()
+    //     returns them at the end of each C-ABI entry point.
     struct Parked {
         void* ptr;
         size_t bytes;
@@ -113,29 +124,111 @@ struct Ctx {
     std::vector<Parked> pool;
     size_t pool_bytes = 0;
     static constexpr size_t POOL_MAX_ENTRIES = 64;
+    static constexpr size_t ARENA_ALIGN = 512;
+    static constexpr size_t ARENA_MAX_REQUEST = 32u << 20;
+    static constexpr size_t ARENA_FIRST_CHUNK = 4u << 20;
+    static constexpr size_t ARENA_MAX_CHUNK = 128u << 20;
+    struct ArenaBlock {
+        size_t size;
+        int chunk;
+    };
+    std::map<char*, ArenaBlock> arena_free;             // by address (coalescing)
+    std::multimap<size_t, char*> arena_by_size;         // best fit
+    std::vector<std::pair<char*, size_t>> arena_chunks;
+    size_t arena_next_chunk = ARENA_FIRST_CHUNK;
+    size_t arena_bytes = 0;
+    bool arena_enabled = true;
+
+    static size_t arena_round(size_t b) { return (b + ARENA_ALIGN - 1) / ARENA_ALIGN * ARENA_ALIGN; }
+    void arena_insert_free(char* p, size_t size, int chunk) {
+        // merge with the free neighbours of the same chunk
+        auto next = arena_free.lower_bound(p);
+        if (next != arena_free.end() && next->second.chunk == chunk && p + size == next->first) {
+            size += next->second.size;
+            arena_erase_size(next->second.size, next->first);
+            next = arena_free.erase(next);
+        }
+        if (next != arena_free.begin()) {
+            auto prev = std::prev(next);
+            if (prev->second.chunk == chunk && prev->first + prev->second.size == p) {
+                arena_erase_size(prev->second.size, prev->first);
+                p = prev->first;
+                size += prev->second.size;
+                arena_free.erase(prev);
+            }
+        }
+        arena_free[p] = ArenaBlock{size, chunk};
+        arena_by_size.emplace(size, p);
+    }
+    void arena_erase_size(size_t size, char* p) {
+        auto range = arena_by_size.equal_range(size);
+        for (auto it = range.first; it != range.second; ++it)
+            if (it->second == p) {
+                arena_by_size.erase(it);
+                return;
+            }
+    }
+    void* arena_alloc(size_t sz) {
+        auto it = arena_by_size.lower_bound(sz);
+        if (it == arena_by_size.end()) {
+            size_t chunk = std::max(arena_next_chunk, sz);
+            arena_next_chunk = std::min(arena_next_chunk * 2, ARENA_MAX_CHUNK);
+            char* base = static_cast<char*>(raw_alloc(chunk));
+            arena_chunks.emplace_back(base, chunk);
+            arena_bytes += chunk;
+            arena_insert_free(base, chunk, (int)arena_chunks.size() - 1);
+            it = arena_by_size.lower_bound(sz);
+        }
+        char* p = it->second;
+        const ArenaBlock blk = arena_free[p];
+        arena_by_size.erase(it);
+        arena_free.erase(p);
+        if (blk.size > sz) {
+            arena_free[p + sz] = ArenaBlock{blk.size - sz, blk.chunk};
+            arena_by_size.emplace(blk.size - sz, p + sz);
+        }
+        return p;
+    }
+    void arena_free_block(char* p, size_t sz) {
+        // the owning chunk: the last chunk whose base is <= p (few chunks: linear scan)
+        int chunk = -1;
+        for (size_t i = 0; i < arena_chunks.size(); ++i)
+            if (p >= arena_chunks[i].first && p < arena_chunks[i].first + arena_chunks[i].second) chunk = (int)i;
+        arena_insert_free(p, sz, chunk);
+    }
+    void release_arena() {
+        for (auto& c : arena_chunks) raw_free(c.first);
+        arena_chunks.clear();
+        arena_free.clear();
+        arena_by_size.clear();
+        arena_bytes = 0;
+        arena_next_chunk = ARENA_FIRST_CHUNK;
+    }
 
     void* alloc(size_t bytes) {
         if (bytes == 0) bytes = 16;
+        bytes_live += bytes;
+        if (bytes_live > bytes_peak) bytes_peak = bytes_live;
+        if (arena_enabled && bytes <= ARENA_MAX_REQUEST) return arena_alloc(arena_round(bytes));
         for (size_t i = pool.size(); i-- > 0;) {
             if (pool[i].bytes == bytes) {
                 void* p = pool[i].ptr;
                 pool[i] = pool.back();
                 pool.pop_back();
                 pool_bytes -= bytes;
-                bytes_live += bytes;
-                if (bytes_live > bytes_peak) bytes_peak = bytes_live;
                 return p;
             }
         }
-        void* p = raw_alloc(bytes);
-        bytes_live += bytes;
-        if (bytes_live > bytes_peak) bytes_peak = bytes_live;
-        return p;
+        return raw_alloc(bytes);
     }
     void free(void* p, size_t bytes) {
         if (!p) return;
         if (bytes == 0) bytes = 16;
         bytes_live -= bytes;
+        if (arena_enabled && bytes <= ARENA_MAX_REQUEST) {
+            arena_free_block(static_cast<char*>(p), arena_round(bytes));
+            return;
+        }
         if (pool_enabled && pool.size() < POOL_MAX_ENTRIES) {
             pool.push_back(Parked{p, bytes});
             pool_bytes += bytes;
@@ -170,7 +263,10 @@ struct Ctx {
             cudaFreeAsync(p, stream);
     }
     void sync() { OL_CUDA(cudaStreamSynchronize(stream)); }
-    ~Ctx() { trim_pool(); }
+    ~Ctx() {
+        trim_pool();
+        release_arena();
+    }
 };
 
 // enables the temporary pool for the duration of one public call

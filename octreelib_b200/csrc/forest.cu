@@ -151,11 +151,13 @@ __global__ void __launch_bounds__(BBOX_THREADS) bbox_kernel(const double* __rest
 // =============================================================================================
 // K1: packed cell key + in-cell Morton code per point (one pass over the raw cloud)
 // =============================================================================================
-template <typename MortT>
+// KeyT = uint32_t when the packed cell key (+ pose bits) fits 32 bits - every BASELINE configuration; the grid-wide
+// sort then moves 4 + 4 bytes per pair and pass instead of 8 + 4.
+template <typename KeyT, typename MortT>
 __global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ xyz, uint32_t n, KeyParams kp,
                                                      const uint32_t* __restrict__ seg_start,
                                                      const int32_t* __restrict__ seg_pose, int n_seg,
-                                                     uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                     KeyT* __restrict__ keys, uint32_t* __restrict__ vals,
                                                      MortT* __restrict__ mort, uint32_t* __restrict__ err) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ 
     int bad;
     MortT m = (MortT)point_morton(p, c, kp.edge, kp.depth, &bad);
     if (bad < kp.depth) m |= MortBits<MortT>::bad;
-    keys[r] = key;
+    keys[r] = (KeyT)key;
     vals[r] = r;  // the sort's payload: the point's rank
     mort[r] = m;
     if (e) atomicOr(err, e);
@@ -221,10 +223,11 @@ __global__ void __launch_bounds__(256) remorton_kernel(const double* __restrict_
 // K3: run-length segmentation of the sorted keys
 // =============================================================================================
 // key / emit functors for segment_runs (primitives.cuh)
+template <typename KeyT>
 struct CellKeyFn {  // grid cell of a sorted position: the packed key without its pose bits
-    const uint64_t* keys;
+    const KeyT* keys;
     int pose_bits;
-    __device__ uint64_t operator()(uint32_t i) const { return keys[i] >> pose_bits; }
+    __device__ uint64_t operator()(uint32_t i) const { return (uint64_t)(keys[i] >> pose_bits); }
 };
 struct CellEmitFn {
     uint64_t* cell_key;
@@ -398,43 +401,60 @@ __host__ __device__ inline uint64_t replay_key(uint32_t cell, uint32_t depth, ui
     return ((uint64_t)cell << 32) | ((uint64_t)depth << 27) | (path & 0x7ffffffull);
 }
 
-__global__ void decide_kernel(uint32_t L, const uint32_t* __restrict__ lstart, const uint8_t* __restrict__ ldepth,
-                              int level, const uint32_t* __restrict__ wcount, long long max_points,
-                              const uint8_t* __restrict__ table, long long table_len, int beyond, int max_depth,
-                              const uint64_t* __restrict__ replay_keys, uint32_t n_replay, const uint32_t* __restrict__ lcell,
-                              const uint64_t* __restrict__ lpath, uint32_t* __restrict__ splitf, uint32_t* __restrict__ expand,
-                              uint32_t* __restrict__ err) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= L) return;
-    bool want = false;
-    if (replay_keys) {
-        // scheme replay (octree_manager.py:171 -> octree.py:222-227): split exactly the nodes of the recorded shape
-        if (ldepth[k] == level && level < REPLAY_MAX_DEPTH) {
-            const uint64_t key = replay_key(lcell[k], (uint32_t)level, lpath[k]);
-            uint32_t lo = 0, hi = n_replay;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (replay_keys[mid] < key)
-                    lo = mid + 1;
-                else
-                    hi = mid;
+// Split decision of one level as the INPUT functor of a scan over the leaves (transform_scan, primitives.cuh): the scan
+// yields the index of every splitting leaf among the splitting leaves, and the output functor packs both into
+//     sinfo[k] = (number of splitting leaves before k) << 1 | (k splits)
+// which is all the partition kernels need: split index s = sinfo >> 1 (if the low bit is set), and the leaf's index in
+// the next level's table = k + 7 * (sinfo >> 1) (every split replaces one leaf by eight).
+struct DecideIn {
+    const uint32_t* lstart;
+    const uint8_t* ldepth;
+    int level;
+    const uint32_t* wcount;
+    long long max_points;
+    const uint8_t* table;
+    long long table_len;
+    int beyond;
+    int max_depth;
+    const uint64_t* replay_keys;
+    uint32_t n_replay;
+    const uint32_t* lcell;
+    const uint64_t* lpath;
+    uint32_t* err;
+    __device__ uint32_t operator()(size_t k) const {
+        bool want = false;
+        if (replay_keys) {
+            // scheme replay (octree_manager.py:171 -> octree.py:222-227): split exactly the nodes of the recorded shape
+            if (ldepth[k] == level && level < REPLAY_MAX_DEPTH) {
+                const uint64_t key = replay_key(lcell[k], (uint32_t)level, lpath[k]);
+                uint32_t lo = 0, hi = n_replay;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (replay_keys[mid] < key)
+                        lo = mid + 1;
+                    else
+                        hi = mid;
+                }
+                want = lo < n_replay && replay_keys[lo] == key;
             }
-            want = lo < n_replay && replay_keys[lo] == key;
+        } else if (ldepth[k] == level) {
+            long long cnt = wcount ? (long long)wcount[k] : (long long)(lstart[k + 1] - lstart[k]);
+            if (table)
+                want = (cnt < table_len) ? (table[cnt] != 0) : (beyond != 0);
+            else
+                want = cnt > max_points;
+            if (want && level >= max_depth) {
+                atomicOr(err, (uint32_t)DEVERR_DEPTH_CAP);
+                want = false;
+            }
         }
-    } else if (ldepth[k] == level) {
-        long long cnt = wcount ? (long long)wcount[k] : (long long)(lstart[k + 1] - lstart[k]);
-        if (table)
-            want = (cnt < table_len) ? (table[cnt] != 0) : (beyond != 0);
-        else
-            want = cnt > max_points;
-        if (want && level >= max_depth) {
-            atomicOr(err, (uint32_t)DEVERR_DEPTH_CAP);
-            want = false;
-        }
+        return want ? 1u : 0u;
     }
-    splitf[k] = want ? 1u : 0u;
-    expand[k] = want ? 8u : 1u;
-}
+};
+struct DecideOut {
+    uint32_t* sinfo;
+    __device__ void operator()(size_t k, uint32_t ex, uint32_t v) const { sinfo[k] = (ex << 1) | v; }
+};
 
 constexpr int PART_THREADS = 256;
 constexpr int PART_ITEMS = 8;
@@ -449,9 +469,9 @@ __device__ __forceinline__ uint32_t level_digit(MortT m, int shift) {
 template <typename MortT>
 __global__ void __launch_bounds__(PART_THREADS) part_hist_kernel(const uint32_t* __restrict__ leaf_of,
                                                                   const MortT* __restrict__ mort,
-                                                                  const uint32_t* __restrict__ sidx, uint32_t n,
+                                                                  const uint32_t* __restrict__ sinfo, uint32_t n,
                                                                   uint32_t num_tiles, uint32_t n_split, int shift,
-                                                                  uint32_t* __restrict__ tile_hist,
+                                                                  uint32_t* __restrict__ tile_hist /*[8][tiles]*/,
                                                                   uint32_t* __restrict__ leaf_cnt /*[8][n_split]*/) {
     __shared__ uint32_t h[8];
     if (threadIdx.x < 8) h[threadIdx.x] = 0;
@@ -463,8 +483,8 @@ __global__ void __launch_bounds__(PART_THREADS) part_hist_kernel(const uint32_t*
         uint32_t i = base + j * PART_THREADS + threadIdx.x;
         uint32_t key = 0xffffffffu;  // (split-leaf index << 3) | digit
         if (i < n) {
-            const uint32_t sp = sidx[leaf_of[i]];
-            if (sp != 0xffffffffu) key = (sp << 3) | level_digit(mort[i], shift);
+            const uint32_t si = sinfo[leaf_of[i]];
+            if (si & 1u) key = ((si >> 1) << 3) | level_digit(mort[i], shift);
         }
         // positions are leaf-ordered, so a warp holds few distinct (leaf, digit) pairs: one atomic per pair
         const uint32_t peers = __match_any_sync(0xffffffffu, key);
@@ -492,29 +512,6 @@ __device__ __forceinline__ void packed_inc(Packed8& p, uint32_t g) {
         p.hi += one;
 }
 
-// split index of every leaf (~0 = does not split): one gather per point in the partition kernels instead of two
-__global__ void split_index_kernel(uint32_t L, const uint32_t* __restrict__ splitf, const uint32_t* __restrict__ iidx,
-                                   uint32_t* __restrict__ sidx) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < L) sidx[k] = splitf[k] ? iidx[k] : 0xffffffffu;
-}
-
-// per split leaf s and digit g: (first destination of the leaf's digit-g child) - S_g(first position of the leaf), so that
-// the move kernel needs ONE 4-byte gather per point instead of walking leaf_cnt / leaf_beg (up to 9 dependent gathers)
-__global__ void part_delta_kernel(uint32_t L, const uint32_t* __restrict__ splitf, const uint32_t* __restrict__ iidx,
-                                  const uint32_t* __restrict__ lstart, const uint32_t* __restrict__ leaf_cnt,
-                                  const uint32_t* __restrict__ leaf_beg, uint32_t n_split, uint32_t* __restrict__ delta /*[n_split][8]*/) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= L || !splitf[k]) return;
-    const uint32_t s = iidx[k];
-    uint32_t run = lstart[k];
-#pragma unroll
-    for (uint32_t g = 0; g < 8; ++g) {
-        delta[(size_t)s * 8 + g] = run - leaf_beg[(size_t)g * n_split + s];
-        run += leaf_cnt[(size_t)g * n_split + s];
-    }
-}
-
 // Stable 8-way partition of every splitting leaf's range in ONE pass (everything else is copied through).
 // With S_g(i) = number of active positions before i whose digit is g (a global running count: the tile's offset from
 // the scanned tile histograms plus a running count inside the tile), the destination of an active position i of leaf k
@@ -526,7 +523,7 @@ __global__ void part_delta_kernel(uint32_t L, const uint32_t* __restrict__ split
 template <typename MortT>
 __global__ void __launch_bounds__(PART_THREADS, 3) part_move_kernel(
     const uint32_t* __restrict__ leaf_of, const MortT* __restrict__ mort, const uint32_t* __restrict__ perm,
-    const uint32_t* __restrict__ sidx, const uint32_t* __restrict__ newidx, const uint32_t* __restrict__ tile_off,
+    const uint32_t* __restrict__ sinfo, const uint32_t* __restrict__ tile_off,
     const uint32_t* __restrict__ delta, uint32_t n, uint32_t num_tiles, int shift, int level,
     uint32_t* __restrict__ leaf_out, MortT* __restrict__ mort_out, uint32_t* __restrict__ perm_out,
     // for the out-of-node re-check
@@ -578,12 +575,12 @@ __global__ void __launch_bounds__(PART_THREADS, 3) part_move_kernel(
         }
     }
 #pragma unroll
-    uint32_t sp[PART_ITEMS];  // split index of the item's leaf (~0: the leaf does not split)
+    uint32_t sp[PART_ITEMS];  // sinfo of the item's leaf
 #pragma unroll
     for (int j = 0; j < PART_ITEMS; ++j) {
         g[j] = 8u;
-        sp[j] = first + j < n ? sidx[leaf[j]] : 0xffffffffu;
-        if (sp[j] != 0xffffffffu) {
+        sp[j] = first + j < n ? sinfo[leaf[j]] : 0u;  // (splits before) << 1 | splits
+        if (sp[j] & 1u) {
             g[j] = level_digit(m[j], shift);
             packed_inc(cnt, g[j]);
         }
@@ -616,11 +613,11 @@ __global__ void __launch_bounds__(PART_THREADS, 3) part_move_kernel(
         const uint32_t i = first + j;
         if (i >= n) break;
         const uint32_t k = leaf[j];
-        uint32_t dst = i, nl = newidx[k];
+        uint32_t dst = i, nl = k + 7u * (sp[j] >> 1);
         if (g[j] < 8u) {
             const uint32_t S = G[g[j]] + packed_get(run, g[j]);
             packed_inc(run, g[j]);
-            dst = S + delta[(size_t)sp[j] * 8 + g[j]];
+            dst = S + delta[(size_t)(sp[j] >> 1) * 8 + g[j]];
             nl += g[j];
             if (m[j] & MortBits<MortT>::bad) {
                 // the point left its node at some level: an error only if that level is being split
@@ -675,9 +672,15 @@ __global__ void __launch_bounds__(PART_THREADS, 3) part_move_kernel(
     }
 }
 
-__global__ void expand_leaves_kernel(uint32_t L, uint32_t A, uint32_t I_old, const uint32_t* __restrict__ splitf,
-                                     const uint32_t* __restrict__ iidx, const uint32_t* __restrict__ newidx,
-                                     const uint32_t* __restrict__ leaf_cnt, uint32_t n_split,
+// New leaf / internal tables of a level, plus the partition deltas.  `scanned` is the exclusive scan of the level's flat
+// histogram buffer [ tile_hist (8 x tiles) | leaf_cnt (8 x n_split) ], `*total` its grand total:
+//   leaf_beg[g][s] = scanned[8 tiles + g n_split + s] - scanned[8 tiles]   (running count of digit g before split leaf s)
+//   leaf_cnt[g][s] = difference to the next entry
+//   delta[s][g]    = (first destination of the leaf's digit-g child) - leaf_beg[g][s], so that the move kernel needs ONE
+//                    4-byte gather per point.
+__global__ void expand_leaves_kernel(uint32_t L, uint32_t A, uint32_t I_old, const uint32_t* __restrict__ sinfo,
+                                     const uint32_t* __restrict__ scanned, const unsigned long long* __restrict__ total,
+                                     uint32_t num_tiles, uint32_t n_split,
                                      const uint32_t* __restrict__ lstart, const uint32_t* __restrict__ lcell,
                                      const int32_t* __restrict__ lparent, const uint64_t* __restrict__ lpath,
                                      const uint8_t* __restrict__ ldepth, const uint8_t* __restrict__ lchild,
@@ -685,11 +688,14 @@ __global__ void expand_leaves_kernel(uint32_t L, uint32_t A, uint32_t I_old, con
                                      int32_t* __restrict__ lparent_n, uint64_t* __restrict__ lpath_n,
                                      uint8_t* __restrict__ ldepth_n, uint8_t* __restrict__ lchild_n,
                                      uint32_t* __restrict__ istart, uint32_t* __restrict__ icell,
-                                     uint8_t* __restrict__ idepth, uint64_t* __restrict__ ipath) {
+                                     uint8_t* __restrict__ idepth, uint64_t* __restrict__ ipath, int32_t* __restrict__ iparent,
+                                     uint8_t* __restrict__ ichild, uint32_t* __restrict__ delta /*[n_split][8]*/) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= L) return;
-    const uint32_t j0 = newidx[k];
-    if (!splitf[k]) {
+    const uint32_t si = sinfo[k];
+    const uint32_t s = si >> 1;
+    const uint32_t j0 = k + 7u * s;
+    if (!(si & 1u)) {
         lstart_n[j0] = lstart[k];
         lcell_n[j0] = lcell[k];
         lparent_n[j0] = lparent[k];
@@ -697,17 +703,24 @@ __global__ void expand_leaves_kernel(uint32_t L, uint32_t A, uint32_t I_old, con
         ldepth_n[j0] = ldepth[k];
         lchild_n[j0] = lchild[k];
     } else {
-        const uint32_t s = iidx[k];
         const uint32_t id = I_old + s;
         istart[id] = lstart[k];
         icell[id] = lcell[k];
         idepth[id] = ldepth[k];
         ipath[id] = lpath[k];
+        iparent[id] = lparent[k];
+        ichild[id] = lchild[k];
+        const size_t flat_len = (size_t)8 * num_tiles + (size_t)8 * n_split;
+        const uint32_t t_tiles = scanned[(size_t)8 * num_tiles];
         uint32_t run = lstart[k];
         for (uint32_t c = 0; c < 8; ++c) {
+            const size_t idx = (size_t)8 * num_tiles + (size_t)c * n_split + s;
+            const uint32_t e0 = scanned[idx];
+            const uint32_t e1 = idx + 1 < flat_len ? scanned[idx + 1] : (uint32_t)*total;
+            delta[(size_t)s * 8 + c] = run - (e0 - t_tiles);
             const uint32_t j = j0 + c;
             lstart_n[j] = run;
-            run += leaf_cnt[(size_t)c * n_split + s];
+            run += e1 - e0;
             lcell_n[j] = lcell[k];
             lparent_n[j] = (int32_t)id;
             lpath_n[j] = (lpath[k] << 3) | (uint64_t)c;
@@ -716,6 +729,18 @@ __global__ void expand_leaves_kernel(uint32_t L, uint32_t A, uint32_t I_old, con
         }
     }
     if (k == L - 1) lstart_n[L_new] = A;
+}
+
+// current shape := one leaf per cell (reset_shape)
+__global__ void init_leaves_kernel(uint32_t L, uint32_t* __restrict__ lcell, int32_t* __restrict__ lparent, uint64_t* __restrict__ lpath,
+                                   uint8_t* __restrict__ ldepth, uint8_t* __restrict__ lchild) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= L) return;
+    lcell[k] = k;
+    lparent[k] = -1;
+    lpath[k] = 0ull;
+    ldepth[k] = 0;
+    lchild[k] = 0;
 }
 
 // ---- scheme replay: record the split nodes by cell COORDINATES (the packed key changes when the grid is rebuilt) ----
@@ -770,48 +795,86 @@ __global__ void replay_keys_kernel(uint32_t n, const long long* __restrict__ q_i
 // =============================================================================================
 // K5: leaf enumeration order (reference `_cached_leaves` order) and leaf geometry
 // =============================================================================================
-__global__ void internal_keys_kernel(uint32_t I, const uint32_t* __restrict__ istart, const uint8_t* __restrict__ idepth,
-                                     uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+// The order needs no sort.  Internal nodes are created level by level (ids of level d are the contiguous range
+// [begin[d], begin[d + 1]) and ascend with the position of the node's range), so the pre-order rank of node i
+// (range start s, depth d) - its rank by (start, depth, id) - is a sum of bisections, one per level:
+//   levels above d: nodes with start <= s, its own level: i - begin[d], levels below d: nodes with start < s.
+// With imask[p] = set of children of p that are internal, node p emits 8 - popc(imask[p]) leaves; an exclusive scan of
+// these counts in rank order (leafbase) gives, for a leaf with parent p and child id c,
+//   cache position = first leaf of the cell + leafbase[rank p] - leafbase[rank of the cell's root] + popc(~imask[p] & below c)
+// (the cell's leaves occupy the same index range in depth-first and in enumeration order).
+struct LevelBegins {
+    uint32_t b[OL_MAX_DEPTH + 2];
+    int n;  // levels
+};
+
+__global__ void internal_mask_kernel(uint32_t I, const int32_t* __restrict__ iparent, const uint8_t* __restrict__ ichild,
+                                     uint32_t* __restrict__ imask) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= I) return;
-    keys[i] = ((uint64_t)istart[i] << 8) | (uint64_t)idepth[i];
-    vals[i] = i;
+    const int32_t p = iparent[i];
+    if (p >= 0) atomicOr(&imask[p], 1u << ichild[i]);
 }
 
-__global__ void internal_rank_kernel(uint32_t I, const uint32_t* __restrict__ sorted_ids, const uint8_t* __restrict__ idepth,
-                                     const uint32_t* __restrict__ icell, uint32_t* __restrict__ irank,
-                                     uint32_t* __restrict__ cell_ifirst) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= I) return;
-    uint32_t id = sorted_ids[j];
-    irank[id] = j;
-    if (idepth[id] == 0) cell_ifirst[icell[id]] = j;
+__global__ void internal_rank_kernel(uint32_t I, const uint32_t* __restrict__ istart, const uint8_t* __restrict__ idepth,
+                                     const uint32_t* __restrict__ icell, const uint32_t* __restrict__ imask, LevelBegins lv,
+                                     uint32_t* __restrict__ irank, uint32_t* __restrict__ nlc_r, uint32_t* __restrict__ cell_ifirst) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= I) return;
+    const uint32_t s = istart[i];
+    const int d = idepth[i];
+    uint32_t rank = 0;
+    for (int dd = 0; dd < lv.n; ++dd) {
+        const uint32_t b0 = lv.b[dd], b1 = lv.b[dd + 1];
+        if (dd == d) {
+            rank += i - b0;
+            continue;
+        }
+        // first id in [b0, b1) whose start is > s (levels above) or >= s (levels below)
+        uint32_t lo = b0, hi = b1;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const uint32_t v = istart[mid];
+            const bool before = dd < d ? (v <= s) : (v < s);
+            if (before)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        rank += lo - b0;
+    }
+    irank[i] = rank;
+    nlc_r[rank] = 8u - (uint32_t)__popc(imask[i]);
+    if (d == 0) cell_ifirst[icell[i]] = rank;
 }
 
-__global__ void leaf_keys_kernel(uint32_t L, const uint32_t* __restrict__ lcell, const int32_t* __restrict__ lparent,
-                                 const uint8_t* __restrict__ lchild, const uint32_t* __restrict__ irank,
-                                 const uint32_t* __restrict__ cell_ifirst, uint64_t* __restrict__ keys,
-                                 uint32_t* __restrict__ vals) {
+// first leaf of every cell (every cell owns at least one leaf; the range is the same in both leaf orders)
+__global__ void cell_first_leaf_kernel(uint32_t L, const uint32_t* __restrict__ lcell, uint32_t* __restrict__ cell_leaf_begin) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= L) return;
-    uint32_t c = lcell[k];
-    uint64_t low = 0;
-    if (lparent[k] >= 0) low = ((uint64_t)(irank[lparent[k]] - cell_ifirst[c]) << 3) | (uint64_t)lchild[k];
-    keys[k] = ((uint64_t)c << 32) | low;
-    vals[k] = k;
+    const uint32_t c = lcell[k];
+    if (k == 0 || lcell[k - 1] != c) cell_leaf_begin[c] = k;
 }
 
-__global__ void leaf_geometry_kernel(uint32_t L, const uint32_t* __restrict__ leaf_by_cache,
-                                     const uint32_t* __restrict__ lcell, const uint64_t* __restrict__ lpath,
-                                     const uint8_t* __restrict__ ldepth, const uint64_t* __restrict__ cell_key,
-                                     KeyParams kp, uint32_t* __restrict__ cache_rank, double* __restrict__ corner,
-                                     double* __restrict__ edge, uint32_t* __restrict__ cell_leaf_begin) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= L) return;
-    const uint32_t k = leaf_by_cache[j];
-    cache_rank[k] = j;
+__global__ void leaf_order_geometry_kernel(uint32_t L, const uint32_t* __restrict__ lcell, const int32_t* __restrict__ lparent,
+                                           const uint8_t* __restrict__ lchild, const uint64_t* __restrict__ lpath,
+                                           const uint8_t* __restrict__ ldepth, const uint32_t* __restrict__ irank,
+                                           const uint32_t* __restrict__ imask, const uint32_t* __restrict__ leafbase,
+                                           const uint32_t* __restrict__ cell_ifirst, const uint32_t* __restrict__ cell_leaf_begin,
+                                           const uint64_t* __restrict__ cell_key, KeyParams kp, uint32_t* __restrict__ cache_rank,
+                                           uint32_t* __restrict__ leaf_by_cache, double* __restrict__ corner,
+                                           double* __restrict__ edge) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= L) return;
     const uint32_t c = lcell[k];
-    if (j == 0 || lcell[leaf_by_cache[j - 1]] != c) cell_leaf_begin[c] = j;
+    uint32_t j = cell_leaf_begin[c];
+    const int32_t p = lparent[k];
+    if (p >= 0) {
+        const uint32_t ch = lchild[k];
+        j += leafbase[irank[p]] - leafbase[cell_ifirst[c]] + (uint32_t)__popc(~imask[p] & ((1u << ch) - 1u));
+    }
+    cache_rank[k] = j;
+    leaf_by_cache[j] = k;
     long long q[3] = {0, 0, 0};
     if (!kp.single_cell) unpack_cell(kp, cell_key[c], q);
     double co[3];

@@ -1,6 +1,7 @@
 // Forest: the device-resident state behind one Grid (many cells x many poses) or one
 // OctreeManager / Octree (a single cell).  See DESIGN.md for the data layout.
 #pragma once
+#include <initializer_list>
 #include <vector>
 
 #include "common.cuh"
@@ -72,10 +73,14 @@ struct Forest {
     DevBuf<uint8_t> ldepth;      // [L]
     DevBuf<uint8_t> lchild;      // [L]
     uint32_t I = 0;
+    size_t icap = 0;             // capacity of the internal-node arrays (grown geometrically: no copy per level)
     DevBuf<uint32_t> istart;     // [I] first position of the internal node's range
     DevBuf<uint32_t> icell;      // [I]
     DevBuf<uint8_t> idepth;      // [I]
     DevBuf<uint64_t> ipath;      // [I] Morton digits from the cell root
+    DevBuf<int32_t> iparent;     // [I] parent internal node, -1 for a cell root
+    DevBuf<uint8_t> ichild;      // [I] child id under the parent
+    std::vector<uint32_t> level_ibegin;  // host: internal ids of depth d are [level_ibegin[d], level_ibegin[d + 1])
     int depth_reached = 0;
 
     // ---- derived tables (rebuilt lazily after the shape or the point set changes) ---------------
@@ -101,6 +106,8 @@ struct Forest {
     DevBuf<int32_t> blk_pose;    // [NB]
     DevBuf<uint32_t> blk_of_pos; // [A] position -> block
     uint32_t max_block = 0;
+    bool max_block_known = false;  // block_max_kernel has been launched into d_max_block but not read back yet
+    DevBuf<uint32_t> d_max_block;  // [1]
 
     // ---- RANSAC results of the last ol_forest_ransac call ----------------------------------------
     bool ransac_valid = false;   // `mask` is aligned with the current point order (not applied yet)
@@ -136,10 +143,36 @@ struct Forest {
     void ensure_alive();     // alive_r := membership in the current order, if apply_keep left it stale
     void extend_morton();    // Morton codes at the full depth (lazy: MORTON_INITIAL_DEPTH levels first)
     void reset_shape();      // current := base (every cell one leaf)
-    void subdivide(int64_t max_points, const uint8_t* table, int64_t table_len, int beyond, const int32_t* poses,
-                   int n_poses_listed);  // K4
-    void split_levels(int64_t max_points, const uint8_t* d_table, int64_t table_len, int beyond, const uint8_t* d_listed,
-                      int n_listed, const uint64_t* replay_keys, uint32_t n_replay);  // the level loop of K4
+    // Split rule of K4, piecewise constant in the octree level (node-size thresholds: criteria.py): entry e applies to the
+    // levels [first_level[e], first_level[e + 1]); threshold form (count > max_points[e]) or table form
+    // (tables[e][count], counts >= table_len use beyond[e]).
+    struct SplitRule {
+        std::vector<int> first_level;
+        std::vector<int64_t> max_points;
+        const uint8_t* tables_host = nullptr;  // [entries][table_len]
+        int64_t table_len = 0;
+        std::vector<int> beyond;
+        int entry_for(int level) const {
+            int e = 0;
+            for (size_t i = 0; i < first_level.size(); ++i)
+                if (first_level[i] <= level) e = (int)i;
+            return e;
+        }
+    };
+    void subdivide(const SplitRule& rule, const int32_t* poses, int n_poses_listed);  // K4
+    void split_levels(const SplitRule* rule, const uint8_t* d_tables, const uint8_t* d_listed, int n_listed,
+                      const uint64_t* replay_keys, uint32_t n_replay);  // the level loop of K4
+    void reserve_internal(size_t need);
+    void ensure_max_block();
+    // copies up to 8 small device objects into the pinned scratch block back to back with ONE stream synchronisation
+    struct ReadItem {
+        const void* src;
+        size_t bytes;
+        void* dst;
+    };
+    void read_back(std::initializer_list<ReadItem> items);
+    void throw_device_errors(uint32_t e);
+    void note_ransac_flags(uint32_t e);
     void save_shape();       // record the split nodes before a rebuild
     void replay_shape();     // impose the recorded shape on the rebuilt grid
     void ensure_shape();

@@ -58,20 +58,40 @@ Forest::~Forest() {
 }
 
 uint32_t Forest::read_u32(const uint32_t* dptr) {
-    OL_CUDA(cudaMemcpyAsync(pinned, dptr, 4, cudaMemcpyDeviceToHost, ctx.stream));
-    ctx.sync();
-    return *(uint32_t*)pinned;
+    uint32_t v = 0;
+    read_back({{dptr, 4, &v}});
+    return v;
 }
 unsigned long long Forest::read_u64(const unsigned long long* dptr) {
-    OL_CUDA(cudaMemcpyAsync(pinned, dptr, 8, cudaMemcpyDeviceToHost, ctx.stream));
-    ctx.sync();
-    return *(unsigned long long*)pinned;
+    unsigned long long v = 0;
+    read_back({{dptr, 8, &v}});
+    return v;
 }
 
-void Forest::check_device_errors() {
-    uint32_t e = read_u32(d_err.get());
-    if (!e) return;
-    d_err.zero();
+// several scalars, one synchronisation (every stream synchronisation costs the GPU ~20 us of idle time: the host has to
+// wake up, read, and issue the next kernels)
+void Forest::read_back(std::initializer_list<ReadItem> items) {
+    size_t off = 0;
+    for (const auto& it : items) {
+        OL_REQUIRE(off + it.bytes <= 256, OL_ERR_INTERNAL, "read_back: scratch block too small");
+        OL_CUDA(cudaMemcpyAsync(static_cast<char*>(pinned) + off, it.src, it.bytes, cudaMemcpyDeviceToHost, ctx.stream));
+        off += (it.bytes + 7) & ~(size_t)7;
+    }
+    ctx.sync();
+    off = 0;
+    for (const auto& it : items) {
+        memcpy(it.dst, static_cast<char*>(pinned) + off, it.bytes);
+        off += (it.bytes + 7) & ~(size_t)7;
+    }
+}
+
+// device error word -> exception (the word is cleared first); the RANSAC bits are not errors and stay
+void Forest::throw_device_errors(uint32_t e) {
+    const uint32_t fatal = e & (DEVERR_NONFINITE | DEVERR_CELL_RANGE | DEVERR_OUT_OF_NODE | DEVERR_DEPTH_CAP);
+    if (!fatal) return;
+    const uint32_t rest = e & ~fatal;
+    OL_CUDA(cudaMemcpyAsync(d_err.get(), &rest, 4, cudaMemcpyHostToDevice, ctx.stream));
+    ctx.sync();
     if (e & DEVERR_NONFINITE) throw Error{OL_ERR_NONFINITE, "point cloud contains NaN or infinite coordinates"};
     if (e & DEVERR_CELL_RANGE) throw Error{OL_ERR_RANGE, "cell coordinates out of the representable range"};
     if (e & DEVERR_OUT_OF_NODE)
@@ -83,6 +103,8 @@ void Forest::check_device_errors() {
                                           std::to_string(max_depth) + " (the reference would keep recursing)"};
 }
 
+void Forest::check_device_errors() { throw_device_errors(read_u32(d_err.get())); }
+
 void Forest::upload_segments() {
     size_t S = seg_pose.size();
     d_seg_start.reset(ctx, S + 1);
@@ -91,7 +113,7 @@ void Forest::upload_segments() {
     h2d(ctx, d_seg_start.get(), seg_start.data(), S + 1);
     h2d(ctx, d_seg_pose.get(), seg_pose.data(), S);
     h2d(ctx, d_seg_first.get(), seg_first.data(), S);
-    ctx.sync();  // host vectors may be modified afterwards
+    // no synchronisation: cudaMemcpyAsync from pageable memory returns once the source has been staged
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -219,7 +241,9 @@ int Forest::insert_batch(const double* const* xyz_dev, const int64_t* sizes, int
         insert_batch_kernel<<<(unsigned)chunks.size(), INSERT_THREADS, 0, ctx.stream>>>(d_chunks.get(), P64.get() + N * 3, d_bbox.get(),
                                                                                         d_err.get());
         OL_CHECK_LAUNCH();
-        ctx.sync();  // the pageable chunk table above and the caller's tensors may be released after return
+        // No synchronisation: the pageable chunk table has been staged when cudaMemcpyAsync returns, and the caller's
+        // clouds are torch tensors whose memory is recycled in stream order on this same stream (documented in
+        // include/octreelib_b200.h: sources must stay valid until the work enqueued here has run).
     }
     if (bbox_done == N) bbox_done = N + total;  // the copy kernel already folded the batch into the bounding box
     N += total;
@@ -242,7 +266,6 @@ void Forest::build() {
         OL_CHECK_LAUNCH();
         bbox_done = N;
     }
-    check_device_errors();
     upload_segments();
     const int S = (int)seg_pose.size();
     kp = KeyParams{};
@@ -253,20 +276,24 @@ void Forest::build() {
     mort32 = kp.depth <= MORTON32_MAX_DEPTH;
     kp.pose_bits = segs_pose_monotone ? 0 : bit_length_u64((uint64_t)std::max(n_poses - 1, 0));
     int bits[3] = {0, 0, 0};
-    if (!cfg.single_cell && N > 0) {
+    {  // read-back 1 of the build: bounding box + error word
         long long hb[6];
-        OL_CUDA(cudaMemcpyAsync(hb, d_bbox.get(), sizeof(hb), cudaMemcpyDeviceToHost, ctx.stream));
-        ctx.sync();
-        for (int a = 0; a < 3; ++a) {
-            double lo = cell_coord(ordered_to_double(hb[a]), kp.corner[a], kp.edge);
-            double hi = cell_coord(ordered_to_double(hb[3 + a]), kp.corner[a], kp.edge);
-            OL_REQUIRE(std::fabs(lo) < 4503599627370496.0 && std::fabs(hi) < 4503599627370496.0, OL_ERR_RANGE,
-                       "cell coordinates exceed 2^52");
-            kp.qmin[a] = (long long)lo;
-            bits[a] = bit_length_u64((uint64_t)((long long)hi - (long long)lo));
+        uint32_t e = 0;
+        read_back({{d_bbox.get(), sizeof(hb), hb}, {d_err.get(), 4, &e}});
+        throw_device_errors(e);
+        if (!cfg.single_cell && N > 0) {
+            for (int a = 0; a < 3; ++a) {
+                double lo = cell_coord(ordered_to_double(hb[a]), kp.corner[a], kp.edge);
+                double hi = cell_coord(ordered_to_double(hb[3 + a]), kp.corner[a], kp.edge);
+                OL_REQUIRE(std::fabs(lo) < 4503599627370496.0 && std::fabs(hi) < 4503599627370496.0, OL_ERR_RANGE,
+                           "cell coordinates exceed 2^52");
+                kp.qmin[a] = (long long)lo;
+                bits[a] = bit_length_u64((uint64_t)((long long)hi - (long long)lo));
+            }
         }
     }
-    key_bits = bits[0] + bits[1] + bits[2] + kp.pose_bits;
+    const int cell_bits = bits[0] + bits[1] + bits[2];
+    key_bits = cell_bits + kp.pose_bits;
     OL_REQUIRE(key_bits <= 64, OL_ERR_RANGE,
                "the grid spans too many cells: packed cell key needs " + std::to_string(key_bits) + " bits (max 64)");
     kp.shift[2] = kp.pose_bits;
@@ -292,25 +319,45 @@ void Forest::build() {
         base_dirty = false;
         return;
     }
-    DevBuf<uint64_t> keys0(ctx, n), keys1(ctx, n), mort_r(ctx, mort_len(n));
+    // the cell tables are sized by what the key space allows (the number of cells is only known after K3)
+    const size_t c_max = cell_bits < 31 ? std::min<size_t>(n, (size_t)1 << cell_bits) : n;
+    cellidx0.reset(ctx, n);
+    cell_key.reset(ctx, c_max);
+    cell_start0.reset(ctx, c_max + 1);
+    DevBuf<unsigned long long> d_total(ctx, 1);
+    DevBuf<uint64_t> mort_r(ctx, mort_len(n));
     DevBuf<uint32_t> vals0(ctx, n), vals1(ctx, n);
-    {
-        ProfScope ps(ctx, "keygen", (double)n);
-        if (mort32)
-            keygen_kernel<uint32_t><<<nblk(n), 256, 0, ctx.stream>>>(P64.get(), n, kp, d_seg_start.get(), d_seg_pose.get(), S, keys0.get(),
-                                                                     vals0.get(), reinterpret_cast<uint32_t*>(mort_r.get()), d_err.get());
-        else
-            keygen_kernel<uint64_t><<<nblk(n), 256, 0, ctx.stream>>>(P64.get(), n, kp, d_seg_start.get(), d_seg_pose.get(), S, keys0.get(),
-                                                                     vals0.get(), mort_r.get(), d_err.get());
-        OL_CHECK_LAUNCH();
-    }
-    int which = radix_sort_pairs<uint64_t>(ctx, keys0.get(), keys1.get(), vals0.get(), vals1.get(), n, 0, key_bits, true);
-    if (which) {
-        keys0.swap(keys1);
-        vals0.swap(vals1);
-    }
-    keys1.release();
-    vals1.release();
+    // K1 + K2 + K3 for one key width
+    auto run = [&](auto key_tag) {
+        using KeyT = decltype(key_tag);
+        DevBuf<KeyT> keys0(ctx, n), keys1(ctx, n);
+        {
+            ProfScope ps(ctx, "keygen", (double)n);
+            if (mort32)
+                keygen_kernel<KeyT, uint32_t><<<nblk(n), 256, 0, ctx.stream>>>(P64.get(), n, kp, d_seg_start.get(), d_seg_pose.get(), S,
+                                                                               keys0.get(), vals0.get(),
+                                                                               reinterpret_cast<uint32_t*>(mort_r.get()), d_err.get());
+            else
+                keygen_kernel<KeyT, uint64_t><<<nblk(n), 256, 0, ctx.stream>>>(P64.get(), n, kp, d_seg_start.get(), d_seg_pose.get(), S,
+                                                                               keys0.get(), vals0.get(), mort_r.get(), d_err.get());
+            OL_CHECK_LAUNCH();
+        }
+        const int which = radix_sort_pairs<KeyT>(ctx, keys0.get(), keys1.get(), vals0.get(), vals1.get(), n, 0, key_bits, true);
+        if (which) {
+            keys0.swap(keys1);
+            vals0.swap(vals1);
+        }
+        keys1.release();
+        vals1.release();
+        // K3: cells = runs of equal cell key
+        ProfScope ps(ctx, "cells", (double)n);
+        segment_runs(ctx, CellKeyFn<KeyT>{keys0.get(), kp.pose_bits}, CellEmitFn{cell_key.get(), cell_start0.get()}, n, cellidx0.get(),
+                     d_total.get());
+    };
+    if (key_bits <= 32)
+        run(uint32_t{});
+    else
+        run(uint64_t{});
     perm0.swap(vals0);
     mort0.reset(ctx, mort_len(n));
     {
@@ -323,28 +370,15 @@ void Forest::build() {
         OL_CHECK_LAUNCH();
     }
     mort_r.release();
-
-    // K3: cells = runs of equal cell key; (cell, pose) pairs = runs of equal (cell, pose) (octree_manager.py:166-169)
-    DevBuf<unsigned long long> d_total(ctx, 1);
-    DevBuf<uint32_t> tile_off;
-    CP = 0;
-    {
-        const CellKeyFn key{keys0.get(), kp.pose_bits};
-        {
-            ProfScope ps(ctx, "cells", (double)n);
-            segment_runs_count(ctx, key, n, tile_off, d_total.get());
-        }
-        C = (uint32_t)read_u64(d_total.get());
-        cellidx0.reset(ctx, n);
-        cell_key.reset(ctx, C);
-        cell_start0.reset(ctx, (size_t)C + 1);
-        ProfScope ps(ctx, "cells", (double)n);
-        segment_runs_emit(ctx, key, CellEmitFn{cell_key.get(), cell_start0.get()}, n, tile_off, cellidx0.get());
+    {  // read-back 2 of the build: number of cells + error word (keygen range checks)
+        unsigned long long c64 = 0;
+        uint32_t e = 0;
+        read_back({{d_total.get(), 8, &c64}, {d_err.get(), 4, &e}});
+        throw_device_errors(e);
+        C = (uint32_t)c64;
     }
     OL_CUDA(cudaMemcpyAsync(cell_start0.get() + C, &n, 4, cudaMemcpyHostToDevice, ctx.stream));
-    keys0.release();
     cp_valid = false;  // the (cell, pose) table is built on first use (ensure_cell_poses)
-    check_device_errors();
     built = true;
     base_dirty = any_dead;  // points removed before a rebuild are dropped from the base order lazily
 }
@@ -356,21 +390,21 @@ void Forest::ensure_cell_poses() {
     if (cp_valid) return;
     const uint32_t n = A0;
     DevBuf<unsigned long long> d_total(ctx, 1);
-    DevBuf<uint32_t> tile_off;
     const GroupPoseKeyFn key{cellidx0.get(), perm0.get(), d_seg_start.get(), d_seg_pose.get(), (int)seg_pose.size()};
+    const size_t cp_max = std::min<size_t>(n, (size_t)C * (size_t)std::max(n_poses, 1));
+    DevBuf<uint32_t> cell_tmp(ctx, cp_max);
+    DevBuf<int32_t> pose_tmp(ctx, cp_max);
+    cell_first_pose.reset(ctx, C);
     {
         ProfScope ps(ctx, "cell_poses", (double)n);
-        segment_runs_count(ctx, key, n, tile_off, d_total.get());
+        segment_runs(ctx, key, CellPoseEmitFn{cell_tmp.get(), pose_tmp.get(), cell_first_pose.get(), cellidx0.get()}, n, nullptr,
+                     d_total.get());
     }
     CP = (uint32_t)read_u64(d_total.get());
     cp_cell.reset(ctx, CP);
     cp_pose.reset(ctx, CP);
-    cell_first_pose.reset(ctx, C);
-    {
-        ProfScope ps(ctx, "cell_poses", (double)n);
-        segment_runs_emit(ctx, key, CellPoseEmitFn{cp_cell.get(), cp_pose.get(), cell_first_pose.get(), cellidx0.get()}, n, tile_off,
-                          nullptr);
-    }
+    d2d(ctx, cp_cell.get(), cell_tmp.get(), CP);
+    d2d(ctx, cp_pose.get(), pose_tmp.get(), CP);
     cp_valid = true;
 }
 
@@ -414,7 +448,11 @@ uint32_t Forest::compact_tables(const uint8_t* keep, const uint32_t* via, uint32
         OL_CHECK_LAUNCH();
     }
     exclusive_scan_u32(ctx, t.tile_off.get(), t.tile_off.get(), tiles, d_total.get());
-    return (uint32_t)read_u64(d_total.get());
+    unsigned long long total = 0;
+    uint32_t e = 0;
+    read_back({{d_total.get(), 8, &total}, {d_err.get(), 4, &e}});  // the error word rides along (RANSAC flags of the launch before)
+    note_ransac_flags(e);
+    return (uint32_t)total;
 }
 
 void Forest::compact_move(CompactTables& t, uint32_t n, const uint32_t* perm_in, const uint64_t* mort_in, const uint32_t* aux_in,
@@ -493,18 +531,10 @@ void Forest::reset_shape() {
     ldepth.reset(ctx, L);
     lchild.reset(ctx, L);
     if (L) {
-        iota_kernel<<<nblk(L), 256, 0, ctx.stream>>>(lcell.get(), L, 0);
-        OL_CHECK_LAUNCH();
-        fill_kernel<int32_t><<<nblk(L), 256, 0, ctx.stream>>>(lparent.get(), L, -1);
+        init_leaves_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, lcell.get(), lparent.get(), lpath.get(), ldepth.get(), lchild.get());
         OL_CHECK_LAUNCH();
     }
-    lpath.zero();
-    ldepth.zero();
-    lchild.zero();
-    istart.reset(ctx, 0);
-    icell.reset(ctx, 0);
-    idepth.reset(ctx, 0);
-    ipath.reset(ctx, 0);
+    level_ibegin.clear();
     shaped = true;
     order_valid = blocks_valid = ransac_valid = false;
 }
@@ -551,7 +581,7 @@ void Forest::replay_shape() {
                                                         v0.get());
     OL_CHECK_LAUNCH();
     const int w = radix_sort_pairs<uint64_t>(ctx, k0.get(), k1.get(), v0.get(), v1.get(), n, 0, 64);
-    split_levels(0, nullptr, 0, 0, nullptr, 0, w ? k1.get() : k0.get(), n);
+    split_levels(nullptr, nullptr, nullptr, 0, w ? k1.get() : k0.get(), n);
     sp_q.release();
     sp_depth.release();
     sp_path.release();
@@ -562,10 +592,12 @@ void Forest::replay_shape() {
 // K4: Grid.subdivide (grid.py:244-258) -> OctreeManager.subdivide (octree_manager.py:36-66).
 // Every call rebuilds the shape from the cell roots, as the reference's fresh scheme octree does.
 // ---------------------------------------------------------------------------------------------
-void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t table_len, int beyond, const int32_t* poses,
-                       int n_listed) {
+void Forest::subdivide(const SplitRule& rule, const int32_t* poses, int n_listed) {
     replay_pending = false;  // a fresh scheme replaces whatever shape was recorded
-    DevBuf<uint8_t> listed, table;
+    OL_REQUIRE(!rule.first_level.empty() && rule.first_level[0] == 0, OL_ERR_INVALID, "split rule must start at level 0");
+    for (size_t e = 1; e < rule.first_level.size(); ++e)
+        OL_REQUIRE(rule.first_level[e] > rule.first_level[e - 1], OL_ERR_INVALID, "split rule levels must ascend");
+    DevBuf<uint8_t> listed, tables;
     if (n_listed > 0) {
         std::vector<uint8_t> h(std::max(n_poses, 1), 0);
         for (int i = 0; i < n_listed; ++i) {
@@ -573,27 +605,53 @@ void Forest::subdivide(int64_t max_points, const uint8_t* table_host, int64_t ta
             h[poses[i]] = 1;
         }
         listed.reset(ctx, h.size());
-        h2d(ctx, listed.get(), h.data(), h.size());
-        ctx.sync();
+        h2d(ctx, listed.get(), h.data(), h.size());  // pageable source: staged before the call returns
     }
-    if (table_host) {
-        OL_REQUIRE(table_len > 0, OL_ERR_INVALID, "empty split table");
-        table.reset(ctx, (size_t)table_len);
-        h2d(ctx, table.get(), table_host, (size_t)table_len);
-        ctx.sync();
+    if (rule.tables_host) {
+        OL_REQUIRE(rule.table_len > 0, OL_ERR_INVALID, "empty split table");
+        const size_t bytes = (size_t)rule.table_len * rule.first_level.size();
+        tables.reset(ctx, bytes);
+        h2d(ctx, tables.get(), rule.tables_host, bytes);
     }
     reset_shape();  // after the argument checks: the deferred copy of the base order must not outlive an early error
     if (L == 0 || A == 0) {
         materialize_order();
         return;
     }
-    split_levels(max_points, table.get(), table_len, beyond, listed.get(), n_listed, nullptr, 0);
+    split_levels(&rule, tables.get(), listed.get(), n_listed, nullptr, 0);
+}
+
+// the internal-node arrays grow geometrically, so a level appends in place
+void Forest::reserve_internal(size_t need) {
+    if (need <= icap && istart.get()) return;
+    const size_t ncap = std::max<size_t>(need, std::max<size_t>(icap * 2, 1024));
+    DevBuf<uint32_t> s2(ctx, ncap), c2(ctx, ncap);
+    DevBuf<uint8_t> d2(ctx, ncap), ch2(ctx, ncap);
+    DevBuf<uint64_t> p2(ctx, ncap);
+    DevBuf<int32_t> pa2(ctx, ncap);
+    if (I) {
+        d2d(ctx, s2.get(), istart.get(), I);
+        d2d(ctx, c2.get(), icell.get(), I);
+        d2d(ctx, d2.get(), idepth.get(), I);
+        d2d(ctx, p2.get(), ipath.get(), I);
+        d2d(ctx, pa2.get(), iparent.get(), I);
+        d2d(ctx, ch2.get(), ichild.get(), I);
+    }
+    istart.swap(s2);
+    icell.swap(c2);
+    idepth.swap(d2);
+    ipath.swap(p2);
+    iparent.swap(pa2);
+    ichild.swap(ch2);
+    icap = ncap;
 }
 
 // The level loop of K4.  Decision per leaf of the current level: count criterion (all points, or the points of
 // the listed poses), count table, or - replay_keys != nullptr - membership in a recorded shape.
-void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t table_len, int beyond, const uint8_t* d_listed,
-                          int n_listed, const uint64_t* replay_keys, uint32_t n_replay) {
+// Per level: [weighted count] -> decide + scan (ONE kernel: transform_scan) -> read-back of (number of splits, error
+// word) -> digit histograms -> ONE scan of the flat histogram buffer -> new tables + deltas -> fused rank-and-move.
+void Forest::split_levels(const SplitRule* rule, const uint8_t* d_tables, const uint8_t* d_listed, int n_listed,
+                          const uint64_t* replay_keys, uint32_t n_replay) {
     const int S = (int)seg_pose.size();
     // an error thrown while the current order is still the un-copied base order: drop the shape, the next call rebuilds it
     struct VirginGuard {
@@ -608,14 +666,14 @@ void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t ta
     } virgin_guard{this};
     DevBuf<unsigned long long> d_tot(ctx, 2);
     const uint32_t tiles = (A + PART_TILE - 1) / PART_TILE;
-    DevBuf<uint32_t> tile_hist(ctx, (size_t)8 * tiles);
     DevBuf<uint32_t> perm_b(ctx, A), leaf_b(ctx, A);
     DevBuf<uint64_t> mort_b(ctx, mort_len(A));
+    level_ibegin.assign(1, 0u);
     for (int level = 0;; ++level) {
         // level 0 of a fresh shape partitions straight out of the base order (reset_shape made no copy)
         const uint32_t* src_leaf = order_virgin ? cellidx0.get() : leaf_of.get();
         const uint32_t* src_perm = order_virgin ? perm0.get() : perm.get();
-        DevBuf<uint32_t> splitf(ctx, L), expand(ctx, L), newidx(ctx, L), iidx(ctx, L), wcount;
+        DevBuf<uint32_t> sinfo(ctx, L), wcount;
         if (n_listed > 0) {
             wcount.reset(ctx, L);
             wcount.zero();
@@ -627,21 +685,35 @@ void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t ta
                 OL_CHECK_LAUNCH();
             }
         }
-        {
-            ProfScope ps(ctx, "part_decide");
-            decide_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, lstart.get(), ldepth.get(), level, wcount.get(), max_points, d_table,
-                                                           table_len, beyond, max_depth, replay_keys, n_replay, lcell.get(),
-                                                           lpath.get(), splitf.get(), expand.get(), d_err.get());
-            OL_CHECK_LAUNCH();
+        DecideIn din{};
+        din.lstart = lstart.get();
+        din.ldepth = ldepth.get();
+        din.level = level;
+        din.wcount = wcount.get();
+        din.max_depth = max_depth;
+        din.replay_keys = replay_keys;
+        din.n_replay = n_replay;
+        din.lcell = lcell.get();
+        din.lpath = lpath.get();
+        din.err = d_err.get();
+        if (rule) {
+            const int e = rule->entry_for(level);
+            if (rule->tables_host) {
+                din.table = d_tables + (size_t)e * (size_t)rule->table_len;
+                din.table_len = rule->table_len;
+                din.beyond = rule->beyond[e];
+            } else {
+                din.max_points = rule->max_points[e];
+            }
         }
-        exclusive_scan_u32(ctx, expand.get(), newidx.get(), L, d_tot.get());
-        exclusive_scan_u32(ctx, splitf.get(), iidx.get(), L, d_tot.get() + 1);
-        unsigned long long tot[2];
-        OL_CUDA(cudaMemcpyAsync(pinned, d_tot.get(), 16, cudaMemcpyDeviceToHost, ctx.stream));
-        ctx.sync();
-        memcpy(tot, pinned, 16);
-        const uint32_t L_new = (uint32_t)tot[0], n_split = (uint32_t)tot[1];
+        transform_scan<uint32_t>(ctx, din, DecideOut{sinfo.get()}, L, d_tot.get(), "part_decide");
+        unsigned long long split64 = 0;
+        uint32_t err_word = 0;
+        read_back({{d_tot.get(), 8, &split64}, {d_err.get(), 4, &err_word}});  // the level's ONE read-back
+        throw_device_errors(err_word);  // depth cap of this level, out-of-node points met by the previous level's move
+        const uint32_t n_split = (uint32_t)split64;
         if (n_split == 0) break;
+        const uint32_t L_new = L + 7u * n_split;
         OL_REQUIRE((unsigned long long)I + n_split < (1ull << 29), OL_ERR_RANGE, "too many internal nodes");
         depth_reached = level + 1;
         if (level >= kp.depth) {
@@ -653,64 +725,49 @@ void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t ta
         }
         const uint64_t* src_mort = order_virgin ? mort0.get() : mort.get();
         const int shift = 3 * (kp.depth - 1 - level);
-        DevBuf<uint32_t> leaf_cnt(ctx, (size_t)n_split * 8), leaf_beg(ctx, (size_t)n_split * 8), sidx(ctx, L);
-        leaf_cnt.zero();
-        {
-            ProfScope ps(ctx, "part_decide");
-            split_index_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, splitf.get(), iidx.get(), sidx.get());
-            OL_CHECK_LAUNCH();
-        }
+        // flat histogram buffer: [ tile_hist (8 x tiles) | leaf_cnt (8 x n_split) ], scanned in place by ONE scan
+        const size_t flat_len = (size_t)8 * tiles + (size_t)8 * n_split;
+        DevBuf<uint32_t> hist(ctx, flat_len), delta(ctx, (size_t)n_split * 8);
+        OL_CUDA(cudaMemsetAsync(hist.get() + (size_t)8 * tiles, 0, (size_t)8 * n_split * 4, ctx.stream));
         {
             ProfScope ps(ctx, "part_hist", (double)A);
             if (mort32)
                 part_hist_kernel<uint32_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(src_leaf, reinterpret_cast<const uint32_t*>(src_mort),
-                                                                                   sidx.get(), A, tiles, n_split, shift, tile_hist.get(),
-                                                                                   leaf_cnt.get());
+                                                                                   sinfo.get(), A, tiles, n_split, shift, hist.get(),
+                                                                                   hist.get() + (size_t)8 * tiles);
             else
-                part_hist_kernel<uint64_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(src_leaf, src_mort, sidx.get(), A, tiles, n_split,
-                                                                                   shift, tile_hist.get(), leaf_cnt.get());
+                part_hist_kernel<uint64_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(src_leaf, src_mort, sinfo.get(), A, tiles, n_split,
+                                                                                   shift, hist.get(), hist.get() + (size_t)8 * tiles);
             OL_CHECK_LAUNCH();
         }
-        exclusive_scan_u32(ctx, tile_hist.get(), tile_hist.get(), (size_t)8 * tiles, nullptr);
-        exclusive_scan_u32(ctx, leaf_cnt.get(), leaf_beg.get(), (size_t)8 * n_split, nullptr);
-        DevBuf<uint32_t> delta(ctx, (size_t)n_split * 8);
+        exclusive_scan_u32(ctx, hist.get(), hist.get(), flat_len, d_tot.get() + 1);
+        // new leaf / internal tables + partition deltas
+        reserve_internal((size_t)I + n_split);
+        DevBuf<uint32_t> lstart_n(ctx, (size_t)L_new + 1), lcell_n(ctx, L_new);
+        DevBuf<int32_t> lparent_n(ctx, L_new);
+        DevBuf<uint64_t> lpath_n(ctx, L_new);
+        DevBuf<uint8_t> ldepth_n(ctx, L_new), lchild_n(ctx, L_new);
         {
-            ProfScope ps(ctx, "part_decide");
-            part_delta_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, splitf.get(), iidx.get(), lstart.get(), leaf_cnt.get(), leaf_beg.get(),
-                                                               n_split, delta.get());
+            ProfScope ps(ctx, "part_expand");
+            expand_leaves_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, A, I, sinfo.get(), hist.get(), d_tot.get() + 1, tiles, n_split,
+                                                                  lstart.get(), lcell.get(), lparent.get(), lpath.get(), ldepth.get(),
+                                                                  lchild.get(), L_new, lstart_n.get(), lcell_n.get(), lparent_n.get(),
+                                                                  lpath_n.get(), ldepth_n.get(), lchild_n.get(), istart.get(),
+                                                                  icell.get(), idepth.get(), ipath.get(), iparent.get(), ichild.get(),
+                                                                  delta.get());
             OL_CHECK_LAUNCH();
         }
         {
             ProfScope ps(ctx, "part_move", (double)A);
             if (mort32)
                 part_move_kernel<uint32_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(
-                    src_leaf, reinterpret_cast<const uint32_t*>(src_mort), src_perm, sidx.get(), newidx.get(), tile_hist.get(),
-                    delta.get(), A, tiles, shift, level, leaf_b.get(), reinterpret_cast<uint32_t*>(mort_b.get()), perm_b.get(), P64.get(),
-                    lcell.get(), cell_key.get(), kp, d_err.get());
+                    src_leaf, reinterpret_cast<const uint32_t*>(src_mort), src_perm, sinfo.get(), hist.get(), delta.get(), A, tiles,
+                    shift, level, leaf_b.get(), reinterpret_cast<uint32_t*>(mort_b.get()), perm_b.get(), P64.get(), lcell.get(),
+                    cell_key.get(), kp, d_err.get());
             else
                 part_move_kernel<uint64_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(
-                    src_leaf, src_mort, src_perm, sidx.get(), newidx.get(), tile_hist.get(), delta.get(), A, tiles, shift, level,
-                    leaf_b.get(), mort_b.get(), perm_b.get(), P64.get(), lcell.get(), cell_key.get(), kp, d_err.get());
-            OL_CHECK_LAUNCH();
-        }
-        // new leaf / internal tables
-        DevBuf<uint32_t> lstart_n(ctx, (size_t)L_new + 1), lcell_n(ctx, L_new), istart_n(ctx, (size_t)I + n_split),
-            icell_n(ctx, (size_t)I + n_split);
-        DevBuf<int32_t> lparent_n(ctx, L_new);
-        DevBuf<uint64_t> lpath_n(ctx, L_new);
-        DevBuf<uint8_t> ldepth_n(ctx, L_new), lchild_n(ctx, L_new), idepth_n(ctx, (size_t)I + n_split);
-        DevBuf<uint64_t> ipath_n(ctx, (size_t)I + n_split);
-        d2d(ctx, ipath_n.get(), ipath.get(), I);
-        d2d(ctx, istart_n.get(), istart.get(), I);
-        d2d(ctx, icell_n.get(), icell.get(), I);
-        d2d(ctx, idepth_n.get(), idepth.get(), I);
-        {
-            ProfScope ps(ctx, "part_expand");
-            expand_leaves_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, A, I, splitf.get(), iidx.get(), newidx.get(), leaf_cnt.get(),
-                                                                  n_split, lstart.get(), lcell.get(), lparent.get(), lpath.get(),
-                                                                  ldepth.get(), lchild.get(), L_new, lstart_n.get(), lcell_n.get(),
-                                                                  lparent_n.get(), lpath_n.get(), ldepth_n.get(), lchild_n.get(),
-                                                                  istart_n.get(), icell_n.get(), idepth_n.get(), ipath_n.get());
+                    src_leaf, src_mort, src_perm, sinfo.get(), hist.get(), delta.get(), A, tiles, shift, level, leaf_b.get(),
+                    mort_b.get(), perm_b.get(), P64.get(), lcell.get(), cell_key.get(), kp, d_err.get());
             OL_CHECK_LAUNCH();
         }
         lstart.swap(lstart_n);
@@ -719,10 +776,6 @@ void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t ta
         lpath.swap(lpath_n);
         ldepth.swap(ldepth_n);
         lchild.swap(lchild_n);
-        istart.swap(istart_n);
-        icell.swap(icell_n);
-        idepth.swap(idepth_n);
-        ipath.swap(ipath_n);
         perm.swap(perm_b);
         mort.swap(mort_b);
         leaf_of.swap(leaf_b);
@@ -734,9 +787,9 @@ void Forest::split_levels(int64_t max_points, const uint8_t* d_table, int64_t ta
         }
         L = L_new;
         I += n_split;
+        level_ibegin.push_back(I);
     }
     materialize_order();  // no level split anything: the current order is the base order
-    check_device_errors();
     order_valid = blocks_valid = ransac_valid = false;
 }
 
@@ -760,52 +813,30 @@ void Forest::ensure_order() {
         order_valid = true;
         return;
     }
-    DevBuf<uint32_t> irank(ctx, I), cell_ifirst(ctx, C);
-    cell_ifirst.zero();
+    ProfScope ps(ctx, "leaf_order", (double)L);
+    DevBuf<uint32_t> irank(ctx, I), imask(ctx, I), nlc_r(ctx, I), leafbase(ctx, I), cell_ifirst(ctx, C);
     if (I) {
-        DevBuf<uint64_t> k0(ctx, I), k1(ctx, I);
-        DevBuf<uint32_t> v0(ctx, I), v1(ctx, I);
-        {
-            ProfScope ps(ctx, "leaf_order");
-            internal_keys_kernel<<<nblk(I), 256, 0, ctx.stream>>>(I, istart.get(), idepth.get(), k0.get(), v0.get());
-            OL_CHECK_LAUNCH();
-        }
-        int w = radix_sort_pairs<uint64_t>(ctx, k0.get(), k1.get(), v0.get(), v1.get(), I, 0, 8 + bit_length_u64(A_shape));
-        {
-            ProfScope ps(ctx, "leaf_order");
-            internal_rank_kernel<<<nblk(I), 256, 0, ctx.stream>>>(I, w ? v1.get() : v0.get(), idepth.get(), icell.get(), irank.get(),
-                                                                  cell_ifirst.get());
-            OL_CHECK_LAUNCH();
-        }
-    }
-    {
-        DevBuf<uint64_t> k0(ctx, L), k1(ctx, L);
-        DevBuf<uint32_t> v0(ctx, L), v1(ctx, L);
-        {
-            ProfScope ps(ctx, "leaf_order");
-            leaf_keys_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, lcell.get(), lparent.get(), lchild.get(), irank.get(),
-                                                              cell_ifirst.get(), k0.get(), v0.get());
-            OL_CHECK_LAUNCH();
-        }
-        // low field: (#internal nodes of a cell) * 8 fits in 3 + bit_length(I) bits; cell index above bit 32
-        int low_bits = 3 + bit_length_u64(I);
-        int w = radix_sort_pairs<uint64_t>(ctx, k0.get(), k1.get(), v0.get(), v1.get(), L, 0, low_bits);
-        uint64_t* ka = w ? k1.get() : k0.get();
-        uint64_t* kb = w ? k0.get() : k1.get();
-        uint32_t* va = w ? v1.get() : v0.get();
-        uint32_t* vb = w ? v0.get() : v1.get();
-        int w2 = radix_sort_pairs<uint64_t>(ctx, ka, kb, va, vb, L, 32, 32 + bit_length_u64(C ? C - 1 : 0));
-        d2d(ctx, leaf_by_cache.get(), w2 ? vb : va, L);
-    }
-    {
-        ProfScope ps(ctx, "leaf_order");
-        leaf_geometry_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, leaf_by_cache.get(), lcell.get(), lpath.get(), ldepth.get(),
-                                                              cell_key.get(), kp, cache_rank.get(), leaf_corner.get(),
-                                                              leaf_edge.get(), cell_leaf_begin.get());
+        OL_REQUIRE((int)level_ibegin.size() == depth_reached + 1 && level_ibegin.back() == I, OL_ERR_INTERNAL,
+                   "internal-node level table out of step with the shape");
+        LevelBegins lv{};
+        lv.n = depth_reached;
+        for (int d = 0; d <= depth_reached; ++d) lv.b[d] = level_ibegin[d];
+        imask.zero();
+        internal_mask_kernel<<<nblk(I), 256, 0, ctx.stream>>>(I, iparent.get(), ichild.get(), imask.get());
         OL_CHECK_LAUNCH();
+        internal_rank_kernel<<<nblk(I), 256, 0, ctx.stream>>>(I, istart.get(), idepth.get(), icell.get(), imask.get(), lv, irank.get(),
+                                                              nlc_r.get(), cell_ifirst.get());
+        OL_CHECK_LAUNCH();
+        exclusive_scan_u32(ctx, nlc_r.get(), leafbase.get(), I, nullptr);
     }
+    cell_first_leaf_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, lcell.get(), cell_leaf_begin.get());
+    OL_CHECK_LAUNCH();
+    leaf_order_geometry_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, lcell.get(), lparent.get(), lchild.get(), lpath.get(), ldepth.get(),
+                                                                irank.get(), imask.get(), leafbase.get(), cell_ifirst.get(),
+                                                                cell_leaf_begin.get(), cell_key.get(), kp, cache_rank.get(),
+                                                                leaf_by_cache.get(), leaf_corner.get(), leaf_edge.get());
+    OL_CHECK_LAUNCH();
     OL_CUDA(cudaMemcpyAsync(cell_leaf_begin.get() + C, &L, 4, cudaMemcpyHostToDevice, ctx.stream));
-    ctx.sync();
     order_valid = true;
 }
 
@@ -818,6 +849,7 @@ void Forest::ensure_blocks() {
     const int S = (int)seg_pose.size();
     NB = 0;
     max_block = 0;
+    max_block_known = true;
     blk_of_pos.reset(ctx, A);
     if (A == 0) {
         blk_start.reset(ctx, 1);
@@ -827,31 +859,36 @@ void Forest::ensure_blocks() {
         blocks_valid = true;
         return;
     }
+    // ONE pass (primitives.cuh: runs_fused_kernel); the tables are sized by the upper bound min(A, L x P)
+    const size_t nb_max = std::min<size_t>(A, (size_t)L * (size_t)std::max(n_poses, 1));
     DevBuf<unsigned long long> d_total(ctx, 1);
-    DevBuf<uint32_t> tile_off;
+    blk_start.reset(ctx, nb_max + 1);
+    blk_leaf.reset(ctx, nb_max);
+    blk_pose.reset(ctx, nb_max);
     const GroupPoseKeyFn key{leaf_of.get(), perm.get(), d_seg_start.get(), d_seg_pose.get(), S};
     {
         ProfScope ps(ctx, "blocks", (double)A);
-        segment_runs_count(ctx, key, A, tile_off, d_total.get());
+        segment_runs(ctx, key, BlockEmitFn{blk_start.get(), blk_leaf.get(), blk_pose.get()}, A, blk_of_pos.get(), d_total.get());
     }
     NB = (uint32_t)read_u64(d_total.get());
-    blk_start.reset(ctx, (size_t)NB + 1);
-    blk_leaf.reset(ctx, NB);
-    blk_pose.reset(ctx, NB);
-    {
-        ProfScope ps(ctx, "blocks", (double)A);
-        segment_runs_emit(ctx, key, BlockEmitFn{blk_start.get(), blk_leaf.get(), blk_pose.get()}, A, tile_off, blk_of_pos.get());
-    }
     OL_CUDA(cudaMemcpyAsync(blk_start.get() + NB, &A, 4, cudaMemcpyHostToDevice, ctx.stream));
-    DevBuf<uint32_t> d_max(ctx, 1);
-    d_max.zero();
+    // the largest block is only read back when somebody needs it (ensure_max_block; RANSAC reads it together with its work size)
+    d_max_block.reset(ctx, 1);
+    d_max_block.zero();
     {
         ProfScope ps(ctx, "blocks");
-        block_max_kernel<<<std::min<unsigned>(nblk(NB), (unsigned)ctx.num_sms * 8), 256, 0, ctx.stream>>>(blk_start.get(), NB, d_max.get());
+        block_max_kernel<<<std::min<unsigned>(nblk(NB), (unsigned)ctx.num_sms * 8), 256, 0, ctx.stream>>>(blk_start.get(), NB,
+                                                                                                          d_max_block.get());
         OL_CHECK_LAUNCH();
     }
-    max_block = read_u32(d_max.get());
+    max_block_known = false;
     blocks_valid = true;
+}
+
+void Forest::ensure_max_block() {
+    if (max_block_known) return;
+    max_block = read_u32(d_max_block.get());
+    max_block_known = true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -899,7 +936,6 @@ void Forest::filter(const uint8_t* keep_table_host, int64_t table_len, const int
         h2d(ctx, listed.get(), h.data(), h.size());
     }
     h2d(ctx, table.get(), keep_table_host, (size_t)table_len);
-    ctx.sync();
     block_keep_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_start.get(), blk_pose.get(), listed.get(), table.get(),
                                                         table_len, keep_blk.get());
     OL_CHECK_LAUNCH();

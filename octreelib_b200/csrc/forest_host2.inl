@@ -48,21 +48,37 @@ __global__ void block_sizes_ref_kernel(uint32_t nb, const uint32_t* __restrict__
     blk_size[b] = (int32_t)sz;
 }
 
-// block sizes and "has at least K points" flags, in block-table order (coalesced)
-__global__ void block_size_flag_kernel(uint32_t nb, const uint32_t* __restrict__ blk_start, int K, int32_t* __restrict__ blk_size,
-                                       uint32_t* __restrict__ flags) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
-    const uint32_t sz = blk_start[b + 1] - blk_start[b];
-    blk_size[b] = (int32_t)sz;
-    flags[b] = sz >= (uint32_t)K ? 1u : 0u;
+// block sizes in block-table order and in reference order (one pass)
+__global__ void block_sizes_kernel(uint32_t nb, const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ ref_order,
+                                   int32_t* __restrict__ blk_size, uint32_t* __restrict__ sizes_ref) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nb) return;
+    blk_size[j] = (int32_t)(blk_start[j + 1] - blk_start[j]);
+    const uint32_t b = ref_order[j];
+    sizes_ref[j] = blk_start[b + 1] - blk_start[b];
 }
 
-__global__ void gather_sizes_kernel(uint32_t nb, const uint32_t* __restrict__ ref_order, const int32_t* __restrict__ blk_size,
-                                    uint32_t* __restrict__ sizes_ref) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < nb) sizes_ref[j] = (uint32_t)blk_size[ref_order[j]];
-}
+// Work list of the RANSAC launch as the functors of ONE packed 64-bit scan over the block table: a block with at least
+// K points contributes (1 << 32 | size); the exclusive prefix of block b is (work index << 32 | first packed point),
+// which the output functor scatters straight into the work list.  Grand total = (n_work << 32 | n_packed).
+struct WorkIn {
+    const uint32_t* blk_start;
+    uint32_t K;
+    __device__ unsigned long long operator()(size_t b) const {
+        const uint32_t sz = blk_start[b + 1] - blk_start[b];
+        return sz >= K ? ((1ull << 32) | (unsigned long long)sz) : 0ull;
+    }
+};
+struct WorkOut {
+    uint32_t* work;
+    uint32_t* pk_start;
+    __device__ void operator()(size_t b, unsigned long long ex, unsigned long long v) const {
+        if (v) {
+            work[ex >> 32] = (uint32_t)b;
+            pk_start[ex >> 32] = (uint32_t)ex;
+        }
+    }
+};
 
 // first point of every batch of `ppb` consecutive pose ranks: the reference positions are sorted by pose rank, so the
 // first block of batch t is found by bisection
@@ -90,19 +106,6 @@ __global__ void work_refstart_kernel(uint32_t nb, int K, int ppb, const uint32_t
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nb || sizes_ref[j] < (uint32_t)K) return;
     blk_ref_start[ref_order[j]] = (long long)refstart[j] - (long long)batch_base[sorted_rank[j] / (uint32_t)ppb];
-}
-
-__global__ void work_emit_kernel(uint32_t nb, const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan_ex,
-                                 uint32_t* __restrict__ work) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < nb && flags[b]) work[scan_ex[b]] = b;
-}
-
-// sizes of the fitted blocks (work items), for the packed layout of their points
-__global__ void work_sizes_kernel(uint32_t n_work, const uint32_t* __restrict__ work, const int32_t* __restrict__ blk_size,
-                                  uint32_t* __restrict__ sizes) {
-    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w < n_work) sizes[w] = (uint32_t)blk_size[work[w]];
 }
 
 // K5b: gather ONLY the points of the fitted blocks, block after block, so that every block is one contiguous float64
@@ -246,8 +249,7 @@ void Forest::compute_ref_order(const int32_t* pose_rank_host, DevBuf<uint32_t>& 
         max_rank = std::max(max_rank, pr[p]);
     }
     d_pose_rank.reset(ctx, pr.size());
-    h2d(ctx, d_pose_rank.get(), pr.data(), pr.size());
-    ctx.sync();
+    h2d(ctx, d_pose_rank.get(), pr.data(), pr.size());  // pageable source: staged before the call returns
     if (NB == 0) {
         ref_order.reset(ctx, 0);
         return;
@@ -297,15 +299,13 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
     int max_rank = 0;
     for (int p = 0; p < n_poses; ++p) max_rank = std::max(max_rank, pose_rank ? pose_rank[p] : p);
     const int n_batches = max_rank / ppb + 1;
-    DevBuf<uint32_t> sizes_ref(ctx, NB), refstart(ctx, NB), batch_base(ctx, n_batches), wflags(ctx, NB), wscan(ctx, NB);
+    DevBuf<uint32_t> sizes_ref(ctx, NB), refstart(ctx, NB), batch_base(ctx, n_batches);
     DevBuf<int32_t> blk_size(ctx, NB);
     DevBuf<long long> blk_ref_start(ctx, NB);
     DevBuf<unsigned long long> d_total(ctx, 1);
     {
         ProfScope ps(ctx, "ransac_prep");
-        block_size_flag_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_start.get(), K, blk_size.get(), wflags.get());
-        OL_CHECK_LAUNCH();
-        gather_sizes_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_size.get(), sizes_ref.get());
+        block_sizes_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_start.get(), ref_order.get(), blk_size.get(), sizes_ref.get());
         OL_CHECK_LAUNCH();
     }
     exclusive_scan_u32(ctx, sizes_ref.get(), refstart.get(), NB, nullptr);
@@ -318,23 +318,20 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
                                                                refstart.get(), batch_base.get(), blk_ref_start.get());
         OL_CHECK_LAUNCH();
     }
-    exclusive_scan_u32(ctx, wflags.get(), wscan.get(), NB, d_total.get());
-    const uint32_t n_work = (uint32_t)read_u64(d_total.get());
-    DevBuf<uint32_t> work(ctx, n_work);
-    {
-        ProfScope ps(ctx, "ransac_prep");
-        work_emit_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, wflags.get(), wscan.get(), work.get());
-        OL_CHECK_LAUNCH();
+    // work list + packed layout of the fitted blocks' points: one scan, one read-back (with the largest block size)
+    const size_t work_max = std::min<size_t>(NB, (size_t)A / (size_t)K);
+    DevBuf<uint32_t> work(ctx, work_max + 1), pk_start(ctx, work_max + 1);
+    transform_scan<unsigned long long>(ctx, WorkIn{blk_start.get(), (uint32_t)K}, WorkOut{work.get(), pk_start.get()}, NB, d_total.get(),
+                                       "ransac_prep");
+    unsigned long long packed_total = 0;
+    if (max_block_known) {
+        read_back({{d_total.get(), 8, &packed_total}});
+    } else {
+        read_back({{d_total.get(), 8, &packed_total}, {d_max_block.get(), 4, &max_block}});
+        max_block_known = true;
     }
-    // K5b: packed copy of the fitted blocks' points
-    DevBuf<uint32_t> wsizes(ctx, n_work), pk_start(ctx, n_work);
-    {
-        ProfScope ps(ctx, "ransac_prep");
-        work_sizes_kernel<<<nblk(n_work), 256, 0, ctx.stream>>>(n_work, work.get(), blk_size.get(), wsizes.get());
-        OL_CHECK_LAUNCH();
-    }
-    exclusive_scan_u32(ctx, wsizes.get(), pk_start.get(), n_work, d_total.get());
-    const uint64_t n_packed = read_u64(d_total.get());
+    const uint32_t n_work = (uint32_t)(packed_total >> 32);
+    const uint64_t n_packed = packed_total & 0xffffffffull;
     DevBuf<double> pleaf(ctx, (size_t)n_packed * 3 + 2);
     if (n_work) {
         ProfScope ps(ctx, "gather_points", (double)n_packed);
@@ -376,18 +373,24 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
         d2d(ctx, sn_leaf.get(), blk_leaf.get(), NB);
     }
     snap_pending = true;
-    // a sample index that left its block is clamped and only counted (see ransac.cu)
-    uint32_t e = read_u32(d_err.get());
-    if (e & (DEVERR_SAMPLE_OOB | DEVERR_FILTER_BOUND)) {
-        const bool bound = (e & DEVERR_FILTER_BOUND) != 0;
-        if (e & DEVERR_SAMPLE_OOB) sample_oob_seen = true;
-        e &= ~(uint32_t)(DEVERR_SAMPLE_OOB | DEVERR_FILTER_BOUND);
-        OL_CUDA(cudaMemcpyAsync(d_err.get(), &e, 4, cudaMemcpyHostToDevice, ctx.stream));
-        ctx.sync();
-        OL_REQUIRE(!bound, OL_ERR_INTERNAL, "RANSAC verify: an exact inlier count left its pre-filter interval");
-    }
     ransac_valid = true;
-    if (apply) apply_mask();
+    if (apply) {
+        apply_mask();  // its read-back also brings the error word (note_ransac_flags)
+    } else {
+        note_ransac_flags(read_u32(d_err.get()));
+    }
+}
+
+// RANSAC bits of the device error word: a sample index that left its block is clamped and only recorded
+// (ol_forest_stats.sample_oob_seen); a violated pre-filter interval (verify mode) is an internal error
+void Forest::note_ransac_flags(uint32_t e) {
+    if (!(e & (DEVERR_SAMPLE_OOB | DEVERR_FILTER_BOUND))) return;
+    const bool bound = (e & DEVERR_FILTER_BOUND) != 0;
+    if (e & DEVERR_SAMPLE_OOB) sample_oob_seen = true;
+    e &= ~(uint32_t)(DEVERR_SAMPLE_OOB | DEVERR_FILTER_BOUND);
+    OL_CUDA(cudaMemcpyAsync(d_err.get(), &e, 4, cudaMemcpyHostToDevice, ctx.stream));
+    ctx.sync();
+    OL_REQUIRE(!bound, OL_ERR_INTERNAL, "RANSAC verify: an exact inlier count left its pre-filter interval");
 }
 
 void Forest::apply_mask() {
@@ -477,9 +480,13 @@ void Forest::pose_counts(int64_t* out_host) {
 void Forest::stats(ol_forest_stats* s, bool light) {
     if (light) {  // no derived table is (re)built: block fields are -1 when the block table is stale
         ensure_shape();
-        ctx.sync();
+        if (blocks_valid)
+            ensure_max_block();
+        else
+            ctx.sync();
     } else {
         ensure_blocks();
+        ensure_max_block();
         ensure_cell_poses();
     }
     memset(s, 0, sizeof(*s));
@@ -495,6 +502,7 @@ void Forest::stats(ol_forest_stats* s, bool light) {
     s->max_depth_reached = depth_reached;
     s->key_bits = key_bits;
     s->device_bytes_peak = (int64_t)ctx.bytes_peak;
+    s->sample_oob_seen = sample_oob_seen ? 1 : 0;
 }
 
 std::string Forest::profile_report() {

@@ -1,5 +1,5 @@
 // Device-wide primitives used by the forest pipeline: exclusive scan (u32), stable LSD radix sort of (key, u32 value)
-// pairs (onesweep.cuh below 2^30 pairs, the three-kernel sort in this file above), run segmentation (count + emit).
+// pairs (onesweep.cuh below 2^30 pairs, the three-kernel sort in this file above), run segmentation (one pass).
 // All work is enqueued on Ctx::stream; temporaries come from Ctx::alloc.
 #pragma once
 #include "common.cuh"
@@ -8,16 +8,31 @@
 namespace ol {
 
 // =============================================================================================
-// exclusive scan (uint32), reduce-then-scan over 4096-element tiles
+// exclusive scan (uint32 / packed uint64), ONE kernel per call
+//   n <= SCAN_SMALL_MAX : a single CTA walks the input in chunks (launch-latency bound inputs: tile counts, tables)
+//   otherwise           : single-pass chained scan with decoupled look-back over 256 x ITEMS element tiles
+//                         (tile order by an atomic ticket, two 64-bit status words per tile: aggregate / inclusive
+//                         prefix, top bit = valid, so the word itself carries the data and no fence is needed).
+// Traffic: element read once, written once.  All partial sums are carried in 64 bits; the outputs wrap to T.
+// The uint64 form scans two packed 32-bit counters at once (hi | lo, no carry between them as long as the low
+// total stays below 2^32) - used where two scans over the same index space would otherwise be needed.
 // =============================================================================================
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 16;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr size_t SCAN_SMALL_MAX = 16384;
+constexpr unsigned long long SCAN_VALID = 1ull << 63;
 
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) >= o) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_inclusive_scan64(unsigned long long v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, v, o);
         if ((threadIdx.x & 31) >= o) v += t;
     }
     return v;
@@ -38,112 +53,204 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
     return wbase + inc - v;
 }
 
-static __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint32_t* __restrict__ in,
-                                                                    uint32_t* __restrict__ tile_sums, size_t n) {
-    __shared__ uint32_t sw[8];
-    size_t base = (size_t)blockIdx.x * SCAN_TILE;
-    uint32_t s = 0;
-#pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-        size_t i = base + (size_t)j * SCAN_THREADS + threadIdx.x;
-        if (i < n) s += in[i];
-    }
-    uint32_t tot;
-    block_exclusive_scan_256(s, sw, &tot);
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+// the same in 64 bits for any block size that is a multiple of 32 (<= 1024 threads)
+__device__ __forceinline__ unsigned long long block_exclusive_scan64(unsigned long long v, unsigned long long* smem_warp /*[32]*/,
+                                                                    unsigned long long* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    unsigned long long inc = warp_inclusive_scan64(v);
+    if (lane == 31) smem_warp[warp] = inc;
+    __syncthreads();
+    unsigned long long wsum = (lane < nwarps) ? smem_warp[lane] : 0ull;
+    unsigned long long winc = warp_inclusive_scan64(wsum);
+    unsigned long long wbase = __shfl_sync(0xffffffffu, winc - wsum, warp);
+    unsigned long long tot = __shfl_sync(0xffffffffu, winc, nwarps - 1);
+    __syncthreads();
+    if (total) *total = tot;
+    return wbase + inc - v;
 }
 
-// single block: in-place exclusive scan of the tile sums; writes the grand total (64-bit)
-static __global__ void __launch_bounds__(1024) scan_tilesums_kernel(uint32_t* __restrict__ sums, size_t m,
-                                                             unsigned long long* __restrict__ total_out) {
-    __shared__ unsigned long long swarp[32];
-    __shared__ unsigned long long carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
+__device__ __forceinline__ unsigned long long scan_ld_status(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void scan_st_status(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Chained-scan building block: the calling CTA owns tile `tile` (tiles are taken in ticket order) with aggregate
+// `aggregate`; returns the sum of the aggregates of all earlier tiles (valid in every thread after the internal
+// barriers) and publishes this tile's inclusive prefix.  status = [2 * tiles] words, zero-initialised:
+// status[2 t] = aggregate of tile t, status[2 t + 1] = inclusive prefix through tile t, both | SCAN_VALID.
+__device__ __forceinline__ unsigned long long lookback_exclusive_prefix(unsigned long long* __restrict__ status, uint32_t tile,
+                                                                        unsigned long long aggregate,
+                                                                        unsigned long long* s_prefix /*shared, 1 word*/) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (size_t base = 0; base < m; base += 1024) {
-        size_t i = base + threadIdx.x;
-        unsigned long long v = (i < m) ? sums[i] : 0;
-        unsigned long long inc = v;
+    if (warp == 0) {
+        if (lane == 0) scan_st_status(status + 2 * (size_t)tile + (tile == 0 ? 1 : 0), SCAN_VALID | aggregate);
+        unsigned long long prefix = 0;
+        if (tile > 0) {
+            long long look = (long long)tile - 1;
+            while (true) {
+                const long long idx = look - lane;
+                unsigned long long val = 0;
+                bool stop = idx < 0;  // before the first tile: an inclusive prefix of 0
+                if (idx >= 0) {
+                    while (true) {
+                        const unsigned long long inc = scan_ld_status(status + 2 * (size_t)idx + 1);
+                        if (inc & SCAN_VALID) {
+                            val = inc & ~SCAN_VALID;
+                            stop = true;
+                            break;
+                        }
+                        const unsigned long long agg = scan_ld_status(status + 2 * (size_t)idx);
+                        if (agg & SCAN_VALID) {
+                            val = agg & ~SCAN_VALID;
+                            break;
+                        }
+                    }
+                }
+                const uint32_t stopmask = __ballot_sync(0xffffffffu, stop);
+                const int first = stopmask ? (__ffs(stopmask) - 1) : 32;
+                unsigned long long v = (lane <= first) ? val : 0ull;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                prefix += v;
+                if (stopmask) break;
+                look -= 32;
+            }
+            if (lane == 0) scan_st_status(status + 2 * (size_t)tile + 1, SCAN_VALID | (prefix + aggregate));
         }
-        if (lane == 31) swarp[warp] = inc;
-        __syncthreads();
-        unsigned long long ws = swarp[lane];
-        unsigned long long wi = ws;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long t = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += t;
-        }
-        unsigned long long wbase = __shfl_sync(0xffffffffu, wi - ws, warp);
-        unsigned long long chunk_total = __shfl_sync(0xffffffffu, wi, 31);
-        unsigned long long carry = carry_s;
-        if (i < m) sums[i] = (uint32_t)(carry + wbase + inc - v);
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + chunk_total;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && total_out) *total_out = carry_s;
-}
-
-static __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t* __restrict__ in,
-                                                                   uint32_t* __restrict__ out,
-                                                                   const uint32_t* __restrict__ tile_offsets, size_t n) {
-    // coalesced load into padded smem, blocked (consecutive) processing per thread, coalesced store
-    __shared__ uint32_t tile[SCAN_TILE + SCAN_TILE / 32];
-    __shared__ uint32_t sw[8];
-    size_t base = (size_t)blockIdx.x * SCAN_TILE;
-#pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-        int li = j * SCAN_THREADS + threadIdx.x;
-        size_t i = base + li;
-        tile[li + (li >> 5)] = (i < n) ? in[i] : 0;
+        if (lane == 0) *s_prefix = prefix;
     }
     __syncthreads();
-    uint32_t v[SCAN_ITEMS];
-    uint32_t s = 0;
+    return *s_prefix;
+}
+
+// input / output functors of the scans: in(i) -> T, out(i, exclusive prefix, in(i)); the plain forms read / write arrays
+template <typename T>
+struct ScanPtrIn {
+    const T* p;
+    __device__ __forceinline__ T operator()(size_t i) const { return p[i]; }
+};
+template <typename T>
+struct ScanPtrOut {
+    T* p;
+    __device__ __forceinline__ void operator()(size_t i, T ex, T) const { p[i] = ex; }
+};
+
+template <typename T, int ITEMS, typename InFn, typename OutFn>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(InFn in, OutFn out, size_t n, uint32_t num_tiles,
+                                                                      unsigned long long* __restrict__ status,
+                                                                      unsigned long long* __restrict__ total_out) {
+    constexpr int TILE = SCAN_THREADS * ITEMS;
+    __shared__ T tile[TILE + TILE / 32];
+    __shared__ unsigned long long sw[32];
+    __shared__ unsigned long long s_prefix;
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(reinterpret_cast<uint32_t*>(status + 2 * (size_t)num_tiles), 1u);
+    __syncthreads();
+    const uint32_t t = s_tile;
+    const size_t base = (size_t)t * TILE;
 #pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-        int li = threadIdx.x * SCAN_ITEMS + j;
+    for (int j = 0; j < ITEMS; ++j) {
+        const int li = j * SCAN_THREADS + threadIdx.x;
+        const size_t i = base + li;
+        tile[li + (li >> 5)] = (i < n) ? in(i) : (T)0;
+    }
+    __syncthreads();
+    T v[ITEMS];
+    unsigned long long s = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const int li = threadIdx.x * ITEMS + j;
         v[j] = tile[li + (li >> 5)];
-        s += v[j];
+        s += (unsigned long long)v[j];
     }
-    uint32_t ex = block_exclusive_scan_256(s, sw, nullptr) + tile_offsets[blockIdx.x];
+    unsigned long long tot;
+    unsigned long long ex = block_exclusive_scan64(s, sw, &tot);
+    const unsigned long long prefix = lookback_exclusive_prefix(status, t, tot, &s_prefix);
+    if (t == num_tiles - 1 && threadIdx.x == 0 && total_out) *total_out = prefix + tot;
+    ex += prefix;
+    // the tile buffer now carries the exclusive prefixes back to the coalesced arrangement; the values stay in a
+    // second pass through it only when the output functor needs them (cheap: shared memory)
+    T w[ITEMS];
 #pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-        int li = threadIdx.x * SCAN_ITEMS + j;
-        tile[li + (li >> 5)] = ex;
-        ex += v[j];
+    for (int j = 0; j < ITEMS; ++j) {
+        const int li = j * SCAN_THREADS + threadIdx.x;
+        w[j] = tile[li + (li >> 5)];  // in(i) of the element this thread will write
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-        int li = j * SCAN_THREADS + threadIdx.x;
-        size_t i = base + li;
-        if (i < n) out[i] = tile[li + (li >> 5)];
+    for (int j = 0; j < ITEMS; ++j) {
+        const int li = threadIdx.x * ITEMS + j;
+        tile[li + (li >> 5)] = (T)ex;
+        ex += (unsigned long long)v[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const int li = j * SCAN_THREADS + threadIdx.x;
+        const size_t i = base + li;
+        if (i < n) out(i, tile[li + (li >> 5)], w[j]);
     }
 }
 
-// out[i] = sum_{j<i} in[j]; in == out allowed.  If d_total != nullptr the 64-bit grand total is
-// written there (device memory).  No host synchronisation.
-inline void exclusive_scan_u32(Ctx& c, const uint32_t* in, uint32_t* out, size_t n, unsigned long long* d_total) {
+// single CTA (1024 threads, 4 consecutive elements per thread and chunk): inputs of a few thousand elements
+template <typename T, typename InFn, typename OutFn>
+__global__ void __launch_bounds__(1024) scan_small_kernel(InFn in, OutFn out, size_t n, unsigned long long* __restrict__ total_out) {
+    __shared__ unsigned long long sw[32];
+    unsigned long long carry = 0;
+    for (size_t base = 0; base < n; base += 4096) {
+        const size_t i0 = base + (size_t)threadIdx.x * 4;
+        T v[4];
+        unsigned long long s = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j] = (i0 + j < n) ? in(i0 + j) : (T)0;
+            s += (unsigned long long)v[j];
+        }
+        unsigned long long tot;
+        unsigned long long ex = carry + block_exclusive_scan64(s, sw, &tot);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i0 + j < n) out(i0 + j, (T)ex, v[j]);
+            ex += (unsigned long long)v[j];
+        }
+        carry += tot;
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+// out(i, sum_{j<i} in(j), in(i)) for i in [0, n).  If d_total != nullptr the 64-bit grand total is written there
+// (device memory).  No host synchronisation.  `name` = profiler stage.
+template <typename T, typename InFn, typename OutFn>
+inline void transform_scan(Ctx& c, InFn in, OutFn out, size_t n, unsigned long long* d_total, const char* name = "scan") {
     if (n == 0) {
         if (d_total) OL_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), c.stream));
         return;
     }
-    size_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    DevBuf<uint32_t> sums(c, tiles);
-    ProfScope ps(c, "scan", (double)n);
-    scan_reduce_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, c.stream>>>(in, sums.get(), n);
+    ProfScope ps(c, name, (double)n);
+    if (n <= SCAN_SMALL_MAX) {
+        scan_small_kernel<T, InFn, OutFn><<<1, 1024, 0, c.stream>>>(in, out, n, d_total);
+        OL_CHECK_LAUNCH();
+        return;
+    }
+    constexpr int ITEMS = sizeof(T) == 4 ? 16 : 8;
+    const size_t tiles = (n + SCAN_THREADS * ITEMS - 1) / (SCAN_THREADS * ITEMS);
+    DevBuf<unsigned long long> status(c, 2 * tiles + 1);  // + the ticket counter
+    status.zero();
+    scan_lookback_kernel<T, ITEMS, InFn, OutFn><<<(unsigned)tiles, SCAN_THREADS, 0, c.stream>>>(in, out, n, (uint32_t)tiles, status.get(),
+                                                                                              d_total);
     OL_CHECK_LAUNCH();
-    scan_tilesums_kernel<<<1, 1024, 0, c.stream>>>(sums.get(), tiles, d_total);
-    OL_CHECK_LAUNCH();
-    scan_apply_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, c.stream>>>(in, out, sums.get(), n);
-    OL_CHECK_LAUNCH();
+}
+// array form: out[i] = sum_{j<i} in[j]; in == out allowed
+template <typename T>
+inline void exclusive_scan(Ctx& c, const T* in, T* out, size_t n, unsigned long long* d_total) {
+    transform_scan<T>(c, ScanPtrIn<T>{in}, ScanPtrOut<T>{out}, n, d_total);
+}
+inline void exclusive_scan_u32(Ctx& c, const uint32_t* in, uint32_t* out, size_t n, unsigned long long* d_total) {
+    exclusive_scan<uint32_t>(c, in, out, n, d_total);
 }
 
 // =============================================================================================
@@ -279,11 +386,9 @@ inline int radix_sort_pairs(Ctx& c, KeyT* keys0, KeyT* keys1, uint32_t* vals0, u
 
 // =============================================================================================
 // run segmentation: maximal runs of equal key(i) over i in [0, n)  (K3 cells, (cell, pose) pairs, (pose, leaf) blocks)
-//   runs_count_kernel  heads per 2048-element tile
-//   (exclusive scan of the tile counts, total = number of runs)
-//   runs_emit_kernel   recomputes the head flags, ranks them with ballots, writes run_of_pos[i] and calls emit(run, i, key)
-//                      for every head
-// Traffic: the key inputs are read twice and run_of_pos is written once; no flag / scan arrays of length n.
+//   runs_fused_kernel  head flags per 2048-element tile, chained scan of the tile head counts (decoupled look-back), ranks
+//                      the heads with ballots, writes run_of_pos[i] and calls emit(run, i, key) for every head
+// Traffic: the key inputs are read ONCE and run_of_pos is written once; no flag / scan arrays of length n.
 // KeyFn:  __device__ uint64_t operator()(uint32_t i) const;      EmitFn: __device__ void operator()(uint32_t run, uint32_t i, uint64_t key) const
 // =============================================================================================
 constexpr int RUNS_THREADS = 256;
@@ -319,33 +424,22 @@ __device__ __forceinline__ void runs_warp_flags(const KeyFn& key, uint32_t wbase
     }
 }
 
-template <typename KeyFn>
-__global__ void __launch_bounds__(RUNS_THREADS) runs_count_kernel(KeyFn key, uint32_t n, uint32_t* __restrict__ tile_counts) {
-    __shared__ uint32_t s_w[RUNS_THREADS / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t wbase = blockIdx.x * RUNS_TILE + warp * (32 * RUNS_ITEMS);
-    uint32_t masks[RUNS_ITEMS];
-    uint64_t keys[RUNS_ITEMS];
-    runs_warp_flags(key, wbase, n, lane, masks, keys);
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int j = 0; j < RUNS_ITEMS; ++j) cnt += __popc(masks[j]);
-    if (lane == 0) s_w[warp] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < RUNS_THREADS / 32; ++w) t += s_w[w];
-        tile_counts[blockIdx.x] = t;
-    }
-}
-
+// ONE pass: head flags per tile (ballots), chained scan of the tile head counts with decoupled look-back
+// (lookback_exclusive_prefix above), emit.  The number of runs is only known when the kernel has finished, so the
+// caller sizes the run tables by an upper bound (n, or what the key space allows) and reads *total_out afterwards.
 template <typename KeyFn, typename EmitFn>
-__global__ void __launch_bounds__(RUNS_THREADS) runs_emit_kernel(KeyFn key, EmitFn emit, uint32_t n,
-                                                                 const uint32_t* __restrict__ tile_offsets,
-                                                                 uint32_t* __restrict__ run_of_pos) {
+__global__ void __launch_bounds__(RUNS_THREADS) runs_fused_kernel(KeyFn key, EmitFn emit, uint32_t n, uint32_t num_tiles,
+                                                                  unsigned long long* __restrict__ status,
+                                                                  uint32_t* __restrict__ run_of_pos,
+                                                                  unsigned long long* __restrict__ total_out) {
     __shared__ uint32_t s_w[RUNS_THREADS / 32];
+    __shared__ unsigned long long s_prefix;
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(reinterpret_cast<uint32_t*>(status + 2 * (size_t)num_tiles), 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t wbase = blockIdx.x * RUNS_TILE + warp * (32 * RUNS_ITEMS);
+    const uint32_t wbase = tile * RUNS_TILE + warp * (32 * RUNS_ITEMS);
     uint32_t masks[RUNS_ITEMS];
     uint64_t keys[RUNS_ITEMS];
     runs_warp_flags(key, wbase, n, lane, masks, keys);
@@ -354,8 +448,15 @@ __global__ void __launch_bounds__(RUNS_THREADS) runs_emit_kernel(KeyFn key, Emit
     for (int j = 0; j < RUNS_ITEMS; ++j) cnt += __popc(masks[j]);
     if (lane == 0) s_w[warp] = cnt;
     __syncthreads();
-    uint32_t run = tile_offsets[blockIdx.x];  // heads before this warp's first element
-    for (int w = 0; w < warp; ++w) run += s_w[w];
+    uint32_t tile_total = 0, before = 0;
+#pragma unroll
+    for (int w = 0; w < RUNS_THREADS / 32; ++w) {
+        if (w < warp) before += s_w[w];
+        tile_total += s_w[w];
+    }
+    const unsigned long long prefix = lookback_exclusive_prefix(status, tile, (unsigned long long)tile_total, &s_prefix);
+    if (tile == num_tiles - 1 && threadIdx.x == 0 && total_out) *total_out = prefix + tile_total;
+    uint32_t run = (uint32_t)prefix + before;  // heads before this warp's first element
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
     for (int j = 0; j < RUNS_ITEMS; ++j) {
@@ -370,26 +471,19 @@ __global__ void __launch_bounds__(RUNS_THREADS) runs_emit_kernel(KeyFn key, Emit
     }
 }
 
-// number of runs is written to d_total (device, 64-bit); run tables must be sized by the caller after reading it, so
-// the emit pass is a separate call
-template <typename KeyFn>
-inline void segment_runs_count(Ctx& c, KeyFn key, size_t n, DevBuf<uint32_t>& tile_offsets, unsigned long long* d_total) {
-    const size_t tiles = (n + RUNS_TILE - 1) / RUNS_TILE;
-    tile_offsets.reset(c, tiles ? tiles : 1);
+// Segments [0, n) into maximal runs of equal key: calls emit(run, first position, key) per run, writes run_of_pos[i]
+// (may be nullptr) and the number of runs to d_total (device, 64-bit).  Run tables must hold the caller's upper bound.
+template <typename KeyFn, typename EmitFn>
+inline void segment_runs(Ctx& c, KeyFn key, EmitFn emit, size_t n, uint32_t* run_of_pos, unsigned long long* d_total) {
     if (n == 0) {
         OL_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), c.stream));
         return;
     }
-    runs_count_kernel<KeyFn><<<(unsigned)tiles, RUNS_THREADS, 0, c.stream>>>(key, (uint32_t)n, tile_offsets.get());
-    OL_CHECK_LAUNCH();
-    exclusive_scan_u32(c, tile_offsets.get(), tile_offsets.get(), tiles, d_total);
-}
-
-template <typename KeyFn, typename EmitFn>
-inline void segment_runs_emit(Ctx& c, KeyFn key, EmitFn emit, size_t n, const DevBuf<uint32_t>& tile_offsets, uint32_t* run_of_pos) {
-    if (n == 0) return;
     const size_t tiles = (n + RUNS_TILE - 1) / RUNS_TILE;
-    runs_emit_kernel<KeyFn, EmitFn><<<(unsigned)tiles, RUNS_THREADS, 0, c.stream>>>(key, emit, (uint32_t)n, tile_offsets.get(), run_of_pos);
+    DevBuf<unsigned long long> status(c, 2 * tiles + 1);
+    status.zero();
+    runs_fused_kernel<KeyFn, EmitFn><<<(unsigned)tiles, RUNS_THREADS, 0, c.stream>>>(key, emit, (uint32_t)n, (uint32_t)tiles, status.get(),
+                                                                                     run_of_pos, d_total);
     OL_CHECK_LAUNCH();
 }
 

@@ -214,6 +214,24 @@ class Forest:
             N.check(self._lib.ol_forest_subdivide_table(self._h, _ptr(tab), len(tab), 1 if beyond else 0, _ptr(arr), n))
         self.version += 1
 
+    def subdivide_levels(self, first_levels: Sequence[int], thresholds: Optional[Sequence[int]] = None, tables=None,
+                         beyonds: Optional[Sequence[bool]] = None, pose_indices: Optional[Sequence[int]] = None):
+        """Level-dependent split rule (node-size thresholds, criteria.py): entry e applies from octree level
+        first_levels[e] on.  Either `thresholds` (split iff count > thresholds[e]) or `tables` + `beyonds`."""
+        arr, n = _i32_array(pose_indices)
+        fl = np.ascontiguousarray(list(first_levels), dtype=np.int32)
+        with self._scope():
+            if tables is None:
+                th = np.ascontiguousarray([min(int(t), 1 << 62) for t in thresholds], dtype=np.int64)
+                N.check(self._lib.ol_forest_subdivide_levels(self._h, _ptr(fl), len(fl), _ptr(th), None, 0, None, _ptr(arr), n))
+            else:
+                tab = np.ascontiguousarray(np.stack([np.asarray(t, dtype=np.uint8) for t in tables]), dtype=np.uint8)
+                by = np.ascontiguousarray([1 if b else 0 for b in beyonds], dtype=np.int32)
+                N.check(self._lib.ol_forest_subdivide_levels(self._h, _ptr(fl), len(fl), None, _ptr(tab), tab.shape[1], _ptr(by),
+                                                             _ptr(arr), n))
+        self._pending_sources.clear()
+        self.version += 1
+
     def filter(self, keep_table: np.ndarray, pose_indices: Optional[Sequence[int]] = None):
         arr, n = _i32_array(pose_indices)
         tab = np.ascontiguousarray(keep_table, dtype=np.uint8)

@@ -66,6 +66,23 @@ class FakeForest:
         self.og.subdivide([lambda pts: bool(table[len(pts)]) if len(pts) < len(table) else bool(beyond)], pose_indices)
         self.version += 1
 
+    def subdivide_levels(self, first_levels, thresholds=None, tables=None, beyonds=None, pose_indices=None):
+        """level-dependent rule (node-size thresholds): the level of the node under test is recovered from its edge"""
+        from octreelib_b200.criteria import _edge_of_node_under_test, halvings
+
+        firsts = [int(f) for f in first_levels]
+
+        def crit(pts):
+            level = halvings(self.edge, _edge_of_node_under_test())
+            e = max(i for i, f in enumerate(firsts) if f <= level)
+            if tables is None:
+                return len(pts) > int(thresholds[e])
+            table = np.asarray(tables[e])
+            return bool(table[len(pts)]) if len(pts) < len(table) else bool(beyonds[e])
+
+        self.og.subdivide([crit], pose_indices)
+        self.version += 1
+
     def filter(self, keep_table, pose_indices=None):
         table = np.asarray(keep_table)
         self.og.filter([lambda pts: bool(table[min(len(pts), len(table) - 1)])], pose_indices)

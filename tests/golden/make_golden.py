@@ -495,9 +495,69 @@ def all_leaves_fixture():
           f"{[int((ref2[p]['size'] == 0).sum()) for p in clouds]}  -- oracle == reference OK")
 
 
+def size_limit_fixture():
+    """S11: size thresholds (BASELINE north_star: "splitting by point-count and size thresholds").  The reference passes a
+    criterion nothing but the points (octree/octree.py:26), so the size-guarded criterion objects of
+    octreelib_b200/criteria.py read the node under test from the caller's frame (`self` of OctreeNode.subdivide); the very
+    same objects drive the UNMODIFIED reference here.  Stored: clustered 2-pose clouds (deep trees) under
+    (a) MaxPoints(6, min_edge=0.5), (b) [MaxPoints(40), MaxPoints(6, max_depth=2)] (any() of two criteria with different
+    limits), (c) [MaxDepth(2)] (uniform refinement: empty nodes split too)."""
+    from octreelib_b200.criteria import MaxDepth, MaxPoints
+
+    r11 = np.random.default_rng(1111)
+
+    def f32(a):
+        return a.astype(np.float32).astype(np.float64)
+
+    clouds = {}
+    for p in range(2):
+        centers = r11.random((5, 3)) * 7 - 3
+        clouds[p] = f32(centers[r11.integers(0, 5, 900)] + r11.normal(0, 0.04, (900, 3)))
+    edge = 4
+    cases = {"a": lambda: [MaxPoints(6, min_edge=0.5)],
+             "b": lambda: [MaxPoints(40), MaxPoints(6, max_depth=2, voxel_edge_length=edge)],
+             "c": lambda: [MaxDepth(2, voxel_edge_length=edge)]}
+    save = {f"cloud{p}": c for p, c in clouds.items()}
+    for tag, crit in cases.items():
+        g = Grid(GridConfig(voxel_edge_length=edge))
+        for pose, c in clouds.items():
+            g.insert_points(pose, c)
+        g.subdivide(crit())
+        asis = dump_reference(g, clouds)
+        with stable_order():
+            gs = Grid(GridConfig(voxel_edge_length=edge))
+            for pose, c in clouds.items():
+                gs.insert_points(pose, c)
+            gs.subdivide(crit())
+            canon = dump_reference(gs, clouds)
+        og = OracleGrid(edge)
+        for pose, c in clouds.items():
+            og.insert_points(pose, c)
+        og.subdivide(crit())
+        ora = dump_oracle(og, clouds)
+        compare(asis, ora, ordered=False, tag=f"size_limit:{tag}/as-is")
+        compare(canon, ora, ordered=True, tag=f"size_limit:{tag}/stable")
+        # the guard must bite: an unguarded MaxPoints(6) goes deeper
+        if tag == "a":
+            free = OracleGrid(edge)
+            for pose, c in clouds.items():
+                free.insert_points(pose, c)
+            free.subdivide([max_points_criterion(6)])
+            assert min(float(l.edge) for l in free.get_leaf_points(0)) < 0.5 <= min(canon["p0_edge"]), "guard without effect"
+        save.update({f"{tag}_{k}": v for k, v in canon.items()})
+        print(f"[golden] size_limit_edge4 case {tag}: leaves/pose {[int(canon[f'p{p}_counts'][0]) for p in clouds]}, "
+              f"smallest leaf edge {min(canon['p0_edge'])}  -- oracle == reference OK")
+    save["edge"] = np.float64(edge)
+    save["poses"] = np.array(list(clouds.keys()), dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "size_limit_edge4.npz"), **save)
+
+
 def main():
     rng = np.random.default_rng(2024)
     only = os.environ.get("GOLDEN_ONLY")  # GOLDEN_ONLY=late regenerates only the late-pose fixture (own RNG stream)
+    if only == "size_limit":
+        size_limit_fixture()
+        return
     if only == "resub":
         resubdivide_fixture()
         return
@@ -583,6 +643,7 @@ def main():
     ransac_degenerate_fixture()
     visualize_fixture()
     all_leaves_fixture()
+    size_limit_fixture()
 
 
 if __name__ == "__main__":

@@ -1,0 +1,119 @@
+"""Criteria folding (octreelib_b200/criteria.py) on the CPU: the count-step detection (a step above the probe
+table used to be mistaken for `> 1024`), the rejection of coordinate-dependent criteria (translation-invariant ones
+included), and the node-size guarded criteria (north_star "point-count and size thresholds") through the public API on the
+oracle-backed forest stand-in, pinned by a fixture recorded from the REAL reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from fake_forest import FakeForest
+from octreelib_b200.criteria import (NO_LEVEL_LIMIT, MaxDepth, MaxPoints, MinEdge, MinPoints, as_threshold, fold_count_criteria,
+                                     fold_levels)
+from octreelib_b200.grid import Grid, GridConfig
+
+
+@pytest.mark.parametrize("n", [0, 1, 100, 1023, 1024, 1025, 1500, 2047, 2048, 2049, 5000, 65535, 65536, 10 ** 6, 2 ** 31 - 2])
+def test_step_threshold_is_found_wherever_it_lies(n):
+    crit = [lambda pts, n=n: len(pts) > n]
+    table, beyond = fold_count_criteria(crit, "any", 1024)
+    assert as_threshold(table, beyond, crit) == n
+    # the two-criteria form of the reference's tests: any() of two steps = the lower one
+    crit2 = [lambda pts, n=n: len(pts) > n, lambda pts, n=n: len(pts) > n + 77]
+    table, beyond = fold_count_criteria(crit2, "any", 1024)
+    assert as_threshold(table, beyond, crit2) == n
+
+
+def test_step_detection_does_not_invent_thresholds():
+    never = [lambda pts: False]
+    t, b = fold_count_criteria(never, "any", 1024)
+    assert as_threshold(t, b, never) >= 1 << 40
+    band = [lambda pts: 3000 < len(pts) < 9000]  # true only on a band above the table: not a step
+    t, b = fold_count_criteria(band, "any", 1024)
+    assert as_threshold(t, b, band) is None
+    low_band = [lambda pts: 10 < len(pts) < 20]
+    t, b = fold_count_criteria(low_band, "any", 1024)
+    assert as_threshold(t, b, low_band) is None
+    # without the criteria themselves a step above the table cannot be located: the caller must use a table
+    high = [lambda pts: len(pts) > 1500]
+    t, b = fold_count_criteria(high, "any", 1024)
+    assert as_threshold(t, b) is None and as_threshold(t, b, high) == 1500
+
+
+@pytest.mark.parametrize("crit", [
+    lambda p: len(p) > 3 and np.ptp(p, axis=0).max() > 0.5,          # extent: translation invariant
+    lambda p: len(p) > 3 and p.std(axis=0).max() > 0.1,              # spread
+    lambda p: len(p) > 0 and p[:, 0].mean() > 1.0,                   # position
+    lambda p: len(p) > 3 and np.linalg.eigvalsh(np.cov(p.T))[0] > 1e-4,  # planarity
+])
+def test_coordinate_dependent_criteria_are_rejected(crit):
+    with pytest.raises(NotImplementedError):
+        fold_count_criteria([crit], "any", 64)
+    grid = Grid(GridConfig(voxel_edge_length=4))
+    grid._host._forest = FakeForest(4)
+    grid.insert_points(0, np.random.default_rng(0).random((50, 3)))
+    with pytest.raises(NotImplementedError):
+        grid.subdivide([crit])
+    with pytest.raises(NotImplementedError):
+        grid.filter([crit])
+
+
+def test_level_limits():
+    assert MaxPoints(5).level_limit(4.0) == NO_LEVEL_LIMIT
+    assert MaxPoints(5, min_edge=0.5).level_limit(4.0) == 3      # edges 4, 2, 1 split; 0.5 does not
+    assert MaxPoints(5, min_edge=0.4).level_limit(4.0) == 4      # 0.5 > 0.4 still splits
+    assert MaxPoints(5, max_depth=2, min_edge=0.5).level_limit(4.0) == 2
+    assert MaxDepth(3).level_limit(1.0) == 3 and MinEdge(1.0).level_limit(8.0) == 3
+    lv = fold_levels([MaxPoints(40), MaxPoints(6, max_depth=2)], 4.0, 64)
+    assert [l[0] for l in lv] == [0, 2]
+    assert as_threshold(lv[0][1], lv[0][2]) == 6 and as_threshold(lv[1][1], lv[1][2]) == 40
+    with pytest.raises(ValueError):
+        MaxPoints(5, min_edge=0.0)
+    with pytest.raises(NotImplementedError):  # a guarded criterion called outside a subdivision has no node to look at
+        MaxPoints(5, min_edge=0.5)(np.zeros((9, 3)))
+
+
+def _check_case(grid, g, tag):
+    for p in (0, 1):
+        vox = grid.get_leaf_points(p)
+        assert (np.array([np.asarray(v.corner_min, dtype=np.float64) for v in vox]).reshape(-1, 3) == g[f"{tag}_p{p}_corner"]).all()
+        assert (np.array([float(v.edge_length) for v in vox]) == g[f"{tag}_p{p}_edge"]).all()
+        assert (np.array([v.n_points for v in vox], dtype=np.int64) == g[f"{tag}_p{p}_size"]).all()
+        pts = np.vstack([np.empty((0, 3))] + [v.get_points() for v in vox])
+        assert (pts == g[f"cloud{p}"][g[f"{tag}_p{p}_idx"]]).all()
+        assert [grid.n_leaves(p), grid.n_points(p), grid.n_nodes(p)] == g[f"{tag}_p{p}_counts"].tolist()
+
+
+SIZE_CASES = {"a": lambda: [MaxPoints(6, min_edge=0.5)], "b": lambda: [MaxPoints(40), MaxPoints(6, max_depth=2)],
+              "c": lambda: [MaxDepth(2)]}
+
+
+@pytest.mark.parametrize("tag", list(SIZE_CASES))
+def test_size_guarded_criteria_match_the_reference(tag):
+    g = golden("size_limit_edge4")
+    grid = Grid(GridConfig(voxel_edge_length=4))
+    grid._host._forest = FakeForest(4)
+    for p in (0, 1):
+        grid.insert_points(p, g[f"cloud{p}"])
+    grid.subdivide(SIZE_CASES[tag]())
+    _check_case(grid, g, tag)
+
+
+def test_size_guarded_criteria_with_a_table_rule():
+    """a non-step count criterion next to a guarded one goes through the per-level TABLE form"""
+    g = golden("size_limit_edge4")
+    grid = Grid(GridConfig(voxel_edge_length=4))
+    grid._host._forest = FakeForest(4)
+    for p in (0, 1):
+        grid.insert_points(p, g[f"cloud{p}"])
+    # same decisions as case "b" (no node of the fixture holds exactly 977 points), but not a step in the count any more
+    grid.subdivide([lambda pts: len(pts) > 40 and len(pts) != 977, MaxPoints(6, max_depth=2)])
+    _check_case(grid, g, "b")
+
+
+def test_filter_rejects_size_guards():
+    grid = Grid(GridConfig(voxel_edge_length=4))
+    grid._host._forest = FakeForest(4)
+    grid.insert_points(0, np.random.default_rng(0).random((50, 3)))
+    with pytest.raises(NotImplementedError):
+        grid.filter([MaxPoints(3, min_edge=1.0)])
+    grid.filter([MinPoints(1)])

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     lib = _native.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ol_abi_version() == 1
+    assert lib.ol_abi_version() == 2
 
 
 def test_floor_divide_matches_numpy():
