@@ -184,10 +184,16 @@ int ol_forest_export_cells(ol_forest *f, int64_t *q, double *corner, int32_t *fi
 int ol_forest_export_cell_poses(ol_forest *f, int32_t *cell, int32_t *pose);
 /* leaves in the reference's enumeration order (cells lexicographic, inside a cell the
  * `_cached_leaves` order of octree/octree_base.py:48-49 + octree/octree.py:183-191):
- *   corner[L][3], edge[L] (octree.py:181-187), cell[L], depth[L] */
-int ol_forest_export_leaves(ol_forest *f, double *corner, double *edge, int32_t *cell, int32_t *depth);
+ *   corner[L][3], edge[L] (octree.py:181-187), cell[L], depth[L], parent_epoch[L] = number of the subdivide call that
+ *   split the leaf's parent (0 for an unsplit cell root).
+ * This is the order of a grid that was subdivided ONCE.  Every pose octree of the reference keeps its leaf list across
+ * calls (octree_base.py:48-49, octree.py:183-191), so after a SECOND subdivide the order of pose p inside a cell is
+ * (max(parent_epoch, number of calls made before p was inserted), order above): the block table below and everything
+ * derived from it (point exports, RANSAC batch layout, apply_pose_mask) follow that order on the device; a caller that
+ * enumerates EMPTY leaves too applies the same rule to this table. */
+int ol_forest_export_leaves(ol_forest *f, double *corner, double *edge, int32_t *cell, int32_t *depth, int32_t *parent_epoch);
 /* non-empty (pose, leaf) blocks in the order Grid.get_leaf_points / the RANSAC batches use
- * (pose rank, then leaf order above):  pose[B], leaf[B] (index into the leaf table), size[B]. */
+ * (pose rank, then the reference's leaf order for that pose):  pose[B], leaf[B] (index into the leaf table), size[B]. */
 int ol_forest_export_blocks(ol_forest *f, const int32_t *pose_rank, int32_t *pose, int32_t *leaf, int32_t *size);
 /* the block table as it was when ol_forest_ransac last ran (before the masks were applied), same
  * order, plus per block: plane[B][4] float32, best[B] (hypothesis index, -1 = skipped because the

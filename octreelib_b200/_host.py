@@ -9,7 +9,6 @@ from typing import Callable, Dict, List, Optional, Sequence
 import numpy as np
 
 from . import _views
-from ._history import LeafHistory
 from .criteria import CountCriterion, as_threshold, fold_count_criteria, fold_levels
 from .forest import Forest
 
@@ -29,10 +28,11 @@ class ForestHost:
         self.pose_numbers: List[int] = []      # pose index -> pose number
         self.pose_inserted: List[int] = []     # points inserted so far per pose index
         self._counts_cache = None
-        # leaf order across several subdivide calls (_history.py): nothing is recorded before a SECOND call
+        # Leaf order across several subdivide calls: the reference's per-pose leaf lists grow across calls, so the order
+        # depends on when a node was split and when a pose arrived.  The native forest tracks both (csrc/forest.cuh) and
+        # exports blocks / points in that order; the host only needs the pose epochs for `non_empty=False` listings.
         self._n_subdivides = 0
         self._pose_epoch: Dict[int, int] = {}  # pose index -> subdivide calls made before the pose was created
-        self._history: Optional[LeafHistory] = None
 
     # ---- plumbing --------------------------------------------------------------------------------
     @property
@@ -82,12 +82,6 @@ class ForestHost:
             table, beyond = fold_count_criteria(criteria, "any", 1024)
             levels = [(0, table, beyond, criteria)]
         thresholds = [as_threshold(t, b, active) if active else (1 << 62) for _, t, b, active in levels]
-        if self._n_subdivides >= 1 and self._history is None:
-            # a second call: from here on the reference's leaf order depends on when a node was split (_history.py);
-            # every node that exists now dates from the first call
-            t = _views.tables(self.forest)
-            self._history = LeafHistory()
-            self._history.record(t["leaves"], t["cells"], self._n_subdivides)
         firsts = [lv[0] for lv in levels]
         if all(t is not None for t in thresholds):
             if len(levels) == 1:
@@ -114,9 +108,6 @@ class ForestHost:
             else:
                 self.forest.subdivide_levels(firsts, tables=tables, beyonds=beyonds, pose_indices=idx)
         self._n_subdivides += 1
-        if self._history is not None:
-            t = _views.tables(self.forest)
-            self._history.record(t["leaves"], t["cells"], self._n_subdivides)
         self._counts_cache = None
 
     def filter(self, criteria: Sequence[Callable], pose_numbers: Optional[Sequence[int]] = None):
@@ -189,8 +180,8 @@ class ForestHost:
     # ---- materialisation -------------------------------------------------------------------------
     def leaf_voxels(self, pose_number: int, non_empty: bool, root_corner, root_edge):
         idx = self.pose_index[pose_number]
-        history = self._history if self._history is not None and not self._history.trivial else None
-        return _views.leaf_voxels(self.forest, idx, non_empty, root_corner, root_edge, history, self._pose_epoch.get(idx, 0))
+        return _views.leaf_voxels(self.forest, idx, non_empty, root_corner, root_edge, self._n_subdivides >= 2,
+                                  self._pose_epoch.get(idx, 0))
 
     def points_dfs(self, pose_number: int) -> np.ndarray:
         if self.empty or pose_number not in self.pose_index:

@@ -76,7 +76,7 @@ SIGNATURES = {
     "ol_forest_pose_counts": (C.c_int, [_p, _p]),
     "ol_forest_export_cells": (C.c_int, [_p, _p, _p, _p, _p, _p]),
     "ol_forest_export_cell_poses": (C.c_int, [_p, _p, _p]),
-    "ol_forest_export_leaves": (C.c_int, [_p, _p, _p, _p, _p]),
+    "ol_forest_export_leaves": (C.c_int, [_p, _p, _p, _p, _p, _p]),
     "ol_forest_export_blocks": (C.c_int, [_p, _p, _p, _p, _p]),
     "ol_forest_export_ransac": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _p, C.POINTER(_i64)]),
     "ol_forest_export_points": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, C.POINTER(_i64)]),

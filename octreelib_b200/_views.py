@@ -22,12 +22,13 @@ def tables(forest) -> dict:
     return cache
 
 
-def leaf_voxels(forest, pose_index: int, non_empty: bool, root_corner, root_edge, history=None, pose_epoch: int = 0):
+def leaf_voxels(forest, pose_index: int, non_empty: bool, root_corner, root_edge, history: bool = False, pose_epoch: int = 0):
     """`get_leaf_points` of one pose (grid/grid.py:217-232 -> octree/octree.py:256-263).
 
-    history: a `_history.LeafHistory` once the grid has been subdivided more than once (the reference's leaf lists
-    grow across calls, so the enumeration order then depends on when a node was split); None = the one-call order
-    the forest exports.
+    The forest's block table is already in the reference's order for this pose.  history = the grid has been subdivided
+    more than once: the reference's leaf lists grow across calls, so the order of a pose's leaves inside a cell is
+    (max(subdivide call that split the leaf's parent, calls made before the pose arrived), one-call order); that only
+    matters here for `non_empty=False`, where the EMPTY leaves are listed from the leaf table as well.
 
     root_corner(cell_index) -> corner object of an unsplit cell root (an int64 array for grid cells,
     grid.py:96-105; the user's array for a stand-alone OctreeManager); root_edge: its edge object.
@@ -47,8 +48,7 @@ def leaf_voxels(forest, pose_index: int, non_empty: bool, root_corner, root_edge
         return LeafVoxel(leaves["corner"][leaf].copy(), np.float64(leaves["edge"][leaf]), pts)
 
     if non_empty:
-        order = range(len(blk_leaf)) if history is None else history.order(blk_leaf, leaves, t["cells"], t["version"], pose_epoch)
-        return [make(int(blk_leaf[j]), xyz[offs[j]:offs[j + 1]]) for j in order]
+        return [make(int(blk_leaf[j]), xyz[offs[j]:offs[j + 1]]) for j in range(len(blk_leaf))]
     # every leaf (empty ones included) of the cells in which this pose owns an octree
     cp = t["cell_poses"]
     cells_of_pose = cp["cell"][cp["pose"] == pose_index]
@@ -58,8 +58,9 @@ def leaf_voxels(forest, pose_index: int, non_empty: bool, root_corner, root_edge
     empty = np.empty((0, 3), dtype=float)
     for c in cells_of_pose:
         ids = np.arange(int(begin[c]), int(begin[c + 1]))
-        if history is not None:
-            ids = ids[history.order(ids, leaves, t["cells"], t["version"], pose_epoch)]
+        if history:
+            eff = np.maximum(np.asarray(leaves["parent_epoch"], dtype=np.int64)[ids], int(pose_epoch))
+            ids = ids[np.argsort(eff, kind="stable")]
         for leaf in ids.tolist():
             j = slot.get(leaf)
             out.append(make(leaf, empty if j is None else xyz[offs[j]:offs[j + 1]]))

@@ -135,7 +135,9 @@ int ol_forest_subdivide_levels(ol_forest* f, const int32_t* first_level, int32_t
         if (split_tables_host) {
             rule.beyond.push_back(split_beyond[e]);
         } else {
-            OL_REQUIRE(level_max_points[e] >= 0, OL_ERR_INVALID, "max_points must be >= 0 (an empty node would split forever)");
+            // -1 = "every node of these levels splits, empty ones included" (MaxDepth / MinEdge: uniform refinement);
+            // it ends at the next entry's first level or at the depth cap
+            OL_REQUIRE(level_max_points[e] >= -1, OL_ERR_INVALID, "level_max_points must be >= -1");
             rule.max_points.push_back(level_max_points[e]);
         }
     }
@@ -248,11 +250,11 @@ int ol_forest_export_cell_poses(ol_forest* f, int32_t* cell, int32_t* pose) {
     OL_API_END
 }
 
-int ol_forest_export_leaves(ol_forest* f, double* corner, double* edge, int32_t* cell, int32_t* depth) {
+int ol_forest_export_leaves(ol_forest* f, double* corner, double* edge, int32_t* cell, int32_t* depth, int32_t* parent_epoch) {
     OL_NEED(f);
     OL_API_BEGIN
     ol::PoolScope pool_scope(f->impl.ctx);
-    f->impl.export_leaves(corner, edge, cell, depth);
+    f->impl.export_leaves(corner, edge, cell, depth, parent_epoch);
     OL_API_END
 }
 

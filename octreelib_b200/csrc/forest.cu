@@ -759,6 +759,30 @@ __global__ void save_shape_kernel(uint32_t I, const uint32_t* __restrict__ icell
     path_out[i] = ipath[i];
 }
 
+// epoch of every internal node of a rebuilt shape: carried over from the recorded shape where the node existed
+// (bisection of its replay key), `epoch` (the current subdivide call) where it is new
+__global__ void assign_epochs_kernel(uint32_t I, const uint32_t* __restrict__ icell, const uint8_t* __restrict__ idepth,
+                                     const uint64_t* __restrict__ ipath, const uint64_t* __restrict__ sorted_keys,
+                                     const uint32_t* __restrict__ sorted_vals, const uint32_t* __restrict__ saved_epoch,
+                                     uint32_t n_saved, uint32_t epoch, uint32_t* __restrict__ iepoch) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= I) return;
+    uint32_t out = epoch;
+    if (n_saved) {
+        const uint64_t key = replay_key(icell[i], idepth[i], ipath[i]);
+        uint32_t lo = 0, hi = n_saved;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (sorted_keys[mid] < key)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        if (lo < n_saved && sorted_keys[lo] == key) out = saved_epoch ? saved_epoch[sorted_vals[lo]] : 1u;
+    }
+    iepoch[i] = out;
+}
+
 // recorded split node -> key under the NEW cell table (binary search of the packed cell key); ~0 if the cell is gone
 __global__ void replay_keys_kernel(uint32_t n, const long long* __restrict__ q_in, const uint32_t* __restrict__ depth_in,
                                    const uint64_t* __restrict__ path_in, const uint64_t* __restrict__ cell_key, uint32_t C,

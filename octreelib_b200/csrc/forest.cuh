@@ -98,6 +98,20 @@ struct Forest {
     DevBuf<long long> sp_q;      // [sp_n][3]
     DevBuf<uint32_t> sp_depth;   // [sp_n]
     DevBuf<uint64_t> sp_path;    // [sp_n]
+    DevBuf<uint32_t> sp_epoch;   // [sp_n] (only while epochs_valid)
+
+    // Leaf enumeration order across SEVERAL subdivide calls.  Every pose octree of the reference keeps its leaf list across
+    // calls (octree_base.py:48-49, octree.py:183-191): with node_epoch(v) = first subdivide call whose scheme split v and
+    // pose_epoch(p) = calls made before pose p was created, the leaves of pose p inside a cell are enumerated by
+    // (max(node_epoch(parent), pose_epoch(p)), one-call order).  One call (every BASELINE configuration): all epochs are 1
+    // and nothing below is touched.  From the second call on the epoch of every internal node is carried over from the
+    // previous shape (matched by cell coordinates, depth, path) and the block order adds the epoch to its sort key.
+    int n_subdivide_calls = 0;
+    std::vector<int> pose_epoch;   // host, per pose index
+    bool epochs_valid = false;     // iepoch[] holds the epochs (false: every internal node has epoch 1)
+    DevBuf<uint32_t> iepoch;       // [I]
+    bool history_active() const { return n_subdivide_calls >= 2 && epochs_valid && I > 0; }
+    void assign_epochs(int epoch, const uint64_t* sorted_keys, const uint32_t* sorted_vals, uint32_t n_saved);
 
     bool blocks_valid = false;
     uint32_t NB = 0;
@@ -194,7 +208,7 @@ struct Forest {
     std::string profile_report();  // "name count total_ms" per line; clears the records
     void export_cells(int64_t* q, double* corner, int32_t* first_pose, int64_t* n_nodes, int64_t* leaf_begin);
     void export_cell_poses(int32_t* cell, int32_t* pose);
-    void export_leaves(double* corner, double* edge, int32_t* cell, int32_t* depth);
+    void export_leaves(double* corner, double* edge, int32_t* cell, int32_t* depth, int32_t* parent_epoch);
     void export_blocks(const int32_t* pose_rank, int32_t* pose, int32_t* leaf, int32_t* size);
     int64_t export_ransac(bool scored_only, bool count_only, int32_t* pose, int32_t* leaf, int32_t* size, float* plane,
                           int32_t* best, int32_t* count);

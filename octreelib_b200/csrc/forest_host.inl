@@ -171,6 +171,7 @@ int Forest::insert(const double* xyz, int64_t n, bool on_device, const int64_t* 
         n_poses = std::max(n_poses, n_poses_total);
     }
     N += (size_t)n;
+    if ((int)pose_epoch.size() < n_poses) pose_epoch.resize(n_poses, n_subdivide_calls);
     built = false;
     shaped = false;
     order_valid = blocks_valid = ransac_valid = false;
@@ -247,6 +248,7 @@ int Forest::insert_batch(const double* const* xyz_dev, const int64_t* sizes, int
     }
     if (bbox_done == N) bbox_done = N + total;  // the copy kernel already folded the batch into the bounding box
     N += total;
+    if ((int)pose_epoch.size() < n_poses) pose_epoch.resize(n_poses, n_subdivide_calls);
     built = false;
     shaped = false;
     order_valid = blocks_valid = ransac_valid = false;
@@ -560,7 +562,8 @@ void Forest::ensure_shape() {
 void Forest::save_shape() {
     if (replay_pending) return;  // still waiting for a rebuild: the recorded shape is the current one
     OL_REQUIRE(depth_reached <= REPLAY_MAX_DEPTH, OL_ERR_STATE,
-               "inserting a pose into a grid subdivided deeper than " + std::to_string(REPLAY_MAX_DEPTH) + " levels is not supported");
+               "keeping the shape of a grid subdivided deeper than " + std::to_string(REPLAY_MAX_DEPTH) +
+                   " levels across a rebuild (a pose inserted after the subdivision, or a second subdivide) is not supported");
     sp_n = I;
     sp_q.reset(ctx, (size_t)I * 3);
     sp_depth.reset(ctx, I);
@@ -568,7 +571,23 @@ void Forest::save_shape() {
     save_shape_kernel<<<nblk(I), 256, 0, ctx.stream>>>(I, icell.get(), idepth.get(), ipath.get(), cell_key.get(), kp, sp_q.get(),
                                                        sp_depth.get(), sp_path.get());
     OL_CHECK_LAUNCH();
+    if (epochs_valid) {
+        sp_epoch.reset(ctx, I);
+        d2d(ctx, sp_epoch.get(), iepoch.get(), I);
+    } else {
+        sp_epoch.release();  // every recorded node has epoch 1
+    }
     replay_pending = true;
+}
+
+void Forest::assign_epochs(int epoch, const uint64_t* sorted_keys, const uint32_t* sorted_vals, uint32_t n_saved) {
+    iepoch.reset(ctx, I);
+    if (I) {
+        assign_epochs_kernel<<<nblk(I), 256, 0, ctx.stream>>>(I, icell.get(), idepth.get(), ipath.get(), sorted_keys, sorted_vals,
+                                                              sp_epoch.get(), n_saved, (uint32_t)epoch, iepoch.get());
+        OL_CHECK_LAUNCH();
+    }
+    epochs_valid = true;
 }
 
 void Forest::replay_shape() {
@@ -582,9 +601,11 @@ void Forest::replay_shape() {
     OL_CHECK_LAUNCH();
     const int w = radix_sort_pairs<uint64_t>(ctx, k0.get(), k1.get(), v0.get(), v1.get(), n, 0, 64);
     split_levels(nullptr, nullptr, nullptr, 0, w ? k1.get() : k0.get(), n);
+    if (n_subdivide_calls >= 2) assign_epochs(n_subdivide_calls, w ? k1.get() : k0.get(), w ? v1.get() : v0.get(), n);
     sp_q.release();
     sp_depth.release();
     sp_path.release();
+    sp_epoch.release();
     sp_n = 0;
 }
 
@@ -593,7 +614,6 @@ void Forest::replay_shape() {
 // Every call rebuilds the shape from the cell roots, as the reference's fresh scheme octree does.
 // ---------------------------------------------------------------------------------------------
 void Forest::subdivide(const SplitRule& rule, const int32_t* poses, int n_listed) {
-    replay_pending = false;  // a fresh scheme replaces whatever shape was recorded
     OL_REQUIRE(!rule.first_level.empty() && rule.first_level[0] == 0, OL_ERR_INVALID, "split rule must start at level 0");
     for (size_t e = 1; e < rule.first_level.size(); ++e)
         OL_REQUIRE(rule.first_level[e] > rule.first_level[e - 1], OL_ERR_INVALID, "split rule levels must ascend");
@@ -613,12 +633,43 @@ void Forest::subdivide(const SplitRule& rule, const int32_t* poses, int n_listed
         tables.reset(ctx, bytes);
         h2d(ctx, tables.get(), rule.tables_host, bytes);
     }
+    // From the second call on the reference's leaf order depends on WHEN a node was split (forest.cuh): keep the current
+    // shape (with its epochs) as the record the new shape's nodes are matched against.
+    const int epoch = n_subdivide_calls + 1;
+    bool have_prev = false;
+    if (epoch >= 2) {
+        if (!replay_pending && shaped && I > 0) save_shape();  // a pending replay already holds the shape it stands for
+        have_prev = replay_pending && sp_n > 0;
+    }
+    replay_pending = false;  // a fresh scheme replaces whatever shape was recorded
     reset_shape();  // after the argument checks: the deferred copy of the base order must not outlive an early error
+    n_subdivide_calls = epoch;
     if (L == 0 || A == 0) {
         materialize_order();
-        return;
+    } else {
+        split_levels(&rule, tables.get(), listed.get(), n_listed, nullptr, 0);
     }
-    split_levels(&rule, tables.get(), listed.get(), n_listed, nullptr, 0);
+    if (epoch >= 2) {
+        if (have_prev && I > 0) {
+            const uint32_t n = sp_n;
+            DevBuf<uint64_t> k0(ctx, n), k1(ctx, n);
+            DevBuf<uint32_t> v0(ctx, n), v1(ctx, n);
+            replay_keys_kernel<<<nblk(n), 256, 0, ctx.stream>>>(n, sp_q.get(), sp_depth.get(), sp_path.get(), cell_key.get(), C, kp,
+                                                                k0.get(), v0.get());
+            OL_CHECK_LAUNCH();
+            const int w = radix_sort_pairs<uint64_t>(ctx, k0.get(), k1.get(), v0.get(), v1.get(), n, 0, 64);
+            assign_epochs(epoch, w ? k1.get() : k0.get(), w ? v1.get() : v0.get(), n);
+        } else {
+            assign_epochs(epoch, nullptr, nullptr, 0);
+        }
+        sp_q.release();
+        sp_depth.release();
+        sp_path.release();
+        sp_epoch.release();
+        sp_n = 0;
+    } else {
+        epochs_valid = false;
+    }
 }
 
 // the internal-node arrays grow geometrically, so a level appends in place

@@ -36,6 +36,31 @@ __global__ void block_arrange_kernel(uint32_t nb, const uint32_t* __restrict__ b
     vals[dst] = b;
 }
 
+// The same arrangement when the grid has been subdivided more than once: the reference's order inside (pose, cell) is then
+// (max(epoch of the leaf's parent, epoch of the pose), one-call order) - forest.cuh - so the sort key carries the pose
+// rank, the cell and that epoch; the one-call order is the initial arrangement and survives the stable sort.
+__global__ void block_arrange_history_kernel(uint32_t nb, const uint32_t* __restrict__ blk_leaf, const int32_t* __restrict__ blk_pose,
+                                             const int32_t* __restrict__ pose_rank, const uint32_t* __restrict__ cache_rank,
+                                             const uint32_t* __restrict__ off_c, const uint32_t* __restrict__ first_b,
+                                             const uint32_t* __restrict__ lcell, const int32_t* __restrict__ lparent,
+                                             const uint32_t* __restrict__ iepoch, const int32_t* __restrict__ pose_epoch,
+                                             int cell_bits, int epoch_bits, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const uint32_t leaf = blk_leaf[b];
+    const uint32_t dst = off_c[cache_rank[leaf]] + (b - first_b[leaf]);
+    const int32_t p = blk_pose[b], par = lparent[leaf];
+    const uint32_t node_epoch = par >= 0 ? iepoch[par] : 0u;
+    const uint32_t eff = max(node_epoch, (uint32_t)pose_epoch[p]);
+    keys[dst] = ((uint64_t)(uint32_t)pose_rank[p] << (cell_bits + epoch_bits)) | ((uint64_t)lcell[leaf] << epoch_bits) | (uint64_t)eff;
+    vals[dst] = b;
+}
+
+__global__ void key_to_rank_kernel(uint32_t nb, const uint64_t* __restrict__ keys, int shift, uint32_t* __restrict__ ranks) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nb) ranks[j] = (uint32_t)(keys[j] >> shift);
+}
+
 __global__ void block_sizes_ref_kernel(uint32_t nb, const uint32_t* __restrict__ ref_order, const uint32_t* __restrict__ blk_start,
                                        uint32_t* __restrict__ sizes_ref, uint32_t* __restrict__ refpos,
                                        int32_t* __restrict__ blk_size) {
@@ -262,6 +287,32 @@ void Forest::compute_ref_order(const int32_t* pose_rank_host, DevBuf<uint32_t>& 
         OL_CHECK_LAUNCH();
     }
     exclusive_scan_u32(ctx, cnt_c.get(), off_c.get(), L, nullptr);
+    if (history_active()) {
+        std::vector<int32_t> pe(std::max(n_poses, 1), 0);
+        for (int p = 0; p < n_poses && p < (int)pose_epoch.size(); ++p) pe[p] = pose_epoch[p];
+        DevBuf<int32_t> d_pe(ctx, pe.size());
+        h2d(ctx, d_pe.get(), pe.data(), pe.size());
+        const int cell_bits = bit_length_u64(C ? C - 1 : 0), epoch_bits = bit_length_u64((uint64_t)n_subdivide_calls),
+                  rank_bits = bit_length_u64((uint64_t)max_rank);
+        OL_REQUIRE(cell_bits + epoch_bits + rank_bits <= 64, OL_ERR_RANGE, "block order key does not fit 64 bits");
+        DevBuf<uint64_t> kk0(ctx, NB), kk1(ctx, NB);
+        {
+            ProfScope ps(ctx, "ransac_prep");
+            block_arrange_history_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_leaf.get(), blk_pose.get(), d_pose_rank.get(),
+                                                                           cache_rank.get(), off_c.get(), first_b.get(), lcell.get(),
+                                                                           lparent.get(), iepoch.get(), d_pe.get(), cell_bits,
+                                                                           epoch_bits, kk0.get(), v0.get());
+            OL_CHECK_LAUNCH();
+        }
+        const int w = radix_sort_pairs<uint64_t>(ctx, kk0.get(), kk1.get(), v0.get(), v1.get(), NB, 0, cell_bits + epoch_bits + rank_bits);
+        ref_order.swap(w ? v1 : v0);
+        if (sorted_rank) {
+            key_to_rank_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, w ? kk1.get() : kk0.get(), cell_bits + epoch_bits, k0.get());
+            OL_CHECK_LAUNCH();
+            sorted_rank->swap(k0);
+        }
+        return;
+    }
     {
         ProfScope ps(ctx, "ransac_prep");
         block_arrange_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_leaf.get(), blk_pose.get(), d_pose_rank.get(), cache_rank.get(),
@@ -570,24 +621,30 @@ void Forest::export_cell_poses(int32_t* cell, int32_t* pose) {
 }
 
 __global__ void leaf_meta_kernel(uint32_t L, const uint32_t* __restrict__ leaf_by_cache, const uint32_t* __restrict__ lcell,
-                                 const uint8_t* __restrict__ ldepth, int32_t* __restrict__ o_cell, int32_t* __restrict__ o_depth) {
+                                 const uint8_t* __restrict__ ldepth, const int32_t* __restrict__ lparent,
+                                 const uint32_t* __restrict__ iepoch, int32_t* __restrict__ o_cell, int32_t* __restrict__ o_depth,
+                                 int32_t* __restrict__ o_epoch) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= L) return;
     uint32_t k = leaf_by_cache[j];
     o_cell[j] = (int32_t)lcell[k];
     o_depth[j] = (int32_t)ldepth[k];
+    const int32_t par = lparent[k];
+    o_epoch[j] = par >= 0 ? (iepoch ? (int32_t)iepoch[par] : 1) : 0;  // subdivide call that split the leaf's parent
 }
 
-void Forest::export_leaves(double* corner, double* edge, int32_t* cell, int32_t* depth) {
+void Forest::export_leaves(double* corner, double* edge, int32_t* cell, int32_t* depth, int32_t* parent_epoch) {
     ensure_order();
     copy_out(ctx, corner, leaf_corner.get(), (size_t)L * 3);
     copy_out(ctx, edge, leaf_edge.get(), L);
-    if ((cell || depth) && L) {
-        DevBuf<int32_t> dc(ctx, L), dd(ctx, L);
-        leaf_meta_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, leaf_by_cache.get(), lcell.get(), ldepth.get(), dc.get(), dd.get());
+    if ((cell || depth || parent_epoch) && L) {
+        DevBuf<int32_t> dc(ctx, L), dd(ctx, L), de(ctx, L);
+        leaf_meta_kernel<<<nblk(L), 256, 0, ctx.stream>>>(L, leaf_by_cache.get(), lcell.get(), ldepth.get(), lparent.get(),
+                                                          epochs_valid ? iepoch.get() : nullptr, dc.get(), dd.get(), de.get());
         OL_CHECK_LAUNCH();
         copy_out(ctx, cell, dc.get(), L);
         copy_out(ctx, depth, dd.get(), L);
+        copy_out(ctx, parent_epoch, de.get(), L);
         ctx.sync();
     }
     ctx.sync();

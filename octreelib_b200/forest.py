@@ -332,9 +332,10 @@ class Forest:
         edge = self._host_array(L, np.float64)
         cell = self._host_array(L, np.int32)
         depth = self._host_array(L, np.int32)
+        epoch = self._host_array(L, np.int32)
         with self._scope():
-            N.check(self._lib.ol_forest_export_leaves(self._h, _ptr(corner), _ptr(edge), _ptr(cell), _ptr(depth)))
-        return dict(corner=corner, edge=edge, cell=cell, depth=depth)
+            N.check(self._lib.ol_forest_export_leaves(self._h, _ptr(corner), _ptr(edge), _ptr(cell), _ptr(depth), _ptr(epoch)))
+        return dict(corner=corner, edge=edge, cell=cell, depth=depth, parent_epoch=epoch)
 
     def export_blocks(self, pose_rank: Optional[Sequence[int]] = None) -> dict:
         st = self.stats()

@@ -33,11 +33,26 @@ class _SinglePose:
         return self._corner_min
 
     def subdivide(self, subdivision_criteria: List[Callable[[PointCloud], bool]]):
-        """Split while any criterion holds (octree.py:20-32, 214-220)."""
+        """Split while any criterion holds (octree.py:20-32, 214-220).
+
+        On a tree that is ALREADY split the reference evaluates the criteria on the root's own (empty) point array
+        (octree.py:26) and does not descend: with count criteria that are false for an empty cloud the call is a no-op,
+        it never deepens or coarsens the tree.  Only `OctreeManager` / `Grid` rebuild the shape from a fresh scheme."""
+        if not self._host.empty and self._host.forest.stats(light=True)["n_internal"] > 0:
+            from ..criteria import CountCriterion, fold_count_criteria
+            plain = [CountCriterion(c.op, c.n) if isinstance(c, CountCriterion) else c for c in subdivision_criteria]
+            table, _ = fold_count_criteria(plain, "any", 0)
+            if not table[0]:
+                return
+            raise NotImplementedError("a subdivision criterion that is true for an empty point cloud, applied to an octree "
+                                      "that is already split (the reference would split the root again over its children)")
         self._host.subdivide(subdivision_criteria)
         self._sync_cache()
 
     def subdivide_as(self, other):
+        """Not part of the native path: copying another octree's shape is what `OctreeManager.subdivide` /
+        `insert_points` do for every pose of a cell (octree_manager.py:65-66, 171) - built into the forest, where all
+        poses of a cell share one leaf table.  A direct call on a stand-alone octree raises."""
         raise NotImplementedError("copying another octree's shape is driven by OctreeManager in the native build")
 
     def get_points(self) -> PointCloud:

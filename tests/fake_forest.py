@@ -1,9 +1,12 @@
 """CPU stand-in for `octreelib_b200.forest.Forest`, backed by the oracle (test infrastructure only).
 
 It answers the calls `ForestHost` / `_views` make with tables in the NATIVE forest's format and order: cells
-lexicographic, leaves of a cell in the one-call order (depth-first rank of the parent, child id) whatever the call
-history was - the native forest rebuilds its shape from scratch on every subdivide.  That lets the host-side logic
-(`_host.py`, `_views.py`, `_history.py`, `grid/grid.py`) run in the `-m "not gpu"` suite.
+lexicographic, the leaf table of a cell in the one-call order (depth-first rank of the parent, child id) plus the epoch of
+every leaf's parent, and the (pose, leaf) blocks ordered by the SAME rule the native forest implements on the device
+(csrc/forest.cuh): inside (pose, cell) by (max(epoch of the leaf's parent, epoch of the pose), one-call order).  The
+rule is restated here from the epochs alone - NOT read off the oracle's leaf lists - so the CPU tests compare the rule
+with the oracle's history-keeping lists.  That lets the host-side logic (`_host.py`, `_views.py`, `grid/grid.py`) run in
+the `-m "not gpu"` suite.
 """
 import numpy as np
 
@@ -47,24 +50,38 @@ class FakeForest:
         self.edge = edge
         self.version = 0
         self.clouds = []
+        self.n_subdivides = 0
+        self.node_epoch = {}   # (cell key, path) of an internal node -> subdivide call that first split it
+        self.pose_epoch = {}   # pose index -> subdivide calls made before the pose was created
 
     # ---- mutations -------------------------------------------------------------------------------
     def insert(self, points):
         idx = len(self.clouds)
         pts = np.asarray(points, dtype=np.float64)
         self.clouds.append(pts)
+        self.pose_epoch[idx] = self.n_subdivides
         self.og.insert_points(idx, pts)
         self.version += 1
         return idx
 
+    def _after_subdivide(self):
+        """epochs of the rebuilt shape: carried over where the node existed before, the current call where it is new"""
+        self.n_subdivides += 1
+        old, self.node_epoch = self.node_epoch, {}
+        for key in self.og.cells:
+            root, _ = self._shape(key)
+            for path in _internal_paths(root):
+                self.node_epoch[(key, path)] = old.get((key, path), self.n_subdivides)
+        self.version += 1
+
     def subdivide(self, max_points, pose_indices=None):
         self.og.subdivide([max_points_criterion(int(max_points))], pose_indices)
-        self.version += 1
+        self._after_subdivide()
 
     def subdivide_table(self, table, beyond, pose_indices=None):
         table = np.asarray(table)
         self.og.subdivide([lambda pts: bool(table[len(pts)]) if len(pts) < len(table) else bool(beyond)], pose_indices)
-        self.version += 1
+        self._after_subdivide()
 
     def subdivide_levels(self, first_levels, thresholds=None, tables=None, beyonds=None, pose_indices=None):
         """level-dependent rule (node-size thresholds): the level of the node under test is recovered from its edge"""
@@ -81,7 +98,7 @@ class FakeForest:
             return bool(table[len(pts)]) if len(pts) < len(table) else bool(beyonds[e])
 
         self.og.subdivide([crit], pose_indices)
-        self.version += 1
+        self._after_subdivide()
 
     def filter(self, keep_table, pose_indices=None):
         table = np.asarray(keep_table)
@@ -120,7 +137,7 @@ class FakeForest:
     def _tables(self):
         keys = self._cell_keys()
         cells_q, cells_corner, first_pose, n_nodes, leaf_begin = [], [], [], [], [0]
-        leaf_corner, leaf_edge, leaf_cell, leaf_depth, leaf_path = [], [], [], [], []
+        leaf_corner, leaf_edge, leaf_cell, leaf_depth, leaf_path, leaf_epoch = [], [], [], [], [], []
         for ci, key in enumerate(keys):
             cell = self.og.cells[key]
             root, paths = self._shape(key)
@@ -135,12 +152,14 @@ class FakeForest:
                 leaf_cell.append(ci)
                 leaf_depth.append(len(path))
                 leaf_path.append((key, path))
+                leaf_epoch.append(self.node_epoch.get((key, path[:-1]), 1) if path else 0)
             leaf_begin.append(len(leaf_cell))
         cells = dict(q=np.array(cells_q, dtype=np.int64).reshape(-1, 3), corner=np.array(cells_corner, dtype=np.float64).reshape(-1, 3),
                      first_pose=np.array(first_pose, dtype=np.int32), n_nodes=np.array(n_nodes, dtype=np.int64),
                      leaf_begin=np.array(leaf_begin, dtype=np.int64))
         leaves = dict(corner=np.array(leaf_corner, dtype=np.float64).reshape(-1, 3), edge=np.array(leaf_edge, dtype=np.float64),
-                      cell=np.array(leaf_cell, dtype=np.int32), depth=np.array(leaf_depth, dtype=np.int32))
+                      cell=np.array(leaf_cell, dtype=np.int32), depth=np.array(leaf_depth, dtype=np.int32),
+                      parent_epoch=np.array(leaf_epoch, dtype=np.int32))
         return keys, cells, leaves, leaf_path
 
     def export_cells(self):
@@ -155,16 +174,22 @@ class FakeForest:
         return dict(cell=np.array([c for c, _ in pairs], dtype=np.int32), pose=np.array([p for _, p in pairs], dtype=np.int32))
 
     def _blocks(self):
-        _, _, _, leaf_path = self._tables()
+        _, cells, leaves, leaf_path = self._tables()
         out = []  # (pose, leaf id, idx array)
+        begin = cells["leaf_begin"]
         for pose in range(len(self.clouds)):
-            for lid, (key, path) in enumerate(leaf_path):
-                tree = self.og.cells[key].trees.get(pose)
-                if tree is None:
-                    continue
-                node = _node_at(tree.root, path)
-                if node is not None and len(node.idx):
-                    out.append((pose, lid, node.idx))
+            for ci in range(len(begin) - 1):
+                ids = list(range(int(begin[ci]), int(begin[ci + 1])))
+                if self.n_subdivides >= 2:  # the device rule: (max(parent epoch, pose epoch), one-call order), stable
+                    ids.sort(key=lambda lid: max(int(leaves["parent_epoch"][lid]), self.pose_epoch.get(pose, 0)))
+                for lid in ids:
+                    key, path = leaf_path[lid]
+                    tree = self.og.cells[key].trees.get(pose)
+                    if tree is None:
+                        continue
+                    node = _node_at(tree.root, path)
+                    if node is not None and len(node.idx):
+                        out.append((pose, lid, node.idx))
         return out
 
     def export_blocks(self, pose_rank=None):
@@ -196,6 +221,7 @@ class FakeForest:
         blocks = self._blocks()
         return dict(n_points_inserted=sum(len(c) for c in self.clouds), n_points_alive=sum(len(b[2]) for b in blocks),
                     n_poses=len(self.clouds), n_cells=len(cells["q"]), n_leaves=len(leaves["edge"]), n_blocks=len(blocks),
+                    n_internal=sum(len(_internal_paths(self._shape(k)[0])) for k in self.og.cells), sample_oob_seen=0,
                     max_block_size=max([len(b[2]) for b in blocks], default=0))
 
     def pose_counts(self, n_poses):
@@ -228,6 +254,7 @@ class FakeSingleCellForest(FakeForest):
         pose = len(self.clouds)
         pts = np.asarray(points, dtype=np.float64).reshape(-1, 3)
         self.clouds.append(pts)
+        self.pose_epoch[pose] = self.n_subdivides
         self._insert_into(pose, np.arange(len(pts)), pts)
         return pose
 

@@ -1,8 +1,10 @@
-"""`get_leaf_points` order after more than one subdivide (octreelib_b200/_history.py), on the CPU.
+"""`get_leaf_points` order after more than one subdivide, on the CPU.
 
-The public API (`Grid`, `ForestHost`, `_views`, `_history`) runs unchanged on top of `fake_forest.FakeForest`, a stand-in
-that serves the native forest's tables in the native (one-call) order.  Expected values: the golden fixture generated
-from the REAL reference, and the oracle's own leaf lists (which restate the reference's `_cached_leaves` history).
+The native forest orders a pose's blocks inside a cell by (max(epoch of the leaf's parent, epoch of the pose), one-call
+order) on the device (csrc/forest.cuh, `block_arrange_history_kernel`); `fake_forest.FakeForest` restates exactly that
+rule from the epochs, and the public API (`Grid`, `ForestHost`, `_views`) runs unchanged on top of it.  Expected values:
+the golden fixture generated from the REAL reference, and the oracle's own leaf lists (which restate the reference's
+`_cached_leaves` history).  The same scenarios run against the CUDA forest in test_gpu_structure.py.
 """
 import numpy as np
 import pytest
@@ -47,13 +49,11 @@ def test_two_subdivides_with_a_pose_in_between_match_the_reference_fixture():
     for p in early:
         grid.insert_points(p, g[f"cloud{p}"])
     grid.subdivide([MaxPoints(int(g["first_max"]))])
-    assert grid._host._history is None  # a single call records nothing (the hot path)
     _check_against_golden(grid, g, early, "s1_")
     for p in late:
         grid.insert_points(p, g[f"cloud{p}"])
     _check_against_golden(grid, g, poses, "s2_")
     grid.subdivide([MaxPoints(int(g["second_max"]))])
-    assert grid._host._history is not None and not grid._host._history.trivial
     _check_against_golden(grid, g, poses, "")
 
 
@@ -89,10 +89,10 @@ def test_three_subdivides_and_poses_arriving_at_different_times_match_the_oracle
             w_corner, w_edge, w_sizes = _oracle_leaf_table(og, p, non_empty)
             assert corner.shape == w_corner.shape and (corner == w_corner).all(), (p, non_empty)
             assert (edge == w_edge).all() and (sizes == w_sizes).all()
-        # the native one-call order of the same leaves, for reference: it must differ for at least one pose
+        # the one-call order of the same leaves (the leaf table's own order), for reference: it must differ for a pose
         t = grid._host._forest.export_blocks()
-        native = grid._host._forest.export_leaves()["corner"][t["leaf"][t["pose"] == p]]
-        moved += int((native != _leaf_table(grid, p)[0]).any())
+        lf = t["leaf"][t["pose"] == p]
+        moved += int((np.sort(lf) != lf).any())
     assert moved > 0
 
 
@@ -124,7 +124,6 @@ def test_same_criterion_twice_keeps_the_one_call_order():
     grid.subdivide([MaxPoints(25)])
     before = _leaf_table(grid, 0)
     grid.subdivide([MaxPoints(25)])
-    assert grid._host._history is not None and grid._host._history.trivial
     after = _leaf_table(grid, 0)
     assert all((a == b).all() for a, b in zip(before, after))
 
@@ -153,3 +152,33 @@ def test_random_call_sequences_match_the_oracle(seed):
             w_corner, w_edge, w_sizes = _oracle_leaf_table(og, p, non_empty)
             assert corner.shape == w_corner.shape and (corner == w_corner).all(), (p, non_empty)
             assert (edge_l == w_edge).all() and (sizes == w_sizes).all()
+
+
+def test_apply_mask_after_a_second_subdivide_hits_the_right_leaves():
+    """a mask built against `get_leaf_points` (octree.py:265-274) after a second, finer subdivide must be
+    applied in that same (history) order - the block order the forest uses for `apply_pose_mask`."""
+    from oracle.structure import OracleGrid, max_points_criterion
+
+    rng = np.random.default_rng(9)
+    centers = rng.random((5, 3)) * 8
+    clouds = {p: np.clip(centers[rng.integers(0, 5, 500)] + rng.normal(0, 0.35, (500, 3)), 0.01, 7.99).astype(np.float32).astype(np.float64)
+              for p in range(2)}
+    grid, og = _grid(8), OracleGrid(8)   # an independent oracle holds the expectation
+    for g in (grid, og):
+        g.insert_points(0, clouds[0])
+    grid.subdivide([MaxPoints(120)])
+    og.subdivide([max_points_criterion(120)])
+    for g in (grid, og):
+        g.insert_points(1, clouds[1])
+    grid.subdivide([MaxPoints(15)])
+    og.subdivide([max_points_criterion(15)])
+    for p in (0, 1):
+        vox = grid.get_leaf_points(p)
+        want = og.get_leaf_points(p)
+        assert [v.n_points for v in vox] == [len(l.idx) for l in want]
+        mask = rng.random(sum(v.n_points for v in vox)) < 0.6
+        grid._host.forest.apply_pose_mask(grid._host.pose_index[p], mask)  # what OctreeManager / Octree.apply_mask call
+        og.apply_mask(p, mask)
+        got = np.vstack([np.empty((0, 3))] + [v.get_points() for v in grid.get_leaf_points(p)])
+        exp = np.vstack([np.empty((0, 3))] + [l.points for l in og.get_leaf_points(p)])
+        assert got.shape == exp.shape and (got == exp).all()

@@ -112,3 +112,19 @@ def test_octree_node():
     assert node.n_points == 4
     assert len(cached) == 15
     assert sorted(v.n_points for v in node.get_leaf_points()) == [2, 2]
+
+
+def test_standalone_octree_second_subdivide_is_a_no_op_like_the_reference():
+    """octree.py:26: on a split root the criteria see the root's own empty point array, so a stand-alone `Octree` /
+    `OctreeNode` never deepens or coarsens on a repeated call (checked against the real reference: n_nodes stays 9)."""
+    pts = np.array([[0, 0, 1], [0, 0, 2], [0, 0, 3], [4, 4, 4], [4, 4, 4.5]], dtype=float)
+    tree = Octree(OctreeConfig(), np.array([0, 0, 0]), 5)
+    tree._host._forest = FakeSingleCellForest(5, np.array([0, 0, 0]))
+    tree.insert_points(pts)
+    tree.subdivide([lambda points: len(points) > 2])
+    before = (tree.n_nodes, tree.n_leaves, [v.n_points for v in tree.get_leaf_points()])
+    tree.subdivide([lambda points: len(points) > 1])   # finer: would deepen if the shape were rebuilt
+    tree.subdivide([lambda points: len(points) > 100])  # coarser: would collapse
+    assert (tree.n_nodes, tree.n_leaves, [v.n_points for v in tree.get_leaf_points()]) == before
+    with pytest.raises(NotImplementedError):
+        tree.subdivide([lambda points: len(points) >= 0])

@@ -6,7 +6,7 @@ import pytest
 
 from conftest import golden
 from gpu_util import compare_grid_with_oracle
-from octreelib_b200.criteria import MaxPoints, MinPoints
+from octreelib_b200.criteria import MaxDepth, MaxPoints, MinPoints
 from octreelib_b200.grid import Grid, GridConfig
 from octreelib_b200.internal import Voxel
 from octreelib_b200.octree import Octree, OctreeConfig, OctreeNode
@@ -63,6 +63,36 @@ def test_golden_structure(name):
         for v, c, e, s in zip(vox, g[f"p{p}_corner"], g[f"p{p}_edge"], g[f"p{p}_size"]):
             assert (np.asarray(v.corner_min, dtype=np.float64) == c).all() and float(v.edge_length) == e
             assert v.n_points == s and v.get_points().shape == (s, 3)
+
+
+SIZE_CASES = {"a": lambda: [MaxPoints(6, min_edge=0.5)], "b": lambda: [MaxPoints(40), MaxPoints(6, max_depth=2)],
+              "c": lambda: [MaxDepth(2)],
+              # case b again through the per-level TABLE form (a count criterion that is not a step)
+              "b_table": lambda: [lambda pts: len(pts) > 40 and len(pts) != 977, MaxPoints(6, max_depth=2)]}
+
+
+@pytest.mark.parametrize("tag", list(SIZE_CASES))
+def test_golden_size_guarded_criteria(tag):
+    """Point-count AND size thresholds (north_star): fixtures recorded from the real reference driven by the same
+    criterion objects (tests/golden/make_golden.py: size_limit_fixture)."""
+    g = golden("size_limit_edge4")
+    grid = Grid(GridConfig(voxel_edge_length=4))
+    for p in (0, 1):
+        grid.insert_points(p, g[f"cloud{p}"])
+    grid.subdivide(SIZE_CASES[tag]())
+    _golden_stage(grid, g, [0, 1], tag.split("_")[0] + "_")
+
+
+def test_size_guards_match_oracle_lidar():
+    clouds = {p: lidar64_scan(p, seed=2)[::3] for p in range(3)}
+    for crit in ([MaxPoints(20, max_depth=2, voxel_edge_length=1.0)], [MaxPoints(8, min_edge=0.2), MaxPoints(300)]):
+        grid, og = Grid(GridConfig(voxel_edge_length=1.0)), OracleGrid(1.0)
+        for p, c in clouds.items():
+            grid.insert_points(p, c)
+            og.insert_points(p, c)
+        grid.subdivide(crit)
+        og.subdivide(crit)  # the same objects: they read the oracle's node from the caller's frame
+        compare_grid_with_oracle(grid, og, clouds)
 
 
 def _golden_stage(grid, g, poses, prefix, ordered=True):
@@ -127,8 +157,8 @@ def test_golden_resubdivide_same_leaves_and_points():
 
 
 def test_golden_resubdivide_public_api_leaf_order():
-    """`get_leaf_points` after a second subdivide: the host puts the forest's one-call order into the reference's
-    history-dependent order (octreelib_b200/_history.py; the same code runs on the CPU in test_cpu_history_order.py)."""
+    """`get_leaf_points` after a second subdivide follows the reference's history-dependent order (ordered on the device;
+    the same scenarios run on the CPU stand-in in test_cpu_history_order.py)."""
     g = golden("resubdivide_deepen_edge4")
     grid, poses = _resubdivide_grid(g, 3)
     for p in poses:
@@ -139,13 +169,61 @@ def test_golden_resubdivide_public_api_leaf_order():
         assert (np.vstack([v.get_points() for v in vox]) == g[f"cloud{p}"][g[f"p{p}_idx"]]).all()
 
 
-@pytest.mark.xfail(reason="known gap (DESIGN.md section 8): the DEVICE tables (export_blocks order, RANSAC batch layout) keep the "
-                          "one-call leaf order after a second subdivide; only the public get_leaf_points is reordered on the host",
-                   strict=False)
 def test_golden_resubdivide_device_table_order():
+    """The DEVICE tables (block order, point exports and with them the RANSAC batch layout) follow the reference's
+    history-dependent leaf order after a second subdivide (csrc/forest.cuh: node / pose epochs)."""
     g = golden("resubdivide_deepen_edge4")
     grid, poses = _resubdivide_grid(g, 3)
     _golden_stage(grid, g, poses, "")
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_resubdivide_sequences_match_oracle_including_ransac_and_masks(seed):
+    """call 1 -> pose 2 -> call 2 -> pose 3 -> call 3 on the device against the oracle's history-keeping leaf lists:
+    block order, `non_empty=False` listings, `apply_mask` against `get_leaf_points` order, and a RANSAC pass whose
+    batch layout (`block_start_indices`, cuda_ransac.py:65-67) depends on that order."""
+    from oracle import ransac as oransac
+
+    rng = np.random.default_rng(seed)
+    centers = rng.random((8, 3)) * 8
+    clouds = {}
+    for p in range(4):
+        pts = centers[rng.integers(0, 8, 900)] + rng.normal(0, 0.3, (900, 3))
+        clouds[p] = np.clip(pts, 0.01, 7.99).astype(np.float32).astype(np.float64)
+    grid, og = Grid(GridConfig(voxel_edge_length=4)), OracleGrid(4)
+
+    def both(fn):
+        fn(grid)
+        fn(og)
+
+    for p in (0, 1):
+        both(lambda g, p=p: g.insert_points(p, clouds[p]))
+    grid.subdivide([MaxPoints(80)])
+    og.subdivide([max_points_criterion(80)])
+    both(lambda g: g.insert_points(2, clouds[2]))
+    grid.subdivide([MaxPoints(30)])
+    og.subdivide([max_points_criterion(30)])
+    both(lambda g: g.insert_points(3, clouds[3]))
+    grid.subdivide([MaxPoints(10)])
+    og.subdivide([max_points_criterion(10)])
+    compare_grid_with_oracle(grid, og, clouds)
+    for p in range(4):
+        vox = grid.get_leaf_points(p, non_empty=False)
+        want = og.get_leaf_points(p, non_empty=False)
+        assert len(vox) == len(want)
+        assert all((np.asarray(v.corner_min, dtype=np.float64) == np.asarray(l.corner, dtype=np.float64)).all()
+                   and v.n_points == len(l.idx) for v, l in zip(vox, want))
+    # a mask in get_leaf_points order
+    m = rng.random(grid.n_points(1)) < 0.7
+    grid._host.forest.apply_pose_mask(grid._host.pose_index[1], m)
+    og.apply_mask(1, m)
+    compare_grid_with_oracle(grid, og, clouds)
+    np.random.seed(5)
+    table = oransac.make_table(256, 6)
+    np.random.seed(5)
+    grid.map_leaf_points_cuda_ransac(poses_per_batch=3, threshold=0.05, hypotheses_number=256)
+    og.map_leaf_points_ransac(table, threshold=0.05, poses_per_batch=3)
+    compare_grid_with_oracle(grid, og, clouds)
 
 
 def test_golden_all_leaves_including_empty_ones():
