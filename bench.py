@@ -269,16 +269,13 @@ def run_step(clouds, numbers, n_poses_total, w, world, profile=False, read_table
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port on a bounded sample
+# CPU baseline / reference arm: the REAL reference (oracle/_ref, made by oracle/make_ref.sh) on a bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_sample(workload, n_sample_points, threads):
-    """Times the CPU oracle (port of the reference, oracle/) on a bounded sample of the workload."""
+def _sample_clouds(workload, n_sample_points):
+    """(clouds {pose: (n,3) f64}, edge, ransac threshold) of the bounded CPU sample of a workload"""
     from octreelib_b200 import synthetic
-    from oracle import ransac as oransac
-    from oracle.structure import OracleGrid, max_points_criterion
 
     w = WORKLOADS[workload]
-    oransac.build()
     if w["kind"] == "street":
         n_poses = max(1, n_sample_points // POINTS_PER_POSE_EST)
         clouds = {p: synthetic.lidar_street_scan(p, seed=0) for p in range(n_poses)}
@@ -288,7 +285,71 @@ def cpu_reference_sample(workload, n_sample_points, threads):
         clouds = {p: synthetic.lidar64_scan(p, seed=0) for p in range(max(1, n_sample_points // 120_000))}
     edge = 1.0 if w["kind"] == "indoor" else w["edge"]
     thr = w["threshold"] / w["edge"] if w["kind"] == "indoor" else w["threshold"]
+    return clouds, edge, thr
+
+
+def cpu_reference_sample(workload, n_sample_points, threads):
+    """One step of the hot path on the host cores, on a bounded sample of the workload.
+
+    kind "reference": the UNMODIFIED reference package (oracle/_ref, a verbatim copy of /root/reference/octreelib; import
+    shim only) runs `Grid.insert_points` x P -> `subdivide([len > max])` -> `map_leaf_points_cuda_ransac` (grid/grid.py:
+    58-109, 244-258, 124-215: batching, `get_leaf_points`, vstack, `apply_mask` all as written) on ONE core - it is
+    single-threaded Python.  The reference has no CPU RANSAC: its `CudaRansac` (a numba CUDA kernel, which cannot even be
+    launched with the default 1024 threads per block on sm_100, see `reference_gpu_kernel` in the bench line) is
+    substituted inside that call by the C restatement of the same kernel (oracle/ransac_oracle.c) on `threads` host threads.
+    kind "port": no oracle/_ref on this machine - the numpy / C oracle port (oracle/structure.py) does everything."""
+    from oracle import ransac as oransac
+
+    w = WORKLOADS[workload]
+    oransac.build()
+    clouds, edge, thr = _sample_clouds(workload, n_sample_points)
     n = sum(len(c) for c in clouds.values())
+    out = dict(points=n, poses=len(clouds))
+    ref = None
+    try:
+        from oracle import ref_loader
+
+        if ref_loader.reference_root() is not None:
+            ref = ref_loader.load(cudasim=True)  # the numba kernel is never launched here
+    except Exception as exc:  # noqa: BLE001
+        out["reference_import_error"] = f"{type(exc).__name__}: {exc}"
+        ref = None
+    if ref is not None:
+        import octreelib.grid.grid as ref_grid_module
+        from octreelib.grid import Grid as RefGrid, GridConfig as RefGridConfig
+
+        timer = {"ransac": 0.0}
+
+        class HostRansac:  # stands in for octreelib.ransac.cuda_ransac.CudaRansac inside the reference's own call
+            def __init__(self, threshold=0.01, hypotheses_number=1024, initial_points_number=6):
+                self.threshold = threshold
+                self.table = np.random.random((min(hypotheses_number, 1024), initial_points_number))  # cuda_ransac.py:39-41
+
+            def evaluate(self, point_cloud, block_sizes):
+                t = time.perf_counter()
+                res = oransac.ransac_evaluate(point_cloud, block_sizes, self.table, self.threshold, threads=threads)
+                timer["ransac"] += time.perf_counter() - t
+                return res["mask"].astype(np.bool_)
+
+        saved = ref_grid_module.CudaRansac
+        ref_grid_module.CudaRansac = HostRansac
+        try:
+            np.random.seed(0)
+            t0 = time.perf_counter()
+            g = RefGrid(RefGridConfig(voxel_edge_length=edge))
+            for p, c in clouds.items():
+                g.insert_points(p, c)
+            g.subdivide([lambda points, m=w["max_points"]: len(points) > m])
+            t1 = time.perf_counter()
+            g.map_leaf_points_cuda_ransac(poses_per_batch=10, threshold=thr, hypotheses_number=H, initial_points_number=K)
+            t2 = time.perf_counter()
+        finally:
+            ref_grid_module.CudaRansac = saved
+        out.update(kind="reference", seconds=t2 - t0, structure_s=(t2 - t0) - timer["ransac"], ransac_s=timer["ransac"],
+                   alive=int(sum(g.n_points(p) for p in clouds)))
+        return out
+    from oracle.structure import OracleGrid, max_points_criterion
+
     np.random.seed(0)
     table = oransac.make_table(H, K)
     t0 = time.perf_counter()
@@ -300,7 +361,17 @@ def cpu_reference_sample(workload, n_sample_points, threads):
     og.map_leaf_points_ransac(table, threshold=thr, poses_per_batch=10,
                               evaluate=lambda pts, bs, tab, th: oransac.ransac_evaluate(pts, bs, tab, th, threads=threads))
     t2 = time.perf_counter()
-    return dict(points=n, seconds=t2 - t0, structure_s=t1 - t0, ransac_s=t2 - t1, poses=len(clouds))
+    out.update(kind="port", seconds=t2 - t0, structure_s=t1 - t0, ransac_s=t2 - t1)
+    return out
+
+
+def _cpu_sample_text(r, workload, threads):
+    if r["kind"] == "reference":
+        return (f"{r['points']} points ({r['poses']} poses) of {workload}: the unmodified reference package (oracle/_ref) on 1 core "
+                f"for insert_points + subdivide + the host side of map_leaf_points_cuda_ransac ({r['structure_s']:.2f} s); its numba "
+                f"CUDA kernel replaced by the C port of that kernel on {threads} host thread(s) ({r['ransac_s']:.2f} s)")
+    return (f"{r['points']} points ({r['poses']} poses) of {workload}: oracle port (no oracle/_ref here), structure "
+            f"{r['structure_s']:.2f} s on 1 core + RANSAC {r['ransac_s']:.2f} s on {threads} thread(s)")
 
 
 def _claim_stdout():
@@ -352,9 +423,8 @@ def main():
         mean = sum(times) / len(times)
         val = pts / mean
         out = dict(base, impl="reference", value=val, ms_per_step=mean * 1e3, dtype="f64",
-                   cpu_baseline={"value": val, "unit": "points/s", "cores": threads, "kind": "port",
-                                 "sample": f"{pts} points ({r['poses']} poses) of {args.workload}; structure on 1 core "
-                                           f"(numpy, like the reference), RANSAC on {threads} threads (C port)"},
+                   cpu_baseline={"value": val, "unit": "points/s", "cores": threads, "kind": r["kind"],
+                                 "sample": _cpu_sample_text(r, args.workload, threads)},
                    e2e={"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                    gpu_launches=0)
         print(json.dumps(out), file=result_out, flush=True)
@@ -493,9 +563,8 @@ def main():
         out["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:
         r = cpu_reference_sample(args.workload, args.cpu_sample, 1)
-        out["cpu_baseline"] = {"value": r["points"] / r["seconds"], "unit": "points/s", "cores": 1, "kind": "port",
-                               "sample": f"{r['points']} points ({r['poses']} poses) of {args.workload}: "
-                                         f"structure {r['structure_s']:.2f} s + RANSAC {r['ransac_s']:.2f} s, 1 thread"}
+        out["cpu_baseline"] = {"value": r["points"] / r["seconds"], "unit": "points/s", "cores": 1, "kind": r["kind"],
+                               "sample": _cpu_sample_text(r, args.workload, 1)}
     print(json.dumps(out), file=result_out, flush=True)
     if world > 1:
         dist.barrier()

@@ -12,6 +12,7 @@ struct ol_forest {
 
 namespace ol {
 unsigned long long g_launch_count = 0;
+int g_debug_sync = -1;
 bool g_force_legacy_sort = false;
 int g_os_variant = 0;
 static thread_local std::string g_last_error;

@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -34,12 +35,28 @@ void set_last_error(int code, const std::string& msg);
         }                                                                                          \
     } while (0)
 
-// every kernel launch in the library is followed by OL_CHECK_LAUNCH(): it also counts launches
+// every kernel launch in the library is followed by OL_CHECK_LAUNCH(): it also counts launches.  With the environment
+// variable OL_DEBUG_SYNC=1 every launch is followed by a device synchronisation, so that an asynchronous fault is reported
+// at the launch that caused it (debug aid; never set in measurements).
 extern unsigned long long g_launch_count;
-#define OL_CHECK_LAUNCH()            \
-    do {                             \
-        ++::ol::g_launch_count;      \
-        OL_CUDA(cudaGetLastError()); \
+extern int g_debug_sync;  // -1 = not read yet
+inline bool debug_sync_enabled() {
+    if (g_debug_sync < 0) {
+        const char* e = getenv("OL_DEBUG_SYNC");
+        g_debug_sync = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_debug_sync == 1;
+}
+#define OL_CHECK_LAUNCH()                                                                                              \
+    do {                                                                                                               \
+        ++::ol::g_launch_count;                                                                                        \
+        OL_CUDA(cudaGetLastError());                                                                                   \
+        if (::ol::debug_sync_enabled()) {                                                                              \
+            cudaError_t _s = cudaDeviceSynchronize();                                                                  \
+            if (_s != cudaSuccess)                                                                                     \
+                throw ::ol::Error{OL_ERR_CUDA, std::string("kernel launched at ") + __FILE__ + ":" + std::to_string(__LINE__) + \
+                                                   " failed: " + cudaGetErrorString(_s)};                              \
+        }                                                                                                              \
     } while (0)
 
 #define OL_REQUIRE(cond, code, text)                 \

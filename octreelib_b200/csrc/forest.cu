@@ -819,10 +819,14 @@ __global__ void replay_keys_kernel(uint32_t n, const long long* __restrict__ q_i
 // =============================================================================================
 // K5: leaf enumeration order (reference `_cached_leaves` order) and leaf geometry
 // =============================================================================================
-// The order needs no sort.  Internal nodes are created level by level (ids of level d are the contiguous range
-// [begin[d], begin[d + 1]) and ascend with the position of the node's range), so the pre-order rank of node i
-// (range start s, depth d) - its rank by (start, depth, id) - is a sum of bisections, one per level:
-//   levels above d: nodes with start <= s, its own level: i - begin[d], levels below d: nodes with start < s.
+// The order needs no sort.  Internal nodes are created level by level (ids of depth d are the contiguous range
+// [begin[d], begin[d + 1])) in depth-first leaf order, so inside a level (cell, path) ascends strictly.  The pre-order
+// rank of node i (cell c, depth d, path p) is a sum of bisections, one per level:
+//   levels above d: nodes whose (cell, path) is <= (c, prefix of p at that depth)   - ancestors come first,
+//   its own level : i - begin[d],
+//   levels below d: nodes whose (cell, prefix of their path at depth d) is < (c, p) - descendants come after.
+// (Keyed by the PATH, not by the range start: nodes without points - uniform refinement with MaxDepth / MinEdge splits
+// them too - share their range start with their neighbours.)
 // With imask[p] = set of children of p that are internal, node p emits 8 - popc(imask[p]) leaves; an exclusive scan of
 // these counts in rank order (leafbase) gives, for a leaf with parent p and child id c,
 //   cache position = first leaf of the cell + leafbase[rank p] - leafbase[rank of the cell's root] + popc(~imask[p] & below c)
@@ -840,12 +844,13 @@ __global__ void internal_mask_kernel(uint32_t I, const int32_t* __restrict__ ipa
     if (p >= 0) atomicOr(&imask[p], 1u << ichild[i]);
 }
 
-__global__ void internal_rank_kernel(uint32_t I, const uint32_t* __restrict__ istart, const uint8_t* __restrict__ idepth,
-                                     const uint32_t* __restrict__ icell, const uint32_t* __restrict__ imask, LevelBegins lv,
+__global__ void internal_rank_kernel(uint32_t I, const uint8_t* __restrict__ idepth, const uint32_t* __restrict__ icell,
+                                     const uint64_t* __restrict__ ipath, const uint32_t* __restrict__ imask, LevelBegins lv,
                                      uint32_t* __restrict__ irank, uint32_t* __restrict__ nlc_r, uint32_t* __restrict__ cell_ifirst) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= I) return;
-    const uint32_t s = istart[i];
+    const uint32_t c = icell[i];
+    const uint64_t p = ipath[i];
     const int d = idepth[i];
     uint32_t rank = 0;
     for (int dd = 0; dd < lv.n; ++dd) {
@@ -854,12 +859,15 @@ __global__ void internal_rank_kernel(uint32_t I, const uint32_t* __restrict__ is
             rank += i - b0;
             continue;
         }
-        // first id in [b0, b1) whose start is > s (levels above) or >= s (levels below)
+        // first id in [b0, b1) that does NOT precede node i in pre-order
+        const int up = dd < d ? 3 * (d - dd) : 0, down = dd > d ? 3 * (dd - d) : 0;
+        const uint64_t want = p >> up;
         uint32_t lo = b0, hi = b1;
         while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
-            const uint32_t v = istart[mid];
-            const bool before = dd < d ? (v <= s) : (v < s);
+            const uint32_t cm = icell[mid];
+            const uint64_t pm = ipath[mid] >> down;
+            const bool before = cm != c ? (cm < c) : (dd < d ? pm <= want : pm < want);
             if (before)
                 lo = mid + 1;
             else
@@ -869,7 +877,7 @@ __global__ void internal_rank_kernel(uint32_t I, const uint32_t* __restrict__ is
     }
     irank[i] = rank;
     nlc_r[rank] = 8u - (uint32_t)__popc(imask[i]);
-    if (d == 0) cell_ifirst[icell[i]] = rank;
+    if (d == 0) cell_ifirst[c] = rank;
 }
 
 // first leaf of every cell (every cell owns at least one leaf; the range is the same in both leaf orders)

@@ -875,7 +875,7 @@ void Forest::ensure_order() {
         imask.zero();
         internal_mask_kernel<<<nblk(I), 256, 0, ctx.stream>>>(I, iparent.get(), ichild.get(), imask.get());
         OL_CHECK_LAUNCH();
-        internal_rank_kernel<<<nblk(I), 256, 0, ctx.stream>>>(I, istart.get(), idepth.get(), icell.get(), imask.get(), lv, irank.get(),
+        internal_rank_kernel<<<nblk(I), 256, 0, ctx.stream>>>(I, idepth.get(), icell.get(), ipath.get(), imask.get(), lv, irank.get(),
                                                               nlc_r.get(), cell_ifirst.get());
         OL_CHECK_LAUNCH();
         exclusive_scan_u32(ctx, nlc_r.get(), leafbase.get(), I, nullptr);
