@@ -247,6 +247,7 @@ def run_step(clouds, numbers, n_poses_total, w, world, profile=False, read_table
     forest = grid._host.forest
     if profile:
         forest.profile(True)
+        forest.extra_ransac_flags = 8  # OL_RANSAC_STATS: tally the executed fits / distance evaluations (profiled step only)
     for number, cloud in zip(numbers, clouds):
         grid.insert_points(number, cloud)
     if world > 1:
@@ -374,6 +375,74 @@ def _cpu_sample_text(r, workload, threads):
             f"{r['structure_s']:.2f} s on 1 core + RANSAC {r['ransac_s']:.2f} s on {threads} thread(s)")
 
 
+def ransac_stats_read(lib, reset=True):
+    import ctypes as C
+
+    out = (C.c_uint64 * 16)()
+    lib.ol_ransac_stats_read(C.byref(out), 1 if reset else 0)
+    keys = ["blocks", "prefiltered_hypotheses", "trivial_intervals", "candidate_evaluations", "early_exits", "interval_violations",
+            "exact_fits", "exact_distance_evals", "fp32_distance_evals"]
+    return {k: int(out[i]) for i, k in enumerate(keys)}
+
+
+FIT_FLOPS_F64 = 152   # one exact plane fit at K = 6 (util.py:28-84: centroid 21, covariance 90, cofactors 15, normalise 9, d 5, indices 12)
+DIST_FLOPS = 6        # one point-plane distance (util.py:16-24: 3 multiplications + 3 additions)
+FIT_FLOPS_F32 = 120   # one float32 pre-filter fit incl. its error bounds
+
+
+def ransac_rooflines(stats, kernel_ms, fp64_tflops, fp32_tflops):
+    """Executed arithmetic of a RANSAC launch against the measured pipe peaks (FMA microbenchmark, 2 flops per FMA)."""
+    f64 = stats["exact_fits"] * FIT_FLOPS_F64 + stats["exact_distance_evals"] * DIST_FLOPS
+    f32 = stats["prefiltered_hypotheses"] * FIT_FLOPS_F32 + stats["fp32_distance_evals"] * DIST_FLOPS
+    t = kernel_ms * 1e-3
+    out = {"fp64_flops_executed": f64, "fp32_flops_executed": f32, "achieved_fp64_tflops": f64 / t / 1e12 if t else None,
+           "achieved_fp32_tflops": f32 / t / 1e12 if t else None, "peak_fp64_tflops": fp64_tflops, "peak_fp32_tflops": fp32_tflops}
+    if t and fp64_tflops and fp32_tflops:
+        # both pipes work for the launch: the time each would need at its peak, added up, over the time taken
+        out["frac"] = (f64 / (fp64_tflops * 1e12) + f32 / (fp32_tflops * 1e12)) / t
+        out["frac_fp64_only"] = f64 / t / (fp64_tflops * 1e12)
+    return out
+
+
+def full_path_ransac(lib, device, fp64_tflops, fp32_tflops, n_points=2_000_000):
+    """RANSAC where the early exit does NOT fire (VERDICT r1 #5c): uniformly random points (no planes), threshold 5 mm -
+    no hypothesis keeps every point of its leaf, so all 1024 hypotheses of every block go through the float32 pre-filter
+    and the surviving candidates through the exact float64 evaluation."""
+    import torch
+
+    from octreelib_b200.criteria import MaxPoints
+    from octreelib_b200.grid import Grid, GridConfig
+
+    g = torch.Generator(device=device)
+    g.manual_seed(7)
+    pts = torch.rand((n_points, 3), generator=g, device=device, dtype=torch.float32).to(torch.float64) * torch.tensor(
+        [40.0, 40.0, 3.0], device=device, dtype=torch.float64)
+    out = None
+    for rep in range(2):  # the first repetition warms the allocator
+        grid = Grid(GridConfig(voxel_edge_length=1.0))
+        grid.insert_points(0, pts)
+        grid.subdivide([MaxPoints(100)])
+        f = grid._host.forest
+        f.profile(True)
+        f.extra_ransac_flags = 8
+        ransac_stats_read(lib)
+        np.random.seed(0)
+        grid.map_leaf_points_cuda_ransac(poses_per_batch=10, threshold=0.005, hypotheses_number=H, initial_points_number=K)
+        st = ransac_stats_read(lib)
+        prof = f.profile_read()
+        alive = f.stats(light=True)["n_points_alive"]
+        ms = prof["ransac_kernel"][1]
+        out = {"workload": f"clutter: {n_points} uniformly random points in 40 x 40 x 3 m, edge 1.0, <= 100 points / leaf, threshold 0.005",
+               "blocks_fitted": st["blocks"], "early_exits": st["early_exits"], "kernel_ms": ms,
+               "hypotheses_per_block": st["prefiltered_hypotheses"] / max(st["blocks"], 1) + 32,
+               "exact_candidate_evaluations_per_block": st["candidate_evaluations"] / max(st["blocks"], 1),
+               "points_kept": alive, "points_per_s": n_points / (ms * 1e-3) if ms else None,
+               "hypothesis_evaluations_per_s": st["blocks"] * H / (ms * 1e-3) if ms else None}
+        out.update(ransac_rooflines(st, ms, fp64_tflops, fp32_tflops))
+        del grid, f
+    return out
+
+
 def _claim_stdout():
     """The driver reads ONE JSON line from stdout, but libraries write there too (NCCL prints its version banner to
     stdout during communicator creation).  Point file descriptor 1 at stderr for the whole run and keep a private
@@ -396,6 +465,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=250_000, help="points of the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-path", action="store_true", help="skip the clutter workload (RANSAC without early exits)")
     args = ap.parse_args()
     rank, world, local = dist_env()
     w = WORKLOADS[args.workload]
@@ -487,8 +557,16 @@ def main():
     stats = res[1]
     del res  # the last timed grid must not stay alive next to the profiled / e2e grids (memory at the 1e9-point scale)
 
-    # profiled step (separate from the timed ones): per-stage times for the roofline object
-    _, _, prof, _ = run_step(clouds, numbers, P, w, world, profile=True)
+    # profiled step (separate from the timed ones): per-stage times for the roofline object, executed-arithmetic tallies of
+    # the RANSAC kernel (OL_RANSAC_STATS instantiation)
+    import ctypes as C
+    fp64_peak, fp32_peak = C.c_double(0.0), C.c_double(0.0)
+    lib.ol_measure_fma_peak(C.c_void_p(torch.cuda.current_stream(device).cuda_stream), C.byref(fp64_peak), C.byref(fp32_peak))
+    ransac_stats_read(lib)
+    _, pstats, prof, _ = run_step(clouds, numbers, P, w, world, profile=True)
+    rstats = ransac_stats_read(lib)
+    assert pstats["sample_oob_seen"] == 0 and stats["sample_oob_seen"] == 0, "a RANSAC sample index left its block"
+    full_path = full_path_ransac(lib, device, fp64_peak.value, fp32_peak.value) if (rank == 0 and not args.no_full_path) else None
 
     # e2e: pinned host inputs, result tables read back
     e2e = None
@@ -520,10 +598,14 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     # algorithmic bytes per processed element of every HBM-bound stage
-    # (Morton codes are 32-bit words for trees of at most 10 levels, which covers every bench workload)
-    BYTES = {"bbox": 24, "keygen": 40, "sort_main_hist": 8, "sort_main_pass": 24, "radix_hist_u64": 8, "radix_scatter_u64": 24,
-             "radix_hist_u32": 4, "radix_scatter_u32": 16, "scan": 12, "gather_morton": 12, "part_hist": 8, "part_move": 24,
-             "gather_points": 52}
+    # (Morton codes are 32-bit words for trees of at most 10 levels, which covers every bench workload; the grid-wide sort
+    # moves 32-bit keys when the packed cell key fits them - `key_bits` <= 32, every BASELINE configuration)
+    kb = 4 if stats["key_bits"] <= 32 else 8
+    BYTES = {"bbox": 24, "insert_batch": 48, "keygen": 24 + kb + 4 + 4, "sort_main_hist": kb, "sort_main_pass": 2 * (kb + 4),
+             "radix_hist_u64": 8, "radix_scatter_u64": 24, "radix_hist_u32": 4, "radix_scatter_u32": 16, "scan": 8,
+             "gather_morton": 12, "cells": kb + 4, "part_hist": 8, "part_move": 24, "gather_points": 52}
+    KERNELS = {"sort_main_pass": f"os_pass_kernel<u{8 * kb}> (one onesweep radix digit pass over all points, K2)",
+               "part_move": "part_move_kernel<u32> (fused rank + stable 8-way partition of one octree level, K4)"}
     stage_ms = {k: v[1] for k, v in (prof or {}).items()}
     stages = {}
     for k, (cnt, tot_ms, units) in (prof or {}).items():
@@ -531,34 +613,70 @@ def main():
             gbs = BYTES[k] * units / (tot_ms * 1e-3) / 1e9
             stages[k] = {"launches": cnt, "ms": tot_ms, "elements": units, "bytes_per_element": BYTES[k], "GB/s": gbs,
                          "frac_of_hbm_peak": gbs / hbm_peak}
+    hbm_total_bytes = sum(v["bytes_per_element"] * v["elements"] for v in stages.values())
+    hbm_total_ms = sum(v["ms"] for v in stages.values())
+    # ncu DRAM traffic per launch of the CURRENT build (profiles/r02_ncu_traffic.json, written by tools/ncu_traffic.py from
+    # an `ncu --set full` capture of this workload); null when no capture of this build exists
+    traffic_table = {}
+    try:
+        traffic_table = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+    except Exception:  # noqa: BLE001
+        pass
     roofline = None
-    if "sort_main_pass" in stages:
-        # the dominant HBM-bound kernel: one onesweep digit pass over all points (K2).  Per launch: 12 B read +
-        # 12 B written per (u64 key, u32 index) pair.  `traffic` is the ncu figure of the same kernel on a 1e8-pair
-        # launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_summary_v1.md) scaled to this launch.
-        st = stages["sort_main_pass"]
+    dominant = max((k for k in KERNELS if k in stages), key=lambda k: stages[k]["ms"], default=None)
+    if dominant:
+        # the dominant HBM-bound kernel by time inside the step
+        st = stages[dominant]
         per_launch_units = st["elements"] / st["launches"]
-        roofline = {"kernel": "os_pass_kernel<u64> (onesweep radix digit pass over all points, K2)", "bound": "hbm",
-                    "achieved": st["GB/s"], "peak": hbm_peak, "unit": "GB/s", "frac": st["frac_of_hbm_peak"],
-                    "traffic": 2.382e9 * per_launch_units / 1e8, "algorithmic_bytes_per_launch": 24 * per_launch_units,
+        tr = traffic_table.get(dominant)
+        traffic = tr["dram_bytes_per_launch"] * per_launch_units / tr["elements_per_launch"] if tr else None
+        roofline = {"kernel": KERNELS[dominant], "bound": "hbm", "achieved": st["GB/s"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": st["frac_of_hbm_peak"], "traffic": traffic,
+                    "traffic_source": (tr or {}).get("source"),
+                    "algorithmic_bytes_per_launch": st["bytes_per_element"] * per_launch_units,
                     "avg_launch_ms": st["ms"] / st["launches"], "peak_source": peak_src, "launches": st["launches"],
-                    "note": "achieved = 24 B x pairs per launch / average CUDA-event duration of the launches of one step; "
-                            "the step's other kernels are listed under `stages`, the FP64-bound RANSAC kernel under "
-                            "`roofline_ransac`"}
+                    "all_hbm_stages": {"bytes": hbm_total_bytes, "ms": hbm_total_ms,
+                                       "GB/s": hbm_total_bytes / (hbm_total_ms * 1e-3) / 1e9 if hbm_total_ms else None,
+                                       "frac": hbm_total_bytes / (hbm_total_ms * 1e-3) / 1e9 / hbm_peak if hbm_total_ms else None},
+                    "note": f"achieved = {st['bytes_per_element']} B x elements per launch / average CUDA-event duration of the "
+                            "launches of one step; `all_hbm_stages` aggregates every HBM-bound stage of the step (`stages`); "
+                            "the FP64-bound RANSAC kernel is under `roofline_ransac`"}
     out = dict(base, value=value, ms_per_step=ms_per_step, dtype="f64", clocks=clocks, gpu_launches=int(launches_total), gpu_launches_per_step=int(launches),
                stage_ms=stage_ms, stages=stages,
                result={k: stats[k] for k in ("n_points_inserted", "n_points_alive", "n_cells", "n_leaves",
-                                             "max_depth_reached", "key_bits", "device_bytes_peak")},
+                                             "max_depth_reached", "key_bits", "device_bytes_peak", "sample_oob_seen")},
                n_poses=P)
     if roofline:
         out["roofline"] = roofline
     if prof and "ransac_kernel" in prof:
         r_ms, r_blocks = prof["ransac_kernel"][1], prof["ransac_kernel"][2]
-        out["roofline_ransac"] = {"kernel": "ransac_small_kernel / ransac_kernel (K6)", "bound": "fp64-pipe (issue)", "ms": r_ms,
-                                  "blocks_fitted": r_blocks,
-                                  "reference_equivalent_hypotheses_per_s": r_blocks * H / (r_ms * 1e-3) if r_ms else None,
-                                  "note": "exact-arithmetic early exit + FP32 interval pre-filter: most blocks evaluate 32 of "
-                                          "the 1024 hypotheses (DESIGN.md 4.6); v1 evaluated all of them in 81 ms"}
+        rr = {"kernel": "ransac_small_kernel (K6; ransac_kernel for blocks > 128 points)", "bound": "fp64 pipe", "ms": r_ms,
+              "blocks_fitted": r_blocks, "executed": rstats,
+              "reference_equivalent_hypotheses_per_s": r_blocks * H / (r_ms * 1e-3) if r_ms else None,
+              "peak_source": "ol_measure_fma_peak: dense FMA microbenchmark on this GPU at the clocks of this run (2 flops per FMA)",
+              "note": "executed flops = exact fits x 152 + exact point distances x 6 (float64), pre-filter fits x 120 + distances x 6 "
+                      "(float32), tallied by the OL_RANSAC_STATS instantiation in the profiled step; the reference's arithmetic "
+                      "forbids FMA contraction (-fmad=false), so a multiply-add pair can reach at most half of the FMA peak. On "
+                      "this workload every block exits after its first group of 8 exact hypotheses (planar leaves); "
+                      "`roofline_ransac_full_path` is the same kernel on a workload without early exits"}
+        rr.update(ransac_rooflines(rstats, r_ms, fp64_peak.value, fp32_peak.value))
+        out["roofline_ransac"] = rr
+    if full_path:
+        out["roofline_ransac_full_path"] = full_path
+    ref_gpu = os.path.join(ROOT, "profiles", "r02_reference_numba_on_b200_v2.json")
+    if os.path.exists(ref_gpu):
+        try:
+            rg = json.load(open(ref_gpu))
+            runs = {r["H"]: r for r in rg.get("runs", [])}
+            out["reference_gpu_kernel"] = {
+                "source": "profiles/r02_reference_numba_on_b200_v2.json (tools/ref_on_gpu.py on a B200 of this pool: the unmodified "
+                          "reference kernel through numba " + str(rg.get("numba_version")) + ", BASELINE config 1 blocks)",
+                "H1024": runs.get(1024, {}).get("reference_error"),
+                "H512_evaluate_wall_ms": {"reference": runs.get(512, {}).get("reference_evaluate", {}).get("wall_ms_best"),
+                                          "ours": runs.get(512, {}).get("ours_evaluate", {}).get("wall_ms_best")},
+                "H512_parity": runs.get(512, {}).get("parity_vs_reference_kernel_on_b200")}
+        except Exception:  # noqa: BLE001
+            pass
     if e2e:
         out["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:

@@ -229,10 +229,18 @@ int ol_ransac_evaluate(void *stream, const double *points_dev, int64_t n, const 
                        float *plane_dev, int32_t *best_dev, int32_t *best_count_dev, uint32_t flags,
                        ol_alloc_fn alloc, ol_free_fn free_fn, void *alloc_user);
 
-/* pre-filter statistics since the last reset (device-wide synchronisation):
- * out[0] blocks, [1] hypotheses filtered, [2] trivial intervals, [3] exact evaluations, [4] early exits,
- * [5] interval violations (verify mode) */
-int ol_ransac_stats_read(uint64_t out[8], int32_t reset);
+/* what the RANSAC kernels executed since the last reset (OL_RANSAC_STATS / OL_RANSAC_VERIFY launches; device-wide
+ * synchronisation): out[0] blocks, [1] hypotheses that went through the float32 pre-filter, [2] trivial intervals,
+ * [3] exact evaluations of pre-filter candidates, [4] early exits, [5] interval violations (verify mode),
+ * [6] exact float64 plane fits (util.py:28-84, ~152 flops each at K = 6), [7] exact float64 point-plane distance
+ * evaluations (util.py:16-24, 6 flops each; the final mask pass included), [8] float32 distance evaluations of the
+ * pre-filter (6 flops each) */
+int ol_ransac_stats_read(uint64_t out[16], int32_t reset);
+
+/* Measured arithmetic peaks of this GPU at its current clocks (dense FMA throughput, 2 flops per FMA, 8 independent chains
+ * per thread): the roofline denominators of the RANSAC kernel, which is bound by the FP64 pipe ("the bench
+ * must calibrate with an FMA microbenchmark at the observed clock").  Either pointer may be NULL.  Synchronises. */
+int ol_measure_fma_peak(void *stream, double *out_fp64_tflops, double *out_fp32_tflops);
 
 /* ---- multi-GPU routing (no counterpart in the single-process reference) --------
  * A cell (all poses of it) is owned by rank ol_host_cell_owner(cell coordinates, world).

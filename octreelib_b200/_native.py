@@ -82,7 +82,8 @@ SIGNATURES = {
     "ol_forest_export_points": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, C.POINTER(_i64)]),
     "ol_ransac_evaluate": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _i32, _i32, _f64, _p, _p, _p, _p, _u32, ALLOC_FN,
                                      FREE_FN, _p]),
-    "ol_ransac_stats_read": (C.c_int, [C.POINTER(_u64 * 8), _i32]),
+    "ol_ransac_stats_read": (C.c_int, [C.POINTER(_u64 * 16), _i32]),
+    "ol_measure_fma_peak": (C.c_int, [_p, C.POINTER(_f64), C.POINTER(_f64)]),
     "ol_host_cell_owner": (_u32, [_i64, _i64, _i64, _u32]),
     "ol_partition_by_owner": (C.c_int, [_p, _p, _i64, _p, _i32, _f64, C.POINTER(_f64 * 3), _i32, _p, _p, ALLOC_FN, FREE_FN,
                                         _p]),

@@ -369,12 +369,72 @@ int ol_ransac_evaluate(void* stream, const double* points_dev, int64_t n, const 
     OL_API_END
 }
 
-int ol_ransac_stats_read(uint64_t out[8], int32_t reset) {
+int ol_ransac_stats_read(uint64_t out[16], int32_t reset) {
     OL_NEED(out);
     OL_API_BEGIN
-    unsigned long long tmp[8];
+    unsigned long long tmp[16];
     ol::ransac_stats_read(tmp, reset != 0);
-    for (int i = 0; i < 8; ++i) out[i] = tmp[i];
+    for (int i = 0; i < 16; ++i) out[i] = tmp[i];
+    OL_API_END
+}
+
+// ---- arithmetic pipe peaks (roofline denominators of the RANSAC kernel) -----------------------------
+extern "C++" {
+namespace {
+// 8 independent fused multiply-add chains per thread, `iters` rounds: 16 flops per thread and round
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* __restrict__ out, int iters, T seed) {
+    T a0 = seed, a1 = seed + (T)1, a2 = seed + (T)2, a3 = seed + (T)3, a4 = seed + (T)4, a5 = seed + (T)5, a6 = seed + (T)6,
+      a7 = seed + (T)7;
+    const T m = (T)0.999999, b = (T)1e-6 * (T)(threadIdx.x + 1);
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, b);
+        a1 = fma(a1, m, b);
+        a2 = fma(a2, m, b);
+        a3 = fma(a3, m, b);
+        a4 = fma(a4, m, b);
+        a5 = fma(a5, m, b);
+        a6 = fma(a6, m, b);
+        a7 = fma(a7, m, b);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+template <typename T>
+double measure_fma(cudaStream_t stream, int sms) {
+    const int blocks = sms * 8, threads = 256, iters = sizeof(T) == 8 ? 4096 : 16384;
+    T* out = nullptr;
+    OL_CUDA(cudaMalloc(&out, (size_t)blocks * threads * sizeof(T)));
+    cudaEvent_t e0, e1;
+    OL_CUDA(cudaEventCreate(&e0));
+    OL_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {  // first repetition = warm-up
+        OL_CUDA(cudaEventRecord(e0, stream));
+        fma_peak_kernel<T><<<blocks, threads, 0, stream>>>(out, iters, (T)1);
+        OL_CUDA(cudaEventRecord(e1, stream));
+        OL_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        OL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double tflops = 16.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tflops > best) best = tflops;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return best;
+}
+}  // namespace
+}  // extern "C++"
+
+int ol_measure_fma_peak(void* stream, double* out_fp64_tflops, double* out_fp32_tflops) {
+    OL_API_BEGIN
+    int dev = 0, sms = 148;
+    OL_CUDA(cudaGetDevice(&dev));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (out_fp64_tflops) *out_fp64_tflops = measure_fma<double>((cudaStream_t)stream, sms);
+    if (out_fp32_tflops) *out_fp32_tflops = measure_fma<float>((cudaStream_t)stream, sms);
     OL_API_END
 }
 

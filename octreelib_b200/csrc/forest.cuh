@@ -226,6 +226,6 @@ void launch_ransac(Ctx& c, const double* points, int64_t n_points, const uint32_
                    uint32_t n_work, uint32_t max_block, const double* table, int H, int K, double threshold, uint8_t* mask, float* plane,
                    int32_t* best, int32_t* best_count, uint32_t flags);
 
-void ransac_stats_read(unsigned long long out[8], bool reset);
+void ransac_stats_read(unsigned long long out[16], bool reset);
 
 }  // namespace ol

@@ -47,7 +47,7 @@ constexpr uint32_t RANSAC_FLAG_STATS = 8u;
 constexpr int RANSAC_COOP_MIN_POINTS = 96;  // blocks at least this large score candidates warp-cooperatively
 
 // statistics of the pre-filter (only with RANSAC_FLAG_STATS / VERIFY): see ol_ransac_stats_read
-__device__ unsigned long long g_ransac_stats[8];
+__device__ unsigned long long g_ransac_stats[16];
 
 struct RansacArgs {
     const double* points;
@@ -57,8 +57,9 @@ struct RansacArgs {
     const long long* blk_ref_start; // block_start_indices[b] of the reference's batch layout
     const uint32_t* work;           // blocks to score (size >= K), indexed by work item w
     uint32_t n_work;
-    const uint32_t* sub;            // optional: the work items this launch handles (CTA kernel); NULL = all of them
+    const uint32_t* sub;            // optional: the work items this launch handles; NULL = all of them
     uint32_t n_sub;
+    const uint32_t* n_sub_dev;      // optional: device-side length of `sub` (warp kernel after the lane passes)
     const uint32_t* pk_start;       // optional [n_work]: first point of work item w inside `points` when `points` only
                                     // holds the fitted blocks back to back; NULL = `points` is indexed by blk_start
     const double* table;            // [H][K] float64 uniform [0,1)
@@ -526,6 +527,9 @@ __global__ void __launch_bounds__(RANSAC_THREADS) ransac_kernel(RansacArgs A) {
                 atomicAdd(&g_ransac_stats[2], (unsigned long long)s_stat[0]);              // trivial intervals
                 atomicAdd(&g_ransac_stats[3], (unsigned long long)nc);                     // exact evaluations
                 atomicAdd(&g_ransac_stats[4], processed < nch ? 1ull : 0ull);              // early exits
+                atomicAdd(&g_ransac_stats[6], (unsigned long long)nc);                     // exact fits
+                atomicAdd(&g_ransac_stats[7], (unsigned long long)nc * n + n);             // exact distance evaluations (+ mask)
+                atomicAdd(&g_ransac_stats[8], (unsigned long long)min(processed * RANSAC_THREADS, A.H) * n);  // float32 ones
             }
         }
     } else {
@@ -561,6 +565,9 @@ __global__ void __launch_bounds__(RANSAC_THREADS) ransac_kernel(RansacArgs A) {
             atomicAdd(&g_ransac_stats[1], (unsigned long long)A.H);
             atomicAdd(&g_ransac_stats[2], (unsigned long long)s_stat[0]);
             atomicAdd(&g_ransac_stats[5], (unsigned long long)s_stat[1]);  // interval violations
+            atomicAdd(&g_ransac_stats[6], (unsigned long long)A.H);
+            atomicAdd(&g_ransac_stats[7], (unsigned long long)A.H * n + n);
+            atomicAdd(&g_ransac_stats[8], (unsigned long long)A.H * n);
         }
     }
 
@@ -628,6 +635,10 @@ __device__ __forceinline__ int exact_count_serial(const double* __restrict__ pts
     return cnt;
 }
 
+// STATS: tally what was executed (pre-filter statistics, exact fits, point-distance evaluations) for ol_ransac_stats_read;
+// the plain instantiation carries no counters.  With A.sub the kernel walks that list of work items (the blocks the lane
+// passes below left undecided) instead of all of them.
+template <bool STATS>
 __global__ void __launch_bounds__(RS_WARPS * 32, 3) ransac_small_kernel(RansacArgs A, uint32_t* __restrict__ counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RansacWarpSmem* sm = reinterpret_cast<RansacWarpSmem*>(smem_raw);
@@ -647,26 +658,29 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) ransac_small_kernel(RansacAr
         __syncwarp();
     }
     uint32_t parity = 0;
-    uint32_t st_blocks = 0, st_filtered = 0, st_trivial = 0, st_exact = 0, st_early = 0, st_viol = 0;  // per-lane / per-warp tallies
+    uint32_t st_blocks = 0, st_filtered = 0, st_trivial = 0, st_exact = 0, st_early = 0, st_viol = 0;  // tallies (STATS only)
+    uint32_t st_fit = 0, st_dist = 0, st_fdist = 0;  // exact plane fits, exact and float32 point-distance evaluations
+    const uint32_t n_items = A.sub ? (A.n_sub_dev ? __ldg(A.n_sub_dev) : A.n_sub) : A.n_work;
     for (;;) {
         // RS_GRAB work items per atomic; their descriptors are fetched by RS_GRAB lanes at once, so the dependent
         // counter -> work[] -> block table round trips are paid once per grab instead of once per block
         uint32_t w0 = 0;
         if (lane == 0) w0 = atomicAdd(counter, (uint32_t)RS_GRAB);
         w0 = __shfl_sync(0xffffffffu, w0, 0);
-        if (w0 >= A.n_work) break;
+        if (w0 >= n_items) break;
         __syncwarp();
-        if (lane < RS_GRAB && w0 + lane < A.n_work) {
-            const uint32_t db = A.work[w0 + lane];
+        if (lane < RS_GRAB && w0 + lane < n_items) {
+            const uint32_t wi = A.sub ? A.sub[w0 + lane] : w0 + lane;
+            const uint32_t db = A.work[wi];
             const uint32_t dps = A.blk_start[db];
             W.d_b[lane] = db;
             W.d_n[lane] = A.blk_size[db];
             W.d_ps[lane] = dps;
             W.d_rs[lane] = A.blk_ref_start[db];
-            W.d_pk[lane] = A.pk_start ? A.pk_start[w0 + lane] : dps;
+            W.d_pk[lane] = A.pk_start ? A.pk_start[wi] : dps;
         }
         __syncwarp();
-        const int items = (int)min((uint32_t)RS_GRAB, A.n_work - w0);
+        const int items = (int)min((uint32_t)RS_GRAB, n_items - w0);
       for (int it = 0; it < items; ++it) {
         const int n = W.d_n[it];
         if (n > RS_MAX_POINTS) continue;  // handled by the CTA-per-block kernel
@@ -744,11 +758,11 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) ransac_small_kernel(RansacAr
                     const Interval v = filter_hypothesis(W.q, A.r32t, A.H, A.K, t, n, Pm, Qm, thr_f);
                     if (cnt < v.lo || cnt > v.hi) {
                         atomicOr(A.err, (uint32_t)DEVERR_FILTER_BOUND);
-                        ++st_viol;
+                        if (STATS) ++st_viol;
                     }
-                    if (v.hi - v.lo == n) ++st_trivial;
-                    ++st_filtered;
+                    if (STATS) st_trivial += (v.hi - v.lo == n), ++st_filtered, st_fdist += n;
                 }
+                if (STATS) ++st_fit, st_dist += n;
             }
             // a hypothesis that keeps every point cannot be beaten by a later index
             if (!verify && __any_sync(0xffffffffu, (int)(my_key >> 32) == n)) done = true;
@@ -768,12 +782,11 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) ransac_small_kernel(RansacAr
                     const unsigned long long key = pack_key(v.lo, t);
                     my_sel = key > my_sel ? key : my_sel;
                     full = v.lo == n;
-                    if (v.hi - v.lo == n) ++st_trivial;
-                    ++st_filtered;
+                    if (STATS) st_trivial += (v.hi - v.lo == n), ++st_filtered, st_fdist += n;
                 }
                 if (__any_sync(0xffffffffu, full)) {
                     k_end = kk + 1;
-                    ++st_early;
+                    if (STATS) st_early += (lane == 0);
                     break;
                 }
             }
@@ -807,12 +820,12 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) ransac_small_kernel(RansacAr
                         my_key = key;
                         my_pl = pl;
                     }
-                    ++st_exact;
+                    if (STATS) ++st_exact, ++st_fit, st_dist += n;
                 }
                 if (__any_sync(0xffffffffu, (int)(my_key >> 32) == n)) break;  // later indices cannot win
             }
         } else if (done) {
-            ++st_early;
+            if (STATS) st_early += (lane == 0);
         }
         // ---- winner, outputs, mask (cuda_ransac.py:149-155) -----------------------------------------------
         const unsigned long long bk = warp_max_u64(my_key);
@@ -829,17 +842,22 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) ransac_small_kernel(RansacAr
         }
         const double a = (double)bp.x, bb = (double)bp.y, c = (double)bp.z, d = (double)bp.w;
         for (int i = lane; i < n; i += 32) A.mask[(size_t)ps + i] = plane_distance(a, bb, c, d, pts + 3 * i) < A.thr ? 1 : 0;
-        ++st_blocks;
+        if (STATS) st_blocks += (lane == 0), st_dist += (lane == 0) ? n : 0;  // + the mask pass
         __syncwarp();
       }
     }
-    if (A.flags & (RANSAC_FLAG_STATS | RANSAC_FLAG_VERIFY)) {
+    if (STATS) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             st_filtered += __shfl_xor_sync(0xffffffffu, st_filtered, o);
             st_trivial += __shfl_xor_sync(0xffffffffu, st_trivial, o);
             st_exact += __shfl_xor_sync(0xffffffffu, st_exact, o);
             st_viol += __shfl_xor_sync(0xffffffffu, st_viol, o);
+            st_blocks += __shfl_xor_sync(0xffffffffu, st_blocks, o);
+            st_early += __shfl_xor_sync(0xffffffffu, st_early, o);
+            st_fit += __shfl_xor_sync(0xffffffffu, st_fit, o);
+            st_dist += __shfl_xor_sync(0xffffffffu, st_dist, o);
+            st_fdist += __shfl_xor_sync(0xffffffffu, st_fdist, o);
         }
         if (lane == 0) {
             atomicAdd(&g_ransac_stats[0], (unsigned long long)st_blocks);
@@ -848,6 +866,81 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) ransac_small_kernel(RansacAr
             atomicAdd(&g_ransac_stats[3], (unsigned long long)st_exact);
             atomicAdd(&g_ransac_stats[4], (unsigned long long)st_early);
             atomicAdd(&g_ransac_stats[5], (unsigned long long)st_viol);
+            atomicAdd(&g_ransac_stats[6], (unsigned long long)st_fit);
+            atomicAdd(&g_ransac_stats[7], (unsigned long long)st_dist);
+            atomicAdd(&g_ransac_stats[8], (unsigned long long)st_fdist);
+        }
+    }
+}
+
+// =============================================================================================
+// Lane-per-block passes: hypothesis t for every block that is still undecided, ONE LANE PER BLOCK.
+//
+// The winner of a block is the lowest-index hypothesis with the maximal inlier count, and no count exceeds n: the first
+// hypothesis that keeps all n points ends the block.  On LiDAR leaves (mean 7 points, K = 6 samples) that is hypothesis
+// 0 for 57 % of the blocks, one of 0..2 for 95 %, one of 0..7 for 98.9 % (tools/block_histogram.py on the 100 M-point
+// workload).  A warp that gives a block 8 or 32 lanes evaluates 8 or 32 exact fits where 1-3 are needed; here pass t
+// evaluates hypothesis t with the reference's exact float64 arithmetic for exactly the blocks that passes 0..t-1 left
+// undecided (a compacted list), so the number of exact fits per block is its winning index + 1.  A decided block gets
+// its outputs at once (plane, index, count = n, mask all ones: every point is an inlier).  What is still undecided after
+// RANSAC_LANE_PASSES passes, and every block above RANSAC_LANE_MAX points, goes to the warp-per-block kernel.
+// The blocks are read straight from the packed point array (each lane its own contiguous run; neighbouring lanes read
+// neighbouring runs), no shared memory.
+// =============================================================================================
+constexpr int RANSAC_LANE_PASSES = 8;
+constexpr int RANSAC_LANE_MAX = 32;
+
+__global__ void __launch_bounds__(256) ransac_lane_kernel(RansacArgs A, int t, const uint32_t* __restrict__ list_in,
+                                                          const uint32_t* __restrict__ n_in_dev, uint32_t n_in_host,
+                                                          uint32_t* __restrict__ list_out, uint32_t* __restrict__ n_out) {
+    const uint32_t n_in = n_in_dev ? __ldg(n_in_dev) : n_in_host;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool keep = false;  // stays on the list
+    uint32_t w = 0;
+    int n = 0;
+    bool fitted = false;
+    if (i < n_in) {
+        w = list_in ? list_in[i] : i;
+        const uint32_t b = A.work[w];
+        n = A.blk_size[b];
+        keep = true;
+        if (n <= RANSAC_LANE_MAX) {
+            const uint32_t ps = A.blk_start[b];
+            const double* pts = A.points + (size_t)(A.pk_start ? A.pk_start[w] : ps) * 3;
+            const float4 pl = fit_plane(pts, A.table, A.K, t, n, A.blk_ref_start[b], A.err);
+            const int cnt = exact_count_serial(pts, n, pl, A.thr);
+            fitted = true;
+            if (cnt == n) {  // keeps every point: no later hypothesis can win, earlier ones did not (the block was still listed)
+                keep = false;
+                if (A.plane) reinterpret_cast<float4*>(A.plane)[b] = pl;
+                if (A.best) A.best[b] = t;
+                if (A.best_count) A.best_count[b] = n;
+                for (int j = 0; j < n; ++j) A.mask[(size_t)ps + j] = 1;
+            }
+        }
+    }
+    // order-preserving-enough compaction: one atomic per warp (the order of the list does not matter)
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (m) {
+        uint32_t base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(n_out, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (keep) list_out[base + __popc(m & ((1u << lane) - 1u))] = w;
+    }
+    if (A.flags & RANSAC_FLAG_STATS) {
+        uint32_t fits = fitted ? 1u : 0u, dist = fitted ? (uint32_t)n : 0u, blocks = (fitted && !keep) ? 1u : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            fits += __shfl_xor_sync(0xffffffffu, fits, o);
+            dist += __shfl_xor_sync(0xffffffffu, dist, o);
+            blocks += __shfl_xor_sync(0xffffffffu, blocks, o);
+        }
+        if (lane == 0 && fits) {
+            atomicAdd(&g_ransac_stats[0], (unsigned long long)blocks);
+            atomicAdd(&g_ransac_stats[4], (unsigned long long)blocks);  // decided = early exits
+            atomicAdd(&g_ransac_stats[6], (unsigned long long)fits);
+            atomicAdd(&g_ransac_stats[7], (unsigned long long)dist);
         }
     }
 }
@@ -903,19 +996,45 @@ void launch_ransac(Ctx& c, const double* points, int64_t n_points, const uint32_
     a.flags = flags;
     a.err = c.d_err;
     if (reinterpret_cast<uintptr_t>(points) & 15u) a.flags |= RANSAC_FLAG_NO_TMA;
-    // ---- warp-per-block kernel: persistent warps over every work item (skips the large blocks) ------------
-    DevBuf<uint32_t> counters(c, 2);
+    // ---- lane-per-block passes (default mode): hypotheses 0 .. RANSAC_LANE_PASSES-1, one exact fit per undecided block
+    // and pass; the lists live on the device, no host synchronisation between the passes ---------------------------------
+    DevBuf<uint32_t> counters(c, 2 + RANSAC_LANE_PASSES), list_a, list_b;
     counters.zero();
+    const bool lane_passes = !(flags & (RANSAC_FLAG_EXACT_ONLY | RANSAC_FLAG_VERIFY)) && H > RANSAC_LANE_PASSES;
+    if (lane_passes) {
+        list_a.reset(c, n_work);
+        list_b.reset(c, n_work);
+        const unsigned grid = (n_work + 255) / 256;
+        const uint32_t* in = nullptr;
+        const uint32_t* n_in = nullptr;
+        for (int t = 0; t < RANSAC_LANE_PASSES; ++t) {
+            uint32_t* out = (t & 1) ? list_b.get() : list_a.get();
+            uint32_t* n_out = counters.get() + 2 + t;
+            // pass t > 0 is launched over the upper bound n_work; the threads beyond the list's device-side length retire at once
+            ransac_lane_kernel<<<grid, 256, 0, c.stream>>>(a, t, in, n_in, n_work, out, n_out);
+            OL_CHECK_LAUNCH();
+            in = out;
+            n_in = n_out;
+        }
+        a.sub = in;
+        a.n_sub = n_work;
+        a.n_sub_dev = n_in;
+    }
+    // ---- warp-per-block kernel: persistent warps over the remaining work items (skips the large blocks) ------------
     {
         const size_t smem_small = sizeof(RansacWarpSmem) * RS_WARPS;
-        OL_CUDA(cudaFuncSetAttribute(ransac_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
+        const bool stats = (flags & (RANSAC_FLAG_STATS | RANSAC_FLAG_VERIFY)) != 0;
+        auto kernel = stats ? ransac_small_kernel<true> : ransac_small_kernel<false>;
+        OL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
         int per_sm = 4;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ransac_small_kernel, RS_WARPS * 32, smem_small);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RS_WARPS * 32, smem_small);
         if (per_sm < 1) per_sm = 1;
         const unsigned long long want = ((unsigned long long)n_work + RS_WARPS - 1) / RS_WARPS;
         const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)c.num_sms * per_sm);
-        ransac_small_kernel<<<grid, RS_WARPS * 32, smem_small, c.stream>>>(a, counters.get());
+        kernel<<<grid, RS_WARPS * 32, smem_small, c.stream>>>(a, counters.get());
         OL_CHECK_LAUNCH();
+        a.sub = nullptr;
+        a.n_sub_dev = nullptr;
     }
     // ---- CTA-per-block kernel for blocks above RS_MAX_POINTS points -------------------------------------------
     if (max_block > (uint32_t)RS_MAX_POINTS) {
@@ -938,11 +1057,11 @@ void launch_ransac(Ctx& c, const double* points, int64_t n_points, const uint32_
     }
 }
 
-void ransac_stats_read(unsigned long long out[8], bool reset) {
+void ransac_stats_read(unsigned long long out[16], bool reset) {
     OL_CUDA(cudaDeviceSynchronize());
-    OL_CUDA(cudaMemcpyFromSymbol(out, g_ransac_stats, sizeof(unsigned long long) * 8));
+    OL_CUDA(cudaMemcpyFromSymbol(out, g_ransac_stats, sizeof(unsigned long long) * 16));
     if (reset) {
-        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         OL_CUDA(cudaMemcpyToSymbol(g_ransac_stats, z, sizeof(z)));
     }
 }

@@ -100,6 +100,7 @@ class Forest:
         with self._scope():
             N.check(self._lib.ol_forest_create(C.byref(cfg), C.byref(self._h)))
         self.version = 0  # bumped by every mutating call; hosts cache exports per version
+        self.extra_ransac_flags = 0  # OR-ed into every RANSAC launch (bench.py: OL_RANSAC_STATS for its profiled step)
 
     def _scope(self, flush: bool = True):
         """Context in which torch's current stream is the forest's stream (the allocator callbacks allocate
@@ -246,7 +247,7 @@ class Forest:
         pr, _ = _i32_array(pose_rank)
         with self._scope():
             N.check(self._lib.ol_forest_ransac(self._h, _ptr(tab), H, K, float(threshold), _ptr(pr), int(poses_per_batch),
-                                               1 if apply else 0, int(flags)))
+                                               1 if apply else 0, int(flags) | int(self.extra_ransac_flags)))
         self.version += 1
 
     def apply_mask(self):

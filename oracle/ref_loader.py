@@ -1,6 +1,7 @@
 """
 TEST / BENCH INFRASTRUCTURE (not product code): imports the REAL reference package from `oracle/_ref/`
-(made by `oracle/make_ref.sh`, a verbatim copy of /root/reference/octreelib) or from /root/reference itself.
+(made by `oracle/make_ref.sh`, a verbatim copy of /root/reference/octreelib; `__graft_entry__.build()` runs the recipe
+whenever /root/reference is present).  /root/reference itself is never read from here: it does not exist on the GPU box.
 
 Import shim only - no reference source is modified:
   * `np.float_ = np.float64`   (octreelib/internal/point.py:15-16, octree/octree.py:181 predate numpy 2)
@@ -15,21 +16,20 @@ import sys
 import types
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-REF_DIRS = [os.path.join(_HERE, "_ref"), os.environ.get("OCTREELIB_REFERENCE", "/root/reference")]
+REF_DIR = os.path.join(_HERE, "_ref")
 
 
 def reference_root():
-    for d in REF_DIRS:
-        if d and os.path.isdir(os.path.join(d, "octreelib")):
-            return d
-    return None
+    if os.environ.get("OL_NO_REFERENCE") == "1":  # tests: exercise the port fallback
+        return None
+    return REF_DIR if os.path.isdir(os.path.join(REF_DIR, "octreelib")) else None
 
 
 def load(cudasim: bool):
     """Returns the imported reference package `octreelib` (or raises ImportError with the reason)."""
     root = reference_root()
     if root is None:
-        raise ImportError("the reference package is neither under oracle/_ref (run oracle/make_ref.sh) nor under /root/reference")
+        raise ImportError("the reference package is not under oracle/_ref (run oracle/make_ref.sh where /root/reference exists)")
     if cudasim:
         os.environ["NUMBA_ENABLE_CUDASIM"] = "1"
     else:

@@ -135,7 +135,7 @@ def test_prefilter_statistics():
     needs the exact float64 evaluation."""
     import ctypes as C
     lib = N.lib()
-    out = (C.c_uint64 * 8)()
+    out = (C.c_uint64 * 16)()
     N.check(lib.ol_ransac_stats_read(C.byref(out), 1))
     clouds = lidar64_scan(0, seed=0)[::3]
     grid = Grid(GridConfig(voxel_edge_length=1.0))

@@ -33,7 +33,7 @@ f = grid._host.forest
 np.random.seed(0)
 table = np.random.random((bench.H, bench.K))
 rank = [int(x) for x in grid._host.pose_numbers]
-out = (C.c_uint64 * 8)()
+out = (C.c_uint64 * 16)()
 results = {}
 for name, flags in (("filtered", N.RANSAC_FLAG_STATS), ("exact_only", N.RANSAC_FLAG_EXACT_ONLY), ("verify", N.RANSAC_FLAG_VERIFY)):
     N.check(lib.ol_ransac_stats_read(C.byref(out), 1))
