@@ -251,7 +251,15 @@ def run_step(clouds, numbers, n_poses_total, w, world, profile=False, read_table
     for number, cloud in zip(numbers, clouds):
         grid.insert_points(number, cloud)
     if world > 1:
+        if profile:
+            import torch
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
         grid.exchange()
+        if profile:
+            ev[1].record()
+            torch.cuda.synchronize()
+            grid.last_exchange["ms"] = ev[0].elapsed_time(ev[1])
     grid.subdivide([MaxPoints(w["max_points"])])
     if sampler is not None:
         sampler.sample()
@@ -563,7 +571,9 @@ def main():
     fp64_peak, fp32_peak = C.c_double(0.0), C.c_double(0.0)
     lib.ol_measure_fma_peak(C.c_void_p(torch.cuda.current_stream(device).cuda_stream), C.byref(fp64_peak), C.byref(fp32_peak))
     ransac_stats_read(lib)
-    _, pstats, prof, _ = run_step(clouds, numbers, P, w, world, profile=True)
+    pgrid, pstats, prof, _ = run_step(clouds, numbers, P, w, world, profile=True)
+    exchange_info = getattr(pgrid, "last_exchange", None)
+    del pgrid
     rstats = ransac_stats_read(lib)
     assert pstats["sample_oob_seen"] == 0 and stats["sample_oob_seen"] == 0, "a RANSAC sample index left its block"
     full_path = full_path_ransac(lib, device, fp64_peak.value, fp32_peak.value) if (rank == 0 and not args.no_full_path) else None
@@ -677,6 +687,10 @@ def main():
                 "H512_parity": runs.get(512, {}).get("parity_vs_reference_kernel_on_b200")}
         except Exception:  # noqa: BLE001
             pass
+    if exchange_info:
+        out["exchange"] = dict(exchange_info, note="rank 0; ms = CUDA events around ShardedGrid.exchange() in the profiled step "
+                                                   "(slab boundaries, owner sort, count all-gather, routed copy, insert); bytes = "
+                                                   "point rows this rank sent to other ranks x 24")
     if e2e:
         out["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:

@@ -145,9 +145,16 @@ int ol_forest_filter(ol_forest *f, const uint8_t *keep_table_host, int64_t table
  * table_host: [H][K] float64 uniform [0,1) hypothesis table (ransac/cuda_ransac.py:39-41).
  * pose_rank[p]: position of pose index p in the reference's batch order (= its pose number when
  * numbers are 0..P-1, grid.py:149-157).  With apply != 0 the inlier masks are applied
- * (grid.py:203-215); otherwise they are only stored for export. */
+ * (grid.py:203-215); otherwise they are only stored for export.
+ * pose_start (NULL for a forest that holds the whole grid): multi-GPU, slab partition - pose_start[p] = index, inside
+ * its batch of the reference's layout (cuda_ransac.py:65-67), of the first point of pose index p that THIS forest holds
+ * = (points of the batch's earlier poses on all ranks) + (points of pose p on the lower ranks); poses_per_batch is then
+ * only informative.  The host derives it from one all-gather of ol_forest_pose_point_counts. */
 int ol_forest_ransac(ol_forest *f, const double *table_host, int32_t H, int32_t K, double threshold,
-                     const int32_t *pose_rank, int32_t poses_per_batch, int32_t apply, uint32_t flags);
+                     const int32_t *pose_rank, int32_t poses_per_batch, int32_t apply, uint32_t flags,
+                     const int64_t *pose_start);
+/* out_host[p] = points currently stored for pose index p ([n_poses] int64) */
+int ol_forest_pose_point_counts(ol_forest *f, int64_t *out_host);
 /* applies the mask of the last ol_forest_ransac(apply = 0) call (grid.py:203-215) */
 int ol_forest_apply_mask(ol_forest *f);
 
@@ -243,14 +250,24 @@ int ol_ransac_stats_read(uint64_t out[16], int32_t reset);
 int ol_measure_fma_peak(void *stream, double *out_fp64_tflops, double *out_fp32_tflops);
 
 /* ---- multi-GPU routing (no counterpart in the single-process reference) --------
- * A cell (all poses of it) is owned by rank ol_host_cell_owner(cell coordinates, world).
+ * A cell (all poses of it) is owned by ONE rank, a function of its cell coordinates:
+ *   hash  (slab_bounds_host == NULL)  ol_host_cell_owner(ix, iy, iz, world)
+ *   slab  (slab_bounds_host = world - 1 ascending cell-x boundaries)  owner = #{k : bound[k] <= ix}; order preserving, so
+ *         the reference's lexicographic cell order (grid/grid.py:79-81) is the rank-major concatenation of the local ones
+ *         and its batch-global block_start_indices (ransac/cuda_ransac.py:65-67) can be reproduced exactly across ranks
+ *         (ol_forest_ransac: pose_start).  ol_slab_histogram gives every rank what it needs to pick the boundaries as
+ *         count quantiles: out_dev = int64[2 + n_bins] {min ix, max ix, counts of n_bins equal-width bins over that
+ *         range}; enqueued on the stream, not synchronised.
  * ol_partition_by_owner reorders a rank's local cloud xyz_dev ([n][3] float64, a concatenation of
  * n_segments runs = poses) into out_xyz_dev grouped by owner rank, stable inside (owner, run), and
  * returns counts[owner][run] (host, int64) - the send layout of one NCCL all-to-all. */
 uint32_t ol_host_cell_owner(int64_t qx, int64_t qy, int64_t qz, uint32_t world);
+int ol_slab_histogram(void *stream, const double *xyz_dev, int64_t n, double edge, double corner_x, int32_t n_bins,
+                      int64_t *out_dev);
 int ol_partition_by_owner(void *stream, const double *xyz_dev, int64_t n, const int64_t *seg_sizes_host, int32_t n_segments,
-                          double edge, const double corner[3], int32_t world, double *out_xyz_dev, int64_t *out_counts_host,
-                          ol_alloc_fn alloc, ol_free_fn free_fn, void *alloc_user);
+                          double edge, const double corner[3], int32_t world, const int64_t *slab_bounds_host,
+                          double *out_xyz_dev, int64_t *out_counts_host, ol_alloc_fn alloc, ol_free_fn free_fn,
+                          void *alloc_user);
 
 /* Fused form used when the ranks of one node can map each other's memory (NVLink peer access):
  * ol_route_plan        = the same owner computation and stable sort, but only the permutation
@@ -261,8 +278,16 @@ int ol_partition_by_owner(void *stream, const double *xyz_dev, int64_t n, const 
  *                        at row recv_row_base_host[o]; owner_first_host[o] = first sorted position owned by rank o
  *                        (world + 1 entries).  The caller orders it against the peers with its own barriers. */
 int ol_route_plan(void *stream, const double *xyz_dev, int64_t n, const int64_t *seg_sizes_host, int32_t n_segments, double edge,
-                  const double corner[3], int32_t world, uint32_t *out_perm_dev, int64_t *out_counts_host, ol_alloc_fn alloc,
-                  ol_free_fn free_fn, void *alloc_user);
+                  const double corner[3], int32_t world, const int64_t *slab_bounds_host, uint32_t *out_perm_dev,
+                  int64_t *out_counts_host, ol_alloc_fn alloc, ol_free_fn free_fn, void *alloc_user);
+/* ol_route_plan without any host synchronisation: the send layout stays on the device as the DENSE table
+ * out_dense_dev[owner][pose number] (int64, world x n_poses_total) followed by ONE extra element, the device error word
+ * (non-zero: NaN / out-of-range coordinates) - ready for one all-gather, after which every rank knows every row count.
+ * seg_pose_host[s] = pose number of local run s. */
+int ol_route_plan_dev(void *stream, const double *xyz_dev, int64_t n, const int64_t *seg_sizes_host, const int32_t *seg_pose_host,
+                      int32_t n_segments, int32_t n_poses_total, double edge, const double corner[3], int32_t world,
+                      const int64_t *slab_bounds_host, uint32_t *out_perm_dev, int64_t *out_dense_dev, ol_alloc_fn alloc,
+                      ol_free_fn free_fn, void *alloc_user);
 int ol_route_to_peers(void *stream, const double *xyz_dev, const uint32_t *perm_dev, int64_t n, int32_t world,
                       const int64_t *owner_first_host, void *const *peer_base_host, const int64_t *recv_row_base_host);
 

@@ -65,7 +65,8 @@ SIGNATURES = {
     "ol_forest_subdivide_table": (C.c_int, [_p, _p, _i64, _i32, _p, _i32]),
     "ol_forest_subdivide_levels": (C.c_int, [_p, _p, _i32, _p, _p, _i64, _p, _p, _i32]),
     "ol_forest_filter": (C.c_int, [_p, _p, _i64, _p, _i32]),
-    "ol_forest_ransac": (C.c_int, [_p, _p, _i32, _i32, _f64, _p, _i32, _i32, _u32]),
+    "ol_forest_ransac": (C.c_int, [_p, _p, _i32, _i32, _f64, _p, _i32, _i32, _u32, _p]),
+    "ol_forest_pose_point_counts": (C.c_int, [_p, _p]),
     "ol_forest_apply_mask": (C.c_int, [_p]),
     "ol_forest_apply_pose_mask": (C.c_int, [_p, _p, _i32, _p, _i64]),
     "ol_forest_profile": (C.c_int, [_p, _i32]),
@@ -85,9 +86,12 @@ SIGNATURES = {
     "ol_ransac_stats_read": (C.c_int, [C.POINTER(_u64 * 16), _i32]),
     "ol_measure_fma_peak": (C.c_int, [_p, C.POINTER(_f64), C.POINTER(_f64)]),
     "ol_host_cell_owner": (_u32, [_i64, _i64, _i64, _u32]),
-    "ol_partition_by_owner": (C.c_int, [_p, _p, _i64, _p, _i32, _f64, C.POINTER(_f64 * 3), _i32, _p, _p, ALLOC_FN, FREE_FN,
+    "ol_slab_histogram": (C.c_int, [_p, _p, _i64, _f64, _f64, _i32, _p]),
+    "ol_partition_by_owner": (C.c_int, [_p, _p, _i64, _p, _i32, _f64, C.POINTER(_f64 * 3), _i32, _p, _p, _p, ALLOC_FN, FREE_FN,
                                         _p]),
-    "ol_route_plan": (C.c_int, [_p, _p, _i64, _p, _i32, _f64, C.POINTER(_f64 * 3), _i32, _p, _p, ALLOC_FN, FREE_FN, _p]),
+    "ol_route_plan": (C.c_int, [_p, _p, _i64, _p, _i32, _f64, C.POINTER(_f64 * 3), _i32, _p, _p, _p, ALLOC_FN, FREE_FN, _p]),
+    "ol_route_plan_dev": (C.c_int, [_p, _p, _i64, _p, _p, _i32, _i32, _f64, C.POINTER(_f64 * 3), _i32, _p, _p, _p, ALLOC_FN, FREE_FN,
+                                    _p]),
     "ol_route_to_peers": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p]),
     "ol_sort_pairs_u64": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, ALLOC_FN, FREE_FN, _p]),
     "ol_sort_pairs_u32": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, ALLOC_FN, FREE_FN, _p]),

@@ -159,12 +159,21 @@ int ol_forest_filter(ol_forest* f, const uint8_t* keep_table_host, int64_t table
 }
 
 int ol_forest_ransac(ol_forest* f, const double* table_host, int32_t H, int32_t K, double threshold, const int32_t* pose_rank,
-                     int32_t poses_per_batch, int32_t apply, uint32_t flags) {
+                     int32_t poses_per_batch, int32_t apply, uint32_t flags, const int64_t* pose_start) {
     OL_NEED(f);
     OL_NEED(table_host);
     OL_API_BEGIN
     ol::PoolScope pool_scope(f->impl.ctx);
-    f->impl.ransac(table_host, H, K, threshold, pose_rank, poses_per_batch, apply != 0, flags);
+    f->impl.ransac(table_host, H, K, threshold, pose_rank, poses_per_batch, apply != 0, flags, pose_start);
+    OL_API_END
+}
+
+int ol_forest_pose_point_counts(ol_forest* f, int64_t* out_host) {
+    OL_NEED(f);
+    OL_NEED(out_host);
+    OL_API_BEGIN
+    ol::PoolScope pool_scope(f->impl.ctx);
+    f->impl.pose_point_counts(out_host);
     OL_API_END
 }
 

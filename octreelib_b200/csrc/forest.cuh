@@ -198,7 +198,8 @@ struct Forest {
     void compute_ref_order(const int32_t* pose_rank_host, DevBuf<uint32_t>& ref_order, DevBuf<int32_t>& d_pose_rank,
                            DevBuf<uint32_t>* sorted_rank = nullptr);
     void ransac(const double* table_host, int H, int K, double threshold, const int32_t* pose_rank, int ppb, bool apply,
-                uint32_t flags);
+                uint32_t flags, const int64_t* pose_start = nullptr);
+    void pose_point_counts(int64_t* out_host);
     void apply_mask();
     void materialize_snapshot();
     void drop_snapshot();

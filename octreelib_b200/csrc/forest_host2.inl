@@ -73,6 +73,17 @@ __global__ void block_sizes_ref_kernel(uint32_t nb, const uint32_t* __restrict__
     blk_size[b] = (int32_t)sz;
 }
 
+// sharded form: start = (batch-global index of the pose's first local point) + offset among the local points of the pose
+__global__ void work_refstart_sharded_kernel(uint32_t nb, int K, const uint32_t* __restrict__ ref_order,
+                                             const uint32_t* __restrict__ sorted_rank, const uint32_t* __restrict__ sizes_ref,
+                                             const uint32_t* __restrict__ refstart, const uint32_t* __restrict__ rank_base,
+                                             const long long* __restrict__ start_by_rank, long long* __restrict__ blk_ref_start) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nb || sizes_ref[j] < (uint32_t)K) return;
+    const uint32_t rk = sorted_rank[j];
+    blk_ref_start[ref_order[j]] = start_by_rank[rk] + ((long long)refstart[j] - (long long)rank_base[rk]);
+}
+
 // block sizes in block-table order and in reference order (one pass)
 __global__ void block_sizes_kernel(uint32_t nb, const uint32_t* __restrict__ blk_start, const uint32_t* __restrict__ ref_order,
                                    int32_t* __restrict__ blk_size, uint32_t* __restrict__ sizes_ref) {
@@ -328,7 +339,7 @@ void Forest::compute_ref_order(const int32_t* pose_rank_host, DevBuf<uint32_t>& 
 // Grid.map_leaf_points_cuda_ransac (grid.py:124-215)
 // ---------------------------------------------------------------------------------------------
 void Forest::ransac(const double* table_host, int H, int K, double threshold, const int32_t* pose_rank, int ppb, bool apply,
-                    uint32_t flags) {
+                    uint32_t flags, const int64_t* pose_start) {
     OL_REQUIRE(threshold > 0, OL_ERR_INVALID, "Threshold must be positive");
     OL_REQUIRE(H >= 1, OL_ERR_INVALID, "Number of RANSAC hypotheses must be positive");
     OL_REQUIRE(H <= 1024, OL_ERR_INVALID, "Number of RANSAC hypotheses must be <= 1024 because of the CUDA thread limit.");
@@ -360,7 +371,26 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
         OL_CHECK_LAUNCH();
     }
     exclusive_scan_u32(ctx, sizes_ref.get(), refstart.get(), NB, nullptr);
-    {
+    if (pose_start) {
+        // This forest holds only a PART of the grid (multi-GPU, slab partition: partition.cu).  The reference's start index
+        // of a block (cuda_ransac.py:65-67, per batch) = pose_start[pose] - the batch-global index of the first point of
+        // that pose held HERE, supplied by the host from one all-gather of the per-rank pose sizes - plus the block's
+        // offset among this forest's points of the pose.
+        const int n_ranks = max_rank + 1;
+        std::vector<long long> by_rank((size_t)n_ranks, 0);
+        for (int p = 0; p < n_poses; ++p) by_rank[pose_rank ? pose_rank[p] : p] = (long long)pose_start[p];
+        DevBuf<long long> d_start(ctx, (size_t)n_ranks);
+        DevBuf<uint32_t> rank_base(ctx, (size_t)n_ranks);
+        h2d(ctx, d_start.get(), by_rank.data(), by_rank.size());
+        ProfScope ps(ctx, "ransac_prep");
+        batch_base_search_kernel<<<nblk((size_t)n_ranks), 256, 0, ctx.stream>>>(n_ranks, 1, NB, sorted_rank.get(), refstart.get(),
+                                                                                rank_base.get());
+        OL_CHECK_LAUNCH();
+        work_refstart_sharded_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, K, ref_order.get(), sorted_rank.get(), sizes_ref.get(),
+                                                                       refstart.get(), rank_base.get(), d_start.get(),
+                                                                       blk_ref_start.get());
+        OL_CHECK_LAUNCH();
+    } else {
         ProfScope ps(ctx, "ransac_prep");
         batch_base_search_kernel<<<nblk((size_t)n_batches), 256, 0, ctx.stream>>>(n_batches, ppb, NB, sorted_rank.get(), refstart.get(),
                                                                                   batch_base.get());
@@ -526,6 +556,22 @@ void Forest::pose_counts(int64_t* out_host) {
     ctx.sync();
     for (int p = 0; p < n_poses; ++p)
         for (int k = 0; k < 3; ++k) out_host[(size_t)p * 3 + k] = (int64_t)h[(size_t)p * 3 + k];
+}
+
+// points stored per pose (multi-GPU: the per-rank pose sizes behind the batch-global block starts)
+void Forest::pose_point_counts(int64_t* out_host) {
+    ensure_blocks();
+    const int P = std::max(n_poses, 1);
+    DevBuf<unsigned long long> counts(ctx, (size_t)P * 3);
+    counts.zero();
+    if (NB) {
+        pose_block_counts_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_start.get(), blk_pose.get(), counts.get());
+        OL_CHECK_LAUNCH();
+    }
+    std::vector<unsigned long long> h((size_t)P * 3);
+    d2h(ctx, h.data(), counts.get(), h.size());
+    ctx.sync();
+    for (int p = 0; p < n_poses; ++p) out_host[p] = (int64_t)h[(size_t)p * 3 + 1];
 }
 
 void Forest::stats(ol_forest_stats* s, bool light) {

@@ -241,14 +241,23 @@ class Forest:
         self.version += 1
 
     def ransac(self, table: np.ndarray, threshold: float, pose_rank: Optional[Sequence[int]] = None,
-               poses_per_batch: int = 10, apply: bool = True, flags: int = 0):
+               poses_per_batch: int = 10, apply: bool = True, flags: int = 0, pose_start=None):
+        """pose_start: multi-GPU only - batch-global index of the first point of every pose index held by this forest
+        (include/octreelib_b200.h, ol_forest_ransac)."""
         tab = np.ascontiguousarray(table, dtype=np.float64)
         H, K = tab.shape
         pr, _ = _i32_array(pose_rank)
+        ps = None if pose_start is None else np.ascontiguousarray(pose_start, dtype=np.int64)
         with self._scope():
             N.check(self._lib.ol_forest_ransac(self._h, _ptr(tab), H, K, float(threshold), _ptr(pr), int(poses_per_batch),
-                                               1 if apply else 0, int(flags) | int(self.extra_ransac_flags)))
+                                               1 if apply else 0, int(flags) | int(self.extra_ransac_flags), _ptr(ps)))
         self.version += 1
+
+    def pose_point_counts(self, n_poses: int) -> np.ndarray:
+        out = np.zeros(max(n_poses, 1), dtype=np.int64)
+        with self._scope():
+            N.check(self._lib.ol_forest_pose_point_counts(self._h, _ptr(out)))
+        return out[:n_poses]
 
     def apply_mask(self):
         with self._scope():

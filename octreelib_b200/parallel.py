@@ -2,9 +2,20 @@
 Multi-GPU grid: one process per GPU, `torch.distributed` (NCCL over NVLink) as the
 plumbing.  Every grid cell is independent in the reference (`Grid.subdivide` / `filter` loop over
 cells, grid/grid.py:255-258, 266-267; the scheme octree is per cell, octree_manager.py:50-66; RANSAC
-is per (pose, leaf) block, cuda_ransac.py:94-97), so the grid shards by CELL:
+is per (pose, leaf) block, cuda_ransac.py:94-97), so the grid shards by CELL, by a function of the cell key:
 
-    owner(cell) = hash(ix, iy, iz) mod world            (csrc/partition.cu, `ol_host_cell_owner`)
+    partition="slab" (default)  owner(cell) = #{k : bound[k] <= ix}: an ORDER-PRESERVING hash of the cell key.  The
+                                world - 1 boundaries are count quantiles of the leading cell coordinate over all ranks
+                                (`ol_slab_histogram` + one all-gather), so the load is balanced, and because the reference
+                                enumerates cells lexicographically (grid/grid.py:79-81) every cell of rank r precedes every
+                                cell of rank r + 1.  That makes the two things that depend on the GLOBAL order exact: the
+                                batch layout of the RANSAC kernel (`block_start_indices`, cuda_ransac.py:65-67: the sample
+                                index is computed on the batch-global start) and the final leaf / plane tables
+                                (`gather_tables`: rank-major concatenation = the reference's order).
+    partition="hash"            owner(cell) = hash(ix, iy, iz) mod world (csrc/partition.cu, `ol_host_cell_owner`): the
+                                layout north_star names; balanced whatever the geometry, but the global order - and with
+                                it the sample index where `R n + start` sits within an ulp of an integer (p ~ 1e-8 per
+                                draw) - would need a merge of all (cell, pose) tables.
 
 `ShardedGrid.insert_points` stages a rank's local clouds; `exchange()` partitions them by owner on the
 GPU (`ol_partition_by_owner`: owner kernel + stable radix sort + gather), moves them with ONE
@@ -26,7 +37,52 @@ from . import _native as N
 from ._host import ForestHost
 from .forest import TorchAllocator, require_cuda
 
-__all__ = ["ShardedGrid", "routing_layout", "exchange_points", "segments_from_counts"]
+__all__ = ["ShardedGrid", "routing_layout", "exchange_points", "segments_from_counts", "slab_boundaries", "pose_starts"]
+
+SLAB_BINS = 1024
+
+
+def slab_boundaries(gathered: np.ndarray, world: int) -> np.ndarray:
+    """world - 1 ascending cell-x boundaries (owner = number of boundaries <= ix) that split the points of all ranks
+    into equal shares.  gathered[r] = [min ix, max ix, counts of SLAB_BINS equal-width bins over that range] as written
+    by `ol_slab_histogram` on rank r (min > max: the rank holds nothing).  Every rank computes the same answer from the
+    same gathered array.  The bins are spread uniformly over their cells, which is exact for bins one cell wide."""
+    g = np.asarray(gathered, dtype=np.int64)
+    have = g[:, 0] <= g[:, 1]
+    if not have.any() or world <= 1:
+        return np.zeros(max(world - 1, 0), dtype=np.int64)
+    lo, hi = int(g[have, 0].min()), int(g[have, 1].max())
+    n_bins = g.shape[1] - 2
+    # cumulative count at candidate boundaries: resolution = the finest rank bin width, at most 1 << 16 candidates
+    span = hi - lo + 1
+    step = max(1, -(-span // (1 << 16)))
+    edges = lo + step * np.arange(-(-span // step) + 1, dtype=np.int64)  # candidate boundaries lo, lo + step, ...
+    cum = np.zeros(len(edges), dtype=np.float64)
+    for r in np.flatnonzero(have):
+        rlo, rhi = int(g[r, 0]), int(g[r, 1])
+        width = max(1, -(-(rhi - rlo + 1) // n_bins))
+        c = np.concatenate([[0], np.cumsum(g[r, 2:], dtype=np.float64)])  # points of rank r with ix < rlo + k * width
+        pos = (edges - rlo) / width
+        cum += np.interp(pos, np.arange(n_bins + 1, dtype=np.float64), c)
+    total = cum[-1]
+    targets = total * np.arange(1, world, dtype=np.float64) / world
+    idx = np.searchsorted(cum, targets, side="left")
+    return edges[np.minimum(idx, len(edges) - 1)].astype(np.int64)
+
+
+def pose_starts(pose_sizes: np.ndarray, rank: int, poses_per_batch: int) -> np.ndarray:
+    """pose_sizes[r][p] = points of pose p held by rank r (slab partition: rank-major = the reference's cell order).
+    Returns, per pose, the index inside its batch of `poses_per_batch` consecutive poses (grid.py:149-157) of the first
+    point of that pose held by `rank`: points of the batch's earlier poses on all ranks + points of the pose on the
+    lower ranks (cuda_ransac.py:65-67: block_start_indices is an exclusive cumulative sum over the batch)."""
+    sizes = np.asarray(pose_sizes, dtype=np.int64)
+    total = sizes.sum(axis=0)
+    P = sizes.shape[1]
+    before = np.zeros(P, dtype=np.int64)
+    for first in range(0, P, poses_per_batch):
+        t = total[first:first + poses_per_batch]
+        before[first:first + poses_per_batch] = np.cumsum(t) - t
+    return before + sizes[:rank].sum(axis=0)
 
 
 def routing_layout(counts_local: np.ndarray, pose_numbers: Sequence[int], n_poses_total: int) -> np.ndarray:
@@ -115,9 +171,13 @@ class _PeerBuffers:
 class ShardedGrid:
     """The `Grid` operations of the hot path on a cell-sharded grid.  Pose numbers must be 0..P-1."""
 
-    def __init__(self, grid_config, n_poses_total: int, group=None):
+    def __init__(self, grid_config, n_poses_total: int, group=None, partition: str = "slab"):
         import torch.distributed as dist
 
+        if partition not in ("slab", "hash"):
+            raise ValueError("partition must be 'slab' or 'hash'")
+        self.partition = partition
+        self.slab_bounds: Optional[np.ndarray] = None
         self._cfg = grid_config
         self._group = group
         self._dist = dist
@@ -176,38 +236,59 @@ class ShardedGrid:
         counts = np.zeros((self.world, n_seg), dtype=np.int64)
         alloc = TorchAllocator(dev)
         corner = (C.c_double * 3)(*self._corner)
+        bounds = None
+        if self.partition == "slab" and self.world > 1:
+            # count quantiles of the leading cell coordinate over all ranks: one small all-gather, one read-back
+            hist = torch.empty(2 + SLAB_BINS, dtype=torch.int64, device=dev)
+            N.check(lib.ol_slab_histogram(C.c_void_p(stream.cuda_stream), C.c_void_p(local.data_ptr()), n,
+                                          float(self._cfg.voxel_edge_length), float(self._corner[0]), SLAB_BINS,
+                                          C.c_void_p(hist.data_ptr())))
+            allh = torch.empty((self.world, 2 + SLAB_BINS), dtype=torch.int64, device=dev)
+            self._dist.all_gather_into_tensor(allh, hist, group=self._group)
+            self.slab_bounds = slab_boundaries(allh.cpu().numpy(), self.world)
+            bounds = np.ascontiguousarray(self.slab_bounds, dtype=np.int64)
+            mark("slabs")
+        bounds_p = None if bounds is None else bounds.ctypes.data_as(C.c_void_p)
         use_p2p = self.world > 1 and os.environ.get("OL_EXCHANGE", "p2p") == "p2p" and self._dist.get_backend(self._group) == "nccl"
         perm = send = None
-        if use_p2p:
-            perm = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-            N.check(lib.ol_route_plan(C.c_void_p(stream.cuda_stream), C.c_void_p(local.data_ptr()), n,
-                                      sizes.ctypes.data_as(C.c_void_p), n_seg, float(self._cfg.voxel_edge_length), C.byref(corner),
-                                      self.world, C.c_void_p(perm.data_ptr()), counts.ctypes.data_as(C.c_void_p), alloc.alloc_cb,
-                                      alloc.free_cb, None))
-        else:
+        recv = None
+        send_counts = None
+
+        def staged_partition():
+            """owner-grouped staging copy + counts on the host (the NCCL all-to-all path)"""
+            nonlocal send, send_counts
             send = torch.empty_like(local)
             N.check(lib.ol_partition_by_owner(C.c_void_p(stream.cuda_stream), C.c_void_p(local.data_ptr()), n,
                                               sizes.ctypes.data_as(C.c_void_p), n_seg, float(self._cfg.voxel_edge_length),
-                                              C.byref(corner), self.world, C.c_void_p(send.data_ptr()),
+                                              C.byref(corner), self.world, bounds_p, C.c_void_p(send.data_ptr()),
                                               counts.ctypes.data_as(C.c_void_p), alloc.alloc_cb, alloc.free_cb, None))
-        mark("partition")
-        send_counts = routing_layout(counts[:, :len(parts)] if parts else counts[:, :0], numbers, self.n_poses_total)
-        recv = None
+            send_counts = routing_layout(counts[:, :len(parts)] if parts else counts[:, :0], numbers, self.n_poses_total)
+
         if use_p2p:
-            # every rank learns the whole (source, destination, pose) count cube: 8 x 8 x P integers
-            mine = torch.from_numpy(send_counts).to(dev)
-            cube_t = torch.empty((self.world,) + tuple(mine.shape), dtype=torch.int64, device=dev)
+            # Owner sort and (owner, pose) row counts stay on the device; the dense send layout of every rank (+ its error
+            # word) is all-gathered and read back ONCE: every rank then knows the whole (source, destination, pose) cube.
+            perm = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+            mine = torch.empty(self.world * self.n_poses_total + 1, dtype=torch.int64, device=dev)
+            seg_pose_local = np.ascontiguousarray(numbers if numbers else [0], dtype=np.int32)
+            N.check(lib.ol_route_plan_dev(C.c_void_p(stream.cuda_stream), C.c_void_p(local.data_ptr()), n,
+                                          sizes.ctypes.data_as(C.c_void_p), seg_pose_local.ctypes.data_as(C.c_void_p), n_seg,
+                                          self.n_poses_total, float(self._cfg.voxel_edge_length), C.byref(corner), self.world, bounds_p,
+                                          C.c_void_p(perm.data_ptr()), C.c_void_p(mine.data_ptr()), alloc.alloc_cb, alloc.free_cb, None))
+            mark("partition")
+            cube_t = torch.empty((self.world, mine.shape[0]), dtype=torch.int64, device=dev)
             self._dist.all_gather_into_tensor(cube_t, mine, group=self._group)
-            cube = cube_t.cpu().numpy()                      # [src][dst][pose]
+            gathered = cube_t.cpu().numpy()
+            if gathered[:, -1].any():
+                bad = int(np.bitwise_or.reduce(gathered[:, -1]))
+                raise ValueError("point cloud contains NaN or infinite coordinates" if bad & 1 else
+                                 "cell coordinates out of the representable range")
+            cube = gathered[:, :-1].reshape(self.world, self.world, self.n_poses_total)   # [src][dst][pose]
+            send_counts = cube[self.rank]
             tot = cube.sum(axis=2)                           # [src][dst]
             pb = _PeerBuffers.get(int(tot.sum(axis=0).max()), dev, self._group, self.world)
             if pb is None:
                 use_p2p = False
-                send = torch.empty_like(local)
-                N.check(lib.ol_partition_by_owner(C.c_void_p(stream.cuda_stream), C.c_void_p(local.data_ptr()), n,
-                                                  sizes.ctypes.data_as(C.c_void_p), n_seg, float(self._cfg.voxel_edge_length),
-                                                  C.byref(corner), self.world, C.c_void_p(send.data_ptr()),
-                                                  counts.ctypes.data_as(C.c_void_p), alloc.alloc_cb, alloc.free_cb, None))
+                staged_partition()
             else:
                 owner_first = np.concatenate([[0], np.cumsum(send_counts.sum(axis=1))]).astype(np.int64)
                 base = (np.cumsum(tot, axis=0) - tot)[self.rank].astype(np.int64)   # rows of lower source ranks, per destination
@@ -236,6 +317,9 @@ class ShardedGrid:
                               f"barrier1 {ev[2].elapsed_time(ev[3]):.3f} ms", flush=True)
                 recv_counts = cube[:, self.rank, :]
                 recv = pb.buf[: int(recv_counts.sum()) * 3].view(-1, 3)
+        else:
+            staged_partition()
+            mark("partition")
         if not use_p2p:
             if self.world > 1:
                 recv, recv_counts = exchange_points(send, send_counts, self._group)
@@ -248,7 +332,9 @@ class ShardedGrid:
             seg_sizes, seg_pose, seg_first = np.array([0], np.int64), np.array([0], np.int32), np.array([0], np.int64)
         self._host.forest.insert_segments(recv, seg_sizes, seg_pose, seg_first, self.n_poses_total)
         self.last_exchange = dict(sent=int(send_counts.sum() - send_counts[self.rank].sum()), received=int(recv.shape[0]),
-                                  kept=int(send_counts[self.rank].sum()))
+                                  kept=int(send_counts[self.rank].sum()), mode="p2p" if use_p2p else ("nccl" if self.world > 1 else "local"),
+                                  partition=self.partition, disabled_reason=_PeerBuffers.disabled_reason,
+                                  bytes=int(send_counts.sum() - send_counts[self.rank].sum()) * 24)
         self._staged = []
         self.exchanged = True
         mark("insert")
@@ -277,7 +363,19 @@ class ShardedGrid:
             raise ValueError("Number of RANSAC hypotheses must be <= 1024 because of the CUDA thread limit.")
         # every rank draws the same table (same seed state is the caller's responsibility, as in the reference)
         ransac = CudaRansac(threshold=threshold, hypotheses_number=hypotheses_number, initial_points_number=initial_points_number)
-        self._host.forest.ransac(ransac.random_hypotheses, threshold, list(range(self.n_poses_total)), poses_per_batch, apply=True)
+        forest = self._host.forest
+        start = None
+        if self.world > 1 and self.partition == "slab":
+            # the reference's batch-global start index of every block (cuda_ransac.py:65-67) across the ranks: one
+            # all-gather of the per-rank pose sizes (P integers per rank)
+            import torch
+
+            mine = torch.from_numpy(forest.pose_point_counts(self.n_poses_total)).to(forest.device)
+            sizes = torch.empty((self.world, self.n_poses_total), dtype=torch.int64, device=forest.device)
+            self._dist.all_gather_into_tensor(sizes, mine, group=self._group)
+            start = pose_starts(sizes.cpu().numpy(), self.rank, poses_per_batch)
+        forest.ransac(ransac.random_hypotheses, threshold, list(range(self.n_poses_total)), poses_per_batch, apply=True,
+                      pose_start=start)
         self._host._counts_cache = None
 
     def _require_exchanged(self):
@@ -306,7 +404,11 @@ class ShardedGrid:
 
     # ---- final gather of the leaf / plane tables ----------------------------------------------------
     def gather_tables(self, dst: int = 0) -> Optional[Dict[str, np.ndarray]]:
-        """Leaf table (corner, edge) and fitted-plane table of every rank, concatenated on `dst`."""
+        """Leaf table (corner, edge, depth) and fitted-plane table of the whole grid on rank `dst`, in the REFERENCE's
+        global order (slab partition): leaves = cells lexicographic x leaf order (grid.py:217-232) = the rank-major
+        concatenation of the local tables; plane rows = (pose, then that leaf order), i.e. the rows of every rank sorted
+        stably by pose.  `leaf` of a plane row indexes the gathered leaf table.  With partition="hash" the tables are
+        concatenated by rank (no global order) and `rank_of_leaf` tells where a leaf lives."""
         forest = self._host.forest
         mine = dict(leaves=forest.export_leaves(), planes=forest.export_ransac(scored_only=True))
         if self.world == 1:
@@ -315,6 +417,13 @@ class ShardedGrid:
         self._dist.gather_object(mine, out, dst=dst, group=self._group)
         if self.rank != dst:
             return None
-        return dict(leaves={k: np.concatenate([o["leaves"][k] for o in out]) for k in mine["leaves"]},
-                    planes={k: np.concatenate([o["planes"][k] for o in out]) for k in mine["planes"]},
-                    rank_of_leaf=np.concatenate([np.full(len(o["leaves"]["edge"]), r) for r, o in enumerate(out)]))
+        n_leaves = [len(o["leaves"]["edge"]) for o in out]
+        leaf_base = np.concatenate([[0], np.cumsum(n_leaves)])
+        leaves = {k: np.concatenate([o["leaves"][k] for o in out]) for k in mine["leaves"]}
+        planes = {k: np.concatenate([o["planes"][k] for o in out]) for k in mine["planes"]}
+        planes["leaf"] = np.concatenate([o["planes"]["leaf"].astype(np.int64) + leaf_base[r] for r, o in enumerate(out)])
+        rank_of_leaf = np.concatenate([np.full(n, r) for r, n in enumerate(n_leaves)])
+        if self.partition == "slab":
+            order = np.argsort(planes["pose"], kind="stable")  # rank-major inside a pose = lexicographic cells
+            planes = {k: v[order] for k, v in planes.items()}
+        return dict(leaves=leaves, planes=planes, rank_of_leaf=rank_of_leaf)

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from octreelib_b200 import _native
-from octreelib_b200.parallel import exchange_points, routing_layout, segments_from_counts
+from octreelib_b200.parallel import exchange_points, pose_starts, routing_layout, segments_from_counts, slab_boundaries
 
 
 def _free_port():
@@ -101,3 +101,47 @@ def test_owner_hash_is_balanced_and_deterministic():
         share = np.bincount(o, minlength=world) / len(o)
         assert share.min() > 0.8 / world and share.max() < 1.2 / world
     assert lib.ol_host_cell_owner(1, 2, 3, 8) == lib.ol_host_cell_owner(1, 2, 3, 8)
+
+
+def test_slab_boundaries_balance_and_are_rank_independent():
+    """count quantiles of the leading cell coordinate from the per-rank (min, max, equal-width histogram) summaries"""
+    rng = np.random.default_rng(1)
+    world, bins = 8, 1024
+    ix = [rng.integers(-50 + 120 * r, 260 + 120 * r, 30000) for r in range(world)]
+    ix[3] = np.empty(0, dtype=np.int64)  # a rank without points
+    g = np.zeros((world, 2 + bins), dtype=np.int64)
+    for r, v in enumerate(ix):
+        if len(v) == 0:
+            g[r, 0], g[r, 1] = np.iinfo(np.int64).max, np.iinfo(np.int64).min
+            continue
+        lo, hi = v.min(), v.max()
+        w = max(1, -(-(hi - lo + 1) // bins))
+        g[r, 0], g[r, 1] = lo, hi
+        g[r, 2:] = np.bincount((v - lo) // w, minlength=bins)
+    b = slab_boundaries(g, world)
+    assert len(b) == world - 1 and (np.diff(b) >= 0).all()
+    allx = np.concatenate(ix)
+    share = np.bincount(np.searchsorted(b, allx, side="right"), minlength=world) / len(allx)
+    assert share.min() > 0.8 / world and share.max() < 1.25 / world, share
+    assert (slab_boundaries(g.copy(), world) == b).all()
+    # every point in ONE column of cells: no split is possible, every boundary coincides (documented limitation)
+    g1 = np.zeros((2, 2 + bins), dtype=np.int64)
+    g1[:, 0] = g1[:, 1] = 5
+    g1[:, 2] = 1000
+    assert len(set(slab_boundaries(g1, 2).tolist())) == 1
+
+
+def test_pose_starts_restate_the_reference_batch_layout():
+    """cuda_ransac.py:65-67 + grid.py:149-157: exclusive cumulative sum over the poses of a batch, cells in rank-major order"""
+    sizes = np.array([[3, 1, 2, 0, 4], [1, 1, 1, 5, 0], [0, 2, 0, 1, 1]])  # [rank][pose]
+    for ppb in (1, 2, 5):
+        flat = []  # the reference's layout: batch, pose, then (rank-major) cells
+        for first in range(0, 5, ppb):
+            pos = 0
+            for p in range(first, min(first + ppb, 5)):
+                for r in range(3):
+                    flat.append((p, r, pos))
+                    pos += sizes[r, p]
+        for r in range(3):
+            got = pose_starts(sizes, r, ppb)
+            assert got.tolist() == [next(pos for (p2, r2, pos) in flat if p2 == p and r2 == r) for p in range(5)]

@@ -16,7 +16,7 @@ from octreelib_b200.synthetic import lidar64_scan
 pytestmark = pytest.mark.gpu
 
 
-def _partition(points_list, edge, world):
+def _partition(points_list, edge, world, bounds=None):
     import torch
 
     lib = N.lib()
@@ -27,11 +27,104 @@ def _partition(points_list, edge, world):
     counts = np.zeros((world, len(points_list)), dtype=np.int64)
     alloc = TorchAllocator(dev)
     corner = (C.c_double * 3)(0.0, 0.0, 0.0)
+    b = None if bounds is None else np.ascontiguousarray(bounds, dtype=np.int64)
     N.check(lib.ol_partition_by_owner(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), C.c_void_p(local.data_ptr()),
                                       len(local), sizes.ctypes.data_as(C.c_void_p), len(sizes), float(edge), C.byref(corner),
-                                      world, C.c_void_p(send.data_ptr()), counts.ctypes.data_as(C.c_void_p), alloc.alloc_cb,
-                                      alloc.free_cb, None))
+                                      world, None if b is None else b.ctypes.data_as(C.c_void_p), C.c_void_p(send.data_ptr()),
+                                      counts.ctypes.data_as(C.c_void_p), alloc.alloc_cb, alloc.free_cb, None))
     return send.cpu().numpy(), counts
+
+
+def test_slab_histogram_boundaries_and_owner():
+    """Slab partition: the device histogram of the leading cell coordinate, the quantile boundaries every rank derives
+    from the gathered histograms, and the owner rule of the partition kernel (owner = number of boundaries <= ix)."""
+    import torch
+
+    from octreelib_b200.parallel import SLAB_BINS, slab_boundaries
+
+    lib = N.lib()
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(4)
+    world = 4
+    clouds = [(rng.normal(0, 40, (20000, 3)) + np.array([60.0 * r, 0, 0])).astype(np.float32).astype(np.float64) for r in range(world)]
+    gathered = np.zeros((world, 2 + SLAB_BINS), dtype=np.int64)
+    for r, c in enumerate(clouds):
+        t = torch.from_numpy(c).to(dev)
+        out = torch.empty(2 + SLAB_BINS, dtype=torch.int64, device=dev)
+        N.check(lib.ol_slab_histogram(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), C.c_void_p(t.data_ptr()), len(c), 2.0, 0.0,
+                                      SLAB_BINS, C.c_void_p(out.data_ptr())))
+        gathered[r] = out.cpu().numpy()
+        ix = np.floor_divide(c[:, 0], 2.0).astype(np.int64)
+        assert gathered[r, 0] == ix.min() and gathered[r, 1] == ix.max() and gathered[r, 2:].sum() == len(c)
+        width = max(1, -(-(ix.max() - ix.min() + 1) // SLAB_BINS))
+        assert (gathered[r, 2:] == np.bincount((ix - ix.min()) // width, minlength=SLAB_BINS)).all()
+    bounds = slab_boundaries(gathered, world)
+    assert len(bounds) == world - 1 and (np.diff(bounds) >= 0).all()
+    allpts = np.vstack(clouds)
+    owner = np.searchsorted(bounds, np.floor_divide(allpts[:, 0], 2.0).astype(np.int64), side="right")
+    share = np.bincount(owner, minlength=world) / len(allpts)
+    assert share.min() > 0.2 and share.max() < 0.3, share
+    send, counts = _partition(clouds, 2.0, world, bounds)
+    run = np.concatenate([np.full(len(c), j) for j, c in enumerate(clouds)])
+    order = np.lexsort((np.arange(len(allpts)), run, owner))
+    assert (send == allpts[order]).all()
+    exp = np.zeros_like(counts)
+    np.add.at(exp, (owner, run), 1)
+    assert (counts == exp).all()
+
+
+def test_emulated_slab_ranks_reproduce_the_single_gpu_batch_layout():
+    """Three 'ranks' with slab ownership, processed one after the other: with `pose_start` from the gathered pose sizes
+    every rank's RANSAC uses the reference's batch-global block starts, so planes / winners / masks are bit-identical to
+    the single-GPU grid at poses_per_batch = 2 - and the rank-major concatenation of the plane tables, sorted stably by
+    pose, is the single-GPU table row for row."""
+    from octreelib_b200.parallel import pose_starts
+    from octreelib_b200.ransac import CudaRansac
+
+    world, P, ppb = 3, 5, 2
+    clouds = {p: lidar64_scan(p, seed=7)[::8] for p in range(P)}
+    ref = Grid(GridConfig(voxel_edge_length=1.0))
+    for p in range(P):
+        ref.insert_points(p, clouds[p])
+    ref.subdivide([MaxPoints(40)])
+    np.random.seed(9)
+    table = CudaRansac(0.02, 128, 6).random_hypotheses
+    ref._host.forest.ransac(table, 0.02, list(range(P)), ppb, apply=False)
+    want = ref._host.forest.export_ransac(scored_only=True)
+    want_leaves = ref._host.forest.export_leaves()
+    # slab boundaries from the true quantiles of ix
+    ix_all = np.concatenate([np.floor_divide(c[:, 0], 1.0).astype(np.int64) for c in clouds.values()])
+    bounds = np.quantile(ix_all, [1 / 3, 2 / 3]).astype(np.int64)
+    forests, sizes = [], np.zeros((world, P), dtype=np.int64)
+    for r in range(world):
+        f = Forest(1.0)
+        seg_sizes, seg_pose, pts = [], [], []
+        for p in range(P):
+            own = np.searchsorted(bounds, np.floor_divide(clouds[p][:, 0], 1.0).astype(np.int64), side="right") == r
+            if own.any():
+                pts.append(clouds[p][own])
+                seg_sizes.append(int(own.sum()))
+                seg_pose.append(p)
+        f.insert_segments(np.vstack(pts), seg_sizes, seg_pose, [0] * len(seg_sizes), P)
+        f.subdivide(40)
+        sizes[r] = f.pose_point_counts(P)
+        forests.append(f)
+    assert (sizes.sum(axis=0) == [len(clouds[p]) for p in range(P)]).all()
+    rows = []
+    leaf_base = 0
+    for r, f in enumerate(forests):
+        f.ransac(table, 0.02, list(range(P)), ppb, apply=False, pose_start=pose_starts(sizes, r, ppb))
+        got = f.export_ransac(scored_only=True)
+        lv = f.export_leaves()
+        for i in range(len(got["best"])):
+            rows.append((int(got["pose"][i]), r, i, tuple(lv["corner"][got["leaf"][i]]), float(lv["edge"][got["leaf"][i]]),
+                         int(got["best"][i]), int(got["best_count"][i]), got["plane"][i].tobytes()))
+        leaf_base += len(lv["edge"])
+    rows.sort(key=lambda t: (t[0], t[1], t[2]))  # stable by pose over the rank-major concatenation
+    assert len(rows) == len(want["best"])
+    for i, row in enumerate(rows):
+        assert row[0] == want["pose"][i] and row[3] == tuple(want_leaves["corner"][want["leaf"][i]])
+        assert row[5] == want["best"][i] and row[6] == want["best_count"][i] and row[7] == want["plane"][i].tobytes()
 
 
 def test_partition_by_owner_matches_host_rule():
@@ -150,7 +243,7 @@ def test_fused_route_to_peers_matches_partition():
     corner = (C.c_double * 3)(0.0, 0.0, 0.0)
     stream = torch.cuda.current_stream(dev)
     N.check(lib.ol_route_plan(C.c_void_p(stream.cuda_stream), C.c_void_p(local.data_ptr()), n, sizes.ctypes.data_as(C.c_void_p),
-                              len(sizes), 1.0, C.byref(corner), world, C.c_void_p(perm.data_ptr()),
+                              len(sizes), 1.0, C.byref(corner), world, None, C.c_void_p(perm.data_ptr()),
                               counts2.ctypes.data_as(C.c_void_p), alloc.alloc_cb, alloc.free_cb, None))
     assert (counts2 == counts).all()
     per_owner = counts.sum(axis=1)
