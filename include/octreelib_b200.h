@@ -257,7 +257,7 @@ int ol_measure_fma_peak(void *stream, double *out_fp64_tflops, double *out_fp32_
  *         and its batch-global block_start_indices (ransac/cuda_ransac.py:65-67) can be reproduced exactly across ranks
  *         (ol_forest_ransac: pose_start).  ol_slab_histogram gives every rank what it needs to pick the boundaries as
  *         count quantiles: out_dev = int64[2 + n_bins] {min ix, max ix, counts of n_bins equal-width bins over that
- *         range}; enqueued on the stream, not synchronised.
+ *         range} of a 1-in-8 sample of the rank's points; enqueued on the stream, not synchronised.
  * ol_partition_by_owner reorders a rank's local cloud xyz_dev ([n][3] float64, a concatenation of
  * n_segments runs = poses) into out_xyz_dev grouped by owner rank, stable inside (owner, run), and
  * returns counts[owner][run] (host, int64) - the send layout of one NCCL all-to-all. */

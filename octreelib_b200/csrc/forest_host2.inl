@@ -184,13 +184,39 @@ __global__ void ransac_snapshot_kernel(uint32_t nb, const uint32_t* __restrict__
     }
 }
 
-__global__ void pose_block_counts_kernel(uint32_t nb, const uint32_t* __restrict__ blk_start, const int32_t* __restrict__ blk_pose,
-                                         unsigned long long* __restrict__ counts /*[P][3]*/) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
-    const int p = blk_pose[b];
-    atomicAdd(&counts[(size_t)p * 3 + 0], 1ull);
-    atomicAdd(&counts[(size_t)p * 3 + 1], (unsigned long long)(blk_start[b + 1] - blk_start[b]));
+// per pose: number of non-empty blocks (= leaves with points of that pose) and number of points.  Millions of blocks fall on
+// a few hundred poses, so the counters are privatised in shared memory (one flush of the non-zero ones per CTA); poses
+// beyond the shared table go straight to global atomics.
+constexpr int POSE_COUNT_SMEM = 2048;
+__global__ void __launch_bounds__(256) pose_block_counts_kernel(uint32_t nb, const uint32_t* __restrict__ blk_start,
+                                                                const int32_t* __restrict__ blk_pose, int n_poses,
+                                                                unsigned long long* __restrict__ counts /*[P][3]*/) {
+    __shared__ unsigned int s_blocks[POSE_COUNT_SMEM], s_points[POSE_COUNT_SMEM];
+    const int np = n_poses < POSE_COUNT_SMEM ? n_poses : POSE_COUNT_SMEM;
+    for (int p = threadIdx.x; p < np; p += blockDim.x) {
+        s_blocks[p] = 0u;
+        s_points[p] = 0u;
+    }
+    __syncthreads();
+    // a CTA never sees more than 2^32 points: its share of the block table is bounded by the point count (< 2^31)
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+        const int p = blk_pose[b];
+        const uint32_t sz = blk_start[b + 1] - blk_start[b];
+        if (p < np) {
+            atomicAdd(&s_blocks[p], 1u);
+            atomicAdd(&s_points[p], sz);
+        } else {
+            atomicAdd(&counts[(size_t)p * 3 + 0], 1ull);
+            atomicAdd(&counts[(size_t)p * 3 + 1], (unsigned long long)sz);
+        }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < np; p += blockDim.x) {
+        if (s_blocks[p]) {
+            atomicAdd(&counts[(size_t)p * 3 + 0], (unsigned long long)s_blocks[p]);
+            atomicAdd(&counts[(size_t)p * 3 + 1], (unsigned long long)s_points[p]);
+        }
+    }
 }
 
 __global__ void cell_leaf_count_kernel(uint32_t L, const uint32_t* __restrict__ lcell, uint32_t* __restrict__ cell_nl) {
@@ -540,7 +566,8 @@ void Forest::pose_counts(int64_t* out_host) {
     DevBuf<unsigned long long> counts(ctx, (size_t)P * 3);
     counts.zero();
     if (NB) {
-        pose_block_counts_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_start.get(), blk_pose.get(), counts.get());
+        pose_block_counts_kernel<<<std::min<unsigned>(nblk(NB), (unsigned)ctx.num_sms * 8), 256, 0, ctx.stream>>>(
+            NB, blk_start.get(), blk_pose.get(), n_poses, counts.get());
         OL_CHECK_LAUNCH();
     }
     if (CP) {
@@ -560,12 +587,18 @@ void Forest::pose_counts(int64_t* out_host) {
 
 // points stored per pose (multi-GPU: the per-rank pose sizes behind the batch-global block starts)
 void Forest::pose_point_counts(int64_t* out_host) {
+    for (int p = 0; p < n_poses; ++p) out_host[p] = 0;
+    if (!any_dead) {  // nothing has been removed yet: the inserted segments say it all, no kernel and no synchronisation
+        for (size_t s = 0; s < seg_pose.size(); ++s) out_host[seg_pose[s]] += (int64_t)seg_start[s + 1] - (int64_t)seg_start[s];
+        return;
+    }
     ensure_blocks();
     const int P = std::max(n_poses, 1);
     DevBuf<unsigned long long> counts(ctx, (size_t)P * 3);
     counts.zero();
     if (NB) {
-        pose_block_counts_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_start.get(), blk_pose.get(), counts.get());
+        pose_block_counts_kernel<<<std::min<unsigned>(nblk(NB), (unsigned)ctx.num_sms * 8), 256, 0, ctx.stream>>>(
+            NB, blk_start.get(), blk_pose.get(), n_poses, counts.get());
         OL_CHECK_LAUNCH();
     }
     std::vector<unsigned long long> h((size_t)P * 3);

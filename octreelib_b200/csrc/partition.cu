@@ -121,11 +121,17 @@ __global__ void __launch_bounds__(256) route_to_peers_kernel(const double* __res
 }
 
 // ---- slab boundaries: range and histogram of the leading cell coordinate ---------------------------------------------
+// Both kernels look at every SLAB_SAMPLE-th point only: the boundaries balance the load, they need not be exact quantiles
+// (ownership itself is decided per point from the boundaries), and a LiDAR sweep keeps thousands of consecutive points in
+// the same column of cells - counted one by one they would all hit the same shared-memory counter.
+constexpr uint32_t SLAB_SAMPLE = 8;
+
 __global__ void __launch_bounds__(256) slab_range_kernel(const double* __restrict__ xyz, uint32_t n, double edge, double c0,
                                                          long long* __restrict__ out /*[0] min ix, [1] max ix*/) {
     long long lo = LLONG_MAX, hi = LLONG_MIN;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const double q = cell_coord(xyz[(size_t)i * 3], c0, edge);
+    const uint32_t m = (n + SLAB_SAMPLE - 1) / SLAB_SAMPLE;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < m; k += gridDim.x * blockDim.x) {
+        const double q = cell_coord(xyz[(size_t)k * SLAB_SAMPLE * 3], c0, edge);
         if (fabs(q) < 4503599627370496.0) {
             const long long ix = (long long)q;
             lo = ix < lo ? ix : lo;
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(256) slab_range_kernel(const double* __restric
     }
 }
 
-// counts[k] = points whose ix falls into bin k = (ix - min ix) / width, width = ceil((max - min + 1) / n_bins)
+// counts[k] = sampled points whose ix falls into bin k = (ix - min ix) / width, width = ceil((max - min + 1) / n_bins)
 __global__ void __launch_bounds__(256) slab_hist_kernel(const double* __restrict__ xyz, uint32_t n, double edge, double c0,
                                                         int n_bins, long long* __restrict__ out /*[2 + n_bins]*/) {
     extern __shared__ unsigned int s_h[];
@@ -152,9 +158,17 @@ __global__ void __launch_bounds__(256) slab_hist_kernel(const double* __restrict
     __syncthreads();
     const long long lo = out[0], hi = out[1];
     const long long width = hi >= lo ? ((hi - lo + 1) + n_bins - 1) / n_bins : 1;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const double q = cell_coord(xyz[(size_t)i * 3], c0, edge);
-        if (fabs(q) < 4503599627370496.0) atomicAdd(&s_h[(int)(((long long)q - lo) / width)], 1u);
+    const uint32_t m = (n + SLAB_SAMPLE - 1) / SLAB_SAMPLE;
+    const uint32_t m_pad = (m + 31u) & ~31u;  // whole warps take part in the match
+    const int lane = threadIdx.x & 31;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < m_pad; k += gridDim.x * blockDim.x) {
+        int bin = -1;
+        if (k < m) {
+            const double q = cell_coord(xyz[(size_t)k * SLAB_SAMPLE * 3], c0, edge);
+            if (fabs(q) < 4503599627370496.0) bin = (int)(((long long)q - lo) / width);
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);  // one shared-memory atomic per distinct bin and warp
+        if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_h[bin], (unsigned int)__popc(peers));
     }
     __syncthreads();
     for (int k = threadIdx.x; k < n_bins; k += blockDim.x)
@@ -178,7 +192,7 @@ int ol_slab_histogram(void* stream, const double* xyz_dev, int64_t n, double edg
         const long long init[2] = {LLONG_MAX, LLONG_MIN};
         OL_CUDA(cudaMemcpyAsync(out_dev, init, sizeof(init), cudaMemcpyHostToDevice, st));
         if (n == 0) return OL_OK;
-        const unsigned g = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8);
+        const unsigned g = (unsigned)std::min<int64_t>((n / SLAB_SAMPLE + 256) / 256, 148 * 8);
         slab_range_kernel<<<g, 256, 0, st>>>(xyz_dev, (uint32_t)n, edge, corner_x, reinterpret_cast<long long*>(out_dev));
         OL_CHECK_LAUNCH();
         slab_hist_kernel<<<g, 256, sizeof(unsigned int) * (size_t)n_bins, st>>>(xyz_dev, (uint32_t)n, edge, corner_x, n_bins,

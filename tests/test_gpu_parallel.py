@@ -54,8 +54,8 @@ def test_slab_histogram_boundaries_and_owner():
         N.check(lib.ol_slab_histogram(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), C.c_void_p(t.data_ptr()), len(c), 2.0, 0.0,
                                       SLAB_BINS, C.c_void_p(out.data_ptr())))
         gathered[r] = out.cpu().numpy()
-        ix = np.floor_divide(c[:, 0], 2.0).astype(np.int64)
-        assert gathered[r, 0] == ix.min() and gathered[r, 1] == ix.max() and gathered[r, 2:].sum() == len(c)
+        ix = np.floor_divide(c[::8, 0], 2.0).astype(np.int64)  # the kernels look at every 8th point
+        assert gathered[r, 0] == ix.min() and gathered[r, 1] == ix.max() and gathered[r, 2:].sum() == len(ix)
         width = max(1, -(-(ix.max() - ix.min() + 1) // SLAB_BINS))
         assert (gathered[r, 2:] == np.bincount((ix - ix.min()) // width, minlength=SLAB_BINS)).all()
     bounds = slab_boundaries(gathered, world)
