@@ -41,7 +41,8 @@ typedef enum ol_status {
     OL_ERR_NONFINITE = 7,   /* NaN / inf input                      -> ValueError */
     OL_ERR_STATE = 8,       /* call not valid in the current state  -> RuntimeError */
     OL_ERR_POSE = 9,        /* unknown pose index                   -> KeyError */
-    OL_ERR_INTERNAL = 10    /* self-check failed (RANSAC verify)    -> AssertionError */
+    OL_ERR_INTERNAL = 10,   /* self-check failed (RANSAC verify)    -> AssertionError */
+    OL_ERR_CAPACITY = 11    /* exchange receive buffer too small    -> the host binding grows it and retries */
 } ol_status;
 
 typedef void *(*ol_alloc_fn)(void *user, size_t bytes);
@@ -290,6 +291,35 @@ int ol_route_plan_dev(void *stream, const double *xyz_dev, int64_t n, const int6
                       ol_free_fn free_fn, void *alloc_user);
 int ol_route_to_peers(void *stream, const double *xyz_dev, const uint32_t *perm_dev, int64_t n, int32_t world,
                       const int64_t *owner_first_host, void *const *peer_base_host, const int64_t *recv_row_base_host);
+
+/* ---- fused exchange over peer-mapped memory (csrc/exchange.cu) ----------------------------------------------------------
+ * The production path of the multi-GPU grid when the ranks of a node can map each other's memory: owner rule, counting,
+ * routing and the hand-over to the receiving forest in one call, with every inter-rank dependency resolved on the device
+ * (flags in peer-mapped control blocks; no library collective, ONE host wait).  The host binding provides the memory:
+ *   ctrl_ptrs_host[r]              control block of rank r mapped into THIS process, ol_exchange_ctrl_bytes(world, n_poses)
+ *                                  bytes each, zero-filled once before the first exchange (all ranks, then a barrier);
+ *   data_ptrs_host[b * world + r]  receive buffer b of rank r (rows_cap x 3 float64), n_buffers >= 1 of them so that a
+ *                                  forest can keep using buffer b while the next exchange fills buffer b + 1.
+ * ol_exchange_run is collective (every rank calls it with the same slabs / buffer): it routes the rank's local clouds
+ * (clouds_dev_ptrs_host[k] = [sizes_host[k]][3] float64 on the device, pose numbers poses_host[k] ascending) and makes the
+ * EMPTY forest f adopt receive buffer `buffer` as its point array: (source rank, pose) runs in the order the reference would
+ * have seen the points of a pose when the ranks hold increasing index ranges of it.  The buffer must stay untouched until f is
+ * destroyed or ol_forest_disown_points(f) copied the points out.  info_out[4] = rows sent to other ranks, rows received,
+ * rows kept, largest receive total of any rank; bounds_out[world - 1] = the slab boundaries chosen (slabs != 0; count
+ * quantiles of the leading cell coordinate, identical on every rank); pose_sizes_out[world][n_poses] (uint32) = rows of every
+ * pose held by every rank afterwards (what the batch-global block starts of ol_forest_ransac's pose_start need).
+ * Returns OL_ERR_CAPACITY (on every rank alike) when a rank would receive more than rows_cap rows: nothing was routed;
+ * create a larger exchange and call again. */
+typedef struct ol_exchange ol_exchange;
+int64_t ol_exchange_ctrl_bytes(int32_t world, int32_t n_poses);
+int ol_exchange_create(int32_t world, int32_t rank, int32_t n_poses, int64_t rows_cap, int32_t n_buffers,
+                       void *const *ctrl_ptrs_host, void *const *data_ptrs_host, int32_t device, ol_exchange **out);
+int ol_exchange_destroy(ol_exchange *x);
+int ol_exchange_run(ol_exchange *x, ol_forest *f, const double *const *clouds_dev_ptrs_host, const int64_t *sizes_host,
+                    const int32_t *poses_host, int32_t count, int32_t slabs, int32_t buffer, int64_t *info_out,
+                    int64_t *bounds_out, uint32_t *pose_sizes_out);
+/* copies an adopted point array into memory of the forest's own (no-op otherwise); synchronises */
+int ol_forest_disown_points(ol_forest *f);
 
 /* ---- primitives, exported so that tests can check them in isolation -------------------------- */
 /* stable LSD radix sort of (key, value) pairs on bits [begin_bit, end_bit); result in keys_dev/vals_dev */

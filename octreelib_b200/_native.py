@@ -19,6 +19,7 @@ OL_ERR_OUT_OF_NODE, OL_ERR_DEPTH_CAP, OL_ERR_NONFINITE, OL_ERR_STATE, OL_ERR_POS
 OL_MAX_DEPTH = 21
 RANSAC_FLAG_NO_TMA, RANSAC_FLAG_EXACT_ONLY, RANSAC_FLAG_VERIFY, RANSAC_FLAG_STATS = 1, 2, 4, 8
 OL_ERR_INTERNAL = 10
+OL_ERR_CAPACITY = 11
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 FREE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
@@ -47,6 +48,10 @@ class ForestStats(C.Structure):
 
 class NativeLibraryMissing(ImportError):
     pass
+
+
+class ExchangeCapacityError(RuntimeError):
+    """a rank would receive more rows than its exchange buffers hold (parallel.py grows them and retries)"""
 
 
 _p = C.c_void_p
@@ -93,6 +98,11 @@ SIGNATURES = {
     "ol_route_plan_dev": (C.c_int, [_p, _p, _i64, _p, _p, _i32, _i32, _f64, C.POINTER(_f64 * 3), _i32, _p, _p, _p, ALLOC_FN, FREE_FN,
                                     _p]),
     "ol_route_to_peers": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p]),
+    "ol_exchange_ctrl_bytes": (_i64, [_i32, _i32]),
+    "ol_exchange_create": (C.c_int, [_i32, _i32, _i32, _i64, _i32, _p, _p, _i32, C.POINTER(_p)]),
+    "ol_exchange_destroy": (C.c_int, [_p]),
+    "ol_exchange_run": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
+    "ol_forest_disown_points": (C.c_int, [_p]),
     "ol_sort_pairs_u64": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, ALLOC_FN, FREE_FN, _p]),
     "ol_sort_pairs_u32": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, ALLOC_FN, FREE_FN, _p]),
     "ol_debug_force_legacy_sort": (C.c_int, [_i32]),
@@ -136,6 +146,7 @@ _EXC = {
     OL_ERR_STATE: RuntimeError,
     OL_ERR_POSE: KeyError,
     OL_ERR_INTERNAL: AssertionError,
+    OL_ERR_CAPACITY: ExchangeCapacityError,
 }
 
 

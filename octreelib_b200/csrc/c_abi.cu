@@ -2,12 +2,19 @@
 #include <algorithm>
 #include <new>
 
+#include "exchange.cuh"
 #include "forest.cuh"
 #include "primitives.cuh"
 
 struct ol_forest {
     ol::Forest impl;
     explicit ol_forest(const ol_forest_config& c) : impl(c) {}
+};
+
+struct ol_exchange {
+    ol::Exchange impl;
+    ol_exchange(int world, int rank, int n_poses, int64_t rows_cap, int nbuf, void* const* ctrl, void* const* data, int device)
+        : impl(world, rank, n_poses, rows_cap, nbuf, ctrl, data, device) {}
 };
 
 namespace ol {
@@ -90,6 +97,43 @@ int ol_forest_insert_segments(ol_forest* f, const double* xyz, int64_t n, int32_
     OL_REQUIRE(n_segments > 0, OL_ERR_INVALID, "n_segments must be positive");
     ol::PoolScope pool_scope(f->impl.ctx);
     f->impl.insert(xyz, n, src_on_device != 0, seg_sizes, seg_pose, seg_first, n_segments, n_poses_total);
+    OL_API_END
+}
+
+int64_t ol_exchange_ctrl_bytes(int32_t world, int32_t n_poses) { return (int64_t)ol::XchgCtrl::bytes(world, n_poses); }
+
+int ol_exchange_create(int32_t world, int32_t rank, int32_t n_poses, int64_t rows_cap, int32_t n_buffers, void* const* ctrl_ptrs_host,
+                       void* const* data_ptrs_host, int32_t device, ol_exchange** out) {
+    OL_NEED(ctrl_ptrs_host);
+    OL_NEED(data_ptrs_host);
+    OL_NEED(out);
+    OL_API_BEGIN
+    *out = new ol_exchange(world, rank, n_poses, rows_cap, n_buffers, ctrl_ptrs_host, data_ptrs_host, device);
+    OL_API_END
+}
+
+int ol_exchange_destroy(ol_exchange* x) {
+    OL_API_BEGIN
+    delete x;
+    OL_API_END
+}
+
+int ol_exchange_run(ol_exchange* x, ol_forest* f, const double* const* clouds_dev_ptrs_host, const int64_t* sizes_host,
+                    const int32_t* poses_host, int32_t count, int32_t slabs, int32_t buffer, int64_t* info_out, int64_t* bounds_out,
+                    uint32_t* pose_sizes_out) {
+    OL_NEED(x);
+    OL_NEED(f);
+    OL_API_BEGIN
+    OL_REQUIRE(count == 0 || (clouds_dev_ptrs_host && sizes_host && poses_host), OL_ERR_INVALID, "NULL cloud tables");
+    ol::PoolScope pool_scope(f->impl.ctx);
+    x->impl.run(f->impl, clouds_dev_ptrs_host, sizes_host, poses_host, count, slabs, buffer, info_out, bounds_out, pose_sizes_out);
+    OL_API_END
+}
+
+int ol_forest_disown_points(ol_forest* f) {
+    OL_NEED(f);
+    OL_API_BEGIN
+    f->impl.disown_points();
     OL_API_END
 }
 

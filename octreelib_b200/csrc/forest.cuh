@@ -21,6 +21,14 @@ struct Forest {
     DevBuf<double> P64;          // [cap][3]
     size_t cap = 0, N = 0;
     size_t bbox_done = 0;        // points already folded into d_bbox / checked for NaN
+    // multi-GPU exchange (exchange.cu): P64 may be a receive buffer the forest does not own (DevBuf without a context), and
+    // the cell-coordinate range of its points is then known without a bounding-box pass
+    bool q_known = false;
+    long long q_lo[3] = {0, 0, 0}, q_hi[3] = {0, 0, 0};
+    bool points_external() const { return P64.ptr != nullptr && P64.ctx == nullptr; }
+    void adopt_points(double* ext, size_t n, const int64_t* seg_sizes, const int32_t* seg_pose_in, const int64_t* seg_first_in,
+                      int n_segments, int n_poses_total, const long long qlo[3], const long long qhi[3]);
+    void disown_points();        // copy an adopted point array into memory of the forest's own
     DevBuf<uint8_t> alive_r;     // [cap] 1 = point still stored; allocated by the first removal (filter / RANSAC mask)
     bool any_dead = false;
     bool alive_stale = false;    // alive_r lags behind the current order (apply_keep); see ensure_alive

@@ -127,6 +127,10 @@ int Forest::insert(const double* xyz, int64_t n, bool on_device, const int64_t* 
     materialize_snapshot();
     ensure_alive();
     if (shaped && I > 0) save_shape();  // a later pose follows the existing subdivision (octree_manager.py:171)
+    if (q_known) {  // points after an adopted buffer: the bounding box is taken over everything again
+        q_known = false;
+        bbox_done = 0;
+    }
     if (N + (size_t)n > cap) {
         size_t ncap = std::max<size_t>(N + (size_t)n, cap + cap / 2 + 1024);
         DevBuf<double> np(ctx, ncap * 3);
@@ -190,6 +194,51 @@ int Forest::insert(const double* xyz, int64_t n, bool on_device, const int64_t* 
     return pose_index;
 }
 
+// Multi-GPU exchange: the receive buffer becomes the point array of an empty forest (no copy).  The (source rank, pose)
+// runs arrive as segments; q_lo / q_hi bound the cell coordinates of everything in the buffer, so build() needs neither a
+// bounding-box pass nor its read-back.  The buffer must stay valid until the forest is destroyed or disown_points() ran.
+void Forest::adopt_points(double* ext, size_t n, const int64_t* seg_sizes, const int32_t* seg_pose_in, const int64_t* seg_first_in,
+                          int n_segments, int n_poses_total, const long long qlo[3], const long long qhi[3]) {
+    OL_REQUIRE(N == 0 && n_poses == 0 && !shaped, OL_ERR_STATE, "only an empty forest can adopt a point array");
+    OL_REQUIRE(n < (1ull << 31), OL_ERR_INVALID, "more than 2^31 - 1 points per forest are not supported");
+    P64.release();
+    P64.ctx = nullptr;
+    P64.ptr = ext;
+    P64.count = n * 3;
+    cap = n;
+    size_t r = 0;
+    for (int s = 0; s < n_segments; ++s) {
+        OL_REQUIRE(seg_sizes[s] >= 0 && seg_pose_in[s] >= 0 && seg_pose_in[s] < n_poses_total, OL_ERR_INVALID, "bad segment description");
+        if (!seg_pose.empty() && seg_pose_in[s] < seg_pose.back()) segs_pose_monotone = false;
+        seg_pose.push_back(seg_pose_in[s]);
+        seg_first.push_back(seg_first_in ? seg_first_in[s] : 0);
+        seg_start.back() = (uint32_t)r;
+        r += (size_t)seg_sizes[s];
+        seg_start.push_back((uint32_t)r);
+    }
+    OL_REQUIRE(r == n, OL_ERR_INVALID, "segment sizes do not add up to n");
+    n_poses = n_poses_total;
+    N = n;
+    bbox_done = n;
+    q_known = true;
+    for (int a = 0; a < 3; ++a) {
+        q_lo[a] = qlo[a];
+        q_hi[a] = qhi[a];
+    }
+    if ((int)pose_epoch.size() < n_poses) pose_epoch.resize(n_poses, n_subdivide_calls);
+    built = false;
+    shaped = false;
+    order_valid = blocks_valid = ransac_valid = false;
+}
+
+void Forest::disown_points() {
+    if (!points_external()) return;
+    DevBuf<double> own(ctx, std::max<size_t>(cap, 1) * 3);
+    d2d(ctx, own.get(), P64.get(), N * 3);
+    P64.swap(own);  // `own` now holds the foreign pointer without a context: its destructor frees nothing
+    ctx.sync();     // the caller may hand the buffer to somebody else as soon as this returns
+}
+
 // Many device-resident poses at once (the Python host defers `insert_points` of CUDA tensors and flushes them here):
 // one exact-size growth of the point array, one pointer-table upload, one copy kernel - instead of a driver call and a
 // possible re-allocation per pose.  Every cloud becomes one new pose; returns the index of the first one.
@@ -206,6 +255,10 @@ int Forest::insert_batch(const double* const* xyz_dev, const int64_t* sizes, int
     materialize_snapshot();
     ensure_alive();
     if (shaped && I > 0) save_shape();
+    if (q_known) {
+        q_known = false;
+        bbox_done = 0;
+    }
     if (N + total > cap) {
         const size_t ncap = N + total;  // the batch is usually the whole map: grow exactly once
         DevBuf<double> np(ctx, ncap * 3);
@@ -278,7 +331,32 @@ void Forest::build() {
     mort32 = kp.depth <= MORTON32_MAX_DEPTH;
     kp.pose_bits = segs_pose_monotone ? 0 : bit_length_u64((uint64_t)std::max(n_poses - 1, 0));
     int bits[3] = {0, 0, 0};
-    {  // read-back 1 of the build: bounding box + error word
+    // The point-sized work buffers are allocated BEFORE the read-back below, while the GPU is still busy with the insert
+    // copy: every large allocation is a trip into the host allocator callback (5-10 us), and nine of them between the
+    // synchronisation and the key kernel left the GPU idle for 50-65 us.  The key width is only known after the
+    // read-back; the buffers are sized by the width of the previous build of this process and re-made if it differs.
+    const uint32_t n_pre = (uint32_t)N;
+    static int s_last_key_bytes = 4;
+    const int pre_key_bytes = s_last_key_bytes;
+    DevBuf<uint64_t> kraw0, kraw1, mort_r;
+    DevBuf<uint32_t> vals0, vals1;
+    DevBuf<unsigned long long> d_total;
+    if (n_pre) {
+        cellidx0.reset(ctx, n_pre);
+        kraw0.reset(ctx, pre_key_bytes == 4 ? ((size_t)n_pre + 1) / 2 : (size_t)n_pre);
+        kraw1.reset(ctx, pre_key_bytes == 4 ? ((size_t)n_pre + 1) / 2 : (size_t)n_pre);
+        mort_r.reset(ctx, mort_len(n_pre));
+        vals0.reset(ctx, n_pre);
+        vals1.reset(ctx, n_pre);
+        d_total.reset(ctx, 1);
+    }
+    if (q_known && bbox_done == N) {  // adopted receive buffer: the cell-coordinate range came with it, nothing to read back
+        if (!cfg.single_cell && N > 0)
+            for (int a = 0; a < 3; ++a) {
+                kp.qmin[a] = q_lo[a];
+                bits[a] = bit_length_u64((uint64_t)(q_hi[a] - q_lo[a]));
+            }
+    } else {  // read-back 1 of the build: bounding box + error word
         long long hb[6];
         uint32_t e = 0;
         read_back({{d_bbox.get(), sizeof(hb), hb}, {d_err.get(), 4, &e}});
@@ -323,16 +401,23 @@ void Forest::build() {
     }
     // the cell tables are sized by what the key space allows (the number of cells is only known after K3)
     const size_t c_max = cell_bits < 31 ? std::min<size_t>(n, (size_t)1 << cell_bits) : n;
-    cellidx0.reset(ctx, n);
     cell_key.reset(ctx, c_max);
     cell_start0.reset(ctx, c_max + 1);
-    DevBuf<unsigned long long> d_total(ctx, 1);
-    DevBuf<uint64_t> mort_r(ctx, mort_len(n));
-    DevBuf<uint32_t> vals0(ctx, n), vals1(ctx, n);
+    const int key_bytes = key_bits <= 32 ? 4 : 8;
+    if (key_bytes != pre_key_bytes) {
+        kraw0.reset(ctx, key_bytes == 4 ? ((size_t)n + 1) / 2 : (size_t)n);
+        kraw1.reset(ctx, key_bytes == 4 ? ((size_t)n + 1) / 2 : (size_t)n);
+    }
+    s_last_key_bytes = key_bytes;
     // K1 + K2 + K3 for one key width
     auto run = [&](auto key_tag) {
         using KeyT = decltype(key_tag);
-        DevBuf<KeyT> keys0(ctx, n), keys1(ctx, n);
+        struct Raw {
+            DevBuf<uint64_t>& b;
+            KeyT* get() const { return reinterpret_cast<KeyT*>(b.get()); }
+            void swap(Raw& o) { b.swap(o.b); }
+            void release() { b.release(); }
+        } keys0{kraw0}, keys1{kraw1};
         {
             ProfScope ps(ctx, "keygen", (double)n);
             if (mort32)

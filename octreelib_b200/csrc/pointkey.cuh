@@ -56,6 +56,17 @@ __host__ __device__ inline unsigned long long point_morton(const double p[3], co
     return m;
 }
 
+// owner rank of a cell under the hash partition of the multi-GPU grid (partition.cu, exchange.cu)
+__host__ __device__ inline uint32_t cell_owner(long long qx, long long qy, long long qz, uint32_t world) {
+    unsigned long long h = (unsigned long long)qx * 0x9E3779B97F4A7C15ull;
+    h ^= (unsigned long long)qy * 0xC2B2AE3D27D4EB4Full;
+    h ^= (unsigned long long)qz * 0x165667B19E3779F9ull;
+    h ^= h >> 32;
+    h *= 0xD6E8FEB86659FD93ull;
+    h ^= h >> 32;
+    return (uint32_t)((h >> 16) % world);
+}
+
 // corner of the cell with integer coordinates q (float64; exact for integer-valued edges)
 __host__ __device__ inline double cell_corner_coord(long long q, double corner, double edge, int single_cell) {
     if (single_cell) return corner;

@@ -661,15 +661,19 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) ransac_small_kernel(RansacAr
     uint32_t st_blocks = 0, st_filtered = 0, st_trivial = 0, st_exact = 0, st_early = 0, st_viol = 0;  // tallies (STATS only)
     uint32_t st_fit = 0, st_dist = 0, st_fdist = 0;  // exact plane fits, exact and float32 point-distance evaluations
     const uint32_t n_items = A.sub ? (A.n_sub_dev ? __ldg(A.n_sub_dev) : A.n_sub) : A.n_work;
+    // items per grab: RS_GRAB when every warp has several grabs' worth of work; fewer when the list is short (what the lane
+    // passes leave of a small map), where a grab of 8 would leave most warps idle while a few walk 8 slow items in a row
+    const uint32_t per_warp = n_items / (gridDim.x * (uint32_t)RS_WARPS);
+    const uint32_t grab = per_warp >= 4u * RS_GRAB ? (uint32_t)RS_GRAB : (per_warp >= 8u ? 4u : (per_warp >= 4u ? 2u : 1u));
     for (;;) {
         // RS_GRAB work items per atomic; their descriptors are fetched by RS_GRAB lanes at once, so the dependent
         // counter -> work[] -> block table round trips are paid once per grab instead of once per block
         uint32_t w0 = 0;
-        if (lane == 0) w0 = atomicAdd(counter, (uint32_t)RS_GRAB);
+        if (lane == 0) w0 = atomicAdd(counter, grab);
         w0 = __shfl_sync(0xffffffffu, w0, 0);
         if (w0 >= n_items) break;
         __syncwarp();
-        if (lane < RS_GRAB && w0 + lane < n_items) {
+        if (lane < (int)grab && w0 + lane < n_items) {
             const uint32_t wi = A.sub ? A.sub[w0 + lane] : w0 + lane;
             const uint32_t db = A.work[wi];
             const uint32_t dps = A.blk_start[db];
@@ -680,7 +684,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) ransac_small_kernel(RansacAr
             W.d_pk[lane] = A.pk_start ? A.pk_start[wi] : dps;
         }
         __syncwarp();
-        const int items = (int)min((uint32_t)RS_GRAB, n_items - w0);
+        const int items = (int)min(grab, n_items - w0);
       for (int it = 0; it < items; ++it) {
         const int n = W.d_n[it];
         if (n > RS_MAX_POINTS) continue;  // handled by the CTA-per-block kernel

@@ -69,7 +69,7 @@ def _ptr(a):
 def _i32_array(values: Optional[Sequence[int]]):
     if values is None:
         return None, 0
-    arr = np.ascontiguousarray(list(values), dtype=np.int32)
+    arr = np.ascontiguousarray(values if isinstance(values, np.ndarray) else list(values), dtype=np.int32)
     return arr, len(arr)
 
 
@@ -182,6 +182,23 @@ class Forest:
         self._pending_sources.append(keep)
         self._n_poses_native = max(self._n_poses_native, int(n_poses_total))
         self.version += 1
+
+    def adopt_exchange(self, exchange, handle, ptrs, sizes, poses, count, slabs, buffer, info, bounds, pose_sizes):
+        """Collective multi-GPU exchange into this (empty) forest: parallel.py `_FusedExchange.run`.  The forest keeps the
+        exchange object (and with it the receive buffer it adopted) alive."""
+        with self._scope():
+            N.check(self._lib.ol_exchange_run(handle, self._h, ptrs, sizes, poses, int(count), int(slabs), int(buffer),
+                                              _ptr(info), _ptr(bounds), _ptr(pose_sizes)))
+        self._adopted = exchange
+        self._n_poses_native = max(self._n_poses_native, int(exchange.n_poses))
+        self.version += 1
+
+    def disown_points(self):
+        """Copy an adopted receive buffer into memory of the forest's own (the exchange is about to reuse the buffer)."""
+        if getattr(self, "_h", None) is not None and self._h:
+            with self._scope():
+                N.check(self._lib.ol_forest_disown_points(self._h))
+        self._adopted = None
 
     def _as_source(self, points):
         torch = self._torch

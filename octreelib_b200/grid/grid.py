@@ -73,10 +73,10 @@ class Grid(GridBase):
             return
         # the reference batches pose NUMBERS range(0, P) (grid.py:149-157); any other numbering is a KeyError
         n_poses = len(host.pose_numbers)
-        for number in range(n_poses):
-            if number not in host.pose_index:
-                raise KeyError(number)
-        pose_rank = [int(p) for p in host.pose_numbers]
+        pose_rank = np.fromiter(host.pose_numbers, dtype=np.int64, count=n_poses)
+        if pose_rank.min() < 0 or pose_rank.max() >= n_poses:  # numbers are unique: inside [0, P) means exactly range(P)
+            raise KeyError(next(number for number in range(n_poses) if number not in host.pose_index))
+        pose_rank = pose_rank.astype(np.int32)
         host.forest.ransac(ransac.random_hypotheses, threshold, pose_rank, poses_per_batch, apply=True)
         host._counts_cache = None
 

@@ -78,10 +78,9 @@ def pose_starts(pose_sizes: np.ndarray, rank: int, poses_per_batch: int) -> np.n
     sizes = np.asarray(pose_sizes, dtype=np.int64)
     total = sizes.sum(axis=0)
     P = sizes.shape[1]
-    before = np.zeros(P, dtype=np.int64)
-    for first in range(0, P, poses_per_batch):
-        t = total[first:first + poses_per_batch]
-        before[first:first + poses_per_batch] = np.cumsum(t) - t
+    excl = np.cumsum(total) - total                                  # points of all earlier poses
+    batch_first = (np.arange(P) // poses_per_batch) * poses_per_batch
+    before = excl - excl[batch_first]                                # ... of the earlier poses of the same batch
     return before + sizes[:rank].sum(axis=0)
 
 
@@ -168,6 +167,105 @@ class _PeerBuffers:
         return pb
 
 
+class _FusedExchange:
+    """Everything `ol_exchange_run` (csrc/exchange.cu) needs of one (group, world, pose count): the peer-mapped control
+    blocks and receive buffers (torch.distributed._symmetric_memory; plain device tensors when world == 1) and the native
+    exchange object.  Two receive buffers alternate, so the forest of one step may still be alive while the next step's
+    exchange runs; a forest that outlives TWO exchanges is made to copy its points out first (`disown_points`)."""
+
+    NBUF = 2
+    _cache: Dict[Tuple[int, int, int], "_FusedExchange"] = {}
+    disabled_reason: Optional[str] = None
+
+    def __init__(self, world: int, rank: int, n_poses: int, rows_cap: int, device, group):
+        import torch
+
+        lib = N.lib()
+        self.world, self.rank, self.n_poses, self.rows_cap = world, rank, n_poses, int(rows_cap)
+        ctrl_words = int(lib.ol_exchange_ctrl_bytes(world, n_poses)) // 8 + 1
+        if world > 1:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+
+            g = group if group is not None else dist.group.WORLD
+            self.ctrl = symm.empty(ctrl_words, dtype=torch.int64, device=device)
+            self.ctrl.zero_()
+            hdl = symm.rendezvous(self.ctrl, g)
+            ctrl_ptrs = [int(p) for p in hdl.buffer_ptrs]
+            self.bufs, data_ptrs = [], []
+            for _ in range(self.NBUF):
+                t = symm.empty(max(self.rows_cap, 1) * 3, dtype=torch.float64, device=device)
+                h = symm.rendezvous(t, g)
+                self.bufs.append(t)
+                data_ptrs += [int(p) for p in h.buffer_ptrs]
+            torch.cuda.synchronize(device)
+            hdl.barrier()  # every rank's flags are zero before anybody raises one
+            torch.cuda.synchronize(device)
+            self._hdl = hdl
+        else:
+            self.ctrl = torch.zeros(ctrl_words, dtype=torch.int64, device=device)
+            self.bufs = [torch.empty(max(self.rows_cap, 1) * 3, dtype=torch.float64, device=device) for _ in range(self.NBUF)]
+            ctrl_ptrs = [self.ctrl.data_ptr()]
+            data_ptrs = [t.data_ptr() for t in self.bufs]
+            torch.cuda.synchronize(device)
+        self._h = C.c_void_p()
+        N.check(lib.ol_exchange_create(world, rank, n_poses, self.rows_cap, self.NBUF, (C.c_void_p * world)(*ctrl_ptrs),
+                                       (C.c_void_p * (self.NBUF * world))(*data_ptrs), device.index, C.byref(self._h)))
+        self._next = 0
+        self._holder = [None] * self.NBUF  # weak reference to the forest that adopted the buffer
+
+    def __del__(self):
+        try:
+            if self._h:
+                N.lib().ol_exchange_destroy(self._h)
+                self._h = None
+        except Exception:  # noqa: BLE001
+            pass
+
+    @classmethod
+    def get(cls, world: int, rank: int, n_poses: int, n_local: int, device, group, dist, min_rows: int = 0) -> "_FusedExchange":
+        """Collective.  Sized on first use from the total point count (one all-reduce): 1.25 x the mean share."""
+        key = (id(group), world, n_poses)
+        xc = cls._cache.get(key)
+        if xc is not None and xc.rows_cap >= min_rows:
+            return xc
+        import torch
+
+        total = n_local
+        if world > 1:
+            t = torch.tensor([n_local], dtype=torch.int64, device=device)
+            dist.all_reduce(t, group=group)
+            total = int(t.item())
+        rows = max(int(1.25 * -(-total // world)) + 65536, int(1.25 * min_rows))
+        cls._cache.pop(key, None)
+        xc = cls(world, rank, n_poses, rows, device, group)
+        cls._cache[key] = xc
+        return xc
+
+    def run(self, forest, tensors, numbers, slabs: bool):
+        """Routes `tensors` (device float64 (n, 3), pose numbers ascending) and lets `forest` adopt what arrives.
+        Returns (info[4], slab bounds, pose sizes [world][n_poses])."""
+        import weakref
+
+        lib = N.lib()
+        b = self._next
+        self._next = (b + 1) % self.NBUF
+        prev = self._holder[b]() if self._holder[b] is not None else None
+        if prev is not None and prev is not forest:
+            prev.disown_points()  # still alive after two exchanges: it gets its own copy, the buffer is reused
+        count = len(tensors)
+        ptrs = (C.c_void_p * max(count, 1))(*[t.data_ptr() for t in tensors])
+        sizes = (C.c_int64 * max(count, 1))(*[t.shape[0] for t in tensors])
+        poses = (C.c_int32 * max(count, 1))(*numbers)
+        info = np.zeros(4, dtype=np.int64)
+        bounds = np.zeros(max(self.world - 1, 1), dtype=np.int64)
+        psz = np.zeros((self.world, self.n_poses), dtype=np.uint32)
+        self.last_info = info
+        forest.adopt_exchange(self, self._h, ptrs, sizes, poses, count, 1 if slabs else 0, b, info, bounds, psz)
+        self._holder[b] = weakref.ref(forest)
+        return info, bounds[: self.world - 1], psz
+
+
 class ShardedGrid:
     """The `Grid` operations of the hot path on a cell-sharded grid.  Pose numbers must be 0..P-1."""
 
@@ -194,6 +292,8 @@ class ShardedGrid:
         self._staged: List[Tuple[int, object]] = []
         self.exchanged = False
         self.last_exchange = None
+        self._pose_sizes: Optional[np.ndarray] = None  # [rank][pose] rows held after the exchange (fused path)
+        self._removed = False                          # a filter / mask has removed points since
 
     # ---- staging + routing ----------------------------------------------------------------------
     def insert_points(self, pose_number: int, points):
@@ -224,6 +324,14 @@ class ShardedGrid:
         lib = N.lib()
         dev = self._host.forest.device
         stream = torch.cuda.current_stream(dev)
+        mode = os.environ.get("OL_EXCHANGE", "fused")
+        if (mode == "fused" and _FusedExchange.disabled_reason is None and not self.exchanged
+                and (self.world == 1 or self._dist.get_backend(self._group) == "nccl")):
+            if self._exchange_fused(dev, mark):
+                if timing and self.rank == 0:
+                    print("[exchange fused] " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f} ms" for a, b in zip(marks, marks[1:])),
+                          flush=True)
+                return
         parts = []
         for _, pts in self._staged:
             t = pts if isinstance(pts, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pts, dtype=np.float64))
@@ -249,7 +357,7 @@ class ShardedGrid:
             bounds = np.ascontiguousarray(self.slab_bounds, dtype=np.int64)
             mark("slabs")
         bounds_p = None if bounds is None else bounds.ctypes.data_as(C.c_void_p)
-        use_p2p = self.world > 1 and os.environ.get("OL_EXCHANGE", "p2p") == "p2p" and self._dist.get_backend(self._group) == "nccl"
+        use_p2p = self.world > 1 and mode in ("fused", "p2p") and self._dist.get_backend(self._group) == "nccl"
         perm = send = None
         recv = None
         send_counts = None
@@ -341,6 +449,46 @@ class ShardedGrid:
         if timing and self.rank == 0:
             print("[exchange] " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f} ms" for a, b in zip(marks, marks[1:])), flush=True)
 
+    def _exchange_fused(self, dev, mark) -> bool:
+        """The production path (csrc/exchange.cu): one native call, no library collective, one host wait.  Returns False
+        when peer-mapped memory is not available (the caller falls back to the staged paths below)."""
+        torch = require_cuda()
+        staged = sorted(self._staged, key=lambda s: s[0])  # stable: poses ascending, insertion order inside a pose
+        tensors = []
+        for _, pts in staged:
+            t = pts if isinstance(pts, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pts, dtype=np.float64))
+            if t.device != dev or t.dtype != torch.float64 or not t.is_contiguous():
+                t = t.to(dev, dtype=torch.float64, non_blocking=True).contiguous()
+            tensors.append(t.reshape(-1, 3) if t.dim() != 2 else t)
+        numbers = [p for p, _ in staged]
+        n_local = sum(int(t.shape[0]) for t in tensors)
+        mark("stage")
+        forest = self._host.forest
+        slabs = self.partition == "slab"
+        min_rows = 0
+        for _attempt in range(3):
+            try:
+                xc = _FusedExchange.get(self.world, self.rank, self.n_poses_total, n_local, dev, self._group, self._dist, min_rows)
+            except Exception as exc:  # noqa: BLE001 - no symmetric memory on this system: the staged exchange still works
+                _FusedExchange.disabled_reason = f"{type(exc).__name__}: {exc}"
+                return False
+            try:
+                info, bounds, psz = xc.run(forest, tensors, numbers, slabs)
+                break
+            except N.ExchangeCapacityError:
+                min_rows = int(xc.last_info[3])  # the same on every rank: everybody grows alike
+        else:
+            raise RuntimeError("exchange buffers could not be sized")
+        mark("exchange")
+        if slabs and self.world > 1:
+            self.slab_bounds = bounds.copy()
+        self._pose_sizes = psz.astype(np.int64)
+        self.last_exchange = dict(sent=int(info[0]), received=int(info[1]), kept=int(info[2]), mode="fused-p2p" if self.world > 1 else "local",
+                                  partition=self.partition, disabled_reason=None, bytes=int(info[0]) * 24)
+        self._staged = []
+        self.exchanged = True
+        return True
+
     # ---- local pipeline -------------------------------------------------------------------------
     def subdivide(self, subdivision_criteria, pose_numbers: Optional[Sequence[int]] = None):
         self._require_exchanged()
@@ -349,6 +497,7 @@ class ShardedGrid:
     def filter(self, filtering_criteria):
         self._require_exchanged()
         self._host.filter(filtering_criteria)
+        self._removed = True
 
     def map_leaf_points_cuda_ransac(self, poses_per_batch: int = 10, threshold: float = 0.01, hypotheses_number: int = 1024,
                                     initial_points_number: int = 6):
@@ -365,7 +514,10 @@ class ShardedGrid:
         ransac = CudaRansac(threshold=threshold, hypotheses_number=hypotheses_number, initial_points_number=initial_points_number)
         forest = self._host.forest
         start = None
-        if self.world > 1 and self.partition == "slab":
+        if self.world > 1 and self.partition == "slab" and self._pose_sizes is not None and not self._removed:
+            # the fused exchange already told every rank how many rows of every pose every rank holds
+            start = pose_starts(self._pose_sizes, self.rank, poses_per_batch)
+        elif self.world > 1 and self.partition == "slab":
             # the reference's batch-global start index of every block (cuda_ransac.py:65-67) across the ranks: one
             # all-gather of the per-rank pose sizes (P integers per rank)
             import torch
@@ -374,8 +526,9 @@ class ShardedGrid:
             sizes = torch.empty((self.world, self.n_poses_total), dtype=torch.int64, device=forest.device)
             self._dist.all_gather_into_tensor(sizes, mine, group=self._group)
             start = pose_starts(sizes.cpu().numpy(), self.rank, poses_per_batch)
-        forest.ransac(ransac.random_hypotheses, threshold, list(range(self.n_poses_total)), poses_per_batch, apply=True,
+        forest.ransac(ransac.random_hypotheses, threshold, np.arange(self.n_poses_total, dtype=np.int32), poses_per_batch, apply=True,
                       pose_start=start)
+        self._removed = True
         self._host._counts_cache = None
 
     def _require_exchanged(self):

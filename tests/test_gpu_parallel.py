@@ -259,3 +259,68 @@ def test_fused_route_to_peers_matches_partition():
         lo, hi = int(base[o]) * 3, int(base[o] + per_owner[o]) * 3
         assert (got[:lo] == -1.0).all() and (got[hi:] == -1.0).all(), "wrote outside the assigned rows"
         assert (got[lo:hi].reshape(-1, 3) == want_send[owner_first[o]:owner_first[o + 1]]).all()
+
+
+def test_fused_exchange_world1_equals_plain_grid(monkeypatch):
+    """The fused exchange (csrc/exchange.cu: count pass, scatter pass, adopted receive buffer, cell range without a bounding
+    box pass) with a single rank must reproduce a plain Grid: same blocks, same points in the same order, same planes.
+    Clouds are staged out of pose order and one pose arrives in two pieces."""
+    import torch
+
+    from octreelib_b200.parallel import ShardedGrid
+
+    monkeypatch.setenv("OL_EXCHANGE", "fused")
+    P = 5
+    clouds = {p: lidar64_scan(p, seed=3)[::4] for p in range(P)}
+    dev = torch.device("cuda", 0)
+    for partition in ("slab", "hash"):
+        for repeat in range(3):  # the receive buffers alternate; the third grid reuses the first one's
+            g = ShardedGrid(GridConfig(voxel_edge_length=1.0), P, partition=partition)
+            for p in (3, 0, 4, 1):
+                g.insert_points(p, torch.from_numpy(clouds[p]).to(dev) if p % 2 else clouds[p])
+            half = len(clouds[2]) // 2
+            g.insert_points(2, clouds[2][:half])
+            g.insert_points(2, clouds[2][half:])
+            g.exchange()
+            assert g.last_exchange["mode"] == "local" and g.last_exchange["received"] == sum(len(c) for c in clouds.values())
+            g.subdivide([MaxPoints(50)])
+            ref = Grid(GridConfig(voxel_edge_length=1.0))
+            for p in range(P):
+                ref.insert_points(p, clouds[p])
+            ref.subdivide([MaxPoints(50)])
+            for f_a, f_b in ((g._host.forest, ref._host.forest),):
+                la, lb = f_a.export_leaves(), f_b.export_leaves()
+                assert (la["corner"] == lb["corner"]).all() and (la["edge"] == lb["edge"]).all()
+                ba, bb = f_a.export_blocks(list(range(P))), f_b.export_blocks(list(range(P)))
+                for k in ("pose", "leaf", "size"):
+                    assert (ba[k] == bb[k]).all()
+                pa = f_a.export_points(-1, order=0, pose_rank=list(range(P)))
+                pb = f_b.export_points(-1, order=0, pose_rank=list(range(P)))
+                assert (pa["xyz"] == pb["xyz"]).all() and (pa["idx"] == pb["idx"]).all()
+            np.random.seed(11)
+            g.map_leaf_points_cuda_ransac(poses_per_batch=2, threshold=0.02, hypotheses_number=128)
+            np.random.seed(11)
+            ref.map_leaf_points_cuda_ransac(poses_per_batch=2, threshold=0.02, hypotheses_number=128)
+            ra, rb = g._host.forest.export_ransac(scored_only=True), ref._host.forest.export_ransac(scored_only=True)
+            for k in ("pose", "leaf", "size", "best", "best_count"):
+                assert (ra[k] == rb[k]).all()
+            assert (ra["plane"].view(np.uint32) == rb["plane"].view(np.uint32)).all()
+            assert [g.n_points(p) for p in range(P)] == [ref.n_points(p) for p in range(P)]
+            if repeat == 0:
+                keep = g  # stays alive across the next two exchanges: must be told to copy its points out
+    assert [keep.n_points(p) for p in range(P)] == [ref.n_points(p) for p in range(P)]
+    pk = keep._host.forest.export_points(-1, order=0, pose_rank=list(range(P)))
+    pr = ref._host.forest.export_points(-1, order=0, pose_rank=list(range(P)))
+    assert (pk["xyz"] == pr["xyz"]).all()
+
+
+def test_fused_exchange_rejects_nonfinite(monkeypatch):
+    from octreelib_b200.parallel import ShardedGrid
+
+    monkeypatch.setenv("OL_EXCHANGE", "fused")
+    g = ShardedGrid(GridConfig(voxel_edge_length=1.0), 1)
+    pts = np.random.default_rng(0).normal(0, 3, (1000, 3))
+    pts[17, 1] = np.nan
+    g.insert_points(0, pts)
+    with pytest.raises(ValueError, match="NaN or infinite"):
+        g.exchange()

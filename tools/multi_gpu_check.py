@@ -20,7 +20,7 @@ import torch.distributed as dist
 
 from octreelib_b200.criteria import MaxPoints
 from octreelib_b200.grid import Grid, GridConfig
-from octreelib_b200.parallel import ShardedGrid, _PeerBuffers
+from octreelib_b200.parallel import ShardedGrid, _FusedExchange, _PeerBuffers
 from octreelib_b200.synthetic import lidar64_scan
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -70,7 +70,8 @@ def sharded(mode, partition):
     return gathered, counts, tables
 
 
-results = {(mode, part): sharded(mode, part) for mode, part in (("p2p", "slab"), ("nccl", "slab"), ("p2p", "hash"))}
+results = {(mode, part): sharded(mode, part) for mode, part in (("fused", "slab"), ("fused", "hash"), ("p2p", "slab"), ("nccl", "slab"),
+                                                                  ("p2p", "hash"))}
 if rank == 0:
     def single(ppb):
         ref = Grid(GridConfig(voxel_edge_length=1.0))
@@ -105,8 +106,9 @@ if rank == 0:
                 assert (tables["planes"][k] == ref["table"][k]).all(), f"{mode}/{part}: gathered plane table column {k} differs"
             assert (tables["planes"]["plane"].view(np.uint32) == ref["table"]["plane"].view(np.uint32)).all()
         sent = sum(g["exch"]["sent"] for g in gathered)
+        assert all(g["exch"]["mode"] == ("fused-p2p" if mode == "fused" else mode) for g in gathered), [g["exch"]["mode"] for g in gathered]
         print(f"[multi_gpu_check] world {world} exchange {mode} partition {part}: OK - {len(ref['before'])} blocks, {len(ref['planes'])} "
               f"fitted planes, {sent} points crossed ranks, shares {[g['exch']['received'] for g in gathered]}; p2p disabled reason: "
-              f"{_PeerBuffers.disabled_reason}", flush=True)
+              f"{_PeerBuffers.disabled_reason} / {_FusedExchange.disabled_reason}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
