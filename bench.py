@@ -238,7 +238,8 @@ def run_step(clouds, numbers, n_poses_total, w, world, profile=False, read_table
     from octreelib_b200.grid import Grid, GridConfig
 
     np.random.seed(0)
-    if world > 1:
+    sharded = world > 1 or os.environ.get("OL_BENCH_SHARDED") == "1"  # debug: the multi-GPU host path on one GPU
+    if sharded:
         from octreelib_b200.parallel import ShardedGrid
 
         grid = ShardedGrid(GridConfig(voxel_edge_length=w["edge"]), n_poses_total)
@@ -250,7 +251,7 @@ def run_step(clouds, numbers, n_poses_total, w, world, profile=False, read_table
         forest.extra_ransac_flags = 8  # OL_RANSAC_STATS: tally the executed fits / distance evaluations (profiled step only)
     for number, cloud in zip(numbers, clouds):
         grid.insert_points(number, cloud)
-    if world > 1:
+    if sharded:
         if profile:
             import torch
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]

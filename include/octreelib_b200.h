@@ -172,6 +172,13 @@ int ol_forest_apply_pose_mask(ol_forest *f, const int32_t *pose_rank, int32_t po
 int ol_forest_profile(ol_forest *f, int32_t enable);
 int ol_forest_profile_read(ol_forest *f, char *buf, int64_t buf_len, int64_t *out_len);
 uint64_t ol_launch_count(void);
+/* Device blocks obtained through the allocator callbacks are kept in a process-wide cache when a forest (or a transient
+ * call context) releases them, keyed by (callbacks, user pointer, stream), and are handed to the next forest on the same
+ * stream - a pipeline step builds a fresh forest and would otherwise re-enter the host allocator ~30 times.  The cache
+ * is bounded (environment OL_CACHE_BYTES, default a quarter of the device memory) and emptied on allocation failure.
+ * ol_release_cached_memory returns every cached block through the free callback it came from (bytes released): call it
+ * before tearing an allocator down.  The reference has no counterpart (numpy / numba manage their own memory). */
+uint64_t ol_release_cached_memory(void);
 
 /* ---- counters: Grid.n_leaves / n_points / n_nodes, grid/grid.py:343-362 ---------------------- */
 int ol_forest_stats_get(ol_forest *f, ol_forest_stats *out);

@@ -13,7 +13,7 @@ import importlib
 import sys
 
 __version__ = "0.1.0"
-__all__ = ["install_as", "grid", "octree", "octree_manager", "internal", "ransac", "criteria"]
+__all__ = ["install_as", "release_cached_memory", "grid", "octree", "octree_manager", "internal", "ransac", "criteria"]
 
 _SUBMODULES = ["internal", "internal.interfaces", "internal.point", "internal.typing", "internal.voxel", "octree",
                "octree.octree_base", "octree.octree", "octree_manager", "octree_manager.octree_manager", "ransac",
@@ -28,6 +28,13 @@ def install_as(name: str = "octreelib"):
     for sub in _SUBMODULES:
         sys.modules[f"{name}.{sub}"] = importlib.import_module(f"{__name__}.{sub}")
     return pkg
+
+
+def release_cached_memory() -> int:
+    """Return the device memory the native library keeps cached between grids to torch's allocator (bytes released)."""
+    from .forest import release_cached_memory as _release
+
+    return _release()
 
 
 def __getattr__(attr):

@@ -75,6 +75,13 @@ class ForestHost:
             return
         idx = self._indices(pose_numbers)
         criteria = list(criteria)
+        if criteria and all(type(c).__call__ is CountCriterion.__call__ and c.op == ">" and not c.size_guarded for c in criteria):
+            # any(len(points) > n_i) == len(points) > min(n_i): nothing to probe (the common case, and the host time of
+            # a subdivide call is time the GPU waits)
+            self.forest.subdivide(max(min(c.n for c in criteria), -1), idx)
+            self._n_subdivides += 1
+            self._counts_cache = None
+            return
         guarded = any(isinstance(c, CountCriterion) and c.size_guarded for c in criteria)
         # [(first level, table, beyond, criteria active from that level on)]; one entry unless node-size guards are used
         levels = fold_levels(criteria, float(self._edge), 1024) if guarded else None

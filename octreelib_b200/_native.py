@@ -77,6 +77,7 @@ SIGNATURES = {
     "ol_forest_profile": (C.c_int, [_p, _i32]),
     "ol_forest_profile_read": (C.c_int, [_p, C.c_char_p, _i64, C.POINTER(_i64)]),
     "ol_launch_count": (_u64, []),
+    "ol_release_cached_memory": (_u64, []),
     "ol_forest_stats_get": (C.c_int, [_p, C.POINTER(ForestStats)]),
     "ol_forest_stats_light": (C.c_int, [_p, C.POINTER(ForestStats)]),
     "ol_forest_pose_counts": (C.c_int, [_p, _p]),

@@ -1,4 +1,5 @@
 // extern "C" entry points of liboctreelib_b200 (declared in include/octreelib_b200.h).
+#include <atomic>
 #include <algorithm>
 #include <new>
 
@@ -21,6 +22,33 @@ namespace ol {
 unsigned long long g_launch_count = 0;
 int g_debug_sync = -1;
 bool g_force_legacy_sort = false;
+BlockCache g_block_cache;
+unsigned long long g_mail_ticket = 0;
+
+MailResult mail_wait(const Mail& m, cudaStream_t stream) {
+    MailResult r;
+    if (!m.slot) return r;
+    unsigned long long spins = 0;
+    bool drained = false;
+    while (m.slot[0] != m.ticket) {
+        if (drained) throw Error{OL_ERR_INTERNAL, "a kernel finished without posting its result to the host mailbox"};
+        if ((++spins & 0x3fffu) == 0) {  // every ~16 k polls: is the producer still alive?
+            const cudaError_t q = cudaStreamQuery(stream);
+            if (q == cudaSuccess)
+                drained = true;  // everything has run: the slot must hold the ticket on the next look
+            else if (q != cudaErrorNotReady)
+                throw Error{OL_ERR_CUDA, std::string("waiting for a kernel result: ") + cudaGetErrorString(q)};
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    r.total = m.slot[1];
+    r.err = (uint32_t)m.slot[2];
+    r.aux = (uint32_t)m.slot[3];
+    return r;
+}
 int g_os_variant = 0;
 static thread_local std::string g_last_error;
 void set_last_error(int code, const std::string& msg) { g_last_error = "[ol_status " + std::to_string(code) + "] " + msg; }
@@ -49,6 +77,13 @@ void set_last_error(int code, const std::string& msg) { g_last_error = "[ol_stat
         return OL_ERR_INVALID;                                                           \
     }
 
+// every forest entry point: counts whose kernels were enqueued by an earlier call are read first (forest.cuh: resolve_pending),
+// and large temporaries are parked for the duration of the call
+struct ForestScope {
+    ol::PoolScope pool;
+    explicit ForestScope(ol::Forest& f) : pool(f.ctx) { f.resolve_pending(); }
+};
+
 extern "C" {
 
 int ol_abi_version(void) { return OL_ABI_VERSION; }
@@ -71,7 +106,7 @@ int ol_forest_destroy(ol_forest* f) {
 int ol_forest_insert(ol_forest* f, const double* xyz, int64_t n, int32_t src_on_device, int32_t* out_pose_index) {
     OL_NEED(f);
     OL_API_BEGIN
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     int p = f->impl.insert(xyz, n, src_on_device != 0, nullptr, nullptr, nullptr, 0, 0);
     if (out_pose_index) *out_pose_index = p;
     OL_API_END
@@ -82,7 +117,7 @@ int ol_forest_insert_batch(ol_forest* f, const double* const* xyz_dev_ptrs_host,
     OL_NEED(f);
     OL_API_BEGIN
     OL_REQUIRE(count == 0 || (xyz_dev_ptrs_host && sizes_host), OL_ERR_INVALID, "NULL batch tables");
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     int p = f->impl.insert_batch(xyz_dev_ptrs_host, sizes_host, count);
     if (out_first_pose_index) *out_first_pose_index = p;
     OL_API_END
@@ -95,7 +130,7 @@ int ol_forest_insert_segments(ol_forest* f, const double* xyz, int64_t n, int32_
     OL_NEED(seg_pose);
     OL_API_BEGIN
     OL_REQUIRE(n_segments > 0, OL_ERR_INVALID, "n_segments must be positive");
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     f->impl.insert(xyz, n, src_on_device != 0, seg_sizes, seg_pose, seg_first, n_segments, n_poses_total);
     OL_API_END
 }
@@ -125,7 +160,7 @@ int ol_exchange_run(ol_exchange* x, ol_forest* f, const double* const* clouds_de
     OL_NEED(f);
     OL_API_BEGIN
     OL_REQUIRE(count == 0 || (clouds_dev_ptrs_host && sizes_host && poses_host), OL_ERR_INVALID, "NULL cloud tables");
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     x->impl.run(f->impl, clouds_dev_ptrs_host, sizes_host, poses_host, count, slabs, buffer, info_out, bounds_out, pose_sizes_out);
     OL_API_END
 }
@@ -141,7 +176,7 @@ int ol_forest_subdivide(ol_forest* f, int64_t max_points, const int32_t* pose_in
     OL_NEED(f);
     OL_API_BEGIN
     OL_REQUIRE(max_points >= 0, OL_ERR_INVALID, "max_points must be >= 0 (an empty node would split forever)");
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     ol::Forest::SplitRule rule;
     rule.first_level = {0};
     rule.max_points = {max_points};
@@ -154,7 +189,7 @@ int ol_forest_subdivide_table(ol_forest* f, const uint8_t* split_table_host, int
     OL_NEED(f);
     OL_NEED(split_table_host);
     OL_API_BEGIN
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     ol::Forest::SplitRule rule;
     rule.first_level = {0};
     rule.tables_host = split_table_host;
@@ -173,7 +208,7 @@ int ol_forest_subdivide_levels(ol_forest* f, const int32_t* first_level, int32_t
     OL_REQUIRE(n_entries >= 1 && n_entries <= 64, OL_ERR_INVALID, "split rule needs 1..64 level entries");
     OL_REQUIRE(split_tables_host ? split_beyond != nullptr : level_max_points != nullptr, OL_ERR_INVALID,
                "split rule needs thresholds or tables");
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     ol::Forest::SplitRule rule;
     for (int e = 0; e < n_entries; ++e) {
         rule.first_level.push_back(first_level[e]);
@@ -197,7 +232,7 @@ int ol_forest_filter(ol_forest* f, const uint8_t* keep_table_host, int64_t table
     OL_NEED(f);
     OL_NEED(keep_table_host);
     OL_API_BEGIN
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     f->impl.filter(keep_table_host, table_len, pose_indices, n_poses);
     OL_API_END
 }
@@ -207,7 +242,7 @@ int ol_forest_ransac(ol_forest* f, const double* table_host, int32_t H, int32_t 
     OL_NEED(f);
     OL_NEED(table_host);
     OL_API_BEGIN
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     f->impl.ransac(table_host, H, K, threshold, pose_rank, poses_per_batch, apply != 0, flags, pose_start);
     OL_API_END
 }
@@ -216,7 +251,7 @@ int ol_forest_pose_point_counts(ol_forest* f, int64_t* out_host) {
     OL_NEED(f);
     OL_NEED(out_host);
     OL_API_BEGIN
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     f->impl.pose_point_counts(out_host);
     OL_API_END
 }
@@ -224,7 +259,7 @@ int ol_forest_pose_point_counts(ol_forest* f, int64_t* out_host) {
 int ol_forest_apply_mask(ol_forest* f) {
     OL_NEED(f);
     OL_API_BEGIN
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     f->impl.apply_mask();
     OL_API_END
 }
@@ -232,7 +267,7 @@ int ol_forest_apply_mask(ol_forest* f) {
 int ol_forest_apply_pose_mask(ol_forest* f, const int32_t* pose_rank, int32_t pose_index, const uint8_t* mask_host, int64_t n) {
     OL_NEED(f);
     OL_API_BEGIN
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     f->impl.apply_pose_mask(pose_rank, pose_index, mask_host, n);
     OL_API_END
 }
@@ -260,12 +295,13 @@ int ol_forest_profile_read(ol_forest* f, char* buf, int64_t buf_len, int64_t* ou
 }
 
 uint64_t ol_launch_count(void) { return ol::g_launch_count; }
+uint64_t ol_release_cached_memory(void) { return (uint64_t)ol::g_block_cache.release_all(); }
 
 int ol_forest_stats_light(ol_forest* f, ol_forest_stats* out) {
     OL_NEED(f);
     OL_NEED(out);
     OL_API_BEGIN
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     f->impl.stats(out, true);
     OL_API_END
 }
@@ -274,7 +310,7 @@ int ol_forest_stats_get(ol_forest* f, ol_forest_stats* out) {
     OL_NEED(f);
     OL_NEED(out);
     OL_API_BEGIN
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     f->impl.stats(out);
     OL_API_END
 }
@@ -283,7 +319,7 @@ int ol_forest_pose_counts(ol_forest* f, int64_t* out_host) {
     OL_NEED(f);
     OL_NEED(out_host);
     OL_API_BEGIN
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     f->impl.pose_counts(out_host);
     OL_API_END
 }
@@ -291,7 +327,7 @@ int ol_forest_pose_counts(ol_forest* f, int64_t* out_host) {
 int ol_forest_export_cells(ol_forest* f, int64_t* q, double* corner, int32_t* first_pose, int64_t* n_nodes, int64_t* leaf_begin) {
     OL_NEED(f);
     OL_API_BEGIN
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     f->impl.export_cells(q, corner, first_pose, n_nodes, leaf_begin);
     OL_API_END
 }
@@ -299,7 +335,7 @@ int ol_forest_export_cells(ol_forest* f, int64_t* q, double* corner, int32_t* fi
 int ol_forest_export_cell_poses(ol_forest* f, int32_t* cell, int32_t* pose) {
     OL_NEED(f);
     OL_API_BEGIN
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     f->impl.export_cell_poses(cell, pose);
     OL_API_END
 }
@@ -307,7 +343,7 @@ int ol_forest_export_cell_poses(ol_forest* f, int32_t* cell, int32_t* pose) {
 int ol_forest_export_leaves(ol_forest* f, double* corner, double* edge, int32_t* cell, int32_t* depth, int32_t* parent_epoch) {
     OL_NEED(f);
     OL_API_BEGIN
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     f->impl.export_leaves(corner, edge, cell, depth, parent_epoch);
     OL_API_END
 }
@@ -315,7 +351,7 @@ int ol_forest_export_leaves(ol_forest* f, double* corner, double* edge, int32_t*
 int ol_forest_export_blocks(ol_forest* f, const int32_t* pose_rank, int32_t* pose, int32_t* leaf, int32_t* size) {
     OL_NEED(f);
     OL_API_BEGIN
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     f->impl.export_blocks(pose_rank, pose, leaf, size);
     OL_API_END
 }
@@ -325,7 +361,7 @@ int ol_forest_export_ransac(ol_forest* f, int32_t scored_only, int32_t* pose, in
     OL_NEED(f);
     OL_API_BEGIN
     const bool count_only = !pose && !leaf && !size && !plane && !best && !best_count;
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     int64_t n = f->impl.export_ransac(scored_only != 0, count_only, pose, leaf, size, plane, best, best_count);
     if (out_n) *out_n = n;
     OL_API_END
@@ -335,7 +371,7 @@ int ol_forest_export_points(ol_forest* f, const int32_t* pose_rank, int32_t pose
                             int32_t* cell, uint8_t* mask, int64_t* out_n) {
     OL_NEED(f);
     OL_API_BEGIN
-    ol::PoolScope pool_scope(f->impl.ctx);
+    ForestScope scope(f->impl);
     int64_t n = f->impl.export_points(pose_rank, pose_index, order, xyz, idx, cell, mask);
     if (out_n) *out_n = n;
     OL_API_END

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <iterator>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -108,6 +109,102 @@ struct Profiler {
         for (auto e : pool) cudaEventDestroy(e);
     }
 };
+
+// ---------------------------------------------------------------------------------------------
+// Process-wide cache of the blocks obtained from a host allocator callback.  A pipeline step builds a fresh forest (the
+// reference builds a fresh Grid), and without the cache every step went back into the host language for each arena
+// chunk and each large buffer (Python: 5-10 us per torch.empty, ~30 calls per step, all of it time the GPU may have to
+// wait for).  Blocks are keyed by (callbacks, user pointer, stream): work on ONE stream is ordered, so a block freed by
+// one context may be handed to the next context on the same stream at once - the same rule torch's caching allocator
+// applies.  A block leaves the cache through the callback it came from (ol_release_cached_memory, the byte cap, or an
+// allocation failure); the host binding keeps its callbacks alive for the life of the process (forest.py).
+// ---------------------------------------------------------------------------------------------
+struct BlockCache {
+    struct Key {
+        ol_alloc_fn a;
+        ol_free_fn f;
+        void* user;
+        cudaStream_t stream;
+        bool operator<(const Key& o) const {
+            if (a != o.a) return (uintptr_t)a < (uintptr_t)o.a;
+            if (f != o.f) return (uintptr_t)f < (uintptr_t)o.f;
+            if (user != o.user) return user < o.user;
+            return stream < o.stream;
+        }
+    };
+    std::mutex mu;
+    std::map<Key, std::multimap<size_t, void*>> free_blocks;
+    std::map<void*, size_t> sizes;  // every block that went through the cache: its true size
+    size_t cached_bytes = 0;
+    size_t cap_bytes = (size_t)-1;  // set on first use (OL_CACHE_BYTES, default 1/4 of the device memory)
+
+    void init_cap() {
+        if (cap_bytes != (size_t)-1) return;
+        const char* e = getenv("OL_CACHE_BYTES");
+        if (e && *e) {
+            cap_bytes = (size_t)strtoull(e, nullptr, 10);
+            return;
+        }
+        size_t fr = 0, tot = 0;
+        cap_bytes = (cudaMemGetInfo(&fr, &tot) == cudaSuccess) ? tot / 4 : ((size_t)8 << 30);
+    }
+    // a cached block of at least `bytes` and at most bytes + bytes / 8 (the steps of a pipeline ask for the same sizes again)
+    void* take(const Key& k, size_t bytes) {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = free_blocks.find(k);
+        if (it == free_blocks.end()) return nullptr;
+        auto b = it->second.lower_bound(bytes);
+        if (b == it->second.end() || b->first > bytes + bytes / 8) return nullptr;
+        void* p = b->second;
+        cached_bytes -= b->first;
+        it->second.erase(b);
+        return p;
+    }
+    void note(void* p, size_t bytes) {
+        std::lock_guard<std::mutex> lock(mu);
+        sizes[p] = bytes;
+    }
+    // returns false if the block must be freed by the caller (unknown block, or the cache is full)
+    bool put(const Key& k, void* p) {
+        std::lock_guard<std::mutex> lock(mu);
+        init_cap();
+        auto s = sizes.find(p);
+        if (s == sizes.end()) return false;
+        if (cached_bytes + s->second > cap_bytes) {
+            sizes.erase(s);
+            return false;
+        }
+        free_blocks[k].emplace(s->second, p);
+        cached_bytes += s->second;
+        return true;
+    }
+    void forget(void* p) {
+        std::lock_guard<std::mutex> lock(mu);
+        sizes.erase(p);
+    }
+    // hands every cached block back to where it came from; returns the bytes released
+    size_t release_all() {
+        std::map<Key, std::multimap<size_t, void*>> drop;
+        size_t bytes;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            drop.swap(free_blocks);
+            bytes = cached_bytes;
+            cached_bytes = 0;
+            for (auto& kv : drop)
+                for (auto& b : kv.second) sizes.erase(b.second);
+        }
+        for (auto& kv : drop)
+            for (auto& b : kv.second) {
+                if (kv.first.f)
+                    kv.first.f(kv.first.user, b.second);
+                else
+                    cudaFree(b.second);
+            }
+        return bytes;
+    }
+};
+extern BlockCache g_block_cache;
 
 // ---------------------------------------------------------------------------------------------
 // execution context: stream + allocator callbacks (the host binding passes torch's caching
@@ -259,21 +356,31 @@ struct Ctx {
         pool_bytes = 0;
     }
     bool pool_enabled = false;
+    BlockCache::Key cache_key() const { return BlockCache::Key{alloc_fn, free_fn, alloc_user, stream}; }
     void* raw_alloc(size_t bytes) {
-        void* p = nullptr;
+        void* p = g_block_cache.take(cache_key(), bytes);
+        if (p) return p;
         if (alloc_fn) {
             p = alloc_fn(alloc_user, bytes);
             if (!p) {
-                trim_pool();  // give the parked buffers back and retry once
+                trim_pool();  // give the parked and the cached buffers back and retry once
+                g_block_cache.release_all();
                 p = alloc_fn(alloc_user, bytes);
             }
             if (!p) throw Error{OL_ERR_ALLOC, "host allocator callback returned NULL for " + std::to_string(bytes) + " bytes"};
         } else {
-            OL_CUDA(cudaMallocAsync(&p, bytes, stream));
+            cudaError_t e = cudaMallocAsync(&p, bytes, stream);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                g_block_cache.release_all();
+                OL_CUDA(cudaMallocAsync(&p, bytes, stream));
+            }
         }
+        g_block_cache.note(p, bytes);
         return p;
     }
     void raw_free(void* p) {
+        if (g_block_cache.put(cache_key(), p)) return;
         if (free_fn)
             free_fn(alloc_user, p);
         else
@@ -317,6 +424,39 @@ struct ProfScope {
         }
     }
 };
+
+// ---------------------------------------------------------------------------------------------
+// Mail: a scalar result posted by a kernel straight into page-locked host memory (zero copy), so that the host learns a
+// count the moment the producing kernel knows it - without a device-to-host copy, a stream synchronisation (each one left
+// the GPU idle for 20-30 us: copy engine, host wake-up, next launch) or an event.  The kernels enqueued BEHIND the
+// producer keep running while the host reads the slot, which is what makes speculative launches and lazily consumed
+// counts possible (forest_host.inl: split_levels, build, ensure_blocks).
+//   slot[0] = ticket (process-wide unique, written last after a system fence), slot[1] = the count,
+//   slot[2] = the device error word, slot[3] = one auxiliary 32-bit device value.
+// ---------------------------------------------------------------------------------------------
+struct Mail {
+    volatile unsigned long long* slot = nullptr;
+    unsigned long long ticket = 0;
+    const uint32_t* err = nullptr;  // device pointers whose current values ride along (may be NULL)
+    const uint32_t* aux = nullptr;
+};
+struct MailResult {
+    unsigned long long total = 0;
+    uint32_t err = 0, aux = 0;
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ void mail_post(const Mail& m, unsigned long long total) {
+    if (!m.slot) return;
+    m.slot[1] = total;
+    m.slot[2] = m.err ? (unsigned long long)*reinterpret_cast<const volatile uint32_t*>(m.err) : 0ull;
+    m.slot[3] = m.aux ? (unsigned long long)*reinterpret_cast<const volatile uint32_t*>(m.aux) : 0ull;
+    __threadfence_system();
+    m.slot[0] = m.ticket;
+}
+#endif
+extern unsigned long long g_mail_ticket;  // last ticket handed out (process-wide; 0 is never a ticket)
+// waits for the ticket; `stream` is only queried now and then to notice a dead producer
+MailResult mail_wait(const Mail& m, cudaStream_t stream);
 
 // RAII device buffer of T, bound to a Ctx.
 template <typename T>

@@ -672,6 +672,11 @@ void Exchange::run(Forest& f, const double* const* clouds, const int64_t* sizes,
     const long long qlo[3] = {hdr[2], hdr[3], hdr[4]}, qhi[3] = {hdr[5], hdr[6], hdr[7]};
     f.adopt_points(data[(size_t)buf * world + rank], (size_t)received, seg_sizes.data(), seg_pose.data(), seg_first.data(),
                    (int)seg_sizes.size(), n_poses, qlo, qhi);
+    // Keys, sort and cell table are enqueued right behind the scatter (the cell-coordinate range came with the plan, so
+    // nothing has to be read back first): the GPU keeps working while the host language returns from this call and
+    // prepares the next one; the number of cells is picked up from the mailbox by that next call.
+    static const bool no_eager = getenv("OL_NO_PREFETCH") != nullptr;
+    if (!no_eager) f.build_enqueue();
 }
 
 }  // namespace ol

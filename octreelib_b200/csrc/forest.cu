@@ -451,6 +451,19 @@ struct DecideIn {
         return want ? 1u : 0u;
     }
 };
+// input of the level's ONE scan: [ tile_hist (8 x tiles) | leaf_cnt[g][s], g < 8, s < n_split ] with leaf_cnt stored at
+// stride `stride` >= n_split (speculative histogram pass: the stride is a bound fixed before n_split was known)
+struct HistIn {
+    const uint32_t* tile_hist;
+    const uint32_t* leaf_cnt;
+    uint32_t n_tile8, n_split, stride;
+    __device__ uint32_t operator()(size_t i) const {
+        if (i < n_tile8) return tile_hist[i];
+        const uint32_t j = (uint32_t)(i - n_tile8);
+        const uint32_t g = j / n_split;
+        return leaf_cnt[(size_t)g * stride + (j - g * n_split)];
+    }
+};
 struct DecideOut {
     uint32_t* sinfo;
     __device__ void operator()(size_t k, uint32_t ex, uint32_t v) const { sinfo[k] = (ex << 1) | v; }
@@ -472,7 +485,12 @@ __global__ void __launch_bounds__(PART_THREADS) part_hist_kernel(const uint32_t*
                                                                   const uint32_t* __restrict__ sinfo, uint32_t n,
                                                                   uint32_t num_tiles, uint32_t n_split, int shift,
                                                                   uint32_t* __restrict__ tile_hist /*[8][tiles]*/,
-                                                                  uint32_t* __restrict__ leaf_cnt /*[8][n_split]*/) {
+                                                                  uint32_t* __restrict__ leaf_cnt /*[8][n_split]*/,
+                                                                  const unsigned long long* __restrict__ d_nsplit) {
+    // n_split = the STRIDE of leaf_cnt: the exact number of splitting leaves, or - when the pass was enqueued before the
+    // host knew that number (d_nsplit != nullptr: speculative, forest_host.inl) - an upper bound.  A level that splits
+    // nothing has nothing to count.
+    if (d_nsplit && *d_nsplit == 0ull) return;
     __shared__ uint32_t h[8];
     if (threadIdx.x < 8) h[threadIdx.x] = 0;
     __syncthreads();
@@ -731,6 +749,15 @@ __global__ void expand_leaves_kernel(uint32_t L, uint32_t A, uint32_t I_old, con
     if (k == L - 1) lstart_n[L_new] = A;
 }
 
+// bounding box (6 ordered-int words) + error word -> the host mailbox (8 words: ticket, box, error); common.cuh: Mail
+__global__ void post_bbox_kernel(const long long* __restrict__ bbox, const Mail m) {
+    if (threadIdx.x != 0) return;
+    for (int a = 0; a < 6; ++a) m.slot[1 + a] = (unsigned long long)bbox[a];
+    m.slot[7] = (unsigned long long)*reinterpret_cast<const volatile uint32_t*>(m.err);
+    __threadfence_system();
+    m.slot[0] = m.ticket;
+}
+
 // current shape := one leaf per cell (reset_shape)
 __global__ void init_leaves_kernel(uint32_t L, uint32_t* __restrict__ lcell, int32_t* __restrict__ lparent, uint64_t* __restrict__ lpath,
                                    uint8_t* __restrict__ ldepth, uint8_t* __restrict__ lchild) {
@@ -932,8 +959,10 @@ __global__ void leaf_order_geometry_kernel(uint32_t L, const uint32_t* __restric
 // (pose, leaf) blocks
 // =============================================================================================
 // largest block: grid-stride walk, one atomic per CTA (one per warp on a single address cost 0.85 ms for 41 M blocks)
-__global__ void __launch_bounds__(256) block_max_kernel(const uint32_t* __restrict__ blk_start, uint32_t nb, uint32_t* __restrict__ out_max) {
+__global__ void __launch_bounds__(256) block_max_kernel(const uint32_t* __restrict__ blk_start, const unsigned long long* __restrict__ d_nb,
+                                                        uint32_t* __restrict__ out_max) {
     __shared__ uint32_t s_w[8];
+    const uint32_t nb = (uint32_t)*d_nb;  // device-side count: the host has not read it yet
     uint32_t v = 0;
     for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
         const uint32_t sz = blk_start[b + 1] - blk_start[b];

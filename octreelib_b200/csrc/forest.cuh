@@ -44,6 +44,26 @@ struct Forest {
     DevBuf<long long> d_bbox;    // [6] ordered-int min xyz, max xyz
     DevBuf<uint32_t> d_err;      // [1]
     void* pinned = nullptr;      // small pinned scratch for read-backs (256 B)
+    // Results posted by kernels straight into page-locked memory (common.cuh: Mail): 8 slots of 4 words.  A count whose
+    // producer has been enqueued may stay unread until somebody needs it (`*_pending`): the eager parts of the pipeline
+    // (build after an exchange, leaf order + block table after a subdivide) return to the host language while the GPU
+    // still works, and every C-ABI entry point starts with resolve_pending().
+    void* mailbox = nullptr;
+    enum MailSlot { MAIL_CELLS = 0, MAIL_BLOCKS = 1, MAIL_LEVEL = 2, MAIL_WORK = 3, MAIL_COMPACT = 4, MAIL_MISC = 5 };
+    Mail mail_open(int slot, const uint32_t* aux = nullptr);
+    MailResult mail_take(const Mail& m) { return mail_wait(m, ctx.stream); }
+    bool cells_pending = false, blocks_pending = false;
+    Mail cells_mail{}, blocks_mail{};
+    DevBuf<unsigned long long> d_nb;  // [1] number of blocks (device copy, read by block_max_kernel)
+    void resolve_cells();
+    void resolve_blocks();
+    void resolve_pending() {
+        resolve_cells();
+        resolve_blocks();
+    }
+    void build_enqueue();          // K1-K3 enqueued, C not read yet
+    void ensure_blocks_enqueue();  // block table enqueued, NB not read yet
+    void prefetch_tables();        // leaf order + block table enqueued right after a subdivide (no wait)
 
     // ---- base structure: points grouped by cell, (pose, input index) order inside a cell --------
     bool built = false;

@@ -48,13 +48,43 @@ Forest::Forest(const ol_forest_config& c) : cfg(c) {
     long long init[6] = {LLONG_MAX, LLONG_MAX, LLONG_MAX, LLONG_MIN, LLONG_MIN, LLONG_MIN};
     OL_CUDA(cudaMemcpyAsync(d_bbox.get(), init, sizeof(init), cudaMemcpyHostToDevice, ctx.stream));
     pinned = pinned_scratch_get();
-    ctx.sync();
+    mailbox = pinned_scratch_get();
+    // no synchronisation: the initial values are pageable sources (staged when cudaMemcpyAsync returns)
     seg_start.push_back(0);
 }
 
 Forest::~Forest() {
-    cudaStreamSynchronize(ctx.stream);
+    cudaStreamSynchronize(ctx.stream);  // also: no kernel may post into the mailbox after it went back to the pool
     pinned_scratch_put(pinned);
+    pinned_scratch_put(mailbox);
+}
+
+Mail Forest::mail_open(int slot, const uint32_t* aux) {
+    Mail m;
+    m.slot = reinterpret_cast<volatile unsigned long long*>(mailbox) + 4 * (size_t)slot;
+    m.ticket = ++g_mail_ticket;
+    m.err = d_err.get();
+    m.aux = aux;
+    return m;
+}
+
+void Forest::resolve_cells() {
+    if (!cells_pending) return;
+    cells_pending = false;
+    const MailResult r = mail_take(cells_mail);
+    try {
+        throw_device_errors(r.err);  // keygen range checks
+    } catch (...) {
+        built = false;
+        throw;
+    }
+    C = (uint32_t)r.total;
+}
+
+void Forest::resolve_blocks() {
+    if (!blocks_pending) return;
+    blocks_pending = false;
+    NB = (uint32_t)mail_take(blocks_mail).total;
 }
 
 uint32_t Forest::read_u32(const uint32_t* dptr) {
@@ -312,7 +342,13 @@ int Forest::insert_batch(const double* const* xyz_dev, const int64_t* sizes, int
 // K1-K3: keys, sort, cells, (cell, pose) table
 // ---------------------------------------------------------------------------------------------
 void Forest::build() {
+    if (!built) build_enqueue();
+    resolve_cells();
+}
+
+void Forest::build_enqueue() {
     if (built) return;
+    cells_pending = false;
     if (bbox_done < N) {  // K0 over everything inserted since the last build
         const size_t m = N - bbox_done;
         unsigned g = std::min<unsigned>(nblk(m * 3, BBOX_THREADS), (unsigned)ctx.num_sms * 10);
@@ -356,10 +392,17 @@ void Forest::build() {
                 kp.qmin[a] = q_lo[a];
                 bits[a] = bit_length_u64((uint64_t)(q_hi[a] - q_lo[a]));
             }
-    } else {  // read-back 1 of the build: bounding box + error word
+    } else {  // the build's one wait for the device: bounding box + error word, posted into the mailbox (slots 6-7)
         long long hb[6];
         uint32_t e = 0;
-        read_back({{d_bbox.get(), sizeof(hb), hb}, {d_err.get(), 4, &e}});
+        {
+            Mail m = mail_open(6);
+            post_bbox_kernel<<<1, 32, 0, ctx.stream>>>(d_bbox.get(), m);
+            OL_CHECK_LAUNCH();
+            mail_take(m);
+            for (int a = 0; a < 6; ++a) hb[a] = (long long)m.slot[1 + a];
+            e = (uint32_t)m.slot[7];
+        }
         throw_device_errors(e);
         if (!cfg.single_cell && N > 0) {
             for (int a = 0; a < 3; ++a) {
@@ -437,9 +480,12 @@ void Forest::build() {
         keys1.release();
         vals1.release();
         // K3: cells = runs of equal cell key
+        // K3: the number of cells is POSTED to the host by the kernel (the host reads it when it needs it: resolve_cells),
+        // and the kernel closes the start table itself (cell_start0[C] = n)
         ProfScope ps(ctx, "cells", (double)n);
+        cells_mail = mail_open(MAIL_CELLS);
         segment_runs(ctx, CellKeyFn<KeyT>{keys0.get(), kp.pose_bits}, CellEmitFn{cell_key.get(), cell_start0.get()}, n, cellidx0.get(),
-                     d_total.get());
+                     d_total.get(), cell_start0.get(), cells_mail);
     };
     if (key_bits <= 32)
         run(uint32_t{});
@@ -457,14 +503,7 @@ void Forest::build() {
         OL_CHECK_LAUNCH();
     }
     mort_r.release();
-    {  // read-back 2 of the build: number of cells + error word (keygen range checks)
-        unsigned long long c64 = 0;
-        uint32_t e = 0;
-        read_back({{d_total.get(), 8, &c64}, {d_err.get(), 4, &e}});
-        throw_device_errors(e);
-        C = (uint32_t)c64;
-    }
-    OL_CUDA(cudaMemcpyAsync(cell_start0.get() + C, &n, 4, cudaMemcpyHostToDevice, ctx.stream));
+    cells_pending = true;  // C arrives through the mailbox
     cp_valid = false;  // the (cell, pose) table is built on first use (ensure_cell_poses)
     built = true;
     base_dirty = any_dead;  // points removed before a rebuild are dropped from the base order lazily
@@ -534,12 +573,12 @@ uint32_t Forest::compact_tables(const uint8_t* keep, const uint32_t* via, uint32
         keep_bits_kernel<<<tiles, CMP_THREADS, 0, ctx.stream>>>(keep, via, n, t.bits.get(), t.tile_off.get());
         OL_CHECK_LAUNCH();
     }
-    exclusive_scan_u32(ctx, t.tile_off.get(), t.tile_off.get(), tiles, d_total.get());
-    unsigned long long total = 0;
-    uint32_t e = 0;
-    read_back({{d_total.get(), 8, &total}, {d_err.get(), 4, &e}});  // the error word rides along (RANSAC flags of the launch before)
-    note_ransac_flags(e);
-    return (uint32_t)total;
+    const Mail mail = mail_open(MAIL_COMPACT);
+    transform_scan<uint32_t>(ctx, ScanPtrIn<uint32_t>{t.tile_off.get()}, ScanPtrOut<uint32_t>{t.tile_off.get()}, tiles, d_total.get(), "scan",
+                             mail);
+    const MailResult r = mail_take(mail);  // the error word rides along (RANSAC flags of the launch before)
+    note_ransac_flags(r.err);
+    return (uint32_t)r.total;
 }
 
 void Forest::compact_move(CompactTables& t, uint32_t n, const uint32_t* perm_in, const uint64_t* mort_in, const uint32_t* aux_in,
@@ -755,12 +794,14 @@ void Forest::subdivide(const SplitRule& rule, const int32_t* poses, int n_listed
     } else {
         epochs_valid = false;
     }
+    static const bool no_prefetch = getenv("OL_NO_PREFETCH") != nullptr;  // debug: build the derived tables on demand only
+    if (!no_prefetch) prefetch_tables();
 }
 
 // the internal-node arrays grow geometrically, so a level appends in place
 void Forest::reserve_internal(size_t need) {
     if (need <= icap && istart.get()) return;
-    const size_t ncap = std::max<size_t>(need, std::max<size_t>(icap * 2, 1024));
+    const size_t ncap = std::max<size_t>(need + need / 2, std::max<size_t>(icap * 4, 65536));  // few re-allocations: each is six copies
     DevBuf<uint32_t> s2(ctx, ncap), c2(ctx, ncap);
     DevBuf<uint8_t> d2(ctx, ncap), ch2(ctx, ncap);
     DevBuf<uint64_t> p2(ctx, ncap);
@@ -805,6 +846,23 @@ void Forest::split_levels(const SplitRule* rule, const uint8_t* d_tables, const 
     DevBuf<uint32_t> perm_b(ctx, A), leaf_b(ctx, A);
     DevBuf<uint64_t> mort_b(ctx, mort_len(A));
     level_ibegin.assign(1, 0u);
+    // Upper bound on the number of leaves one level can split: a leaf only splits when it holds more points than the
+    // smallest count the rule accepts.  It sizes the buffers of the SPECULATIVE histogram pass below.
+    auto split_bound = [&](int level) -> size_t {
+        size_t per_leaf = 1;  // smallest point count of a splitting leaf
+        if (!rule) return std::min<size_t>(L, n_replay);
+        const int e = rule->entry_for(level);
+        if (rule->tables_host) {
+            const uint8_t* t = rule->tables_host + (size_t)e * (size_t)rule->table_len;
+            int64_t c = 0;
+            while (c < rule->table_len && !t[c]) ++c;
+            per_leaf = (size_t)std::max<int64_t>(c, 0);
+        } else {
+            per_leaf = rule->max_points[e] >= (int64_t)A ? (size_t)A + 1 : (size_t)std::max<int64_t>(rule->max_points[e] + 1, 0);
+        }
+        return per_leaf == 0 ? (size_t)L : std::min<size_t>(L, (size_t)A / per_leaf);
+    };
+    constexpr size_t SPEC_MAX_LEAVES = (size_t)4 << 20;  // 128 MB of speculative counters at most
     for (int level = 0;; ++level) {
         // level 0 of a fresh shape partitions straight out of the base order (reset_shape made no copy)
         const uint32_t* src_leaf = order_virgin ? cellidx0.get() : leaf_of.get();
@@ -842,41 +900,61 @@ void Forest::split_levels(const SplitRule* rule, const uint8_t* d_tables, const 
                 din.max_points = rule->max_points[e];
             }
         }
-        transform_scan<uint32_t>(ctx, din, DecideOut{sinfo.get()}, L, d_tot.get(), "part_decide");
-        unsigned long long split64 = 0;
-        uint32_t err_word = 0;
-        read_back({{d_tot.get(), 8, &split64}, {d_err.get(), 4, &err_word}});  // the level's ONE read-back
-        throw_device_errors(err_word);  // depth cap of this level, out-of-node points met by the previous level's move
-        const uint32_t n_split = (uint32_t)split64;
+        // decide + scan; the number of splitting leaves (and the error word) is POSTED to the host by the kernel
+        const Mail mail = mail_open(MAIL_LEVEL);
+        transform_scan<uint32_t>(ctx, din, DecideOut{sinfo.get()}, L, d_tot.get(), "part_decide", mail);
+        // Speculation: the digit histograms of the level only need the decisions (device side), not their number, so the
+        // pass is enqueued BEHIND the decision kernel with counters sized by the bound - the host reads the mailbox while
+        // it runs and the GPU never waits for the host.  A level that splits nothing makes the pass return at once.
+        const size_t bound = std::max<size_t>(split_bound(level), 1);
+        const bool speculate = level < kp.depth && bound <= SPEC_MAX_LEAVES;
+        DevBuf<uint32_t> tile_hist(ctx, (size_t)8 * tiles), leaf_cnt;
+        auto launch_hist = [&](size_t stride, const unsigned long long* d_nsplit) {
+            const uint64_t* sm = order_virgin ? mort0.get() : mort.get();
+            const int shift = 3 * (kp.depth - 1 - level);
+            OL_CUDA(cudaMemsetAsync(leaf_cnt.get(), 0, (size_t)8 * stride * 4, ctx.stream));
+            ProfScope ps(ctx, "part_hist", (double)A);
+            if (mort32)
+                part_hist_kernel<uint32_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(src_leaf, reinterpret_cast<const uint32_t*>(sm), sinfo.get(),
+                                                                                   A, tiles, (uint32_t)stride, shift, tile_hist.get(),
+                                                                                   leaf_cnt.get(), d_nsplit);
+            else
+                part_hist_kernel<uint64_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(src_leaf, sm, sinfo.get(), A, tiles, (uint32_t)stride, shift,
+                                                                                   tile_hist.get(), leaf_cnt.get(), d_nsplit);
+            OL_CHECK_LAUNCH();
+        };
+        if (speculate) {
+            leaf_cnt.reset(ctx, (size_t)8 * bound);
+            launch_hist(bound, d_tot.get());
+        }
+        const MailResult res = mail_take(mail);  // the level's ONE host wait (no stream synchronisation)
+        throw_device_errors(res.err);  // depth cap of this level, out-of-node points met by the previous level's move
+        const uint32_t n_split = (uint32_t)res.total;
         if (n_split == 0) break;
         const uint32_t L_new = L + 7u * n_split;
         OL_REQUIRE((unsigned long long)I + n_split < (1ull << 29), OL_ERR_RANGE, "too many internal nodes");
+        OL_REQUIRE(!speculate || n_split <= bound, OL_ERR_INTERNAL, "split bound violated");
         depth_reached = level + 1;
-        if (level >= kp.depth) {
-            materialize_order();
-            src_leaf = leaf_of.get();
-            src_perm = perm.get();
-            extend_morton();
-            mort_b.reset(ctx, mort_len(A));  // the word size may have changed
+        size_t stride = bound;
+        if (!speculate) {
+            if (level >= kp.depth) {
+                materialize_order();
+                src_leaf = leaf_of.get();
+                src_perm = perm.get();
+                extend_morton();
+                mort_b.reset(ctx, mort_len(A));  // the word size may have changed
+            }
+            stride = n_split;
+            leaf_cnt.reset(ctx, (size_t)8 * stride);
+            launch_hist(stride, nullptr);
         }
         const uint64_t* src_mort = order_virgin ? mort0.get() : mort.get();
-        const int shift = 3 * (kp.depth - 1 - level);
-        // flat histogram buffer: [ tile_hist (8 x tiles) | leaf_cnt (8 x n_split) ], scanned in place by ONE scan
+        const int shift_now = 3 * (kp.depth - 1 - level);  // kp.depth may have grown (extend_morton)
+        // ONE scan over [ tile_hist (8 x tiles) | leaf_cnt (8 x n_split, gathered out of the strided counters) ]
         const size_t flat_len = (size_t)8 * tiles + (size_t)8 * n_split;
         DevBuf<uint32_t> hist(ctx, flat_len), delta(ctx, (size_t)n_split * 8);
-        OL_CUDA(cudaMemsetAsync(hist.get() + (size_t)8 * tiles, 0, (size_t)8 * n_split * 4, ctx.stream));
-        {
-            ProfScope ps(ctx, "part_hist", (double)A);
-            if (mort32)
-                part_hist_kernel<uint32_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(src_leaf, reinterpret_cast<const uint32_t*>(src_mort),
-                                                                                   sinfo.get(), A, tiles, n_split, shift, hist.get(),
-                                                                                   hist.get() + (size_t)8 * tiles);
-            else
-                part_hist_kernel<uint64_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(src_leaf, src_mort, sinfo.get(), A, tiles, n_split,
-                                                                                   shift, hist.get(), hist.get() + (size_t)8 * tiles);
-            OL_CHECK_LAUNCH();
-        }
-        exclusive_scan_u32(ctx, hist.get(), hist.get(), flat_len, d_tot.get() + 1);
+        transform_scan<uint32_t>(ctx, HistIn{tile_hist.get(), leaf_cnt.get(), 8u * tiles, n_split, (uint32_t)stride},
+                                 ScanPtrOut<uint32_t>{hist.get()}, flat_len, d_tot.get() + 1);
         // new leaf / internal tables + partition deltas
         reserve_internal((size_t)I + n_split);
         DevBuf<uint32_t> lstart_n(ctx, (size_t)L_new + 1), lcell_n(ctx, L_new);
@@ -898,11 +976,11 @@ void Forest::split_levels(const SplitRule* rule, const uint8_t* d_tables, const 
             if (mort32)
                 part_move_kernel<uint32_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(
                     src_leaf, reinterpret_cast<const uint32_t*>(src_mort), src_perm, sinfo.get(), hist.get(), delta.get(), A, tiles,
-                    shift, level, leaf_b.get(), reinterpret_cast<uint32_t*>(mort_b.get()), perm_b.get(), P64.get(), lcell.get(),
+                    shift_now, level, leaf_b.get(), reinterpret_cast<uint32_t*>(mort_b.get()), perm_b.get(), P64.get(), lcell.get(),
                     cell_key.get(), kp, d_err.get());
             else
                 part_move_kernel<uint64_t><<<tiles, PART_THREADS, 0, ctx.stream>>>(
-                    src_leaf, src_mort, src_perm, sinfo.get(), hist.get(), delta.get(), A, tiles, shift, level, leaf_b.get(),
+                    src_leaf, src_mort, src_perm, sinfo.get(), hist.get(), delta.get(), A, tiles, shift_now, level, leaf_b.get(),
                     mort_b.get(), perm_b.get(), P64.get(), lcell.get(), cell_key.get(), kp, d_err.get());
             OL_CHECK_LAUNCH();
         }
@@ -980,12 +1058,18 @@ void Forest::ensure_order() {
 // non-empty (pose, leaf) blocks = maximal runs of equal (leaf, pose) in the current point order
 // ---------------------------------------------------------------------------------------------
 void Forest::ensure_blocks() {
+    ensure_blocks_enqueue();
+    resolve_blocks();
+}
+
+void Forest::ensure_blocks_enqueue() {
     ensure_shape();
     if (blocks_valid) return;
     const int S = (int)seg_pose.size();
     NB = 0;
     max_block = 0;
     max_block_known = true;
+    blocks_pending = false;
     blk_of_pos.reset(ctx, A);
     if (A == 0) {
         blk_start.reset(ctx, 1);
@@ -995,30 +1079,41 @@ void Forest::ensure_blocks() {
         blocks_valid = true;
         return;
     }
-    // ONE pass (primitives.cuh: runs_fused_kernel); the tables are sized by the upper bound min(A, L x P)
+    // ONE pass (primitives.cuh: runs_fused_kernel); the tables are sized by the upper bound min(A, L x P).  The kernel
+    // posts the number of blocks to the host (read when somebody needs it: resolve_blocks) and closes the start table
+    // itself (blk_start[NB] = A).
     const size_t nb_max = std::min<size_t>(A, (size_t)L * (size_t)std::max(n_poses, 1));
-    DevBuf<unsigned long long> d_total(ctx, 1);
+    d_nb.reset(ctx, 1);
     blk_start.reset(ctx, nb_max + 1);
     blk_leaf.reset(ctx, nb_max);
     blk_pose.reset(ctx, nb_max);
     const GroupPoseKeyFn key{leaf_of.get(), perm.get(), d_seg_start.get(), d_seg_pose.get(), S};
     {
         ProfScope ps(ctx, "blocks", (double)A);
-        segment_runs(ctx, key, BlockEmitFn{blk_start.get(), blk_leaf.get(), blk_pose.get()}, A, blk_of_pos.get(), d_total.get());
+        blocks_mail = mail_open(MAIL_BLOCKS);
+        segment_runs(ctx, key, BlockEmitFn{blk_start.get(), blk_leaf.get(), blk_pose.get()}, A, blk_of_pos.get(), d_nb.get(),
+                     blk_start.get(), blocks_mail);
     }
-    NB = (uint32_t)read_u64(d_total.get());
-    OL_CUDA(cudaMemcpyAsync(blk_start.get() + NB, &A, 4, cudaMemcpyHostToDevice, ctx.stream));
+    blocks_pending = true;
     // the largest block is only read back when somebody needs it (ensure_max_block; RANSAC reads it together with its work size)
     d_max_block.reset(ctx, 1);
     d_max_block.zero();
     {
         ProfScope ps(ctx, "blocks");
-        block_max_kernel<<<std::min<unsigned>(nblk(NB), (unsigned)ctx.num_sms * 8), 256, 0, ctx.stream>>>(blk_start.get(), NB,
-                                                                                                          d_max_block.get());
+        block_max_kernel<<<(unsigned)ctx.num_sms * 8, 256, 0, ctx.stream>>>(blk_start.get(), d_nb.get(), d_max_block.get());
         OL_CHECK_LAUNCH();
     }
     max_block_known = false;
     blocks_valid = true;
+}
+
+// Enqueued at the end of a subdivide: nearly every next operation (RANSAC, filter, get_leaf_points, the counters) starts
+// from the leaf order and the block table, and the host language needs tens of microseconds between two calls - the GPU
+// builds the tables meanwhile instead of idling.  Nothing is waited for.
+void Forest::prefetch_tables() {
+    if (!shaped || A == 0 || L == 0) return;
+    ensure_order();
+    ensure_blocks_enqueue();
 }
 
 void Forest::ensure_max_block() {

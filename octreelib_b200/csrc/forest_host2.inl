@@ -428,13 +428,23 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
     // work list + packed layout of the fitted blocks' points: one scan, one read-back (with the largest block size)
     const size_t work_max = std::min<size_t>(NB, (size_t)A / (size_t)K);
     DevBuf<uint32_t> work(ctx, work_max + 1), pk_start(ctx, work_max + 1);
+    // (the number of fitted blocks, their point total and the largest block size are POSTED by the scan kernel; the
+    // result tables are initialised behind it, so the GPU has work while the host reads the mailbox)
+    const Mail mail = mail_open(MAIL_WORK, max_block_known ? nullptr : d_max_block.get());
     transform_scan<unsigned long long>(ctx, WorkIn{blk_start.get(), (uint32_t)K}, WorkOut{work.get(), pk_start.get()}, NB, d_total.get(),
-                                       "ransac_prep");
-    unsigned long long packed_total = 0;
-    if (max_block_known) {
-        read_back({{d_total.get(), 8, &packed_total}});
-    } else {
-        read_back({{d_total.get(), 8, &packed_total}, {d_max_block.get(), 4, &max_block}});
+                                       "ransac_prep", mail);
+    DevBuf<double> table(ctx, (size_t)H * K);
+    h2d(ctx, table.get(), table_host, (size_t)H * K);
+    DevBuf<float> plane(ctx, (size_t)NB * 4);
+    DevBuf<int32_t> best(ctx, NB), best_count(ctx, NB);
+    plane.zero();
+    best_count.zero();
+    fill_kernel<int32_t><<<nblk(NB), 256, 0, ctx.stream>>>(best.get(), NB, -1);
+    OL_CHECK_LAUNCH();
+    const MailResult posted = mail_take(mail);
+    const unsigned long long packed_total = posted.total;
+    if (!max_block_known) {
+        max_block = posted.aux;
         max_block_known = true;
     }
     const uint32_t n_work = (uint32_t)(packed_total >> 32);
@@ -446,14 +456,6 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
                                                                                 pk_start.get(), P64.get(), perm.get(), pleaf.get());
         OL_CHECK_LAUNCH();
     }
-    DevBuf<double> table(ctx, (size_t)H * K);
-    h2d(ctx, table.get(), table_host, (size_t)H * K);
-    DevBuf<float> plane(ctx, (size_t)NB * 4);
-    DevBuf<int32_t> best(ctx, NB), best_count(ctx, NB);
-    plane.zero();
-    best_count.zero();
-    fill_kernel<int32_t><<<nblk(NB), 256, 0, ctx.stream>>>(best.get(), NB, -1);
-    OL_CHECK_LAUNCH();
     {
         ProfScope ps(ctx, "ransac_kernel", (double)n_work);
         launch_ransac(ctx, pleaf.get(), (int64_t)n_packed, blk_start.get(), blk_size.get(), blk_ref_start.get(), work.get(), pk_start.get(),

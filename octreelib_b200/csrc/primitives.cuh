@@ -142,7 +142,7 @@ struct ScanPtrOut {
 template <typename T, int ITEMS, typename InFn, typename OutFn>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(InFn in, OutFn out, size_t n, uint32_t num_tiles,
                                                                       unsigned long long* __restrict__ status,
-                                                                      unsigned long long* __restrict__ total_out) {
+                                                                      unsigned long long* __restrict__ total_out, const Mail mail) {
     constexpr int TILE = SCAN_THREADS * ITEMS;
     __shared__ T tile[TILE + TILE / 32];
     __shared__ unsigned long long sw[32];
@@ -170,7 +170,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(InFn in, Ou
     unsigned long long tot;
     unsigned long long ex = block_exclusive_scan64(s, sw, &tot);
     const unsigned long long prefix = lookback_exclusive_prefix(status, t, tot, &s_prefix);
-    if (t == num_tiles - 1 && threadIdx.x == 0 && total_out) *total_out = prefix + tot;
+    if (t == num_tiles - 1 && threadIdx.x == 0) {
+        if (total_out) *total_out = prefix + tot;
+        mail_post(mail, prefix + tot);
+    }
     ex += prefix;
     // the tile buffer now carries the exclusive prefixes back to the coalesced arrangement; the values stay in a
     // second pass through it only when the output functor needs them (cheap: shared memory)
@@ -198,7 +201,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(InFn in, Ou
 
 // single CTA (1024 threads, 4 consecutive elements per thread and chunk): inputs of a few thousand elements
 template <typename T, typename InFn, typename OutFn>
-__global__ void __launch_bounds__(1024) scan_small_kernel(InFn in, OutFn out, size_t n, unsigned long long* __restrict__ total_out) {
+__global__ void __launch_bounds__(1024) scan_small_kernel(InFn in, OutFn out, size_t n, unsigned long long* __restrict__ total_out,
+                                                          const Mail mail) {
     __shared__ unsigned long long sw[32];
     unsigned long long carry = 0;
     for (size_t base = 0; base < n; base += 4096) {
@@ -219,20 +223,21 @@ __global__ void __launch_bounds__(1024) scan_small_kernel(InFn in, OutFn out, si
         }
         carry += tot;
     }
-    if (threadIdx.x == 0 && total_out) *total_out = carry;
+    if (threadIdx.x == 0) {
+        if (total_out) *total_out = carry;
+        mail_post(mail, carry);
+    }
 }
 
 // out(i, sum_{j<i} in(j), in(i)) for i in [0, n).  If d_total != nullptr the 64-bit grand total is written there
 // (device memory).  No host synchronisation.  `name` = profiler stage.
 template <typename T, typename InFn, typename OutFn>
-inline void transform_scan(Ctx& c, InFn in, OutFn out, size_t n, unsigned long long* d_total, const char* name = "scan") {
-    if (n == 0) {
-        if (d_total) OL_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), c.stream));
-        return;
-    }
+inline void transform_scan(Ctx& c, InFn in, OutFn out, size_t n, unsigned long long* d_total, const char* name = "scan",
+                           const Mail& mail = Mail{}) {
+    // n == 0 still launches (one CTA that finds nothing to do): the total and the mail are written by the kernel
     ProfScope ps(c, name, (double)n);
     if (n <= SCAN_SMALL_MAX) {
-        scan_small_kernel<T, InFn, OutFn><<<1, 1024, 0, c.stream>>>(in, out, n, d_total);
+        scan_small_kernel<T, InFn, OutFn><<<1, 1024, 0, c.stream>>>(in, out, n, d_total, mail);
         OL_CHECK_LAUNCH();
         return;
     }
@@ -241,7 +246,7 @@ inline void transform_scan(Ctx& c, InFn in, OutFn out, size_t n, unsigned long l
     DevBuf<unsigned long long> status(c, 2 * tiles + 1);  // + the ticket counter
     status.zero();
     scan_lookback_kernel<T, ITEMS, InFn, OutFn><<<(unsigned)tiles, SCAN_THREADS, 0, c.stream>>>(in, out, n, (uint32_t)tiles, status.get(),
-                                                                                              d_total);
+                                                                                              d_total, mail);
     OL_CHECK_LAUNCH();
 }
 // array form: out[i] = sum_{j<i} in[j]; in == out allowed
@@ -431,7 +436,8 @@ template <typename KeyFn, typename EmitFn>
 __global__ void __launch_bounds__(RUNS_THREADS) runs_fused_kernel(KeyFn key, EmitFn emit, uint32_t n, uint32_t num_tiles,
                                                                   unsigned long long* __restrict__ status,
                                                                   uint32_t* __restrict__ run_of_pos,
-                                                                  unsigned long long* __restrict__ total_out) {
+                                                                  unsigned long long* __restrict__ total_out,
+                                                                  uint32_t* __restrict__ sentinel, const Mail mail) {
     __shared__ uint32_t s_w[RUNS_THREADS / 32];
     __shared__ unsigned long long s_prefix;
     __shared__ uint32_t s_tile;
@@ -455,7 +461,11 @@ __global__ void __launch_bounds__(RUNS_THREADS) runs_fused_kernel(KeyFn key, Emi
         tile_total += s_w[w];
     }
     const unsigned long long prefix = lookback_exclusive_prefix(status, tile, (unsigned long long)tile_total, &s_prefix);
-    if (tile == num_tiles - 1 && threadIdx.x == 0 && total_out) *total_out = prefix + tile_total;
+    if (tile == num_tiles - 1 && threadIdx.x == 0) {
+        if (total_out) *total_out = prefix + tile_total;
+        if (sentinel) sentinel[prefix + tile_total] = n;  // run_start[number of runs] = n closes the start table
+        mail_post(mail, prefix + tile_total);
+    }
     uint32_t run = (uint32_t)prefix + before;  // heads before this warp's first element
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
@@ -473,17 +483,17 @@ __global__ void __launch_bounds__(RUNS_THREADS) runs_fused_kernel(KeyFn key, Emi
 
 // Segments [0, n) into maximal runs of equal key: calls emit(run, first position, key) per run, writes run_of_pos[i]
 // (may be nullptr) and the number of runs to d_total (device, 64-bit).  Run tables must hold the caller's upper bound.
+// `sentinel` (may be nullptr): a run-start table whose entry [number of runs] is set to n by the kernel itself, so that
+// the host does not have to know the count to close the table.  `mail`: the count posted to the host (common.cuh).
 template <typename KeyFn, typename EmitFn>
-inline void segment_runs(Ctx& c, KeyFn key, EmitFn emit, size_t n, uint32_t* run_of_pos, unsigned long long* d_total) {
-    if (n == 0) {
-        OL_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), c.stream));
-        return;
-    }
+inline void segment_runs(Ctx& c, KeyFn key, EmitFn emit, size_t n, uint32_t* run_of_pos, unsigned long long* d_total,
+                         uint32_t* sentinel = nullptr, const Mail& mail = Mail{}) {
+    OL_REQUIRE(n > 0, OL_ERR_INTERNAL, "segment_runs: empty input");
     const size_t tiles = (n + RUNS_TILE - 1) / RUNS_TILE;
     DevBuf<unsigned long long> status(c, 2 * tiles + 1);
     status.zero();
     runs_fused_kernel<KeyFn, EmitFn><<<(unsigned)tiles, RUNS_THREADS, 0, c.stream>>>(key, emit, (uint32_t)n, (uint32_t)tiles, status.get(),
-                                                                                     run_of_pos, d_total);
+                                                                                     run_of_pos, d_total, sentinel, mail);
     OL_CHECK_LAUNCH();
 }
 

@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _native as N
 
-__all__ = ["Forest", "TorchAllocator", "require_cuda"]
+__all__ = ["Forest", "TorchAllocator", "require_cuda", "release_cached_memory"]
 
 
 _NULL_SCOPE = contextlib.nullcontext()
@@ -40,8 +40,24 @@ class TorchAllocator:
     only be released by Python's cyclic garbage collector, several steps later and all at once - measured as
     100-300 ms stalls (cudaMalloc of new multi-GB blocks while the dead forests still held theirs)."""
 
-    def __init__(self, device):
+    _per_device: dict = {}
+
+    def __new__(cls, device):
+        # ONE allocator per device for the life of the process: the native library keeps released blocks in a process-wide
+        # cache and hands them to the next forest (csrc/common.cuh, BlockCache), so the callbacks - and the tensors behind
+        # the cached blocks - must outlive every single forest.  `release_cached_memory()` returns the blocks to torch.
         torch = require_cuda()
+        device = torch.device(device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self = cls._per_device.get(device.index)
+        if self is None:
+            self = super().__new__(cls)
+            self._setup(torch, device)
+            cls._per_device[device.index] = self
+        return self
+
+    def _setup(self, torch, device):
         self.device = device
         live = {}
         self.live = live
@@ -60,6 +76,11 @@ class TorchAllocator:
 
         self.alloc_cb = N.ALLOC_FN(_alloc)
         self.free_cb = N.FREE_FN(_free)
+
+
+def release_cached_memory() -> int:
+    """Return the device blocks the native library caches between forests to torch's allocator (bytes released)."""
+    return int(N.lib().ol_release_cached_memory())
 
 
 def _ptr(a):

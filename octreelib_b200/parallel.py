@@ -269,6 +269,8 @@ class _FusedExchange:
 class ShardedGrid:
     """The `Grid` operations of the hot path on a cell-sharded grid.  Pose numbers must be 0..P-1."""
 
+    _identity_tables: Dict[int, tuple] = {}
+
     def __init__(self, grid_config, n_poses_total: int, group=None, partition: str = "slab"):
         import torch.distributed as dist
 
@@ -286,9 +288,13 @@ class ShardedGrid:
         self._corner = corner
         self._host = ForestHost(grid_config.voxel_edge_length, corner, single_cell=False)
         # the local forest knows every pose number (index == number)
-        self._host.pose_numbers = list(range(self.n_poses_total))
-        self._host.pose_index = {p: p for p in range(self.n_poses_total)}
-        self._host.pose_inserted = [0] * self.n_poses_total
+        P = self.n_poses_total
+        cached = ShardedGrid._identity_tables.get(P)
+        if cached is None:
+            cached = ShardedGrid._identity_tables[P] = (list(range(P)), {p: p for p in range(P)})
+        self._host.pose_numbers = cached[0].copy()
+        self._host.pose_index = cached[1].copy()
+        self._host.pose_inserted = [0] * P
         self._staged: List[Tuple[int, object]] = []
         self.exchanged = False
         self.last_exchange = None
@@ -453,15 +459,20 @@ class ShardedGrid:
         """The production path (csrc/exchange.cu): one native call, no library collective, one host wait.  Returns False
         when peer-mapped memory is not available (the caller falls back to the staged paths below)."""
         torch = require_cuda()
-        staged = sorted(self._staged, key=lambda s: s[0])  # stable: poses ascending, insertion order inside a pose
-        tensors = []
+        staged = self._staged
+        numbers = [s[0] for s in staged]
+        if any(a > b for a, b in zip(numbers, numbers[1:])):
+            staged = sorted(staged, key=lambda s: s[0])  # stable: poses ascending, insertion order inside a pose
+            numbers = [s[0] for s in staged]
+        # the host time of this loop is time the GPU idles: one attribute test per cloud on the fast path
+        tensors, f64 = [], torch.float64
         for _, pts in staged:
-            t = pts if isinstance(pts, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pts, dtype=np.float64))
-            if t.device != dev or t.dtype != torch.float64 or not t.is_contiguous():
-                t = t.to(dev, dtype=torch.float64, non_blocking=True).contiguous()
-            tensors.append(t.reshape(-1, 3) if t.dim() != 2 else t)
-        numbers = [p for p, _ in staged]
-        n_local = sum(int(t.shape[0]) for t in tensors)
+            t = pts
+            if not (type(t) is torch.Tensor and t.dtype is f64 and t.device == dev and t.dim() == 2 and t.is_contiguous()):
+                t = pts if isinstance(pts, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pts, dtype=np.float64))
+                t = t.to(dev, dtype=torch.float64, non_blocking=True).contiguous().reshape(-1, 3)
+            tensors.append(t)
+        n_local = sum([t.shape[0] for t in tensors])
         mark("stage")
         forest = self._host.forest
         slabs = self.partition == "slab"

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--gap-us", type=float, default=8.0)
     ap.add_argument("--out", default="gpurun_out/timeline.json")
     ap.add_argument("--workload", default="c4_street_100M")
+    ap.add_argument("--list", action="store_true", help="print every GPU activity in order (start, duration, gap before it)")
     args = ap.parse_args()
     rank, world, local = bench.dist_env()
     torch.cuda.set_device(local)
@@ -72,6 +73,19 @@ def main():
     print(f"[timeline] rank 0 of {world}, scale {args.scale}: {len(gpu)} GPU activities over {args.steps} step(s), span {span / 1e3:.3f} ms, "
           f"busy {busy / 1e3:.3f} ms ({100 * busy / span:.1f} %), {len(gaps)} gaps >= {args.gap_us} us totalling "
           f"{sum(g[0] for g in gaps) / 1e3:.3f} ms")
+    if args.list:
+        print("[timeline] sequence (start ms | dur us | gap before us | name | host calls in the gap):")
+        prev_end = gpu[0]["ts"]
+        for e in gpu:
+            gap = e["ts"] - prev_end
+            calls = {}
+            if gap >= 4.0:
+                for r in rt:
+                    if r["ts"] + r["dur"] >= prev_end and r["ts"] <= e["ts"]:
+                        calls[r["name"]] = calls.get(r["name"], 0) + 1
+            cs = ", ".join(f"{k.replace('cuda', '')} x{v}" for k, v in sorted(calls.items(), key=lambda kv: -kv[1])[:5])
+            print(f"    {(e['ts'] - t0) / 1e3:7.3f} | {e['dur']:7.1f} | {gap:7.1f} | {e['name'].replace('ol::', '').replace('(anonymous namespace)::', '')[:44]:44s} | {cs}")
+            prev_end = max(prev_end, e["ts"] + e["dur"])
     byname = {}
     for e in gpu:
         k = e["name"].split("<")[0].split("(")[0][:48]
