@@ -406,13 +406,20 @@ __host__ __device__ inline uint64_t replay_key(uint32_t cell, uint32_t depth, ui
 //     sinfo[k] = (number of splitting leaves before k) << 1 | (k splits)
 // which is all the partition kernels need: split index s = sinfo >> 1 (if the low bit is set), and the leaf's index in
 // the next level's table = k + 7 * (sinfo >> 1) (every split replaces one leaf by eight).
+// MODE: what decides (count threshold / count table / membership in a recorded shape); CAP = the level is the maximum
+// depth: nothing may split, a leaf that wants to is an error.  Template parameters, so that the threshold and table
+// instantiations are straight-line code without stores: the scan evaluates 16 leaves per thread back to back, and only
+// then does the compiler issue the loads of all of them together (with the branches of the other modes in the way every
+// leaf cost its own one or two round trips to memory: 25 us for a scan over 600 k leaves).
+enum DecideMode { DECIDE_THRESHOLD = 0, DECIDE_TABLE = 1, DECIDE_REPLAY = 2 };
+template <int MODE, bool CAP>
 struct DecideIn {
-    const uint32_t* lstart;
-    const uint8_t* ldepth;
+    const uint32_t* __restrict__ lstart;
+    const uint8_t* __restrict__ ldepth;
     int level;
-    const uint32_t* wcount;
+    const uint32_t* __restrict__ wcount;
     long long max_points;
-    const uint8_t* table;
+    const uint8_t* __restrict__ table;
     long long table_len;
     int beyond;
     int max_depth;
@@ -421,9 +428,9 @@ struct DecideIn {
     const uint32_t* lcell;
     const uint64_t* lpath;
     uint32_t* err;
-    __device__ uint32_t operator()(size_t k) const {
+    __device__ __forceinline__ uint32_t operator()(size_t k) const {
         bool want = false;
-        if (replay_keys) {
+        if (MODE == DECIDE_REPLAY) {
             // scheme replay (octree_manager.py:171 -> octree.py:222-227): split exactly the nodes of the recorded shape
             if (ldepth[k] == level && level < REPLAY_MAX_DEPTH) {
                 const uint64_t key = replay_key(lcell[k], (uint32_t)level, lpath[k]);
@@ -437,14 +444,20 @@ struct DecideIn {
                 }
                 want = lo < n_replay && replay_keys[lo] == key;
             }
-        } else if (ldepth[k] == level) {
-            long long cnt = wcount ? (long long)wcount[k] : (long long)(lstart[k + 1] - lstart[k]);
-            if (table)
-                want = (cnt < table_len) ? (table[cnt] != 0) : (beyond != 0);
-            else
+        } else {
+            const uint32_t depth = ldepth[k];
+            const uint32_t s0 = lstart[k], s1 = lstart[k + 1];
+            const long long cnt = wcount ? (long long)wcount[k] : (long long)(s1 - s0);
+            if (MODE == DECIDE_TABLE) {
+                const long long at = cnt < table_len ? cnt : table_len - 1;  // always a valid entry: the load is unconditional
+                const uint8_t t = table[at];
+                want = cnt < table_len ? (t != 0) : (beyond != 0);
+            } else {
                 want = cnt > max_points;
-            if (want && level >= max_depth) {
-                atomicOr(err, (uint32_t)DEVERR_DEPTH_CAP);
+            }
+            want = want && (int)depth == level;
+            if (CAP) {
+                if (want) atomicOr(err, (uint32_t)DEVERR_DEPTH_CAP);
                 want = false;
             }
         }
@@ -458,10 +471,10 @@ struct HistIn {
     const uint32_t* leaf_cnt;
     uint32_t n_tile8, n_split, stride;
     __device__ uint32_t operator()(size_t i) const {
-        if (i < n_tile8) return tile_hist[i];
-        const uint32_t j = (uint32_t)(i - n_tile8);
+        const uint32_t j = i < n_tile8 ? 0u : (uint32_t)(i - n_tile8);
         const uint32_t g = j / n_split;
-        return leaf_cnt[(size_t)g * stride + (j - g * n_split)];
+        const uint32_t* p = i < n_tile8 ? tile_hist + i : leaf_cnt + ((size_t)g * stride + (j - g * n_split));
+        return *p;  // one unconditional load: the 16 elements of a thread are fetched together
     }
 };
 struct DecideOut {

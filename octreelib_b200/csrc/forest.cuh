@@ -38,6 +38,7 @@ struct Forest {
     std::vector<int64_t> seg_first;   // host: index of the segment's first point inside its pose's cloud
     bool segs_pose_monotone = true;
     int n_poses = 0;
+    DevBuf<uint8_t> seg_blob;    // the three segment tables in one allocation (upload_segments); d_seg_* are views
     DevBuf<uint32_t> d_seg_start;
     DevBuf<int32_t> d_seg_pose;
     DevBuf<int64_t> d_seg_first;

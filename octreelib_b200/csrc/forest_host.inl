@@ -136,14 +136,28 @@ void Forest::throw_device_errors(uint32_t e) {
 void Forest::check_device_errors() { throw_device_errors(read_u32(d_err.get())); }
 
 void Forest::upload_segments() {
-    size_t S = seg_pose.size();
-    d_seg_start.reset(ctx, S + 1);
-    d_seg_pose.reset(ctx, S ? S : 1);
-    d_seg_first.reset(ctx, S ? S : 1);
-    h2d(ctx, d_seg_start.get(), seg_start.data(), S + 1);
-    h2d(ctx, d_seg_pose.get(), seg_pose.data(), S);
-    h2d(ctx, d_seg_first.get(), seg_first.data(), S);
+    // ONE allocation and ONE copy for the three tables: [seg_first (int64) | seg_start (uint32, + sentinel) | seg_pose (int32)];
+    // d_seg_* are views into it (DevBuf without a context: nothing to free)
+    const size_t S = seg_pose.size(), Sp = S ? S : 1;
+    const size_t off_start = Sp * 8, off_pose = off_start + (S + 1) * 4, bytes = off_pose + Sp * 4;
+    std::vector<unsigned char> blob(bytes, 0);
+    if (S) {
+        memcpy(blob.data(), seg_first.data(), S * 8);
+        memcpy(blob.data() + off_pose, seg_pose.data(), S * 4);
+    }
+    memcpy(blob.data() + off_start, seg_start.data(), (S + 1) * 4);
+    seg_blob.reset(ctx, bytes);
+    h2d(ctx, seg_blob.get(), blob.data(), bytes);
     // no synchronisation: cudaMemcpyAsync from pageable memory returns once the source has been staged
+    auto view = [](auto& buf, void* p, size_t count) {
+        buf.release();
+        buf.ctx = nullptr;
+        buf.ptr = static_cast<decltype(buf.ptr)>(p);
+        buf.count = count;
+    };
+    view(d_seg_first, seg_blob.get(), Sp);
+    view(d_seg_start, seg_blob.get() + off_start, S + 1);
+    view(d_seg_pose, seg_blob.get() + off_pose, Sp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -863,6 +877,9 @@ void Forest::split_levels(const SplitRule* rule, const uint8_t* d_tables, const 
         return per_leaf == 0 ? (size_t)L : std::min<size_t>(L, (size_t)A / per_leaf);
     };
     constexpr size_t SPEC_MAX_LEAVES = (size_t)4 << 20;  // 128 MB of speculative counters at most
+    // internal-node arrays: room for two full levels of splits at once, so that a typical run never re-allocates (each
+    // re-allocation is six device-to-device copies)
+    if (rule && !rule->tables_host && L && A) reserve_internal(std::min<size_t>((size_t)I + 2 * std::max<size_t>(split_bound(0) , A / ((size_t)std::max<int64_t>(rule->max_points[0], 0) + 1)), (size_t)8 << 20));
     for (int level = 0;; ++level) {
         // level 0 of a fresh shape partitions straight out of the base order (reset_shape made no copy)
         const uint32_t* src_leaf = order_virgin ? cellidx0.get() : leaf_of.get();
@@ -879,7 +896,7 @@ void Forest::split_levels(const SplitRule* rule, const uint8_t* d_tables, const 
                 OL_CHECK_LAUNCH();
             }
         }
-        DecideIn din{};
+        DecideIn<DECIDE_THRESHOLD, false> din{};
         din.lstart = lstart.get();
         din.ldepth = ldepth.get();
         din.level = level;
@@ -890,19 +907,33 @@ void Forest::split_levels(const SplitRule* rule, const uint8_t* d_tables, const 
         din.lcell = lcell.get();
         din.lpath = lpath.get();
         din.err = d_err.get();
+        int mode = replay_keys ? DECIDE_REPLAY : DECIDE_THRESHOLD;
         if (rule) {
             const int e = rule->entry_for(level);
             if (rule->tables_host) {
                 din.table = d_tables + (size_t)e * (size_t)rule->table_len;
                 din.table_len = rule->table_len;
                 din.beyond = rule->beyond[e];
+                mode = DECIDE_TABLE;
             } else {
                 din.max_points = rule->max_points[e];
             }
         }
         // decide + scan; the number of splitting leaves (and the error word) is POSTED to the host by the kernel
         const Mail mail = mail_open(MAIL_LEVEL);
-        transform_scan<uint32_t>(ctx, din, DecideOut{sinfo.get()}, L, d_tot.get(), "part_decide", mail);
+        auto run_decide = [&](auto tag) {  // every instantiation has the same fields
+            decltype(tag) d{};
+            static_assert(sizeof(d) == sizeof(din), "DecideIn instantiations must share one layout");
+            memcpy(&d, &din, sizeof(din));
+            transform_scan<uint32_t>(ctx, d, DecideOut{sinfo.get()}, L, d_tot.get(), "part_decide", mail);
+        };
+        const bool cap = level >= max_depth;
+        if (mode == DECIDE_REPLAY)
+            run_decide(DecideIn<DECIDE_REPLAY, false>{});  // a recorded shape never reaches the depth cap
+        else if (mode == DECIDE_TABLE)
+            cap ? run_decide(DecideIn<DECIDE_TABLE, true>{}) : run_decide(DecideIn<DECIDE_TABLE, false>{});
+        else
+            cap ? run_decide(DecideIn<DECIDE_THRESHOLD, true>{}) : run_decide(DecideIn<DECIDE_THRESHOLD, false>{});
         // Speculation: the digit histograms of the level only need the decisions (device side), not their number, so the
         // pass is enqueued BEHIND the decision kernel with counters sized by the bound - the host reads the mailbox while
         // it runs and the GPU never waits for the host.  A level that splits nothing makes the pass return at once.

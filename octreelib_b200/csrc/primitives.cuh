@@ -77,54 +77,74 @@ __device__ __forceinline__ unsigned long long scan_ld_status(const unsigned long
 __device__ __forceinline__ void scan_st_status(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-
+// both status words of a tile (aggregate, inclusive prefix) in ONE 16-byte load: every word validates itself (top bit), so
+// it does not matter whether the pair is read atomically - and a look-back round costs one trip to L2 instead of two
+__device__ __forceinline__ void scan_ld_status2(const unsigned long long* p, unsigned long long& agg, unsigned long long& inc) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(agg), "=l"(inc) : "l"(p) : "memory");
+}
 // Chained-scan building block: the calling CTA owns tile `tile` (tiles are taken in ticket order) with aggregate
 // `aggregate`; returns the sum of the aggregates of all earlier tiles (valid in every thread after the internal
 // barriers) and publishes this tile's inclusive prefix.  status = [2 * tiles] words, zero-initialised:
 // status[2 t] = aggregate of tile t, status[2 t + 1] = inclusive prefix through tile t, both | SCAN_VALID.
 __device__ __forceinline__ unsigned long long lookback_exclusive_prefix(unsigned long long* __restrict__ status, uint32_t tile,
                                                                         unsigned long long aggregate,
-                                                                        unsigned long long* s_prefix /*shared, 1 word*/) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (warp == 0) {
-        if (lane == 0) scan_st_status(status + 2 * (size_t)tile + (tile == 0 ? 1 : 0), SCAN_VALID | aggregate);
-        unsigned long long prefix = 0;
-        if (tile > 0) {
-            long long look = (long long)tile - 1;
-            while (true) {
-                const long long idx = look - lane;
-                unsigned long long val = 0;
-                bool stop = idx < 0;  // before the first tile: an inclusive prefix of 0
-                if (idx >= 0) {
-                    while (true) {
-                        const unsigned long long inc = scan_ld_status(status + 2 * (size_t)idx + 1);
-                        if (inc & SCAN_VALID) {
-                            val = inc & ~SCAN_VALID;
-                            stop = true;
-                            break;
-                        }
-                        const unsigned long long agg = scan_ld_status(status + 2 * (size_t)idx);
-                        if (agg & SCAN_VALID) {
-                            val = agg & ~SCAN_VALID;
-                            break;
-                        }
+                                                                        unsigned long long* s_prefix /*shared, 1 word (unused)*/) {
+    // The WHOLE CTA looks back, blockDim.x predecessors per round.  All tiles of a launch become resident at about the
+    // same time (a B200 holds more than a thousand 256-thread CTAs), so the nearest predecessor that already knows its
+    // inclusive prefix is typically hundreds of tiles away: with one warp per round (32 tiles, one trip to L2 each) the
+    // look-back alone took 15-25 us per scan; with 256 tiles per round it is a handful of rounds.
+    (void)s_prefix;
+    __shared__ unsigned long long s_sum[32];
+    __shared__ uint32_t s_stop[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (int)(blockDim.x >> 5);
+    if (threadIdx.x == 0) scan_st_status(status + 2 * (size_t)tile + (tile == 0 ? 1 : 0), SCAN_VALID | aggregate);
+    unsigned long long prefix = 0;
+    if (tile > 0) {
+        long long look = (long long)tile - 1;
+        while (true) {
+            const long long idx = look - (long long)threadIdx.x;
+            unsigned long long val = 0;
+            bool stop = idx < 0;  // before the first tile: an inclusive prefix of 0
+            if (idx >= 0) {
+                while (true) {
+                    unsigned long long agg, inc;
+                    scan_ld_status2(status + 2 * (size_t)idx, agg, inc);
+                    if (inc & SCAN_VALID) {
+                        val = inc & ~SCAN_VALID;
+                        stop = true;
+                        break;
+                    }
+                    if (agg & SCAN_VALID) {
+                        val = agg & ~SCAN_VALID;
+                        break;
                     }
                 }
-                const uint32_t stopmask = __ballot_sync(0xffffffffu, stop);
-                const int first = stopmask ? (__ffs(stopmask) - 1) : 32;
-                unsigned long long v = (lane <= first) ? val : 0ull;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                prefix += v;
-                if (stopmask) break;
-                look -= 32;
             }
-            if (lane == 0) scan_st_status(status + 2 * (size_t)tile + 1, SCAN_VALID | (prefix + aggregate));
+            const uint32_t stopmask = __ballot_sync(0xffffffffu, stop);
+            const int first = stopmask ? (__ffs(stopmask) - 1) : 32;
+            unsigned long long v = (lane <= first) ? val : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) {
+                s_sum[warp] = v;
+                s_stop[warp] = stopmask ? 1u : 0u;
+            }
+            __syncthreads();
+            bool done = false;
+            for (int w = 0; w < nwarps; ++w) {  // warps in look-back order: nearest predecessors first
+                prefix += s_sum[w];
+                if (s_stop[w]) {
+                    done = true;
+                    break;
+                }
+            }
+            __syncthreads();  // the partial sums are overwritten by the next round
+            if (done) break;
+            look -= (long long)blockDim.x;
         }
-        if (lane == 0) *s_prefix = prefix;
+        if (threadIdx.x == 0) scan_st_status(status + 2 * (size_t)tile + 1, SCAN_VALID | (prefix + aggregate));
     }
-    __syncthreads();
-    return *s_prefix;
+    return prefix;
 }
 
 // input / output functors of the scans: in(i) -> T, out(i, exclusive prefix, in(i)); the plain forms read / write arrays
@@ -152,11 +172,20 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(InFn in, Ou
     __syncthreads();
     const uint32_t t = s_tile;
     const size_t base = (size_t)t * TILE;
+    {
+        // all inputs of the thread first, THEN the shared-memory stores: the loads behind in(i) are independent and must be
+        // in flight together (a store between two of them makes the warp wait for each load in turn)
+        T staged[ITEMS];
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-        const int li = j * SCAN_THREADS + threadIdx.x;
-        const size_t i = base + li;
-        tile[li + (li >> 5)] = (i < n) ? in(i) : (T)0;
+        for (int j = 0; j < ITEMS; ++j) {
+            const size_t i = base + (size_t)(j * SCAN_THREADS + threadIdx.x);
+            staged[j] = (i < n) ? in(i) : (T)0;
+        }
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const int li = j * SCAN_THREADS + threadIdx.x;
+            tile[li + (li >> 5)] = staged[j];
+        }
     }
     __syncthreads();
     T v[ITEMS];
@@ -243,9 +272,14 @@ inline void transform_scan(Ctx& c, InFn in, OutFn out, size_t n, unsigned long l
     }
     constexpr int ITEMS = sizeof(T) == 4 ? 16 : 8;
     const size_t tiles = (n + SCAN_THREADS * ITEMS - 1) / (SCAN_THREADS * ITEMS);
-    DevBuf<unsigned long long> status(c, 2 * tiles + 1);  // + the ticket counter
-    status.zero();
-    scan_lookback_kernel<T, ITEMS, InFn, OutFn><<<(unsigned)tiles, SCAN_THREADS, 0, c.stream>>>(in, out, n, (uint32_t)tiles, status.get(),
+    DevBuf<unsigned long long> own;
+    unsigned long long* status = c.status_words(2 * tiles + 1);  // + the ticket counter
+    if (!status) {
+        own.reset(c, 2 * tiles + 1);
+        own.zero();
+        status = own.get();
+    }
+    scan_lookback_kernel<T, ITEMS, InFn, OutFn><<<(unsigned)tiles, SCAN_THREADS, 0, c.stream>>>(in, out, n, (uint32_t)tiles, status,
                                                                                               d_total, mail);
     OL_CHECK_LAUNCH();
 }
@@ -410,11 +444,17 @@ __device__ __forceinline__ void runs_warp_flags(const KeyFn& key, uint32_t wbase
         carry = key(wbase - 1);
         have_carry = true;
     }
+    // every key of the lane first (independent loads, all in flight together), then the shuffles
+#pragma unroll
+    for (int j = 0; j < RUNS_ITEMS; ++j) {
+        const uint32_t i = wbase + 32 * j + lane;
+        keys[j] = i < n ? key(i) : 0ull;
+    }
 #pragma unroll
     for (int j = 0; j < RUNS_ITEMS; ++j) {
         const uint32_t i = wbase + 32 * j + lane;
         const bool valid = i < n;
-        const uint64_t k = valid ? key(i) : 0ull;
+        const uint64_t k = keys[j];
         uint64_t prev = __shfl_up_sync(0xffffffffu, k, 1);
         bool has_prev = true;
         if (lane == 0) {
@@ -423,7 +463,6 @@ __device__ __forceinline__ void runs_warp_flags(const KeyFn& key, uint32_t wbase
         }
         const bool head = valid && (!has_prev || prev != k);
         masks[j] = __ballot_sync(0xffffffffu, head);
-        keys[j] = k;
         carry = __shfl_sync(0xffffffffu, k, 31);
         have_carry = true;
     }
@@ -490,9 +529,14 @@ inline void segment_runs(Ctx& c, KeyFn key, EmitFn emit, size_t n, uint32_t* run
                          uint32_t* sentinel = nullptr, const Mail& mail = Mail{}) {
     OL_REQUIRE(n > 0, OL_ERR_INTERNAL, "segment_runs: empty input");
     const size_t tiles = (n + RUNS_TILE - 1) / RUNS_TILE;
-    DevBuf<unsigned long long> status(c, 2 * tiles + 1);
-    status.zero();
-    runs_fused_kernel<KeyFn, EmitFn><<<(unsigned)tiles, RUNS_THREADS, 0, c.stream>>>(key, emit, (uint32_t)n, (uint32_t)tiles, status.get(),
+    DevBuf<unsigned long long> own;
+    unsigned long long* status = c.status_words(2 * tiles + 1);
+    if (!status) {
+        own.reset(c, 2 * tiles + 1);
+        own.zero();
+        status = own.get();
+    }
+    runs_fused_kernel<KeyFn, EmitFn><<<(unsigned)tiles, RUNS_THREADS, 0, c.stream>>>(key, emit, (uint32_t)n, (uint32_t)tiles, status,
                                                                                      run_of_pos, d_total, sentinel, mail);
     OL_CHECK_LAUNCH();
 }
