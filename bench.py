@@ -612,9 +612,13 @@ def main():
     # (Morton codes are 32-bit words for trees of at most 10 levels, which covers every bench workload; the grid-wide sort
     # moves 32-bit keys when the packed cell key fits them - `key_bits` <= 32, every BASELINE configuration)
     kb = 4 if stats["key_bits"] <= 32 else 8
-    BYTES = {"bbox": 24, "insert_batch": 48, "keygen": 24 + kb + 4 + 4, "sort_main_hist": kb, "sort_main_pass": 2 * (kb + 4),
+    # (when the Morton code rides in the low bits of the 32-bit sort key - no "gather_morton" stage - keygen writes no
+    # Morton array and the cell segmentation peels the code off while it reads the sorted keys)
+    embedded = bool(prof) and "gather_morton" not in prof
+    BYTES = {"bbox": 24, "insert_batch": 48, "keygen": 24 + kb + 4 + (0 if embedded else 4), "sort_main_hist": kb,
+             "sort_main_pass": 2 * (kb + 4),
              "radix_hist_u64": 8, "radix_scatter_u64": 24, "radix_hist_u32": 4, "radix_scatter_u32": 16, "scan": 8,
-             "gather_morton": 12, "cells": kb + 4, "part_hist": 8, "part_move": 24, "gather_points": 52}
+             "gather_morton": 12, "cells": kb + 4 + (4 if embedded else 0), "part_hist": 8, "part_move": 24, "gather_points": 52}
     KERNELS = {"sort_main_pass": f"os_pass_kernel<u{8 * kb}> (one onesweep radix digit pass over all points, K2)",
                "part_move": "part_move_kernel<u32> (fused rank + stable 8-way partition of one octree level, K4)"}
     stage_ms = {k: v[1] for k, v in (prof or {}).items()}

@@ -53,17 +53,20 @@ class ForestHost:
 
     # ---- insertion ------------------------------------------------------------------------------
     def insert(self, pose_number: int, points, allow_append: bool):
-        n = int(points.shape[0]) if hasattr(points, "shape") and len(points.shape) == 2 else len(points)
-        if pose_number in self.pose_index:
+        # (called once per pose of a map: every attribute lookup here is host time the GPU waits for)
+        shape = getattr(points, "shape", None)
+        n = int(shape[0]) if shape is not None and len(shape) == 2 else len(points)
+        pose_index = self.pose_index
+        if pose_number in pose_index:
             if not allow_append:
                 raise ValueError(f"Cannot insert points to existing pose {pose_number}")
-            idx = self.pose_index[pose_number]
+            idx = pose_index[pose_number]
             self.forest.insert_segments(points, [n], [idx], [self.pose_inserted[idx]], len(self.pose_numbers))
             self.pose_inserted[idx] += n
         else:
-            idx = self.forest.insert(points)
+            idx = (self._forest or self.forest).insert(points)
             assert idx == len(self.pose_numbers)
-            self.pose_index[pose_number] = idx
+            pose_index[pose_number] = idx
             self.pose_numbers.append(pose_number)
             self.pose_inserted.append(n)
             self._pose_epoch[idx] = self._n_subdivides

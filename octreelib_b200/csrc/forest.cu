@@ -158,7 +158,10 @@ __global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ 
                                                      const uint32_t* __restrict__ seg_start,
                                                      const int32_t* __restrict__ seg_pose, int n_seg,
                                                      KeyT* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                     MortT* __restrict__ mort, uint32_t* __restrict__ err) {
+                                                     MortT* __restrict__ mort, uint32_t* __restrict__ err, int embed_levels) {
+    // embed_levels > 0: the Morton code (3 x embed_levels bits) and the out-of-node flag (1 bit) ride in the LOW bits of the
+    // sort key, below the packed cell key - the sort only looks at the bits above them, so the code arrives in sorted
+    // order for free (no separate 4-byte array to write here and to gather through the permutation afterwards)
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     double p[3] = {xyz[(size_t)r * 3 + 0], xyz[(size_t)r * 3 + 1], xyz[(size_t)r * 3 + 2]};
@@ -188,10 +191,14 @@ __global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ 
     for (int a = 0; a < 3; ++a) c[a] = cell_corner_coord(q[a], kp.corner[a], kp.edge, kp.single_cell);
     int bad;
     MortT m = (MortT)point_morton(p, c, kp.edge, kp.depth, &bad);
-    if (bad < kp.depth) m |= MortBits<MortT>::bad;
+    if (embed_levels > 0) {
+        key = (key << (3 * embed_levels + 1)) | ((uint64_t)(bad < kp.depth ? 1u : 0u) << (3 * embed_levels)) | (uint64_t)m;
+    } else {
+        if (bad < kp.depth) m |= MortBits<MortT>::bad;
+        mort[r] = m;
+    }
     keys[r] = (KeyT)key;
     vals[r] = r;  // the sort's payload: the point's rank
-    mort[r] = m;
     if (e) atomicOr(err, e);
 }
 
@@ -228,6 +235,21 @@ struct CellKeyFn {  // grid cell of a sorted position: the packed key without it
     const KeyT* keys;
     int pose_bits;
     __device__ uint64_t operator()(uint32_t i) const { return (uint64_t)(keys[i] >> pose_bits); }
+};
+// the same for keys that carry the Morton field in their low `fw` bits (keygen_kernel, embed_levels > 0): the field is
+// peeled off into the 32-bit Morton array of the base order while the cell segmentation reads the key anyway
+template <typename KeyT>
+struct CellKeyEmbedFn {
+    const KeyT* keys;
+    int shift;  // pose bits + fw
+    int fw;     // 3 x levels + 1
+    uint32_t* mort_out;
+    __device__ uint64_t operator()(uint32_t i) const {
+        const KeyT k = keys[i];
+        const uint32_t field = (uint32_t)k & ((1u << fw) - 1u);
+        mort_out[i] = (field & ((1u << (fw - 1)) - 1u)) | ((field >> (fw - 1)) ? MortBits<uint32_t>::bad : 0u);
+        return (uint64_t)(k >> shift);
+    }
 };
 struct CellEmitFn {
     uint64_t* cell_key;

@@ -70,6 +70,7 @@ struct Forest {
     bool built = false;
     KeyParams kp{};
     int key_bits = 0;
+    int key_embed = 0;           // Morton levels carried in the low bits of the 32-bit sort key (0: separate Morton array)
     uint32_t A0 = 0;             // alive points in the base order
     DevBuf<uint32_t> perm0;      // [A0] base position -> r
     DevBuf<uint64_t> mort0;      // [A0] Morton code of the point (top bit: out-of-node somewhere); 32-bit words packed two

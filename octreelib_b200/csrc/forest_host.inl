@@ -27,6 +27,8 @@ static void pinned_scratch_put(void* p) {
     g_pinned_free.push_back(p);
 }
 
+static size_t g_last_build_points = 0;  // points of the last grid built by this process (capacity guess of the next one)
+
 Forest::Forest(const ol_forest_config& c) : cfg(c) {
     OL_REQUIRE(c.voxel_edge_length > 0 && std::isfinite(c.voxel_edge_length), OL_ERR_INVALID,
                "voxel_edge_length must be a positive finite number");
@@ -304,7 +306,17 @@ int Forest::insert_batch(const double* const* xyz_dev, const int64_t* sizes, int
         bbox_done = 0;
     }
     if (N + total > cap) {
-        const size_t ncap = N + total;  // the batch is usually the whole map: grow exactly once
+        // The host hands its clouds over in several batches while it is still inserting (forest.py flushes every 64 poses,
+        // so that the copy runs while the host language works through the remaining insert calls).  The final size is
+        // not known yet: the point count of the previous build of this process is the first guess (a pipeline builds
+        // maps of similar size step after step: no growth copy and no slack in the steady state), geometric growth
+        // otherwise.
+        size_t ncap = N + total;
+        const size_t guess = g_last_build_points;
+        if (guess >= ncap && ncap >= guess / 32)
+            ncap = guess;
+        else if (cap > 0)
+            ncap = std::max(ncap, cap * 2);
         DevBuf<double> np(ctx, ncap * 3);
         d2d(ctx, np.get(), P64.get(), N * 3);
         P64.swap(np);
@@ -363,6 +375,7 @@ void Forest::build() {
 void Forest::build_enqueue() {
     if (built) return;
     cells_pending = false;
+    g_last_build_points = N;
     if (bbox_done < N) {  // K0 over everything inserted since the last build
         const size_t m = N - bbox_done;
         unsigned g = std::min<unsigned>(nblk(m * 3, BBOX_THREADS), (unsigned)ctx.num_sms * 10);
@@ -431,6 +444,16 @@ void Forest::build_enqueue() {
     }
     const int cell_bits = bits[0] + bits[1] + bits[2];
     key_bits = cell_bits + kp.pose_bits;
+    // Morton levels that fit into a 32-bit sort key below the packed cell key (+ 1 bit for the out-of-node flag): they ride
+    // through the sort for free.  Deeper levels are computed on demand (extend_morton), like the levels beyond
+    // MORTON_INITIAL_DEPTH of the separate-array layout.
+    static const bool no_embed = getenv("OL_NO_EMBED") != nullptr;
+    key_embed = 0;
+    if (!no_embed && N > 0 && key_bits + 1 + 3 * std::min(kp.depth, 3) <= 32) {
+        key_embed = std::min(kp.depth, (32 - key_bits - 1) / 3);
+        kp.depth = key_embed;
+    }
+    const int fw = key_embed ? 3 * key_embed + 1 : 0;
     OL_REQUIRE(key_bits <= 64, OL_ERR_RANGE,
                "the grid spans too many cells: packed cell key needs " + std::to_string(key_bits) + " bits (max 64)");
     kp.shift[2] = kp.pose_bits;
@@ -460,7 +483,7 @@ void Forest::build_enqueue() {
     const size_t c_max = cell_bits < 31 ? std::min<size_t>(n, (size_t)1 << cell_bits) : n;
     cell_key.reset(ctx, c_max);
     cell_start0.reset(ctx, c_max + 1);
-    const int key_bytes = key_bits <= 32 ? 4 : 8;
+    const int key_bytes = key_bits + fw <= 32 ? 4 : 8;
     if (key_bytes != pre_key_bytes) {
         kraw0.reset(ctx, key_bytes == 4 ? ((size_t)n + 1) / 2 : (size_t)n);
         kraw1.reset(ctx, key_bytes == 4 ? ((size_t)n + 1) / 2 : (size_t)n);
@@ -480,13 +503,14 @@ void Forest::build_enqueue() {
             if (mort32)
                 keygen_kernel<KeyT, uint32_t><<<nblk(n), 256, 0, ctx.stream>>>(P64.get(), n, kp, d_seg_start.get(), d_seg_pose.get(), S,
                                                                                keys0.get(), vals0.get(),
-                                                                               reinterpret_cast<uint32_t*>(mort_r.get()), d_err.get());
+                                                                               reinterpret_cast<uint32_t*>(mort_r.get()), d_err.get(),
+                                                                               key_embed);
             else
                 keygen_kernel<KeyT, uint64_t><<<nblk(n), 256, 0, ctx.stream>>>(P64.get(), n, kp, d_seg_start.get(), d_seg_pose.get(), S,
-                                                                               keys0.get(), vals0.get(), mort_r.get(), d_err.get());
+                                                                               keys0.get(), vals0.get(), mort_r.get(), d_err.get(), 0);
             OL_CHECK_LAUNCH();
         }
-        const int which = radix_sort_pairs<KeyT>(ctx, keys0.get(), keys1.get(), vals0.get(), vals1.get(), n, 0, key_bits, true);
+        const int which = radix_sort_pairs<KeyT>(ctx, keys0.get(), keys1.get(), vals0.get(), vals1.get(), n, fw, fw + key_bits, true);
         if (which) {
             keys0.swap(keys1);
             vals0.swap(vals1);
@@ -498,16 +522,23 @@ void Forest::build_enqueue() {
         // and the kernel closes the start table itself (cell_start0[C] = n)
         ProfScope ps(ctx, "cells", (double)n);
         cells_mail = mail_open(MAIL_CELLS);
-        segment_runs(ctx, CellKeyFn<KeyT>{keys0.get(), kp.pose_bits}, CellEmitFn{cell_key.get(), cell_start0.get()}, n, cellidx0.get(),
-                     d_total.get(), cell_start0.get(), cells_mail);
+        if (key_embed) {
+            mort0.reset(ctx, mort_len(n));
+            segment_runs(ctx, CellKeyEmbedFn<KeyT>{keys0.get(), kp.pose_bits + fw, fw, reinterpret_cast<uint32_t*>(mort0.get())},
+                         CellEmitFn{cell_key.get(), cell_start0.get()}, n, cellidx0.get(), d_total.get(), cell_start0.get(), cells_mail);
+        } else {
+            segment_runs(ctx, CellKeyFn<KeyT>{keys0.get(), kp.pose_bits}, CellEmitFn{cell_key.get(), cell_start0.get()}, n,
+                         cellidx0.get(), d_total.get(), cell_start0.get(), cells_mail);
+        }
     };
-    if (key_bits <= 32)
+    if (key_embed) mort_r.release();
+    if (key_bytes == 4)
         run(uint32_t{});
     else
         run(uint64_t{});
     perm0.swap(vals0);
-    mort0.reset(ctx, mort_len(n));
-    {
+    if (!key_embed) {
+        mort0.reset(ctx, mort_len(n));
         ProfScope ps(ctx, "gather_morton", (double)n);
         if (mort32)
             gather_kernel<uint32_t><<<nblk(n), 256, 0, ctx.stream>>>(reinterpret_cast<uint32_t*>(mort0.get()),
@@ -629,7 +660,8 @@ void Forest::ensure_alive() {
 // recomputes them at the full depth for the base order and for the current order.
 void Forest::extend_morton() {
     if (kp.depth >= max_depth) return;
-    kp.depth = max_depth;
+    // in two stages: up to MORTON32_MAX_DEPTH levels the codes stay 32-bit words (a quarter less partition traffic)
+    kp.depth = kp.depth < MORTON32_MAX_DEPTH ? std::min(max_depth, MORTON32_MAX_DEPTH) : max_depth;
     const bool was32 = mort32;
     mort32 = kp.depth <= MORTON32_MAX_DEPTH;
     ProfScope ps(ctx, "keygen", (double)(A0 + (shaped ? A : 0)));

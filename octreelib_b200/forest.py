@@ -95,6 +95,9 @@ def _i32_array(values: Optional[Sequence[int]]):
 
 
 class Forest:
+    FLUSH_EVERY = 64            # deferred CUDA-tensor inserts are handed over in batches of this many poses ...
+    FLUSH_MIN_ROWS = 1 << 20    # ... once they hold at least this many points (small grids: one batch at the end)
+
     def __init__(self, edge: float, corner=(0.0, 0.0, 0.0), single_cell: bool = False, max_depth: int = N.OL_MAX_DEPTH,
                  device=None):
         torch = require_cuda()
@@ -116,6 +119,7 @@ class Forest:
         cfg.alloc_user = None
         self._pending_sources = []  # sources of inserts that may still be in flight
         self._batch = []            # CUDA tensors whose insert is deferred (one native call for all of them)
+        self._batch_rows = 0
         self._n_poses_native = 0    # poses the native forest knows about
         self._h = C.c_void_p()
         with self._scope():
@@ -166,8 +170,12 @@ class Forest:
             if t.dim() != 2 or t.shape[1] != 3:
                 t = t.reshape(-1, 3)
             self._batch.append(t)
+            self._batch_rows += t.shape[0]
             self.version += 1
-            return self._n_poses_native + len(self._batch) - 1
+            index = self._n_poses_native + len(self._batch) - 1
+            if len(self._batch) >= self.FLUSH_EVERY and self._batch_rows >= self.FLUSH_MIN_ROWS:
+                self._flush()  # the copy kernel runs while the caller is still inserting the following poses
+            return index
         out = C.c_int32(-1)
         src, n, on_dev, keep = self._as_source(points)
         with self._scope():
@@ -181,6 +189,7 @@ class Forest:
     def _flush(self):
         """Hand the deferred CUDA-tensor inserts to the native forest (one call)."""
         batch, self._batch = self._batch, []
+        self._batch_rows = 0
         if not batch:
             return
         count = len(batch)

@@ -46,9 +46,10 @@ class Grid(GridBase):
         Ordinary (pageable) host arrays are consumed before the call returns, like in the reference.  A PAGE-LOCKED
         (pinned) host array is uploaded asynchronously: leave it unchanged until the next call that returns results
         (`subdivide`, `n_points`, `get_leaf_points`, ...)."""
-        if pose_number in self._host.pose_index:
+        host = self._host
+        if pose_number in host.pose_index:
             raise ValueError(f"Cannot insert points to existing pose {pose_number}")
-        self._host.insert(pose_number, points if hasattr(points, "device") else np.asarray(points), allow_append=False)
+        host.insert(pose_number, points if hasattr(points, "device") else np.asarray(points), allow_append=False)
 
     # ---- grid.py:111-122 ------------------------------------------------------------------------
     def map_leaf_points(self, function: Callable[[PointCloud], PointCloud], pose_numbers: Optional[List[int]] = None):

@@ -5,7 +5,10 @@
 
     ncu --set full --clock-control none --import-source on -k regex:'os_pass_kernel|part_move_kernel|...' -o gpurun_out/x python bench.py ...
     ncu -i gpurun_out/x.ncu-rep --page raw --csv > gpurun_out/x_raw.csv        (here: no GPU needed)
-    python tools/ncu_traffic.py gpurun_out/x_raw.csv profiles/r02_ncu_traffic.json profiles/r02_ncu_summary_v1.md
+    python tools/ncu_traffic.py gpurun_out/x_raw.csv profiles/r02_ncu_traffic.json profiles/r02_ncu_summary_v1.md [points]
+
+`points` = the number of points of the captured workload (default 100 000 000: c4_street_100M); every kernel listed below
+walks all of them once per launch, which is what bench.py scales the per-launch traffic by.
 """
 import csv
 import json
@@ -40,6 +43,7 @@ def to_ns(v, unit):
 
 def main():
     raw, out_json, out_md = sys.argv[1], sys.argv[2], sys.argv[3]
+    points = float(sys.argv[4]) if len(sys.argv) > 4 else 1e8
     rows = list(csv.reader(open(raw, newline="")))
     header = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     names, units = rows[header], rows[header + 1]
@@ -80,7 +84,7 @@ def main():
             return sum(vals) / len(vals) if vals else float("nan")
 
         table[stage] = {"kernel": big[0]["kernel"][:120], "launches_captured": len(big), "dram_bytes_per_launch": traffic,
-                        "time_us_under_ncu": t_us, "grid": gmax, "source": f"{raw} (ncu --set full, serialised launches)"}
+                        "time_us_under_ncu": t_us, "grid": gmax, "elements_per_launch": points, "source": f"{raw} (ncu --set full, serialised launches)"}
         md.append(f"| `{big[0]['kernel'][:70]}` | {len(big)} | {int(gmax)} x {int(avg('block'))} | {int(avg('regs'))} | {t_us:.1f} | "
                   f"{traffic / 1e6:.1f} | {avg('dram_pct'):.1f} | {avg('sm_pct'):.1f} | {avg('issue'):.1f} | {avg('warps'):.1f} | {avg('fp64'):.1f} |")
     json.dump(table, open(out_json, "w"), indent=1)
