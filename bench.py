@@ -575,6 +575,16 @@ def main():
     pgrid, pstats, prof, _ = run_step(clouds, numbers, P, w, world, profile=True)
     exchange_info = getattr(pgrid, "last_exchange", None)
     del pgrid
+    # per-rank view of the profiled step (multi-GPU): the step time is set by the slowest rank, the others wait inside the
+    # exchange's flag rounds - kernel time, the share of it spent in the two exchange stages, and the shard sizes
+    ranks_info = None
+    if world > 1 and dist is not None:
+        mine = dict(rank=rank, kernel_ms=round(sum(v[1] for v in (prof or {}).values()), 3),
+                    exchange_ms=round(sum(v[1] for k, v in (prof or {}).items() if k.startswith("exchange")), 3),
+                    points=int(pstats["n_points_inserted"]), leaves=int(pstats["n_leaves"]), cells=int(pstats["n_cells"]))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        ranks_info = gathered
     rstats = ransac_stats_read(lib)
     assert pstats["sample_oob_seen"] == 0 and stats["sample_oob_seen"] == 0, "a RANSAC sample index left its block"
     full_path = full_path_ransac(lib, device, fp64_peak.value, fp32_peak.value) if (rank == 0 and not args.no_full_path) else None
@@ -692,6 +702,8 @@ def main():
                 "H512_parity": runs.get(512, {}).get("parity_vs_reference_kernel_on_b200")}
         except Exception:  # noqa: BLE001
             pass
+    if ranks_info:
+        out["ranks"] = ranks_info
     if exchange_info:
         out["exchange"] = dict(exchange_info, note="rank 0; ms = CUDA events around ShardedGrid.exchange() in the profiled step "
                                                    "(slab boundaries, owner sort, count all-gather, routed copy, insert); bytes = "

@@ -44,6 +44,10 @@ struct Forest {
     DevBuf<int64_t> d_seg_first;
     DevBuf<long long> d_bbox;    // [6] ordered-int min xyz, max xyz
     DevBuf<uint32_t> d_err;      // [1]
+    bool uploads_pending = false;  // copies of pinned host clouds in flight on the upload streams (forest_host.inl)
+    int upload_turn = 0;
+    cudaStream_t upload_stream();
+    void join_uploads();
     void* pinned = nullptr;      // small pinned scratch for read-backs (256 B)
     // Results posted by kernels straight into page-locked memory (common.cuh: Mail): 8 slots of 4 words.  A count whose
     // producer has been enqueued may stay unread until somebody needs it (`*_pending`): the eager parts of the pipeline

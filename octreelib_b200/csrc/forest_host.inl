@@ -27,6 +27,48 @@ static void pinned_scratch_put(void* p) {
     g_pinned_free.push_back(p);
 }
 
+// upload streams of the pinned-source inserts (process-wide, created on first use) and the events that order them against
+// a forest's own stream
+constexpr int UPLOAD_MAX_DEVICES = 64;
+struct UploadLane {
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaEvent_t events[3] = {nullptr, nullptr, nullptr};
+};
+static UploadLane g_upload[UPLOAD_MAX_DEVICES];
+static UploadLane& upload_lane(int device) {
+    OL_REQUIRE(device >= 0 && device < UPLOAD_MAX_DEVICES, OL_ERR_INVALID, "device index out of range");
+    UploadLane& u = g_upload[device];
+    if (!u.streams[0]) {
+        for (auto& s : u.streams) OL_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        for (auto& e : u.events) OL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    return u;
+}
+
+// next upload stream; the first copy after work on the forest's stream that the copies must follow (allocation, growth)
+// makes both upload streams wait for that work
+cudaStream_t Forest::upload_stream() {
+    UploadLane& u = upload_lane(cfg.device);
+    if (!uploads_pending) {
+        OL_CUDA(cudaEventRecord(u.events[2], ctx.stream));
+        for (auto s : u.streams) OL_CUDA(cudaStreamWaitEvent(s, u.events[2], 0));
+        uploads_pending = true;
+    }
+    upload_turn ^= 1;
+    return u.streams[upload_turn];
+}
+
+// the forest's stream waits for every copy issued on the upload streams
+void Forest::join_uploads() {
+    if (!uploads_pending) return;
+    UploadLane& u = upload_lane(cfg.device);
+    for (int k = 0; k < 2; ++k) {
+        OL_CUDA(cudaEventRecord(u.events[k], u.streams[k]));
+        OL_CUDA(cudaStreamWaitEvent(ctx.stream, u.events[k], 0));
+    }
+    uploads_pending = false;
+}
+
 static size_t g_last_build_points = 0;  // points of the last grid built by this process (capacity guess of the next one)
 
 Forest::Forest(const ol_forest_config& c) : cfg(c) {
@@ -56,6 +98,8 @@ Forest::Forest(const ol_forest_config& c) : cfg(c) {
 }
 
 Forest::~Forest() {
+    if (uploads_pending)
+        for (auto s : g_upload[cfg.device].streams) cudaStreamSynchronize(s);  // copies into the point array that is about to be released
     cudaStreamSynchronize(ctx.stream);  // also: no kernel may post into the mailbox after it went back to the pool
     pinned_scratch_put(pinned);
     pinned_scratch_put(mailbox);
@@ -178,7 +222,10 @@ int Forest::insert(const double* xyz, int64_t n, bool on_device, const int64_t* 
         bbox_done = 0;
     }
     if (N + (size_t)n > cap) {
+        join_uploads();  // copies still in flight on the upload streams target the old array
         size_t ncap = std::max<size_t>(N + (size_t)n, cap + cap / 2 + 1024);
+        // first guess: the size of the previous map of this process (see insert_batch) - no growth copy in the steady state
+        if (g_last_build_points >= N + (size_t)n && N + (size_t)n >= g_last_build_points / 1024) ncap = std::max(ncap, g_last_build_points);
         DevBuf<double> np(ctx, ncap * 3);
         d2d(ctx, np.get(), P64.get(), N * 3);
         P64.swap(np);
@@ -191,9 +238,23 @@ int Forest::insert(const double* xyz, int64_t n, bool on_device, const int64_t* 
         cap = ncap;
     }
     // one copy per insert; the bounding box / non-finite check of the new points runs once, in build()
-    if (n > 0)
-        OL_CUDA(cudaMemcpyAsync(P64.get() + N * 3, xyz, (size_t)n * 24, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                                ctx.stream));
+    bool src_pinned = false;
+    if (!on_device && n > 0) {
+        cudaPointerAttributes attr{};
+        src_pinned = cudaPointerGetAttributes(&attr, xyz) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        if (!src_pinned) cudaGetLastError();  // an unregistered pointer may leave a sticky-free error code behind on old drivers
+    }
+    if (n > 0) {
+        if (src_pinned) {
+            // Page-locked sources go through TWO upload streams in turn: the DMA set-up of one copy overlaps the transfer
+            // of the other (838 copies of 2.9 MB on one stream: 4 us bubble each, 51 GB/s while busy).  build() joins them.
+            cudaStream_t up = upload_stream();
+            OL_CUDA(cudaMemcpyAsync(P64.get() + N * 3, xyz, (size_t)n * 24, cudaMemcpyHostToDevice, up));
+        } else {
+            OL_CUDA(cudaMemcpyAsync(P64.get() + N * 3, xyz, (size_t)n * 24, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                    ctx.stream));
+        }
+    }
     int pose_index;
     if (n_segments <= 0) {
         pose_index = n_poses;
@@ -225,17 +286,12 @@ int Forest::insert(const double* xyz, int64_t n, bool on_device, const int64_t* 
     built = false;
     shaped = false;
     order_valid = blocks_valid = ransac_valid = false;
-    if (!on_device && n > 0) {
+    if (!on_device && n > 0 && !src_pinned) {
         // Pageable host memory: cudaMemcpyAsync returns once the source has been staged, so the caller may reuse it.
         // Page-locked (pinned) host memory is read by DMA later: the caller deliberately handed over an asynchronous
         // buffer and must leave it unchanged until the next call that returns results (documented in Grid.insert_points);
         // waiting here would serialise 839 copies of a 100 M-point map with ~25 us bubbles each.
-        cudaPointerAttributes attr{};
-        const bool pinned = cudaPointerGetAttributes(&attr, xyz) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-        if (!pinned) {
-            cudaGetLastError();  // an unregistered pointer may leave a sticky-free error code behind on old drivers
-            ctx.sync();
-        }
+        ctx.sync();
     }
     return pose_index;
 }
@@ -305,6 +361,7 @@ int Forest::insert_batch(const double* const* xyz_dev, const int64_t* sizes, int
         q_known = false;
         bbox_done = 0;
     }
+    join_uploads();  // (mixed use: host arrays inserted before this batch)
     if (N + total > cap) {
         // The host hands its clouds over in several batches while it is still inserting (forest.py flushes every 64 poses,
         // so that the copy runs while the host language works through the remaining insert calls).  The final size is
@@ -328,14 +385,18 @@ int Forest::insert_batch(const double* const* xyz_dev, const int64_t* sizes, int
         }
         cap = ncap;
     }
+    // chunk length: at least ~16 chunks per SM (a batch of 64 poses is small next to the whole map: with full-size chunks it
+    // was 5 CTAs per SM and ran at 60 % of the bandwidth of the single big launch), a multiple of 3, at most INSERT_CHUNK
+    unsigned long long chunk_len = (unsigned long long)total * 3ull / ((unsigned long long)ctx.num_sms * 16ull);
+    chunk_len = std::min<unsigned long long>(std::max<unsigned long long>(chunk_len / 3ull * 3ull, 3ull * 1024ull), INSERT_CHUNK);
     std::vector<InsertChunk> chunks;
-    chunks.reserve(total * 3 / INSERT_CHUNK + (size_t)count + 1);
+    chunks.reserve(total * 3 / chunk_len + (size_t)count + 1);
     size_t r = N;
     unsigned long long dst = 0;
     for (int c = 0; c < count; ++c) {
         const unsigned long long len = (unsigned long long)sizes[c] * 3ull;
-        for (unsigned long long off = 0; off < len; off += INSERT_CHUNK)
-            chunks.push_back(InsertChunk{xyz_dev[c] + off, dst + off, (unsigned)std::min<unsigned long long>(INSERT_CHUNK, len - off), 0u});
+        for (unsigned long long off = 0; off < len; off += chunk_len)
+            chunks.push_back(InsertChunk{xyz_dev[c] + off, dst + off, (unsigned)std::min<unsigned long long>(chunk_len, len - off), 0u});
         dst += len;
         seg_pose.push_back(n_poses);
         seg_first.push_back(0);
@@ -374,6 +435,7 @@ void Forest::build() {
 
 void Forest::build_enqueue() {
     if (built) return;
+    join_uploads();
     cells_pending = false;
     g_last_build_points = N;
     if (bbox_done < N) {  // K0 over everything inserted since the last build

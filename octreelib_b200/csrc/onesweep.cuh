@@ -23,6 +23,9 @@ constexpr int OS_ITEMS = 16;
 constexpr int OS_TILE = OS_THREADS * OS_ITEMS;
 constexpr int OS_WARPS = OS_THREADS / 32;
 constexpr int OS_MAX_PASSES = 8;
+#ifndef OS_LOOKBACK
+#define OS_LOOKBACK 8
+#endif
 constexpr uint32_t OS_FLAG_AGG = 1u << 30;
 constexpr uint32_t OS_FLAG_INC = 2u << 30;
 constexpr uint32_t OS_VAL_MASK = (1u << 30) - 1u;
@@ -73,26 +76,45 @@ inline OsPlan os_make_plan(int begin_bit, int end_bit) {
 template <typename KeyT>
 __global__ void __launch_bounds__(OS_THREADS) os_hist_kernel(const KeyT* __restrict__ keys, uint32_t n, OsPlan plan,
                                                              uint32_t* __restrict__ ghist /*[passes][256]*/) {
+    // Every thread walks CONSECUTIVE keys (16 bytes per load) and counts runs of equal digits in registers: one shared
+    // atomic per run instead of a MATCH.ANY + atomic per key and pass.  The pipeline's keys are spatially coherent (a LiDAR
+    // scan sweeps through neighbouring cells), so a thread's four keys nearly always share their upper digits.
     __shared__ uint32_t h[OS_MAX_PASSES][256];
     for (int i = threadIdx.x; i < plan.passes * 256; i += OS_THREADS) (&h[0][0])[i] = 0;
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const uint32_t num_tiles = (n + OS_TILE - 1) / OS_TILE;
-    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const uint32_t base = tile * OS_TILE + threadIdx.x;
-#pragma unroll 4
-        for (int j = 0; j < OS_ITEMS; ++j) {
-            const uint32_t i = base + j * OS_THREADS;
-            const bool valid = i < n;
-            const KeyT k = valid ? keys[i] : (KeyT)0;
+    constexpr int VEC = 16 / (int)sizeof(KeyT);  // keys per 16-byte load
+    const uint32_t n_vec = (reinterpret_cast<uintptr_t>(keys) & 15u) ? 0u : n / VEC;  // unaligned input: key by key
+    uint32_t run_d[OS_MAX_PASSES], run_c[OS_MAX_PASSES];
 #pragma unroll
-            for (int p = 0; p < OS_MAX_PASSES; ++p) {
-                if (p >= plan.passes) break;
-                const uint32_t d = (uint32_t)((k >> plan.bit[p]) & (KeyT)((1u << plan.nbits[p]) - 1u));
-                const uint32_t peers = os_match_digit(d, plan.nbits[p], valid);
-                if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&h[p][d], (uint32_t)__popc(peers));
+    for (int p = 0; p < OS_MAX_PASSES; ++p) run_d[p] = 0u, run_c[p] = 0u;
+    auto add = [&](KeyT k) {
+#pragma unroll
+        for (int p = 0; p < OS_MAX_PASSES; ++p) {
+            if (p >= plan.passes) break;
+            const uint32_t d = (uint32_t)((k >> plan.bit[p]) & (KeyT)((1u << plan.nbits[p]) - 1u));
+            if (d == run_d[p]) {
+                ++run_c[p];
+            } else {
+                if (run_c[p]) atomicAdd(&h[p][run_d[p]], run_c[p]);
+                run_d[p] = d;
+                run_c[p] = 1u;
             }
         }
+    };
+    for (uint32_t v = blockIdx.x * OS_THREADS + threadIdx.x; v < n_vec; v += gridDim.x * OS_THREADS) {
+        if (sizeof(KeyT) == 4) {
+            const uint4 q = reinterpret_cast<const uint4*>(keys)[v];
+            add((KeyT)q.x), add((KeyT)q.y), add((KeyT)q.z), add((KeyT)q.w);
+        } else {
+            const ulonglong2 q = reinterpret_cast<const ulonglong2*>(keys)[v];
+            add((KeyT)q.x), add((KeyT)q.y);
+        }
+    }
+    for (uint32_t i = n_vec * VEC + blockIdx.x * OS_THREADS + threadIdx.x; i < n; i += gridDim.x * OS_THREADS) add(keys[i]);  // the rest
+#pragma unroll
+    for (int p = 0; p < OS_MAX_PASSES; ++p) {
+        if (p >= plan.passes) break;
+        if (run_c[p]) atomicAdd(&h[p][run_d[p]], run_c[p]);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < plan.passes * 256; i += OS_THREADS) {
@@ -251,14 +273,26 @@ __global__ void __launch_bounds__(OS_THREADS, MIN_BLOCKS) os_pass_kernel(const K
     if (digit_thread) {
         uint32_t excl = 0;
         if (tile > 0) {
+            // OS_LOOKBACK predecessors per round, their loads issued back to back: a walk that fetched one status word
+            // per trip to L2 (~0.7 us each) could not keep up with the rate at which tiles start - several hundred tiles
+            // are in flight, and most of them have only published their aggregate when a successor looks back
             const uint32_t* st = status + d;
-            for (long long t = (long long)tile - 1; t >= 0; --t) {
-                uint32_t sv;
-                do {
-                    sv = os_ld_status(st + (size_t)t * 256);
-                } while ((sv >> 30) == 0u);
-                excl += sv & OS_VAL_MASK;
-                if ((sv >> 30) == 2u) break;
+            long long t = (long long)tile - 1;
+            bool done = false;
+            while (!done && t >= 0) {
+                uint32_t sv[OS_LOOKBACK];
+#pragma unroll
+                for (int w = 0; w < OS_LOOKBACK; ++w)
+                    sv[w] = (t - w >= 0) ? os_ld_status(st + (size_t)(t - w) * 256) : (OS_FLAG_INC | 0u);
+#pragma unroll
+                for (int w = 0; w < OS_LOOKBACK; ++w) {
+                    if (!done) {
+                        while ((sv[w] >> 30) == 0u) sv[w] = os_ld_status(st + (size_t)(t - w) * 256);
+                        excl += sv[w] & OS_VAL_MASK;
+                        if ((sv[w] >> 30) == 2u) done = true;
+                    }
+                }
+                t -= OS_LOOKBACK;
             }
             os_st_status(my_status, OS_FLAG_INC | ((excl + count) & OS_VAL_MASK));
         }

@@ -520,6 +520,77 @@ __global__ void __launch_bounds__(RUNS_THREADS) runs_fused_kernel(KeyFn key, Emi
     }
 }
 
+// TWO passes for large inputs (reduce-then-scan): the chained single-pass kernel above spends most of its time in the
+// look-back (2048-element tiles, ~49 k of them for 100 M elements, hundreds in flight: 1.5 TB/s), whereas two streaming
+// kernels with a small scan between them run at memory speed although the keys are evaluated again for the run heads:
+//   runs_flags_kernel  head flags -> one bit word per 32 elements + the head count of every tile
+//   (exclusive scan of the tile counts; its kernel posts the number of runs to the host)
+//   runs_emit2_kernel  run index of every element from the bit words, emit for the heads
+template <typename KeyFn>
+__global__ void __launch_bounds__(RUNS_THREADS) runs_flags_kernel(KeyFn key, uint32_t n, uint32_t* __restrict__ flag_words,
+                                                                  uint32_t* __restrict__ tile_cnt) {
+    __shared__ uint32_t s_w[RUNS_THREADS / 32];
+    const uint32_t tile = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t wbase = tile * RUNS_TILE + warp * (32 * RUNS_ITEMS);
+    uint32_t masks[RUNS_ITEMS];
+    uint64_t keys[RUNS_ITEMS];
+    runs_warp_flags(key, wbase, n, lane, masks, keys);
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int j = 0; j < RUNS_ITEMS; ++j) {
+        cnt += __popc(masks[j]);
+        if (lane == j && wbase + 32 * j < n) flag_words[(wbase >> 5) + j] = masks[j];
+    }
+    if (lane == 0) s_w[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < RUNS_THREADS / 32; ++w) t += s_w[w];
+        tile_cnt[tile] = t;
+    }
+}
+
+template <typename KeyFn, typename EmitFn>
+__global__ void __launch_bounds__(RUNS_THREADS) runs_emit2_kernel(KeyFn key, EmitFn emit, uint32_t n, uint32_t num_tiles,
+                                                                  const uint32_t* __restrict__ flag_words,
+                                                                  const uint32_t* __restrict__ tile_off,
+                                                                  const unsigned long long* __restrict__ d_total,
+                                                                  uint32_t* __restrict__ run_of_pos, uint32_t* __restrict__ sentinel) {
+    __shared__ uint32_t s_w[RUNS_THREADS / 32];
+    const uint32_t tile = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t wbase = tile * RUNS_TILE + warp * (32 * RUNS_ITEMS);
+    uint32_t masks[RUNS_ITEMS];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int j = 0; j < RUNS_ITEMS; ++j) {
+        masks[j] = wbase + 32 * j < n ? flag_words[(wbase >> 5) + j] : 0u;
+        cnt += __popc(masks[j]);
+    }
+    if (lane == 0) s_w[warp] = cnt;
+    __syncthreads();
+    uint32_t run = tile_off[tile];
+#pragma unroll
+    for (int w = 0; w < RUNS_THREADS / 32; ++w)
+        if (w < warp) run += s_w[w];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < RUNS_ITEMS; ++j) {
+        const uint32_t i = wbase + 32 * j + lane;
+        const bool head = (masks[j] >> lane) & 1u;
+        const uint32_t mine = run + __popc(masks[j] & lt) + (head ? 1u : 0u) - 1u;
+        if (i < n) {
+            if (run_of_pos) run_of_pos[i] = mine;
+            if (head) emit(mine, i, key(i));
+        }
+        run += __popc(masks[j]);
+    }
+    if (tile == num_tiles - 1 && threadIdx.x == 0 && sentinel) sentinel[*d_total] = n;
+}
+constexpr size_t RUNS_TWO_PASS_MIN = (size_t)1 << 20;
+
 // Segments [0, n) into maximal runs of equal key: calls emit(run, first position, key) per run, writes run_of_pos[i]
 // (may be nullptr) and the number of runs to d_total (device, 64-bit).  Run tables must hold the caller's upper bound.
 // `sentinel` (may be nullptr): a run-start table whose entry [number of runs] is set to n by the kernel itself, so that
@@ -529,6 +600,19 @@ inline void segment_runs(Ctx& c, KeyFn key, EmitFn emit, size_t n, uint32_t* run
                          uint32_t* sentinel = nullptr, const Mail& mail = Mail{}) {
     OL_REQUIRE(n > 0, OL_ERR_INTERNAL, "segment_runs: empty input");
     const size_t tiles = (n + RUNS_TILE - 1) / RUNS_TILE;
+    static const bool one_pass = getenv("OL_RUNS_ONE_PASS") != nullptr;  // debug / A-B: the chained kernel for every size
+    if (n >= RUNS_TWO_PASS_MIN && !one_pass) {
+        OL_REQUIRE(d_total != nullptr, OL_ERR_INTERNAL, "segment_runs: the two-pass form needs a device total");
+        DevBuf<uint32_t> flag_words(c, (n + 31) / 32), tile_cnt(c, tiles);
+        runs_flags_kernel<KeyFn><<<(unsigned)tiles, RUNS_THREADS, 0, c.stream>>>(key, (uint32_t)n, flag_words.get(), tile_cnt.get());
+        OL_CHECK_LAUNCH();
+        transform_scan<uint32_t>(c, ScanPtrIn<uint32_t>{tile_cnt.get()}, ScanPtrOut<uint32_t>{tile_cnt.get()}, tiles, d_total, "scan", mail);
+        runs_emit2_kernel<KeyFn, EmitFn><<<(unsigned)tiles, RUNS_THREADS, 0, c.stream>>>(key, emit, (uint32_t)n, (uint32_t)tiles,
+                                                                                         flag_words.get(), tile_cnt.get(), d_total,
+                                                                                         run_of_pos, sentinel);
+        OL_CHECK_LAUNCH();
+        return;
+    }
     DevBuf<unsigned long long> own;
     unsigned long long* status = c.status_words(2 * tiles + 1);
     if (!status) {

@@ -383,7 +383,7 @@ class Forest:
         return dict(cell=cell, pose=pose)
 
     def export_leaves(self) -> dict:
-        st = self.stats()
+        st = self.stats(light=True)  # the leaf count needs no derived table (a full stats call rebuilds the block table)
         L = st["n_leaves"]
         corner = self._host_array((L, 3), np.float64)
         edge = self._host_array(L, np.float64)
