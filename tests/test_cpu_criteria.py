@@ -117,3 +117,47 @@ def test_filter_rejects_size_guards():
     with pytest.raises(NotImplementedError):
         grid.filter([MaxPoints(3, min_edge=1.0)])
     grid.filter([MinPoints(1)])
+
+
+def test_count_thresholds_skip_the_probing():
+    """`any(len(points) > n_i)` goes to the device as `count > min(n_i)` without a single probe call."""
+    from octreelib_b200._host import ForestHost
+
+    calls = []
+
+    class RecordingForest:
+        def subdivide(self, threshold, idx):
+            calls.append((threshold, idx))
+
+    host = ForestHost(1.0, (0.0, 0.0, 0.0), single_cell=False)
+    host.pose_numbers = [0]
+    host._forest = RecordingForest()
+    host.subdivide([MaxPoints(100), MaxPoints(40), MaxPoints(70)])
+    assert calls == [(40, None)]
+
+
+def test_folded_lambdas_are_memoised_only_when_self_contained():
+    from octreelib_b200 import criteria as C
+
+    C._fold_memo.clear()
+    def seventeen():  # the same lambda EXPRESSION evaluated again: a new function object with the same code
+        return lambda pts: len(pts) > 17
+
+    t1, b1 = C.fold_count_criteria([seventeen()], "any", 64)
+    assert len(C._fold_memo) == 1
+    t2, b2 = C.fold_count_criteria([seventeen()], "any", 64)
+    assert len(C._fold_memo) == 1 and (t1 == t2).all() and b1 == b2 and C.as_threshold(t2, b2) == 17
+
+    def make(n):
+        return lambda pts: len(pts) > n
+
+    ta, _ = C.fold_count_criteria([make(5)], "any", 64)
+    tb, _ = C.fold_count_criteria([make(9)], "any", 64)   # same code, different closure value: a different entry
+    assert C.as_threshold(ta, True) == 5 and C.as_threshold(tb, True) == 9
+
+    before = len(C._fold_memo)
+    C.fold_count_criteria([lambda pts: len(pts) > _MODULE_LEVEL_N], "any", 64)  # reads module state: never memoised
+    assert len(C._fold_memo) == before
+
+
+_MODULE_LEVEL_N = 21
