@@ -165,6 +165,16 @@ int ol_forest_apply_mask(ol_forest *f);
 int ol_forest_apply_pose_mask(ol_forest *f, const int32_t *pose_rank, int32_t pose_index, const uint8_t *mask_host,
                               int64_t n);
 
+/* Octree.subdivide_as / OctreeNode.subdivide_as (octree/octree.py:34-53, 222-227): copy the subdivision scheme of one
+ * octree onto another.  ol_forest_export_shape lists the split nodes of a forest (cell coordinates q[n][3], depth, Morton
+ * path from the cell root: 3 bits per level); with NULL arrays only *out_n is written.  ol_forest_impose_shape makes
+ * exactly the listed nodes the split nodes of the target (rebuilt from its cell roots the next time the shape is
+ * needed): nodes the target lacks are split, nodes the list lacks are collapsed, points are re-routed; n = 0 collapses
+ * every cell to one leaf.  Depth limit: 9 levels.  (The reference forgets to put a collapsed node back into its leaf
+ * list, octree.py:48-53; this library keeps it, like the CPU oracle.) */
+int ol_forest_export_shape(ol_forest *f, int64_t *q, uint32_t *depth, uint64_t *path, int64_t *out_n);
+int ol_forest_impose_shape(ol_forest *f, const int64_t *q, const uint32_t *depth, const uint64_t *path, int64_t n);
+
 /* ---- measurement support (bench.py): per-stage CUDA-event timers on the forest's stream -------
  * ol_forest_profile(f, 1) clears and enables the timers; ol_forest_profile_read synchronises, writes
  * one line "stage_name launches total_ms" per stage into buf and clears the records.

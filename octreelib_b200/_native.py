@@ -69,6 +69,8 @@ SIGNATURES = {
     "ol_forest_subdivide": (C.c_int, [_p, _i64, _p, _i32]),
     "ol_forest_subdivide_table": (C.c_int, [_p, _p, _i64, _i32, _p, _i32]),
     "ol_forest_subdivide_levels": (C.c_int, [_p, _p, _i32, _p, _p, _i64, _p, _p, _i32]),
+    "ol_forest_export_shape": (C.c_int, [_p, _p, _p, _p, C.POINTER(_i64)]),
+    "ol_forest_impose_shape": (C.c_int, [_p, _p, _p, _p, _i64]),
     "ol_forest_filter": (C.c_int, [_p, _p, _i64, _p, _i32]),
     "ol_forest_ransac": (C.c_int, [_p, _p, _i32, _i32, _f64, _p, _i32, _i32, _u32, _p]),
     "ol_forest_pose_point_counts": (C.c_int, [_p, _p]),

@@ -227,6 +227,25 @@ int ol_forest_subdivide_levels(ol_forest* f, const int32_t* first_level, int32_t
     OL_API_END
 }
 
+int ol_forest_export_shape(ol_forest* f, int64_t* q, uint32_t* depth, uint64_t* path, int64_t* out_n) {
+    OL_NEED(f);
+    OL_NEED(out_n);
+    OL_API_BEGIN
+    ForestScope scope(f->impl);
+    *out_n = (int64_t)f->impl.export_shape(reinterpret_cast<long long*>(q), depth, reinterpret_cast<unsigned long long*>(path));
+    OL_API_END
+}
+
+int ol_forest_impose_shape(ol_forest* f, const int64_t* q, const uint32_t* depth, const uint64_t* path, int64_t n) {
+    OL_NEED(f);
+    OL_API_BEGIN
+    OL_REQUIRE(n >= 0 && n < (1ll << 29), OL_ERR_INVALID, "bad node count");
+    OL_REQUIRE(n == 0 || (q && depth && path), OL_ERR_INVALID, "NULL shape arrays");
+    ForestScope scope(f->impl);
+    f->impl.impose_shape(reinterpret_cast<const long long*>(q), depth, reinterpret_cast<const unsigned long long*>(path), (uint32_t)n);
+    OL_API_END
+}
+
 int ol_forest_filter(ol_forest* f, const uint8_t* keep_table_host, int64_t table_len, const int32_t* pose_indices,
                      int32_t n_poses) {
     OL_NEED(f);

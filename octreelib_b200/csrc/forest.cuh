@@ -221,6 +221,8 @@ struct Forest {
     void read_back(std::initializer_list<ReadItem> items);
     void throw_device_errors(uint32_t e);
     void note_ransac_flags(uint32_t e);
+    uint32_t export_shape(long long* q_host, uint32_t* depth_host, unsigned long long* path_host);  // NULL: count only
+    void impose_shape(const long long* q_host, const uint32_t* depth_host, const unsigned long long* path_host, uint32_t n);
     void save_shape();       // record the split nodes before a rebuild
     void replay_shape();     // impose the recorded shape on the rebuilt grid
     void ensure_shape();

@@ -812,6 +812,49 @@ void Forest::save_shape() {
     replay_pending = true;
 }
 
+// The shape as data: the split (internal) nodes by cell coordinates, depth and Morton path.  `Octree.subdivide_as`
+// (octree.py:34-53, 222-227) copies one octree's subdivision scheme onto another: export the one, impose it on the other.
+uint32_t Forest::export_shape(long long* q_host, uint32_t* depth_host, unsigned long long* path_host) {
+    ensure_shape();
+    if (!q_host || I == 0) return I;
+    OL_REQUIRE(depth_reached <= REPLAY_MAX_DEPTH, OL_ERR_STATE,
+               "exporting the shape of a tree deeper than " + std::to_string(REPLAY_MAX_DEPTH) + " levels is not supported");
+    DevBuf<long long> q(ctx, (size_t)I * 3);
+    DevBuf<uint32_t> d(ctx, I);
+    DevBuf<uint64_t> p(ctx, I);
+    save_shape_kernel<<<nblk(I), 256, 0, ctx.stream>>>(I, icell.get(), idepth.get(), ipath.get(), cell_key.get(), kp, q.get(), d.get(), p.get());
+    OL_CHECK_LAUNCH();
+    d2h(ctx, q_host, q.get(), (size_t)I * 3);
+    d2h(ctx, depth_host, d.get(), I);
+    d2h(ctx, reinterpret_cast<uint64_t*>(path_host), p.get(), I);
+    ctx.sync();
+    return I;
+}
+
+// The next time the shape is needed it is rebuilt from the cell roots and exactly the listed nodes are split (where the
+// forest has them: cells it does not hold, and nodes below an unlisted parent, are ignored); n = 0 collapses everything.
+void Forest::impose_shape(const long long* q_host, const uint32_t* depth_host, const unsigned long long* path_host, uint32_t n) {
+    for (uint32_t i = 0; i < n; ++i)
+        OL_REQUIRE(depth_host[i] < (uint32_t)REPLAY_MAX_DEPTH, OL_ERR_INVALID,
+                   "a shape deeper than " + std::to_string(REPLAY_MAX_DEPTH) + " levels cannot be imposed");
+    materialize_snapshot();
+    sp_n = n;
+    sp_q.reset(ctx, (size_t)std::max<uint32_t>(n, 1) * 3);
+    sp_depth.reset(ctx, std::max<uint32_t>(n, 1));
+    sp_path.reset(ctx, std::max<uint32_t>(n, 1));
+    sp_epoch.release();
+    if (n) {
+        h2d(ctx, sp_q.get(), q_host, (size_t)n * 3);
+        h2d(ctx, sp_depth.get(), depth_host, n);
+        h2d(ctx, sp_path.get(), reinterpret_cast<const uint64_t*>(path_host), n);
+        ctx.sync();  // the host arrays belong to the caller
+    }
+    replay_pending = true;
+    shaped = false;
+    epochs_valid = false;
+    order_valid = blocks_valid = ransac_valid = false;
+}
+
 void Forest::assign_epochs(int epoch, const uint64_t* sorted_keys, const uint32_t* sorted_vals, uint32_t n_saved) {
     iepoch.reset(ctx, I);
     if (I) {

@@ -280,6 +280,28 @@ class Forest:
         self._pending_sources.clear()
         self.version += 1
 
+    def export_shape(self) -> dict:
+        """The split nodes of the forest: cell coordinates, depth and Morton path (`ol_forest_export_shape`)."""
+        n = C.c_int64(0)
+        with self._scope():
+            N.check(self._lib.ol_forest_export_shape(self._h, None, None, None, C.byref(n)))
+        q = np.zeros((n.value, 3), dtype=np.int64)
+        depth = np.zeros(n.value, dtype=np.uint32)
+        path = np.zeros(n.value, dtype=np.uint64)
+        if n.value:
+            with self._scope():
+                N.check(self._lib.ol_forest_export_shape(self._h, _ptr(q), _ptr(depth), _ptr(path), C.byref(n)))
+        return dict(q=q, depth=depth, path=path)
+
+    def impose_shape(self, shape: dict):
+        """Make exactly the listed nodes the split nodes of this forest (`ol_forest_impose_shape`)."""
+        q = np.ascontiguousarray(shape["q"], dtype=np.int64).reshape(-1, 3)
+        depth = np.ascontiguousarray(shape["depth"], dtype=np.uint32)
+        path = np.ascontiguousarray(shape["path"], dtype=np.uint64)
+        with self._scope():
+            N.check(self._lib.ol_forest_impose_shape(self._h, _ptr(q), _ptr(depth), _ptr(path), len(depth)))
+        self.version += 1
+
     def filter(self, keep_table: np.ndarray, pose_indices: Optional[Sequence[int]] = None):
         arr, n = _i32_array(pose_indices)
         tab = np.ascontiguousarray(keep_table, dtype=np.uint8)

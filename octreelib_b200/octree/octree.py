@@ -50,10 +50,22 @@ class _SinglePose:
         self._sync_cache()
 
     def subdivide_as(self, other):
-        """Not part of the native path: copying another octree's shape is what `OctreeManager.subdivide` /
-        `insert_points` do for every pose of a cell (octree_manager.py:65-66, 171) - built into the forest, where all
-        poses of a cell share one leaf table.  A direct call on a stand-alone octree raises."""
-        raise NotImplementedError("copying another octree's shape is driven by OctreeManager in the native build")
+        """Copy the subdivision scheme of another octree / octree node (octree.py:34-53, 222-227): nodes that `other`
+        splits and this tree does not are split, nodes this tree splits and `other` does not are collapsed, the points
+        are re-routed.  Both trees are taken by their own root (the reference does not compare the roots either; the
+        scheme is copied node for node).  Difference by design: the reference forgets to put a COLLAPSED node back into
+        its leaf list (octree.py:48-53), so its points vanish from `get_leaf_points`; here the node stays a leaf."""
+        if not isinstance(other, _SinglePose):
+            raise TypeError("subdivide_as expects an Octree / OctreeNode of this package")
+        if other._host.empty:
+            shape = dict(q=np.zeros((0, 3), np.int64), depth=np.zeros(0, np.uint32), path=np.zeros(0, np.uint64))
+        else:
+            shape = other._host.forest.export_shape()
+        if self._host.empty:
+            return  # nothing stored yet: the reference would create empty children, which hold no points either
+        self._host.forest.impose_shape(shape)
+        self._host._counts_cache = None
+        self._sync_cache()
 
     def get_points(self) -> PointCloud:
         """Stored points in depth-first leaf order (octree.py:55-65); input order while unsplit."""

@@ -250,6 +250,37 @@ class FakeSingleCellForest(FakeForest):
         tree.subdivide_as(tree.root, cell.scheme.root)
         self.version += 1
 
+    # ---- Octree.subdivide_as: the scheme as data (ol_forest_export_shape / ol_forest_impose_shape) ----
+    def export_shape(self):
+        out = []
+
+        def walk(node, depth, path):
+            if node.children is None:
+                return
+            out.append((depth, path))
+            for c, ch in enumerate(node.children):
+                walk(ch, depth + 1, (path << 3) | c)
+
+        walk(self.og.cells[self.key].scheme.root, 0, 0)
+        return dict(q=np.zeros((len(out), 3), np.int64), depth=np.array([d for d, _ in out], np.uint32),
+                    path=np.array([p for _, p in out], np.uint64))
+
+    def impose_shape(self, shape):
+        from oracle.structure import _Tree
+
+        cell = self.og.cells[self.key]
+        skeleton = _Tree(cell.key, cell.edge)
+        for depth, path in sorted(zip(shape["depth"].tolist(), shape["path"].tolist())):
+            node = skeleton.root
+            for level in range(depth):
+                node = node.children[(path >> (3 * (depth - 1 - level))) & 7]
+            if node.children is None:
+                skeleton._generate_children(node)
+        cell.scheme = skeleton
+        for tree in cell.trees.values():
+            tree.subdivide_as(tree.root, skeleton.root)
+        self.version += 1
+
     def insert(self, points):
         pose = len(self.clouds)
         pts = np.asarray(points, dtype=np.float64).reshape(-1, 3)

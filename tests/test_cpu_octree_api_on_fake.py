@@ -96,8 +96,15 @@ def test_octree():
     assert octree.n_leaves == 3 and octree.n_points == 5 and octree.n_nodes == 17
     octree.filter([lambda points: len(points) >= 2])
     assert octree.n_points == 4
-    with pytest.raises(NotImplementedError):
-        octree.subdivide_as(octree)
+    octree.subdivide_as(octree)  # its own scheme: nothing changes
+    assert octree.n_leaves == 2 and octree.n_points == 4 and octree.n_nodes == 17
+    other = Octree(OctreeConfig(), np.array([0, 0, 0]), np.float64(10))
+    other._host._forest = FakeSingleCellForest(np.float64(10), np.array([0, 0, 0]))
+    other.insert_points(_CLOUD)
+    other.subdivide_as(octree)   # octree.py:34-53: the other tree's scheme, this tree's points
+    assert other.n_nodes == 17 and other.n_points == 5 and other.n_leaves == 3
+    with pytest.raises(TypeError):
+        other.subdivide_as("not an octree")
 
 
 def test_octree_node():

@@ -160,3 +160,21 @@ def test_degenerate_hypothesis_wins():
     pts = np.tile(np.array([[1.0, 2.0, 3.0]]), (8, 1))
     res = oransac.ransac_evaluate(pts, np.array([8], dtype=np.int32), oransac.make_table(16, 6, seed=1), 0.01, full=True)
     assert res["best"][0] == 0 and res["best_count"][0] == 8 and (res["plane"][0] == 0).all() and res["mask"].all()
+
+
+def test_oracle_subdivide_as_matches_the_reference_fixture():
+    """tests/golden/subdivide_as_edge16.npz (tests/golden/make_subdivide_as.py, real reference): B copies A's scheme."""
+    from oracle.structure import _Tree
+
+    g = golden("subdivide_as_edge16")
+    corner, edge = g["corner"], np.float64(g["edge"])
+    ta, tb = _Tree(corner, edge), _Tree(corner, edge)
+    ta.insert(ta.root, np.arange(len(g["a"])), g["a"])
+    ta.subdivide(ta.root, [lambda p: len(p) > int(g["max_points"])])
+    tb.insert(tb.root, np.arange(len(g["b"])), g["b"])
+    tb.subdivide_as(tb.root, ta.root)
+    leaves = [n for n in tb.cache.values() if len(n.idx)]
+    assert [len(n.idx) for n in leaves] == g["b_sizes"].tolist()
+    assert (np.array([n.corner for n in leaves], dtype=np.float64) == g["b_corner"]).all()
+    assert (np.vstack([n.pts for n in leaves]) == g["b_points"]).all()
+    assert tb.n_nodes() == int(g["b_n_nodes"])
