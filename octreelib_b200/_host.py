@@ -140,41 +140,91 @@ class ForestHost:
     # ---- generic per-leaf callback (grid.py:111-122 -> octree_manager.py:68-83 -> octree.py:114-123) -----
     def map_leaf_points(self, function: Callable, pose_numbers: Optional[Sequence[int]] = None):
         """Host-callback compatibility path: every non-empty (pose, leaf) block is copied to the
-        host, handed to the opaque Python `function`, and the result is written back.  The forest stores points
-        by reference into the inserted clouds, so the result must be a selection of the leaf's own rows (the
-        reference's tests use `lambda cloud: [cloud[0]]`); a function that invents new coordinates raises
-        NotImplementedError.  Like the reference, empty leaves are skipped and unknown poses are ignored."""
+        host, handed to the opaque Python `function`, and the result replaces the block's points
+        (grid.py:111-122 -> octree_manager.py:68-83 -> octree.py:114-123).  Like the reference, empty leaves are skipped
+        and unknown poses are ignored.
+
+        * A result that is a SELECTION of the leaf's own rows (the reference's tests use `lambda cloud: [cloud[0]]`)
+          becomes a keep-mask on the device (K7 compaction).
+        * Any other result (new coordinates, more or fewer points: centroids, projections onto a fitted plane, ...)
+          replaces the block: its old points are removed and the new ones are appended to the same pose, after which the
+          grid is rebuilt with the SAME shape (the scheme replay that also serves poses inserted after a subdivision,
+          octree_manager.py:171).  Every new point must lie inside the leaf it was produced from - the forest finds a
+          point's leaf from its coordinates, whereas the reference would keep a stray point in the old leaf object until
+          the next subdivide mis-routes it (octree.py:94-98); a result that leaves its leaf raises NotImplementedError
+          before anything is changed."""
         if self.empty:
             return
         numbers = list(self.pose_numbers) if pose_numbers is None else [p for p in pose_numbers if p in self.pose_index]
-        blocks = _views.tables(self.forest)["blocks"]
+        tabs = _views.tables(self.forest)
+        blocks, leaves = tabs["blocks"], tabs["leaves"]
         plan = []
         for number in numbers:
             idx = self.pose_index[number]
-            sizes = blocks["size"][blocks["pose"] == idx].astype(np.int64)
+            sel = np.flatnonzero(blocks["pose"] == idx)
+            sizes = blocks["size"][sel].astype(np.int64)
             if sizes.sum() == 0:
                 continue
             xyz = self.forest.export_points(idx, order=0, n_hint=int(sizes.sum()))["xyz"]
             mask = np.zeros(len(xyz), dtype=bool)
+            fresh, expect = [], []   # replacement clouds in block order / what the pose must hold afterwards
             start = 0
-            for n in sizes:
+            for b, n in zip(sel, sizes):
                 block = xyz[start:start + n]
                 res = np.asarray(function(block.copy()), dtype=np.float64).reshape(-1, 3)
-                j = 0
-                for row in res:  # the result must be a subsequence of the leaf's rows
-                    while j < n and not (block[j] == row).all():
-                        j += 1
-                    if j == n:
+                keep = self._as_selection(block, res)
+                if keep is not None:
+                    mask[start:start + n] = keep
+                    expect.append((False, block[keep]))
+                else:
+                    leaf = int(blocks["leaf"][b])
+                    if leaves["depth"][leaf] == 0 and not self._single_cell:
+                        cell = int(leaves["cell"][leaf])
+                        lo = np.asarray(tabs["cells"]["corner"][cell], dtype=np.float64)
+                        edge = float(self._edge)
+                    elif leaves["depth"][leaf] == 0:
+                        lo, edge = np.asarray(self._corner, dtype=np.float64).reshape(3), float(self._edge)
+                    else:
+                        lo, edge = np.asarray(leaves["corner"][leaf], dtype=np.float64), float(leaves["edge"][leaf])
+                    if not np.isfinite(res).all() or ((res < lo) | (res >= lo + edge)).any():
                         raise NotImplementedError(
-                            "map_leaf_points: the function returned points that are not a selection of the leaf's own "
-                            "points; coordinate-changing maps are outside the GPU path (DESIGN.md section 8)")
-                    mask[start + j] = True
-                    j += 1
+                            "map_leaf_points: the function returned points outside the leaf they were computed from; the "
+                            "native grid locates a point by its coordinates (DESIGN.md section 8)")
+                    fresh.append(res)
+                    expect.append((True, res))
                 start += n
-            plan.append((idx, mask))
-        for idx, mask in plan:
+            plan.append((idx, mask, fresh, expect))
+        for idx, mask, fresh, expect in plan:
             self.forest.apply_pose_mask(idx, mask)
+            if fresh:
+                new = np.ascontiguousarray(np.vstack(fresh))
+                if len(new):
+                    self.forest.insert_segments(new, [len(new)], [idx], [self.pose_inserted[idx]], len(self.pose_numbers))
+                    self.pose_inserted[idx] += len(new)
         self._counts_cache = None
+        for idx, mask, fresh, expect in plan:
+            if not fresh:
+                continue
+            # the rebuilt grid must hold, leaf by leaf, exactly what the reference would hold
+            want = np.vstack([np.empty((0, 3))] + [pts for _, pts in expect])
+            got = self.forest.export_points(idx, order=0)["xyz"]
+            if got.shape != want.shape or not (got == want).all():
+                raise RuntimeError("map_leaf_points: a replaced point changed its leaf during the rebuild (a point on a leaf "
+                                   "boundary); the grid no longer matches the reference's result")
+
+    @staticmethod
+    def _as_selection(block: np.ndarray, res: np.ndarray):
+        """keep-mask if `res` is a subsequence of the rows of `block` (bit-equal rows, in order), else None"""
+        keep = np.zeros(len(block), dtype=bool)
+        j, n = 0, len(block)
+        for row in res:
+            while j < n and not (block[j] == row).all():
+                j += 1
+            if j == n:
+                return None
+            keep[j] = True
+            j += 1
+        return keep
 
     # ---- counters (grid.py:343-362) --------------------------------------------------------------
     def counts(self) -> np.ndarray:
