@@ -9,7 +9,7 @@ from typing import Callable, Dict, List, Optional, Sequence
 import numpy as np
 
 from . import _views
-from .criteria import CountCriterion, as_threshold, fold_count_criteria, fold_levels
+from .criteria import CountCriterion, NotCountOnly, as_threshold, fold_count_criteria, fold_levels
 from .forest import Forest
 
 __all__ = ["ForestHost"]
@@ -89,7 +89,16 @@ class ForestHost:
         # [(first level, table, beyond, criteria active from that level on)]; one entry unless node-size guards are used
         levels = fold_levels(criteria, float(self._edge), 1024) if guarded else None
         if levels is None:
-            table, beyond = fold_count_criteria(criteria, "any", 1024)
+            try:
+                table, beyond = fold_count_criteria(criteria, "any", 1024)
+            except NotCountOnly:
+                # opaque criteria (they look at coordinates): the scheme is worked out on the host, node by node like the
+                # reference does, and imposed on the device (the partition itself still runs there)
+                # (the native forest does not count an imposed scheme as a subdivide call: the history-dependent leaf
+                # order of a SECOND subdivide, DESIGN.md section 8, is only tracked for device-evaluated criteria)
+                self._subdivide_on_host(criteria, idx)
+                self._counts_cache = None
+                return
             levels = [(0, table, beyond, criteria)]
         thresholds = [as_threshold(t, b, active) if active else (1 << 62) for _, t, b, active in levels]
         firsts = [lv[0] for lv in levels]
@@ -128,7 +137,12 @@ class ForestHost:
             raise NotImplementedError("node-size guards (max_depth / min_edge) apply to subdivision criteria, not to filters")
         max_block = self.forest.stats()["max_block_size"]
         upto = min(max_block + 1, _TABLE_CAP)
-        table, beyond = fold_count_criteria(criteria, "all", upto)
+        try:
+            table, beyond = fold_count_criteria(criteria, "all", upto)
+        except NotCountOnly:
+            self._filter_on_host(list(criteria), idx)
+            self._counts_cache = None
+            return
         if upto <= max_block:  # blocks larger than the table share its last entry
             if beyond is None:
                 raise NotImplementedError("count criterion without a settled answer for very large leaves")
@@ -136,6 +150,79 @@ class ForestHost:
         # an EMPTY leaf is also "filtered" by the reference, which changes nothing
         self.forest.filter(table, idx)
         self._counts_cache = None
+
+    # ---- opaque (coordinate-dependent) criteria: evaluated on the host like the reference does -------------------------
+    _HOST_SCHEME_MAX_DEPTH = 9  # what ol_forest_impose_shape can replay
+
+    def _subdivide_on_host(self, criteria: Sequence[Callable], idx: Optional[List[int]]):
+        """OctreeManager.subdivide with criteria the device cannot evaluate (octree_manager.py:36-66): per cell a scheme
+        octree over the points of the listed poses (pose after pose, input order: octree_manager.py:57-61), split while any
+        criterion holds (octree.py:20-32) with the reference's own routing arithmetic (octree.py:73-75, 94-97, 181-190),
+        and the resulting set of split nodes imposed on the forest (`ol_forest_impose_shape`)."""
+        forest = self.forest
+        poses = list(range(len(self.pose_numbers))) if idx is None else list(idx)
+        rows = []
+        for p in poses:
+            e = forest.export_points(p, order=1)
+            if len(e["idx"]):
+                rows.append((e["cell"].astype(np.int64), np.full(len(e["idx"]), poses.index(p), dtype=np.int64), e["idx"], e["xyz"]))
+        if not rows:
+            forest.impose_shape(dict(q=np.zeros((0, 3), np.int64), depth=np.zeros(0, np.uint32), path=np.zeros(0, np.uint64)))
+            return
+        cell = np.concatenate([r[0] for r in rows])
+        order = np.lexsort((np.concatenate([r[2] for r in rows]), np.concatenate([r[1] for r in rows]), cell))
+        cell, xyz = cell[order], np.vstack([r[3] for r in rows])[order]
+        cells = _views.tables(forest)["cells"]
+        out_q, out_depth, out_path = [], [], []
+
+        def split(points, corner, edge, q, depth, path):
+            if not any([criterion(points) for criterion in criteria]):
+                return
+            if depth >= self._HOST_SCHEME_MAX_DEPTH:
+                raise RecursionError(f"subdivision criterion still true {depth} levels below the grid cell "
+                                     "(host-evaluated criteria are limited to 9 levels)")
+            out_q.append(q)
+            out_depth.append(depth)
+            out_path.append(path)
+            half = edge / np.float64(2)
+            sub = ((points - corner) // half).astype(int)
+            if ((sub < 0) | (sub > 1)).any():
+                raise IndexError("point outside of its octree node (reference: octree.py:98)")
+            child = sub[:, 0] * 4 + sub[:, 1] * 2 + sub[:, 2]
+            for c in range(8):
+                off = np.array([(c >> 2) & 1, (c >> 1) & 1, c & 1]) * half
+                split(points[child == c], corner + off, half, q, depth + 1, (path << 3) | c)
+
+        bounds = np.flatnonzero(np.diff(cell)) + 1
+        for lo, hi in zip(np.concatenate([[0], bounds]), np.concatenate([bounds, [len(cell)]])):
+            k = int(cell[lo])
+            if self._single_cell:
+                corner, q = np.asarray(self._corner, dtype=np.float64).reshape(3), (0, 0, 0)
+            else:
+                corner, q = np.asarray(cells["corner"][k], dtype=np.float64), tuple(int(v) for v in cells["q"][k])
+            split(xyz[lo:hi], corner, np.float64(self._edge), q, 0, 0)
+        forest.impose_shape(dict(q=np.array(out_q, dtype=np.int64).reshape(-1, 3), depth=np.array(out_depth, dtype=np.uint32),
+                                 path=np.array(out_path, dtype=np.uint64)))
+
+    def _filter_on_host(self, criteria: Sequence[Callable], idx: Optional[List[int]]):
+        """filter with opaque criteria (octree.py:102-112): every non-empty (pose, leaf) block goes to the host, the
+        blocks for which not all criteria hold are emptied (keep-mask per pose -> K7 compaction)."""
+        poses = list(range(len(self.pose_numbers))) if idx is None else list(idx)
+        blocks = _views.tables(self.forest)["blocks"]
+        plan = []
+        for p in poses:
+            sizes = blocks["size"][blocks["pose"] == p].astype(np.int64)
+            if sizes.sum() == 0:
+                continue
+            xyz = self.forest.export_points(p, order=0, n_hint=int(sizes.sum()))["xyz"]
+            mask = np.zeros(len(xyz), dtype=bool)
+            start = 0
+            for n in sizes:
+                mask[start:start + n] = all([criterion(xyz[start:start + n].copy()) for criterion in criteria])
+                start += n
+            plan.append((p, mask))
+        for p, mask in plan:
+            self.forest.apply_pose_mask(p, mask)
 
     # ---- generic per-leaf callback (grid.py:111-122 -> octree_manager.py:68-83 -> octree.py:114-123) -----
     def map_leaf_points(self, function: Callable, pose_numbers: Optional[Sequence[int]] = None):

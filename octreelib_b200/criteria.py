@@ -11,7 +11,8 @@ and docs is (`lambda points: len(points) > 100`):
   * `MaxPoints(n)` / `MinPoints(n)` are declarative callables (usable with the reference too);
   * any other callable is probed with (n,3) arrays of several sizes - constant-filled ones and two random clouds of
     different spread; if its answers depend on the size only, the resulting truth table is used.
-    Criteria that look at coordinates are rejected (NotImplementedError) -- no CPU fallback.
+    Criteria that look at coordinates are never folded (NotCountOnly): `subdivide` / `filter` then evaluate them on the
+    host node by node, like the reference, and impose the resulting scheme / keep-masks on the device (_host.py).
 
 Size thresholds.  The reference hands a criterion nothing but the points, so "stop splitting below a node size" cannot
 be written as a pure function of its argument; the declarative criteria therefore carry optional NODE-SIZE guards:
@@ -31,7 +32,14 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import numpy as np
 
 __all__ = ["MaxPoints", "MinPoints", "MaxDepth", "MinEdge", "CountCriterion", "fold_count_criteria", "as_threshold",
-           "fold_levels", "NO_LEVEL_LIMIT"]
+           "fold_levels", "NO_LEVEL_LIMIT", "NotCountOnly"]
+
+
+class NotCountOnly(NotImplementedError):
+    """A criterion could not be folded into a function of the point count (it looks at coordinates, or it failed on the
+    probe arrays).  `Grid.subdivide` / `filter` then evaluate it on the host, node by node, like the reference does, and
+    hand the resulting scheme / keep-masks to the device (ForestHost._subdivide_on_host); callers that need a
+    device-evaluable rule (node-size guards) let it propagate as the NotImplementedError it is."""
 
 NO_LEVEL_LIMIT = 1 << 20  # "may split at every level"
 
@@ -239,14 +247,14 @@ def _eval(criterion: Callable, n: int) -> bool:
         if n <= _SPREAD_CAP:
             answers += [bool(criterion(_spread_probe(n, 0))), bool(criterion(_spread_probe(n, 1)))]
     except Exception as exc:  # noqa: BLE001
-        raise NotImplementedError(
+        raise NotCountOnly(
             "octreelib_b200 evaluates subdivision / filtering criteria on the GPU as functions of the point count; "
             f"criterion {criterion!r} failed on a probe array of {n} points ({exc!r}). Use criteria such as "
             "`lambda points: len(points) > N` or octreelib_b200.criteria.MaxPoints / MinPoints.") from exc
     if len(set(answers)) != 1:
-        raise NotImplementedError(
+        raise NotCountOnly(
             f"criterion {criterion!r} depends on the point coordinates, not only on the point count; "
-            "coordinate-dependent criteria are not supported by the GPU path (there is no CPU fallback)")
+            "coordinate-dependent criteria cannot be evaluated on the GPU")
     return answers[0]
 
 

@@ -100,6 +100,36 @@ class FakeForest:
         self.og.subdivide([crit], pose_indices)
         self._after_subdivide()
 
+    def impose_shape(self, shape):
+        """ol_forest_impose_shape: exactly the listed nodes (cell coordinates, depth, Morton path) become the split nodes"""
+        from oracle.structure import _Tree
+
+        keys, cells, _, _ = self._tables()
+        by_q = {tuple(int(v) for v in cells["q"][i]): keys[i] for i in range(len(keys))}
+        wanted = {key: [] for key in keys}
+        for q, depth, path in zip(np.asarray(shape["q"]).reshape(-1, 3).tolist(), shape["depth"].tolist(), shape["path"].tolist()):
+            key = by_q.get(tuple(int(v) for v in q))
+            if key is not None:
+                wanted[key].append((int(depth), int(path)))
+        for key in keys:
+            cell = self.og.cells[key]
+            skeleton = _Tree(cell.key, cell.edge)
+            for depth, path in sorted(wanted[key]):
+                node = skeleton.root
+                for level in range(depth):
+                    node = None if node is None or node.children is None else node.children[(path >> (3 * (depth - 1 - level))) & 7]
+                if node is not None and node.children is None:
+                    skeleton._generate_children(node)
+            cell.scheme = skeleton
+            for tree in cell.trees.values():
+                tree.subdivide_as(tree.root, skeleton.root)
+        old, self.node_epoch = self.node_epoch, {}
+        for key in keys:
+            root, _ = self._shape(key)
+            for path in _internal_paths(root):
+                self.node_epoch[(key, path)] = old.get((key, path), max(self.n_subdivides, 1))
+        self.version += 1
+
     def filter(self, keep_table, pose_indices=None):
         table = np.asarray(keep_table)
         self.og.filter([lambda pts: bool(table[min(len(pts), len(table) - 1)])], pose_indices)

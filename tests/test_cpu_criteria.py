@@ -42,19 +42,35 @@ def test_step_detection_does_not_invent_thresholds():
 @pytest.mark.parametrize("crit", [
     lambda p: len(p) > 3 and np.ptp(p, axis=0).max() > 0.5,          # extent: translation invariant
     lambda p: len(p) > 3 and p.std(axis=0).max() > 0.1,              # spread
-    lambda p: len(p) > 0 and p[:, 0].mean() > 1.0,                   # position
+    lambda p: len(p) > 6 and p[:, 0].mean() > 1.0,                   # position
     lambda p: len(p) > 3 and np.linalg.eigvalsh(np.cov(p.T))[0] > 1e-4,  # planarity
 ])
-def test_coordinate_dependent_criteria_are_rejected(crit):
+def test_coordinate_dependent_criteria_are_not_folded_but_evaluated_on_the_host(crit):
+    """They never become a count table (no silent wrong answer); `subdivide` / `filter` evaluate them on the host node by
+    node, like the reference, and hand the scheme / the keep-masks to the forest - checked here against the oracle, which
+    evaluates the same callables the way the reference does."""
+    from oracle.structure import OracleGrid
+
     with pytest.raises(NotImplementedError):
         fold_count_criteria([crit], "any", 64)
+    cloud = np.random.default_rng(0).random((300, 3)) * np.array([7.5, 3.0, 2.0])
     grid = Grid(GridConfig(voxel_edge_length=4))
     grid._host._forest = FakeForest(4)
-    grid.insert_points(0, np.random.default_rng(0).random((50, 3)))
-    with pytest.raises(NotImplementedError):
-        grid.subdivide([crit])
-    with pytest.raises(NotImplementedError):
-        grid.filter([crit])
+    grid.insert_points(0, cloud)
+    og = OracleGrid(4)
+    og.insert_points(0, cloud)
+    grid.subdivide([crit])
+    og.subdivide([crit])
+
+    def table(leaves, corner, edge, pts):
+        return [(tuple(np.asarray(corner(l), dtype=float)), float(edge(l)), np.asarray(pts(l)).tolist()) for l in leaves]
+
+    want = table(og.get_leaf_points(0), lambda l: l.corner, lambda l: l.edge, lambda l: l.points)
+    got = table(grid.get_leaf_points(0), lambda v: v.corner_min, lambda v: v.edge_length, lambda v: v.get_points())
+    assert got == want and grid.n_nodes(0) == og.n_nodes(0)
+    grid.filter([crit])
+    og.filter([crit])
+    assert grid.n_points(0) == og.n_points(0)
 
 
 def test_level_limits():
