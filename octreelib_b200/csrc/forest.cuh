@@ -166,6 +166,8 @@ struct Forest {
     DevBuf<float> res_plane;     // [res_n][4]
     bool snap_pending = false;   // res_* not gathered yet: raw per-block arrays of the last run (block-table order)
     DevBuf<uint32_t> sn_ref_order, sn_leaf;
+    DevBuf<uint32_t> sn_arr_rank, sn_arr_blk;  // sort-free batch layout: (pose rank, block) in arranged order, sorted on demand
+    int sn_rank_bits = 0;
     DevBuf<int32_t> sn_pose, sn_size, sn_best, sn_count;
     DevBuf<float> sn_plane;
     bool sample_oob_seen = false;

@@ -363,7 +363,7 @@ int Forest::insert_batch(const double* const* xyz_dev, const int64_t* sizes, int
     }
     join_uploads();  // (mixed use: host arrays inserted before this batch)
     if (N + total > cap) {
-        // The host hands its clouds over in several batches while it is still inserting (forest.py flushes every 64 poses,
+        // The host hands its clouds over in several batches while it is still inserting (forest.py flushes every 128 poses,
         // so that the copy runs while the host language works through the remaining insert calls).  The final size is
         // not known yet: the point count of the previous build of this process is the first guess (a pipeline builds
         // maps of similar size step after step: no growth copy and no slack in the steady state), geometric growth
@@ -385,7 +385,7 @@ int Forest::insert_batch(const double* const* xyz_dev, const int64_t* sizes, int
         }
         cap = ncap;
     }
-    // chunk length: at least ~16 chunks per SM (a batch of 64 poses is small next to the whole map: with full-size chunks it
+    // chunk length: at least ~16 chunks per SM (a batch of 128 poses is small next to the whole map: with full-size chunks it
     // was 5 CTAs per SM and ran at 60 % of the bandwidth of the single big launch), a multiple of 3, at most INSERT_CHUNK
     unsigned long long chunk_len = (unsigned long long)total * 3ull / ((unsigned long long)ctx.num_sms * 16ull);
     chunk_len = std::min<unsigned long long>(std::max<unsigned long long>(chunk_len / 3ull * 3ull, 3ull * 1024ull), INSERT_CHUNK);

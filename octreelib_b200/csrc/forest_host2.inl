@@ -56,6 +56,135 @@ __global__ void block_arrange_history_kernel(uint32_t nb, const uint32_t* __rest
     vals[dst] = b;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batch layout of the RANSAC kernel WITHOUT sorting the block table (the common case: one subdivide call, at most
+// REFSTART_MAX_RANKS poses).  The reference's start index of block (pose p, leaf l) inside its batch is
+//     [points of the batch's earlier poses] + [points of pose p in the leaves that precede l in enumeration order]
+// (cuda_ransac.py:65-67 over grid.py:173-191).  With the blocks ARRANGED by (leaf enumeration order, pose) - a
+// permutation of whole leaf segments, block_arrange above - the second term is the exclusive prefix, over the arranged
+// slots, of the sizes of the blocks of pose p: a WEIGHTED stable ranking by pose.  Nothing has to move for that:
+//   refstart_count_kernel   per chunk of 4096 arranged slots, the points of every pose rank -> table[rank][chunk]
+//   (flat exclusive scan of the table: table[p][c] becomes points of ranks < p + points of rank p in chunks < c)
+//   refstart_assign_kernel  the same chunks again: ordered prefix inside the chunk (per-warp counters, like the digit
+//                           ranking of the radix sort but weighted with the block sizes) on top of the chunk's start
+// instead of two radix passes over (pose rank, block) pairs, a size gather, a scan over the blocks and a search per
+// block.  The sorted order itself is only needed when somebody asks for the result TABLE of all blocks in reference
+// order (materialize_snapshot): the sort is deferred until then.
+// ---------------------------------------------------------------------------------------------
+constexpr int REFSTART_THREADS = 256;
+constexpr int REFSTART_ROWS = 16;                                   // rows of 32 slots per warp
+constexpr int REFSTART_CHUNK = REFSTART_THREADS * REFSTART_ROWS;    // arranged slots per CTA
+constexpr int REFSTART_MAX_RANKS = 2048;
+
+__global__ void block_arrange2_kernel(uint32_t nb, const uint32_t* __restrict__ blk_leaf, const int32_t* __restrict__ blk_pose,
+                                      const uint32_t* __restrict__ blk_start, const int32_t* __restrict__ pose_rank,
+                                      const uint32_t* __restrict__ cache_rank, const uint32_t* __restrict__ off_c,
+                                      const uint32_t* __restrict__ first_b, uint32_t* __restrict__ a_rank,
+                                      uint32_t* __restrict__ a_size, uint32_t* __restrict__ a_blk, int32_t* __restrict__ blk_size) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const uint32_t leaf = blk_leaf[b];
+    const uint32_t dst = off_c[cache_rank[leaf]] + (b - first_b[leaf]);
+    const uint32_t sz = blk_start[b + 1] - blk_start[b];
+    a_rank[dst] = (uint32_t)pose_rank[blk_pose[b]];
+    a_size[dst] = sz;
+    a_blk[dst] = b;
+    blk_size[b] = (int32_t)sz;
+}
+
+__global__ void __launch_bounds__(REFSTART_THREADS) refstart_count_kernel(uint32_t nb, const uint32_t* __restrict__ a_rank,
+                                                                          const uint32_t* __restrict__ a_size, int n_ranks,
+                                                                          uint32_t n_chunks, uint32_t* __restrict__ table) {
+    extern __shared__ uint32_t s_cnt[];
+    for (int p = threadIdx.x; p < n_ranks; p += REFSTART_THREADS) s_cnt[p] = 0u;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * REFSTART_CHUNK;
+#pragma unroll 4
+    for (int k = 0; k < REFSTART_ROWS; ++k) {
+        const uint32_t j = base + (uint32_t)k * REFSTART_THREADS + threadIdx.x;
+        if (j < nb) atomicAdd(&s_cnt[a_rank[j]], a_size[j]);
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < n_ranks; p += REFSTART_THREADS) table[(size_t)p * n_chunks + blockIdx.x] = s_cnt[p];
+}
+
+// start_by_rank != nullptr: this forest holds only a part of the grid (multi-GPU slab partition) and the host supplied the
+// batch-global index of the first local point of every pose rank; otherwise the start of a rank inside its batch of `ppb`
+// consecutive ranks comes out of the scanned table itself.
+__global__ void __launch_bounds__(REFSTART_THREADS) refstart_assign_kernel(uint32_t nb, uint32_t K, uint32_t ppb,
+                                                                           const uint32_t* __restrict__ a_rank,
+                                                                           const uint32_t* __restrict__ a_size,
+                                                                           const uint32_t* __restrict__ a_blk, int n_ranks,
+                                                                           uint32_t n_chunks, const uint32_t* __restrict__ scanned,
+                                                                           const long long* __restrict__ start_by_rank,
+                                                                           long long* __restrict__ blk_ref_start) {
+    extern __shared__ __align__(8) unsigned char rs_smem[];
+    long long* s_base = reinterpret_cast<long long*>(rs_smem);                        // [n_ranks] start of the rank in this chunk
+    uint32_t* s_w = reinterpret_cast<uint32_t*>(rs_smem + 8 * (size_t)n_ranks);       // [8 warps][n_ranks]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t chunk = blockIdx.x;
+    for (int p = threadIdx.x; p < n_ranks; p += REFSTART_THREADS) {
+        const uint32_t here = scanned[(size_t)p * n_chunks + chunk];
+        if (start_by_rank)
+            s_base[p] = start_by_rank[p] + (long long)(here - scanned[(size_t)p * n_chunks]);
+        else
+            s_base[p] = (long long)(here - scanned[(size_t)(p / ppb * ppb) * n_chunks]);
+    }
+    for (int i = threadIdx.x; i < 8 * n_ranks; i += REFSTART_THREADS) s_w[i] = 0u;
+    __syncthreads();
+    uint32_t* wh = s_w + (size_t)warp * n_ranks;
+    const uint32_t wbase = chunk * REFSTART_CHUNK + (uint32_t)warp * (32 * REFSTART_ROWS);
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t rk[REFSTART_ROWS], sz[REFSTART_ROWS], local[REFSTART_ROWS];
+#pragma unroll
+    for (int r = 0; r < REFSTART_ROWS; ++r) {
+        const uint32_t j = wbase + 32 * r + lane;
+        rk[r] = j < nb ? a_rank[j] : 0xffffffffu;
+        sz[r] = j < nb ? a_size[j] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < REFSTART_ROWS; ++r) {
+        // the lanes with this lane's rank, and the sizes of those before it (slot order = lane order): a few iterations,
+        // consecutive arranged slots are (leaf, pose ascending), so a rank repeats about once per leaf
+        const uint32_t peers = __match_any_sync(0xffffffffu, rk[r]);
+        uint32_t below = peers & lt, mine = 0u;
+        while (__any_sync(0xffffffffu, below != 0u)) {
+            const int src = below ? (__ffs(below) - 1) : lane;
+            const uint32_t v = __shfl_sync(0xffffffffu, sz[r], src);
+            if (below) {
+                mine += v;
+                below &= below - 1u;
+            }
+        }
+        const int leader = __ffs(peers) - 1, last = 31 - __clz(peers);
+        const uint32_t group = __shfl_sync(0xffffffffu, mine + sz[r], last);  // points of the whole group
+        uint32_t old = 0u;
+        if (rk[r] != 0xffffffffu && lane == leader) {
+            old = wh[rk[r]];
+            wh[rk[r]] = old + group;
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        local[r] = old + mine;
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < n_ranks; p += REFSTART_THREADS) {  // exclusive prefix over the eight warps
+        uint32_t run = 0u;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t t = s_w[(size_t)w * n_ranks + p];
+            s_w[(size_t)w * n_ranks + p] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < REFSTART_ROWS; ++r) {
+        const uint32_t j = wbase + 32 * r + lane;
+        if (j < nb && sz[r] >= K) blk_ref_start[a_blk[j]] = s_base[rk[r]] + (long long)(wh[rk[r]] + local[r]);
+    }
+}
+
 __global__ void key_to_rank_kernel(uint32_t nb, const uint64_t* __restrict__ keys, int shift, uint32_t* __restrict__ ranks) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < nb) ranks[j] = (uint32_t)(keys[j] >> shift);
@@ -373,7 +502,16 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
     OL_REQUIRE(ppb >= 1, OL_ERR_INVALID, "poses_per_batch must be positive");
     DevBuf<uint32_t> ref_order, sorted_rank;
     DevBuf<int32_t> d_pose_rank;
-    compute_ref_order(pose_rank, ref_order, d_pose_rank, &sorted_rank);
+    int max_rank = 0;
+    for (int p = 0; p < n_poses; ++p) {
+        OL_REQUIRE(!pose_rank || pose_rank[p] >= 0, OL_ERR_INVALID, "negative pose rank");
+        max_rank = std::max(max_rank, pose_rank ? pose_rank[p] : p);
+    }
+    static const bool no_fast_layout = getenv("OL_RANSAC_SORTED_LAYOUT") != nullptr;  // debug / A-B: always sort the block table
+    ensure_order();
+    ensure_blocks();
+    const bool fast_layout = !no_fast_layout && !history_active() && max_rank < REFSTART_MAX_RANKS && NB > 0;
+    if (!fast_layout) compute_ref_order(pose_rank, ref_order, d_pose_rank, &sorted_rank);
     drop_snapshot();
     res_n = NB;
     mask.reset(ctx, A);
@@ -384,13 +522,62 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
         last_ransac_work = 0;
         return;
     }
-    int max_rank = 0;
-    for (int p = 0; p < n_poses; ++p) max_rank = std::max(max_rank, pose_rank ? pose_rank[p] : p);
     const int n_batches = max_rank / ppb + 1;
-    DevBuf<uint32_t> sizes_ref(ctx, NB), refstart(ctx, NB), batch_base(ctx, n_batches);
     DevBuf<int32_t> blk_size(ctx, NB);
     DevBuf<long long> blk_ref_start(ctx, NB);
     DevBuf<unsigned long long> d_total(ctx, 1);
+    DevBuf<uint32_t> a_rank, a_blk;  // fast layout: the arranged (pose rank, block) tables, kept for a deferred sort
+    if (fast_layout) {
+        const int n_ranks = max_rank + 1;
+        std::vector<int32_t> pr(std::max(n_poses, 1));
+        for (int p = 0; p < n_poses; ++p) pr[p] = pose_rank ? pose_rank[p] : p;
+        d_pose_rank.reset(ctx, pr.size());
+        h2d(ctx, d_pose_rank.get(), pr.data(), pr.size());
+        const uint32_t n_chunks = (NB + REFSTART_CHUNK - 1) / REFSTART_CHUNK;
+        DevBuf<uint32_t> cnt_c(ctx, L), off_c(ctx, L), first_b(ctx, L), a_size(ctx, NB), table(ctx, (size_t)n_ranks * n_chunks);
+        DevBuf<long long> d_start;
+        a_rank.reset(ctx, NB);
+        a_blk.reset(ctx, NB);
+        cnt_c.zero();
+        if (pose_start) {  // multi-GPU: batch-global index of the first local point of every pose rank (see below)
+            std::vector<long long> by_rank((size_t)n_ranks, 0);
+            for (int p = 0; p < n_poses; ++p) by_rank[pr[p]] = (long long)pose_start[p];
+            d_start.reset(ctx, (size_t)n_ranks);
+            h2d(ctx, d_start.get(), by_rank.data(), by_rank.size());
+        }
+        {
+            ProfScope ps(ctx, "ransac_prep");
+            leaf_block_count_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_leaf.get(), cache_rank.get(), cnt_c.get(), first_b.get());
+            OL_CHECK_LAUNCH();
+        }
+        exclusive_scan_u32(ctx, cnt_c.get(), off_c.get(), L, nullptr);
+        {
+            ProfScope ps(ctx, "ransac_prep");
+            block_arrange2_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_leaf.get(), blk_pose.get(), blk_start.get(), d_pose_rank.get(),
+                                                                    cache_rank.get(), off_c.get(), first_b.get(), a_rank.get(),
+                                                                    a_size.get(), a_blk.get(), blk_size.get());
+            OL_CHECK_LAUNCH();
+            refstart_count_kernel<<<n_chunks, REFSTART_THREADS, (size_t)n_ranks * 4, ctx.stream>>>(NB, a_rank.get(), a_size.get(), n_ranks,
+                                                                                                  n_chunks, table.get());
+            OL_CHECK_LAUNCH();
+        }
+        exclusive_scan_u32(ctx, table.get(), table.get(), (size_t)n_ranks * n_chunks, nullptr);
+        {
+            ProfScope ps(ctx, "ransac_prep");
+            const size_t smem = (size_t)n_ranks * (8 + 8 * 4);
+            static bool attr_set = false;
+            if (!attr_set) {
+                OL_CUDA(cudaFuncSetAttribute(refstart_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             REFSTART_MAX_RANKS * (8 + 8 * 4)));
+                attr_set = true;
+            }
+            refstart_assign_kernel<<<n_chunks, REFSTART_THREADS, smem, ctx.stream>>>(NB, (uint32_t)K, (uint32_t)ppb, a_rank.get(),
+                                                                                    a_size.get(), a_blk.get(), n_ranks, n_chunks,
+                                                                                    table.get(), d_start.get(), blk_ref_start.get());
+            OL_CHECK_LAUNCH();
+        }
+    } else {
+    DevBuf<uint32_t> sizes_ref(ctx, NB), refstart(ctx, NB), batch_base(ctx, n_batches);
     {
         ProfScope ps(ctx, "ransac_prep");
         block_sizes_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_start.get(), ref_order.get(), blk_size.get(), sizes_ref.get());
@@ -425,6 +612,7 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
                                                                refstart.get(), batch_base.get(), blk_ref_start.get());
         OL_CHECK_LAUNCH();
     }
+    }  // sorted layout
     // work list + packed layout of the fitted blocks' points: one scan, one read-back (with the largest block size)
     const size_t work_max = std::min<size_t>(NB, (size_t)A / (size_t)K);
     DevBuf<uint32_t> work(ctx, work_max + 1), pk_start(ctx, work_max + 1);
@@ -467,6 +655,9 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
     // (materialize_snapshot): keep the raw inputs of that gather.  The block table itself is consumed by the
     // mask application, so it is moved, not copied, when the mask is applied right away.
     sn_ref_order.swap(ref_order);
+    sn_arr_rank.swap(a_rank);  // fast layout: the reference order is sorted out of these when a result table is asked for
+    sn_arr_blk.swap(a_blk);
+    sn_rank_bits = bit_length_u64((uint64_t)max_rank);
     sn_size.swap(blk_size);
     sn_plane.swap(plane);
     sn_best.swap(best);
@@ -782,6 +973,8 @@ __global__ void scored_compact_kernel(uint32_t n, const uint32_t* __restrict__ f
 void Forest::drop_snapshot() {
     snap_pending = false;
     sn_ref_order.release();
+    sn_arr_rank.release();
+    sn_arr_blk.release();
     sn_pose.release();
     sn_leaf.release();
     sn_size.release();
@@ -801,6 +994,14 @@ void Forest::materialize_snapshot() {
     res_plane.reset(ctx, (size_t)nb * 4);
     res_best.reset(ctx, nb);
     res_count.reset(ctx, nb);
+    if (nb && !sn_ref_order.get()) {
+        // the RANSAC launch took the sort-free batch layout: the reference order of the blocks is produced now, by the
+        // stable sort on the pose rank that compute_ref_order does up front on the other path
+        OL_REQUIRE(sn_arr_rank.get() && sn_arr_blk.get(), OL_ERR_INTERNAL, "RANSAC snapshot without a block order");
+        DevBuf<uint32_t> k1(ctx, nb), v1(ctx, nb);
+        const int w = radix_sort_pairs<uint32_t>(ctx, sn_arr_rank.get(), k1.get(), sn_arr_blk.get(), v1.get(), nb, 0, sn_rank_bits);
+        sn_ref_order.swap(w ? v1 : sn_arr_blk);
+    }
     if (nb) {
         ProfScope ps(ctx, "ransac_prep");
         ransac_snapshot_kernel<<<nblk(nb), 256, 0, ctx.stream>>>(nb, sn_ref_order.get(), sn_pose.get(), sn_leaf.get(), cache_rank.get(),

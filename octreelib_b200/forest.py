@@ -95,7 +95,7 @@ def _i32_array(values: Optional[Sequence[int]]):
 
 
 class Forest:
-    FLUSH_EVERY = 64            # deferred CUDA-tensor inserts are handed over in batches of this many poses ...
+    FLUSH_EVERY = 128           # deferred CUDA-tensor inserts are handed over in batches of this many poses ...
     FLUSH_MIN_ROWS = 1 << 20    # ... once they hold at least this many points (small grids: one batch at the end)
 
     def __init__(self, edge: float, corner=(0.0, 0.0, 0.0), single_cell: bool = False, max_depth: int = N.OL_MAX_DEPTH,
