@@ -154,7 +154,9 @@ struct Forest {
     DevBuf<int32_t> blk_pose;    // [NB]
     DevBuf<uint32_t> blk_of_pos; // [A] position -> block
     uint32_t max_block = 0;
-    bool max_block_known = false;  // block_max_kernel has been launched into d_max_block but not read back yet
+    bool max_block_known = false;  // max_block holds the size of the largest block
+    bool max_block_enqueued = false;  // ... or a kernel that leaves it in d_max_block has been launched
+    void enqueue_max_block();
     DevBuf<uint32_t> d_max_block;  // [1]
 
     // ---- RANSAC results of the last ol_forest_ransac call ----------------------------------------
@@ -168,6 +170,7 @@ struct Forest {
     DevBuf<uint32_t> sn_ref_order, sn_leaf;
     DevBuf<uint32_t> sn_arr_rank, sn_arr_blk;  // sort-free batch layout: (pose rank, block) in arranged order, sorted on demand
     int sn_rank_bits = 0;
+    int sn_K = 0;            // blocks with fewer points were not fitted: their result rows are undefined
     DevBuf<int32_t> sn_pose, sn_size, sn_best, sn_count;
     DevBuf<float> sn_plane;
     bool sample_oob_seen = false;

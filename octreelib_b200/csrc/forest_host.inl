@@ -1263,16 +1263,21 @@ void Forest::ensure_blocks_enqueue() {
                      blk_start.get(), blocks_mail);
     }
     blocks_pending = true;
-    // the largest block is only read back when somebody needs it (ensure_max_block; RANSAC reads it together with its work size)
+    // the largest block is only computed when somebody needs it (ensure_max_block; the RANSAC batch layout folds it into
+    // a pass it makes over the block sizes anyway and reads it together with its work size)
     d_max_block.reset(ctx, 1);
     d_max_block.zero();
-    {
-        ProfScope ps(ctx, "blocks");
-        block_max_kernel<<<(unsigned)ctx.num_sms * 8, 256, 0, ctx.stream>>>(blk_start.get(), d_nb.get(), d_max_block.get());
-        OL_CHECK_LAUNCH();
-    }
     max_block_known = false;
+    max_block_enqueued = false;
     blocks_valid = true;
+}
+
+void Forest::enqueue_max_block() {
+    if (max_block_known || max_block_enqueued) return;
+    ProfScope ps(ctx, "blocks");
+    block_max_kernel<<<(unsigned)ctx.num_sms * 8, 256, 0, ctx.stream>>>(blk_start.get(), d_nb.get(), d_max_block.get());
+    OL_CHECK_LAUNCH();
+    max_block_enqueued = true;
 }
 
 // Enqueued at the end of a subdivide: nearly every next operation (RANSAC, filter, get_leaf_points, the counters) starts
@@ -1286,6 +1291,7 @@ void Forest::prefetch_tables() {
 
 void Forest::ensure_max_block() {
     if (max_block_known) return;
+    enqueue_max_block();
     max_block = read_u32(d_max_block.get());
     max_block_known = true;
 }

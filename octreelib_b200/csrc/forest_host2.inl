@@ -71,6 +71,26 @@ __global__ void block_arrange_history_kernel(uint32_t nb, const uint32_t* __rest
 // block.  The sorted order itself is only needed when somebody asks for the result TABLE of all blocks in reference
 // order (materialize_snapshot): the sort is deferred until then.
 // ---------------------------------------------------------------------------------------------
+// first and one-past-last block of every leaf (the blocks of a leaf are consecutive in the block table): two coalesced
+// compares per block, no loop - the head of a leaf's run writes the one, its tail the other; leaves without blocks keep 0, 0
+__global__ void leaf_block_span_kernel(uint32_t nb, const uint32_t* __restrict__ blk_leaf, uint32_t* __restrict__ first_b,
+                                       uint32_t* __restrict__ last_b) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const uint32_t leaf = blk_leaf[b];
+    if (b == 0 || blk_leaf[b - 1] != leaf) first_b[leaf] = b;
+    if (b + 1 == nb || blk_leaf[b + 1] != leaf) last_b[leaf] = b + 1;
+}
+struct LeafSpanIn {  // number of blocks of the leaf at enumeration position c
+    const uint32_t* leaf_by_cache;
+    const uint32_t* first_b;
+    const uint32_t* last_b;
+    __device__ __forceinline__ uint32_t operator()(size_t c) const {
+        const uint32_t leaf = leaf_by_cache[c];
+        return last_b[leaf] - first_b[leaf];
+    }
+};
+
 constexpr int REFSTART_THREADS = 256;
 constexpr int REFSTART_ROWS = 16;                                   // rows of 32 slots per warp
 constexpr int REFSTART_CHUNK = REFSTART_THREADS * REFSTART_ROWS;    // arranged slots per CTA
@@ -94,15 +114,29 @@ __global__ void block_arrange2_kernel(uint32_t nb, const uint32_t* __restrict__ 
 
 __global__ void __launch_bounds__(REFSTART_THREADS) refstart_count_kernel(uint32_t nb, const uint32_t* __restrict__ a_rank,
                                                                           const uint32_t* __restrict__ a_size, int n_ranks,
-                                                                          uint32_t n_chunks, uint32_t* __restrict__ table) {
+                                                                          uint32_t n_chunks, uint32_t* __restrict__ table,
+                                                                          uint32_t* __restrict__ max_size) {
     extern __shared__ uint32_t s_cnt[];
     for (int p = threadIdx.x; p < n_ranks; p += REFSTART_THREADS) s_cnt[p] = 0u;
     __syncthreads();
     const uint32_t base = blockIdx.x * REFSTART_CHUNK;
+    uint32_t big = 0u;
 #pragma unroll 4
     for (int k = 0; k < REFSTART_ROWS; ++k) {
         const uint32_t j = base + (uint32_t)k * REFSTART_THREADS + threadIdx.x;
-        if (j < nb) atomicAdd(&s_cnt[a_rank[j]], a_size[j]);
+        if (j < nb) {
+            const uint32_t sz = a_size[j];
+            atomicAdd(&s_cnt[a_rank[j]], sz);
+            big = sz > big ? sz : big;
+        }
+    }
+    if (max_size) {  // the largest block of the table, on the way (the RANSAC launch sizes its shared memory by it)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint32_t t = __shfl_xor_sync(0xffffffffu, big, o);
+            big = t > big ? t : big;
+        }
+        if ((threadIdx.x & 31) == 0 && big) atomicMax(max_size, big);
     }
     __syncthreads();
     for (int p = threadIdx.x; p < n_ranks; p += REFSTART_THREADS) table[(size_t)p * n_chunks + blockIdx.x] = s_cnt[p];
@@ -299,7 +333,7 @@ __global__ void ransac_snapshot_kernel(uint32_t nb, const uint32_t* __restrict__
                                        const int32_t* __restrict__ best, const int32_t* __restrict__ best_count,
                                        int32_t* __restrict__ o_pose, int32_t* __restrict__ o_leaf, int32_t* __restrict__ o_size,
                                        float* __restrict__ o_plane, int32_t* __restrict__ o_best,
-                                       int32_t* __restrict__ o_count) {
+                                       int32_t* __restrict__ o_count, int K) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nb) return;
     uint32_t b = ref_order[j];
@@ -307,9 +341,10 @@ __global__ void ransac_snapshot_kernel(uint32_t nb, const uint32_t* __restrict__
     o_leaf[j] = (int32_t)cache_rank[blk_leaf[b]];
     o_size[j] = blk_size[b];
     if (plane) {
-        for (int c = 0; c < 4; ++c) o_plane[(size_t)j * 4 + c] = plane[(size_t)b * 4 + c];
-        o_best[j] = best[b];
-        o_count[j] = best_count[b];
+        const bool fitted = blk_size[b] >= K;  // the result rows of smaller blocks were never written (nor initialised)
+        for (int c = 0; c < 4; ++c) o_plane[(size_t)j * 4 + c] = fitted ? plane[(size_t)b * 4 + c] : 0.0f;
+        o_best[j] = fitted ? best[b] : -1;
+        o_count[j] = fitted ? best_count[b] : 0;
     }
 }
 
@@ -534,11 +569,13 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
         d_pose_rank.reset(ctx, pr.size());
         h2d(ctx, d_pose_rank.get(), pr.data(), pr.size());
         const uint32_t n_chunks = (NB + REFSTART_CHUNK - 1) / REFSTART_CHUNK;
-        DevBuf<uint32_t> cnt_c(ctx, L), off_c(ctx, L), first_b(ctx, L), a_size(ctx, NB), table(ctx, (size_t)n_ranks * n_chunks);
+        DevBuf<uint32_t> off_c(ctx, L), span(ctx, (size_t)2 * L), a_size(ctx, NB), table(ctx, (size_t)n_ranks * n_chunks);
+        uint32_t* first_b = span.get();
+        uint32_t* last_b = span.get() + L;
         DevBuf<long long> d_start;
         a_rank.reset(ctx, NB);
         a_blk.reset(ctx, NB);
-        cnt_c.zero();
+        span.zero();
         if (pose_start) {  // multi-GPU: batch-global index of the first local point of every pose rank (see below)
             std::vector<long long> by_rank((size_t)n_ranks, 0);
             for (int p = 0; p < n_poses; ++p) by_rank[pr[p]] = (long long)pose_start[p];
@@ -547,19 +584,21 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
         }
         {
             ProfScope ps(ctx, "ransac_prep");
-            leaf_block_count_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_leaf.get(), cache_rank.get(), cnt_c.get(), first_b.get());
+            leaf_block_span_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_leaf.get(), first_b, last_b);
             OL_CHECK_LAUNCH();
         }
-        exclusive_scan_u32(ctx, cnt_c.get(), off_c.get(), L, nullptr);
+        transform_scan<uint32_t>(ctx, LeafSpanIn{leaf_by_cache.get(), first_b, last_b}, ScanPtrOut<uint32_t>{off_c.get()}, L, nullptr);
         {
             ProfScope ps(ctx, "ransac_prep");
             block_arrange2_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, blk_leaf.get(), blk_pose.get(), blk_start.get(), d_pose_rank.get(),
-                                                                    cache_rank.get(), off_c.get(), first_b.get(), a_rank.get(),
+                                                                    cache_rank.get(), off_c.get(), first_b, a_rank.get(),
                                                                     a_size.get(), a_blk.get(), blk_size.get());
             OL_CHECK_LAUNCH();
             refstart_count_kernel<<<n_chunks, REFSTART_THREADS, (size_t)n_ranks * 4, ctx.stream>>>(NB, a_rank.get(), a_size.get(), n_ranks,
-                                                                                                  n_chunks, table.get());
+                                                                                                  n_chunks, table.get(),
+                                                                                                  max_block_known || max_block_enqueued ? nullptr : d_max_block.get());
             OL_CHECK_LAUNCH();
+            max_block_enqueued = true;
         }
         exclusive_scan_u32(ctx, table.get(), table.get(), (size_t)n_ranks * n_chunks, nullptr);
         {
@@ -618,17 +657,17 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
     DevBuf<uint32_t> work(ctx, work_max + 1), pk_start(ctx, work_max + 1);
     // (the number of fitted blocks, their point total and the largest block size are POSTED by the scan kernel; the
     // result tables are initialised behind it, so the GPU has work while the host reads the mailbox)
+    enqueue_max_block();  // (a no-op when the batch layout above already left the maximum in d_max_block)
     const Mail mail = mail_open(MAIL_WORK, max_block_known ? nullptr : d_max_block.get());
     transform_scan<unsigned long long>(ctx, WorkIn{blk_start.get(), (uint32_t)K}, WorkOut{work.get(), pk_start.get()}, NB, d_total.get(),
                                        "ransac_prep", mail);
     DevBuf<double> table(ctx, (size_t)H * K);
     h2d(ctx, table.get(), table_host, (size_t)H * K);
+    // per-block results: written by the kernels for exactly the fitted blocks (size >= K) and never read for the others
+    // (ransac_snapshot_kernel tells them apart by their size), so the 24 bytes per block are not initialised - on a LiDAR
+    // map 93 % of the 41 M blocks are too small to be fitted, and clearing their rows cost a gigabyte of stores per step
     DevBuf<float> plane(ctx, (size_t)NB * 4);
     DevBuf<int32_t> best(ctx, NB), best_count(ctx, NB);
-    plane.zero();
-    best_count.zero();
-    fill_kernel<int32_t><<<nblk(NB), 256, 0, ctx.stream>>>(best.get(), NB, -1);
-    OL_CHECK_LAUNCH();
     const MailResult posted = mail_take(mail);
     const unsigned long long packed_total = posted.total;
     if (!max_block_known) {
@@ -658,6 +697,7 @@ void Forest::ransac(const double* table_host, int H, int K, double threshold, co
     sn_arr_rank.swap(a_rank);  // fast layout: the reference order is sorted out of these when a result table is asked for
     sn_arr_blk.swap(a_blk);
     sn_rank_bits = bit_length_u64((uint64_t)max_rank);
+    sn_K = K;
     sn_size.swap(blk_size);
     sn_plane.swap(plane);
     sn_best.swap(best);
@@ -939,7 +979,7 @@ void Forest::export_blocks(const int32_t* pose_rank, int32_t* pose, int32_t* lea
         ProfScope ps(ctx, "ransac_prep");
         ransac_snapshot_kernel<<<nblk(NB), 256, 0, ctx.stream>>>(NB, ref_order.get(), blk_pose.get(), blk_leaf.get(), cache_rank.get(),
                                                                  blk_size.get(), nullptr, nullptr, nullptr, o_pose.get(), o_leaf.get(),
-                                                                 o_size.get(), nullptr, nullptr, nullptr);
+                                                                 o_size.get(), nullptr, nullptr, nullptr, 0);
         OL_CHECK_LAUNCH();
     }
     copy_out(ctx, pose, o_pose.get(), NB);
@@ -1007,7 +1047,7 @@ void Forest::materialize_snapshot() {
         ransac_snapshot_kernel<<<nblk(nb), 256, 0, ctx.stream>>>(nb, sn_ref_order.get(), sn_pose.get(), sn_leaf.get(), cache_rank.get(),
                                                                  sn_size.get(), sn_plane.get(), sn_best.get(), sn_count.get(),
                                                                  res_pose.get(), res_leaf.get(), res_size.get(), res_plane.get(),
-                                                                 res_best.get(), res_count.get());
+                                                                 res_best.get(), res_count.get(), sn_K);
         OL_CHECK_LAUNCH();
     }
     drop_snapshot();
