@@ -56,6 +56,27 @@ def dist_env():
     return rank, world, local
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this process to the CPU cores NVML reports as local to its GPU (one process per GPU: the page-locked host
+    buffers of the e2e leg are then first-touched on the GPU's own NUMA node and the host thread that drives the GPU runs
+    next to it; torchrun does not bind its workers).  Returns a short description for the bench line, None if NVML or the
+    affinity call is unavailable."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local), n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return f"{len(allowed)} cores local to GPU {local} ({allowed[0]}-{allowed[-1]})"
+    except Exception:  # noqa: BLE001 - a measurement convenience, never a failure
+        return None
+
+
 def init_dist(world, local, backend="nccl"):
     import torch
     import torch.distributed as dist
@@ -515,6 +536,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    cpu_binding = bind_to_gpu_numa_node(local) if world > 1 else None
     dist = init_dist(world, local)
     from octreelib_b200 import _native
 
@@ -702,6 +724,8 @@ def main():
                 "H512_parity": runs.get(512, {}).get("parity_vs_reference_kernel_on_b200")}
         except Exception:  # noqa: BLE001
             pass
+    if cpu_binding:
+        out["cpu_binding"] = cpu_binding
     if ranks_info:
         out["ranks"] = ranks_info
     if exchange_info:
