@@ -169,33 +169,32 @@ __global__ void __launch_bounds__(REFSTART_THREADS) refstart_assign_kernel(uint3
     uint32_t* wh = s_w + (size_t)warp * n_ranks;
     const uint32_t wbase = chunk * REFSTART_CHUNK + (uint32_t)warp * (32 * REFSTART_ROWS);
     const uint32_t lt = (1u << lane) - 1u;
-    uint32_t rk[REFSTART_ROWS], sz[REFSTART_ROWS], local[REFSTART_ROWS];
-#pragma unroll
+    // (only the in-chunk prefixes stay in registers between the two phases; ranks and sizes are read again for the
+    // stores - 103 registers and 23 % occupancy when all three were kept)
+    uint32_t local[REFSTART_ROWS];
+#pragma unroll 4
     for (int r = 0; r < REFSTART_ROWS; ++r) {
         const uint32_t j = wbase + 32 * r + lane;
-        rk[r] = j < nb ? a_rank[j] : 0xffffffffu;
-        sz[r] = j < nb ? a_size[j] : 0u;
-    }
-#pragma unroll
-    for (int r = 0; r < REFSTART_ROWS; ++r) {
+        const uint32_t rk = j < nb ? a_rank[j] : 0xffffffffu;
+        const uint32_t sz = j < nb ? a_size[j] : 0u;
         // the lanes with this lane's rank, and the sizes of those before it (slot order = lane order): a few iterations,
         // consecutive arranged slots are (leaf, pose ascending), so a rank repeats about once per leaf
-        const uint32_t peers = __match_any_sync(0xffffffffu, rk[r]);
+        const uint32_t peers = __match_any_sync(0xffffffffu, rk);
         uint32_t below = peers & lt, mine = 0u;
         while (__any_sync(0xffffffffu, below != 0u)) {
             const int src = below ? (__ffs(below) - 1) : lane;
-            const uint32_t v = __shfl_sync(0xffffffffu, sz[r], src);
+            const uint32_t v = __shfl_sync(0xffffffffu, sz, src);
             if (below) {
                 mine += v;
                 below &= below - 1u;
             }
         }
         const int leader = __ffs(peers) - 1, last = 31 - __clz(peers);
-        const uint32_t group = __shfl_sync(0xffffffffu, mine + sz[r], last);  // points of the whole group
+        const uint32_t group = __shfl_sync(0xffffffffu, mine + sz, last);  // points of the whole group
         uint32_t old = 0u;
-        if (rk[r] != 0xffffffffu && lane == leader) {
-            old = wh[rk[r]];
-            wh[rk[r]] = old + group;
+        if (rk != 0xffffffffu && lane == leader) {
+            old = wh[rk];
+            wh[rk] = old + group;
         }
         old = __shfl_sync(0xffffffffu, old, leader);
         local[r] = old + mine;
@@ -215,7 +214,10 @@ __global__ void __launch_bounds__(REFSTART_THREADS) refstart_assign_kernel(uint3
 #pragma unroll
     for (int r = 0; r < REFSTART_ROWS; ++r) {
         const uint32_t j = wbase + 32 * r + lane;
-        if (j < nb && sz[r] >= K) blk_ref_start[a_blk[j]] = s_base[rk[r]] + (long long)(wh[rk[r]] + local[r]);
+        if (j < nb && a_size[j] >= K) {
+            const uint32_t rk = a_rank[j];
+            blk_ref_start[a_blk[j]] = s_base[rk] + (long long)(wh[rk] + local[r]);
+        }
     }
 }
 

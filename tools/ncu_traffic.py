@@ -16,7 +16,11 @@ import sys
 
 STAGE_OF = [("os_pass_kernel", "sort_main_pass"), ("part_move_kernel", "part_move"), ("part_hist_kernel", "part_hist"),
             ("keygen_kernel", "keygen"), ("os_hist_kernel", "sort_main_hist"), ("runs_fused_kernel", "runs"),
+            ("runs_flags_kernel", "runs_flags"), ("runs_emit2_kernel", "runs_emit"),
             ("ransac_lane_kernel", "ransac_lane"), ("ransac_small_kernel", "ransac_small"), ("gather_kernel", "gather_morton"),
+            ("gather_blocks_kernel", "gather_points"), ("refstart_assign_kernel", "refstart_assign"),
+            ("refstart_count_kernel", "refstart_count"), ("block_arrange2_kernel", "block_arrange"),
+            ("leaf_block_span_kernel", "leaf_block_span"), ("compact_move_kernel", "compact_move"),
             ("insert_batch_kernel", "insert_batch")]
 COLS = {"dram_r": "dram__bytes_read.sum", "dram_w": "dram__bytes_write.sum", "time": "gpu__time_duration.sum",
         "dram_pct": "dram__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct": "sm__throughput.avg.pct_of_peak_sustained_elapsed",
