@@ -609,7 +609,8 @@ int ol_exclusive_scan_u32(void* stream, const uint32_t* in_dev, uint32_t* out_de
     OL_API_END
 }
 
-double ol_host_floor_divide(double a, double b) { return ol::npy_floor_divide(a, b); }
+// (what the kernels evaluate: the reciprocal fast path for power-of-two divisors, the division otherwise)
+double ol_host_floor_divide(double a, double b) { return ol::npy_floor_divide_inv(a, b, ol::pow2_reciprocal(b)); }
 
 int ol_host_point_key(double edge, const double corner[3], int32_t single_cell, int32_t depth, const double p[3], int64_t q[3],
                       uint64_t* morton, int32_t* bad_level) {
@@ -617,7 +618,7 @@ int ol_host_point_key(double edge, const double corner[3], int32_t single_cell, 
     OL_REQUIRE(depth >= 0 && depth <= OL_MAX_DEPTH, OL_ERR_INVALID, "depth out of range");
     double c0[3];
     for (int a = 0; a < 3; ++a) {
-        long long qa = single_cell ? 0 : (long long)ol::cell_coord(p[a], corner[a], edge);
+        long long qa = single_cell ? 0 : (long long)ol::cell_coord_inv(p[a], corner[a], edge, ol::pow2_reciprocal(edge));
         q[a] = qa;
         c0[a] = ol::cell_corner_coord(qa, corner[a], edge, single_cell);
     }

@@ -43,6 +43,7 @@ struct XTile {
 
 struct XParams {
     double edge, c0, c1, c2;
+    double inv_edge;  // 1 / edge for power-of-two edges (exact), else 0: common.cuh, npy_floor_divide_inv
     int world, rank, n_poses, slabs;
     long long rows_cap;
     unsigned long long epoch;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(256) xchg_range_kernel(const XTile* __restrict
         const XTile T = tiles[t];
         const uint32_t k = threadIdx.x * XCHG_SAMPLE;
         if (k < T.n) {
-            const double q = cell_coord(T.src[(size_t)k * 3], p.c0, p.edge);
+            const double q = cell_coord_inv(T.src[(size_t)k * 3], p.c0, p.edge, p.inv_edge);
             if (fabs(q) < 4503599627370496.0) {
                 const long long ix = (long long)q;
                 lo = ix < lo ? ix : lo;
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(256) xchg_hist_kernel(const XTile* __restrict_
         const uint32_t k = threadIdx.x * XCHG_SAMPLE;
         int bin = -1;
         if (k < T.n) {
-            const double q = cell_coord(T.src[(size_t)k * 3], p.c0, p.edge);
+            const double q = cell_coord_inv(T.src[(size_t)k * 3], p.c0, p.edge, p.inv_edge);
             if (fabs(q) < 4503599627370496.0) bin = (int)(((long long)q - lo) / width);
         }
         const uint32_t peers = __match_any_sync(0xffffffffu, bin);  // one shared-memory atomic per distinct bin and warp
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(256) xchg_count_kernel(const XTile* __restrict
                 mn0 = fmin(mn0, x), mx0 = fmax(mx0, x);
                 mn1 = fmin(mn1, y), mx1 = fmax(mx1, y);
                 mn2 = fmin(mn2, z), mx2 = fmax(mx2, z);
-                const double qx = cell_coord(x, p.c0, p.edge);
+                const double qx = cell_coord_inv(x, p.c0, p.edge, p.inv_edge);
                 if (p.slabs) {
                     if (fabs(qx) < 4503599627370496.0) {
                         const long long ix = (long long)qx;
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(256) xchg_count_kernel(const XTile* __restrict
                     } else
                         err |= DEVERR_CELL_RANGE;
                 } else {
-                    const double qy = cell_coord(y, p.c1, p.edge), qz = cell_coord(z, p.c2, p.edge);
+                    const double qy = cell_coord_inv(y, p.c1, p.edge, p.inv_edge), qz = cell_coord_inv(z, p.c2, p.edge, p.inv_edge);
                     if (fabs(qx) < 4503599627370496.0 && fabs(qy) < 4503599627370496.0 && fabs(qz) < 4503599627370496.0)
                         o = cell_owner((long long)qx, (long long)qy, (long long)qz, (uint32_t)p.world);
                     else
@@ -581,6 +582,7 @@ void Exchange::run(Forest& f, const double* const* clouds, const int64_t* sizes,
     ++epoch;
     XParams p{};
     p.edge = f.cfg.voxel_edge_length;
+    p.inv_edge = pow2_reciprocal(p.edge);
     p.c0 = f.cfg.corner[0], p.c1 = f.cfg.corner[1], p.c2 = f.cfg.corner[2];
     p.world = world, p.rank = rank, p.n_poses = n_poses, p.slabs = slabs ? 1 : 0;
     p.rows_cap = rows_cap;

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ 
     if (!kp.single_cell) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            double qa = cell_coord(p[a], kp.corner[a], kp.edge);
+            double qa = cell_coord_inv(p[a], kp.corner[a], kp.edge, kp.inv_edge);
             if (!(fabs(qa) < 4503599627370496.0)) {  // 2^52
                 e |= DEVERR_CELL_RANGE;
                 qa = 0.0;

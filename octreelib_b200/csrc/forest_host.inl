@@ -450,6 +450,7 @@ void Forest::build_enqueue() {
     const int S = (int)seg_pose.size();
     kp = KeyParams{};
     kp.edge = cfg.voxel_edge_length;
+    kp.inv_edge = pow2_reciprocal(kp.edge);
     for (int a = 0; a < 3; ++a) kp.corner[a] = cfg.corner[a];
     kp.single_cell = cfg.single_cell;
     kp.depth = std::min(max_depth, MORTON_INITIAL_DEPTH);  // deeper levels are computed on demand (extend_morton)

@@ -23,6 +23,7 @@ struct KeyParams {
     long long qmin[3];   // packed key = sum (q[a] - qmin[a]) << shift[a]
     int shift[3];
     int pose_bits;       // low bits of the sort key reserved for the pose index (multi-segment input)
+    double inv_edge;     // 1 / edge when the edge is a power of two (exact: see npy_floor_divide_inv), else 0
 };
 
 constexpr unsigned long long MORTON_BAD_BIT = 1ull << 63;
@@ -30,6 +31,9 @@ constexpr unsigned long long MORTON_BAD_BIT = 1ull << 63;
 // integer cell coordinate of p along one axis (grid.py:72-76 without the `* edge` rescale)
 __host__ __device__ inline double cell_coord(double p, double corner, double edge) {
     return npy_floor_divide(p - corner, edge);
+}
+__host__ __device__ inline double cell_coord_inv(double p, double corner, double edge, double inv_edge) {
+    return npy_floor_divide_inv(p - corner, edge, inv_edge);
 }
 
 // Returns the Morton code (3 bits per level, level 0 in the most significant used bits);

@@ -173,7 +173,9 @@ class Forest:
             self._batch_rows += t.shape[0]
             self.version += 1
             index = self._n_poses_native + len(self._batch) - 1
-            if len(self._batch) >= self.FLUSH_EVERY and self._batch_rows >= self.FLUSH_MIN_ROWS:
+            # (the FIRST batch goes out after a quarter of that, so that the GPU starts early)
+            due = self.FLUSH_EVERY if self._n_poses_native else max(self.FLUSH_EVERY // 4, 1)
+            if len(self._batch) >= due and self._batch_rows >= self.FLUSH_MIN_ROWS:
                 self._flush()  # the copy kernel runs while the caller is still inserting the following poses
             return index
         out = C.c_int32(-1)

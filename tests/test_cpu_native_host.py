@@ -42,7 +42,8 @@ def test_floor_divide_fast_path_adversarial():
     to 2^50 and for edges that are not exactly representable."""
     lib = _native.lib()
     rng = np.random.default_rng(1)
-    for b in [1.0, 0.1, 0.3, 1.0 / 3.0, 0.7, 2.5, 1e-3, 1e-6, 123.456, 2.0 ** -20, 3e7]:
+    # (powers of two take the reciprocal path, npy_floor_divide_inv: a * (1 / b) instead of a / b)
+    for b in [1.0, 0.1, 0.3, 1.0 / 3.0, 0.7, 2.5, 1e-3, 1e-6, 123.456, 2.0 ** -20, 3e7, 0.5, 0.25, 4.0, 2.0 ** 30, 2.0 ** -300]:
         k = np.concatenate([rng.integers(-10 ** 6, 10 ** 6, 3000), rng.integers(-2 ** 50, 2 ** 50, 1000), [0, 1, -1, 2, -2]])
         base = k.astype(np.float64) * b  # (rounded) multiples of b
         cand = [base, np.nextafter(base, np.inf), np.nextafter(base, -np.inf), base + b * 0.5, base * (1 + 2.0 ** -52),
