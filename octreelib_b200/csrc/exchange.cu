@@ -41,6 +41,16 @@ struct XTile {
     int32_t pad;
 };
 
+// one local cloud; the tile table is expanded from these on the device (xchg_tiles_kernel): the host uploads ~100 rows
+// instead of building and staging thousands of tile descriptors per step
+struct XCloud {
+    const double* src;
+    uint32_t n;           // points
+    uint32_t first_row;   // index of the cloud's first point in the rank's concatenated local cloud
+    uint32_t first_tile;  // index of the cloud's first tile
+    int32_t pose;
+};
+
 struct XParams {
     double edge, c0, c1, c2;
     double inv_edge;  // 1 / edge for power-of-two edges (exact), else 0: common.cuh, npy_floor_divide_inv
@@ -258,6 +268,29 @@ __global__ void __launch_bounds__(1024) xchg_sync_a_kernel(XParams p, const __gr
         bounds[tid] = b;
         reinterpret_cast<volatile long long*>(host + XchgHost::BOUNDS)[tid] = b;
     }
+}
+
+// tile t -> its cloud (bisection over the clouds' first tiles) -> descriptor
+__global__ void xchg_tiles_kernel(const XCloud* __restrict__ clouds, int n_clouds, uint32_t n_tiles, XTile* __restrict__ tiles) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    int lo = 0, hi = n_clouds;  // last cloud with first_tile <= t (clouds without points own no tile and are skipped by the search)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (clouds[mid].first_tile <= t)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    const XCloud c = clouds[lo];
+    const uint32_t off = (t - c.first_tile) * (uint32_t)XCHG_TILE;
+    XTile T;
+    T.src = c.src + (size_t)off * 3;
+    T.n = min((uint32_t)XCHG_TILE, c.n - off);
+    T.first_row = c.first_row + off;
+    T.pose = c.pose;
+    T.pad = 0;
+    tiles[t] = T;
 }
 
 // ---- counting pass ------------------------------------------------------------------------------------------------------
@@ -565,20 +598,20 @@ void Exchange::run(Forest& f, const double* const* clouds, const int64_t* sizes,
     Ctx& c = f.ctx;
     cudaStream_t st = c.stream;
     // tile table of the local clouds (poses ascending, so that a (source rank, pose) run is contiguous at the receiver)
-    std::vector<XTile> tiles;
-    size_t n_local = 0;
+    std::vector<XCloud> cloud_rows;
+    cloud_rows.reserve((size_t)count);
+    size_t n_local = 0, n_tiles_sz = 0;
     int last_pose = -1;
     for (int k = 0; k < count; ++k) {
         OL_REQUIRE(sizes[k] >= 0 && poses[k] >= 0 && poses[k] < n_poses, OL_ERR_POSE, "pose number out of range");
         OL_REQUIRE(poses[k] >= last_pose, OL_ERR_INVALID, "clouds must be ordered by pose number");
         last_pose = poses[k];
-        for (int64_t off = 0; off < sizes[k]; off += XCHG_TILE)
-            tiles.push_back(XTile{clouds[k] + off * 3, (uint32_t)std::min<int64_t>(XCHG_TILE, sizes[k] - off), (uint32_t)(n_local + off),
-                                  poses[k], 0});
+        if (sizes[k] > 0) cloud_rows.push_back(XCloud{clouds[k], (uint32_t)sizes[k], (uint32_t)n_local, (uint32_t)n_tiles_sz, poses[k]});
+        n_tiles_sz += (size_t)((sizes[k] + XCHG_TILE - 1) / XCHG_TILE);
         n_local += (size_t)sizes[k];
         OL_REQUIRE(n_local < (1ull << 31), OL_ERR_INVALID, "more than 2^31 - 1 points per rank are not supported");
     }
-    const uint32_t n_tiles = (uint32_t)tiles.size();
+    const uint32_t n_tiles = (uint32_t)n_tiles_sz;
     ++epoch;
     XParams p{};
     p.edge = f.cfg.voxel_edge_length;
@@ -596,7 +629,12 @@ void Exchange::run(Forest& f, const double* const* clouds, const int64_t* sizes,
     DevBuf<XTile> d_tiles(c, std::max<size_t>(n_tiles, 1));
     DevBuf<uint8_t> d_owner(c, std::max<size_t>(n_local, 1));
     DevBuf<uint32_t> tile_cnt(c, (size_t)world * std::max<uint32_t>(n_tiles, 1));
-    h2d(c, d_tiles.get(), tiles.data(), tiles.size());
+    DevBuf<XCloud> d_clouds(c, std::max<size_t>(cloud_rows.size(), 1));
+    h2d(c, d_clouds.get(), cloud_rows.data(), cloud_rows.size());
+    if (n_tiles) {
+        xchg_tiles_kernel<<<(n_tiles + 255) / 256, 256, 0, st>>>(d_clouds.get(), (int)cloud_rows.size(), n_tiles, d_tiles.get());
+        OL_CHECK_LAUNCH();
+    }
     volatile long long* hdr = reinterpret_cast<volatile long long*>(host + XchgHost::HDR);
     hdr[8] = 0;
     {

@@ -465,10 +465,11 @@ class ShardedGrid:
             staged = sorted(staged, key=lambda s: s[0])  # stable: poses ascending, insertion order inside a pose
             numbers = [s[0] for s in staged]
         # the host time of this loop is time the GPU idles: one attribute test per cloud on the fast path
-        tensors, f64 = [], torch.float64
+        tensors, f64, dev_index = [], torch.float64, dev.index
         for _, pts in staged:
             t = pts
-            if not (type(t) is torch.Tensor and t.dtype is f64 and t.device == dev and t.dim() == 2 and t.is_contiguous()):
+            if not (type(t) is torch.Tensor and t.dtype is f64 and t.is_cuda and t.get_device() == dev_index and t.dim() == 2
+                    and t.is_contiguous()):
                 t = pts if isinstance(pts, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pts, dtype=np.float64))
                 t = t.to(dev, dtype=torch.float64, non_blocking=True).contiguous().reshape(-1, 3)
             tensors.append(t)
