@@ -895,6 +895,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 3) ransac_small_kernel(RansacAr
 // neighbouring runs), no shared memory.
 // =============================================================================================
 constexpr int RANSAC_LANE_PASSES = 8;
+constexpr int RANSAC_LANE_SINGLE = 3;  // hypotheses 0..2 get a launch each, 3..7 share one (ransac_lane_group_kernel)
 constexpr int RANSAC_LANE_MAX = 32;
 
 __global__ void __launch_bounds__(256) ransac_lane_kernel(RansacArgs A, int t, const uint32_t* __restrict__ list_in,
@@ -950,6 +951,70 @@ __global__ void __launch_bounds__(256) ransac_lane_kernel(RansacArgs A, int t, c
             atomicAdd(&g_ransac_stats[7], (unsigned long long)dist);
         }
     }
+}
+
+// The tail of the lane passes in ONE launch: after three passes only a few percent of the blocks are still undecided, and a
+// launch per hypothesis over them is all launch latency.  Eight lanes per listed block evaluate hypotheses t0 .. t1-1 side
+// by side (exact arithmetic, like ransac_lane_kernel); the lowest one that keeps every point decides the block - exactly
+// the hypothesis the sequential passes would have stopped at - and a block none of them decides stays on the list.
+__global__ void __launch_bounds__(256) ransac_lane_group_kernel(RansacArgs A, int t0, int t1, const uint32_t* __restrict__ list_in,
+                                                                const uint32_t* __restrict__ n_in_dev, uint32_t* __restrict__ list_out,
+                                                                uint32_t* __restrict__ n_out) {
+    const uint32_t n_in = __ldg(n_in_dev);
+    const int lane = threadIdx.x & 31, sub = lane & 7;
+    const int t = t0 + sub;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    // four listed blocks per warp and round; the list's length only exists on the device, so the warps stride over it
+    for (uint32_t first = warp_global * 4u; first < n_in; first += n_warps * 4u) {
+    const uint32_t item = first + (uint32_t)(lane >> 3);
+    bool listed = item < n_in, decided = false, fitted = false;
+    uint32_t w = 0, b = 0, ps = 0;
+    int n = 0;
+    float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (listed) {
+        w = list_in[item];
+        b = A.work[w];
+        n = A.blk_size[b];
+        if (n <= RANSAC_LANE_MAX && t < t1) {
+            ps = A.blk_start[b];
+            const double* pts = A.points + (size_t)(A.pk_start ? A.pk_start[w] : ps) * 3;
+            pl = fit_plane(pts, A.table, A.K, t, n, A.blk_ref_start[b], A.err);
+            decided = exact_count_serial(pts, n, pl, A.thr) == n;
+            fitted = true;
+        }
+    }
+    const uint32_t dm = __ballot_sync(0xffffffffu, decided);
+    const uint32_t mine = (dm >> (lane & ~7)) & 0xffu;  // decided hypotheses of this lane's block
+    if (listed && mine && sub == __ffs(mine) - 1) {  // the lowest deciding hypothesis writes the block's result
+        if (A.plane) reinterpret_cast<float4*>(A.plane)[b] = pl;
+        if (A.best) A.best[b] = t;
+        if (A.best_count) A.best_count[b] = n;
+        for (int j = 0; j < n; ++j) A.mask[(size_t)ps + j] = 1;
+    }
+    const bool keep = listed && !mine && sub == 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (m) {
+        uint32_t base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(n_out, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (keep) list_out[base + __popc(m & ((1u << lane) - 1u))] = w;
+    }
+    if (A.flags & RANSAC_FLAG_STATS) {
+        uint32_t fits = fitted ? 1u : 0u, dist = fitted ? (uint32_t)n : 0u, blocks = (listed && mine && sub == 0) ? 1u : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            fits += __shfl_xor_sync(0xffffffffu, fits, o);
+            dist += __shfl_xor_sync(0xffffffffu, dist, o);
+            blocks += __shfl_xor_sync(0xffffffffu, blocks, o);
+        }
+        if (lane == 0 && fits) {
+            atomicAdd(&g_ransac_stats[0], (unsigned long long)blocks);
+            atomicAdd(&g_ransac_stats[4], (unsigned long long)blocks);
+            atomicAdd(&g_ransac_stats[6], (unsigned long long)fits);
+            atomicAdd(&g_ransac_stats[7], (unsigned long long)dist);
+        }
+    }
+    }  // rounds
 }
 
 // work items whose block is too large for the warp kernel -> compact list for the CTA kernel
@@ -1014,11 +1079,22 @@ void launch_ransac(Ctx& c, const double* points, int64_t n_points, const uint32_
         const unsigned grid = (n_work + 255) / 256;
         const uint32_t* in = nullptr;
         const uint32_t* n_in = nullptr;
-        for (int t = 0; t < RANSAC_LANE_PASSES; ++t) {
+        for (int t = 0; t < RANSAC_LANE_SINGLE; ++t) {
             uint32_t* out = (t & 1) ? list_b.get() : list_a.get();
             uint32_t* n_out = counters.get() + 2 + t;
             // pass t > 0 is launched over the upper bound n_work; the threads beyond the list's device-side length retire at once
             ransac_lane_kernel<<<grid, 256, 0, c.stream>>>(a, t, in, n_in, n_work, out, n_out);
+            OL_CHECK_LAUNCH();
+            in = out;
+            n_in = n_out;
+        }
+        {  // hypotheses RANSAC_LANE_SINGLE .. RANSAC_LANE_PASSES-1 of what is left, eight lanes per block, one launch.  The
+           // list is short by now (a few percent of the blocks), but its length only exists on the device: a fixed grid
+           // strides over it
+            uint32_t* out = (RANSAC_LANE_SINGLE & 1) ? list_b.get() : list_a.get();
+            uint32_t* n_out = counters.get() + 2 + RANSAC_LANE_SINGLE;
+            const unsigned ggrid = std::min<unsigned>(grid, (unsigned)c.num_sms * 16);
+            ransac_lane_group_kernel<<<ggrid, 256, 0, c.stream>>>(a, RANSAC_LANE_SINGLE, RANSAC_LANE_PASSES, in, n_in, out, n_out);
             OL_CHECK_LAUNCH();
             in = out;
             n_in = n_out;
