@@ -54,21 +54,22 @@ class ForestHost:
     # ---- insertion ------------------------------------------------------------------------------
     def insert(self, pose_number: int, points, allow_append: bool):
         # (called once per pose of a map: every attribute lookup here is host time the GPU waits for)
-        shape = getattr(points, "shape", None)
-        n = int(shape[0]) if shape is not None and len(shape) == 2 else len(points)
         pose_index = self.pose_index
         if pose_number in pose_index:
             if not allow_append:
                 raise ValueError(f"Cannot insert points to existing pose {pose_number}")
+            shape = getattr(points, "shape", None)
+            n = int(shape[0]) if shape is not None and len(shape) == 2 else len(points)
             idx = pose_index[pose_number]
             self.forest.insert_segments(points, [n], [idx], [self.pose_inserted[idx]], len(self.pose_numbers))
             self.pose_inserted[idx] += n
         else:
-            idx = (self._forest or self.forest).insert(points)
+            forest = self._forest or self.forest
+            idx = forest.insert(points)
             assert idx == len(self.pose_numbers)
             pose_index[pose_number] = idx
             self.pose_numbers.append(pose_number)
-            self.pose_inserted.append(n)
+            self.pose_inserted.append(forest.last_insert_rows)  # (the forest looked at the shape already)
             self._pose_epoch[idx] = self._n_subdivides
         self._counts_cache = None
 

@@ -120,6 +120,10 @@ class Forest:
         self._pending_sources = []  # sources of inserts that may still be in flight
         self._batch = []            # CUDA tensors whose insert is deferred (one native call for all of them)
         self._batch_rows = 0
+        self._batch_sizes = []      # rows of every deferred tensor
+        self.last_insert_rows = 0   # rows of the cloud handed to the last insert() call
+        self._first_flush = max(self.FLUSH_EVERY // 4, 1)
+        self._Tensor, self._f64 = torch.Tensor, torch.float64
         self._n_poses_native = 0    # poses the native forest knows about
         self._h = C.c_void_p()
         with self._scope():
@@ -143,6 +147,7 @@ class Forest:
 
     def close(self):
         self._batch = []
+        self._batch_sizes = []
         if getattr(self, "_h", None) is not None and self._h:
             with self._scope():
                 self._lib.ol_forest_destroy(self._h)
@@ -162,24 +167,29 @@ class Forest:
         call before the next grid operation (`ol_forest_insert_batch`: one growth of the point array, one copy kernel
         instead of a driver call per pose).  Do not modify such a tensor in place between `insert_points` and the next
         operation on the grid."""
-        torch = self._torch
-        if isinstance(points, torch.Tensor) and points.device.type == "cuda":
+        # (one call per pose of a map, 839 on the bench workload: every attribute access here is host time in front of the
+        # first kernel - `t.device.type` alone costs as much as six of the tests below)
+        if type(points) is self._Tensor and points.is_cuda:
             t = points
-            if t.dtype != torch.float64 or not t.is_contiguous():
-                t = t.to(torch.float64).contiguous()
-            if t.dim() != 2 or t.shape[1] != 3:
-                t = t.reshape(-1, 3)
-            self._batch.append(t)
-            self._batch_rows += t.shape[0]
+            shape = t.shape
+            if t.dtype is not self._f64 or len(shape) != 2 or shape[1] != 3 or not t.is_contiguous():
+                t = t.to(self._f64).contiguous().reshape(-1, 3)
+                shape = t.shape
+            rows = shape[0]
+            self.last_insert_rows = rows
+            batch = self._batch
+            batch.append(t)
+            self._batch_sizes.append(rows)
+            self._batch_rows += rows
             self.version += 1
-            index = self._n_poses_native + len(self._batch) - 1
-            # (the FIRST batch goes out after a quarter of that, so that the GPU starts early)
-            due = self.FLUSH_EVERY if self._n_poses_native else max(self.FLUSH_EVERY // 4, 1)
-            if len(self._batch) >= due and self._batch_rows >= self.FLUSH_MIN_ROWS:
+            index = self._n_poses_native + len(batch) - 1
+            # (the FIRST batch goes out after a quarter of FLUSH_EVERY poses, so that the GPU starts early)
+            if len(batch) >= (self.FLUSH_EVERY if self._n_poses_native else self._first_flush) and self._batch_rows >= self.FLUSH_MIN_ROWS:
                 self._flush()  # the copy kernel runs while the caller is still inserting the following poses
             return index
         out = C.c_int32(-1)
         src, n, on_dev, keep = self._as_source(points)
+        self.last_insert_rows = n
         with self._scope():
             N.check(self._lib.ol_forest_insert(self._h, src, n, on_dev, C.byref(out)))
         # a pinned host source is read asynchronously (csrc/forest_host.inl): keep it alive until the next synchronising call
@@ -191,12 +201,13 @@ class Forest:
     def _flush(self):
         """Hand the deferred CUDA-tensor inserts to the native forest (one call)."""
         batch, self._batch = self._batch, []
+        rows, self._batch_sizes = self._batch_sizes, []
         self._batch_rows = 0
         if not batch:
             return
         count = len(batch)
         ptrs = (C.c_void_p * count)(*[t.data_ptr() for t in batch])
-        sizes = (C.c_int64 * count)(*[t.shape[0] for t in batch])
+        sizes = (C.c_int64 * count)(*rows)
         first = C.c_int32(-1)
         with self._scope(flush=False):
             N.check(self._lib.ol_forest_insert_batch(self._h, ptrs, sizes, count, C.byref(first)))

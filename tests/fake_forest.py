@@ -58,6 +58,7 @@ class FakeForest:
     def insert(self, points):
         idx = len(self.clouds)
         pts = np.asarray(points, dtype=np.float64)
+        self.last_insert_rows = len(pts)
         self.clouds.append(pts)
         self.pose_epoch[idx] = self.n_subdivides
         self.og.insert_points(idx, pts)
@@ -314,6 +315,7 @@ class FakeSingleCellForest(FakeForest):
     def insert(self, points):
         pose = len(self.clouds)
         pts = np.asarray(points, dtype=np.float64).reshape(-1, 3)
+        self.last_insert_rows = len(pts)
         self.clouds.append(pts)
         self.pose_epoch[pose] = self.n_subdivides
         self._insert_into(pose, np.arange(len(pts)), pts)
