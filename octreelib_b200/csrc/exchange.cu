@@ -313,12 +313,27 @@ __global__ void __launch_bounds__(256) xchg_count_kernel(const XTile* __restrict
     __syncthreads();
     double mn0 = INFINITY, mn1 = INFINITY, mn2 = INFINITY, mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY;
     uint32_t err = 0u;
-#pragma unroll 2
-    for (int r = 0; r < XCHG_TILE / 256; ++r) {
+    // the tile in groups of four rows: the twelve loads of a group are issued together, then the arithmetic and the
+    // warp-synchronous counting (inside one loop every row waited for its own loads)
+    constexpr int XG = 4;
+    static_assert((XCHG_TILE / 256) % XG == 0, "tile rows must come in groups of XG");
+    for (int r0 = 0; r0 < XCHG_TILE / 256; r0 += XG) {
+    double px[XG], py[XG], pz[XG];
+#pragma unroll
+    for (int g = 0; g < XG; ++g) {
+        const uint32_t idx = (uint32_t)(r0 + g) * 256u + (uint32_t)tid;
+        const bool in = idx < T.n;
+        px[g] = in ? T.src[(size_t)idx * 3] : 0.0;
+        py[g] = in ? T.src[(size_t)idx * 3 + 1] : 0.0;
+        pz[g] = in ? T.src[(size_t)idx * 3 + 2] : 0.0;
+    }
+#pragma unroll
+    for (int g = 0; g < XG; ++g) {
+        const int r = r0 + g;
         const uint32_t idx = (uint32_t)r * 256u + (uint32_t)tid;
         uint32_t o = 0xffffffffu;
         if (idx < T.n) {
-            const double x = T.src[(size_t)idx * 3], y = T.src[(size_t)idx * 3 + 1], z = T.src[(size_t)idx * 3 + 2];
+            const double x = px[g], y = py[g], z = pz[g];
             o = 0u;
             if (!isfinite(x + y + z)) {
                 err |= DEVERR_NONFINITE;
@@ -346,6 +361,7 @@ __global__ void __launch_bounds__(256) xchg_count_kernel(const XTile* __restrict
         const uint32_t peers = __match_any_sync(0xffffffffu, o);
         if (o != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[o], (uint32_t)__popc(peers));
     }
+    }  // groups of rows
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         mn0 = fmin(mn0, __shfl_xor_sync(0xffffffffu, mn0, o)), mx0 = fmax(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
@@ -500,12 +516,14 @@ __global__ void __launch_bounds__(256) xchg_scatter_kernel(const XTile* __restri
     __syncthreads();
     uint32_t own[XCHG_TILE / 256], rnk[XCHG_TILE / 256];
 #pragma unroll
-    for (int r = 0; r < XCHG_TILE / 256; ++r) {
+    for (int r = 0; r < XCHG_TILE / 256; ++r) {  // every owner byte of the thread first, then the warp-synchronous ranking
         const uint32_t idx = (uint32_t)r * 256u + (uint32_t)tid;
-        uint32_t o = 0xffffffffu;
-        if (idx < T.n) o = owner[(size_t)T.first_row + idx];
+        own[r] = idx < T.n ? (uint32_t)owner[(size_t)T.first_row + idx] : 0xffffffffu;
+    }
+#pragma unroll
+    for (int r = 0; r < XCHG_TILE / 256; ++r) {
+        const uint32_t o = own[r];
         const uint32_t m = __match_any_sync(0xffffffffu, o);
-        own[r] = o;
         rnk[r] = (uint32_t)__popc(m & ((1u << lane) - 1u));
         if (o != 0xffffffffu && lane == __ffs(m) - 1) s_wcnt[(r * 8 + warp) * W + (int)o] = (uint32_t)__popc(m);
     }

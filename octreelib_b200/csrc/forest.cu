@@ -531,14 +531,26 @@ __global__ void __launch_bounds__(PART_THREADS) part_hist_kernel(const uint32_t*
     __syncthreads();
     const uint32_t base = blockIdx.x * PART_TILE;
     const int lane = threadIdx.x & 31;
+    // loads first, for all of the thread's positions (leaf and Morton word, then the dependent split info), and only then
+    // the warp-synchronous counting: with the loads inside the loop every position paid its two round trips to memory
+    // one after the other
+    uint32_t lf[PART_ITEMS], keys[PART_ITEMS];
+    MortT mo[PART_ITEMS];
 #pragma unroll
     for (int j = 0; j < PART_ITEMS; ++j) {
-        uint32_t i = base + j * PART_THREADS + threadIdx.x;
-        uint32_t key = 0xffffffffu;  // (split-leaf index << 3) | digit
-        if (i < n) {
-            const uint32_t si = sinfo[leaf_of[i]];
-            if (si & 1u) key = ((si >> 1) << 3) | level_digit(mort[i], shift);
-        }
+        const uint32_t i = base + j * PART_THREADS + threadIdx.x;
+        lf[j] = i < n ? leaf_of[i] : 0u;
+        mo[j] = i < n ? mort[i] : (MortT)0;
+    }
+#pragma unroll
+    for (int j = 0; j < PART_ITEMS; ++j) {
+        const uint32_t i = base + j * PART_THREADS + threadIdx.x;
+        const uint32_t si = i < n ? sinfo[lf[j]] : 0u;
+        keys[j] = (si & 1u) ? (((si >> 1) << 3) | level_digit(mo[j], shift)) : 0xffffffffu;  // (split-leaf index << 3) | digit
+    }
+#pragma unroll
+    for (int j = 0; j < PART_ITEMS; ++j) {
+        const uint32_t key = keys[j];
         // positions are leaf-ordered, so a warp holds few distinct (leaf, digit) pairs: one atomic per pair
         const uint32_t peers = __match_any_sync(0xffffffffu, key);
         if (key != 0xffffffffu && lane == (__ffs(peers) - 1)) {
