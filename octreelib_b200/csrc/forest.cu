@@ -315,11 +315,18 @@ __global__ void __launch_bounds__(CMP_THREADS) keep_bits_kernel(const uint8_t* _
     const uint32_t base = blockIdx.x * CMP_TILE;
     const int lane = threadIdx.x & 31;
     uint32_t c = 0;
+    // (every keep flag of the thread first, then the ballots: loads inside a warp-synchronous loop are issued one trip to
+    // memory at a time)
+    uint8_t flag[CMP_TILE / CMP_THREADS];
 #pragma unroll
     for (int j = 0; j < CMP_TILE / CMP_THREADS; ++j) {
         const uint32_t i = base + j * CMP_THREADS + threadIdx.x;
-        bool k = false;
-        if (i < n) k = keep[via ? via[i] : i] != 0;
+        flag[j] = i < n ? keep[via ? via[i] : i] : (uint8_t)0;
+    }
+#pragma unroll
+    for (int j = 0; j < CMP_TILE / CMP_THREADS; ++j) {
+        const uint32_t i = base + j * CMP_THREADS + threadIdx.x;
+        const bool k = flag[j] != 0;
         const uint32_t m = __ballot_sync(0xffffffffu, k);
         if (lane == 0 && i < n) {
             bits[i >> 5] = m;

@@ -172,11 +172,21 @@ __global__ void __launch_bounds__(REFSTART_THREADS) refstart_assign_kernel(uint3
     // (only the in-chunk prefixes stay in registers between the two phases; ranks and sizes are read again for the
     // stores - 103 registers and 23 % occupancy when all three were kept)
     uint32_t local[REFSTART_ROWS];
-#pragma unroll 4
-    for (int r = 0; r < REFSTART_ROWS; ++r) {
-        const uint32_t j = wbase + 32 * r + lane;
-        const uint32_t rk = j < nb ? a_rank[j] : 0xffffffffu;
-        const uint32_t sz = j < nb ? a_size[j] : 0u;
+    constexpr int RG = 8;  // rows whose loads are issued together, ahead of the warp-synchronous ranking
+    static_assert(REFSTART_ROWS % RG == 0, "rows come in groups");
+#pragma unroll
+    for (int r0 = 0; r0 < REFSTART_ROWS; r0 += RG) {
+    uint32_t rks[RG], szs[RG];
+#pragma unroll
+    for (int g = 0; g < RG; ++g) {
+        const uint32_t j = wbase + 32 * (r0 + g) + lane;
+        rks[g] = j < nb ? a_rank[j] : 0xffffffffu;
+        szs[g] = j < nb ? a_size[j] : 0u;
+    }
+#pragma unroll
+    for (int g = 0; g < RG; ++g) {
+        const int r = r0 + g;
+        const uint32_t rk = rks[g], sz = szs[g];
         // the lanes with this lane's rank, and the sizes of those before it (slot order = lane order): a few iterations,
         // consecutive arranged slots are (leaf, pose ascending), so a rank repeats about once per leaf
         const uint32_t peers = __match_any_sync(0xffffffffu, rk);
@@ -200,6 +210,7 @@ __global__ void __launch_bounds__(REFSTART_THREADS) refstart_assign_kernel(uint3
         local[r] = old + mine;
         __syncwarp();
     }
+    }  // groups of rows
     __syncthreads();
     for (int p = threadIdx.x; p < n_ranks; p += REFSTART_THREADS) {  // exclusive prefix over the eight warps
         uint32_t run = 0u;
