@@ -101,13 +101,31 @@ __global__ void __launch_bounds__(OS_THREADS) os_hist_kernel(const KeyT* __restr
             }
         }
     };
-    for (uint32_t v = blockIdx.x * OS_THREADS + threadIdx.x; v < n_vec; v += gridDim.x * OS_THREADS) {
+    // four 16-byte loads in flight per thread, then their keys (a shared-memory atomic between two loads would make the
+    // thread wait for each load in turn)
+    constexpr int UNR = 4;
+    const uint32_t stride = gridDim.x * OS_THREADS;
+    for (uint32_t v0 = blockIdx.x * OS_THREADS + threadIdx.x; v0 < n_vec; v0 += stride * UNR) {
         if (sizeof(KeyT) == 4) {
-            const uint4 q = reinterpret_cast<const uint4*>(keys)[v];
-            add((KeyT)q.x), add((KeyT)q.y), add((KeyT)q.z), add((KeyT)q.w);
+            uint4 q[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const uint32_t v = v0 + (uint32_t)u * stride;
+                q[u] = v < n_vec ? reinterpret_cast<const uint4*>(keys)[v] : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+                if (v0 + (uint32_t)u * stride < n_vec) add((KeyT)q[u].x), add((KeyT)q[u].y), add((KeyT)q[u].z), add((KeyT)q[u].w);
         } else {
-            const ulonglong2 q = reinterpret_cast<const ulonglong2*>(keys)[v];
-            add((KeyT)q.x), add((KeyT)q.y);
+            ulonglong2 q[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const uint32_t v = v0 + (uint32_t)u * stride;
+                q[u] = v < n_vec ? reinterpret_cast<const ulonglong2*>(keys)[v] : make_ulonglong2(0ull, 0ull);
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+                if (v0 + (uint32_t)u * stride < n_vec) add((KeyT)q[u].x), add((KeyT)q[u].y);
         }
     }
     for (uint32_t i = n_vec * VEC + blockIdx.x * OS_THREADS + threadIdx.x; i < n; i += gridDim.x * OS_THREADS) add(keys[i]);  // the rest
