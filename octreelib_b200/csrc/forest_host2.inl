@@ -334,9 +334,26 @@ __global__ void __launch_bounds__(256) gather_blocks_kernel(uint32_t n_work, con
     const uint32_t b = work[w];
     const uint32_t src0 = blk_start[b], dst0 = pk_start[w];
     const uint32_t n3 = (uint32_t)blk_size[b] * 3u;
-    for (uint32_t e = sub; e < n3; e += 8) {
-        const uint32_t j = e / 3u, c = e - j * 3u;
-        out[(size_t)dst0 * 3 + e] = xyz[(size_t)perm[src0 + j] * 3 + c];
+    // four elements per lane and round: their rank loads, then their coordinate loads, then the stores (a loop of
+    // dependent rank -> coordinate loads paid two trips to memory per element)
+    for (uint32_t e0 = sub; e0 < n3; e0 += 32) {
+        uint32_t r[4];
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t e = e0 + 8u * u;
+            r[u] = e < n3 ? perm[src0 + e / 3u] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t e = e0 + 8u * u;
+            v[u] = e < n3 ? xyz[(size_t)r[u] * 3 + (e - (e / 3u) * 3u)] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t e = e0 + 8u * u;
+            if (e < n3) out[(size_t)dst0 * 3 + e] = v[u];
+        }
     }
 }
 
