@@ -730,8 +730,10 @@ def main():
         out["ranks"] = ranks_info
     if exchange_info:
         out["exchange"] = dict(exchange_info, note="rank 0; ms = CUDA events around ShardedGrid.exchange() in the profiled step "
-                                                   "(slab boundaries, owner sort, count all-gather, routed copy, insert); bytes = "
-                                                   "point rows this rank sent to other ranks x 24")
+                                                   "(fused exchange: slab boundaries from a sample histogram, counting pass, flag "
+                                                   "rounds over peer-mapped control blocks, scatter into the owners' receive buffers, "
+                                                   "key / sort / cell kernels enqueued behind it; includes the wait for the slowest "
+                                                   "rank); bytes = point rows this rank sent to other ranks x 24")
     if e2e:
         out["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:
