@@ -785,18 +785,28 @@ __global__ void expand_leaves_kernel(uint32_t L, uint32_t A, uint32_t I_old, con
         const size_t flat_len = (size_t)8 * num_tiles + (size_t)8 * n_split;
         const uint32_t t_tiles = scanned[(size_t)8 * num_tiles];
         uint32_t run = lstart[k];
+        // the sixteen scanned counts of the eight children first (strided gathers, all in flight), then the stores
+        uint32_t e0s[8], e1s[8];
+#pragma unroll
         for (uint32_t c = 0; c < 8; ++c) {
             const size_t idx = (size_t)8 * num_tiles + (size_t)c * n_split + s;
-            const uint32_t e0 = scanned[idx];
-            const uint32_t e1 = idx + 1 < flat_len ? scanned[idx + 1] : (uint32_t)*total;
+            e0s[c] = scanned[idx];
+            e1s[c] = idx + 1 < flat_len ? scanned[idx + 1] : (uint32_t)*total;
+        }
+        const uint32_t cell_k = lcell[k];
+        const uint64_t path_k = lpath[k];
+        const uint8_t depth_k = ldepth[k];
+#pragma unroll
+        for (uint32_t c = 0; c < 8; ++c) {
+            const uint32_t e0 = e0s[c], e1 = e1s[c];
             delta[(size_t)s * 8 + c] = run - (e0 - t_tiles);
             const uint32_t j = j0 + c;
             lstart_n[j] = run;
             run += e1 - e0;
-            lcell_n[j] = lcell[k];
+            lcell_n[j] = cell_k;
             lparent_n[j] = (int32_t)id;
-            lpath_n[j] = (lpath[k] << 3) | (uint64_t)c;
-            ldepth_n[j] = (uint8_t)(ldepth[k] + 1);
+            lpath_n[j] = (path_k << 3) | (uint64_t)c;
+            ldepth_n[j] = (uint8_t)(depth_k + 1);
             lchild_n[j] = (uint8_t)c;
         }
     }

@@ -121,14 +121,17 @@ __global__ void __launch_bounds__(REFSTART_THREADS) refstart_count_kernel(uint32
     __syncthreads();
     const uint32_t base = blockIdx.x * REFSTART_CHUNK;
     uint32_t big = 0u;
-#pragma unroll 4
+    uint32_t rk[REFSTART_ROWS], sz[REFSTART_ROWS];  // all loads of the thread first, then the shared-memory atomics
+#pragma unroll
     for (int k = 0; k < REFSTART_ROWS; ++k) {
         const uint32_t j = base + (uint32_t)k * REFSTART_THREADS + threadIdx.x;
-        if (j < nb) {
-            const uint32_t sz = a_size[j];
-            atomicAdd(&s_cnt[a_rank[j]], sz);
-            big = sz > big ? sz : big;
-        }
+        rk[k] = j < nb ? a_rank[j] : 0u;
+        sz[k] = j < nb ? a_size[j] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < REFSTART_ROWS; ++k) {
+        if (sz[k]) atomicAdd(&s_cnt[rk[k]], sz[k]);  // (a block holds at least one point: size 0 = past the end)
+        big = sz[k] > big ? sz[k] : big;
     }
     if (max_size) {  // the largest block of the table, on the way (the RANSAC launch sizes its shared memory by it)
 #pragma unroll
