@@ -224,8 +224,10 @@ int Forest::insert(const double* xyz, int64_t n, bool on_device, const int64_t* 
     if (N + (size_t)n > cap) {
         join_uploads();  // copies still in flight on the upload streams target the old array
         size_t ncap = std::max<size_t>(N + (size_t)n, cap + cap / 2 + 1024);
-        // first guess: the size of the previous map of this process (see insert_batch) - no growth copy in the steady state
-        if (g_last_build_points >= N + (size_t)n && N + (size_t)n >= g_last_build_points / 1024) ncap = std::max(ncap, g_last_build_points);
+        // first guess: the size of the previous map of this process (see insert_batch) - once this map has reached 1/32 of it,
+        // so that a small grid after a large one does not reserve the large one's memory (the geometric growth up to that
+        // point copies a few percent of the final size)
+        if (g_last_build_points >= N + (size_t)n && N + (size_t)n >= g_last_build_points / 32) ncap = std::max(ncap, g_last_build_points);
         DevBuf<double> np(ctx, ncap * 3);
         d2d(ctx, np.get(), P64.get(), N * 3);
         P64.swap(np);
