@@ -1,6 +1,6 @@
 """The pipeline's result must not depend on the host-side hand-over of the clouds nor on the library's internal switches:
 Morton levels embedded in the sort key or kept in their own array, two-pass or chained run segmentation, eager or lazy
-derived tables, cached or fresh device blocks.  One digest over every exported table, several ways to get there."""
+derived tables, cached or fresh device blocks, sorted or sort-free RANSAC batch layout.  One digest over every exported table, several ways to get there."""
 import os
 import subprocess
 import sys
@@ -34,7 +34,8 @@ def test_internal_switches_do_not_change_results():
     from toggle_digest import digest
 
     ref = digest("numpy")
-    every = {"OL_NO_EMBED": "1", "OL_RUNS_ONE_PASS": "1", "OL_NO_PREFETCH": "1", "OL_CACHE_BYTES": "0"}
+    every = {"OL_NO_EMBED": "1", "OL_RUNS_ONE_PASS": "1", "OL_NO_PREFETCH": "1", "OL_CACHE_BYTES": "0",
+             "OL_RANSAC_SORTED_LAYOUT": "1"}  # the last one: batch layout from the sorted block table instead of the ranking
     assert _digest_in_subprocess(every) == ref
     assert _digest_in_subprocess({"OL_NO_EMBED": "1"}, mode="cuda_batches") == ref
 
