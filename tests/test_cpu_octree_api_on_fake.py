@@ -135,3 +135,31 @@ def test_standalone_octree_second_subdivide_is_a_no_op_like_the_reference():
     assert (tree.n_nodes, tree.n_leaves, [v.n_points for v in tree.get_leaf_points()]) == before
     with pytest.raises(NotImplementedError):
         tree.subdivide([lambda points: len(points) >= 0])
+
+
+def test_map_leaf_points_with_new_coordinates_on_the_stand_in():
+    """octree.py:114-123 with a function that changes coordinates (every leaf shrunk towards its centroid): the host layer
+    masks the old points, appends the new ones to the pose and checks, leaf by leaf, that the rebuilt tree holds exactly
+    what the function returned (ForestHost.map_leaf_points); a result that leaves its leaf is refused up front."""
+    rng = np.random.default_rng(8)
+    cloud = np.vstack([rng.normal([3, 3, 3], 0.8, (150, 3)), rng.uniform(0, 10, (100, 3))])
+    cloud = cloud[((cloud >= 0) & (cloud < 10)).all(axis=1)]
+    tree = Octree(OctreeConfig(), np.array([0, 0, 0]), np.float64(10))
+    tree._host._forest = FakeSingleCellForest(np.float64(10), np.array([0, 0, 0]))
+    tree.insert_points(cloud)
+    tree.subdivide([lambda points: len(points) > 12])
+    before = [v.get_points().copy() for v in tree.get_leaf_points()]
+    n_nodes = tree.n_nodes
+
+    def shrink(points):
+        c = points.mean(axis=0)
+        return c + 0.5 * (points - c)
+
+    tree.map_leaf_points(shrink)
+    after = tree.get_leaf_points()
+    assert len(after) == len(before) and tree.n_nodes == n_nodes
+    for v, b in zip(after, before):
+        assert (v.get_points() == shrink(b)).all()
+    with pytest.raises(NotImplementedError):
+        tree.map_leaf_points(lambda points: points + 100.0)
+    assert tree.n_points == sum(len(b) for b in before)
