@@ -47,8 +47,20 @@ class Grid(GridBase):
         (pinned) host array is uploaded asynchronously: leave it unchanged until the next call that returns results
         (`subdivide`, `n_points`, `get_leaf_points`, ...)."""
         host = self._host
-        if pose_number in host.pose_index:
+        pose_index = host.pose_index
+        if pose_number in pose_index:
             raise ValueError(f"Cannot insert points to existing pose {pose_number}")
+        forest = host._forest
+        if forest is not None and getattr(points, "is_cuda", False) and type(points) is forest._Tensor:
+            # CUDA tensors, one call per pose of a map (839 on the 100 M-point workload): the bookkeeping of
+            # ForestHost.insert inline - a Python frame less per pose is 0.2 ms of host time in front of the first kernel
+            idx = forest.insert(points)
+            pose_index[pose_number] = idx
+            host.pose_numbers.append(pose_number)
+            host.pose_inserted.append(forest.last_insert_rows)
+            host._pose_epoch[idx] = host._n_subdivides
+            host._counts_cache = None
+            return
         host.insert(pose_number, points if hasattr(points, "device") else np.asarray(points), allow_append=False)
 
     # ---- grid.py:111-122 ------------------------------------------------------------------------
