@@ -75,9 +75,37 @@ struct InsertChunk {
     unsigned len;
     unsigned pad;
 };
-__global__ void __launch_bounds__(INSERT_THREADS) insert_batch_kernel(const InsertChunk* __restrict__ chunks, double* __restrict__ dst,
+// one cloud of the batch; the chunk descriptors are derived from these on the device (a batch of 128 poses is ~2400 chunks:
+// the host uploads 128 rows instead of building and staging the chunk table - host time in front of the first kernel)
+struct InsertCloud {
+    const double* src;
+    unsigned long long dst;    // first destination double
+    unsigned long long len;    // doubles
+    unsigned first_chunk;
+    unsigned pad;
+};
+__global__ void __launch_bounds__(INSERT_THREADS) insert_batch_kernel(const InsertCloud* __restrict__ clouds, int n_clouds,
+                                                                      unsigned chunk_len, double* __restrict__ dst,
                                                                       long long* __restrict__ bbox, uint32_t* __restrict__ err) {
-    const InsertChunk c = chunks[blockIdx.x];
+    __shared__ InsertChunk s_chunk;
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = n_clouds;  // last cloud with first_chunk <= blockIdx.x (clouds without points own no chunk)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (clouds[mid].first_chunk <= blockIdx.x)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const InsertCloud cl = clouds[lo];
+        const unsigned long long off = (unsigned long long)(blockIdx.x - cl.first_chunk) * chunk_len;
+        s_chunk.src = cl.src + off;
+        s_chunk.dst = cl.dst + off;
+        s_chunk.len = (unsigned)min((unsigned long long)chunk_len, cl.len - off);
+        s_chunk.pad = 0u;
+    }
+    __syncthreads();
+    const InsertChunk c = s_chunk;
     const double* __restrict__ s = c.src;
     double* __restrict__ d = dst + c.dst;
     long long mn = LLONG_MAX, mx = LLONG_MIN;

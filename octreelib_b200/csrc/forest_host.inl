@@ -391,14 +391,14 @@ int Forest::insert_batch(const double* const* xyz_dev, const int64_t* sizes, int
     // was 5 CTAs per SM and ran at 60 % of the bandwidth of the single big launch), a multiple of 3, at most INSERT_CHUNK
     unsigned long long chunk_len = (unsigned long long)total * 3ull / ((unsigned long long)ctx.num_sms * 16ull);
     chunk_len = std::min<unsigned long long>(std::max<unsigned long long>(chunk_len / 3ull * 3ull, 3ull * 1024ull), INSERT_CHUNK);
-    std::vector<InsertChunk> chunks;
-    chunks.reserve(total * 3 / chunk_len + (size_t)count + 1);
+    std::vector<InsertCloud> rows;
+    rows.reserve((size_t)count);
     size_t r = N;
-    unsigned long long dst = 0;
+    unsigned long long dst = 0, n_chunks = 0;
     for (int c = 0; c < count; ++c) {
         const unsigned long long len = (unsigned long long)sizes[c] * 3ull;
-        for (unsigned long long off = 0; off < len; off += chunk_len)
-            chunks.push_back(InsertChunk{xyz_dev[c] + off, dst + off, (unsigned)std::min<unsigned long long>(chunk_len, len - off), 0u});
+        if (len) rows.push_back(InsertCloud{xyz_dev[c], dst, len, (unsigned)n_chunks, 0u});
+        n_chunks += (len + chunk_len - 1) / chunk_len;
         dst += len;
         seg_pose.push_back(n_poses);
         seg_first.push_back(0);
@@ -407,14 +407,14 @@ int Forest::insert_batch(const double* const* xyz_dev, const int64_t* sizes, int
         seg_start.push_back((uint32_t)r);
         n_poses += 1;
     }
-    if (!chunks.empty()) {
-        DevBuf<InsertChunk> d_chunks(ctx, chunks.size());
-        h2d(ctx, d_chunks.get(), chunks.data(), chunks.size());
+    if (n_chunks) {
+        DevBuf<InsertCloud> d_rows(ctx, rows.size());
+        h2d(ctx, d_rows.get(), rows.data(), rows.size());
         ProfScope ps(ctx, "insert_batch", (double)total);
-        insert_batch_kernel<<<(unsigned)chunks.size(), INSERT_THREADS, 0, ctx.stream>>>(d_chunks.get(), P64.get() + N * 3, d_bbox.get(),
-                                                                                        d_err.get());
+        insert_batch_kernel<<<(unsigned)n_chunks, INSERT_THREADS, 0, ctx.stream>>>(d_rows.get(), (int)rows.size(), (unsigned)chunk_len,
+                                                                                   P64.get() + N * 3, d_bbox.get(), d_err.get());
         OL_CHECK_LAUNCH();
-        // No synchronisation: the pageable chunk table has been staged when cudaMemcpyAsync returns, and the caller's
+        // No synchronisation: the pageable cloud table has been staged when cudaMemcpyAsync returns, and the caller's
         // clouds are torch tensors whose memory is recycled in stream order on this same stream (documented in
         // include/octreelib_b200.h: sources must stay valid until the work enqueued here has run).
     }
